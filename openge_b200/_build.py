@@ -1,0 +1,99 @@
+"""In-tree builds of the native pieces (no JIT cache: the .so files travel with the repo).
+
+  libopenge_b200.so   CUDA kernels + C-ABI   (nvcc, sm_100a)      openge_b200/csrc/
+  libogesynth.so      synthetic workloads    (gcc)                tools/synth/
+  liboge_oracle.so    TEST-ONLY CPU oracle   (gcc)                oracle/
+  oracle/_ref/...     the reference itself   (g++, only where /root/reference exists)
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "openge_b200", "csrc")
+GPU_LIB = os.path.join(ROOT, "openge_b200", "libopenge_b200.so")
+SYNTH_LIB = os.path.join(ROOT, "tools", "synth", "libogesynth.so")
+ORACLE_LIB = os.path.join(ROOT, "oracle", "liboge_oracle.so")
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "oge_ref_dedup")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "--use_fast_math", "-Xcompiler", "-fPIC", "-shared"]
+
+
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources if os.path.exists(s))
+
+
+def _run(cmd, **kw):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, **kw)
+    if r.returncode != 0:
+        raise RuntimeError("build failed: %s\n%s" % (" ".join(cmd), r.stdout))
+    return r.stdout
+
+
+def _have(tool):
+    from shutil import which
+    return which(tool) is not None
+
+
+def gpu_sources():
+    out = []
+    for d, _, files in os.walk(CSRC):
+        for f in sorted(files):
+            if f.endswith((".cu", ".cuh", ".h")):
+                out.append(os.path.join(d, f))
+    out.append(os.path.join(ROOT, "include", "oge_gpu_dedup.h"))
+    return out
+
+
+def build_gpu(force=False, verbose=False):
+    srcs = gpu_sources()
+    cu = [s for s in srcs if s.endswith(".cu")]
+    if force or _stale(GPU_LIB, srcs):
+        if not _have("nvcc"):
+            if os.path.exists(GPU_LIB):
+                return GPU_LIB
+            raise RuntimeError("nvcc not found and %s is missing" % GPU_LIB)
+        flags = list(NVCC_FLAGS)
+        if verbose:
+            flags += ["-Xptxas", "-v"]
+        out = _run(["nvcc"] + flags + ["-I", os.path.join(ROOT, "include"), "-I", CSRC] + cu +
+                   ["-o", GPU_LIB, "-lcudart"])
+        if verbose:
+            print(out)
+    return GPU_LIB
+
+
+def ensure_synth(force=False):
+    src = os.path.join(ROOT, "tools", "synth", "oge_synth.c")
+    if force or _stale(SYNTH_LIB, [src]):
+        _run(["gcc", "-O2", "-fPIC", "-shared", "-pthread", src, "-o", SYNTH_LIB, "-lm"])
+    return SYNTH_LIB
+
+
+def ensure_oracle(force=False):
+    """TEST-ONLY: the CPU restatement.  Never called from the product path."""
+    src = os.path.join(ROOT, "oracle", "markdup_oracle.c")
+    if force or _stale(ORACLE_LIB, [src]):
+        _run(["gcc", "-O2", "-fPIC", "-shared", src, "-o", ORACLE_LIB])
+    return ORACLE_LIB
+
+
+def ensure_ref(force=False):
+    """TEST-ONLY: compile the reference's dedup path in place (only where its sources exist)."""
+    if os.path.isdir("/root/reference/openge/src"):
+        d = os.path.join(ROOT, "oracle", "ref_build")
+        if force or _stale(REF_BIN, [os.path.join(d, "ref_driver.cpp"), os.path.join(d, "Makefile")]):
+            _run(["make", "-C", d] + (["-B"] if force else []))
+    return REF_BIN if os.path.exists(REF_BIN) else None
+
+
+def build_all(verbose=False):
+    ensure_synth()
+    ensure_oracle()
+    ensure_ref()
+    return build_gpu(verbose=verbose)

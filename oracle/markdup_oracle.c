@@ -1,0 +1,480 @@
+/*
+ * TEST INFRASTRUCTURE ONLY.  CPU restatement of the reference's duplicate-marking path.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load this.
+ * The product path (openge_b200/csrc) never calls it and has no CPU fallback.
+ *
+ * Parity status: PINNED against the compiled reference itself (oracle/_ref/oge_ref_dedup,
+ * built in place from /root/reference by oracle/ref_build/Makefile): tests/test_oracle.py
+ * checks this restatement against the reference's flags on test/data/208.yhet.bam
+ * (6642 of 15419 flagged), on the SURVEY A.3 known-answer fixtures and on seeded synthetic
+ * BAMs.  The reference's own tests hold no golden vector for dedup (test/CMakeLists.txt:32
+ * is exit-code only).
+ *
+ * Plain C, single threaded, sequential -- it follows the reference line by line rather
+ * than the GPU design.  Citations are into /root/reference/openge/src/.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* One 5' end, as util/picard_structures.h:29-54 (ReadEnds). */
+typedef struct {
+    int16_t libraryId;
+    int16_t score;
+    int32_t orientation;       /* RE_NONE=0,F=1,R=2,FF=3,RR=4,FR=5,RF=6  picard_structures.h:24-27 */
+    int32_t read1Sequence;
+    int32_t read1Coordinate;
+    int64_t read1IndexInFile;
+    int32_t read2Sequence;
+    int32_t read2Coordinate;
+    int64_t read2IndexInFile;
+} ReadEnds;
+
+/* Per-record view of the end-building step, exported for field-by-field parity of K1. */
+typedef struct {
+    int32_t eligible;          /* mapped && refID != -1 && primary          mark_duplicates.cpp:202-205 */
+    int32_t pair_eligible;     /* eligible && paired && mate mapped         mark_duplicates.cpp:209 */
+    int32_t ref;               /* read1Sequence */
+    int32_t coord;             /* read1Coordinate (unclipped 5' end) */
+    int32_t orientation;       /* RE_F / RE_R */
+    int32_t read2Sequence;     /* mate refID when paired && mate mapped, else -1 */
+    int16_t score;
+    int16_t lib;
+} OracleEnd;
+
+enum { RE_NONE, RE_F, RE_R, RE_FF, RE_RR, RE_FR, RE_RF };
+
+static int32_t rd_i32(const uint8_t *p) { int32_t v; memcpy(&v, p, 4); return v; }
+static uint32_t rd_u32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static uint16_t rd_u16(const uint8_t *p) { uint16_t v; memcpy(&v, p, 2); return v; }
+
+/* Decoded view of one raw BAM record (util/bam_deserializer.h:144-193). */
+typedef struct {
+    const uint8_t *base;       /* points at block_size */
+    uint32_t block_size;
+    int32_t ref_id, pos, mate_ref, mate_pos;
+    uint32_t l_read_name, n_cigar, l_seq;
+    uint16_t flag;
+    const uint8_t *name, *cigar, *qual, *tags;
+    uint32_t tags_len;
+} Rec;
+
+static void decode(const uint8_t *p, Rec *r) {
+    r->base = p;
+    r->block_size = rd_u32(p);
+    r->ref_id = rd_i32(p + 4);
+    r->pos = rd_i32(p + 8);
+    r->l_read_name = p[12];
+    r->n_cigar = rd_u16(p + 16);
+    r->flag = rd_u16(p + 18);
+    r->l_seq = rd_u32(p + 20);
+    r->mate_ref = rd_i32(p + 24);
+    r->mate_pos = rd_i32(p + 28);
+    r->name = p + 36;
+    r->cigar = r->name + r->l_read_name;
+    r->qual = r->cigar + 4u * r->n_cigar + (r->l_seq + 1) / 2;
+    r->tags = r->qual + r->l_seq;
+    {
+        int64_t used = (int64_t)(r->tags - (p + 4));
+        int64_t left = (int64_t) r->block_size - used;
+        r->tags_len = left > 0 ? (uint32_t) left : 0;
+    }
+}
+
+/* bamtools/BamConstants.h:48: op index into "MIDNSHP=X" */
+static int cig_op(const Rec *r, uint32_t i) { return (int)(rd_u32(r->cigar + 4 * i) & 0xf); }
+static int32_t cig_len(const Rec *r, uint32_t i) { return (int32_t)(rd_u32(r->cigar + 4 * i) >> 4); }
+
+/* mark_duplicates.cpp:44-61  getReferenceLength: sum of M D N = X */
+static int32_t reference_length(const Rec *r) {
+    int32_t len = 0;
+    for (uint32_t i = 0; i < r->n_cigar; i++) {
+        int op = cig_op(r, i);
+        if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) len += cig_len(r, i);
+    }
+    return len;
+}
+
+/* mark_duplicates.cpp:88-103  getUnclippedStart */
+static int32_t unclipped_start(const Rec *r) {
+    int32_t pos = r->pos;
+    for (uint32_t i = 0; i < r->n_cigar; i++) {
+        int op = cig_op(r, i);
+        if (op == 4 || op == 5) pos -= cig_len(r, i); else break;
+    }
+    return pos;
+}
+
+/* mark_duplicates.cpp:73-79,112-129  getAlignmentEnd + getUnclippedEnd */
+static int32_t unclipped_end(const Rec *r) {
+    int32_t pos = (r->flag & 0x4) ? -1 : r->pos + reference_length(r) - 1;
+    for (int64_t i = (int64_t) r->n_cigar - 1; i >= 0; i--) {
+        int op = cig_op(r, (uint32_t) i);
+        if (op == 4 || op == 5) pos += cig_len(r, (uint32_t) i); else break;
+    }
+    return pos;
+}
+
+/* mark_duplicates.cpp:135-144 + bamtools/BamAlignment.cpp:846-851: short accumulator,
+ * every raw quality byte b (uint8) with b >= 15 is added; wraps mod 2^16. */
+static int16_t score_of(const Rec *r) {
+    int16_t score = 0;
+    for (uint32_t i = 0; i < r->l_seq; i++) {
+        uint8_t b = r->qual[i];
+        if (b >= 15) score = (int16_t)(score + b);
+    }
+    return score;
+}
+
+/* bamtools/BamAlignment.cpp:270-294 FindTag + :699-786 SkipToNextTag, for tag "RG".
+ * Returns pointer to the value (any type code: GetTag<string> never checks it,
+ * BamAlignment.h:575-606) and its strlen bounded by the record end. */
+static const uint8_t *find_rg(const Rec *r, uint32_t *len) {
+    const uint8_t *p = r->tags;
+    uint32_t n = r->tags_len, parsed = 0;
+    *len = 0;
+    if (n == 0) return NULL;
+    while (parsed < n) {
+        const uint8_t *name = p;
+        uint8_t type;
+        if (n - parsed < 3) return NULL;      /* truncated tag header: the reference reads past the end here */
+        type = p[2];
+        p += 3; parsed += 3;
+        if (name[0] == 'R' && name[1] == 'G') {
+            uint32_t l = 0;
+            while (parsed + l < n && p[l]) l++;
+            *len = l;
+            return p;
+        }
+        if (type == 0) return NULL;
+        switch (type) {
+            case 'A': case 'c': case 'C': p += 1; parsed += 1; break;
+            case 's': case 'S': p += 2; parsed += 2; break;
+            case 'f': case 'i': case 'I': p += 4; parsed += 4; break;
+            case 'Z': case 'H':
+                while (parsed < n && *p) { p++; parsed++; }
+                p++; parsed++;
+                break;
+            case 'B': {
+                uint8_t at;
+                int32_t cnt;
+                int64_t skip;
+                if (parsed + 5 > n) return NULL;
+                at = *p; p++; parsed++;
+                cnt = rd_i32(p); p += 4; parsed += 4;
+                if (at == 'c' || at == 'C') skip = cnt;
+                else if (at == 's' || at == 'S') skip = 2 * (int64_t) cnt;
+                else if (at == 'f' || at == 'i' || at == 'I') skip = 4 * (int64_t) cnt;
+                else return NULL;
+                if (skip < 0 || parsed + skip > n) return NULL;
+                p += skip; parsed += (uint32_t) skip;
+                break;
+            }
+            default: return NULL;
+        }
+        if (parsed >= n) return NULL;
+        if (*p == 0) return NULL;
+    }
+    return NULL;
+}
+
+/* mark_duplicates.cpp:282-318 getLibraryId/getLibraryName with the host-resolved table
+ * (rg id -> library id; see openge_b200/header.py for the @RG parsing rules). */
+typedef struct {
+    const char *const *rg_ids;
+    const int16_t *rg_lib;
+    int32_t n_rg;
+    int16_t unknown_lib;
+} LibTable;
+
+static int16_t library_id(const LibTable *t, const uint8_t *rg, uint32_t rg_len) {
+    if (rg && rg_len > 0) {
+        for (int32_t i = 0; i < t->n_rg; i++) {
+            if (strlen(t->rg_ids[i]) == rg_len && memcmp(t->rg_ids[i], rg, rg_len) == 0)
+                return t->rg_lib[i];
+        }
+    }
+    return t->unknown_lib;
+}
+
+/* mark_duplicates.cpp:147-164 buildReadEnds */
+static void build_read_ends(const LibTable *t, int64_t index, const Rec *r, ReadEnds *e) {
+    uint32_t rg_len;
+    const uint8_t *rg = find_rg(r, &rg_len);
+    int rev = (r->flag & 0x10) != 0;
+    e->libraryId = -1; e->score = -1; e->orientation = RE_NONE;
+    e->read1Sequence = -1; e->read1Coordinate = -1; e->read1IndexInFile = -1;
+    e->read2Sequence = -1; e->read2Coordinate = -1; e->read2IndexInFile = -1;
+    e->read1Sequence = r->ref_id;
+    e->read1Coordinate = rev ? unclipped_end(r) : unclipped_start(r);
+    e->orientation = rev ? RE_R : RE_F;
+    e->read1IndexInFile = index;
+    e->score = score_of(r);
+    if ((r->flag & 0x1) && !(r->flag & 0x8)) e->read2Sequence = r->mate_ref;
+    e->libraryId = library_id(t, rg, rg_len);
+}
+
+/* mark_duplicates.cpp:169-178 getOrientationByte */
+static int orientation_byte(int neg1, int neg2) {
+    if (neg1) return neg2 ? RE_RR : RE_RF;
+    return neg2 ? RE_FR : RE_FF;
+}
+
+/* picard_structures.h:56-68 ReadEnds::compare (exact three-way compares in place of the
+ * reference's int subtraction; identical wherever the subtraction does not overflow). */
+#define CMP(a, b) do { if ((a) < (b)) return -1; if ((a) > (b)) return 1; } while (0)
+static int ends_compare(const void *pa, const void *pb) {
+    const ReadEnds *l = *(const ReadEnds *const *) pa, *r = *(const ReadEnds *const *) pb;
+    CMP(l->libraryId, r->libraryId);
+    CMP(l->read1Sequence, r->read1Sequence);
+    CMP(l->read1Coordinate, r->read1Coordinate);
+    CMP(l->orientation, r->orientation);
+    CMP(l->read2Sequence, r->read2Sequence);
+    CMP(l->read2Coordinate, r->read2Coordinate);
+    CMP(l->read1IndexInFile, r->read1IndexInFile);
+    CMP(l->read2IndexInFile, r->read2IndexInFile);
+    return 0;
+}
+
+/* ReadEndsMap (picard_structures.h:82-109): exact string-keyed map, key = RG + ":" + name
+ * (mark_duplicates.cpp:210-214).  Open addressing with tombstone-free backward-shift delete;
+ * equality is on the full key bytes, the hash only picks the probe start. */
+typedef struct { const uint8_t *rg; uint32_t rg_len; const uint8_t *name; uint32_t name_len; ReadEnds *val; } Slot;
+typedef struct { Slot *s; uint64_t cap, used; } Map;
+
+static uint64_t key_hash(const uint8_t *rg, uint32_t rg_len, const uint8_t *name, uint32_t name_len) {
+    uint64_t h = 1469598103934665603ULL;
+    uint32_t i;
+    for (i = 0; i < rg_len; i++) { h ^= rg[i]; h *= 1099511628211ULL; }
+    h ^= ':'; h *= 1099511628211ULL;
+    for (i = 0; i < name_len; i++) { h ^= name[i]; h *= 1099511628211ULL; }
+    return h ^ (h >> 29);
+}
+
+/* Compare the logical concatenations RG + ":" + name byte by byte. */
+static int key_equal(const Slot *s, const uint8_t *rg, uint32_t rg_len, const uint8_t *name, uint32_t name_len) {
+    uint32_t la = s->rg_len + 1 + s->name_len, lb = rg_len + 1 + name_len, i;
+    if (la != lb) return 0;
+    for (i = 0; i < la; i++) {
+        uint8_t a = i < s->rg_len ? s->rg[i] : (i == s->rg_len ? ':' : s->name[i - s->rg_len - 1]);
+        uint8_t b = i < rg_len ? rg[i] : (i == rg_len ? ':' : name[i - rg_len - 1]);
+        if (a != b) return 0;
+    }
+    return 1;
+}
+
+static void map_init(Map *m, uint64_t cap) {
+    m->cap = 1024; while (m->cap < cap) m->cap <<= 1;
+    m->s = (Slot *) calloc(m->cap, sizeof(Slot));
+    m->used = 0;
+}
+
+static void map_grow(Map *m);
+
+static Slot *map_find(Map *m, const uint8_t *rg, uint32_t rg_len, const uint8_t *name, uint32_t name_len) {
+    uint64_t i = key_hash(rg, rg_len, name, name_len) & (m->cap - 1);
+    while (m->s[i].val) {
+        if (key_equal(&m->s[i], rg, rg_len, name, name_len)) return &m->s[i];
+        i = (i + 1) & (m->cap - 1);
+    }
+    return &m->s[i];
+}
+
+static void map_put(Map *m, const uint8_t *rg, uint32_t rg_len, const uint8_t *name, uint32_t name_len, ReadEnds *v) {
+    Slot *s;
+    if ((m->used + 1) * 2 > m->cap) map_grow(m);
+    s = map_find(m, rg, rg_len, name, name_len);
+    if (!s->val) m->used++;
+    s->rg = rg; s->rg_len = rg_len; s->name = name; s->name_len = name_len; s->val = v;
+}
+
+static void map_grow(Map *m) {
+    Slot *old = m->s; uint64_t oc = m->cap, i;
+    m->cap <<= 1; m->s = (Slot *) calloc(m->cap, sizeof(Slot)); m->used = 0;
+    for (i = 0; i < oc; i++) if (old[i].val) map_put(m, old[i].rg, old[i].rg_len, old[i].name, old[i].name_len, old[i].val);
+    free(old);
+}
+
+static void map_erase(Map *m, Slot *s) {
+    uint64_t mask = m->cap - 1, i = (uint64_t)(s - m->s), j = i;
+    m->s[i].val = NULL; m->used--;
+    for (;;) {
+        uint64_t k;
+        j = (j + 1) & mask;
+        if (!m->s[j].val) break;
+        k = key_hash(m->s[j].rg, m->s[j].rg_len, m->s[j].name, m->s[j].name_len) & mask;
+        if ((i <= j) ? (i < k && k <= j) : (i < k || k <= j)) continue;
+        m->s[i] = m->s[j]; m->s[j].val = NULL; i = j;
+    }
+}
+
+typedef struct { ReadEnds **v; uint64_t n, cap; } Vec;
+static void vec_push(Vec *v, ReadEnds *e) {
+    if (v->n == v->cap) { v->cap = v->cap ? v->cap * 2 : 1024; v->v = (ReadEnds **) realloc(v->v, v->cap * sizeof(*v->v)); }
+    v->v[v->n++] = e;
+}
+
+/* mark_duplicates.cpp:402-414 */
+static int comparable(const ReadEnds *l, const ReadEnds *r, int compare_read2) {
+    int ret = l->libraryId == r->libraryId && l->read1Sequence == r->read1Sequence &&
+              l->read1Coordinate == r->read1Coordinate && l->orientation == r->orientation;
+    if (ret && compare_read2) ret = l->read2Sequence == r->read2Sequence && l->read2Coordinate == r->read2Coordinate;
+    return ret;
+}
+
+/* mark_duplicates.cpp:477-480: std::set<int> insert (long -> int truncation). */
+static void add_dup(uint8_t *dup, uint64_t n, int64_t idx, uint64_t *calls) {
+    int32_t t = (int32_t) idx;
+    (*calls)++;
+    if (t >= 0 && (uint64_t) t < n) dup[t] = 1;
+}
+
+/* mark_duplicates.cpp:488-507 */
+static void mark_pairs(ReadEnds **list, uint64_t cnt, uint8_t *dup, uint64_t n, uint64_t *calls) {
+    int16_t max_score = 0; ReadEnds *best = NULL; uint64_t i;
+    for (i = 0; i < cnt; i++) if (list[i]->score > max_score || best == NULL) { max_score = list[i]->score; best = list[i]; }
+    for (i = 0; i < cnt; i++) if (list[i] != best) { add_dup(dup, n, list[i]->read1IndexInFile, calls); add_dup(dup, n, list[i]->read2IndexInFile, calls); }
+}
+
+/* mark_duplicates.cpp:515-540 */
+static void mark_frags(ReadEnds **list, uint64_t cnt, int contains_pairs, uint8_t *dup, uint64_t n, uint64_t *calls) {
+    uint64_t i;
+    if (contains_pairs) {
+        for (i = 0; i < cnt; i++) if (list[i]->read2Sequence == -1) add_dup(dup, n, list[i]->read1IndexInFile, calls);
+    } else {
+        int16_t max_score = 0; ReadEnds *best = NULL;
+        for (i = 0; i < cnt; i++) if (list[i]->score > max_score || best == NULL) { max_score = list[i]->score; best = list[i]; }
+        for (i = 0; i < cnt; i++) if (list[i] != best) add_dup(dup, n, list[i]->read1IndexInFile, calls);
+    }
+}
+
+/*
+ * The whole path: MarkDuplicates::runInternal (mark_duplicates.cpp:422-475).
+ *   records/offsets : raw BAM records back to back, offsets[n+1]
+ *   compat_quiet    : reproduce the reference's non-verbose behaviour (index never
+ *                     increments, mark_duplicates.cpp:250).  0 = canonical (-v).
+ *   flags_out       : n u16 flag words after the rewrite loop (:443-465)
+ *   ends_out        : optional, n OracleEnd
+ *   stats_out       : optional [4]: frag entries, pair entries, addIndexAsDuplicate calls, unmatched
+ * returns 0, or -1 on allocation failure.
+ */
+int oge_oracle_markdup(const uint8_t *records, const uint64_t *offsets, uint64_t n,
+                       const char *const *rg_ids, const int16_t *rg_lib, int32_t n_rg, int16_t unknown_lib,
+                       int compat_quiet, uint16_t *flags_out, OracleEnd *ends_out, uint64_t *stats_out) {
+    LibTable lt;
+    Map tmp;
+    Vec pair_sort = {0, 0, 0}, frag_sort = {0, 0, 0};
+    uint8_t *dup = (uint8_t *) calloc(n ? n : 1, 1);
+    uint64_t calls = 0, i;
+    int64_t index = 0;
+    if (!dup) return -1;
+    lt.rg_ids = rg_ids; lt.rg_lib = rg_lib; lt.n_rg = n_rg; lt.unknown_lib = unknown_lib;
+    map_init(&tmp, 1 << 16);
+
+    /* buildSortedReadEndLists, mark_duplicates.cpp:185-279 */
+    for (i = 0; i < n; i++) {
+        Rec r;
+        decode(records + offsets[i], &r);
+        if (ends_out) memset(&ends_out[i], 0, sizeof(OracleEnd));
+        if ((r.flag & 0x4) || r.ref_id == -1) {
+            /* unmapped / no coordinate: passes through (:202-204) */
+        } else if (!(r.flag & 0x100)) {
+            ReadEnds *frag = (ReadEnds *) malloc(sizeof(ReadEnds));
+            build_read_ends(&lt, index, &r, frag);
+            vec_push(&frag_sort, frag);
+            if (ends_out) {
+                OracleEnd *o = &ends_out[i];
+                o->eligible = 1; o->ref = frag->read1Sequence; o->coord = frag->read1Coordinate;
+                o->orientation = frag->orientation; o->read2Sequence = frag->read2Sequence;
+                o->score = frag->score; o->lib = frag->libraryId;
+                o->pair_eligible = (r.flag & 0x1) && !(r.flag & 0x8);
+            }
+            if ((r.flag & 0x1) && !(r.flag & 0x8)) {
+                uint32_t rg_len; const uint8_t *rg = find_rg(&r, &rg_len);
+                uint32_t name_len = r.l_read_name ? r.l_read_name - 1 : 0;
+                Slot *s = map_find(&tmp, rg, rg_len, r.name, name_len);
+                ReadEnds *paired = s->val;
+                if (paired) map_erase(&tmp, s);
+                if (paired == NULL) {
+                    paired = (ReadEnds *) malloc(sizeof(ReadEnds));
+                    build_read_ends(&lt, index, &r, paired);
+                    map_put(&tmp, rg, rg_len, r.name, name_len, paired);
+                } else {
+                    int32_t sequence = frag->read1Sequence, coordinate = frag->read1Coordinate;
+                    int rev = (r.flag & 0x10) != 0;
+                    if (sequence > paired->read1Sequence ||
+                        (sequence == paired->read1Sequence && coordinate >= paired->read1Coordinate)) {
+                        paired->read2Sequence = sequence;
+                        paired->read2Coordinate = coordinate;
+                        paired->read2IndexInFile = index;
+                        paired->orientation = orientation_byte(paired->orientation == RE_R, rev);
+                    } else {
+                        paired->read2Sequence = paired->read1Sequence;
+                        paired->read2Coordinate = paired->read1Coordinate;
+                        paired->read2IndexInFile = paired->read1IndexInFile;
+                        paired->read1Sequence = sequence;
+                        paired->read1Coordinate = coordinate;
+                        paired->read1IndexInFile = index;
+                        paired->orientation = orientation_byte(rev, paired->orientation == RE_R);
+                    }
+                    paired->score = (int16_t)(paired->score + score_of(&r));
+                    vec_push(&pair_sort, paired);
+                }
+            }
+        }
+        if (!compat_quiet) ++index;   /* :250 -- only advances when verbose */
+    }
+
+    if (pair_sort.n) qsort(pair_sort.v, pair_sort.n, sizeof(ReadEnds *), ends_compare);   /* :262-265 */
+    if (frag_sort.n) qsort(frag_sort.v, frag_sort.n, sizeof(ReadEnds *), ends_compare);   /* :267-271 */
+
+    if (stats_out) { stats_out[0] = frag_sort.n; stats_out[1] = pair_sort.n; stats_out[3] = tmp.used; }
+
+    /* generateDuplicateIndexes, mark_duplicates.cpp:326-400 */
+    {
+        ReadEnds *first = NULL;
+        uint64_t chunk_start = 0, chunk_n = 0;
+        int contains_pairs = 0, contains_frags = 0;
+        for (i = 0; i < pair_sort.n; i++) {
+            ReadEnds *next = pair_sort.v[i];
+            if (first == NULL) { first = next; chunk_start = i; chunk_n = 1; }
+            else if (comparable(first, next, 1)) chunk_n++;
+            else {
+                if (chunk_n > 1) mark_pairs(pair_sort.v + chunk_start, chunk_n, dup, n, &calls);
+                chunk_start = i; chunk_n = 1; first = next;
+            }
+        }
+        mark_pairs(pair_sort.v + chunk_start, chunk_n, dup, n, &calls);
+
+        first = NULL; chunk_start = 0; chunk_n = 0;
+        for (i = 0; i < frag_sort.n; i++) {
+            ReadEnds *next = frag_sort.v[i];
+            if (first != NULL && comparable(first, next, 0)) {
+                chunk_n++;
+                contains_pairs = contains_pairs || next->read2Sequence != -1;
+                contains_frags = contains_frags || next->read2Sequence == -1;
+            } else {
+                if (chunk_n > 1 && contains_frags) mark_frags(frag_sort.v + chunk_start, chunk_n, contains_pairs, dup, n, &calls);
+                chunk_start = i; chunk_n = 1; first = next;
+                contains_pairs = next->read2Sequence != -1;
+                contains_frags = next->read2Sequence == -1;
+            }
+        }
+        mark_frags(frag_sort.v + chunk_start, chunk_n, contains_pairs, dup, n, &calls);
+    }
+    if (stats_out) stats_out[2] = calls;
+
+    /* rewrite loop, mark_duplicates.cpp:443-465 + BamAlignment.cpp:600-603 */
+    for (i = 0; i < n; i++) {
+        uint16_t flag = rd_u16(records + offsets[i] + 18);
+        if (!(flag & 0x100)) flag = dup[i] ? (uint16_t)(flag | 0x400) : (uint16_t)(flag & ~0x400);
+        flags_out[i] = flag;
+    }
+
+    for (i = 0; i < pair_sort.n; i++) free(pair_sort.v[i]);
+    for (i = 0; i < frag_sort.n; i++) free(frag_sort.v[i]);
+    for (i = 0; i < tmp.cap; i++) if (tmp.s[i].val) free(tmp.s[i].val);   /* :274-278 */
+    free(pair_sort.v); free(frag_sort.v); free(tmp.s); free(dup);
+    return 0;
+}

@@ -1,0 +1,130 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes front-end of oracle/markdup_oracle.c and of the
+compiled reference (oracle/_ref/oge_ref_dedup).  Import only from tests/, smoke() and
+bench.py's cpu_baseline / --impl reference legs."""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from openge_b200 import _build, bamio, header  # noqa: E402
+
+
+class OracleEnd(C.Structure):
+    _fields_ = [("eligible", C.c_int32), ("pair_eligible", C.c_int32), ("ref", C.c_int32),
+                ("coord", C.c_int32), ("orientation", C.c_int32), ("read2Sequence", C.c_int32),
+                ("score", C.c_int16), ("lib", C.c_int16)]
+
+
+END_DTYPE = np.dtype([("eligible", "<i4"), ("pair_eligible", "<i4"), ("ref", "<i4"), ("coord", "<i4"),
+                      ("orientation", "<i4"), ("read2Sequence", "<i4"), ("score", "<i2"), ("lib", "<i2")])
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(_build.ensure_oracle())
+        L.oge_oracle_markdup.restype = C.c_int
+        L.oge_oracle_markdup.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_char_p), C.c_void_p,
+                                         C.c_int32, C.c_int16, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def markdup(records: np.ndarray, offsets: np.ndarray, text: str, compat_quiet: bool = False, want_ends: bool = False):
+    """CPU oracle over framed records -> flags (u16 per record) [, ends, stats]."""
+    L = lib()
+    rg_ids, lib_ids, unknown, _ = header.library_table(text)
+    n = len(offsets) - 1
+    ids = (C.c_char_p * max(1, len(rg_ids)))(*rg_ids)
+    libs = np.asarray(lib_ids if lib_ids else [0], dtype=np.int16)
+    flags = np.zeros(n, dtype=np.uint16)
+    ends = np.zeros(n, dtype=END_DTYPE) if want_ends else None
+    stats = np.zeros(4, dtype=np.uint64)
+    records = np.ascontiguousarray(records)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    rc = L.oge_oracle_markdup(records.ctypes.data, offsets.ctypes.data, n, ids, libs.ctypes.data, len(rg_ids),
+                              unknown, int(compat_quiet), flags.ctypes.data,
+                              ends.ctypes.data if want_ends else None, stats.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("oracle failed")
+    if want_ends:
+        return flags, ends, stats
+    return flags
+
+
+def markdup_split(bam, n_chains: int):
+    """Compat F2: independent runs over refID % n sub-streams (split_by_chromosome.cpp:45-50)."""
+    off = bam.offsets[:-1].astype(np.int64)
+    ref = bam.records[off[:, None] + np.arange(4, 8)].copy().view("<i4").ravel()
+    chain = np.where(ref < 0, 0, ref % n_chains)
+    flags = np.zeros(bam.n, dtype=np.uint16)
+    sizes = np.diff(bam.offsets.astype(np.int64))
+    for c in range(n_chains):
+        idx = np.nonzero(chain == c)[0]
+        if len(idx) == 0:
+            continue
+        recs = [bam.records[off[i]: off[i] + sizes[i]].tobytes() for i in idx]
+        r, o = bamio.concat_records(recs)
+        flags[idx] = markdup(r, o, bam.text)
+    return flags
+
+
+def ref_available() -> bool:
+    return _build.ensure_ref() is not None
+
+
+def ref_dedup(bam, nosplit=True, verbose=True, remove=False, threads=None, tmpdir=None):
+    """Run the compiled reference (file -> file, rawbam both ways) -> output BamFile."""
+    exe = _build.ensure_ref()
+    if exe is None:
+        raise RuntimeError("oracle/_ref/oge_ref_dedup not built")
+    base = tmpdir or ("/dev/shm" if os.path.isdir("/dev/shm") else None)
+    with tempfile.TemporaryDirectory(dir=base) as d:
+        inp, out = os.path.join(d, "in.rawbam"), os.path.join(d, "out.rawbam")
+        bamio.write_bam(inp, bam, raw=True)
+        cmd = [exe, "-T", d, "-F", "rawbam"]
+        if verbose:
+            cmd.append("-v")
+        if nosplit:
+            cmd.append("--nosplit")
+        if remove:
+            cmd.append("-r")
+        if threads:
+            cmd += ["-t", str(threads)]
+        cmd += [inp, out]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        if r.returncode != 0:
+            raise RuntimeError("reference failed: %s" % r.stderr.decode()[-2000:])
+        return bamio.read_bam(out)
+
+
+def ref_time_mem(bam, reps=1, threads=None, tmpdir=None):
+    """Time MarkDuplicates::runInternal in the compiled reference with records preloaded in RAM.
+    -> dict(records, threads, seconds[list], duplicates)"""
+    exe = _build.ensure_ref()
+    if exe is None:
+        raise RuntimeError("oracle/_ref/oge_ref_dedup not built")
+    base = tmpdir or ("/dev/shm" if os.path.isdir("/dev/shm") else None)
+    with tempfile.TemporaryDirectory(dir=base) as d:
+        inp = os.path.join(d, "in.rawbam")
+        bamio.write_bam(inp, bam, raw=True)
+        cmd = [exe, "--mem", "-v", "-T", d, "--reps", str(reps)]
+        if threads:
+            cmd += ["-t", str(threads)]
+        cmd.append(inp)
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+        if r.returncode != 0:
+            raise RuntimeError("reference failed")
+        return json.loads(r.stdout.decode().strip().splitlines()[-1])
