@@ -1,0 +1,137 @@
+"""Known-answer fixtures of SURVEY.md appendix A.3, rebuilt as raw BAM records.
+
+Expected flags were produced by the compiled reference (`--nosplit -v`) and are re-checked
+against it by tests/golden/make_golden.py whenever /root/reference is present.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from openge_b200 import bamio
+
+SEQ100 = "ACGT" * 25
+
+
+def _rec(name, flag, ref, pos1, cigar, mref, mpos1, q, rg="rg1", seq=None):
+    seq = SEQ100 if seq is None else seq
+    qual = ord(q) - 33 if isinstance(q, str) else q
+    tags = bamio.tag_z("RG", rg) if rg else b""
+    return bamio.build_record(name, flag, ref, pos1 - 1, 60 if not (flag & 4) else 0, cigar,
+                              mref, (mpos1 - 1) if mpos1 else -1, 0, seq, qual, tags)
+
+
+def fixture1():
+    """27 records, two contigs, two libraries.  -> (BamFile, expected dup bit per record)."""
+    text = ("@HD\tVN:1.4\tSO:coordinate\n@SQ\tSN:chr1\tLN:100000\n@SQ\tSN:chr2\tLN:100000\n"
+            "@RG\tID:rg1\tLB:libA\tSM:s\n@RG\tID:rg2\tLB:libB\tSM:s\n")
+    R = [
+        # name, flag, ref, pos, cigar, mate ref, mate pos, qual, rg, expected dup
+        ("A_tie_first", 99, 0, 1000, "100M", 0, 1300, "I", "rg1", 0),
+        ("B_tie_second", 99, 0, 1000, "100M", 0, 1300, "I", "rg1", 1),
+        ("H_frag_vs_pairs", 0, 0, 1000, "100M", -1, 0, "I", "rg1", 1),
+        ("S_otherlib", 99, 0, 1000, "100M", 0, 1300, "I", "rg2", 0),
+        ("A_tie_first", 147, 0, 1300, "100M", 0, 1000, "I", "rg1", 0),
+        ("B_tie_second", 147, 0, 1300, "100M", 0, 1000, "I", "rg1", 1),
+        ("S_otherlib", 147, 0, 1300, "100M", 0, 1000, "I", "rg2", 0),
+        ("D_lowscore", 99, 0, 5000, "100M", 0, 5300, "?", "rg1", 1),
+        ("E_highscore", 99, 0, 5000, "100M", 0, 5300, "I", "rg1", 0),
+        ("D_lowscore", 147, 0, 5300, "100M", 0, 5000, "?", "rg1", 1),
+        ("E_highscore", 147, 0, 5300, "100M", 0, 5000, "I", "rg1", 0),
+        ("F_noclip", 99, 0, 8000, "100M", 0, 8300, "I", "rg1", 0),
+        ("G_softclip", 99, 0, 8005, "5S95M", 0, 8300, "I", "rg1", 1),
+        ("F_noclip", 147, 0, 8300, "100M", 0, 8000, "I", "rg1", 0),
+        ("G_softclip", 147, 0, 8300, "100M", 0, 8005, "I", "rg1", 1),
+        ("I_fragR_low", 16, 0, 12000, "100M", -1, 0, "5", "rg1", 0),
+        ("J_fragR_high", 16, 0, 12010, "90M10S", -1, 0, "I", "rg1", 0),
+        ("K_xchrom_first", 99, 0, 20000, "100M", 1, 500, "I", "rg1", 0),
+        ("L_xchrom_second", 99, 0, 20000, "100M", 1, 500, "I", "rg1", 1),
+        ("M_mateunmapped1", 73, 0, 30000, "100M", 0, 30000, "I", "rg1", 0),
+        ("M_mateunmapped1", 133, 0, 30000, "*", 0, 30000, "I", "rg1", 0),
+        ("N_mateunmapped2", 73, 0, 30000, "100M", 0, 30000, "I", "rg1", 1),
+        ("N_mateunmapped2", 133, 0, 30000, "*", 0, 30000, "I", "rg1", 0),
+        ("P_q14", 0, 0, 40000, "100M", -1, 0, "/", "rg1", 1),
+        ("R_q15", 0, 0, 40000, "100M", -1, 0, "0", "rg1", 0),
+        ("K_xchrom_first", 147, 1, 500, "100M", 0, 20000, "I", "rg1", 0),
+        ("L_xchrom_second", 147, 1, 500, "100M", 0, 20000, "I", "rg1", 1),
+    ]
+    recs = [_rec(n, f, r, p, c, mr, mp, q, rg) for n, f, r, p, c, mr, mp, q, rg, _ in R]
+    records, offsets = bamio.concat_records(recs)
+    bam = bamio.BamFile(text=text, refs=[("chr1", 100000), ("chr2", 100000)], records=records, offsets=offsets)
+    return bam, np.array([x[-1] for x in R], dtype=np.uint8)
+
+
+def fixture2():
+    """Less obvious rules: short wrap, repeated names, supplementary, pre-set 0x400."""
+    text = "@HD\tVN:1.4\tSO:coordinate\n@SQ\tSN:chr1\tLN:100000\n@RG\tID:rg1\tLB:libA\tSM:s\n"
+    R = [
+        # name, flag, pos, cigar, mate pos, seq len, expected flag out
+        ("X_long_wraps", 0, 1000, "1000M", 0, 1000, 1024),
+        ("Y_short", 0, 1000, "100M", 0, 100, 0),
+        ("T_multi", 99, 5000, "100M", 5300, 100, 99),
+        ("T_multi", 99, 5000, "100M", 5300, 100, 99),
+        ("T_multi", 147, 5300, "100M", 5000, 100, 147),
+        ("T_multi", 147, 5300, "100M", 5000, 100, 147),
+        ("U_pair", 99, 9000, "100M", 9300, 100, 99),
+        ("V_pair", 99, 9000, "100M", 9300, 100, 99),
+        ("U_pair", 2147, 9100, "50M50H", 9300, 50, 2147),
+        ("U_pair", 147, 9300, "100M", 9000, 100, 147),
+        ("V_pair", 147, 9300, "100M", 9000, 100, 147),
+        ("W_secondary_predup", 1280, 20000, "100M", 0, 100, 1280),
+        ("Z_primary_predup", 1024, 30000, "100M", 0, 100, 0),
+    ]
+    recs = []
+    for n, f, p, c, mp, ls, _ in R:
+        seq = ("ACGT" * 250)[:ls]
+        recs.append(_rec(n, f, 0, p, c, 0 if mp else -1, mp, "I", "rg1", seq=seq))
+    records, offsets = bamio.concat_records(recs)
+    bam = bamio.BamFile(text=text, refs=[("chr1", 100000)], records=records, offsets=offsets)
+    return bam, np.array([x[-1] for x in R], dtype=np.uint16)
+
+
+def edge_cases():
+    """Extra hand-built cases beyond A.3 (tag walk, RG typing, key ':' ambiguity, negative
+    unclipped coordinates, empty names).  Expected values come from the oracle/reference."""
+    text = ("@HD\tVN:1.4\tSO:coordinate\n@SQ\tSN:chr1\tLN:100000\n@SQ\tSN:chr2\tLN:5000\n"
+            "@RG\tID:a\tLB:L1\n@RG\tID:a:\tLB:L1\n@RG\tID:b\tLB:L2\n@RG\tID:c\n@RG\tID:a\tLB:L9\n")
+    recs = []
+
+    def add(name, flag, ref, pos1, cigar, mref, mpos1, q=40, tags=b"", ls=50):
+        seq = ("ACGT" * 100)[:ls]
+        recs.append(bamio.build_record(name, flag, ref, pos1 - 1, 30, cigar, mref,
+                                       (mpos1 - 1) if mpos1 else -1, 0, seq, q, tags))
+
+    # reads whose unclipped start goes negative (leading clip longer than pos)
+    add("neg1", 0, 0, 3, "10S40M", -1, 0, tags=bamio.tag_z("RG", "a"))
+    add("neg2", 0, 0, 5, "12S38M", -1, 0, tags=bamio.tag_z("RG", "a"))
+    # key ambiguity: RG "a:" + ":" + "x"  ==  RG "a" + ":" + ":x" in the reference's map
+    add(":x", 99, 0, 100, "50M", 0, 300, tags=bamio.tag_z("RG", "a"))
+    add("x", 147, 0, 300, "50M", 0, 100, tags=bamio.tag_z("RG", "a:"))
+    add(":x", 99, 0, 100, "50M", 0, 300, tags=bamio.tag_z("RG", "a"))
+    add("x", 147, 0, 300, "50M", 0, 100, tags=bamio.tag_z("RG", "a:"))
+    # tags in front of RG: integer, string, array; RG found after them
+    pre = b"NMC\x03" + b"ASi\x10\x00\x00\x00" + b"XBBs\x02\x00\x00\x00\x01\x00\x02\x00" + bamio.tag_z("MD", "50")
+    add("t1", 0, 0, 1000, "50M", -1, 0, tags=pre + bamio.tag_z("RG", "b"))
+    add("t2", 0, 0, 1000, "50M", -1, 0, q=20, tags=bamio.tag_z("RG", "b") + pre)
+    add("t3", 0, 0, 1000, "50M", -1, 0, q=30, tags=pre)                      # no RG -> Unknown Library
+    add("t4", 0, 0, 1000, "50M", -1, 0, q=25, tags=bamio.tag_z("RG", "c"))   # RG without LB -> Unknown Library
+    add("t5", 0, 0, 1000, "50M", -1, 0, q=35, tags=bamio.tag_z("RG", "zz"))  # unknown id -> Unknown Library
+    # a tag whose type byte is NUL stops the walk before RG is seen
+    add("t6", 0, 0, 1000, "50M", -1, 0, q=39, tags=b"XX\x00" + bamio.tag_z("RG", "b"))
+    # RG with a non-Z type code is still taken as a string by the reference
+    add("t7", 0, 0, 1000, "50M", -1, 0, q=38, tags=b"RGAb\x00")
+    # zero-length read name pairs, =/X/N/D/I/P ops, reverse strand ends
+    add("", 99, 0, 2000, "10=5X5N10D5I2P25M", 0, 2500, tags=bamio.tag_z("RG", "a"))
+    add("", 147, 0, 2500, "20M5S5H", 0, 2000, tags=bamio.tag_z("RG", "a"), ls=25)
+    add("dupe", 99, 0, 2000, "20M20N10M20S", 0, 2480, tags=bamio.tag_z("RG", "a"))
+    add("dupe", 147, 0, 2480, "5H10S40M", 0, 2000, tags=bamio.tag_z("RG", "a"))
+    # paired flag with mate "mapped" but mate refID -1
+    add("odd", 65, 0, 3000, "50M", -1, 0, tags=bamio.tag_z("RG", "a"))
+    add("odd2", 0, 0, 3000, "50M", -1, 0, q=10, tags=bamio.tag_z("RG", "a"))
+    # missing qualities (0xFF) count as 255 each
+    add("ff1", 0, 1, 100, "50M", -1, 0, q=255, tags=bamio.tag_z("RG", "a"))
+    add("ff2", 0, 1, 100, "50M", -1, 0, q=40, tags=bamio.tag_z("RG", "a"))
+    # mapped flag but refID -1; unmapped with coordinates
+    add("noref", 0, -1, 0, "50M", -1, 0)
+    add("unm", 4, 1, 100, "*", -1, 0)
+    records, offsets = bamio.concat_records(recs)
+    return bamio.BamFile(text=text, refs=[("chr1", 100000), ("chr2", 5000)], records=records, offsets=offsets)
