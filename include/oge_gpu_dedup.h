@@ -1,0 +1,159 @@
+/*
+ * oge_gpu_dedup.h -- C ABI of the B200 duplicate-marking path (libopenge_b200.so).
+ *
+ * The reference (adaptivegenome/openge) has no FFI for this path: the operator interface is the
+ * C++ class MarkDuplicates : AlgorithmModule (src/algorithms/mark_duplicates.h:27-68,
+ * src/algorithms/algorithm_module.h:33-107).  This header is the boundary a drop-in
+ * MarkDuplicates (openge_b200/host/mark_duplicates_gpu.{h,cpp}) binds instead of the CPU code.
+ * Each entry point names the reference code it stands in for.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every function returns 0 on success
+ * and a negative OGE_ERR_* code on failure (the reference's convention is message + exit(-1),
+ * e.g. util/bam_deserializer.h:155-163; the host shim maps codes back to that);
+ * oge_gpu_last_error() gives the message.  A context is used by one host thread at a time
+ * (one MarkDuplicates instance = one pthread, algorithm_module.cpp:118-122); several contexts
+ * may coexist (split-by-chromosome mode, command_dedup.cpp:71-95).
+ *
+ * Record format = raw BAM records exactly as the reference (de)serialises them
+ * (util/bam_deserializer.h:144-193, util/bam_serializer.h:106-141): 4-byte block_size, 32-byte
+ * core, name, cigar, packed bases, qualities, tags; records back to back; offsets[n+1] byte
+ * offsets relative to the first record of the batch.
+ */
+#ifndef OGE_GPU_DEDUP_H
+#define OGE_GPU_DEDUP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OGE_GPU_DEDUP_ABI_VERSION 1
+
+enum {
+    OGE_OK = 0,
+    OGE_ERR_INVALID_ARG = -1,
+    OGE_ERR_CUDA = -2,          /* CUDA runtime failure or no usable device (never a CPU fallback) */
+    OGE_ERR_NOMEM = -3,
+    OGE_ERR_KEY_RANGE = -4,     /* a record's refID/coordinate/library does not fit the key layout */
+    OGE_ERR_STATE = -5,         /* call order violated (e.g. flags before run) */
+    OGE_ERR_TOO_LARGE = -6,     /* more than 2^30 records in one context */
+    OGE_ERR_BAD_RECORD = -7     /* malformed record chain (block_size < 32, offsets not increasing) */
+};
+
+typedef struct oge_gpu_dedup_ctx oge_gpu_dedup_ctx;
+
+/* Mirrors the knobs of MarkDuplicates + DedupCommand (mark_duplicates.h:41, command_dedup.cpp:39-48). */
+typedef struct oge_gpu_dedup_config {
+    int32_t abi_version;            /* OGE_GPU_DEDUP_ABI_VERSION */
+    int32_t device;                 /* CUDA device ordinal */
+    int32_t n_ref;                  /* number of @SQ entries (BamHeader::getSequences().size()) */
+    int32_t max_ref_len;            /* largest @SQ LN; <=0 -> full 32-bit coordinate field */
+    int32_t clip_margin;            /* slack for clipped ends beyond [0, max_ref_len); <=0 -> 1<<20 */
+    int32_t remove_duplicates;      /* MarkDuplicates::removeDuplicates (-r); affects oge_gpu_dedup_pull only */
+    int32_t verify_names;           /* 1 (default when <0): hash-matched mates are confirmed by comparing the
+                                       RG+":"+name bytes (ReadEndsMap is keyed by that string,
+                                       picard_structures.h:82-109, mark_duplicates.cpp:210-214) */
+    int32_t compat_quiet_index_bug; /* 1: reproduce non-verbose runs of the reference, where the record index
+                                       never advances (mark_duplicates.cpp:250).  Default 0. */
+    int32_t debug_keep_ends;        /* 1: keep a copy of the per-record end entries for oge_gpu_dedup_debug_ends */
+    int32_t reserved0;
+    uint64_t capacity_records;      /* optional preallocation hints (0 = grow on demand) */
+    uint64_t capacity_bytes;
+    /* multi-GPU range sharding; world <= 1 means single GPU */
+    int32_t rank;
+    int32_t world;
+    uint64_t index_base;            /* global ordinal of this shard's first record */
+} oge_gpu_dedup_config;
+
+/* Per-run counters (the reference prints the analogous numbers under -v, mark_duplicates.cpp:261,433). */
+typedef struct oge_gpu_dedup_stats {
+    uint64_t n_records;
+    uint64_t n_frag_entries;        /* fragSort.size() */
+    uint64_t n_pair_entries;        /* pairSort.size() */
+    uint64_t n_duplicates;          /* records whose 0x400 bit is set after the run (primary only) */
+    uint64_t n_complex_names;       /* half-pair entries resolved on the exact slow path (name seen != 2 times) */
+    uint64_t n_hash_mismatch;       /* hash-equal mates rejected by the name comparison */
+    uint32_t frag_key_bits, pair_key_bits;
+    uint32_t frag_sort_passes, pair_sort_passes;
+    float ms_total;                 /* device time of the last oge_gpu_dedup_run, CUDA events */
+    float ms_endbuild, ms_join, ms_sort_frag, ms_sort_pair, ms_select, ms_flags;
+    uint64_t launches;              /* kernels launched by the last run */
+} oge_gpu_dedup_stats;
+
+/* Per-record view of the end-building kernel (buildReadEnds, mark_duplicates.cpp:147-164). */
+typedef struct oge_gpu_end {
+    int32_t eligible;               /* mapped && refID != -1 && primary (:202-205) */
+    int32_t pair_eligible;          /* eligible && paired && mate mapped (:209) */
+    int32_t ref;                    /* read1Sequence */
+    int32_t coord;                  /* read1Coordinate: unclipped 5' end (:88-129) */
+    int32_t orientation;            /* 1 = RE_F, 2 = RE_R (picard_structures.h:24-27) */
+    int32_t read2Sequence;          /* != -1 iff ReadEnds::isPaired() (picard_structures.h:54); only the
+                                       predicate is kept on the device: -1, or 0 for "paired" */
+    int16_t score;                  /* getScore (:135-144) */
+    int16_t lib;                    /* getLibraryId (:282-294) */
+} oge_gpu_end;
+
+/* MarkDuplicates::MarkDuplicates (mark_duplicates.cpp:27-39). */
+int oge_gpu_dedup_create(const oge_gpu_dedup_config *cfg, oge_gpu_dedup_ctx **out);
+void oge_gpu_dedup_destroy(oge_gpu_dedup_ctx *ctx);
+
+/* The header lookup getLibraryName/getLibraryId does per record (mark_duplicates.cpp:282-318,
+ * util/bam_header.h:214-241), resolved once on the host: ids[i] (NUL-terminated @RG ID, first
+ * occurrence of an ID wins) -> lib_ids[i] in 1..n_libs; reads with no/unknown RG or an @RG without
+ * LB get unknown_lib_id ("Unknown Library"). */
+int oge_gpu_dedup_set_readgroups(oge_gpu_dedup_ctx *ctx, const char *const *ids, const int16_t *lib_ids,
+                                 int32_t n, int16_t unknown_lib_id, int32_t n_libs);
+
+/* Stands in for the getInputAlignment() loop + temp-file spill of buildSortedReadEndLists
+ * (mark_duplicates.cpp:192-256): appends a batch of raw records to the device-resident record
+ * array.  `records` should be pinned (oge_gpu_host_alloc) for the copy to overlap; the call
+ * returns once the batch has been queued and the host buffer may be reused after
+ * oge_gpu_dedup_sync().  May be called repeatedly; record ordinals continue across batches. */
+int oge_gpu_dedup_push(oge_gpu_dedup_ctx *ctx, const uint8_t *records, uint64_t nbytes,
+                       const uint64_t *offsets, uint64_t nrec);
+int oge_gpu_dedup_sync(oge_gpu_dedup_ctx *ctx);
+
+/* buildSortedReadEndLists + generateDuplicateIndexes + the flag rewrite of runInternal
+ * (mark_duplicates.cpp:185-279, 326-400, 443-465) over everything pushed so far.  Idempotent:
+ * may be called again on the same resident records. */
+int oge_gpu_dedup_run(oge_gpu_dedup_ctx *ctx);
+
+/* Output side of runInternal (:443-465): the flag word of every record, in input order. */
+int oge_gpu_dedup_flags(oge_gpu_dedup_ctx *ctx, uint16_t *out, uint64_t n);
+
+/* Output side with records: copies the (flag-patched) records back; with remove_duplicates set,
+ * records whose flag has 0x400 are dropped (:456-458) and the rest are compacted in order.
+ * out_offsets (optional) receives out_nrec+1 offsets. */
+int oge_gpu_dedup_pull(oge_gpu_dedup_ctx *ctx, uint8_t *out_records, uint64_t cap_bytes,
+                       uint64_t *out_offsets, uint64_t cap_records, uint64_t *out_bytes, uint64_t *out_nrec);
+
+/* Forget the pushed records (keeps allocations); a context can then take the next file. */
+int oge_gpu_dedup_reset(oge_gpu_dedup_ctx *ctx);
+
+int oge_gpu_dedup_get_stats(oge_gpu_dedup_ctx *ctx, oge_gpu_dedup_stats *out);
+int oge_gpu_dedup_debug_ends(oge_gpu_dedup_ctx *ctx, oge_gpu_end *out, uint64_t n);
+
+/* Device pointers of the resident arrays, for callers that keep working on the GPU
+ * (and for bench.py's device-resident timing): records, offsets (u64, n+1), flags (u16, n). */
+int oge_gpu_dedup_device_ptrs(oge_gpu_dedup_ctx *ctx, void **records, void **offsets, void **flags);
+
+/* Test hook for the radix sort alone (K3): sorts n 16-byte little-endian 128-bit entries held in
+ * host memory by the bit range [bit_lo, bit_hi), stably, on `device`. */
+int oge_gpu_debug_sort128(int device, void *entries, uint64_t n, int bit_lo, int bit_hi);
+
+/* Pinned host memory for push/pull buffers. */
+void *oge_gpu_host_alloc(size_t nbytes);
+void oge_gpu_host_free(void *p);
+
+/* Number of CUDA devices visible (0 if none / driver missing). */
+int oge_gpu_device_count(void);
+
+const char *oge_gpu_last_error(void);
+int oge_gpu_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

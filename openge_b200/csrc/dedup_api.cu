@@ -1,0 +1,622 @@
+// C ABI of the B200 duplicate-marking path (include/oge_gpu_dedup.h).
+//
+// A context keeps the pushed BAM records resident in HBM and runs, on oge_gpu_dedup_run():
+//   K1 end-build -> K2 mate join (insert / resolve / exact slow path) -> K3 onesweep radix sort
+//   of pair and fragment entries -> K4 group-and-select -> K5 flag write
+// i.e. MarkDuplicates::runInternal (reference algorithms/mark_duplicates.cpp:422-475) without
+// the temp-file spill.  There is no CPU fallback: every entry point fails with OGE_ERR_CUDA when
+// no device is usable.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "oge_gpu_dedup.h"
+#include "radix_sort.cuh"
+
+namespace oge {
+
+static thread_local char g_err[512] = "";
+
+int fail_cuda(cudaError_t e, const char *what, const char *file, int line) {
+    snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s:%d: %s", (int) e, cudaGetErrorString(e), file, line, what);
+    cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? OGE_ERR_NOMEM : OGE_ERR_CUDA;
+}
+
+int fail_msg(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+static int bit_length(uint64_t v) {
+    int b = 0;
+    while (v) { b++; v >>= 1; }
+    return b;
+}
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;      // elements
+    int reserve(size_t n, bool keep, cudaStream_t s) {
+        if (n <= cap) return 0;
+        size_t want = keep && cap ? std::max(n, cap + cap / 2) : n;
+        T *q = nullptr;
+        cudaError_t e = cudaMalloc((void **) &q, want * sizeof(T) + 256);
+        if (e != cudaSuccess && want > n) {
+            cudaGetLastError();
+            want = n;
+            e = cudaMalloc((void **) &q, want * sizeof(T) + 256);
+        }
+        if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc", __FILE__, __LINE__);
+        if (keep && p && cap) {
+            e = cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) { cudaFree(q); return fail_cuda(e, "grow copy", __FILE__, __LINE__); }
+        }
+        if (p) cudaFree(p);
+        p = q;
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace oge
+
+using namespace oge;
+
+struct oge_gpu_dedup_ctx {
+    oge_gpu_dedup_config cfg;
+    int sms = 148;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t copy_done = nullptr;
+    cudaEvent_t ev[10];
+
+    // resident input
+    DevBuf<uint8_t> rec;
+    DevBuf<uint64_t> off;
+    uint64_t n = 0, rec_bytes = 0;
+
+    // read-group table
+    DevBuf<uint8_t> rg_bytes;
+    DevBuf<uint32_t> rg_off;
+    DevBuf<int16_t> rg_lib;
+    int n_rg = 0, n_libs = 1;
+    int16_t unknown_lib = 1;
+
+    // work arrays
+    DevBuf<E128> frag, sortbuf, pair, pair2;
+    DevBuf<uint64_t> hk;
+    DevBuf<uint16_t> rgcode, flag_in, flag_out;
+    DevBuf<uint8_t> dup, scratch, cplx_state;
+    DevBuf<uint32_t> mate_of, counters;
+    DevBuf<MateSlot> table;
+    uint32_t *h_counters = nullptr;      // pinned
+
+    KeyLayout kl;
+    bool ran = false;
+    oge_gpu_dedup_stats stats;
+};
+
+namespace {
+
+int compute_layout(oge_gpu_dedup_ctx *c, KeyLayout *L) {
+    memset(L, 0, sizeof(*L));
+    uint64_t top = c->cfg.index_base + c->n;
+    L->idx_bits = std::max(1, bit_length(top ? top - 1 : 0));
+    L->ref_bits = std::max(1, bit_length(c->cfg.n_ref > 1 ? (uint64_t) c->cfg.n_ref - 1 : 1));
+    if (c->cfg.max_ref_len > 0) {
+        int64_t margin = c->cfg.clip_margin > 0 ? c->cfg.clip_margin : (1 << 20);
+        uint64_t span = (uint64_t) c->cfg.max_ref_len + 2 * (uint64_t) margin;
+        L->coord_bits = bit_length(span - 1);
+        L->coord_bias = margin;
+        if (L->coord_bits > 32) { L->coord_bits = 32; L->coord_bias = 1ll << 31; }
+    } else {
+        L->coord_bits = 32;      // the whole int32 range
+        L->coord_bias = 1ll << 31;
+    }
+    L->lib_bits = bit_length((uint64_t) c->n_libs + 1);
+    L->lib_invalid = (1u << L->lib_bits) - 1;
+    int b = 16;
+    L->f_idx = b; b += L->idx_bits;
+    L->f_paired = b; b += 1;
+    L->f_orient = b; b += 1;
+    L->f_coord = b; b += L->coord_bits;
+    L->f_ref = b; b += L->ref_bits;
+    L->f_lib = b; b += L->lib_bits;
+    L->f_end = b;
+    b = 16;
+    L->p_idx = b; b += L->idx_bits;
+    L->p_coord2 = b; b += L->coord_bits;
+    L->p_ref2 = b; b += L->ref_bits;
+    L->p_orient = b; b += 2;
+    L->p_coord1 = b; b += L->coord_bits;
+    L->p_ref1 = b; b += L->ref_bits;
+    L->p_lib = b; b += L->lib_bits;
+    L->p_end = b;
+    if (L->f_end > 128 || L->p_end > 128)
+        return fail_msg(OGE_ERR_KEY_RANGE,
+                        "key layout needs %d (frag) / %d (pair) bits, more than the 128 of a 16-byte entry: "
+                        "idx %d, coord %d, ref %d, lib %d bits (set max_ref_len / n_ref in the config)",
+                        L->f_end, L->p_end, L->idx_bits, L->coord_bits, L->ref_bits, L->lib_bits);
+    return 0;
+}
+
+RgTable rg_table(oge_gpu_dedup_ctx *c) {
+    RgTable t;
+    t.bytes = c->rg_bytes.p;
+    t.off = c->rg_off.p;
+    t.lib = c->rg_lib.p;
+    t.n = c->n_rg;
+    t.unknown_lib = c->unknown_lib;
+    return t;
+}
+
+__global__ void offsets_rebase(uint64_t *off, uint64_t n, uint64_t base) {
+    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) off[i] += base;
+}
+
+int ensure_work(oge_gpu_dedup_ctx *c) {
+    const uint64_t n = c->n;
+    cudaStream_t s = c->stream;
+    int rc;
+    if ((rc = c->frag.reserve(n, false, s))) return rc;
+    if ((rc = c->sortbuf.reserve(n, false, s))) return rc;
+    if ((rc = c->hk.reserve(n, false, s))) return rc;
+    if ((rc = c->rgcode.reserve(n, false, s))) return rc;
+    if ((rc = c->flag_in.reserve(n, false, s))) return rc;
+    if ((rc = c->flag_out.reserve(n, false, s))) return rc;
+    if ((rc = c->dup.reserve(n, false, s))) return rc;
+    if ((rc = c->mate_of.reserve(n, false, s))) return rc;
+    if ((rc = c->scratch.reserve(std::max(sort_scratch_bytes(n), compact_scratch_bytes(n)), false, s))) return rc;
+    return 0;
+}
+
+float ms_between(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+}
+
+}  // namespace
+
+extern "C" {
+
+int oge_gpu_abi_version(void) { return OGE_GPU_DEDUP_ABI_VERSION; }
+
+const char *oge_gpu_last_error(void) { return g_err; }
+
+int oge_gpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void *oge_gpu_host_alloc(size_t nbytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, nbytes ? nbytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void oge_gpu_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+int oge_gpu_dedup_create(const oge_gpu_dedup_config *cfg, oge_gpu_dedup_ctx **out) {
+    if (!cfg || !out) return fail_msg(OGE_ERR_INVALID_ARG, "create: null argument");
+    if (cfg->abi_version != OGE_GPU_DEDUP_ABI_VERSION)
+        return fail_msg(OGE_ERR_INVALID_ARG, "create: ABI version %d, library is %d", cfg->abi_version, OGE_GPU_DEDUP_ABI_VERSION);
+    int ndev = oge_gpu_device_count();
+    if (ndev <= 0) return fail_msg(OGE_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail_msg(OGE_ERR_INVALID_ARG, "create: device %d of %d", cfg->device, ndev);
+    OGE_CUDA_TRY(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    OGE_CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10)
+        return fail_msg(OGE_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+    oge_gpu_dedup_ctx *c = new oge_gpu_dedup_ctx();
+    c->cfg = *cfg;
+    if (c->cfg.verify_names < 0) c->cfg.verify_names = 1;
+    c->sms = prop.multiProcessorCount;
+    memset(&c->stats, 0, sizeof(c->stats));
+    int rc = 0;
+    do {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming) != cudaSuccess) {
+            rc = fail_cuda(cudaGetLastError(), "stream/event create", __FILE__, __LINE__);
+            break;
+        }
+        for (auto &e : c->ev) cudaEventCreate(&e);
+        if (cudaHostAlloc((void **) &c->h_counters, CNT_N * 4, cudaHostAllocDefault) != cudaSuccess) {
+            rc = fail_cuda(cudaGetLastError(), "cudaHostAlloc", __FILE__, __LINE__);
+            break;
+        }
+        if ((rc = c->counters.reserve(CNT_N, false, c->stream))) break;
+        if ((rc = radix_sort_init())) break;
+        if (cfg->capacity_bytes && (rc = c->rec.reserve(cfg->capacity_bytes, false, c->stream))) break;
+        if (cfg->capacity_records && (rc = c->off.reserve(cfg->capacity_records + 1, false, c->stream))) break;
+    } while (0);
+    if (rc) {
+        oge_gpu_dedup_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return OGE_OK;
+}
+
+void oge_gpu_dedup_destroy(oge_gpu_dedup_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    c->rec.release(); c->off.release(); c->rg_bytes.release(); c->rg_off.release(); c->rg_lib.release();
+    c->frag.release(); c->sortbuf.release(); c->pair.release(); c->pair2.release(); c->hk.release();
+    c->rgcode.release(); c->flag_in.release(); c->flag_out.release(); c->dup.release(); c->scratch.release();
+    c->cplx_state.release(); c->mate_of.release(); c->counters.release(); c->table.release();
+    if (c->h_counters) cudaFreeHost(c->h_counters);
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->copy_done) cudaEventDestroy(c->copy_done);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    delete c;
+}
+
+int oge_gpu_dedup_set_readgroups(oge_gpu_dedup_ctx *c, const char *const *ids, const int16_t *lib_ids, int32_t n,
+                                 int16_t unknown_lib_id, int32_t n_libs) {
+    if (!c || n < 0 || (n > 0 && (!ids || !lib_ids))) return fail_msg(OGE_ERR_INVALID_ARG, "set_readgroups: bad argument");
+    if (n >= (int32_t) RGC_UNKNOWN) return fail_msg(OGE_ERR_INVALID_ARG, "set_readgroups: more than %u read groups", RGC_UNKNOWN - 1);
+    if (n_libs < 1 || unknown_lib_id < 1 || unknown_lib_id > n_libs)
+        return fail_msg(OGE_ERR_INVALID_ARG, "set_readgroups: library ids must lie in 1..n_libs");
+    OGE_CUDA_TRY(cudaSetDevice(c->cfg.device));
+    std::vector<uint8_t> bytes;
+    std::vector<uint32_t> off(1, 0);
+    std::vector<int16_t> lib;
+    for (int i = 0; i < n; i++) {
+        if (!ids[i]) return fail_msg(OGE_ERR_INVALID_ARG, "set_readgroups: null id");
+        if (lib_ids[i] < 1 || lib_ids[i] > n_libs) return fail_msg(OGE_ERR_INVALID_ARG, "set_readgroups: library id %d out of 1..%d", lib_ids[i], n_libs);
+        size_t l = strlen(ids[i]);
+        bytes.insert(bytes.end(), ids[i], ids[i] + l);
+        off.push_back((uint32_t) bytes.size());
+        lib.push_back(lib_ids[i]);
+    }
+    int rc;
+    if ((rc = c->rg_bytes.reserve(bytes.size() + 1, false, c->stream))) return rc;
+    if ((rc = c->rg_off.reserve(off.size(), false, c->stream))) return rc;
+    if ((rc = c->rg_lib.reserve(lib.size() + 1, false, c->stream))) return rc;
+    if (!bytes.empty()) OGE_CUDA_TRY(cudaMemcpy(c->rg_bytes.p, bytes.data(), bytes.size(), cudaMemcpyHostToDevice));
+    OGE_CUDA_TRY(cudaMemcpy(c->rg_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+    if (!lib.empty()) OGE_CUDA_TRY(cudaMemcpy(c->rg_lib.p, lib.data(), lib.size() * 2, cudaMemcpyHostToDevice));
+    c->n_rg = n;
+    c->unknown_lib = unknown_lib_id;
+    c->n_libs = n_libs;
+    return OGE_OK;
+}
+
+int oge_gpu_dedup_push(oge_gpu_dedup_ctx *c, const uint8_t *records, uint64_t nbytes, const uint64_t *offsets, uint64_t nrec) {
+    if (!c || (nrec && (!records || !offsets))) return fail_msg(OGE_ERR_INVALID_ARG, "push: null argument");
+    if (nrec == 0) return OGE_OK;
+    if (offsets[0] != 0 || offsets[nrec] != nbytes) return fail_msg(OGE_ERR_BAD_RECORD, "push: offsets[0] must be 0 and offsets[nrec] == nbytes");
+    if (c->n + nrec >= (1ull << 30)) return fail_msg(OGE_ERR_TOO_LARGE, "push: more than 2^30-1 records in one context");
+    OGE_CUDA_TRY(cudaSetDevice(c->cfg.device));
+    int rc;
+    // growing moves the resident data: drain the copy stream first
+    if (c->rec_bytes + nbytes > c->rec.cap || c->n + nrec + 1 > c->off.cap) OGE_CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+    if ((rc = c->rec.reserve(c->rec_bytes + nbytes, true, c->copy_stream))) return rc;
+    if ((rc = c->off.reserve(c->n + nrec + 1, true, c->copy_stream))) return rc;
+    OGE_CUDA_TRY(cudaMemcpyAsync(c->rec.p + c->rec_bytes, records, nbytes, cudaMemcpyHostToDevice, c->copy_stream));
+    OGE_CUDA_TRY(cudaMemcpyAsync(c->off.p + c->n, offsets, (nrec + 1) * 8, cudaMemcpyHostToDevice, c->copy_stream));
+    if (c->rec_bytes) {
+        uint64_t cnt = nrec + 1;
+        offsets_rebase<<<(uint32_t) ((cnt + 255) / 256), 256, 0, c->copy_stream>>>(c->off.p + c->n, cnt, c->rec_bytes);
+        OGE_CUDA_TRY(cudaGetLastError());
+    }
+    c->rec_bytes += nbytes;
+    c->n += nrec;
+    c->ran = false;
+    return OGE_OK;
+}
+
+int oge_gpu_dedup_sync(oge_gpu_dedup_ctx *c) {
+    if (!c) return fail_msg(OGE_ERR_INVALID_ARG, "sync: null context");
+    OGE_CUDA_TRY(cudaSetDevice(c->cfg.device));
+    OGE_CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+    OGE_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return OGE_OK;
+}
+
+int oge_gpu_dedup_reset(oge_gpu_dedup_ctx *c) {
+    if (!c) return fail_msg(OGE_ERR_INVALID_ARG, "reset: null context");
+    int rc = oge_gpu_dedup_sync(c);
+    if (rc) return rc;
+    c->n = 0;
+    c->rec_bytes = 0;
+    c->ran = false;
+    return OGE_OK;
+}
+
+int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
+    if (!c) return fail_msg(OGE_ERR_INVALID_ARG, "run: null context");
+    OGE_CUDA_TRY(cudaSetDevice(c->cfg.device));
+    cudaStream_t s = c->stream;
+    memset(&c->stats, 0, sizeof(c->stats));
+    c->stats.n_records = c->n;
+    if (c->n == 0) {
+        c->ran = true;
+        return OGE_OK;
+    }
+    int rc;
+    if ((rc = compute_layout(c, &c->kl))) return rc;
+    if ((rc = ensure_work(c))) return rc;
+    const uint64_t n = c->n;
+    uint64_t launches = 0;
+
+    // the pushes ran on the copy stream
+    OGE_CUDA_TRY(cudaEventRecord(c->copy_done, c->copy_stream));
+    OGE_CUDA_TRY(cudaStreamWaitEvent(s, c->copy_done, 0));
+
+    OGE_CUDA_TRY(cudaEventRecord(c->ev[0], s));
+    OGE_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, CNT_N * 4, s));
+    OGE_CUDA_TRY(cudaMemsetAsync(c->dup.p, 0, n, s));
+
+    // ---- K1 end-build
+    EndbuildParams eb;
+    eb.rec = c->rec.p; eb.off = c->off.p; eb.n = n; eb.idx_base = c->cfg.index_base;
+    eb.frag = c->frag.p; eb.hk = c->hk.p; eb.rgcode = c->rgcode.p; eb.flag_in = c->flag_in.p;
+    eb.counters = c->counters.p; eb.rg = rg_table(c); eb.kl = c->kl;
+    if ((rc = launch_endbuild(eb, (uint32_t) (c->rec_bytes / n), c->sms, s, &launches))) return rc;
+    OGE_CUDA_TRY(cudaEventRecord(c->ev[1], s));
+    OGE_CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, s));
+    OGE_CUDA_TRY(cudaStreamSynchronize(s));
+    if (c->h_counters[CNT_ERR] & DEV_ERR_BAD_RECORD)
+        return fail_msg(OGE_ERR_BAD_RECORD, "run: malformed record (block_size disagrees with offsets, or sections overrun the record)");
+    if (c->h_counters[CNT_ERR] & DEV_ERR_KEY_RANGE)
+        return fail_msg(OGE_ERR_KEY_RANGE, "run: a record's refID / unclipped coordinate / library does not fit the key layout "
+                                           "(n_ref=%d max_ref_len=%d clip_margin=%d)", c->cfg.n_ref, c->cfg.max_ref_len, c->cfg.clip_margin);
+    const uint64_t n_frag = c->h_counters[CNT_FRAG], n_pe = c->h_counters[CNT_PAIR_ELIGIBLE];
+
+    // ---- K2 mate join
+    uint64_t n_pairs = 0, n_cplx = 0;
+    if (n_pe) {
+        uint64_t n_slots = n_pe + n_pe / 2 + 1024;
+        if ((rc = c->table.reserve(n_slots, false, s))) return rc;
+        if ((rc = c->pair.reserve(n_pe / 2 + 1, false, s))) return rc;
+        if ((rc = c->pair2.reserve(n_pe / 2 + 1, false, s))) return rc;
+        OGE_CUDA_TRY(cudaMemsetAsync(c->table.p, 0, n_slots * sizeof(MateSlot), s));
+        JoinParams jp;
+        jp.rec = c->rec.p; jp.off = c->off.p; jp.n = n; jp.idx_base = c->cfg.index_base;
+        jp.frag = c->frag.p; jp.hk = c->hk.p; jp.rgcode = c->rgcode.p;
+        jp.table = c->table.p; jp.n_slots = n_slots;
+        jp.pair = c->pair.p; jp.mate_of = c->mate_of.p; jp.cplx = c->sortbuf.p;
+        jp.counters = c->counters.p; jp.rg = rg_table(c); jp.kl = c->kl; jp.verify_names = c->cfg.verify_names;
+        if ((rc = launch_mate_insert(jp, s, &launches))) return rc;
+        if ((rc = launch_mate_resolve(jp, s, &launches))) return rc;
+        OGE_CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, s));
+        OGE_CUDA_TRY(cudaStreamSynchronize(s));
+        n_cplx = c->h_counters[CNT_COMPLEX];
+        if (n_cplx) {
+            // exact path: sort (hash, ordinal), replay the toggle map per hash value.  The mate
+            // table is dead by now and is at least as large as the list: it is the ping-pong buffer.
+            E128 *sorted = nullptr;
+            if ((rc = radix_sort_128(c->sortbuf.p, reinterpret_cast<E128 *>(c->table.p), n_cplx, nullptr, 0, 96, c->scratch.p, s,
+                                     &sorted, &launches)))
+                return rc;
+            if ((rc = c->cplx_state.reserve(n_cplx, false, s))) return rc;
+            if ((rc = launch_mate_complex(jp, sorted, (uint32_t) n_cplx, c->cplx_state.p, s, &launches))) return rc;
+            OGE_CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, s));
+            OGE_CUDA_TRY(cudaStreamSynchronize(s));
+        }
+        n_pairs = c->h_counters[CNT_PAIRS];
+    }
+    OGE_CUDA_TRY(cudaEventRecord(c->ev[2], s));
+
+    // ---- K3 + K4 on the pairs
+    SelectParams sp;
+    sp.dup = c->dup.p; sp.mate_of = c->mate_of.p; sp.idx_base = c->cfg.index_base; sp.n_records = n;
+    sp.counters = c->counters.p; sp.kl = c->kl; sp.n_dev = nullptr;
+    E128 *sorted_pairs = c->pair.p;
+    if (n_pairs) {
+        if ((rc = radix_sort_128(c->pair.p, c->pair2.p, n_pairs, nullptr, c->kl.p_coord2, c->kl.p_end, c->scratch.p, s, &sorted_pairs,
+                                 &launches)))
+            return rc;
+    }
+    OGE_CUDA_TRY(cudaEventRecord(c->ev[3], s));
+    if (n_pairs) {
+        sp.sorted = sorted_pairs; sp.n_max = (uint32_t) n_pairs;
+        if ((rc = launch_select_pairs(sp, s, &launches))) return rc;
+    }
+    OGE_CUDA_TRY(cudaEventRecord(c->ev[4], s));
+
+    // ---- K3 + K4 on the fragments (ineligible records carry the all-ones key and sort last)
+    E128 *sorted_frags = c->frag.p;
+    if (n_frag) {
+        if ((rc = radix_sort_128(c->frag.p, c->sortbuf.p, n, nullptr, c->kl.f_orient, c->kl.f_end, c->scratch.p, s, &sorted_frags,
+                                 &launches)))
+            return rc;
+    }
+    OGE_CUDA_TRY(cudaEventRecord(c->ev[5], s));
+    if (n_frag) {
+        sp.sorted = sorted_frags; sp.n_max = (uint32_t) n_frag;
+        if ((rc = launch_select_frags(sp, s, &launches))) return rc;
+    }
+    OGE_CUDA_TRY(cudaEventRecord(c->ev[6], s));
+
+    // ---- K5 flag write
+    FlagParams fp;
+    fp.rec = c->rec.p; fp.off = c->off.p; fp.n = n; fp.flag_in = c->flag_in.p; fp.flag_out = c->flag_out.p;
+    fp.dup = c->dup.p; fp.counters = c->counters.p; fp.quiet_index_bug = c->cfg.compat_quiet_index_bug;
+    if ((rc = launch_flags(fp, s, &launches))) return rc;
+    OGE_CUDA_TRY(cudaEventRecord(c->ev[7], s));
+    OGE_CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, s));
+    OGE_CUDA_TRY(cudaStreamSynchronize(s));
+    // the fragment sort moved the end entries: keep them findable for debug_ends
+    if (c->cfg.debug_keep_ends && sorted_frags != c->frag.p && n_frag)
+        OGE_CUDA_TRY(cudaMemcpy(c->frag.p, sorted_frags, n * sizeof(E128), cudaMemcpyDeviceToDevice));
+
+    oge_gpu_dedup_stats &st = c->stats;
+    st.n_frag_entries = n_frag;
+    st.n_pair_entries = n_pairs;
+    st.n_duplicates = c->h_counters[CNT_DUPS];
+    st.n_complex_names = n_cplx;
+    st.n_hash_mismatch = c->h_counters[CNT_HASH_MISMATCH];
+    st.frag_key_bits = c->kl.f_end - c->kl.f_orient;
+    st.pair_key_bits = c->kl.p_end - c->kl.p_coord2;
+    st.frag_sort_passes = make_sort_plan(c->kl.f_orient, c->kl.f_end).n_pass;
+    st.pair_sort_passes = make_sort_plan(c->kl.p_coord2, c->kl.p_end).n_pass;
+    st.ms_total = ms_between(c->ev[0], c->ev[7]);
+    st.ms_endbuild = ms_between(c->ev[0], c->ev[1]);
+    st.ms_join = ms_between(c->ev[1], c->ev[2]);
+    st.ms_sort_pair = ms_between(c->ev[2], c->ev[3]);
+    st.ms_sort_frag = ms_between(c->ev[4], c->ev[5]);
+    st.ms_select = ms_between(c->ev[3], c->ev[4]) + ms_between(c->ev[5], c->ev[6]);
+    st.ms_flags = ms_between(c->ev[6], c->ev[7]);
+    st.launches = launches;
+    c->ran = true;
+    return OGE_OK;
+}
+
+int oge_gpu_dedup_flags(oge_gpu_dedup_ctx *c, uint16_t *out, uint64_t n) {
+    if (!c || (n && !out)) return fail_msg(OGE_ERR_INVALID_ARG, "flags: null argument");
+    if (!c->ran) return fail_msg(OGE_ERR_STATE, "flags: call oge_gpu_dedup_run first");
+    if (n != c->n) return fail_msg(OGE_ERR_INVALID_ARG, "flags: n=%llu but the context holds %llu records", (unsigned long long) n, (unsigned long long) c->n);
+    if (n == 0) return OGE_OK;
+    OGE_CUDA_TRY(cudaSetDevice(c->cfg.device));
+    OGE_CUDA_TRY(cudaMemcpyAsync(out, c->flag_out.p, n * 2, cudaMemcpyDeviceToHost, c->stream));
+    OGE_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return OGE_OK;
+}
+
+int oge_gpu_dedup_pull(oge_gpu_dedup_ctx *c, uint8_t *out_records, uint64_t cap_bytes, uint64_t *out_offsets, uint64_t cap_records,
+                       uint64_t *out_bytes, uint64_t *out_nrec) {
+    if (!c || !out_bytes || !out_nrec) return fail_msg(OGE_ERR_INVALID_ARG, "pull: null argument");
+    if (!c->ran) return fail_msg(OGE_ERR_STATE, "pull: call oge_gpu_dedup_run first");
+    OGE_CUDA_TRY(cudaSetDevice(c->cfg.device));
+    cudaStream_t s = c->stream;
+    *out_bytes = 0;
+    *out_nrec = 0;
+    if (c->n == 0) {
+        if (out_offsets && cap_records >= 1) out_offsets[0] = 0;
+        return OGE_OK;
+    }
+    if (!c->cfg.remove_duplicates) {
+        if (cap_bytes < c->rec_bytes || !out_records) return fail_msg(OGE_ERR_INVALID_ARG, "pull: need %llu bytes", (unsigned long long) c->rec_bytes);
+        if (out_offsets && cap_records < c->n + 1) return fail_msg(OGE_ERR_INVALID_ARG, "pull: need %llu offsets", (unsigned long long) c->n + 1);
+        OGE_CUDA_TRY(cudaMemcpyAsync(out_records, c->rec.p, c->rec_bytes, cudaMemcpyDeviceToHost, s));
+        if (out_offsets) OGE_CUDA_TRY(cudaMemcpyAsync(out_offsets, c->off.p, (c->n + 1) * 8, cudaMemcpyDeviceToHost, s));
+        OGE_CUDA_TRY(cudaStreamSynchronize(s));
+        *out_bytes = c->rec_bytes;
+        *out_nrec = c->n;
+        return OGE_OK;
+    }
+    // -r: drop what is flagged after the rewrite (:456-458), compact in order
+    DevBuf<uint8_t> tmp_rec;
+    DevBuf<uint64_t> tmp_off;
+    int rc;
+    uint64_t launches = 0;
+    if ((rc = tmp_rec.reserve(c->rec_bytes, false, s))) return rc;
+    if ((rc = tmp_off.reserve(c->n + 1, false, s))) { tmp_rec.release(); return rc; }
+    rc = launch_compact(c->rec.p, c->off.p, c->n, c->flag_out.p, 1, tmp_rec.p, tmp_off.p, reinterpret_cast<uint64_t *>(c->scratch.p),
+                        c->counters.p, s, &launches);
+    uint64_t totals[2] = {0, 0};
+    if (!rc && cudaMemcpyAsync(totals, c->scratch.p, 16, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = fail_cuda(cudaGetLastError(), "pull totals", __FILE__, __LINE__);
+    if (!rc && cudaStreamSynchronize(s) != cudaSuccess) rc = fail_cuda(cudaGetLastError(), "pull sync", __FILE__, __LINE__);
+    if (!rc && (totals[1] > cap_bytes || (totals[1] && !out_records))) rc = fail_msg(OGE_ERR_INVALID_ARG, "pull: need %llu bytes", (unsigned long long) totals[1]);
+    if (!rc && out_offsets && cap_records < totals[0] + 1) rc = fail_msg(OGE_ERR_INVALID_ARG, "pull: need %llu offsets", (unsigned long long) totals[0] + 1);
+    if (!rc && totals[1] && cudaMemcpyAsync(out_records, tmp_rec.p, totals[1], cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = fail_cuda(cudaGetLastError(), "pull copy", __FILE__, __LINE__);
+    if (!rc && out_offsets && cudaMemcpyAsync(out_offsets, tmp_off.p, (totals[0] + 1) * 8, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = fail_cuda(cudaGetLastError(), "pull copy", __FILE__, __LINE__);
+    if (!rc && cudaStreamSynchronize(s) != cudaSuccess) rc = fail_cuda(cudaGetLastError(), "pull sync", __FILE__, __LINE__);
+    tmp_rec.release();
+    tmp_off.release();
+    if (rc) return rc;
+    *out_bytes = totals[1];
+    *out_nrec = totals[0];
+    return OGE_OK;
+}
+
+int oge_gpu_dedup_get_stats(oge_gpu_dedup_ctx *c, oge_gpu_dedup_stats *out) {
+    if (!c || !out) return fail_msg(OGE_ERR_INVALID_ARG, "get_stats: null argument");
+    *out = c->stats;
+    return OGE_OK;
+}
+
+int oge_gpu_dedup_debug_ends(oge_gpu_dedup_ctx *c, oge_gpu_end *out, uint64_t n) {
+    if (!c || (n && !out)) return fail_msg(OGE_ERR_INVALID_ARG, "debug_ends: null argument");
+    if (!c->ran || !c->cfg.debug_keep_ends) return fail_msg(OGE_ERR_STATE, "debug_ends: needs debug_keep_ends and a completed run");
+    if (n != c->n) return fail_msg(OGE_ERR_INVALID_ARG, "debug_ends: n mismatch");
+    if (n == 0) return OGE_OK;
+    OGE_CUDA_TRY(cudaSetDevice(c->cfg.device));
+    std::vector<E128> ents(n);
+    std::vector<uint64_t> hk(n);
+    OGE_CUDA_TRY(cudaMemcpy(ents.data(), c->frag.p, n * sizeof(E128), cudaMemcpyDeviceToHost));
+    OGE_CUDA_TRY(cudaMemcpy(hk.data(), c->hk.p, n * 8, cudaMemcpyDeviceToHost));
+    const KeyLayout &L = c->kl;
+    memset(out, 0, n * sizeof(oge_gpu_end));
+    for (uint64_t j = 0; j < n; j++) {      // entries are in sorted order: place each by its ordinal
+        const E128 &e = ents[j];
+        if (bits_get(e, L.f_lib, L.lib_bits) == L.lib_invalid) continue;
+        uint64_t i = bits_get(e, L.f_idx, L.idx_bits) - c->cfg.index_base;
+        if (i >= n) return fail_msg(OGE_ERR_STATE, "debug_ends: corrupt entry");
+        oge_gpu_end &o = out[i];
+        o.eligible = 1;
+        o.pair_eligible = hk[i] != 0;
+        o.ref = (int32_t) bits_get(e, L.f_ref, L.ref_bits);
+        o.coord = (int32_t) ((int64_t) bits_get(e, L.f_coord, L.coord_bits) - L.coord_bias);
+        o.orientation = bits_get(e, L.f_orient, 1) ? 2 : 1;
+        o.read2Sequence = bits_get(e, L.f_paired, 1) ? 0 : -1;
+        o.score = (int16_t) (uint16_t) (e.lo & 0xFFFF);
+        o.lib = (int16_t) bits_get(e, L.f_lib, L.lib_bits);
+    }
+    return OGE_OK;
+}
+
+int oge_gpu_debug_sort128(int device, void *entries, uint64_t n, int bit_lo, int bit_hi) {
+    if ((n && !entries) || bit_lo < 0 || bit_hi > 128 || bit_lo > bit_hi) return fail_msg(OGE_ERR_INVALID_ARG, "debug_sort128: bad argument");
+    if (oge_gpu_device_count() <= 0) return fail_msg(OGE_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    if (n == 0) return OGE_OK;
+    OGE_CUDA_TRY(cudaSetDevice(device));
+    int rc = radix_sort_init();
+    if (rc) return rc;
+    DevBuf<E128> a, b;
+    DevBuf<uint8_t> scratch;
+    uint64_t launches = 0;
+    E128 *res = nullptr;
+    rc = a.reserve(n, false, 0);
+    if (!rc) rc = b.reserve(n, false, 0);
+    if (!rc) rc = scratch.reserve(sort_scratch_bytes(n), false, 0);
+    if (!rc && cudaMemcpy(a.p, entries, n * sizeof(E128), cudaMemcpyHostToDevice) != cudaSuccess) rc = fail_cuda(cudaGetLastError(), "sort h2d", __FILE__, __LINE__);
+    if (!rc) rc = radix_sort_128(a.p, b.p, n, nullptr, bit_lo, bit_hi, scratch.p, 0, &res, &launches);
+    if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = fail_cuda(cudaGetLastError(), "sort sync", __FILE__, __LINE__);
+    if (!rc && cudaMemcpy(entries, res, n * sizeof(E128), cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail_cuda(cudaGetLastError(), "sort d2h", __FILE__, __LINE__);
+    a.release(); b.release(); scratch.release();
+    return rc;
+}
+
+int oge_gpu_dedup_device_ptrs(oge_gpu_dedup_ctx *c, void **records, void **offsets, void **flags) {
+    if (!c) return fail_msg(OGE_ERR_INVALID_ARG, "device_ptrs: null context");
+    if (records) *records = c->rec.p;
+    if (offsets) *offsets = c->off.p;
+    if (flags) *flags = c->flag_out.p;
+    return OGE_OK;
+}
+
+}  // extern "C"

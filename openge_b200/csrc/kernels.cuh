@@ -1,0 +1,108 @@
+// Kernel parameter blocks and launchers of the dedup path (one .cu per stage).
+#pragma once
+#include "common.cuh"
+
+namespace oge {
+
+// ---- K1 end-build (endbuild.cu) ---------------------------------------------------------------
+constexpr int EB_THREADS = 128;     // records per tile = threads per CTA
+constexpr int EB_STAGES = 2;
+static_assert(EB_STAGES >= 2, "stage metadata is only ordered by the next iteration's barrier");
+
+constexpr uint32_t RGC_UNKNOWN = 0xFFFEu;   // RG value not listed in the header
+constexpr uint32_t RGC_ABSENT = 0xFFFFu;    // no RG tag, or an empty value
+
+// Host-resolved @RG table (reference: util/bam_header.h:214-241 lookups done per record by
+// mark_duplicates.cpp:282-318): ids concatenated in `bytes`, id i = bytes[off[i], off[i+1]).
+struct RgTable {
+    const uint8_t *bytes;
+    const uint32_t *off;
+    const int16_t *lib;
+    int n;
+    int16_t unknown_lib;
+};
+
+struct EndbuildParams {
+    const uint8_t *rec;
+    const uint64_t *off;
+    uint64_t n;
+    uint64_t idx_base;      // global ordinal of record 0 (multi-GPU shards)
+    E128 *frag;
+    uint64_t *hk;
+    uint16_t *rgcode;
+    uint16_t *flag_in;
+    uint32_t *counters;
+    RgTable rg;
+    KeyLayout kl;
+};
+
+int launch_endbuild(const EndbuildParams &P, uint32_t avg_rec_bytes, int sms, cudaStream_t stream, uint64_t *launches);
+
+// ---- K2 mate join (join.cu) -------------------------------------------------------------------
+struct __align__(16) MateSlot {
+    uint64_t key;       // 64-bit hash of RG + ":" + name; 0 = empty
+    uint64_t val;       // (arrivals << 32) + sum of the arrivals' record ordinals
+};
+
+struct JoinParams {
+    const uint8_t *rec;
+    const uint64_t *off;
+    uint64_t n;
+    uint64_t idx_base;
+    const E128 *frag;
+    const uint64_t *hk;
+    const uint16_t *rgcode;
+    MateSlot *table;
+    uint64_t n_slots;
+    E128 *pair;             // output pair entries (appended; counters[CNT_PAIRS])
+    uint32_t *mate_of;      // [n] local ordinal of the pair's other record, for idx1's record
+    E128 *cplx;             // output: (hash << idx_bits | local ordinal) of records for the slow path
+    uint32_t *counters;
+    RgTable rg;
+    KeyLayout kl;
+    int verify_names;
+};
+
+int launch_mate_insert(const JoinParams &P, cudaStream_t stream, uint64_t *launches);
+int launch_mate_resolve(const JoinParams &P, cudaStream_t stream, uint64_t *launches);
+// exact path over the sorted complex list (sorted by hash then ordinal); state = n_cplx bytes of scratch
+int launch_mate_complex(const JoinParams &P, const E128 *sorted_cplx, uint32_t n_cplx, uint8_t *state, cudaStream_t stream,
+                        uint64_t *launches);
+
+// ---- K4 group-and-select (select.cu) ----------------------------------------------------------
+struct SelectParams {
+    const E128 *sorted;
+    uint32_t n_max;
+    const uint32_t *n_dev;      // device count (pairs) or nullptr
+    uint8_t *dup;               // [n records] duplicate set, indexed by local ordinal
+    const uint32_t *mate_of;
+    uint64_t idx_base;
+    uint64_t n_records;
+    uint32_t *counters;
+    KeyLayout kl;
+};
+
+int launch_select_pairs(const SelectParams &P, cudaStream_t stream, uint64_t *launches);
+int launch_select_frags(const SelectParams &P, cudaStream_t stream, uint64_t *launches);
+
+// ---- K5 flag write (flags.cu) -----------------------------------------------------------------
+struct FlagParams {
+    uint8_t *rec;
+    const uint64_t *off;
+    uint64_t n;
+    const uint16_t *flag_in;
+    uint16_t *flag_out;
+    const uint8_t *dup;
+    uint32_t *counters;
+    int quiet_index_bug;        // compat F1: the duplicate set collapses to {0}
+};
+
+int launch_flags(const FlagParams &P, cudaStream_t stream, uint64_t *launches);
+
+// pull with remove_duplicates: compaction of the kept records
+int launch_compact(const uint8_t *rec, const uint64_t *off, uint64_t n, const uint16_t *flag_out, int remove_dups,
+                   uint8_t *out_rec, uint64_t *out_off, uint64_t *scratch /* n+1 + blocks */, uint32_t *counters,
+                   cudaStream_t stream, uint64_t *launches);
+size_t compact_scratch_bytes(uint64_t n);
+
+}  // namespace oge

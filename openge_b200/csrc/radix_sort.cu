@@ -1,0 +1,291 @@
+// K3: LSD "onesweep" radix sort of 16-byte end entries, sm_100a.
+//
+// Replaces ogeSortMt(..., compareReadEnds()) (reference util/thread_pool.h:359-397,
+// algorithms/mark_duplicates.cpp:262-271).  The comparison order of ReadEnds::compare
+// (util/picard_structures.h:56-68) is not reproduced -- only the grouping of equal keys is
+// needed downstream, and the survivor choice is order-independent (select.cu).
+//
+// Structure (one read of the input for all histograms, then one read + one write per pass):
+//   rs_histogram      every pass's 256-bin digit histogram in one sweep (shared-memory bins)
+//   rs_scan           exclusive scan of each histogram -> global digit offsets
+//   rs_onesweep_pass  per 4096-entry tile: 128-bit coalesced loads, warp-private digit counters
+//                     ranked with match.any, chained-scan (decoupled look-back) across tiles,
+//                     reorder through shared memory, coalesced 128-bit stores
+// The sort is stable per pass (warp-striped tile order + tile-ordered look-back), which LSD needs.
+// HBM-bound integer work: no tensor cores.  Algorithmic bytes per entry: 16 (histogram) +
+// 32 per pass.
+#include "radix_sort.cuh"
+
+namespace oge {
+
+constexpr uint32_t LB_FLAG_AGG = 1u << 30;      // tile aggregate published
+constexpr uint32_t LB_FLAG_INC = 2u << 30;      // inclusive prefix published
+constexpr uint32_t LB_VALUE_MASK = (1u << 30) - 1;
+
+SortPlan make_sort_plan(int bit_lo, int bit_hi) {
+    SortPlan p;
+    p.n_pass = 0;
+    for (int s = bit_lo; s < bit_hi && p.n_pass < RS_MAX_PASSES; s += RS_RADIX_BITS) {
+        p.shift[p.n_pass] = s;
+        p.bits[p.n_pass] = (bit_hi - s) < RS_RADIX_BITS ? (bit_hi - s) : RS_RADIX_BITS;
+        p.n_pass++;
+    }
+    return p;
+}
+
+static inline uint64_t tiles_of(uint64_t n) { return (n + RS_TILE - 1) / RS_TILE; }
+
+// scratch: [hist: MAXP*256 u32][offsets: MAXP*256 u32][tile counters: MAXP u32 (+pad)][status: tiles*256 u32]
+size_t sort_scratch_bytes(uint64_t n) {
+    return (size_t) (2 * RS_MAX_PASSES * RS_RADIX + 64) * 4 + (size_t) tiles_of(n) * RS_RADIX * 4;
+}
+
+__device__ __forceinline__ E128 ld_entry(const E128 *p) {
+    ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(p));
+    E128 e;
+    e.lo = v.x;
+    e.hi = v.y;
+    return e;
+}
+
+__device__ __forceinline__ void st_entry(E128 *p, const E128 &e) {
+    *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(e.lo, e.hi);
+}
+
+// ------------------------------------------------------------------------------------------------
+// All digit histograms in one read of the entries.
+constexpr int HIST_THREADS = 512;
+constexpr int HIST_UNROLL = 4;
+
+__global__ void __launch_bounds__(HIST_THREADS) rs_histogram(const E128 *__restrict__ in, uint32_t n_max,
+                                                              const uint32_t *__restrict__ n_dev, SortPlan plan,
+                                                              uint32_t *__restrict__ ghist) {
+    __shared__ uint32_t sh[RS_MAX_PASSES * RS_RADIX];
+    const uint32_t n = n_dev ? min(*n_dev, n_max) : n_max;
+    for (int i = threadIdx.x; i < plan.n_pass * RS_RADIX; i += HIST_THREADS) sh[i] = 0;
+    __syncthreads();
+
+    const uint32_t chunk = HIST_THREADS * HIST_UNROLL;
+    const uint32_t n_chunks = (n + chunk - 1) / chunk;
+    for (uint32_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        E128 e[HIST_UNROLL];
+        bool ok[HIST_UNROLL];
+#pragma unroll
+        for (int k = 0; k < HIST_UNROLL; k++) {
+            uint32_t i = c * chunk + k * HIST_THREADS + threadIdx.x;
+            ok[k] = i < n;
+            if (ok[k]) e[k] = ld_entry(in + i);
+        }
+#pragma unroll
+        for (int k = 0; k < HIST_UNROLL; k++) {
+            for (int p = 0; p < plan.n_pass; p++) {
+                uint32_t d = ok[k] ? digit_of(e[k], plan.shift[p], (1u << plan.bits[p]) - 1) : 0xFFFFFFFFu;
+                // coordinate-sorted input makes the high digits warp-uniform: one add per warp then
+                int uniform;
+                __match_all_sync(0xFFFFFFFFu, d, &uniform);
+                if (uniform) {
+                    if ((threadIdx.x & 31) == 0 && ok[k]) atomicAdd(&sh[p * RS_RADIX + d], 32u);
+                } else if (ok[k]) {
+                    atomicAdd(&sh[p * RS_RADIX + d], 1u);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < plan.n_pass * RS_RADIX; i += HIST_THREADS) {
+        uint32_t v = sh[i];
+        if (v) atomicAdd(&ghist[i], v);
+    }
+}
+
+// One CTA of 256 threads per pass: exclusive scan of the 256 bins.
+__global__ void __launch_bounds__(RS_RADIX) rs_scan(const uint32_t *__restrict__ ghist, uint32_t *__restrict__ goff) {
+    __shared__ uint32_t wsum[RS_RADIX / 32];
+    const int p = blockIdx.x, d = threadIdx.x, lane = d & 31, w = d >> 5;
+    uint32_t v = ghist[p * RS_RADIX + d], x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[w] = x;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int i = 0; i < w; i++) base += wsum[i];
+    goff[p * RS_RADIX + d] = base + x - v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One scatter pass.  Dynamic shared memory: [sorted: RS_TILE * 16 B][warp counters: RS_WARPS * 256 * 4 B]
+constexpr size_t PASS_SMEM = (size_t) RS_TILE * sizeof(E128) + (size_t) RS_WARPS * RS_RADIX * 4;
+
+__global__ void __launch_bounds__(RS_THREADS, 2)
+rs_onesweep_pass(const E128 *__restrict__ in, E128 *__restrict__ out, uint32_t n_max, const uint32_t *__restrict__ n_dev,
+                 int shift, int bits, const uint32_t *__restrict__ digit_offset, uint32_t *__restrict__ status,
+                 uint32_t *__restrict__ tile_counter) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    E128 *s_sorted = reinterpret_cast<E128 *>(smem_raw);
+    uint32_t *s_warp_cnt = reinterpret_cast<uint32_t *>(smem_raw + (size_t) RS_TILE * sizeof(E128));
+    __shared__ uint32_t s_tile_base[RS_RADIX];
+    __shared__ long long s_delta[RS_RADIX];
+    __shared__ uint32_t s_scan[RS_WARPS];
+    __shared__ uint32_t s_tile;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n = n_dev ? min(*n_dev, n_max) : n_max;
+    const uint32_t n_tiles = (n + RS_TILE - 1) / RS_TILE;
+    const uint32_t mask = (1u << bits) - 1;
+
+    // tile ids are handed out in launch order so that every predecessor of a tile is already
+    // running (or done): the look-back below can never wait on a CTA that has not started
+    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+    for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) s_warp_cnt[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if (tile >= n_tiles) return;
+    const uint32_t base = tile * RS_TILE;
+
+    // ---- load: warp-striped, 16 B per lane, 512 B contiguous per warp instruction
+    E128 e[RS_ITEMS];
+    const uint32_t wbase = base + warp * (32 * RS_ITEMS) + lane;
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; k++) {
+        uint32_t i = wbase + k * 32;
+        if (i < n) e[k] = ld_entry(in + i);
+    }
+
+    // ---- rank inside the warp: match.any groups equal digits; the group's highest lane owns the
+    //      warp-private counter update, so no atomics are needed
+    uint32_t rank[RS_ITEMS];
+    uint32_t *wc = s_warp_cnt + warp * RS_RADIX;
+    const uint32_t lt_mask = (1u << lane) - 1;
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; k++) {
+        uint32_t d = (wbase + k * 32 < n) ? digit_of(e[k], shift, mask) : 0xFFFFFFFFu;
+        uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+        int leader = 31 - __clz(peers);
+        uint32_t old = 0;
+        if (lane == leader && d != 0xFFFFFFFFu) {
+            old = wc[d];
+            wc[d] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xFFFFFFFFu, old, leader);
+        rank[k] = old + __popc(peers & lt_mask);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- per digit: exclusive scan over warps, tile total, publish, block scan, look-back
+    uint32_t total = 0;
+    if (tid < RS_RADIX) {
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) {
+            uint32_t c = s_warp_cnt[w * RS_RADIX + tid];
+            s_warp_cnt[w * RS_RADIX + tid] = total;
+            total += c;
+        }
+        uint32_t word = (tile == 0 ? LB_FLAG_INC : LB_FLAG_AGG) | total;
+        asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(status + (size_t) tile * RS_RADIX + tid), "r"(word) : "memory");
+    }
+    // block-wide exclusive scan of `total` over the 256 digit threads (other threads carry 0)
+    uint32_t x = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_scan[warp] = x;
+    __syncthreads();
+    if (tid < RS_RADIX) {
+        uint32_t wprefix = 0;
+        for (int i = 0; i < warp; i++) wprefix += s_scan[i];
+        uint32_t tile_base = wprefix + x - total;
+
+        uint32_t excl = 0;
+        if (tile > 0) {
+            const uint32_t *sp = status + (size_t) (tile - 1) * RS_RADIX + tid;
+            while (true) {
+                uint32_t s;
+                asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(s) : "l"(sp) : "memory");
+                uint32_t f = s >> 30;
+                if (f == 0) continue;
+                excl += s & LB_VALUE_MASK;
+                if (f == 2) break;
+                sp -= RS_RADIX;
+            }
+            uint32_t word = LB_FLAG_INC | (excl + total);
+            asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(status + (size_t) tile * RS_RADIX + tid), "r"(word) : "memory");
+        }
+        s_tile_base[tid] = tile_base;
+        s_delta[tid] = (long long) digit_offset[tid] + (long long) excl - (long long) tile_base;
+    }
+    __syncthreads();
+
+    // ---- reorder through shared memory
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; k++) {
+        if (wbase + k * 32 < n) {
+            uint32_t d = digit_of(e[k], shift, mask);
+            uint32_t pos = s_tile_base[d] + wc[d] + rank[k];
+            st_entry(s_sorted + pos, e[k]);
+        }
+    }
+    __syncthreads();
+
+    // ---- store: consecutive threads write consecutive sorted slots; runs of one digit are
+    //      contiguous in the output
+    const uint32_t count = min((uint32_t) RS_TILE, n - base);
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; k++) {
+        uint32_t j = k * RS_THREADS + tid;
+        if (j < count) {
+            E128 v = s_sorted[j];
+            uint32_t d = digit_of(v, shift, mask);
+            st_entry(out + (long long) j + s_delta[d], v);
+        }
+    }
+}
+
+int radix_sort_init() {
+    OGE_CUDA_TRY(cudaFuncSetAttribute(rs_onesweep_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) PASS_SMEM));
+    return 0;
+}
+
+int radix_sort_128(E128 *a, E128 *b, uint64_t n, const uint32_t *n_dev, int bit_lo, int bit_hi, void *scratch,
+                   cudaStream_t stream, E128 **result, uint64_t *launches) {
+    *result = a;
+    if (n == 0 || bit_hi <= bit_lo) return 0;
+    if (n >= (1ull << 30)) return fail_msg(-6, "radix sort: more than 2^30-1 entries");
+    SortPlan plan = make_sort_plan(bit_lo, bit_hi);
+    uint32_t *hist = (uint32_t *) scratch;
+    uint32_t *goff = hist + RS_MAX_PASSES * RS_RADIX;
+    uint32_t *tile_counters = goff + RS_MAX_PASSES * RS_RADIX;
+    uint32_t *status = tile_counters + 64;
+    const uint64_t tiles = tiles_of(n);
+
+    OGE_CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t) (2 * RS_MAX_PASSES * RS_RADIX + 64) * 4, stream));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    uint64_t chunks = (n + HIST_THREADS * HIST_UNROLL - 1) / (HIST_THREADS * HIST_UNROLL);
+    uint32_t hgrid = (uint32_t) (chunks < (uint64_t) sms * 4 ? chunks : (uint64_t) sms * 4);
+    rs_histogram<<<hgrid, HIST_THREADS, 0, stream>>>(a, (uint32_t) n, n_dev, plan, hist);
+    rs_scan<<<plan.n_pass, RS_RADIX, 0, stream>>>(hist, goff);
+    *launches += 2;
+
+    E128 *src = a, *dst = b;
+    for (int p = 0; p < plan.n_pass; p++) {
+        OGE_CUDA_TRY(cudaMemsetAsync(status, 0, (size_t) tiles * RS_RADIX * 4, stream));
+        rs_onesweep_pass<<<(uint32_t) tiles, RS_THREADS, PASS_SMEM, stream>>>(
+            src, dst, (uint32_t) n, n_dev, plan.shift[p], plan.bits[p], goff + p * RS_RADIX, status, tile_counters + p);
+        *launches += 1;
+        E128 *t = src;
+        src = dst;
+        dst = t;
+    }
+    OGE_CUDA_TRY(cudaGetLastError());
+    *result = src;
+    return 0;
+}
+
+}  // namespace oge

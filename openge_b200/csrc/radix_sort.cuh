@@ -1,0 +1,36 @@
+// LSD onesweep radix sort of 16-byte entries on a bit range (replaces ogeSortMt,
+// reference util/thread_pool.h:359-397, called at algorithms/mark_duplicates.cpp:262-271).
+#pragma once
+#include "common.cuh"
+
+namespace oge {
+
+constexpr int RS_MAX_PASSES = 16;       // 128 key bits / 8
+constexpr int RS_RADIX_BITS = 8;
+constexpr int RS_RADIX = 1 << RS_RADIX_BITS;
+constexpr int RS_THREADS = 512;
+constexpr int RS_ITEMS = 8;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;      // 4096 entries = 64 KB of shared memory
+constexpr int RS_WARPS = RS_THREADS / 32;
+
+struct SortPlan {
+    int n_pass;
+    int shift[RS_MAX_PASSES];
+    int bits[RS_MAX_PASSES];
+};
+
+SortPlan make_sort_plan(int bit_lo, int bit_hi);
+
+// Scratch a sort of up to `n` entries needs (bytes), excluding the ping-pong buffer.
+size_t sort_scratch_bytes(uint64_t n);
+
+// Sorts `n` entries by bits [bit_lo, bit_hi).  `a` holds the input; `b` is a same-sized
+// ping-pong buffer.  Returns the buffer holding the result through *result (a or b).
+// `n_dev`, when not null, is a device word holding the real entry count (<= n); the kernels
+// then ignore the tail, so no host round trip is needed to size the sort.
+int radix_sort_128(E128 *a, E128 *b, uint64_t n, const uint32_t *n_dev, int bit_lo, int bit_hi, void *scratch,
+                   cudaStream_t stream, E128 **result, uint64_t *launches);
+
+int radix_sort_init();   // one-time function attributes
+
+}  // namespace oge

@@ -1,0 +1,273 @@
+"""ctypes binding of libopenge_b200.so (include/oge_gpu_dedup.h) + a MarkDuplicates front-end.
+
+This is host plumbing for tests, the CLI and bench.py; the algorithm runs in the CUDA
+library.  There is no CPU fallback: loading fails loudly when the library is missing, and
+``oge_gpu_dedup_create`` fails when no sm_100 device is present.
+
+``MarkDuplicates`` mirrors the reference's algorithm module
+(/root/reference/openge/src/algorithms/mark_duplicates.h:27-68): constructor takes the temp
+directory (unused here: nothing is spilled), ``removeDuplicates`` is a public attribute, and
+``run(bam)`` does what ``runInternal`` does to the record stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _build, header as _header
+from .bamio import BamFile
+
+ABI_VERSION = 1
+
+OGE_OK = 0
+ERRORS = {-1: "OGE_ERR_INVALID_ARG", -2: "OGE_ERR_CUDA", -3: "OGE_ERR_NOMEM", -4: "OGE_ERR_KEY_RANGE",
+          -5: "OGE_ERR_STATE", -6: "OGE_ERR_TOO_LARGE", -7: "OGE_ERR_BAD_RECORD"}
+
+
+class Config(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("n_ref", C.c_int32), ("max_ref_len", C.c_int32),
+                ("clip_margin", C.c_int32), ("remove_duplicates", C.c_int32), ("verify_names", C.c_int32),
+                ("compat_quiet_index_bug", C.c_int32), ("debug_keep_ends", C.c_int32), ("reserved0", C.c_int32),
+                ("capacity_records", C.c_uint64), ("capacity_bytes", C.c_uint64),
+                ("rank", C.c_int32), ("world", C.c_int32), ("index_base", C.c_uint64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_records", C.c_uint64), ("n_frag_entries", C.c_uint64), ("n_pair_entries", C.c_uint64),
+                ("n_duplicates", C.c_uint64), ("n_complex_names", C.c_uint64), ("n_hash_mismatch", C.c_uint64),
+                ("frag_key_bits", C.c_uint32), ("pair_key_bits", C.c_uint32),
+                ("frag_sort_passes", C.c_uint32), ("pair_sort_passes", C.c_uint32),
+                ("ms_total", C.c_float), ("ms_endbuild", C.c_float), ("ms_join", C.c_float),
+                ("ms_sort_frag", C.c_float), ("ms_sort_pair", C.c_float), ("ms_select", C.c_float),
+                ("ms_flags", C.c_float), ("launches", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+END_DTYPE = np.dtype([("eligible", "<i4"), ("pair_eligible", "<i4"), ("ref", "<i4"), ("coord", "<i4"),
+                      ("orientation", "<i4"), ("read2Sequence", "<i4"), ("score", "<i2"), ("lib", "<i2")])
+
+EXPORTS = ["oge_gpu_dedup_create", "oge_gpu_dedup_destroy", "oge_gpu_dedup_set_readgroups", "oge_gpu_dedup_push",
+           "oge_gpu_dedup_sync", "oge_gpu_dedup_run", "oge_gpu_dedup_flags", "oge_gpu_dedup_pull",
+           "oge_gpu_dedup_reset", "oge_gpu_dedup_get_stats", "oge_gpu_dedup_debug_ends",
+           "oge_gpu_dedup_device_ptrs", "oge_gpu_host_alloc", "oge_gpu_host_free", "oge_gpu_device_count",
+           "oge_gpu_last_error", "oge_gpu_abi_version", "oge_gpu_debug_sort128"]
+
+
+class DedupError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("%s (%d): %s" % (ERRORS.get(code, "error"), code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load (building if a compiler is present and sources are newer) the CUDA library."""
+    global _lib
+    if _lib is None:
+        path = _build.build_gpu()
+        if not os.path.exists(path):
+            raise ImportError("libopenge_b200.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(path)
+        vp, u64 = C.c_void_p, C.c_uint64
+        L.oge_gpu_dedup_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+        L.oge_gpu_dedup_destroy.argtypes = [vp]
+        L.oge_gpu_dedup_destroy.restype = None
+        L.oge_gpu_dedup_set_readgroups.argtypes = [vp, C.POINTER(C.c_char_p), vp, C.c_int32, C.c_int16, C.c_int32]
+        L.oge_gpu_dedup_push.argtypes = [vp, vp, u64, vp, u64]
+        L.oge_gpu_dedup_sync.argtypes = [vp]
+        L.oge_gpu_dedup_run.argtypes = [vp]
+        L.oge_gpu_dedup_flags.argtypes = [vp, vp, u64]
+        L.oge_gpu_dedup_pull.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64), C.POINTER(u64)]
+        L.oge_gpu_dedup_reset.argtypes = [vp]
+        L.oge_gpu_dedup_get_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.oge_gpu_dedup_debug_ends.argtypes = [vp, vp, u64]
+        L.oge_gpu_dedup_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+        L.oge_gpu_host_alloc.argtypes = [C.c_size_t]
+        L.oge_gpu_host_alloc.restype = vp
+        L.oge_gpu_host_free.argtypes = [vp]
+        L.oge_gpu_host_free.restype = None
+        L.oge_gpu_last_error.restype = C.c_char_p
+        L.oge_gpu_debug_sort128.argtypes = [C.c_int, vp, u64, C.c_int, C.c_int]
+        for name in EXPORTS:
+            getattr(L, name)
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != OGE_OK:
+        raise DedupError(rc, lib().oge_gpu_last_error().decode("utf-8", "replace"))
+
+
+def device_count() -> int:
+    return int(lib().oge_gpu_device_count())
+
+
+def debug_sort128(entries: np.ndarray, bit_lo: int, bit_hi: int, device: int = 0) -> np.ndarray:
+    """Test hook: K3 alone.  entries: (n, 2) uint64 (lo, hi); returns the sorted copy."""
+    e = np.ascontiguousarray(entries, dtype=np.uint64).copy()
+    _check(lib().oge_gpu_debug_sort128(device, e.ctypes.data, len(e), bit_lo, bit_hi))
+    return e
+
+
+class PinnedBuffer:
+    """Page-locked host memory from oge_gpu_host_alloc, viewed as a uint8 numpy array."""
+
+    def __init__(self, nbytes: int):
+        self.nbytes = int(nbytes)
+        self.ptr = lib().oge_gpu_host_alloc(max(1, self.nbytes))
+        if not self.ptr:
+            raise MemoryError("oge_gpu_host_alloc(%d) failed" % nbytes)
+        self.array = np.ctypeslib.as_array((C.c_uint8 * max(1, self.nbytes)).from_address(self.ptr))[: self.nbytes]
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().oge_gpu_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DedupContext:
+    """One oge_gpu_dedup_ctx (one MarkDuplicates instance on one GPU)."""
+
+    def __init__(self, n_ref=0, max_ref_len=0, device=0, remove_duplicates=False, verify_names=True,
+                 compat_quiet_index_bug=False, debug_keep_ends=False, clip_margin=0, capacity_records=0,
+                 capacity_bytes=0, index_base=0, rank=0, world=1):
+        self._h = C.c_void_p()
+        cfg = Config(abi_version=ABI_VERSION, device=device, n_ref=n_ref, max_ref_len=max_ref_len, clip_margin=clip_margin,
+                     remove_duplicates=int(remove_duplicates), verify_names=int(verify_names),
+                     compat_quiet_index_bug=int(compat_quiet_index_bug), debug_keep_ends=int(debug_keep_ends),
+                     capacity_records=capacity_records, capacity_bytes=capacity_bytes, rank=rank, world=world,
+                     index_base=index_base)
+        _check(lib().oge_gpu_dedup_create(C.byref(cfg), C.byref(self._h)))
+        self.n = 0
+        self.nbytes = 0
+
+    def close(self):
+        if self._h:
+            lib().oge_gpu_dedup_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_header(self, text: str):
+        """Resolve @RG ID -> LB -> library id on the host (openge_b200.header) and upload the table."""
+        rg_ids, lib_ids, unknown, n_libs = _header.library_table(text)
+        ids = (C.c_char_p * max(1, len(rg_ids)))(*rg_ids)
+        libs = np.asarray(lib_ids if lib_ids else [0], dtype=np.int16)
+        _check(lib().oge_gpu_dedup_set_readgroups(self._h, ids, libs.ctypes.data, len(rg_ids), unknown, n_libs))
+
+    def push(self, records, offsets):
+        """records: uint8 array (or PinnedBuffer.array); offsets: u64 n+1, relative to records[0]."""
+        records = np.ascontiguousarray(records, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        nrec = len(offsets) - 1
+        _check(lib().oge_gpu_dedup_push(self._h, records.ctypes.data, records.nbytes, offsets.ctypes.data, nrec))
+        _check(lib().oge_gpu_dedup_sync(self._h))      # numpy buffers may go away
+        self.n += nrec
+        self.nbytes += records.nbytes
+
+    def push_async(self, records_ptr, nbytes, offsets_ptr, nrec):
+        _check(lib().oge_gpu_dedup_push(self._h, records_ptr, nbytes, offsets_ptr, nrec))
+        self.n += nrec
+        self.nbytes += nbytes
+
+    def sync(self):
+        _check(lib().oge_gpu_dedup_sync(self._h))
+
+    def reset(self):
+        _check(lib().oge_gpu_dedup_reset(self._h))
+        self.n = 0
+        self.nbytes = 0
+
+    def run(self):
+        _check(lib().oge_gpu_dedup_run(self._h))
+
+    def flags(self, out=None) -> np.ndarray:
+        if out is None:
+            out = np.empty(self.n, dtype=np.uint16)
+        _check(lib().oge_gpu_dedup_flags(self._h, out.ctypes.data, self.n))
+        return out
+
+    def pull(self):
+        """-> (records uint8, offsets u64) after the flag rewrite (and -r compaction)."""
+        rec = np.empty(self.nbytes, dtype=np.uint8)
+        off = np.empty(self.n + 1, dtype=np.uint64)
+        nb, nr = C.c_uint64(), C.c_uint64()
+        _check(lib().oge_gpu_dedup_pull(self._h, rec.ctypes.data, rec.nbytes, off.ctypes.data, len(off), C.byref(nb), C.byref(nr)))
+        if nr.value == 0:
+            off[0] = 0
+        return rec[: nb.value], off[: nr.value + 1]
+
+    def stats(self) -> dict:
+        st = Stats()
+        _check(lib().oge_gpu_dedup_get_stats(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def ends(self) -> np.ndarray:
+        out = np.zeros(self.n, dtype=END_DTYPE)
+        _check(lib().oge_gpu_dedup_debug_ends(self._h, out.ctypes.data, self.n))
+        return out
+
+    def device_ptrs(self):
+        r, o, f = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _check(lib().oge_gpu_dedup_device_ptrs(self._h, C.byref(r), C.byref(o), C.byref(f)))
+        return r.value, o.value, f.value
+
+
+def context_for(bam: BamFile, **kw) -> DedupContext:
+    """A context whose key layout is sized from the BAM's reference dictionary."""
+    max_len = max([l for _, l in bam.refs], default=0)
+    ctx = DedupContext(n_ref=len(bam.refs), max_ref_len=max_len, **kw)
+    ctx.set_header(bam.text)
+    return ctx
+
+
+class MarkDuplicates:
+    """Drop-in for the reference's MarkDuplicates module (mark_duplicates.h:27-68) over whole BamFiles."""
+
+    def __init__(self, temp_directory: str = "/tmp", device: int = 0):
+        self.temp_directory = temp_directory      # kept for signature parity; nothing is spilled
+        self.removeDuplicates = False             # mark_duplicates.h:41
+        self.verbose = True                       # AlgorithmModule::verbose; False reproduces SURVEY F1
+        self.device = device
+        self.last_stats = None
+
+    def run(self, bam: BamFile) -> BamFile:
+        with context_for(bam, device=self.device, remove_duplicates=self.removeDuplicates,
+                         compat_quiet_index_bug=not self.verbose) as ctx:
+            ctx.push(bam.records, bam.offsets)
+            ctx.run()
+            rec, off = ctx.pull()
+            self.last_stats = ctx.stats()
+        return BamFile(text=bam.text, refs=list(bam.refs), records=rec, offsets=off)
+
+    def flags(self, bam: BamFile) -> np.ndarray:
+        with context_for(bam, device=self.device, compat_quiet_index_bug=not self.verbose) as ctx:
+            ctx.push(bam.records, bam.offsets)
+            ctx.run()
+            out = ctx.flags()
+            self.last_stats = ctx.stats()
+        return out

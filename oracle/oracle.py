@@ -85,7 +85,11 @@ def ref_available() -> bool:
     return _build.ensure_ref() is not None
 
 
-def ref_dedup(bam, nosplit=True, verbose=True, remove=False, threads=None, tmpdir=None):
+class RefHang(RuntimeError):
+    pass
+
+
+def ref_dedup(bam, nosplit=True, verbose=True, remove=False, threads=None, tmpdir=None, timeout=60):
     """Run the compiled reference (file -> file, rawbam both ways) -> output BamFile."""
     exe = _build.ensure_ref()
     if exe is None:
@@ -104,13 +108,20 @@ def ref_dedup(bam, nosplit=True, verbose=True, remove=False, threads=None, tmpdi
         if threads:
             cmd += ["-t", str(threads)]
         cmd += [inp, out]
-        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
-        if r.returncode != 0:
-            raise RuntimeError("reference failed: %s" % r.stderr.decode()[-2000:])
-        return bamio.read_bam(out)
+        # the reference's pipeline is racy (getInputAlignment tail-drop window) and
+        # now and then never terminates: bound every run and retry
+        for attempt in range(4):
+            try:
+                r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout)
+            except subprocess.TimeoutExpired:
+                continue
+            if r.returncode != 0:
+                raise RuntimeError("reference failed: %s" % r.stderr.decode()[-2000:])
+            return bamio.read_bam(out)
+        raise RefHang("reference did not terminate in %d s (4 attempts)" % timeout)
 
 
-def ref_time_mem(bam, reps=1, threads=None, tmpdir=None):
+def ref_time_mem(bam, reps=1, threads=None, tmpdir=None, timeout=900):
     """Time MarkDuplicates::runInternal in the compiled reference with records preloaded in RAM.
     -> dict(records, threads, seconds[list], duplicates)"""
     exe = _build.ensure_ref()
@@ -124,7 +135,10 @@ def ref_time_mem(bam, reps=1, threads=None, tmpdir=None):
         if threads:
             cmd += ["-t", str(threads)]
         cmd.append(inp)
-        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+        try:
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=timeout)
+        except subprocess.TimeoutExpired:
+            raise RefHang("reference did not terminate in %d s" % timeout)
         if r.returncode != 0:
             raise RuntimeError("reference failed")
         return json.loads(r.stdout.decode().strip().splitlines()[-1])

@@ -1,0 +1,206 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against the oracle and the
+golden flag words of the compiled reference.  Bit-exact: every comparison is array equality."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import fixtures
+import oracle
+from conftest import GOLDEN_CASES, load_golden
+from openge_b200 import bamio, dedup, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_flags(bam, **kw):
+    with dedup.context_for(bam, **kw) as ctx:
+        ctx.push(bam.records, bam.offsets)
+        ctx.run()
+        return ctx.flags(), ctx.stats()
+
+
+# ------------------------------------------------------------------ K3 alone
+@pytest.mark.parametrize("n,lo,hi", [(1, 0, 8), (31, 0, 16), (4096, 16, 52), (4097, 40, 110), (100_003, 0, 128),
+                                     (1_000_000, 43, 79), (3_000_000, 42, 112)])
+def test_radix_sort_matches_numpy(n, lo, hi):
+    rng = np.random.default_rng(n)
+    e = rng.integers(0, 2**64, size=(n, 2), dtype=np.uint64)
+    if n > 1000:      # long equal-key runs + nearly sorted stretches
+        e[: n // 3, 1] = e[0, 1]
+        e[n // 2:, 0] &= np.uint64(0xFFFF)
+    out = dedup.debug_sort128(e, lo, hi)
+
+    def key(a):      # python ints: exact 128-bit arithmetic
+        v = (a[:, 1].astype(object) << 64) | a[:, 0].astype(object)
+        return (v >> lo) & ((1 << (hi - lo)) - 1)
+
+    k_in, k_out = key(e), key(out)
+    order = sorted(range(n), key=lambda i: (k_in[i], i))      # stable reference
+    assert np.array_equal(out, e[order])
+    assert all(k_out[i] <= k_out[i + 1] for i in range(n - 1))
+
+
+# ------------------------------------------------------------------ full path vs golden / oracle
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_flags_match_reference_golden(case):
+    bam, g = load_golden(case)
+    flags, st = gpu_flags(bam)
+    assert np.array_equal(flags, g["flags_nosplit_v"])
+    assert st["n_duplicates"] == int(((flags & 0x400) != 0).sum() - ((flags & 0x500) == 0x500).sum())
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_compat_quiet_matches_reference(case):
+    bam, g = load_golden(case)
+    flags, _ = gpu_flags(bam, compat_quiet_index_bug=True)
+    assert np.array_equal(flags, g["flags_quiet"])
+
+
+@pytest.mark.parametrize("case", ["a3_fixture1", "a3_fixture2", "edge_cases", "synth_C3", "yhet208"])
+def test_end_building_field_by_field(case):
+    bam, _ = load_golden(case)
+    _, ends, ostats = oracle.markdup(bam.records, bam.offsets, bam.text, want_ends=True)
+    with dedup.context_for(bam, debug_keep_ends=True) as ctx:
+        ctx.push(bam.records, bam.offsets)
+        ctx.run()
+        got = ctx.ends()
+        st = ctx.stats()
+    assert st["n_frag_entries"] == int(ostats[0]) and st["n_pair_entries"] == int(ostats[1])
+    for f in ("eligible", "pair_eligible", "ref", "coord", "orientation", "score"):
+        assert np.array_equal(got[f], ends[f]), f
+    assert np.array_equal(got["read2Sequence"] != -1, ends["read2Sequence"] != -1)
+    # library ids are arbitrary labels: compare the partition
+    el = ends["eligible"] != 0
+    pairs = set(zip(got["lib"][el].tolist(), ends["lib"][el].tolist()))
+    assert len(pairs) == len({a for a, _ in pairs}) == len({b for _, b in pairs})
+
+
+def test_survey_a3_expected_values():
+    b1, exp1 = fixtures.fixture1()
+    f1, _ = gpu_flags(b1)
+    assert np.array_equal(((f1 & 0x400) != 0).astype(np.uint8), exp1)
+    b2, exp2 = fixtures.fixture2()
+    f2, st = gpu_flags(b2)
+    assert np.array_equal(f2, exp2)
+    assert st["n_complex_names"] >= 4      # T_multi x4 and U_pair x3 go through the exact path
+
+
+@pytest.mark.parametrize("name,scale,seed", [("C1", 0.5, 101), ("C2", 0.02, 102), ("C3", 0.08, 103),
+                                             ("C4", 0.03, 104), ("C5", 0.001, 105)])
+def test_synthetic_configs_vs_oracle(name, scale, seed):
+    bam = synth.make(name, scale, seed=seed)
+    want = oracle.markdup(bam.records, bam.offsets, bam.text)
+    got, st = gpu_flags(bam)
+    assert np.array_equal(got, want)
+    assert st["n_hash_mismatch"] == 0
+
+
+def test_remove_duplicates_pull_matches_reference():
+    bam, g = load_golden("synth_C3")
+    with dedup.context_for(bam, remove_duplicates=True) as ctx:
+        ctx.push(bam.records, bam.offsets)
+        ctx.run()
+        rec, off = ctx.pull()
+    assert len(off) - 1 == int(g["removed_n"])
+    assert hashlib.sha256(rec.tobytes()).hexdigest() == str(g["removed_sha256"])
+    assert np.array_equal(off, bamio.frame_records(rec.tobytes()))
+
+
+def test_pull_patches_only_the_duplicate_bit():
+    bam, g = load_golden("synth_C1")
+    with dedup.context_for(bam) as ctx:
+        ctx.push(bam.records, bam.offsets)
+        ctx.run()
+        rec, off = ctx.pull()
+        flags = ctx.flags()
+    assert np.array_equal(off, bam.offsets)
+    out = bamio.BamFile(text=bam.text, refs=bam.refs, records=rec, offsets=off)
+    assert np.array_equal(out.flags(), flags) and np.array_equal(flags, g["flags_nosplit_v"])
+    o = bam.offsets[:-1].astype(np.int64)
+    a, b = bam.records.copy(), rec.copy()
+    a[o + 19] = 0
+    b[o + 19] = 0
+    assert np.array_equal(a, b)
+
+
+def test_batched_push_and_rerun_are_equivalent():
+    bam = synth.make("C3", 0.02, seed=7)
+    want = oracle.markdup(bam.records, bam.offsets, bam.text)
+    with dedup.context_for(bam) as ctx:
+        cuts = [0, bam.n // 7, bam.n // 2, bam.n // 2, bam.n]
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            lo, hi = int(bam.offsets[a]), int(bam.offsets[b])
+            ctx.push(bam.records[lo:hi], bam.offsets[a:b + 1] - bam.offsets[a])
+        ctx.run()
+        f1 = ctx.flags()
+        ctx.run()                      # idempotent on the resident (already patched) records
+        f2 = ctx.flags()
+        ctx.reset()
+        ctx.push(bam.records, bam.offsets)
+        ctx.run()
+        f3 = ctx.flags()
+    assert np.array_equal(f1, want) and np.array_equal(f2, want) and np.array_equal(f3, want)
+
+
+def test_empty_and_tiny_inputs():
+    text = "@HD\tVN:1.4\tSO:coordinate\n@SQ\tSN:chr1\tLN:1000\n"
+    with dedup.DedupContext(n_ref=1, max_ref_len=1000) as ctx:
+        ctx.set_header(text)
+        ctx.run()
+        assert len(ctx.flags()) == 0
+        rec, off = ctx.pull()
+        assert len(rec) == 0
+    one = bamio.build_record("r", 0, 0, 10, 60, "50M", -1, -1, 0, "A" * 50, 30)
+    r, o = bamio.concat_records([one, one])
+    bam = bamio.BamFile(text=text, refs=[("chr1", 1000)], records=r, offsets=o)
+    flags, _ = gpu_flags(bam)
+    assert flags.tolist() == [0, 0x400]
+
+
+def test_errors_are_reported_not_swallowed():
+    text = "@HD\tVN:1.4\tSO:coordinate\n@SQ\tSN:chr1\tLN:1000\n"
+    far = bamio.build_record("r", 0, 0, 50_000_000, 60, "50M", -1, -1, 0, "A" * 50, 30)
+    r, o = bamio.concat_records([far])
+    with dedup.DedupContext(n_ref=1, max_ref_len=1000, clip_margin=100) as ctx:
+        ctx.set_header(text)
+        ctx.push(r, o)
+        with pytest.raises(dedup.DedupError) as e:
+            ctx.run()
+        assert e.value.code == -4
+    bad = r.copy()
+    bad[0] = 200      # block_size no longer matches the offsets
+    with dedup.DedupContext(n_ref=1, max_ref_len=0) as ctx:
+        ctx.set_header(text)
+        ctx.push(bad, o)
+        with pytest.raises(dedup.DedupError) as e:
+            ctx.run()
+        assert e.value.code == -7
+        with pytest.raises(dedup.DedupError):
+            ctx.flags()
+
+
+def test_full_int32_coordinate_layout_and_wide_reference_ids():
+    """max_ref_len unknown -> 32-bit coordinate field; still bit-exact."""
+    bam, g = load_golden("a3_fixture1")
+    with dedup.DedupContext(n_ref=2, max_ref_len=0) as ctx:
+        ctx.set_header(bam.text)
+        ctx.push(bam.records, bam.offsets)
+        ctx.run()
+        assert np.array_equal(ctx.flags(), g["flags_nosplit_v"])
+
+
+def test_size_independent_properties_at_scale():
+    """1 M reads (config C1 at full size): idempotence + agreement with the oracle's count."""
+    bam = synth.make("C1", 1.0)
+    flags, st = gpu_flags(bam)
+    out = bamio.BamFile(text=bam.text, refs=bam.refs, records=bam.records.copy(), offsets=bam.offsets)
+    o = bam.offsets[:-1].astype(np.int64)
+    out.records[o + 18] = (flags & 0xFF).astype(np.uint8)
+    out.records[o + 19] = (flags >> 8).astype(np.uint8)
+    again, _ = gpu_flags(out)
+    assert np.array_equal(again, flags)                       # marking is idempotent
+    want = oracle.markdup(bam.records, bam.offsets, bam.text)
+    assert np.array_equal(flags, want)
+    # mates of a duplicate pair are flagged together
+    assert st["n_duplicates"] % 2 == 0
