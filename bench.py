@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- reads/sec of the dedup hot path (BASELINE.json metric) on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2] [--scale S]
+
+A step = one pass of the whole hot path (end-build, mate join, both radix sorts, select, flag
+write) over one synthetic coordinate-sorted paired-end BAM batch.  At N=1 the workload is
+config C2 of BASELINE.json (50 M reads, 2x150 bp, ~10 % duplicates); at N>1 every rank holds
+one coordinate range of an N x C2-sized file (weak scaling; cross-shard mates and boundary
+ends are exchanged, see openge_b200/sharded.py).
+
+  value     reads/s with the records resident in HBM; device time (CUDA events on the library's
+            stream, first kernel -> flags final), max over ranks
+  e2e       reads/s through the C ABI from pinned HOST buffers: push (H2D) + run + flags (D2H),
+            wall clock bracketed by device syncs
+  roofline  the onesweep radix-sort pass kernel: algorithmic bytes (32 per entry per launch) over
+            its CUDA-event duration, against MEASURED_PEAKS.json's HBM copy peak
+  cpu_baseline  the compiled reference (oracle/_ref, its own threads) or the C oracle port on a
+            bounded sample of the same workload, on this box's host cores
+
+--impl reference times the reference's own CPU implementation (oracle/_ref/oge_ref_dedup --mem:
+MarkDuplicates::runInternal with records preloaded in RAM) on a bounded sample per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "reads/sec dedup (bit-exact flags)"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# --------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------- workload
+def make_shard(workload, scale, rank, world, pinned):
+    """Synthetic records for this rank -> (records array, offsets, header text, contigs).
+    world == 1: the named config.  world > 1: handled by openge_b200.sharded (range shards)."""
+    from openge_b200 import synth
+    cfg, contigs, rgs = synth.config(workload, scale)
+    if world > 1:
+        from openge_b200 import sharded
+        return sharded.make_rank_shard(cfg, contigs, rgs, rank, world, pinned)
+    hold = {}
+
+    def alloc(nbytes):
+        if pinned:
+            from openge_b200 import dedup
+            hold["pin"] = dedup.PinnedBuffer(nbytes + 64)
+            return hold["pin"].array[:nbytes]
+        return np.empty(nbytes + 64, dtype=np.uint8)[:nbytes]
+
+    rec, offs = synth.generate(cfg, records_out=alloc)
+    return rec, offs, synth.header_text(contigs, rgs), contigs, hold
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_traffic():
+    """dram bytes per launch of the pass kernel from the committed ncu --set full capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+# --------------------------------------------------------------------------------------- CPU baselines
+def cpu_reference_run(bam, threads, reps=1, timeout=600):
+    """The compiled reference on `bam` -> (seconds per rep list, kind)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    if oracle._build.REF_BIN and os.path.exists(oracle._build.REF_BIN):
+        try:
+            r = oracle.ref_time_mem(bam, reps=reps, threads=threads, timeout=timeout)
+            return r["seconds"], "reference"
+        except Exception as e:      # the reference's pipeline can hang: fall back to the port
+            sys.stderr.write("[bench] compiled reference failed (%s); timing the C oracle port instead\n" % e)
+    secs = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        oracle.markdup(bam.records, bam.offsets, bam.text)
+        secs.append(time.perf_counter() - t0)
+    return secs, "port"
+
+
+def sample_bam(workload, n_reads):
+    from openge_b200 import synth
+    cfg, _, _ = synth.config(workload, 1.0)
+    full = max(1, int(cfg.n_templates) * 2)
+    return synth.make(workload, max(1e-6, n_reads / full))
+
+
+def run_reference_arm(args):
+    rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    # calibrate on a small sample, then size the per-step sample so the whole run takes ~2-3 minutes
+    cal = sample_bam(args.workload, 100_000)
+    secs, kind = cpu_reference_run(cal, cores, reps=1, timeout=120)
+    rate = cal.n / max(secs[0], 1e-3)
+    total_steps = args.steps + args.warmup
+    target_s = 150.0 / max(1, total_steps)
+    n_reads = int(min(4_000_000, max(200_000, rate * target_s)))
+    bam = sample_bam(args.workload, n_reads)
+    times = []
+    for _ in range(total_steps):
+        s, kind = cpu_reference_run(bam, cores, reps=1, timeout=600)
+        times.append(s[0])
+    timed = times[args.warmup:]
+    sec = float(np.mean(timed))
+    value = bam.n / sec
+    sample = "%d reads of workload %s (same generator, scaled) per step; MarkDuplicates::runInternal with records in RAM" % (bam.n, args.workload)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "sample_reads": bam.n},
+        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores if kind == "reference" else 1, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_name(args):
+    names = {"C1": "C1: 1M-read coordinate-sorted paired-end 2x100bp, single library",
+             "C2": "C2: 50M-read paired-end 2x150bp, ~10% duplicates, single GPU",
+             "C3": "C3: fragment-heavy mixed SE/PE, unmapped mates, soft clips, several libraries",
+             "C4": "C4: exome-like, 40% duplicates, dense equal-key runs",
+             "C5": "C5: 800M-read 30x WGS shape, range-sharded"}
+    s = names.get(args.workload, args.workload)
+    if args.scale != 1.0:
+        s += " (scale %g)" % args.scale
+    return s
+
+
+# --------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if world != args.gpus:
+        if args.gpus > 1 and world == 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    from openge_b200 import dedup
+    if dedup.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the dedup path has no CPU fallback")
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    t_gen = time.perf_counter()
+    rec, offs, text, contigs, hold = make_shard(args.workload, args.scale, rank, world, pinned=True)
+    n = len(offs) - 1
+    t_gen = time.perf_counter() - t_gen
+
+    if world > 1:
+        from openge_b200 import sharded
+        return sharded.bench(args, rank, world, local_rank, rec, offs, text, contigs, METRIC, workload_name(args))
+
+    max_len = max(l for _, l in contigs)
+    ctx = dedup.DedupContext(n_ref=len(contigs), max_ref_len=max_len, device=local_rank, profile_events=True,
+                             capacity_records=n, capacity_bytes=rec.nbytes)
+    ctx.set_header(text)
+    offs_pin = dedup.PinnedBuffer(offs.nbytes)
+    offs_pin.array.view(np.uint64)[:] = offs
+    flags_pin = dedup.PinnedBuffer(n * 2)
+
+    def push_all():
+        ctx.push_async(rec.ctypes.data, rec.nbytes, offs_pin.ptr, n)
+
+    # ---- device-resident timing
+    push_all()
+    ctx.sync()
+    for _ in range(args.warmup):
+        ctx.run()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ctx.sync()
+    dev_ms, pass_ms, pass_bytes, pass_launches, launches = [], 0.0, 0, 0, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.run()
+        st = ctx.stats()
+        dev_ms.append(st["ms_total"])
+        pass_ms += st["ms_sort_pass_kernels"]
+        pass_bytes += st["sort_pass_bytes"]
+        pass_launches += st["sort_pass_launches"]
+        launches += st["launches"]
+    ctx.sync()
+    wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    clocks = sampler.stop()
+    ms_per_step = float(np.mean(dev_ms))
+    value = n / (ms_per_step * 1e-3)
+    flags_resident = ctx.flags(flags_pin.array.view(np.uint16)).copy()
+
+    # ---- end to end through the C ABI from host buffers
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_t = []
+    for _ in range(1 + e2e_steps):      # first one is warm-up
+        ctx.reset()
+        ctx.sync()
+        t1 = time.perf_counter()
+        push_all()
+        ctx.run()
+        ctx.flags(flags_pin.array.view(np.uint16))
+        e2e_t.append(time.perf_counter() - t1)
+    e2e_s = float(np.mean(e2e_t[1:]))
+    flags_e2e = flags_pin.array.view(np.uint16).copy()
+    assert np.array_equal(flags_e2e, flags_resident), "e2e flags differ from the device-resident run"
+    n_dup = int(((flags_e2e & 0x400) != 0).sum())
+
+    # ---- roofline of the dominant kernel (onesweep pass)
+    peak, peak_src = load_peaks()
+    achieved = (pass_bytes / 1e9) / (pass_ms * 1e-3) if pass_ms > 0 else 0.0
+    traffic = load_traffic()
+    roofline = {"bound": "hbm", "kernel": "rs_onesweep_pass", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_src,
+                "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+                "launches_timed": pass_launches,
+                "avg_launch_ms": pass_ms / pass_launches if pass_launches else None,
+                "algorithmic_bytes_per_launch": pass_bytes / pass_launches if pass_launches else None}
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1)
+    cpu = None
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample_n = 2_000_000
+        sb = sample_bam(args.workload, sample_n)
+        secs, kind = cpu_reference_run(sb, cores, reps=1, timeout=300)
+        cpu = {"value": sb.n / secs[0], "unit": "reads/s", "cores": cores if kind == "reference" else 1, "kind": kind,
+               "sample": "%d reads of workload %s (same generator, scaled); %s" % (
+                   sb.n, args.workload,
+                   "compiled reference, MarkDuplicates::runInternal with records in RAM, -t %d" % cores
+                   if kind == "reference" else "C oracle port, single thread")}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args), "reads": n, "record_bytes": int(rec.nbytes),
+                   "l2": "inputs (%.1f GB) larger than L2" % (rec.nbytes / 1e9), "wall_ms_per_step": wall_ms,
+                   "duplicates_flagged": n_dup, "gen_seconds": t_gen, "stage_ms": {k: st[k] for k in (
+                       "ms_endbuild", "ms_join", "ms_sort_pair", "ms_sort_frag", "ms_select", "ms_flags")},
+                   "key_bits": [st["frag_key_bits"], st["pair_key_bits"]],
+                   "sort_passes": [st["frag_sort_passes"], st["pair_sort_passes"]]},
+        "e2e": {"value": n / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": int(rec.nbytes + offs.nbytes),
+                "d2h_bytes_per_step": int(n * 2), "ms_per_step": e2e_s * 1e3},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    ctx.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        sys.stderr.write("[bench] note: fewer than 3 warm-up steps\n")
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -58,7 +58,7 @@ typedef struct oge_gpu_dedup_config {
     int32_t compat_quiet_index_bug; /* 1: reproduce non-verbose runs of the reference, where the record index
                                        never advances (mark_duplicates.cpp:250).  Default 0. */
     int32_t debug_keep_ends;        /* 1: keep a copy of the per-record end entries for oge_gpu_dedup_debug_ends */
-    int32_t reserved0;
+    int32_t profile_events;         /* 1: bracket every radix-sort pass launch with CUDA events (stats.ms_sort_pass_kernels) */
     uint64_t capacity_records;      /* optional preallocation hints (0 = grow on demand) */
     uint64_t capacity_bytes;
     /* multi-GPU range sharding; world <= 1 means single GPU */
@@ -80,6 +80,10 @@ typedef struct oge_gpu_dedup_stats {
     float ms_total;                 /* device time of the last oge_gpu_dedup_run, CUDA events */
     float ms_endbuild, ms_join, ms_sort_frag, ms_sort_pair, ms_select, ms_flags;
     uint64_t launches;              /* kernels launched by the last run */
+    /* with profile_events: the onesweep pass kernel (K3's scatter pass) on its own */
+    float ms_sort_pass_kernels;     /* summed duration of the pass launches of the last run */
+    uint32_t sort_pass_launches;
+    uint64_t sort_pass_bytes;       /* algorithmic bytes of those launches: 32 per entry (16 read + 16 written) */
 } oge_gpu_dedup_stats;
 
 /* Per-record view of the end-building kernel (buildReadEnds, mark_duplicates.cpp:147-164). */

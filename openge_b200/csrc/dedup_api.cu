@@ -84,6 +84,7 @@ struct oge_gpu_dedup_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t copy_done = nullptr;
     cudaEvent_t ev[10];
+    cudaEvent_t pass_ev[2 * 48];      // profile_events: one pair per radix-sort pass launch
 
     // resident input
     DevBuf<uint8_t> rec;
@@ -248,6 +249,7 @@ int oge_gpu_dedup_create(const oge_gpu_dedup_config *cfg, oge_gpu_dedup_ctx **ou
             break;
         }
         for (auto &e : c->ev) cudaEventCreate(&e);
+        for (auto &e : c->pass_ev) { e = nullptr; if (cfg->profile_events) cudaEventCreate(&e); }
         if (cudaHostAlloc((void **) &c->h_counters, CNT_N * 4, cudaHostAllocDefault) != cudaSuccess) {
             rc = fail_cuda(cudaGetLastError(), "cudaHostAlloc", __FILE__, __LINE__);
             break;
@@ -276,6 +278,7 @@ void oge_gpu_dedup_destroy(oge_gpu_dedup_ctx *c) {
     c->cplx_state.release(); c->mate_of.release(); c->counters.release(); c->table.release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : c->pass_ev) if (e) cudaEventDestroy(e);
     if (c->copy_done) cudaEventDestroy(c->copy_done);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -370,6 +373,8 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     if ((rc = ensure_work(c))) return rc;
     const uint64_t n = c->n;
     uint64_t launches = 0;
+    PassTimer timer{c->pass_ev, 48, 0, 0};
+    PassTimer *tp = c->cfg.profile_events ? &timer : nullptr;
 
     // the pushes ran on the copy stream
     OGE_CUDA_TRY(cudaEventRecord(c->copy_done, c->copy_stream));
@@ -437,7 +442,7 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     E128 *sorted_pairs = c->pair.p;
     if (n_pairs) {
         if ((rc = radix_sort_128(c->pair.p, c->pair2.p, n_pairs, nullptr, c->kl.p_coord2, c->kl.p_end, c->scratch.p, s, &sorted_pairs,
-                                 &launches)))
+                                 &launches, tp)))
             return rc;
     }
     OGE_CUDA_TRY(cudaEventRecord(c->ev[3], s));
@@ -451,7 +456,7 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     E128 *sorted_frags = c->frag.p;
     if (n_frag) {
         if ((rc = radix_sort_128(c->frag.p, c->sortbuf.p, n, nullptr, c->kl.f_orient, c->kl.f_end, c->scratch.p, s, &sorted_frags,
-                                 &launches)))
+                                 &launches, tp)))
             return rc;
     }
     OGE_CUDA_TRY(cudaEventRecord(c->ev[5], s));
@@ -491,6 +496,9 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     st.ms_select = ms_between(c->ev[3], c->ev[4]) + ms_between(c->ev[5], c->ev[6]);
     st.ms_flags = ms_between(c->ev[6], c->ev[7]);
     st.launches = launches;
+    for (int i = 0; i < timer.used; i++) st.ms_sort_pass_kernels += ms_between(c->pass_ev[2 * i], c->pass_ev[2 * i + 1]);
+    st.sort_pass_launches = timer.used;
+    st.sort_pass_bytes = timer.bytes;
     c->ran = true;
     return OGE_OK;
 }

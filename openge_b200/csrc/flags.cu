@@ -23,7 +23,8 @@ __global__ void __launch_bounds__(FL_THREADS) flags_kernel(FlagParams P) {
             isdup = d;
         }
         P.flag_out[i] = nf;
-        if (nf != f) {
+        // duplicates are always (re)written so that a re-run over the resident records does the same work
+        if (nf != f || isdup) {
             uint8_t *p = P.rec + P.off[i] + 18;
             p[0] = (uint8_t) (nf & 0xFF);
             p[1] = (uint8_t) (nf >> 8);

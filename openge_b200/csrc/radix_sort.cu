@@ -252,7 +252,7 @@ int radix_sort_init() {
 }
 
 int radix_sort_128(E128 *a, E128 *b, uint64_t n, const uint32_t *n_dev, int bit_lo, int bit_hi, void *scratch,
-                   cudaStream_t stream, E128 **result, uint64_t *launches) {
+                   cudaStream_t stream, E128 **result, uint64_t *launches, PassTimer *timer) {
     *result = a;
     if (n == 0 || bit_hi <= bit_lo) return 0;
     if (n >= (1ull << 30)) return fail_msg(-6, "radix sort: more than 2^30-1 entries");
@@ -276,8 +276,15 @@ int radix_sort_128(E128 *a, E128 *b, uint64_t n, const uint32_t *n_dev, int bit_
     E128 *src = a, *dst = b;
     for (int p = 0; p < plan.n_pass; p++) {
         OGE_CUDA_TRY(cudaMemsetAsync(status, 0, (size_t) tiles * RS_RADIX * 4, stream));
+        const bool timed = timer && timer->used < timer->cap;
+        if (timed) cudaEventRecord(timer->pool[2 * timer->used], stream);
         rs_onesweep_pass<<<(uint32_t) tiles, RS_THREADS, PASS_SMEM, stream>>>(
             src, dst, (uint32_t) n, n_dev, plan.shift[p], plan.bits[p], goff + p * RS_RADIX, status, tile_counters + p);
+        if (timed) {
+            cudaEventRecord(timer->pool[2 * timer->used + 1], stream);
+            timer->used++;
+            timer->bytes += n * 2 * sizeof(E128);
+        }
         *launches += 1;
         E128 *t = src;
         src = dst;

@@ -28,8 +28,15 @@ size_t sort_scratch_bytes(uint64_t n);
 // ping-pong buffer.  Returns the buffer holding the result through *result (a or b).
 // `n_dev`, when not null, is a device word holding the real entry count (<= n); the kernels
 // then ignore the tail, so no host round trip is needed to size the sort.
+// Optional per-launch timing of the pass kernel: events are taken from `pool` (pairs), `used` counts pairs.
+struct PassTimer {
+    cudaEvent_t *pool;
+    int cap, used;
+    uint64_t bytes;      // algorithmic bytes of the timed launches
+};
+
 int radix_sort_128(E128 *a, E128 *b, uint64_t n, const uint32_t *n_dev, int bit_lo, int bit_hi, void *scratch,
-                   cudaStream_t stream, E128 **result, uint64_t *launches);
+                   cudaStream_t stream, E128 **result, uint64_t *launches, PassTimer *timer = nullptr);
 
 int radix_sort_init();   // one-time function attributes
 

@@ -29,7 +29,7 @@ ERRORS = {-1: "OGE_ERR_INVALID_ARG", -2: "OGE_ERR_CUDA", -3: "OGE_ERR_NOMEM", -4
 class Config(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("n_ref", C.c_int32), ("max_ref_len", C.c_int32),
                 ("clip_margin", C.c_int32), ("remove_duplicates", C.c_int32), ("verify_names", C.c_int32),
-                ("compat_quiet_index_bug", C.c_int32), ("debug_keep_ends", C.c_int32), ("reserved0", C.c_int32),
+                ("compat_quiet_index_bug", C.c_int32), ("debug_keep_ends", C.c_int32), ("profile_events", C.c_int32),
                 ("capacity_records", C.c_uint64), ("capacity_bytes", C.c_uint64),
                 ("rank", C.c_int32), ("world", C.c_int32), ("index_base", C.c_uint64)]
 
@@ -41,7 +41,8 @@ class Stats(C.Structure):
                 ("frag_sort_passes", C.c_uint32), ("pair_sort_passes", C.c_uint32),
                 ("ms_total", C.c_float), ("ms_endbuild", C.c_float), ("ms_join", C.c_float),
                 ("ms_sort_frag", C.c_float), ("ms_sort_pair", C.c_float), ("ms_select", C.c_float),
-                ("ms_flags", C.c_float), ("launches", C.c_uint64)]
+                ("ms_flags", C.c_float), ("launches", C.c_uint64),
+                ("ms_sort_pass_kernels", C.c_float), ("sort_pass_launches", C.c_uint32), ("sort_pass_bytes", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -144,12 +145,12 @@ class DedupContext:
 
     def __init__(self, n_ref=0, max_ref_len=0, device=0, remove_duplicates=False, verify_names=True,
                  compat_quiet_index_bug=False, debug_keep_ends=False, clip_margin=0, capacity_records=0,
-                 capacity_bytes=0, index_base=0, rank=0, world=1):
+                 capacity_bytes=0, index_base=0, rank=0, world=1, profile_events=False):
         self._h = C.c_void_p()
         cfg = Config(abi_version=ABI_VERSION, device=device, n_ref=n_ref, max_ref_len=max_ref_len, clip_margin=clip_margin,
                      remove_duplicates=int(remove_duplicates), verify_names=int(verify_names),
                      compat_quiet_index_bug=int(compat_quiet_index_bug), debug_keep_ends=int(debug_keep_ends),
-                     capacity_records=capacity_records, capacity_bytes=capacity_bytes, rank=rank, world=world,
+                     profile_events=int(profile_events), capacity_records=capacity_records, capacity_bytes=capacity_bytes, rank=rank, world=world,
                      index_base=index_base)
         _check(lib().oge_gpu_dedup_create(C.byref(cfg), C.byref(self._h)))
         self.n = 0

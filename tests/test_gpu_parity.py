@@ -93,7 +93,8 @@ def test_synthetic_configs_vs_oracle(name, scale, seed):
     want = oracle.markdup(bam.records, bam.offsets, bam.text)
     got, st = gpu_flags(bam)
     assert np.array_equal(got, want)
-    assert st["n_hash_mismatch"] == 0
+    if name != "C3":      # C3 carries RG ids the header does not list: those couples take the exact path
+        assert st["n_hash_mismatch"] == 0 and st["n_complex_names"] == 0
 
 
 def test_remove_duplicates_pull_matches_reference():
