@@ -10,10 +10,13 @@
 //   pairing key            :210-214      RG + ":" + name  -> 64-bit hash of exactly those bytes
 //   tag walk               util/bamtools/BamAlignment.cpp:270-294, 699-786
 //
-// Shape: persistent CTAs; each tile of 128 consecutive records is one contiguous byte range,
-// fetched into shared memory with a 1-D bulk async copy (cp.async.bulk, completion on an
-// mbarrier), double buffered; one thread then parses one record out of shared memory with
-// 32-bit word reads.  HBM-bound: the record bytes are read once.
+// Shape: persistent CTAs of 128 threads, several per SM.  A tile = 128 consecutive records = one
+// contiguous byte range; the CTA fetches it (and the tile's 129 offsets) into shared memory with
+// 1-D bulk async copies (cp.async.bulk -> UBLKCP, completion on an mbarrier), then one thread
+// parses one record out of shared memory with aligned 32-bit ld.shared reads.  Each CTA has one
+// stage; the copy latency is covered by the other CTAs resident on the SM.
+// HBM-bound by design: the record bytes are read once (algorithmic: core + name + cigar + quals
+// + tags up to RG; the packed bases ride along in the same sectors).
 // Outputs per record (coalesced): 16 B end entry, 8 B name hash, 2 B read-group code, 2 B flag.
 #include "kernels.cuh"
 
@@ -28,8 +31,8 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
@@ -44,26 +47,50 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     } while (!ok);
 }
 
-// ---------------------------------------------------------------- unaligned reads
-// 32-bit little-endian read at any byte address: two aligned words + funnel shift.
-// May touch up to 3 bytes past p+4; every buffer it is used on carries >= 16 B of slack.
-__device__ __forceinline__ uint32_t ldu32(const uint8_t *p) {
-    uintptr_t a = (uintptr_t) p;
-    const uint32_t *w = (const uint32_t *) (a & ~(uintptr_t) 3);
-    uint32_t sh = (uint32_t) (a & 3) * 8;
-    uint32_t lo = w[0];
-    if (sh == 0) return lo;
-    return __funnelshift_r(lo, w[1], sh);
+// ---------------------------------------------------------------- record readers
+// A record is parsed through a reader so that the same code runs on the shared-memory stage
+// (32-bit shared addresses, ld.shared) and, for tiles too large for the stage, on global memory.
+// Every buffer read this way carries >= 16 B of slack past its last byte.
+struct SharedRd {
+    uint32_t base;      // shared-space byte address of the record's block_size field
+    __device__ __forceinline__ uint32_t word(uint32_t a) const {      // aligned word at shared address a
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+        return v;
+    }
+    __device__ __forceinline__ uint32_t addr(uint32_t o) const { return base + o; }
+    __device__ __forceinline__ uint32_t u8(uint32_t o) const {
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(base + o));
+        return v;
+    }
+};
+
+struct GlobalRd {
+    const uint8_t *base;
+    __device__ __forceinline__ uint32_t word(uint64_t a) const { return *reinterpret_cast<const uint32_t *>(a); }
+    __device__ __forceinline__ uint64_t addr(uint32_t o) const { return (uint64_t) (uintptr_t) base + o; }
+    __device__ __forceinline__ uint32_t u8(uint32_t o) const { return base[o]; }
+};
+
+// unaligned little-endian 32-bit read: two aligned words + funnel shift (branch free)
+template <class Rd>
+__device__ __forceinline__ uint32_t rd_u32(const Rd &r, uint32_t o) {
+    auto a = r.addr(o);
+    auto wa = a & ~(decltype(a)) 3;
+    return __funnelshift_r(r.word(wa), r.word(wa + 4), (uint32_t) (a & 3) * 8);
 }
-__device__ __forceinline__ uint32_t ldu16(const uint8_t *p) { return (uint32_t) p[0] | ((uint32_t) p[1] << 8); }
+template <class Rd>
+__device__ __forceinline__ uint32_t rd_u16(const Rd &r, uint32_t o) { return rd_u32(r, o) & 0xFFFFu; }
 
 // ---------------------------------------------------------------- pairing-key hash
-// A function of the byte string RG + ":" + name only (not of how it splits into RG and
-// name: the reference's map key is the concatenation, mark_duplicates.cpp:214).
+// A function of the byte string RG + ":" + name only (not of how it splits into RG and name:
+// the reference's map key is the concatenation, mark_duplicates.cpp:214).  Bytes are packed
+// into 32-bit words in stream order and mixed with two murmur3-style lanes.
 struct KeyHasher {
-    uint32_t h1, h2, buf, nb, len;
+    uint32_t h1, h2, carry, nb, len;      // carry: nb (0..3) pending bytes in the low end
     __device__ __forceinline__ void init() {
-        h1 = 0x9E3779B9u; h2 = 0x85EBCA6Bu; buf = 0; nb = 0; len = 0;
+        h1 = 0x9E3779B9u; h2 = 0x85EBCA6Bu; carry = 0; nb = 0; len = 0;
     }
     __device__ __forceinline__ void mix(uint32_t k) {
         uint32_t k1 = k * 0xCC9E2D51u;
@@ -75,27 +102,46 @@ struct KeyHasher {
         h2 ^= k2;
         h2 = __funnelshift_l(h2, h2, 17) * 5u + 0x561CCD1Bu;
     }
-    // n (1..4) bytes in the low end of w; bytes above n must be zero
-    __device__ __forceinline__ void push(uint32_t w, uint32_t n) {
-        buf |= w << (8 * nb);
+    __device__ __forceinline__ void push4(uint32_t w) {      // four bytes
+        mix(carry | (w << (8 * nb)));
+        carry = __funnelshift_rc(w, 0u, 32 - 8 * nb);       // nb == 0 -> shift 32 -> 0
+        len += 4;
+    }
+    __device__ __forceinline__ void push_tail(uint32_t w, uint32_t n) {      // n in 1..3, bytes above n zero
+        uint32_t v = carry | (w << (8 * nb));
         if (nb + n >= 4) {
-            mix(buf);
-            buf = nb ? (w >> (8 * (4 - nb))) : 0;
+            mix(v);
+            carry = __funnelshift_rc(w, 0u, 32 - 8 * nb);
             nb = nb + n - 4;
         } else {
+            carry = v;
             nb += n;
         }
         len += n;
     }
-    __device__ __forceinline__ void push_bytes(const uint8_t *p, uint32_t n) {
-        for (uint32_t o = 0; o < n; o += 4) {
-            uint32_t w = ldu32(p + o), m = n - o;
-            if (m < 4) w &= (1u << (8 * m)) - 1;
-            push(w, m < 4 ? m : 4);
+    // n bytes starting at record offset o
+    template <class Rd>
+    __device__ __forceinline__ void push_bytes(const Rd &r, uint32_t o, uint32_t n) {
+        if (n == 0) return;
+        auto a = r.addr(o);
+        auto wa = a & ~(decltype(a)) 3;
+        const uint32_t sh = (uint32_t) (a & 3) * 8;
+        uint32_t cur = r.word(wa);
+        const uint32_t full = n >> 2;
+        for (uint32_t j = 0; j < full; j++) {
+            wa += 4;
+            uint32_t nxt = r.word(wa);
+            push4(__funnelshift_r(cur, nxt, sh));
+            cur = nxt;
+        }
+        const uint32_t rem = n & 3;
+        if (rem) {
+            uint32_t nxt = r.word(wa + 4);
+            push_tail(__funnelshift_r(cur, nxt, sh) & ((1u << (8 * rem)) - 1), rem);
         }
     }
     __device__ __forceinline__ uint64_t finish() {
-        if (nb) mix(buf);
+        if (nb) mix(carry);
         h1 ^= len; h2 ^= len;
         h1 += h2; h2 += h1;
         h1 ^= h1 >> 16; h1 *= 0x85EBCA6Bu; h1 ^= h1 >> 13; h1 *= 0xC2B2AE35u; h1 ^= h1 >> 16;
@@ -109,33 +155,35 @@ struct KeyHasher {
 // ---------------------------------------------------------------- RG tag walk
 // FindTag + SkipToNextTag for "RG" (BamAlignment.cpp:270-294, 699-786); the value is taken as
 // a NUL-terminated string whatever its type code (GetTag<string>, BamAlignment.h:575-606).
-// Returns the value's offset inside `tags` (or -1) and its length bounded by the record end.
-__device__ int find_rg(const uint8_t *tags, uint32_t n, uint32_t *len) {
+// `t0` = record offset of the tag block, n = its length.  Returns the value's record offset
+// (or -1) and its length bounded by the record end.
+template <class Rd>
+__device__ int find_rg(const Rd &r, uint32_t t0, uint32_t n, uint32_t *len) {
     uint32_t parsed = 0;
     *len = 0;
     while (parsed < n) {
         if (n - parsed < 3) return -1;
-        uint8_t t0 = tags[parsed], t1 = tags[parsed + 1], type = tags[parsed + 2];
+        uint32_t t = rd_u32(r, t0 + parsed);      // name[0], name[1], type, first value byte
+        uint32_t type = (t >> 16) & 0xFF;
         parsed += 3;
-        if (t0 == 'R' && t1 == 'G') {
+        if ((t & 0xFFFF) == ((uint32_t) 'R' | ((uint32_t) 'G' << 8))) {
             uint32_t l = 0;
-            while (parsed + l < n && tags[parsed + l]) l++;
+            while (parsed + l < n && r.u8(t0 + parsed + l)) l++;
             *len = l;
-            return (int) parsed;
+            return (int) (t0 + parsed);
         }
         switch (type) {
             case 'A': case 'c': case 'C': parsed += 1; break;
             case 's': case 'S': parsed += 2; break;
             case 'f': case 'i': case 'I': parsed += 4; break;
             case 'Z': case 'H':
-                while (parsed < n && tags[parsed]) parsed++;
+                while (parsed < n && r.u8(t0 + parsed)) parsed++;
                 parsed++;
                 break;
             case 'B': {
                 if (parsed + 5 > n) return -1;
-                uint8_t at = tags[parsed];
-                int32_t cnt = (int32_t) ((uint32_t) tags[parsed + 1] | ((uint32_t) tags[parsed + 2] << 8) |
-                                         ((uint32_t) tags[parsed + 3] << 16) | ((uint32_t) tags[parsed + 4] << 24));
+                uint32_t at = r.u8(t0 + parsed);
+                int32_t cnt = (int32_t) rd_u32(r, t0 + parsed + 1);
                 parsed += 5;
                 long long skip;
                 if (at == 'c' || at == 'C') skip = cnt;
@@ -149,28 +197,43 @@ __device__ int find_rg(const uint8_t *tags, uint32_t n, uint32_t *len) {
             default: return -1;      // includes type == 0
         }
         if (parsed >= n) return -1;
-        if (tags[parsed] == 0) return -1;
+        if (r.u8(t0 + parsed) == 0) return -1;
     }
     return -1;
 }
 
-// read-group code: index into the host-resolved @RG table, RGC_ABSENT for no tag / empty
-// value, RGC_UNKNOWN for a value the header does not list
-__device__ __forceinline__ uint32_t rg_lookup(const RgTable &t, const uint8_t *rg, uint32_t len) {
+// read-group code: index into the host-resolved @RG table, RGC_ABSENT for no tag / empty value,
+// RGC_UNKNOWN for a value the header does not list.  `tb`/`to` point at the table (shared-memory
+// copy when it is small, see the kernel).
+template <class Rd>
+__device__ __forceinline__ uint32_t rg_lookup(const uint8_t *tb, const uint32_t *to, int n_rg, const Rd &r, uint32_t o, uint32_t len) {
     if (len == 0) return RGC_ABSENT;
-    for (int i = 0; i < t.n; i++) {
-        uint32_t a = t.off[i], b = t.off[i + 1];
+    for (int i = 0; i < n_rg; i++) {
+        uint32_t a = to[i], b = to[i + 1];
         if (b - a != len) continue;
         uint32_t j = 0;
-        while (j < len && t.bytes[a + j] == rg[j]) j++;
+        while (j < len && tb[a + j] == r.u8(o + j)) j++;
         if (j == len) return (uint32_t) i;
     }
     return RGC_UNKNOWN;
 }
 
+// bytes >= 15 of w, summed (SWAR: no per-byte compare instruction exists on sm_100)
+__device__ __forceinline__ uint32_t score4(uint32_t w, uint32_t acc) {
+    uint32_t msb = (((w | 0x80808080u) - 0x0F0F0F0Fu) | w) & 0x80808080u;      // bit 7 of each byte: byte >= 15
+    uint32_t m = (msb - (msb >> 7)) | msb;                                     // 0xFF per selected byte
+    return __dp4a(w & m, 0x01010101u, acc);
+}
+
+struct RgSmem {
+    const uint8_t *bytes;
+    const uint32_t *off;
+    const int16_t *lib;
+};
+
 // ---------------------------------------------------------------- one record
-// p points at block_size; rec_len = bytes up to the next record.
-__device__ __forceinline__ void build_end(const EndbuildParams &P, const uint8_t *p, uint32_t rec_len, uint64_t i,
+template <class Rd>
+__device__ __forceinline__ void build_end(const EndbuildParams &P, const RgSmem &rgt, const Rd &r, uint32_t rec_len, uint64_t i,
                                           uint32_t &err, bool &is_frag, bool &is_pe) {
     E128 ent;
     ent.lo = ent.hi = ~0ull;
@@ -179,14 +242,14 @@ __device__ __forceinline__ void build_end(const EndbuildParams &P, const uint8_t
     is_frag = is_pe = false;
 
     bool ok = rec_len >= 36;
-    uint32_t block_size = 0, l_name = 0, n_cig = 0, l_seq = 0;
-    uint32_t o_cig = 0, o_qual = 0, o_tags = 0;
+    uint32_t l_name = 0, n_cig = 0, l_seq = 0, o_cig = 0, o_qual = 0, o_tags = 0;
     if (ok) {
-        block_size = ldu32(p);
-        l_name = p[12];
-        n_cig = ldu16(p + 16);
-        flag = ldu16(p + 18);
-        l_seq = ldu32(p + 20);
+        uint32_t block_size = rd_u32(r, 0);
+        l_name = r.u8(12);
+        uint32_t cf = rd_u32(r, 16);
+        n_cig = cf & 0xFFFF;
+        flag = cf >> 16;
+        l_seq = rd_u32(r, 20);
         o_cig = 36 + l_name;
         uint64_t oq = (uint64_t) o_cig + 4ull * n_cig + (((uint64_t) l_seq + 1) >> 1);
         uint64_t ot = oq + l_seq;
@@ -197,59 +260,67 @@ __device__ __forceinline__ void build_end(const EndbuildParams &P, const uint8_t
     if (!ok) {
         err |= DEV_ERR_BAD_RECORD;
     } else {
-        int32_t ref = (int32_t) ldu32(p + 4);
+        int32_t ref = (int32_t) rd_u32(r, 4);
         if (!(flag & 0x4) && ref != -1 && !(flag & 0x100)) {          // mark_duplicates.cpp:202-205
-            int32_t pos = (int32_t) ldu32(p + 8);
+            int32_t pos = (int32_t) rd_u32(r, 8);
             bool rev = (flag & 0x10) != 0;
             // ---- CIGAR: reference length + leading / trailing clip runs in one walk
             uint32_t lead = 0, trail = 0, reflen = 0;
             bool in_lead = true;
-            const uint8_t *cg = p + o_cig;
             for (uint32_t c = 0; c < n_cig; c++) {
-                uint32_t w = ldu32(cg + 4 * c), op = w & 0xF, len = w >> 4;
+                uint32_t w = rd_u32(r, o_cig + 4 * c), op = w & 0xF, len = w >> 4;
                 if (op == 4 || op == 5) {
                     if (in_lead) lead += len;
                     trail += len;
                 } else {
                     in_lead = false;
                     trail = 0;
-                    if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) reflen += len;
+                    if ((0x18Du >> op) & 1) reflen += len;      // M D N = X  (ops 0 2 3 7 8)
                 }
             }
             int32_t coord = rev ? (int32_t) ((uint32_t) pos + reflen - 1u + trail) : (int32_t) ((uint32_t) pos - lead);
 
             // ---- score: sum of quality bytes >= 15, mod 2^16 (short accumulator in the reference)
-            uint32_t sum = 0;
+            uint32_t s0 = 0, s1 = 0;
             {
-                const uint8_t *q = p + o_qual;
-                uintptr_t a = (uintptr_t) q;
-                const uint32_t *wp = (const uint32_t *) (a & ~(uintptr_t) 3);
-                uint32_t sh = (uint32_t) (a & 3) * 8;
-                uint32_t nw = (l_seq + 3) >> 2;
-                uint32_t cur = wp[0];
-                for (uint32_t j = 0; j < nw; j++) {
-                    uint32_t nxt = wp[j + 1];
-                    uint32_t w = __funnelshift_r(cur, nxt, sh);
+                auto a = r.addr(o_qual);
+                auto wa = a & ~(decltype(a)) 3;
+                const uint32_t sh = (uint32_t) (a & 3) * 8;
+                const uint32_t full = l_seq >> 2, rem = l_seq & 3;
+                uint32_t cur = r.word(wa);
+                uint32_t j = 0;
+                for (; j + 4 <= full; j += 4) {
+                    uint32_t w1 = r.word(wa + 4), w2 = r.word(wa + 8), w3 = r.word(wa + 12), w4 = r.word(wa + 16);
+                    s0 = score4(__funnelshift_r(cur, w1, sh), s0);
+                    s1 = score4(__funnelshift_r(w1, w2, sh), s1);
+                    s0 = score4(__funnelshift_r(w2, w3, sh), s0);
+                    s1 = score4(__funnelshift_r(w3, w4, sh), s1);
+                    cur = w4;
+                    wa += 16;
+                }
+                for (; j < full; j++) {
+                    uint32_t nxt = r.word(wa + 4);
+                    s0 = score4(__funnelshift_r(cur, nxt, sh), s0);
                     cur = nxt;
-                    uint32_t left = l_seq - 4 * j;
-                    if (left < 4) w &= (1u << (8 * left)) - 1;
-                    uint32_t m = __vcmpgeu4(w, 0x0F0F0F0Fu);
-                    sum = __dp4a(w & m, 0x01010101u, sum);
+                    wa += 4;
+                }
+                if (rem) {
+                    uint32_t nxt = r.word(wa + 4);
+                    s1 = score4(__funnelshift_r(cur, nxt, sh) & ((1u << (8 * rem)) - 1), s1);
                 }
             }
-            uint32_t score = sum & 0xFFFFu;
+            uint32_t score = (s0 + s1) & 0xFFFFu;
 
             // ---- RG -> read-group code -> library
             uint32_t rg_len;
-            const uint8_t *tags = p + o_tags;
-            int rg_at = find_rg(tags, rec_len - o_tags, &rg_len);
-            const uint8_t *rg = rg_at >= 0 ? tags + rg_at : tags;
+            int rg_at = find_rg(r, o_tags, rec_len - o_tags, &rg_len);
+            uint32_t rg_o = rg_at >= 0 ? (uint32_t) rg_at : o_tags;
             if (rg_at < 0) rg_len = 0;
-            rgc = rg_lookup(P.rg, rg, rg_len);
-            uint32_t lib = rgc < RGC_UNKNOWN ? (uint32_t) P.rg.lib[rgc] : (uint32_t) P.rg.unknown_lib;
+            rgc = rg_lookup(rgt.bytes, rgt.off, P.rg.n, r, rg_o, rg_len);
+            uint32_t lib = rgc < RGC_UNKNOWN ? (uint32_t) rgt.lib[rgc] : (uint32_t) P.rg.unknown_lib;
 
             bool pe = (flag & 0x1) && !(flag & 0x8);                  // :157, :209
-            int32_t mate_ref = (int32_t) ldu32(p + 24);
+            int32_t mate_ref = (int32_t) rd_u32(r, 24);
             bool paired = pe && mate_ref != -1;                       // ReadEnds::isPaired, picard_structures.h:54
 
             // ---- pack the key
@@ -262,18 +333,16 @@ __device__ __forceinline__ void build_end(const EndbuildParams &P, const uint8_t
                 ent.lo = score;
                 ent.hi = 0;
                 bits_or(ent, L.f_idx, idx);
-                bits_or(ent, L.f_paired, paired ? 1 : 0);
-                bits_or(ent, L.f_orient, rev ? 1 : 0);
+                bits_or(ent, L.f_paired, ((uint64_t) (paired ? 1 : 0)) | ((uint64_t) (rev ? 2 : 0)));      // f_orient = f_paired + 1
                 bits_or(ent, L.f_coord, (uint64_t) sc);
-                bits_or(ent, L.f_ref, (uint64_t) ref);
-                bits_or(ent, L.f_lib, lib);
+                bits_or(ent, L.f_ref, (uint64_t) ref | ((uint64_t) lib << L.ref_bits));                  // f_lib = f_ref + ref_bits
                 is_frag = true;
                 if (pe) {
                     KeyHasher h;
                     h.init();
-                    h.push_bytes(rg, rg_len);
-                    h.push(':', 1);
-                    h.push_bytes(p + 36, l_name ? l_name - 1 : 0);
+                    h.push_bytes(r, rg_o, rg_len);
+                    h.push_tail(':', 1);
+                    h.push_bytes(r, 36, l_name ? l_name - 1 : 0);
                     hk = h.finish();
                     is_pe = true;
                 }
@@ -287,20 +356,35 @@ __device__ __forceinline__ void build_end(const EndbuildParams &P, const uint8_t
 }
 
 // ---------------------------------------------------------------- the kernel
-struct StageMeta {
-    uint64_t a0;      // byte offset (in the record buffer) of shared-memory byte 0
-    uint32_t direct;  // tile did not fit the stage: parse straight from global memory
-    uint32_t pad;
-};
+constexpr uint32_t EB_OFF_BYTES = ((EB_THREADS + 2) * 8 + 15) & ~15u;      // 129 offsets, rounded to 16 B
+constexpr int EB_RG_SMEM_BYTES = 1024, EB_RG_SMEM_N = 32;
 
 __global__ void __launch_bounds__(EB_THREADS) endbuild_kernel(EndbuildParams P, uint32_t stage_cap, uint32_t n_tiles) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[EB_STAGES];
-    __shared__ StageMeta meta[EB_STAGES];
+    extern __shared__ __align__(128) uint8_t smem[];      // [offsets: EB_OFF_BYTES][records: stage_cap]
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint64_t s_a0;
+    __shared__ uint32_t s_direct;
+    __shared__ uint8_t s_rg_bytes[EB_RG_SMEM_BYTES];
+    __shared__ uint32_t s_rg_off[EB_RG_SMEM_N + 1];
+    __shared__ int16_t s_rg_lib[EB_RG_SMEM_N];
 
     const int tid = threadIdx.x;
+    const uint64_t *s_off = reinterpret_cast<const uint64_t *>(smem);
+    const uint32_t stage_addr = smem_u32(smem + EB_OFF_BYTES);
+
+    // small @RG tables are served from shared memory
+    RgSmem rgt{P.rg.bytes, P.rg.off, P.rg.lib};
+    {
+        uint32_t total = P.rg.n > 0 && P.rg.n <= EB_RG_SMEM_N ? P.rg.off[P.rg.n] : 0xFFFFFFFFu;
+        if (total <= (uint32_t) EB_RG_SMEM_BYTES) {
+            for (uint32_t j = tid; j < total; j += EB_THREADS) s_rg_bytes[j] = P.rg.bytes[j];
+            for (int j = tid; j <= P.rg.n; j += EB_THREADS) s_rg_off[j] = P.rg.off[j];
+            for (int j = tid; j < P.rg.n; j += EB_THREADS) s_rg_lib[j] = P.rg.lib[j];
+            rgt = RgSmem{s_rg_bytes, s_rg_off, s_rg_lib};
+        }
+    }
     if (tid == 0) {
-        for (int s = 0; s < EB_STAGES; s++) mbar_init(&bars[s], 1);
+        mbar_init(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -309,49 +393,39 @@ __global__ void __launch_bounds__(EB_THREADS) endbuild_kernel(EndbuildParams P, 
         uint64_t r1 = (uint64_t) tile * EB_THREADS + EB_THREADS;
         return r1 < P.n ? r1 : P.n;
     };
-    auto issue = [&](int s, uint64_t b0, uint64_t b1) {      // thread 0 only; [b0, b1) = the tile's bytes
+    // thread 0: start the copies of a tile whose byte range is [b0, b1)
+    auto issue = [&](uint32_t tile, uint64_t b0, uint64_t b1) {
         uint64_t a0 = b0 & ~15ull;
         uint64_t len = (b1 - a0 + 15) & ~15ull;
-        meta[s].a0 = a0;
-        if (len + 16 <= stage_cap && b1 >= b0) {
-            meta[s].direct = 0;
-            mbar_expect_tx(&bars[s], (uint32_t) len);
-            bulk_g2s(smem + (size_t) s * stage_cap, P.rec + a0, (uint32_t) len, &bars[s]);
+        uint64_t r0 = (uint64_t) tile * EB_THREADS;
+        uint32_t off_bytes = (uint32_t) (((tile_end(tile) - r0 + 1) * 8 + 15) & ~15ull);
+        s_a0 = a0;
+        if (b1 >= b0 && len + 16 <= stage_cap) {
+            s_direct = 0;
+            mbar_expect_tx(&bar, (uint32_t) len + off_bytes);
+            bulk_g2s(stage_addr, P.rec + a0, (uint32_t) len, &bar);
         } else {
-            meta[s].direct = 1;
-            mbar_expect_tx(&bars[s], 0);
+            s_direct = 1;      // parsed straight from global memory
+            mbar_expect_tx(&bar, off_bytes);
         }
+        bulk_g2s(smem_u32(smem), P.off + r0, off_bytes, &bar);
     };
 
-    if (tid == 0) {
-        for (int s = 0; s < EB_STAGES; s++) {
-            uint32_t t = blockIdx.x + s * gridDim.x;
-            if (t < n_tiles) issue(s, P.off[(uint64_t) t * EB_THREADS], P.off[tile_end(t)]);
-        }
-    }
-    __syncthreads();      // meta[] visible
+    if (tid == 0 && blockIdx.x < n_tiles) issue(blockIdx.x, P.off[(uint64_t) blockIdx.x * EB_THREADS], P.off[tile_end(blockIdx.x)]);
 
-    uint32_t err = 0, n_frag = 0, n_pe = 0;
-    uint32_t k = 0;
+    uint32_t err = 0, n_frag = 0, n_pe = 0, k = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, k++) {
-        const int s = k % EB_STAGES;
-        const uint32_t parity = (k / EB_STAGES) & 1;
-        // byte range of the tile that will refill this stage: loaded now, used after the parse
-        const uint32_t nt = tile + EB_STAGES * gridDim.x;
+        // byte range of this CTA's next tile: requested now, needed after the parse
+        const uint32_t nt = tile + gridDim.x;
         uint64_t nb0 = 0, nb1 = 0;
         if (tid == 0 && nt < n_tiles) {
-            nb0 = P.off[(uint64_t) nt * EB_THREADS];
-            nb1 = P.off[tile_end(nt)];
+            nb0 = __ldg(P.off + (uint64_t) nt * EB_THREADS);
+            nb1 = __ldg(P.off + tile_end(nt));
         }
-        uint64_t r = (uint64_t) tile * EB_THREADS + tid;
-        uint64_t o0 = 0, o1 = 0;
+        mbar_wait(&bar, k & 1);
+        const uint64_t r = (uint64_t) tile * EB_THREADS + tid;
         if (r < P.n) {
-            o0 = P.off[r];
-            o1 = P.off[r + 1];
-        }
-        mbar_wait(&bars[s], parity);
-        const StageMeta m = meta[s];
-        if (r < P.n) {
+            const uint64_t o0 = s_off[tid], o1 = s_off[tid + 1];
             bool f = false, pe = false;
             if (o1 < o0 || o1 - o0 > 0xFFFFFFFFull) {
                 err |= DEV_ERR_BAD_RECORD;
@@ -359,16 +433,18 @@ __global__ void __launch_bounds__(EB_THREADS) endbuild_kernel(EndbuildParams P, 
                 P.hk[r] = 0;
                 P.rgcode[r] = (uint16_t) RGC_ABSENT;
                 P.flag_in[r] = 0;
+            } else if (s_direct) {
+                GlobalRd rd{P.rec + o0};
+                build_end(P, rgt, rd, (uint32_t) (o1 - o0), r, err, f, pe);
             } else {
-                const uint8_t *p = m.direct ? P.rec + o0 : smem + (size_t) s * stage_cap + (o0 - m.a0);
-                build_end(P, p, (uint32_t) (o1 - o0), r, err, f, pe);
+                SharedRd rd{stage_addr + (uint32_t) (o0 - s_a0)};
+                build_end(P, rgt, rd, (uint32_t) (o1 - o0), r, err, f, pe);
             }
             n_frag += f;
             n_pe += pe;
         }
-        __syncthreads();      // everyone is done with stage s (and has read meta[s])
-        // refill; meta[s] is next read EB_STAGES (>= 2) iterations on, behind a later barrier
-        if (tid == 0 && nt < n_tiles) issue(s, nb0, nb1);
+        __syncthreads();      // everyone is done with the stage
+        if (tid == 0 && nt < n_tiles) issue(nt, nb0, nb1);
     }
 
     // counters: one atomic per warp
@@ -386,16 +462,18 @@ __global__ void __launch_bounds__(EB_THREADS) endbuild_kernel(EndbuildParams P, 
 
 int launch_endbuild(const EndbuildParams &P, uint32_t avg_rec_bytes, int sms, cudaStream_t stream, uint64_t *launches) {
     if (P.n == 0) return 0;
-    // stage sized for a typical tile + 25 % (tiles that do not fit are parsed from global memory)
-    uint64_t want = ((uint64_t) avg_rec_bytes * EB_THREADS * 5 / 4 + 1024 + 127) & ~127ull;
-    uint32_t stage_cap = (uint32_t) (want < 16384 ? 16384 : (want > 100 * 1024 ? 100 * 1024 : want));
-    size_t smem = (size_t) stage_cap * EB_STAGES;
-    static size_t configured = 0;
-    if (smem > configured) {
+    if (P.kl.f_orient != P.kl.f_paired + 1 || P.kl.f_lib != P.kl.f_ref + P.kl.ref_bits)
+        return fail_msg(-1, "endbuild: key layout must keep paired|orient and ref|lib adjacent");
+    // stage sized for a typical tile + 6 % (a tile that does not fit is parsed from global memory)
+    uint64_t want = ((uint64_t) avg_rec_bytes * EB_THREADS * 17 / 16 + 512 + 127) & ~127ull;
+    uint32_t stage_cap = (uint32_t) (want < 8192 ? 8192 : (want > 160 * 1024 ? 160 * 1024 : want));
+    size_t smem = (size_t) stage_cap + EB_OFF_BYTES;
+    static bool configured = false;
+    if (!configured) {
         OGE_CUDA_TRY(cudaFuncSetAttribute(endbuild_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (200 * 1024)));
-        configured = 200 * 1024;
+        configured = true;
     }
-    int per_sm = (int) ((220 * 1024) / (smem + 2048));
+    int per_sm = (int) ((224 * 1024) / (smem + 3 * 1024));      // + static shared memory and the per-CTA reserve
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
     uint64_t n_tiles = (P.n + EB_THREADS - 1) / EB_THREADS;

@@ -8,7 +8,7 @@
 // Structure (one read of the input for all histograms, then one read + one write per pass):
 //   rs_histogram      every pass's 256-bin digit histogram in one sweep (shared-memory bins)
 //   rs_scan           exclusive scan of each histogram -> global digit offsets
-//   rs_onesweep_pass  per 4096-entry tile: 128-bit coalesced loads, warp-private digit counters
+//   rs_onesweep_pass  per 2048-entry tile: 128-bit coalesced loads, warp-private digit counters
 //                     ranked with match.any, chained-scan (decoupled look-back) across tiles,
 //                     reorder through shared memory, coalesced 128-bit stores
 // The sort is stable per pass (warp-striped tile order + tile-ordered look-back), which LSD needs.
@@ -21,6 +21,7 @@ namespace oge {
 constexpr uint32_t LB_FLAG_AGG = 1u << 30;      // tile aggregate published
 constexpr uint32_t LB_FLAG_INC = 2u << 30;      // inclusive prefix published
 constexpr uint32_t LB_VALUE_MASK = (1u << 30) - 1;
+constexpr int LB_WINDOW = 8;
 
 SortPlan make_sort_plan(int bit_lo, int bit_hi) {
     SortPlan p;
@@ -115,11 +116,28 @@ __global__ void __launch_bounds__(RS_RADIX) rs_scan(const uint32_t *__restrict__
     goff[p * RS_RADIX + d] = base + x - v;
 }
 
+// Lanes holding the same digit, from one ballot per digit bit (cheaper than match.any on the
+// 8-bit digits: the ncu capture of the first version had every FLO behind a MATCH.ANY stalled).
+// Out-of-range lanes carry 0xFFFFFFFF and are kept apart by a ninth ballot.
+__device__ __forceinline__ uint32_t match_digit(uint32_t d, int bits) {
+    uint32_t peers = __ballot_sync(0xFFFFFFFFu, d != 0xFFFFFFFFu);
+    if (d == 0xFFFFFFFFu) peers = ~peers;
+#pragma unroll
+    for (int b = 0; b < RS_RADIX_BITS; b++) {
+        if (b < bits) {
+            bool bit = (d >> b) & 1;
+            uint32_t v = __ballot_sync(0xFFFFFFFFu, bit);
+            peers &= bit ? v : ~v;
+        }
+    }
+    return peers;
+}
+
 // ------------------------------------------------------------------------------------------------
 // One scatter pass.  Dynamic shared memory: [sorted: RS_TILE * 16 B][warp counters: RS_WARPS * 256 * 4 B]
 constexpr size_t PASS_SMEM = (size_t) RS_TILE * sizeof(E128) + (size_t) RS_WARPS * RS_RADIX * 4;
 
-__global__ void __launch_bounds__(RS_THREADS, 2)
+__global__ void __launch_bounds__(RS_THREADS, 4)
 rs_onesweep_pass(const E128 *__restrict__ in, E128 *__restrict__ out, uint32_t n_max, const uint32_t *__restrict__ n_dev,
                  int shift, int bits, const uint32_t *__restrict__ digit_offset, uint32_t *__restrict__ status,
                  uint32_t *__restrict__ tile_counter) {
@@ -162,7 +180,7 @@ rs_onesweep_pass(const E128 *__restrict__ in, E128 *__restrict__ out, uint32_t n
 #pragma unroll
     for (int k = 0; k < RS_ITEMS; k++) {
         uint32_t d = (wbase + k * 32 < n) ? digit_of(e[k], shift, mask) : 0xFFFFFFFFu;
-        uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+        uint32_t peers = match_digit(d, bits);
         int leader = 31 - __clz(peers);
         uint32_t old = 0;
         if (lane == leader && d != 0xFFFFFFFFu) {
@@ -203,15 +221,28 @@ rs_onesweep_pass(const E128 *__restrict__ in, E128 *__restrict__ out, uint32_t n
 
         uint32_t excl = 0;
         if (tile > 0) {
-            const uint32_t *sp = status + (size_t) (tile - 1) * RS_RADIX + tid;
-            while (true) {
-                uint32_t s;
-                asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(s) : "l"(sp) : "memory");
-                uint32_t f = s >> 30;
-                if (f == 0) continue;
-                excl += s & LB_VALUE_MASK;
-                if (f == 2) break;
-                sp -= RS_RADIX;
+            // decoupled look-back, LB_WINDOW predecessors per round trip: the status words of
+            // tiles t-1 .. t-W are independent loads, so the chain costs one L2 latency per W tiles
+            long long p = (long long) tile - 1;
+            bool done = false;
+            while (!done) {
+                uint32_t s[LB_WINDOW];
+#pragma unroll
+                for (int j = 0; j < LB_WINDOW; j++) {
+                    long long q = p - j;
+                    s[j] = 0;
+                    if (q >= 0)
+                        asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(s[j]) : "l"(status + (size_t) q * RS_RADIX + tid) : "memory");
+                }
+#pragma unroll
+                for (int j = 0; j < LB_WINDOW; j++) {
+                    if (done) break;
+                    uint32_t f = s[j] >> 30;
+                    if (f == 0) break;          // not published yet: poll again from this tile
+                    excl += s[j] & LB_VALUE_MASK;
+                    p--;
+                    if (f == 2) done = true;
+                }
             }
             uint32_t word = LB_FLAG_INC | (excl + total);
             asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(status + (size_t) tile * RS_RADIX + tid), "r"(word) : "memory");

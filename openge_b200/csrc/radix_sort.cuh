@@ -8,9 +8,9 @@ namespace oge {
 constexpr int RS_MAX_PASSES = 16;       // 128 key bits / 8
 constexpr int RS_RADIX_BITS = 8;
 constexpr int RS_RADIX = 1 << RS_RADIX_BITS;
-constexpr int RS_THREADS = 512;
+constexpr int RS_THREADS = 256;
 constexpr int RS_ITEMS = 8;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;      // 4096 entries = 64 KB of shared memory
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;      // 2048 entries = 32 KB of shared memory
 constexpr int RS_WARPS = RS_THREADS / 32;
 
 struct SortPlan {
