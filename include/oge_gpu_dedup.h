@@ -147,6 +147,15 @@ int oge_gpu_dedup_device_ptrs(oge_gpu_dedup_ctx *ctx, void **records, void **off
  * host memory by the bit range [bit_lo, bit_hi), stably, on `device`. */
 int oge_gpu_debug_sort128(int device, void *entries, uint64_t n, int bit_lo, int bit_hi);
 
+/* Measurement hook for K3 alone: sorts n device-generated entries (mode 0 uniform random, 1 = high key
+ * bits follow the ordinal like a coordinate-sorted file) `reps` times after one warm-up; reports the
+ * average CUDA-event time of one pass launch and of the whole sort, and verifies the result on the
+ * device (no key inversion on [bit_lo, bit_hi), order-independent checksums unchanged). */
+int oge_gpu_debug_sort_bench(int device, uint64_t n, int bit_lo, int bit_hi, int variant, int mode, int reps, uint64_t seed,
+                             float *ms_pass_avg, float *ms_sort_avg, int *n_pass, int *verified);
+/* Tuning hook: pass-kernel variant (bit 0: match.any ranking; bit 1: 4096-entry tiles; -1: first-generation kernel). */
+int oge_gpu_set_sort_variant(int variant);
+
 /* Pinned host memory for push/pull buffers. */
 void *oge_gpu_host_alloc(size_t nbytes);
 void oge_gpu_host_free(void *p);

@@ -628,3 +628,130 @@ int oge_gpu_dedup_device_ptrs(oge_gpu_dedup_ctx *c, void **records, void **offse
 }
 
 }  // extern "C"
+
+// ---- K3 measurement hook: device-generated entries, CUDA-event timing, on-device verification ----
+namespace {
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+// mode 0: uniform random bits; mode 1: "coordinate sorted": high key bits grow with i, low bits random
+__global__ void sb_fill(E128 *e, uint64_t n, uint64_t seed, int mode, int bit_lo, int bit_hi) {
+    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    E128 v;
+    v.lo = mix64(seed + 2 * i);
+    v.hi = mix64(seed + 2 * i + 1);
+    if (mode == 1) {
+        int kb = bit_hi - bit_lo;
+        int top = kb > 24 ? 24 : kb;      // top bits follow the ordinal
+        uint64_t t = (uint64_t) ((double) i / (double) n * (double) (1ull << top));
+        E128 m;      // clear then set bits [bit_hi - top, bit_hi)
+        m.lo = m.hi = 0;
+        bits_or(m, bit_hi - top, (1ull << top) - 1);
+        v.lo &= ~m.lo; v.hi &= ~m.hi;
+        bits_or(v, bit_hi - top, t);
+    }
+    e[i] = v;
+}
+
+// sum and xor of all words (order independent) + count of adjacent key inversions
+__global__ void sb_check(const E128 *e, uint64_t n, int bit_lo, int bit_hi, unsigned long long *out /* [4] */) {
+    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long sum = 0, x = 0, inv = 0;
+    if (i < n) {
+        E128 a = e[i];
+        sum = a.lo + 3 * a.hi;
+        x = a.lo ^ (a.hi * 0x9E3779B97F4A7C15ull);
+        if (i + 1 < n) {
+            E128 b = e[i + 1];
+            E128 ka = bits_from(a, bit_lo), kb = bits_from(b, bit_lo);
+            int w = bit_hi - bit_lo;
+            if (w < 128) {
+                if (w <= 64) { uint64_t m = w == 64 ? ~0ull : (1ull << w) - 1; ka.lo &= m; kb.lo &= m; ka.hi = kb.hi = 0; }
+                else { uint64_t m = (1ull << (w - 64)) - 1; ka.hi &= m; kb.hi &= m; }
+            }
+            inv = (ka.hi > kb.hi || (ka.hi == kb.hi && ka.lo > kb.lo)) ? 1 : 0;
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+        x ^= __shfl_xor_sync(0xFFFFFFFFu, x, o);
+        inv += __shfl_xor_sync(0xFFFFFFFFu, inv, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&out[0], sum);
+        atomicXor(&out[1], x);
+        atomicAdd(&out[2], inv);
+    }
+}
+
+}  // namespace
+
+extern "C" int oge_gpu_debug_sort_bench(int device, uint64_t n, int bit_lo, int bit_hi, int variant, int mode, int reps,
+                                        uint64_t seed, float *ms_pass_avg, float *ms_sort_avg, int *n_pass, int *verified) {
+    if (!ms_pass_avg || !ms_sort_avg || !n_pass || !verified || n == 0 || bit_lo < 0 || bit_hi > 128 || bit_lo >= bit_hi || reps < 1)
+        return fail_msg(OGE_ERR_INVALID_ARG, "debug_sort_bench: bad argument");
+    if (oge_gpu_device_count() <= 0) return fail_msg(OGE_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    OGE_CUDA_TRY(cudaSetDevice(device));
+    int rc = radix_sort_init();
+    if (rc) return rc;
+    const int saved = radix_sort_get_variant();
+    radix_sort_set_variant(variant);
+    DevBuf<E128> a, b;
+    DevBuf<uint8_t> scratch;
+    DevBuf<unsigned long long> chk;
+    cudaEvent_t ev[2 * 48 + 2];
+    for (auto &e : ev) cudaEventCreate(&e);
+    uint64_t launches = 0;
+    float pass_ms = 0, sort_ms = 0;
+    int passes = 0, ok = 1;
+    do {
+        if ((rc = a.reserve(n, false, 0)) || (rc = b.reserve(n, false, 0)) || (rc = scratch.reserve(sort_scratch_bytes(n), false, 0)) ||
+            (rc = chk.reserve(8, false, 0)))
+            break;
+        const uint32_t grid = (uint32_t) ((n + 255) / 256);
+        for (int r = 0; r < reps + 1 && !rc; r++) {      // first repetition is warm-up
+            unsigned long long h0[4], h1[4];
+            sb_fill<<<grid, 256>>>(a.p, n, seed + r, mode, bit_lo, bit_hi);
+            cudaMemset(chk.p, 0, 64);
+            sb_check<<<grid, 256>>>(a.p, n, bit_lo, bit_hi, chk.p);
+            cudaMemcpy(h0, chk.p, 32, cudaMemcpyDeviceToHost);
+            PassTimer timer{ev + 2, 48, 0, 0};
+            E128 *res = nullptr;
+            cudaEventRecord(ev[0], 0);
+            rc = radix_sort_128(a.p, b.p, n, nullptr, bit_lo, bit_hi, scratch.p, 0, &res, &launches, &timer);
+            cudaEventRecord(ev[1], 0);
+            if (rc) break;
+            if (cudaDeviceSynchronize() != cudaSuccess) { rc = fail_cuda(cudaGetLastError(), "sort bench sync", __FILE__, __LINE__); break; }
+            cudaMemset(chk.p, 0, 64);
+            sb_check<<<grid, 256>>>(res, n, bit_lo, bit_hi, chk.p);
+            cudaMemcpy(h1, chk.p, 32, cudaMemcpyDeviceToHost);
+            if (h0[0] != h1[0] || h0[1] != h1[1] || h1[2] != 0) ok = 0;
+            if (r > 0) {
+                sort_ms += ms_between(ev[0], ev[1]);
+                for (int i = 0; i < timer.used; i++) pass_ms += ms_between(ev[2 + 2 * i], ev[2 + 2 * i + 1]);
+                passes = timer.used;
+            }
+        }
+    } while (0);
+    for (auto &e : ev) cudaEventDestroy(e);
+    a.release(); b.release(); scratch.release(); chk.release();
+    radix_sort_set_variant(saved);
+    if (rc) return rc;
+    *ms_pass_avg = passes ? pass_ms / (reps * passes) : 0;
+    *ms_sort_avg = sort_ms / reps;
+    *n_pass = passes;
+    *verified = ok;
+    return OGE_OK;
+}
+
+extern "C" int oge_gpu_set_sort_variant(int variant) {
+    if (variant < -1 || variant > 63) return fail_msg(OGE_ERR_INVALID_ARG, "set_sort_variant: %d", variant);
+    radix_sort_set_variant(variant);
+    return OGE_OK;
+}

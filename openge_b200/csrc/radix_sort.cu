@@ -277,8 +277,254 @@ rs_onesweep_pass(const E128 *__restrict__ in, E128 *__restrict__ out, uint32_t n
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Second-generation pass kernel.  The first one was issue-bound (ncu: 60 % issue slots busy, ~2000
+// warp instructions per warp and tile, dram at 25 %), so this one is written for instruction count:
+//   * the digit comes out of a 32-bit word pair chosen at compile time (WORD = shift / 32):
+//     one funnel shift + one AND instead of a 128-bit variable shift, and it is computed once
+//   * full tiles take a path without any bounds predicate
+//   * the warp ranking is either eight ballots or one match.any per entry (MATCH); the group
+//     leader bumps the warp-private counter with a single shared-memory atomic
+//   * 32-bit scatter deltas
+//   * THREADS = 256 or 512: tile = THREADS * 8 entries; a larger tile halves the look-backs per
+//     entry and doubles the length of the contiguous runs written to HBM
+template <int WORD>
+__device__ __forceinline__ uint32_t digit_word(const E128 &e, int sh, uint32_t mask) {
+    uint32_t a, b;
+    if (WORD == 0) { a = (uint32_t) e.lo; b = (uint32_t) (e.lo >> 32); }
+    else if (WORD == 1) { a = (uint32_t) (e.lo >> 32); b = (uint32_t) e.hi; }
+    else if (WORD == 2) { a = (uint32_t) e.hi; b = (uint32_t) (e.hi >> 32); }
+    else { a = (uint32_t) (e.hi >> 32); b = 0; }
+    return __funnelshift_r(a, b, sh) & mask;
+}
+
+// lanes of the warp holding the same 8-bit digit (all lanes valid)
+template <int MATCH>
+__device__ __forceinline__ uint32_t peers_of(uint32_t d) {
+    if (MATCH) return __match_any_sync(0xFFFFFFFFu, d);
+    uint32_t peers = 0xFFFFFFFFu;
+#pragma unroll
+    for (int b = 0; b < RS_RADIX_BITS; b++) {
+        uint32_t v;
+        asm("{\n .reg .pred p;\n .reg .b32 t;\n and.b32 t, %1, %2;\n setp.ne.u32 p, t, 0;\n vote.sync.ballot.b32 %0, p, 0xffffffff;\n"
+            " @!p not.b32 %0, %0;\n}\n"
+            : "=r"(v)
+            : "r"(d), "r"(1u << b));
+        peers &= v;
+    }
+    return peers;
+}
+
+template <int THREADS>
+struct PassCfg {
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr int TILE = THREADS * RS_ITEMS;
+    static constexpr size_t SMEM = (size_t) TILE * sizeof(E128) + (size_t) WARPS * RS_RADIX * 4;
+    static constexpr int CTAS_PER_SM = THREADS == 256 ? 4 : 2;
+};
+
+template <int THREADS, int WORD, int MATCH>
+__global__ void __launch_bounds__(THREADS, PassCfg<THREADS>::CTAS_PER_SM)
+rs_pass_v2(const E128 *__restrict__ in, E128 *__restrict__ out, uint32_t n_max, const uint32_t *__restrict__ n_dev, int shift,
+           int bits, const uint32_t *__restrict__ digit_offset, uint32_t *__restrict__ status, uint32_t *__restrict__ tile_counter,
+           int dbg) {
+    using Cfg = PassCfg<THREADS>;
+    constexpr int WARPS = Cfg::WARPS, TILE = Cfg::TILE;
+    static_assert(THREADS >= RS_RADIX, "one thread per digit in the scan phase");
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    E128 *s_sorted = reinterpret_cast<E128 *>(smem_raw);
+    uint32_t *s_warp_cnt = reinterpret_cast<uint32_t *>(smem_raw + (size_t) TILE * sizeof(E128));
+    __shared__ uint32_t s_tile_base[RS_RADIX];
+    __shared__ int s_delta[RS_RADIX];
+    __shared__ uint32_t s_scan[RS_RADIX / 32];
+    __shared__ uint32_t s_tile;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n = n_dev ? min(*n_dev, n_max) : n_max;
+    const uint32_t n_tiles = (n + TILE - 1) / TILE;
+    const uint32_t mask = (1u << bits) - 1;
+    const int sh = shift & 31;
+    uint32_t *wc = s_warp_cnt + warp * RS_RADIX;
+
+    // tile ids in launch order: every predecessor of a tile is running or done (look-back cannot starve)
+    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+    {
+        uint4 z = make_uint4(0, 0, 0, 0);
+        reinterpret_cast<uint4 *>(wc)[lane] = z;
+        reinterpret_cast<uint4 *>(wc)[lane + 32] = z;
+    }
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if (tile >= n_tiles) return;
+    const uint32_t base = tile * TILE;
+    const bool full = base + TILE <= n;
+    const uint32_t count = full ? (uint32_t) TILE : n - base;
+
+    // ---- load (warp-striped: 512 B contiguous per warp instruction) + digits
+    E128 e[RS_ITEMS];
+    uint32_t d[RS_ITEMS], rank[RS_ITEMS];
+    const uint32_t wslot = warp * (32 * RS_ITEMS) + lane;      // slot of item 0 inside the tile
+    const E128 *src = in + base + wslot;
+    if (full) {
+#pragma unroll
+        for (int k = 0; k < RS_ITEMS; k++) e[k] = ld_entry(src + k * 32);
+#pragma unroll
+        for (int k = 0; k < RS_ITEMS; k++) d[k] = digit_word<WORD>(e[k], sh, mask);
+    } else {
+#pragma unroll
+        for (int k = 0; k < RS_ITEMS; k++) {
+            d[k] = 0xFFFFFFFFu;
+            if (wslot + k * 32 < count) {
+                e[k] = ld_entry(src + k * 32);
+                d[k] = digit_word<WORD>(e[k], sh, mask);
+            }
+        }
+    }
+
+    // ---- rank inside the warp
+    const uint32_t lt_mask = (1u << lane) - 1;
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; k++) {
+        uint32_t peers;
+        if (MATCH || full) peers = peers_of<MATCH>(d[k]);
+        else peers = match_digit(d[k], RS_RADIX_BITS);
+        const int leader = 31 - __clz(peers);
+        uint32_t old = 0;
+        if (lane == leader && (full || d[k] != 0xFFFFFFFFu)) old = atomicAdd(&wc[d[k]], (uint32_t) __popc(peers));
+        old = __shfl_sync(0xFFFFFFFFu, old, leader);
+        rank[k] = old + __popc(peers & lt_mask);
+    }
+    __syncthreads();
+
+    // ---- per digit: exclusive scan over warps, tile total, publish the aggregate, block scan
+    uint32_t total = 0;
+    uint32_t *my_status = status + (size_t) tile * RS_RADIX + tid;
+    if (tid < RS_RADIX) {
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) {
+            uint32_t c = s_warp_cnt[w * RS_RADIX + tid];
+            s_warp_cnt[w * RS_RADIX + tid] = total;
+            total += c;
+        }
+        {
+            uint32_t word = (tile == 0 ? LB_FLAG_INC : LB_FLAG_AGG) | total;
+            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(my_status), "r"(word) : "memory");
+        }
+        uint32_t x = total;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_scan[warp] = x;
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // the eight digit warps only
+        uint32_t wprefix = 0;
+#pragma unroll
+        for (int i = 0; i < RS_RADIX / 32; i++) wprefix += i < warp ? s_scan[i] : 0u;
+        s_tile_base[tid] = wprefix + x - total;
+    }
+
+    // decoupled look-back over the predecessors' status words (LB_WINDOW independent loads per round
+    // trip), then the scatter delta of this digit.  It runs AFTER the shared-memory reorder: the
+    // aggregate above is already visible to the successors, and the later this tile looks back the
+    // more of its predecessors have published, so fewer polls come back empty.
+    auto look_back = [&]() {
+        uint32_t excl = 0;
+        if (tile > 0 && !(dbg & 1)) {
+            const uint32_t *q = my_status - RS_RADIX;      // predecessor's word for this digit
+            uint32_t left = tile;                          // predecessors not yet folded in
+            while (true) {
+                uint32_t s[LB_WINDOW];
+#pragma unroll
+                for (int j = 0; j < LB_WINDOW; j++) {
+                    s[j] = 0;
+                    if ((uint32_t) j < left) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(s[j]) : "l"(q - j * RS_RADIX) : "memory");
+                }
+                bool done = false;
+                int used = 0;
+#pragma unroll
+                for (int j = 0; j < LB_WINDOW; j++) {
+                    uint32_t f = s[j] >> 30;
+                    if (!done && used == j && f != 0) {
+                        excl += s[j] & LB_VALUE_MASK;
+                        used = j + 1;
+                        done = f == 2;
+                    }
+                }
+                if (done) break;
+                q -= used * RS_RADIX;
+                left -= used;
+                if (used < LB_WINDOW) __nanosleep(20);
+            }
+            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(my_status), "r"(LB_FLAG_INC | (excl + total)) : "memory");
+        }
+        s_delta[tid] = (dbg & 2) ? (int) base : (int) (digit_offset[tid] + excl) - (int) s_tile_base[tid];
+    };
+    const bool late = !(dbg & 4);
+    if (!late && tid < RS_RADIX) look_back();
+    __syncthreads();
+
+    // ---- reorder through shared memory
+    if (full) {
+#pragma unroll
+        for (int k = 0; k < RS_ITEMS; k++) st_entry(s_sorted + (s_tile_base[d[k]] + wc[d[k]] + rank[k]), e[k]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < RS_ITEMS; k++)
+            if (d[k] != 0xFFFFFFFFu) st_entry(s_sorted + (s_tile_base[d[k]] + wc[d[k]] + rank[k]), e[k]);
+    }
+    if (late && tid < RS_RADIX) look_back();
+    __syncthreads();
+
+    // ---- store: consecutive threads write consecutive sorted slots; a digit's run is contiguous in the output
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; k++) {
+        const uint32_t j = k * THREADS + tid;
+        if (full || j < count) {
+            ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(s_sorted + j);
+            E128 ev;
+            ev.lo = v.x;
+            ev.hi = v.y;
+            st_entry(out + ((int) j + s_delta[digit_word<WORD>(ev, sh, mask)]), ev);
+        }
+    }
+}
+
+// variant: bit 0 = match.any ranking, bit 1 = 512-thread tiles; -1 = the first-generation kernel
+static int g_sort_variant = 0;
+void radix_sort_set_variant(int v) { g_sort_variant = v; }
+int radix_sort_get_variant() { return g_sort_variant; }
+
+template <int THREADS, int MATCH>
+static cudaError_t launch_pass_v2(int word, uint32_t grid, cudaStream_t stream, const E128 *src, E128 *dst, uint32_t n,
+                                  const uint32_t *n_dev, int shift, int bits, const uint32_t *goff, uint32_t *status, uint32_t *tc, int dbg) {
+    const size_t smem = PassCfg<THREADS>::SMEM;
+    switch (word) {
+        case 0: rs_pass_v2<THREADS, 0, MATCH><<<grid, THREADS, smem, stream>>>(src, dst, n, n_dev, shift, bits, goff, status, tc, dbg); break;
+        case 1: rs_pass_v2<THREADS, 1, MATCH><<<grid, THREADS, smem, stream>>>(src, dst, n, n_dev, shift, bits, goff, status, tc, dbg); break;
+        case 2: rs_pass_v2<THREADS, 2, MATCH><<<grid, THREADS, smem, stream>>>(src, dst, n, n_dev, shift, bits, goff, status, tc, dbg); break;
+        default: rs_pass_v2<THREADS, 3, MATCH><<<grid, THREADS, smem, stream>>>(src, dst, n, n_dev, shift, bits, goff, status, tc, dbg); break;
+    }
+    return cudaGetLastError();
+}
+
+template <int THREADS, int MATCH>
+static cudaError_t init_pass_v2() {
+    const int smem = (int) PassCfg<THREADS>::SMEM;
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(rs_pass_v2<THREADS, 0, MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(rs_pass_v2<THREADS, 1, MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(rs_pass_v2<THREADS, 2, MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(rs_pass_v2<THREADS, 3, MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
 int radix_sort_init() {
     OGE_CUDA_TRY(cudaFuncSetAttribute(rs_onesweep_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) PASS_SMEM));
+    OGE_CUDA_TRY((init_pass_v2<256, 0>()));
+    OGE_CUDA_TRY((init_pass_v2<256, 1>()));
+    OGE_CUDA_TRY((init_pass_v2<512, 0>()));
+    OGE_CUDA_TRY((init_pass_v2<512, 1>()));
     return 0;
 }
 
@@ -305,12 +551,25 @@ int radix_sort_128(E128 *a, E128 *b, uint64_t n, const uint32_t *n_dev, int bit_
     *launches += 2;
 
     E128 *src = a, *dst = b;
+    const int dbg = g_sort_variant >= 0 ? (g_sort_variant >> 4) : 0;      // measurement only: results are wrong
+    const int variant = g_sort_variant >= 0 ? (g_sort_variant & 15) : -1;
+    const uint64_t vtiles = variant >= 0 && (variant & 2) ? (n + PassCfg<512>::TILE - 1) / PassCfg<512>::TILE : tiles;
     for (int p = 0; p < plan.n_pass; p++) {
-        OGE_CUDA_TRY(cudaMemsetAsync(status, 0, (size_t) tiles * RS_RADIX * 4, stream));
+        OGE_CUDA_TRY(cudaMemsetAsync(status, 0, (size_t) vtiles * RS_RADIX * 4, stream));
         const bool timed = timer && timer->used < timer->cap;
         if (timed) cudaEventRecord(timer->pool[2 * timer->used], stream);
-        rs_onesweep_pass<<<(uint32_t) tiles, RS_THREADS, PASS_SMEM, stream>>>(
-            src, dst, (uint32_t) n, n_dev, plan.shift[p], plan.bits[p], goff + p * RS_RADIX, status, tile_counters + p);
+        const int shift = plan.shift[p], bits = plan.bits[p];
+        uint32_t *tc = tile_counters + p;
+        const uint32_t *go = goff + p * RS_RADIX;
+        switch (variant) {
+            case 0: OGE_CUDA_TRY((launch_pass_v2<256, 0>(shift >> 5, (uint32_t) vtiles, stream, src, dst, (uint32_t) n, n_dev, shift, bits, go, status, tc, dbg))); break;
+            case 1: OGE_CUDA_TRY((launch_pass_v2<256, 1>(shift >> 5, (uint32_t) vtiles, stream, src, dst, (uint32_t) n, n_dev, shift, bits, go, status, tc, dbg))); break;
+            case 2: OGE_CUDA_TRY((launch_pass_v2<512, 0>(shift >> 5, (uint32_t) vtiles, stream, src, dst, (uint32_t) n, n_dev, shift, bits, go, status, tc, dbg))); break;
+            case 3: OGE_CUDA_TRY((launch_pass_v2<512, 1>(shift >> 5, (uint32_t) vtiles, stream, src, dst, (uint32_t) n, n_dev, shift, bits, go, status, tc, dbg))); break;
+            default:
+                rs_onesweep_pass<<<(uint32_t) tiles, RS_THREADS, PASS_SMEM, stream>>>(src, dst, (uint32_t) n, n_dev, shift, bits, go, status, tc);
+                break;
+        }
         if (timed) {
             cudaEventRecord(timer->pool[2 * timer->used + 1], stream);
             timer->used++;

@@ -55,7 +55,8 @@ EXPORTS = ["oge_gpu_dedup_create", "oge_gpu_dedup_destroy", "oge_gpu_dedup_set_r
            "oge_gpu_dedup_sync", "oge_gpu_dedup_run", "oge_gpu_dedup_flags", "oge_gpu_dedup_pull",
            "oge_gpu_dedup_reset", "oge_gpu_dedup_get_stats", "oge_gpu_dedup_debug_ends",
            "oge_gpu_dedup_device_ptrs", "oge_gpu_host_alloc", "oge_gpu_host_free", "oge_gpu_device_count",
-           "oge_gpu_last_error", "oge_gpu_abi_version", "oge_gpu_debug_sort128"]
+           "oge_gpu_last_error", "oge_gpu_abi_version", "oge_gpu_debug_sort128", "oge_gpu_debug_sort_bench",
+           "oge_gpu_set_sort_variant"]
 
 
 class DedupError(RuntimeError):
@@ -95,6 +96,9 @@ def lib():
         L.oge_gpu_host_free.restype = None
         L.oge_gpu_last_error.restype = C.c_char_p
         L.oge_gpu_debug_sort128.argtypes = [C.c_int, vp, u64, C.c_int, C.c_int]
+        L.oge_gpu_debug_sort_bench.argtypes = [C.c_int, u64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u64,
+                                               C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.oge_gpu_set_sort_variant.argtypes = [C.c_int]
         for name in EXPORTS:
             getattr(L, name)
         _lib = L
@@ -115,6 +119,22 @@ def debug_sort128(entries: np.ndarray, bit_lo: int, bit_hi: int, device: int = 0
     e = np.ascontiguousarray(entries, dtype=np.uint64).copy()
     _check(lib().oge_gpu_debug_sort128(device, e.ctypes.data, len(e), bit_lo, bit_hi))
     return e
+
+
+def set_sort_variant(variant: int):
+    """Tuning hook: which onesweep pass kernel runs (see radix_sort.cuh)."""
+    _check(lib().oge_gpu_set_sort_variant(variant))
+
+
+def debug_sort_bench(n, bit_lo, bit_hi, variant=0, mode=0, reps=3, seed=1, device=0) -> dict:
+    """K3 alone on device-generated entries: CUDA-event time per pass launch and per whole sort,
+    verified on the device (sortedness on the bit range + order-independent checksums)."""
+    ms_pass, ms_sort, n_pass, ok = C.c_float(), C.c_float(), C.c_int(), C.c_int()
+    _check(lib().oge_gpu_debug_sort_bench(device, n, bit_lo, bit_hi, variant, mode, reps, seed, C.byref(ms_pass),
+                                          C.byref(ms_sort), C.byref(n_pass), C.byref(ok)))
+    return {"n": n, "bits": [bit_lo, bit_hi], "variant": variant, "mode": mode, "ms_per_pass": ms_pass.value,
+            "ms_sort": ms_sort.value, "passes": n_pass.value, "verified": bool(ok.value),
+            "pass_GBps": n * 32 / 1e9 / (ms_pass.value * 1e-3) if ms_pass.value > 0 else None}
 
 
 class PinnedBuffer:

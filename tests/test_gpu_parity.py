@@ -41,6 +41,35 @@ def test_radix_sort_matches_numpy(n, lo, hi):
     assert all(k_out[i] <= k_out[i + 1] for i in range(n - 1))
 
 
+@pytest.mark.parametrize("variant", [-1, 0, 1, 2, 3])
+@pytest.mark.parametrize("n,lo,hi", [(2048, 0, 8), (4099, 30, 41), (1_000_003, 42, 112)])
+def test_radix_sort_variants_stable(variant, n, lo, hi):
+    """Every pass-kernel variant is a stable sort on the bit range (LSD needs per-pass stability)."""
+    rng = np.random.default_rng(n + variant)
+    e = rng.integers(0, 2**64, size=(n, 2), dtype=np.uint64)
+    e[: n // 4, 1] = e[0, 1]
+    e[: n // 4, 0] &= np.uint64((1 << 40) - 1)
+    dedup.set_sort_variant(variant)
+    try:
+        out = dedup.debug_sort128(e, lo, hi)
+    finally:
+        dedup.set_sort_variant(0)
+    v = (e[:, 1].astype(object) << 64) | e[:, 0].astype(object)
+    k = np.array([int((x >> lo) & ((1 << (hi - lo)) - 1)) >> max(0, hi - lo - 63) for x in v], dtype=np.uint64)
+    if hi - lo <= 63:
+        order = np.argsort(k, kind="stable")
+    else:
+        kk = [(x >> lo) & ((1 << (hi - lo)) - 1) for x in v]
+        order = sorted(range(n), key=lambda i: (kk[i], i))
+    assert np.array_equal(out, e[order])
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+def test_sort_bench_hook_verifies(variant):
+    r = dedup.debug_sort_bench(3_000_001, 43, 79, variant=variant, mode=1, reps=1)
+    assert r["verified"] and r["passes"] == 5
+
+
 # ------------------------------------------------------------------ full path vs golden / oracle
 @pytest.mark.parametrize("case", GOLDEN_CASES)
 def test_flags_match_reference_golden(case):
