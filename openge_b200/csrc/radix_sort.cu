@@ -36,9 +36,10 @@ SortPlan make_sort_plan(int bit_lo, int bit_hi) {
 
 static inline uint64_t tiles_of(uint64_t n) { return (n + RS_TILE - 1) / RS_TILE; }
 
-// scratch: [hist: MAXP*256 u32][offsets: MAXP*256 u32][tile counters: MAXP u32 (+pad)][status: tiles*256 u32]
+// scratch: [hist: MAXP*256 u32][offsets: MAXP*256 u32][tile counters: MAXP u32 (+pad)][status: 2 x tiles*256 u32]
+// (two status arrays: pass p works on one while its tiles zero the other for pass p+1)
 size_t sort_scratch_bytes(uint64_t n) {
-    return (size_t) (2 * RS_MAX_PASSES * RS_RADIX + 64) * 4 + (size_t) tiles_of(n) * RS_RADIX * 4;
+    return (size_t) (2 * RS_MAX_PASSES * RS_RADIX + 64) * 4 + (size_t) 2 * tiles_of(n) * RS_RADIX * 4;
 }
 
 __device__ __forceinline__ E128 ld_entry(const E128 *p) {
@@ -63,7 +64,11 @@ __global__ void __launch_bounds__(HIST_THREADS) rs_histogram(const E128 *__restr
                                                               uint32_t *__restrict__ ghist) {
     __shared__ uint32_t sh[RS_MAX_PASSES * RS_RADIX];
     const uint32_t n = n_dev ? min(*n_dev, n_max) : n_max;
-    for (int i = threadIdx.x; i < plan.n_pass * RS_RADIX; i += HIST_THREADS) sh[i] = 0;
+    const int n_pass = plan.n_pass, bit_lo = plan.shift[0];
+    const int width = plan.shift[n_pass - 1] + plan.bits[n_pass - 1] - bit_lo;      // key bits, 1..128
+    const uint64_t mask_lo = width >= 64 ? ~0ull : (1ull << width) - 1;
+    const uint64_t mask_hi = width >= 128 ? ~0ull : (width > 64 ? (1ull << (width - 64)) - 1 : 0ull);
+    for (int i = threadIdx.x; i < n_pass * RS_RADIX; i += HIST_THREADS) sh[i] = 0;
     __syncthreads();
 
     const uint32_t chunk = HIST_THREADS * HIST_UNROLL;
@@ -79,15 +84,23 @@ __global__ void __launch_bounds__(HIST_THREADS) rs_histogram(const E128 *__restr
         }
 #pragma unroll
         for (int k = 0; k < HIST_UNROLL; k++) {
-            for (int p = 0; p < plan.n_pass; p++) {
-                uint32_t d = ok[k] ? digit_of(e[k], plan.shift[p], (1u << plan.bits[p]) - 1) : 0xFFFFFFFFu;
-                // coordinate-sorted input makes the high digits warp-uniform: one add per warp then
-                int uniform;
-                __match_all_sync(0xFFFFFFFFu, d, &uniform);
-                if (uniform) {
-                    if ((threadIdx.x & 31) == 0 && ok[k]) atomicAdd(&sh[p * RS_RADIX + d], 32u);
-                } else if (ok[k]) {
-                    atomicAdd(&sh[p * RS_RADIX + d], 1u);
+            // the key, shifted down to bit 0 and cut at its width: digit p is then simply byte p
+            E128 key = bits_from(e[k], bit_lo);
+            key.lo &= mask_lo;
+            key.hi &= mask_hi;
+            const uint32_t w[4] = {(uint32_t) key.lo, (uint32_t) (key.lo >> 32), (uint32_t) key.hi, (uint32_t) (key.hi >> 32)};
+#pragma unroll
+            for (int p = 0; p < RS_MAX_PASSES; p++) {
+                if (p < n_pass) {      // uniform
+                    uint32_t d = ok[k] ? ((w[p >> 2] >> (8 * (p & 3))) & 0xFFu) : 0xFFFFFFFFu;
+                    // coordinate-sorted input makes the high digits warp-uniform: one add per warp then
+                    int uniform;
+                    __match_all_sync(0xFFFFFFFFu, d, &uniform);
+                    if (uniform) {
+                        if ((threadIdx.x & 31) == 0 && ok[k]) atomicAdd(&sh[p * RS_RADIX + d], 32u);
+                    } else if (ok[k]) {
+                        atomicAdd(&sh[p * RS_RADIX + d], 1u);
+                    }
                 }
             }
         }
@@ -327,8 +340,8 @@ struct PassCfg {
 template <int THREADS, int WORD, int MATCH>
 __global__ void __launch_bounds__(THREADS, PassCfg<THREADS>::CTAS_PER_SM)
 rs_pass_v2(const E128 *__restrict__ in, E128 *__restrict__ out, uint32_t n_max, const uint32_t *__restrict__ n_dev, int shift,
-           int bits, const uint32_t *__restrict__ digit_offset, uint32_t *__restrict__ status, uint32_t *__restrict__ tile_counter,
-           int dbg) {
+           int bits, const uint32_t *__restrict__ digit_offset, uint32_t *__restrict__ status, uint32_t *__restrict__ status_next,
+           uint32_t *__restrict__ tile_counter, int dbg) {
     using Cfg = PassCfg<THREADS>;
     constexpr int WARPS = Cfg::WARPS, TILE = Cfg::TILE;
     static_assert(THREADS >= RS_RADIX, "one thread per digit in the scan phase");
@@ -360,6 +373,17 @@ rs_pass_v2(const E128 *__restrict__ in, E128 *__restrict__ out, uint32_t n_max, 
     const uint32_t base = tile * TILE;
     const bool full = base + TILE <= n;
     const uint32_t count = full ? (uint32_t) TILE : n - base;
+
+    // pull the tile that the CTA replacing this one will work on from HBM into L2 now, so that its
+    // loads pay L2 latency instead of DRAM latency (gridDim tiles = one wave ahead is too far for
+    // nothing: the L2 holds 126 MB, a wave is < 20 MB)
+    if (tid == 0 && !(dbg & 8)) {
+        const uint32_t ahead = tile + (uint32_t) (dbg >> 8);
+        if (ahead < n_tiles) {
+            const uint32_t bytes = min((uint32_t) TILE, n - ahead * TILE) * (uint32_t) sizeof(E128);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(in + (size_t) ahead * TILE), "r"(bytes) : "memory");
+        }
+    }
 
     // ---- load (warp-striped: 512 B contiguous per warp instruction) + digits
     E128 e[RS_ITEMS];
@@ -401,6 +425,7 @@ rs_pass_v2(const E128 *__restrict__ in, E128 *__restrict__ out, uint32_t n_max, 
     uint32_t total = 0;
     uint32_t *my_status = status + (size_t) tile * RS_RADIX + tid;
     if (tid < RS_RADIX) {
+        status_next[(size_t) tile * RS_RADIX + tid] = 0;      // the next pass finds its status array cleared
 #pragma unroll
         for (int w = 0; w < WARPS; w++) {
             uint32_t c = s_warp_cnt[w * RS_RADIX + tid];
@@ -492,19 +517,22 @@ rs_pass_v2(const E128 *__restrict__ in, E128 *__restrict__ out, uint32_t n_max, 
 }
 
 // variant: bit 0 = match.any ranking, bit 1 = 512-thread tiles; -1 = the first-generation kernel
-static int g_sort_variant = 0;
+static int g_sort_variant = 2;
+static int g_sort_prefetch = 0;      // tiles ahead (0 = one wave)
+void radix_sort_set_prefetch(int tiles) { g_sort_prefetch = tiles; }
 void radix_sort_set_variant(int v) { g_sort_variant = v; }
 int radix_sort_get_variant() { return g_sort_variant; }
 
 template <int THREADS, int MATCH>
 static cudaError_t launch_pass_v2(int word, uint32_t grid, cudaStream_t stream, const E128 *src, E128 *dst, uint32_t n,
-                                  const uint32_t *n_dev, int shift, int bits, const uint32_t *goff, uint32_t *status, uint32_t *tc, int dbg) {
+                                  const uint32_t *n_dev, int shift, int bits, const uint32_t *goff, uint32_t *status, uint32_t *status_next, uint32_t *tc,
+                                  int dbg) {
     const size_t smem = PassCfg<THREADS>::SMEM;
     switch (word) {
-        case 0: rs_pass_v2<THREADS, 0, MATCH><<<grid, THREADS, smem, stream>>>(src, dst, n, n_dev, shift, bits, goff, status, tc, dbg); break;
-        case 1: rs_pass_v2<THREADS, 1, MATCH><<<grid, THREADS, smem, stream>>>(src, dst, n, n_dev, shift, bits, goff, status, tc, dbg); break;
-        case 2: rs_pass_v2<THREADS, 2, MATCH><<<grid, THREADS, smem, stream>>>(src, dst, n, n_dev, shift, bits, goff, status, tc, dbg); break;
-        default: rs_pass_v2<THREADS, 3, MATCH><<<grid, THREADS, smem, stream>>>(src, dst, n, n_dev, shift, bits, goff, status, tc, dbg); break;
+        case 0: rs_pass_v2<THREADS, 0, MATCH><<<grid, THREADS, smem, stream>>>(src, dst, n, n_dev, shift, bits, goff, status, status_next, tc, dbg); break;
+        case 1: rs_pass_v2<THREADS, 1, MATCH><<<grid, THREADS, smem, stream>>>(src, dst, n, n_dev, shift, bits, goff, status, status_next, tc, dbg); break;
+        case 2: rs_pass_v2<THREADS, 2, MATCH><<<grid, THREADS, smem, stream>>>(src, dst, n, n_dev, shift, bits, goff, status, status_next, tc, dbg); break;
+        default: rs_pass_v2<THREADS, 3, MATCH><<<grid, THREADS, smem, stream>>>(src, dst, n, n_dev, shift, bits, goff, status, status_next, tc, dbg); break;
     }
     return cudaGetLastError();
 }
@@ -551,23 +579,29 @@ int radix_sort_128(E128 *a, E128 *b, uint64_t n, const uint32_t *n_dev, int bit_
     *launches += 2;
 
     E128 *src = a, *dst = b;
-    const int dbg = g_sort_variant >= 0 ? (g_sort_variant >> 4) : 0;      // measurement only: results are wrong
+    // dbg bits 0-2 are measurement knobs (bits 0, 1 give wrong results); bits 8.. = prefetch distance in tiles
+    int dbg = g_sort_variant >= 0 ? ((g_sort_variant >> 4) & 15) : 0;
     const int variant = g_sort_variant >= 0 ? (g_sort_variant & 15) : -1;
     const uint64_t vtiles = variant >= 0 && (variant & 2) ? (n + PassCfg<512>::TILE - 1) / PassCfg<512>::TILE : tiles;
+    {
+        int pf = g_sort_prefetch > 0 ? g_sort_prefetch : sms * (variant >= 0 && (variant & 2) ? 2 : 4);
+        dbg |= pf << 8;
+    }
     for (int p = 0; p < plan.n_pass; p++) {
-        OGE_CUDA_TRY(cudaMemsetAsync(status, 0, (size_t) vtiles * RS_RADIX * 4, stream));
+        uint32_t *st = status + (size_t) (p & 1) * tiles * RS_RADIX, *st_next = status + (size_t) ((p + 1) & 1) * tiles * RS_RADIX;
+        if (p == 0 || variant < 0) OGE_CUDA_TRY(cudaMemsetAsync(st, 0, (size_t) tiles * RS_RADIX * 4, stream));
         const bool timed = timer && timer->used < timer->cap;
         if (timed) cudaEventRecord(timer->pool[2 * timer->used], stream);
         const int shift = plan.shift[p], bits = plan.bits[p];
         uint32_t *tc = tile_counters + p;
         const uint32_t *go = goff + p * RS_RADIX;
         switch (variant) {
-            case 0: OGE_CUDA_TRY((launch_pass_v2<256, 0>(shift >> 5, (uint32_t) vtiles, stream, src, dst, (uint32_t) n, n_dev, shift, bits, go, status, tc, dbg))); break;
-            case 1: OGE_CUDA_TRY((launch_pass_v2<256, 1>(shift >> 5, (uint32_t) vtiles, stream, src, dst, (uint32_t) n, n_dev, shift, bits, go, status, tc, dbg))); break;
-            case 2: OGE_CUDA_TRY((launch_pass_v2<512, 0>(shift >> 5, (uint32_t) vtiles, stream, src, dst, (uint32_t) n, n_dev, shift, bits, go, status, tc, dbg))); break;
-            case 3: OGE_CUDA_TRY((launch_pass_v2<512, 1>(shift >> 5, (uint32_t) vtiles, stream, src, dst, (uint32_t) n, n_dev, shift, bits, go, status, tc, dbg))); break;
+            case 0: OGE_CUDA_TRY((launch_pass_v2<256, 0>(shift >> 5, (uint32_t) vtiles, stream, src, dst, (uint32_t) n, n_dev, shift, bits, go, st, st_next, tc, dbg))); break;
+            case 1: OGE_CUDA_TRY((launch_pass_v2<256, 1>(shift >> 5, (uint32_t) vtiles, stream, src, dst, (uint32_t) n, n_dev, shift, bits, go, st, st_next, tc, dbg))); break;
+            case 2: OGE_CUDA_TRY((launch_pass_v2<512, 0>(shift >> 5, (uint32_t) vtiles, stream, src, dst, (uint32_t) n, n_dev, shift, bits, go, st, st_next, tc, dbg))); break;
+            case 3: OGE_CUDA_TRY((launch_pass_v2<512, 1>(shift >> 5, (uint32_t) vtiles, stream, src, dst, (uint32_t) n, n_dev, shift, bits, go, st, st_next, tc, dbg))); break;
             default:
-                rs_onesweep_pass<<<(uint32_t) tiles, RS_THREADS, PASS_SMEM, stream>>>(src, dst, (uint32_t) n, n_dev, shift, bits, go, status, tc);
+                rs_onesweep_pass<<<(uint32_t) tiles, RS_THREADS, PASS_SMEM, stream>>>(src, dst, (uint32_t) n, n_dev, shift, bits, go, st, tc);
                 break;
         }
         if (timed) {

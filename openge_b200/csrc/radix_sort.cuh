@@ -44,5 +44,6 @@ int radix_sort_init();   // one-time function attributes
 // bit 1 = 512-thread CTAs (4096-entry tiles); -1 = first-generation kernel.
 void radix_sort_set_variant(int v);
 int radix_sort_get_variant();
+void radix_sort_set_prefetch(int tiles);
 
 }  // namespace oge

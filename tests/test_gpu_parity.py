@@ -53,7 +53,7 @@ def test_radix_sort_variants_stable(variant, n, lo, hi):
     try:
         out = dedup.debug_sort128(e, lo, hi)
     finally:
-        dedup.set_sort_variant(0)
+        dedup.set_sort_variant(2)
     v = (e[:, 1].astype(object) << 64) | e[:, 0].astype(object)
     k = np.array([int((x >> lo) & ((1 << (hi - lo)) - 1)) >> max(0, hi - lo - 63) for x in v], dtype=np.uint64)
     if hi - lo <= 63:
