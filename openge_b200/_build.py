@@ -16,6 +16,7 @@ GPU_LIB = os.path.join(ROOT, "openge_b200", "libopenge_b200.so")
 SYNTH_LIB = os.path.join(ROOT, "tools", "synth", "libogesynth.so")
 ORACLE_LIB = os.path.join(ROOT, "oracle", "liboge_oracle.so")
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "oge_ref_dedup")
+HOST_BIN = os.path.join(ROOT, "openge_b200", "host", "_build", "oge_dedup_gpu")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--use_fast_math", "-Xcompiler", "-fPIC", "-shared"]
@@ -92,8 +93,23 @@ def ensure_ref(force=False):
     return REF_BIN if os.path.exists(REF_BIN) else None
 
 
+def ensure_host(force=False):
+    """The drop-in `openge dedup` binary: the reference's pipeline compiled in place with this repo's
+    MarkDuplicates (openge_b200/host/mark_duplicates_gpu.cpp) linked instead of the reference's.
+    Needs the reference sources; elsewhere the prebuilt binary (it travels with the snapshot) is used."""
+    if os.path.isdir("/root/reference/openge/src"):
+        d = os.path.join(ROOT, "openge_b200", "host")
+        deps = [os.path.join(d, "mark_duplicates_gpu.cpp"), os.path.join(d, "Makefile"), GPU_LIB,
+                os.path.join(ROOT, "oracle", "ref_build", "ref_driver.cpp"), os.path.join(ROOT, "include", "oge_gpu_dedup.h")]
+        if force or _stale(HOST_BIN, deps):
+            _run(["make", "-C", d] + (["-B"] if force else []))
+    return HOST_BIN if os.path.exists(HOST_BIN) else None
+
+
 def build_all(verbose=False):
     ensure_synth()
     ensure_oracle()
     ensure_ref()
-    return build_gpu(verbose=verbose)
+    lib = build_gpu(verbose=verbose)
+    ensure_host()
+    return lib
