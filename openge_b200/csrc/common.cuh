@@ -88,6 +88,8 @@ enum {
     CNT_DUPS,           // records with 0x400 after the flag pass
     CNT_KEPT,           // records kept by pull (remove_duplicates)
     CNT_COMPLEX_SEGS,
+    CNT_COMPLEX_SLOTS,  // slots that saw a third arrival
+    CNT_PAIRS_RETRACTED,
     CNT_SCRATCH0,
     CNT_N = 16
 };

@@ -103,7 +103,7 @@ struct oge_gpu_dedup_ctx {
     DevBuf<uint64_t> hk;
     DevBuf<uint16_t> rgcode, flag_in, flag_out;
     DevBuf<uint8_t> dup, scratch, cplx_state;
-    DevBuf<uint32_t> mate_of, counters;
+    DevBuf<uint32_t> mate_of, counters, cplx_slots;
     DevBuf<MateSlot> table;
     uint32_t *h_counters = nullptr;      // pinned
 
@@ -275,7 +275,7 @@ void oge_gpu_dedup_destroy(oge_gpu_dedup_ctx *c) {
     c->rec.release(); c->off.release(); c->rg_bytes.release(); c->rg_off.release(); c->rg_lib.release();
     c->frag.release(); c->sortbuf.release(); c->pair.release(); c->pair2.release(); c->hk.release();
     c->rgcode.release(); c->flag_in.release(); c->flag_out.release(); c->dup.release(); c->scratch.release();
-    c->cplx_state.release(); c->mate_of.release(); c->counters.release(); c->table.release();
+    c->cplx_state.release(); c->cplx_slots.release(); c->mate_of.release(); c->counters.release(); c->table.release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->pass_ev) if (e) cudaEventDestroy(e);
@@ -401,27 +401,38 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     const uint64_t n_frag = c->h_counters[CNT_FRAG], n_pe = c->h_counters[CNT_PAIR_ELIGIBLE];
 
     // ---- K2 mate join
-    uint64_t n_pairs = 0, n_cplx = 0;
+    uint64_t n_pairs = 0, n_cplx = 0, n_retracted = 0;
     if (n_pe) {
-        uint64_t n_slots = n_pe + n_pe / 2 + 1024;
+        uint64_t n_slots = n_pe + 1024;      // two records per name: half full
         if ((rc = c->table.reserve(n_slots, false, s))) return rc;
-        if ((rc = c->pair.reserve(n_pe / 2 + 1, false, s))) return rc;
-        if ((rc = c->pair2.reserve(n_pe / 2 + 1, false, s))) return rc;
+        if ((rc = c->pair.reserve(n_pe / 2 + 1024, false, s))) return rc;
+        if ((rc = c->pair2.reserve(n_pe / 2 + 1024, false, s))) return rc;
+        if ((rc = c->cplx_slots.reserve(n_pe / 3 + 1024, false, s))) return rc;
         OGE_CUDA_TRY(cudaMemsetAsync(c->table.p, 0, n_slots * sizeof(MateSlot), s));
         JoinParams jp;
         jp.rec = c->rec.p; jp.off = c->off.p; jp.n = n; jp.idx_base = c->cfg.index_base;
         jp.frag = c->frag.p; jp.hk = c->hk.p; jp.rgcode = c->rgcode.p;
         jp.table = c->table.p; jp.n_slots = n_slots;
-        jp.pair = c->pair.p; jp.mate_of = c->mate_of.p; jp.cplx = c->sortbuf.p;
+        jp.pair = c->pair.p; jp.mate_of = c->mate_of.p; jp.cplx = c->sortbuf.p; jp.cplx_slots = c->cplx_slots.p;
         jp.counters = c->counters.p; jp.rg = rg_table(c); jp.kl = c->kl; jp.verify_names = c->cfg.verify_names;
-        if ((rc = launch_mate_insert(jp, s, &launches))) return rc;
-        if ((rc = launch_mate_resolve(jp, s, &launches))) return rc;
+        if ((rc = launch_mate_join(jp, s, &launches))) return rc;
         OGE_CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, s));
         OGE_CUDA_TRY(cudaStreamSynchronize(s));
-        n_cplx = c->h_counters[CNT_COMPLEX];
-        if (n_cplx) {
-            // exact path: sort (hash, ordinal), replay the toggle map per hash value.  The mate
-            // table is dead by now and is at least as large as the list: it is the ping-pong buffer.
+        if (c->h_counters[CNT_COMPLEX]) {
+            // names seen other than twice, or hash-equal couples with different names: the exact path
+            if ((rc = launch_mate_fixup(jp, c->h_counters[CNT_COMPLEX_SLOTS], s, &launches))) return rc;
+            OGE_CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, s));
+            OGE_CUDA_TRY(cudaStreamSynchronize(s));
+            n_cplx = c->h_counters[CNT_COMPLEX];
+            n_retracted = c->h_counters[CNT_PAIRS_RETRACTED];
+            const uint64_t need = c->h_counters[CNT_PAIRS] + n_cplx / 2 + 1;
+            if (need > c->pair.cap) {
+                if ((rc = c->pair.reserve(need, true, s))) return rc;
+                jp.pair = c->pair.p;
+            }
+            if ((rc = c->pair2.reserve(need, false, s))) return rc;
+            // sort (hash, ordinal), replay the toggle map per hash value.  The mate table is dead by
+            // now and at least as large as the list: it is the ping-pong buffer.
             E128 *sorted = nullptr;
             if ((rc = radix_sort_128(c->sortbuf.p, reinterpret_cast<E128 *>(c->table.p), n_cplx, nullptr, 0, 96, c->scratch.p, s,
                                      &sorted, &launches)))
@@ -446,8 +457,8 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
             return rc;
     }
     OGE_CUDA_TRY(cudaEventRecord(c->ev[3], s));
-    if (n_pairs) {
-        sp.sorted = sorted_pairs; sp.n_max = (uint32_t) n_pairs;
+    if (n_pairs > n_retracted) {      // retracted provisional pairs are all-ones entries: they sorted to the tail
+        sp.sorted = sorted_pairs; sp.n_max = (uint32_t) (n_pairs - n_retracted);
         if ((rc = launch_select_pairs(sp, s, &launches))) return rc;
     }
     OGE_CUDA_TRY(cudaEventRecord(c->ev[4], s));
@@ -480,7 +491,7 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
 
     oge_gpu_dedup_stats &st = c->stats;
     st.n_frag_entries = n_frag;
-    st.n_pair_entries = n_pairs;
+    st.n_pair_entries = n_pairs - n_retracted;
     st.n_duplicates = c->h_counters[CNT_DUPS];
     st.n_complex_names = n_cplx;
     st.n_hash_mismatch = c->h_counters[CNT_HASH_MISMATCH];

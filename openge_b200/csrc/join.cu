@@ -4,18 +4,21 @@
 // The reference walks the file once with a string-keyed map: the first sighting of a key
 // RG + ":" + name is stored, the second removes it and forms a pair, a third is stored again,
 // and so on.  For a key seen k times the sightings therefore pair up (1,2), (3,4), ... in file
-// order.  On the device:
-//   mate_insert   every map-eligible record adds itself to an open-addressing table slot chosen
-//                 by the 64-bit hash of the key bytes: val += (1 << 32) + ordinal
-//   mate_resolve  a slot with exactly two arrivals is the ordinary case: mate = sum - self.
-//                 The earlier record of the two confirms the match by comparing the read-group
-//                 code and the name bytes, builds the pair entry (flip rule :226-243, orientation
-//                 :169-178, short score sum :245) and appends it.  Anything else -- more than two
-//                 arrivals, or a hash-equal couple that fails the comparison -- is sent to
+// order.  On the device, one pass over the records:
+//   mate_join     every map-eligible record claims/finds the open-addressing slot of its 64-bit key
+//                 hash and adds (1 << 32) + ordinal + 1 to the slot's counter word.  The record that
+//                 gets back an arrival count of 1 is the second of its name: the sum field is its
+//                 mate's ordinal.  It confirms the match by comparing read-group code and name
+//                 bytes, builds the pair entry (flip rule :226-243, orientation :169-178, short
+//                 score sum :245), appends it and leaves (first, second, pair position) in the slot.
+//                 An arrival count of 2 or more means the name is not a plain pair: the record goes
+//                 to the exact path, and the third arrival also lists the slot, so that
+//   mate_fixup    retracts the provisional pair of such a slot and sends its two records after the others;
 //   mate_complex  the exact path: those records sorted by (hash, ordinal), one thread per hash
 //                 value replays the reference's toggle map with full byte comparison of the keys.
-// Random 16-byte slot traffic; mates of a coordinate-sorted file sit a few hundred records
-// apart, so the second touch of a slot is an L2 hit.
+//                 Hash-equal couples whose names differ take the same path.
+// One random 32-byte slot per record (two atomics); mates of a coordinate-sorted file sit a few
+// hundred records apart, so the second touch of a slot and the mate's name are L2 hits.
 #include "kernels.cuh"
 
 namespace oge {
@@ -23,25 +26,6 @@ namespace oge {
 constexpr int JOIN_THREADS = 256;
 
 __device__ __forceinline__ uint64_t slot_of(uint64_t h, uint64_t n_slots) { return __umul64hi(h, n_slots); }
-
-__global__ void __launch_bounds__(JOIN_THREADS) mate_insert_kernel(JoinParams P) {
-    uint64_t i = (uint64_t) blockIdx.x * JOIN_THREADS + threadIdx.x;
-    if (i >= P.n) return;
-    uint64_t h = P.hk[i];
-    if (!h) return;
-    uint64_t s = slot_of(h, P.n_slots);
-    while (true) {
-        unsigned long long *kp = reinterpret_cast<unsigned long long *>(&P.table[s].key);
-        unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(kp);
-        if (k == h) break;
-        if (k == 0) {
-            unsigned long long old = atomicCAS(kp, 0ull, (unsigned long long) h);
-            if (old == 0 || old == h) break;
-        }
-        if (++s == P.n_slots) s = 0;
-    }
-    atomicAdd(reinterpret_cast<unsigned long long *>(&P.table[s].val), (1ull << 32) + (uint32_t) i);
-}
 
 // ---- exact key comparison -----------------------------------------------------------------------
 // (shared with the slow path)  RG value location by the same tag walk as endbuild.cu.
@@ -169,64 +153,97 @@ __device__ __forceinline__ E128 complex_entry(uint64_t h, uint32_t ordinal) {
     return e;
 }
 
-__global__ void __launch_bounds__(JOIN_THREADS) mate_resolve_kernel(JoinParams P) {
+// unaligned little-endian 32-bit read from global memory: two aligned words + funnel shift
+__device__ __forceinline__ uint32_t ldg_u32_unaligned(const uint8_t *p) {
+    const uintptr_t a = (uintptr_t) p, wa = a & ~(uintptr_t) 3;
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(wa);
+    return __funnelshift_r(w[0], w[1], (uint32_t) (a & 3) * 8);
+}
+
+// name bytes (l_name - 1 of them, the NUL excluded) of records a and b equal?  Reads past the name
+// stay inside the record: the 32-byte core precedes it and cigar/bases/quals follow.
+__device__ __forceinline__ bool names_equal(const uint8_t *pa, const uint8_t *pb) {
+    const uint32_t la = pa[12], lb = pb[12];
+    if (la != lb) return false;
+    const uint32_t n = la ? la - 1 : 0;
+    uint32_t j = 0;
+    for (; j + 4 <= n; j += 4)
+        if (ldg_u32_unaligned(pa + 36 + j) != ldg_u32_unaligned(pb + 36 + j)) return false;
+    for (; j < n; j++)
+        if (pa[36 + j] != pb[36 + j]) return false;
+    return true;
+}
+
+constexpr uint32_t SLOT_NO_PAIR = 0xFFFFFFFFu;
+
+__global__ void __launch_bounds__(JOIN_THREADS) mate_join_kernel(JoinParams P) {
     const uint64_t i = (uint64_t) blockIdx.x * JOIN_THREADS + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1;
-    uint64_t h = i < P.n ? P.hk[i] : 0;
+    const uint64_t h = i < P.n ? P.hk[i] : 0;
 
-    bool emit = false, cplx_self = false, cplx_mate = false;
-    uint32_t mate = 0;
+    bool emit = false, cplx_self = false, cplx_other = false, list_slot = false;
+    uint32_t other = 0, i1 = 0, i2 = 0;
+    uint64_t s = 0;
     E128 ent;
     ent.lo = ent.hi = 0;
-    uint32_t i1 = 0, i2 = 0;
     if (h) {
-        uint64_t s = slot_of(h, P.n_slots);
-        while (P.table[s].key != h)
-            if (++s == P.n_slots) s = 0;
-        uint64_t val = P.table[s].val;
-        uint32_t cnt = (uint32_t) (val >> 32);
-        if (cnt == 2) {
-            mate = (uint32_t) val - (uint32_t) i;
-            if (mate > (uint32_t) i) {      // this record came first in the file
-                bool same = true;
-                if (P.verify_names) {
-                    uint32_t ra = P.rgcode[i], rb = P.rgcode[mate];
-                    const uint8_t *pa = P.rec + P.off[i], *pb = P.rec + P.off[mate];
-                    uint32_t la = pa[12], lb = pb[12];
-                    same = ra == rb && ra != RGC_UNKNOWN && la == lb;
-                    for (uint32_t j = 0; same && j + 1 < la; j++) same = pa[36 + j] == pb[36 + j];
-                }
-                if (same) {
-                    E128 a = ld_frag(P.frag + i), b = ld_frag(P.frag + mate);
-                    ent = make_pair_entry(P.kl, a, b, &i1, &i2, P.idx_base);
-                    emit = true;
-                } else {
-                    cplx_self = cplx_mate = true;
-                }
+        s = slot_of(h, P.n_slots);
+        while (true) {
+            unsigned long long *kp = reinterpret_cast<unsigned long long *>(&P.table[s].key);
+            unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(kp);
+            if (k == h) break;
+            if (k == 0) {
+                unsigned long long old = atomicCAS(kp, 0ull, (unsigned long long) h);
+                if (old == 0 || old == h) break;
             }
-        } else if (cnt > 2) {
+            if (++s == P.n_slots) s = 0;
+        }
+        const unsigned long long old =
+            atomicAdd(reinterpret_cast<unsigned long long *>(&P.table[s].val), (1ull << 32) + (uint32_t) i + 1u);
+        const uint32_t arrivals = (uint32_t) (old >> 32);
+        if (arrivals == 1) {
+            other = (uint32_t) old - 1u;
+            bool same = true;
+            if (P.verify_names) {
+                const uint32_t ra = P.rgcode[i], rb = P.rgcode[other];
+                same = ra == rb && ra != RGC_UNKNOWN && names_equal(P.rec + P.off[i], P.rec + P.off[other]);
+            }
+            if (same) {
+                const uint32_t first = min((uint32_t) i, other), second = max((uint32_t) i, other);      // file order
+                ent = make_pair_entry(P.kl, ld_frag(P.frag + first), ld_frag(P.frag + second), &i1, &i2, P.idx_base);
+                emit = true;
+            } else {
+                cplx_self = cplx_other = true;      // two names, one hash (or read groups the header does not list)
+            }
+        } else if (arrivals >= 2) {
             cplx_self = true;
+            list_slot = arrivals == 2;
         }
     }
 
     // ---- warp-aggregated appends
     uint32_t m = __ballot_sync(0xFFFFFFFFu, emit);
+    uint32_t pair_pos = SLOT_NO_PAIR;
     if (m) {
         int leader = __ffs(m) - 1;
         uint32_t base = 0;
         if (lane == leader) base = atomicAdd(&P.counters[CNT_PAIRS], (uint32_t) __popc(m));
         base = __shfl_sync(0xFFFFFFFFu, base, leader);
         if (emit) {
-            reinterpret_cast<ulonglong2 *>(P.pair)[base + __popc(m & lt)] = make_ulonglong2(ent.lo, ent.hi);
+            pair_pos = base + __popc(m & lt);
+            reinterpret_cast<ulonglong2 *>(P.pair)[pair_pos] = make_ulonglong2(ent.lo, ent.hi);
             P.mate_of[i1] = i2;
         }
     }
-    uint32_t nc = (cplx_self ? 1u : 0u) + (cplx_mate ? 1u : 0u);
+    if (emit || cplx_other) {      // what mate_fixup needs should a third record of this name turn up
+        P.table[s].who = ((uint64_t) (uint32_t) i << 32) | other;
+        P.table[s].pair_pos = pair_pos;
+    }
+    uint32_t nc = (cplx_self ? 1u : 0u) + (cplx_other ? 1u : 0u);
     uint32_t any = __ballot_sync(0xFFFFFFFFu, nc != 0);
     if (any) {
-        // exclusive prefix of nc over the warp
-        uint32_t x = nc;
+        uint32_t x = nc;      // exclusive prefix of nc over the warp
         for (int o = 1; o < 32; o <<= 1) {
             uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
             if (lane >= o) x += y;
@@ -235,11 +252,34 @@ __global__ void __launch_bounds__(JOIN_THREADS) mate_resolve_kernel(JoinParams P
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(&P.counters[CNT_COMPLEX], total);
         base = __shfl_sync(0xFFFFFFFFu, base, 0) + x - nc;
-        if (cplx_self) reinterpret_cast<ulonglong2 *>(P.cplx)[base++] = make_ulonglong2(complex_entry(h, (uint32_t) i).lo, complex_entry(h, (uint32_t) i).hi);
-        if (cplx_mate) {
-            reinterpret_cast<ulonglong2 *>(P.cplx)[base] = make_ulonglong2(complex_entry(h, mate).lo, complex_entry(h, mate).hi);
+        if (cplx_self) {
+            E128 c = complex_entry(h, (uint32_t) i);
+            reinterpret_cast<ulonglong2 *>(P.cplx)[base++] = make_ulonglong2(c.lo, c.hi);
+        }
+        if (cplx_other) {
+            E128 c = complex_entry(h, other);
+            reinterpret_cast<ulonglong2 *>(P.cplx)[base] = make_ulonglong2(c.lo, c.hi);
             atomicAdd(&P.counters[CNT_HASH_MISMATCH], 1u);
         }
+    }
+    if (list_slot) P.cplx_slots[atomicAdd(&P.counters[CNT_COMPLEX_SLOTS], 1u)] = (uint32_t) s;
+}
+
+// One thread per slot that saw a third arrival: its first two records follow the others to the exact
+// path, and the pair they formed provisionally is retracted (an all-ones entry sorts behind every
+// real key; the host shortens the pair list by the number of retractions).
+__global__ void __launch_bounds__(JOIN_THREADS) mate_fixup_kernel(JoinParams P, uint32_t n_slots_listed) {
+    uint32_t j = blockIdx.x * JOIN_THREADS + threadIdx.x;
+    if (j >= n_slots_listed) return;
+    const MateSlot &sl = P.table[P.cplx_slots[j]];
+    const uint32_t a = (uint32_t) (sl.who >> 32), b = (uint32_t) sl.who;
+    if (sl.pair_pos != SLOT_NO_PAIR) {      // else: a hash-mismatched couple, already on the exact path
+        reinterpret_cast<ulonglong2 *>(P.pair)[sl.pair_pos] = make_ulonglong2(~0ull, ~0ull);
+        atomicAdd(&P.counters[CNT_PAIRS_RETRACTED], 1u);
+        uint32_t base = atomicAdd(&P.counters[CNT_COMPLEX], 2u);
+        E128 ca = complex_entry(sl.key, a), cb = complex_entry(sl.key, b);
+        reinterpret_cast<ulonglong2 *>(P.cplx)[base] = make_ulonglong2(ca.lo, ca.hi);
+        reinterpret_cast<ulonglong2 *>(P.cplx)[base + 1] = make_ulonglong2(cb.lo, cb.hi);
     }
 }
 
@@ -292,17 +332,17 @@ __global__ void __launch_bounds__(JOIN_THREADS) mate_complex_kernel(JoinParams P
     }
 }
 
-int launch_mate_insert(const JoinParams &P, cudaStream_t stream, uint64_t *launches) {
+int launch_mate_join(const JoinParams &P, cudaStream_t stream, uint64_t *launches) {
     if (P.n == 0) return 0;
-    mate_insert_kernel<<<(uint32_t) ((P.n + JOIN_THREADS - 1) / JOIN_THREADS), JOIN_THREADS, 0, stream>>>(P);
+    mate_join_kernel<<<(uint32_t) ((P.n + JOIN_THREADS - 1) / JOIN_THREADS), JOIN_THREADS, 0, stream>>>(P);
     *launches += 1;
     OGE_CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
-int launch_mate_resolve(const JoinParams &P, cudaStream_t stream, uint64_t *launches) {
-    if (P.n == 0) return 0;
-    mate_resolve_kernel<<<(uint32_t) ((P.n + JOIN_THREADS - 1) / JOIN_THREADS), JOIN_THREADS, 0, stream>>>(P);
+int launch_mate_fixup(const JoinParams &P, uint32_t n_slots_listed, cudaStream_t stream, uint64_t *launches) {
+    if (n_slots_listed == 0) return 0;
+    mate_fixup_kernel<<<(n_slots_listed + JOIN_THREADS - 1) / JOIN_THREADS, JOIN_THREADS, 0, stream>>>(P, n_slots_listed);
     *launches += 1;
     OGE_CUDA_TRY(cudaGetLastError());
     return 0;

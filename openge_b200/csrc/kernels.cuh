@@ -39,9 +39,12 @@ struct EndbuildParams {
 int launch_endbuild(const EndbuildParams &P, uint32_t avg_rec_bytes, int sms, cudaStream_t stream, uint64_t *launches);
 
 // ---- K2 mate join (join.cu) -------------------------------------------------------------------
-struct __align__(16) MateSlot {
+struct __align__(32) MateSlot {      // one 32-byte sector
     uint64_t key;       // 64-bit hash of RG + ":" + name; 0 = empty
-    uint64_t val;       // (arrivals << 32) + sum of the arrivals' record ordinals
+    uint64_t val;       // (arrivals << 32) + sum of (ordinal + 1) over the arrivals
+    uint64_t who;       // written by the second arrival: (its ordinal << 32) | the first arrival's
+    uint32_t pair_pos;  // where it put their pair entry, or SLOT_NO_PAIR
+    uint32_t pad;
 };
 
 struct JoinParams {
@@ -56,15 +59,16 @@ struct JoinParams {
     uint64_t n_slots;
     E128 *pair;             // output pair entries (appended; counters[CNT_PAIRS])
     uint32_t *mate_of;      // [n] local ordinal of the pair's other record, for idx1's record
-    E128 *cplx;             // output: (hash << idx_bits | local ordinal) of records for the slow path
+    E128 *cplx;             // output: (hash << 32 | local ordinal) of records for the exact path
+    uint32_t *cplx_slots;   // output: slots that saw a third arrival (counters[CNT_COMPLEX_SLOTS])
     uint32_t *counters;
     RgTable rg;
     KeyLayout kl;
     int verify_names;
 };
 
-int launch_mate_insert(const JoinParams &P, cudaStream_t stream, uint64_t *launches);
-int launch_mate_resolve(const JoinParams &P, cudaStream_t stream, uint64_t *launches);
+int launch_mate_join(const JoinParams &P, cudaStream_t stream, uint64_t *launches);
+int launch_mate_fixup(const JoinParams &P, uint32_t n_slots_listed, cudaStream_t stream, uint64_t *launches);
 // exact path over the sorted complex list (sorted by hash then ordinal); state = n_cplx bytes of scratch
 int launch_mate_complex(const JoinParams &P, const E128 *sorted_cplx, uint32_t n_cplx, uint8_t *state, cudaStream_t stream,
                         uint64_t *launches);
