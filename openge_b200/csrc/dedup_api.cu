@@ -101,7 +101,8 @@ struct oge_gpu_dedup_ctx {
     // work arrays
     DevBuf<E128> frag, sortbuf, pair, pair2;
     DevBuf<uint64_t> hk;
-    DevBuf<uint16_t> rgcode, flag_in, flag_out;
+    DevBuf<uint16_t> flag_in, flag_out;
+    DevBuf<NameTag> tag;
     DevBuf<uint8_t> dup, scratch, cplx_state;
     DevBuf<uint32_t> mate_of, counters, cplx_slots;
     DevBuf<MateSlot> table;
@@ -178,7 +179,7 @@ int ensure_work(oge_gpu_dedup_ctx *c) {
     if ((rc = c->frag.reserve(n, false, s))) return rc;
     if ((rc = c->sortbuf.reserve(n, false, s))) return rc;
     if ((rc = c->hk.reserve(n, false, s))) return rc;
-    if ((rc = c->rgcode.reserve(n, false, s))) return rc;
+    if ((rc = c->tag.reserve(n, false, s))) return rc;
     if ((rc = c->flag_in.reserve(n, false, s))) return rc;
     if ((rc = c->flag_out.reserve(n, false, s))) return rc;
     if ((rc = c->dup.reserve(n, false, s))) return rc;
@@ -274,7 +275,7 @@ void oge_gpu_dedup_destroy(oge_gpu_dedup_ctx *c) {
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     c->rec.release(); c->off.release(); c->rg_bytes.release(); c->rg_off.release(); c->rg_lib.release();
     c->frag.release(); c->sortbuf.release(); c->pair.release(); c->pair2.release(); c->hk.release();
-    c->rgcode.release(); c->flag_in.release(); c->flag_out.release(); c->dup.release(); c->scratch.release();
+    c->tag.release(); c->flag_in.release(); c->flag_out.release(); c->dup.release(); c->scratch.release();
     c->cplx_state.release(); c->cplx_slots.release(); c->mate_of.release(); c->counters.release(); c->table.release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
@@ -387,7 +388,7 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     // ---- K1 end-build
     EndbuildParams eb;
     eb.rec = c->rec.p; eb.off = c->off.p; eb.n = n; eb.idx_base = c->cfg.index_base;
-    eb.frag = c->frag.p; eb.hk = c->hk.p; eb.rgcode = c->rgcode.p; eb.flag_in = c->flag_in.p;
+    eb.frag = c->frag.p; eb.hk = c->hk.p; eb.tag = c->tag.p; eb.flag_in = c->flag_in.p;
     eb.counters = c->counters.p; eb.rg = rg_table(c); eb.kl = c->kl;
     if ((rc = launch_endbuild(eb, (uint32_t) (c->rec_bytes / n), c->sms, s, &launches))) return rc;
     OGE_CUDA_TRY(cudaEventRecord(c->ev[1], s));
@@ -411,7 +412,7 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
         OGE_CUDA_TRY(cudaMemsetAsync(c->table.p, 0, n_slots * sizeof(MateSlot), s));
         JoinParams jp;
         jp.rec = c->rec.p; jp.off = c->off.p; jp.n = n; jp.idx_base = c->cfg.index_base;
-        jp.frag = c->frag.p; jp.hk = c->hk.p; jp.rgcode = c->rgcode.p;
+        jp.frag = c->frag.p; jp.hk = c->hk.p; jp.tag = c->tag.p;
         jp.table = c->table.p; jp.n_slots = n_slots;
         jp.pair = c->pair.p; jp.mate_of = c->mate_of.p; jp.cplx = c->sortbuf.p; jp.cplx_slots = c->cplx_slots.p;
         jp.counters = c->counters.p; jp.rg = rg_table(c); jp.kl = c->kl; jp.verify_names = c->cfg.verify_names;

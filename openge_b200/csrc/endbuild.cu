@@ -17,7 +17,8 @@
 // stage; the copy latency is covered by the other CTAs resident on the SM.
 // HBM-bound by design: the record bytes are read once (algorithmic: core + name + cigar + quals
 // + tags up to RG; the packed bases ride along in the same sectors).
-// Outputs per record (coalesced): 16 B end entry, 8 B name hash, 2 B read-group code, 2 B flag.
+// Outputs per record (coalesced): 16 B end entry, 8 B name hash, 2 B flag, and for records that enter
+// the mate map a 32 B pairing-key tag (read-group code + name).
 #include "kernels.cuh"
 
 namespace oge {
@@ -345,13 +346,30 @@ __device__ __forceinline__ void build_end(const EndbuildParams &P, const RgSmem 
                     h.push_bytes(r, 36, l_name ? l_name - 1 : 0);
                     hk = h.finish();
                     is_pe = true;
+                    // compact key copy for the join
+                    const uint32_t nlen = l_name ? l_name - 1 : 0;
+                    uint32_t w[8];
+                    w[0] = rgc | (l_name << 16) | (nlen ? (r.u8(36) << 24) : 0u);
+#pragma unroll
+                    for (int k = 1; k < 8; k++) {
+                        const uint32_t first = 4 * k - 3;      // name bytes [first, first + 4)
+                        uint32_t v = 0;
+                        if (first < nlen) {
+                            v = rd_u32(r, 36 + first);
+                            const uint32_t have = nlen - first;
+                            if (have < 4) v &= (1u << (8 * have)) - 1;
+                        }
+                        w[k] = v;
+                    }
+                    uint4 *t = reinterpret_cast<uint4 *>(P.tag + i);
+                    t[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                    t[1] = make_uint4(w[4], w[5], w[6], w[7]);
                 }
             }
         }
     }
     reinterpret_cast<ulonglong2 *>(P.frag)[i] = make_ulonglong2(ent.lo, ent.hi);
     P.hk[i] = hk;
-    P.rgcode[i] = (uint16_t) rgc;
     P.flag_in[i] = (uint16_t) flag;
 }
 
@@ -431,7 +449,6 @@ __global__ void __launch_bounds__(EB_THREADS) endbuild_kernel(EndbuildParams P, 
                 err |= DEV_ERR_BAD_RECORD;
                 reinterpret_cast<ulonglong2 *>(P.frag)[r] = make_ulonglong2(~0ull, ~0ull);
                 P.hk[r] = 0;
-                P.rgcode[r] = (uint16_t) RGC_ABSENT;
                 P.flag_in[r] = 0;
             } else if (s_direct) {
                 GlobalRd rd{P.rec + o0};

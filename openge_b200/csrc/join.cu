@@ -160,13 +160,11 @@ __device__ __forceinline__ uint32_t ldg_u32_unaligned(const uint8_t *p) {
     return __funnelshift_r(w[0], w[1], (uint32_t) (a & 3) * 8);
 }
 
-// name bytes (l_name - 1 of them, the NUL excluded) of records a and b equal?  Reads past the name
-// stay inside the record: the 32-byte core precedes it and cigar/bases/quals follow.
-__device__ __forceinline__ bool names_equal(const uint8_t *pa, const uint8_t *pb) {
-    const uint32_t la = pa[12], lb = pb[12];
-    if (la != lb) return false;
-    const uint32_t n = la ? la - 1 : 0;
-    uint32_t j = 0;
+// name bytes from NAME_TAG_BYTES on (the part the tags do not cover) of records a and b equal?
+// l_name is known equal.  Reads past the name stay inside the record buffer (cigar/bases/quals follow).
+__device__ bool name_tails_equal(const uint8_t *pa, const uint8_t *pb, uint32_t l_name) {
+    const uint32_t n = l_name ? l_name - 1 : 0;
+    uint32_t j = NAME_TAG_BYTES;
     for (; j + 4 <= n; j += 4)
         if (ldg_u32_unaligned(pa + 36 + j) != ldg_u32_unaligned(pb + 36 + j)) return false;
     for (; j < n; j++)
@@ -189,13 +187,14 @@ __global__ void __launch_bounds__(JOIN_THREADS) mate_join_kernel(JoinParams P) {
     ent.lo = ent.hi = 0;
     if (h) {
         s = slot_of(h, P.n_slots);
-        while (true) {
+        while (true) {      // claim or find the key's slot (a plain L2 read first: half of the arrivals find their key there)
             unsigned long long *kp = reinterpret_cast<unsigned long long *>(&P.table[s].key);
-            unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(kp);
+            unsigned long long k;
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(k) : "l"(kp) : "memory");
             if (k == h) break;
             if (k == 0) {
-                unsigned long long old = atomicCAS(kp, 0ull, (unsigned long long) h);
-                if (old == 0 || old == h) break;
+                k = atomicCAS(kp, 0ull, (unsigned long long) h);
+                if (k == 0 || k == h) break;
             }
             if (++s == P.n_slots) s = 0;
         }
@@ -206,8 +205,12 @@ __global__ void __launch_bounds__(JOIN_THREADS) mate_join_kernel(JoinParams P) {
             other = (uint32_t) old - 1u;
             bool same = true;
             if (P.verify_names) {
-                const uint32_t ra = P.rgcode[i], rb = P.rgcode[other];
-                same = ra == rb && ra != RGC_UNKNOWN && names_equal(P.rec + P.off[i], P.rec + P.off[other]);
+                const uint4 *ta = reinterpret_cast<const uint4 *>(P.tag + i), *tb = reinterpret_cast<const uint4 *>(P.tag + other);
+                const uint4 a0 = ta[0], a1 = ta[1], b0 = tb[0], b1 = tb[1];
+                same = a0.x == b0.x && a0.y == b0.y && a0.z == b0.z && a0.w == b0.w && a1.x == b1.x && a1.y == b1.y &&
+                       a1.z == b1.z && a1.w == b1.w && (a0.x & 0xFFFFu) != RGC_UNKNOWN;
+                const uint32_t l_name = (a0.x >> 16) & 0xFFu;
+                if (same && l_name > NAME_TAG_BYTES + 1) same = name_tails_equal(P.rec + P.off[i], P.rec + P.off[other], l_name);
             }
             if (same) {
                 const uint32_t first = min((uint32_t) i, other), second = max((uint32_t) i, other);      // file order

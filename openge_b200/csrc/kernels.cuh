@@ -22,6 +22,16 @@ struct RgTable {
     int16_t unknown_lib;
 };
 
+// Compact copy of what the pairing key is made of (mark_duplicates.cpp:210-214): read-group code,
+// name length and the first 29 name bytes, zero padded, in one 32-byte sector per record.  Two keys
+// with l_name - 1 <= 29 are equal iff their tags are bit-equal (and the code is a listed read group);
+// longer names are compared tag first, then tail against tail in the records.  The join reads
+// these instead of the records: 32 B per record, and the mate's tag is an L2 hit.
+struct __align__(32) NameTag {
+    uint32_t w[8];      // w[0] = rgcode | l_name << 16 | name[0] << 24, w[1..7] = name[1..28]
+};
+constexpr uint32_t NAME_TAG_BYTES = 29;
+
 struct EndbuildParams {
     const uint8_t *rec;
     const uint64_t *off;
@@ -29,7 +39,7 @@ struct EndbuildParams {
     uint64_t idx_base;      // global ordinal of record 0 (multi-GPU shards)
     E128 *frag;
     uint64_t *hk;
-    uint16_t *rgcode;
+    NameTag *tag;           // [n] compact pairing-key copy, written for records that enter the mate map
     uint16_t *flag_in;
     uint32_t *counters;
     RgTable rg;
@@ -54,7 +64,7 @@ struct JoinParams {
     uint64_t idx_base;
     const E128 *frag;
     const uint64_t *hk;
-    const uint16_t *rgcode;
+    const NameTag *tag;
     MateSlot *table;
     uint64_t n_slots;
     E128 *pair;             // output pair entries (appended; counters[CNT_PAIRS])
