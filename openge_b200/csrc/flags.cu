@@ -9,34 +9,84 @@
 namespace oge {
 
 constexpr int FL_THREADS = 256;
+constexpr int FL_ITEMS = 8;      // records per thread: one 16-byte load of flags, one 8-byte load of marks
 
+__device__ __forceinline__ uint32_t flag_of(const uint4 &v, int k) {
+    const uint32_t w = k < 2 ? v.x : (k < 4 ? v.y : (k < 6 ? v.z : v.w));
+    return (k & 1) ? (w >> 16) : (w & 0xFFFFu);
+}
+
+// The kernel is latency-bound by construction (flag -> mark -> offset -> store is a dependent chain
+// per record), so every thread takes eight records with all of its loads issued up front.
 __global__ void __launch_bounds__(FL_THREADS) flags_kernel(FlagParams P) {
-    uint64_t i = (uint64_t) blockIdx.x * FL_THREADS + threadIdx.x;
-    uint32_t isdup = 0;
-    if (i < P.n) {
-        uint16_t f = P.flag_in[i], nf = f;
-        if (!(f & 0x100)) {
-            bool d;
-            if (P.quiet_index_bug) d = (i == 0) && P.counters[CNT_MARKS] > 0;   // every index is 0
-            else d = P.dup[i] != 0;
-            nf = d ? (uint16_t) (f | 0x400) : (uint16_t) (f & ~0x400);
-            isdup = d;
+    const uint64_t i0 = ((uint64_t) blockIdx.x * FL_THREADS + threadIdx.x) * FL_ITEMS;
+    uint32_t n_dup = 0;
+    if (i0 + FL_ITEMS <= P.n) {
+        const uint4 fi = *reinterpret_cast<const uint4 *>(P.flag_in + i0);
+        const uint2 dm = *reinterpret_cast<const uint2 *>(P.dup + i0);
+        const bool quiet_hit = P.quiet_index_bug && i0 == 0 && P.counters[CNT_MARKS] > 0;   // every index is 0
+        uint32_t out[FL_ITEMS], changed = 0;
+#pragma unroll
+        for (int k = 0; k < FL_ITEMS; k++) {
+            const uint32_t f = flag_of(fi, k);
+            uint32_t nf = f;
+            if (!(f & 0x100)) {
+                bool d;
+                if (P.quiet_index_bug) d = quiet_hit && k == 0;
+                else d = (((k < 4 ? dm.x : dm.y) >> (8 * (k & 3))) & 0xFFu) != 0;
+                nf = d ? (f | 0x400u) : (f & ~0x400u);
+                n_dup += d;
+                // duplicates are always (re)written so that a re-run over the resident records does the same work
+                if (nf != f || d) changed |= 1u << k;
+            }
+            out[k] = nf;
         }
-        P.flag_out[i] = nf;
-        // duplicates are always (re)written so that a re-run over the resident records does the same work
-        if (nf != f || isdup) {
-            uint8_t *p = P.rec + P.off[i] + 18;
-            p[0] = (uint8_t) (nf & 0xFF);
-            p[1] = (uint8_t) (nf >> 8);
+        *reinterpret_cast<uint4 *>(P.flag_out + i0) =
+            make_uint4(out[0] | (out[1] << 16), out[2] | (out[3] << 16), out[4] | (out[5] << 16), out[6] | (out[7] << 16));
+        // scatter into the resident records: all offsets first, then the stores
+        uint64_t o[FL_ITEMS];
+#pragma unroll
+        for (int k = 0; k < FL_ITEMS; k++)
+            if (changed & (1u << k)) o[k] = P.off[i0 + k];
+#pragma unroll
+        for (int k = 0; k < FL_ITEMS; k++)
+            if (changed & (1u << k)) {
+                uint8_t *p = P.rec + o[k] + 18;
+                p[0] = (uint8_t) (out[k] & 0xFF);
+                p[1] = (uint8_t) (out[k] >> 8);
+            }
+    } else {
+        for (uint64_t i = i0; i < P.n; i++) {      // the last, partial group
+            const uint32_t f = P.flag_in[i];
+            uint32_t nf = f;
+            bool d = false;
+            if (!(f & 0x100)) {
+                if (P.quiet_index_bug) d = (i == 0) && P.counters[CNT_MARKS] > 0;
+                else d = P.dup[i] != 0;
+                nf = d ? (f | 0x400u) : (f & ~0x400u);
+                n_dup += d;
+            }
+            P.flag_out[i] = (uint16_t) nf;
+            if (nf != f || d) {
+                uint8_t *p = P.rec + P.off[i] + 18;
+                p[0] = (uint8_t) (nf & 0xFF);
+                p[1] = (uint8_t) (nf >> 8);
+            }
         }
     }
-    uint32_t m = __ballot_sync(0xFFFFFFFFu, isdup);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&P.counters[CNT_DUPS], (uint32_t) __popc(m));
+    for (int o = 16; o; o >>= 1) n_dup += __shfl_xor_sync(0xFFFFFFFFu, n_dup, o);
+    __shared__ uint32_t s_dup;
+    if (threadIdx.x == 0) s_dup = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && n_dup) atomicAdd(&s_dup, n_dup);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_dup) atomicAdd(&P.counters[CNT_DUPS], s_dup);
 }
 
 int launch_flags(const FlagParams &P, cudaStream_t stream, uint64_t *launches) {
     if (P.n == 0) return 0;
-    flags_kernel<<<(uint32_t) ((P.n + FL_THREADS - 1) / FL_THREADS), FL_THREADS, 0, stream>>>(P);
+    const uint64_t per_cta = (uint64_t) FL_THREADS * FL_ITEMS;
+    flags_kernel<<<(uint32_t) ((P.n + per_cta - 1) / per_cta), FL_THREADS, 0, stream>>>(P);
     *launches += 1;
     OGE_CUDA_TRY(cudaGetLastError());
     return 0;
