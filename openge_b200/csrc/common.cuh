@@ -90,8 +90,13 @@ enum {
     CNT_COMPLEX_SEGS,
     CNT_COMPLEX_SLOTS,  // slots that saw a third arrival
     CNT_PAIRS_RETRACTED,
+    CNT_FOREIGN_MARKS,  // sharded: marks on records of other ranks
+    CNT_PUB,            // sharded: published entries
+    CNT_ROUTE,          // sharded: entries handed to their key owner
+    CNT_FRAG_EXTRA,     // sharded: fragment entries received
+    CNT_FM,             // sharded: foreign-mate couples
     CNT_SCRATCH0,
-    CNT_N = 16
+    CNT_N = 32
 };
 
 // ---- launch bookkeeping ----------------------------------------------------------------------

@@ -1,0 +1,110 @@
+// Internal: the context object shared by the single-GPU path (dedup_api.cu) and the range-sharded
+// path (shard_api.cu).  Not part of the C ABI.
+#pragma once
+#include <algorithm>
+#include <vector>
+
+#include "kernels.cuh"
+#include "oge_gpu_dedup.h"
+#include "radix_sort.cuh"
+
+namespace oge {
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;      // elements
+    int reserve(size_t n, bool keep, cudaStream_t s) {
+        if (n <= cap) return 0;
+        size_t want = keep && cap ? std::max(n, cap + cap / 2) : n;
+        T *q = nullptr;
+        cudaError_t e = cudaMalloc((void **) &q, want * sizeof(T) + 256);
+        if (e != cudaSuccess && want > n) {
+            cudaGetLastError();
+            want = n;
+            e = cudaMalloc((void **) &q, want * sizeof(T) + 256);
+        }
+        if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc", __FILE__, __LINE__);
+        if (keep && p && cap) {
+            e = cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) { cudaFree(q); return fail_cuda(e, "grow copy", __FILE__, __LINE__); }
+        }
+        if (p) cudaFree(p);
+        p = q;
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// ---- multi-GPU range sharding
+struct ShardState {
+    bool on = false;
+    uint64_t global_n = 0;
+    std::vector<uint64_t> bases;          // world + 1 record ordinals
+    std::vector<uint64_t> split_keys;     // world - 1 packed (ref << coord_bits | biased coord): first key of ranks 1..
+    DevBuf<uint64_t> d_split;
+    DevBuf<PubEntry> pub, pub2;           // published entries, rounds 1 and 2
+    DevBuf<RouteEntry> route;
+    DevBuf<uint32_t> marks, pub_list;
+    DevBuf<uint64_t> fm;                  // foreign mates: (idx1 << 32 | idx2), sorted by idx1
+    DevBuf<E128> fm_sort, w_sort, w_sort2;
+    uint64_t n_frag = 0, n_pe = 0, n_pairs = 0, n_retracted = 0, n_slots = 0, n_fm = 0, n_frag_total = 0, n_w = 0;
+    int phase = 0;
+};
+
+}  // namespace oge
+
+using namespace oge;      // internal header: only this library's .cu files include it
+
+struct oge_gpu_dedup_ctx {
+    oge_gpu_dedup_config cfg;
+    int sms = 148;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t copy_done = nullptr;
+    cudaEvent_t ev[10];
+    cudaEvent_t pass_ev[2 * 48];      // profile_events: one pair per radix-sort pass launch
+
+    // resident input
+    DevBuf<uint8_t> rec;
+    DevBuf<uint64_t> off;
+    uint64_t n = 0, rec_bytes = 0;
+
+    // read-group table
+    DevBuf<uint8_t> rg_bytes;
+    DevBuf<uint32_t> rg_off;
+    DevBuf<int16_t> rg_lib;
+    int n_rg = 0, n_libs = 1;
+    int16_t unknown_lib = 1;
+
+    // work arrays
+    DevBuf<E128> frag, sortbuf, pair, pair2;
+    DevBuf<uint64_t> hk;
+    DevBuf<uint16_t> flag_in, flag_out;
+    DevBuf<NameTag> tag;
+    DevBuf<uint8_t> dup, scratch, cplx_state;
+    DevBuf<uint32_t> mate_of, counters, cplx_slots;
+    DevBuf<MateSlot> table;
+    uint32_t *h_counters = nullptr;      // pinned
+
+    KeyLayout kl;
+    bool ran = false;
+    oge::ShardState sh;
+    oge_gpu_dedup_stats stats;
+};
+
+
+namespace oge {
+
+int compute_layout(oge_gpu_dedup_ctx *c, KeyLayout *L);
+RgTable rg_table(oge_gpu_dedup_ctx *c);
+int ensure_work(oge_gpu_dedup_ctx *c);
+float ms_between(cudaEvent_t a, cudaEvent_t b);
+int check_endbuild_errors(oge_gpu_dedup_ctx *c);
+
+}  // namespace oge

@@ -14,9 +14,7 @@
 #include <string>
 #include <vector>
 
-#include "kernels.cuh"
-#include "oge_gpu_dedup.h"
-#include "radix_sort.cuh"
+#include "ctx.cuh"
 
 namespace oge {
 
@@ -42,82 +40,15 @@ static int bit_length(uint64_t v) {
     return b;
 }
 
-template <typename T>
-struct DevBuf {
-    T *p = nullptr;
-    size_t cap = 0;      // elements
-    int reserve(size_t n, bool keep, cudaStream_t s) {
-        if (n <= cap) return 0;
-        size_t want = keep && cap ? std::max(n, cap + cap / 2) : n;
-        T *q = nullptr;
-        cudaError_t e = cudaMalloc((void **) &q, want * sizeof(T) + 256);
-        if (e != cudaSuccess && want > n) {
-            cudaGetLastError();
-            want = n;
-            e = cudaMalloc((void **) &q, want * sizeof(T) + 256);
-        }
-        if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc", __FILE__, __LINE__);
-        if (keep && p && cap) {
-            e = cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-            if (e != cudaSuccess) { cudaFree(q); return fail_cuda(e, "grow copy", __FILE__, __LINE__); }
-        }
-        if (p) cudaFree(p);
-        p = q;
-        cap = want;
-        return 0;
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-};
-
 }  // namespace oge
 
 using namespace oge;
 
-struct oge_gpu_dedup_ctx {
-    oge_gpu_dedup_config cfg;
-    int sms = 148;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t copy_done = nullptr;
-    cudaEvent_t ev[10];
-    cudaEvent_t pass_ev[2 * 48];      // profile_events: one pair per radix-sort pass launch
-
-    // resident input
-    DevBuf<uint8_t> rec;
-    DevBuf<uint64_t> off;
-    uint64_t n = 0, rec_bytes = 0;
-
-    // read-group table
-    DevBuf<uint8_t> rg_bytes;
-    DevBuf<uint32_t> rg_off;
-    DevBuf<int16_t> rg_lib;
-    int n_rg = 0, n_libs = 1;
-    int16_t unknown_lib = 1;
-
-    // work arrays
-    DevBuf<E128> frag, sortbuf, pair, pair2;
-    DevBuf<uint64_t> hk;
-    DevBuf<uint16_t> flag_in, flag_out;
-    DevBuf<NameTag> tag;
-    DevBuf<uint8_t> dup, scratch, cplx_state;
-    DevBuf<uint32_t> mate_of, counters, cplx_slots;
-    DevBuf<MateSlot> table;
-    uint32_t *h_counters = nullptr;      // pinned
-
-    KeyLayout kl;
-    bool ran = false;
-    oge_gpu_dedup_stats stats;
-};
-
-namespace {
+namespace oge {
 
 int compute_layout(oge_gpu_dedup_ctx *c, KeyLayout *L) {
     memset(L, 0, sizeof(*L));
-    uint64_t top = c->cfg.index_base + c->n;
+    uint64_t top = std::max<uint64_t>(c->cfg.index_base + c->n, c->sh.global_n);
     L->idx_bits = std::max(1, bit_length(top ? top - 1 : 0));
     L->ref_bits = std::max(1, bit_length(c->cfg.n_ref > 1 ? (uint64_t) c->cfg.n_ref - 1 : 1));
     if (c->cfg.max_ref_len > 0) {
@@ -188,13 +119,24 @@ int ensure_work(oge_gpu_dedup_ctx *c) {
     return 0;
 }
 
+int check_endbuild_errors(oge_gpu_dedup_ctx *c) {
+    if (c->h_counters[CNT_ERR] & DEV_ERR_BAD_RECORD)
+        return fail_msg(OGE_ERR_BAD_RECORD, "run: malformed record (block_size disagrees with offsets, or sections overrun the record)");
+    if (c->h_counters[CNT_ERR] & DEV_ERR_KEY_RANGE)
+        return fail_msg(OGE_ERR_KEY_RANGE, "run: a record's refID / unclipped coordinate / library does not fit the key layout "
+                                           "(n_ref=%d max_ref_len=%d clip_margin=%d)", c->cfg.n_ref, c->cfg.max_ref_len, c->cfg.clip_margin);
+    if ((c->cfg.index_base + c->n > (1ull << 32)) || c->sh.global_n > (1ull << 32))
+        return fail_msg(OGE_ERR_TOO_LARGE, "run: global record ordinals must stay below 2^32");
+    return 0;
+}
+
 float ms_between(cudaEvent_t a, cudaEvent_t b) {
     float ms = 0;
     cudaEventElapsedTime(&ms, a, b);
     return ms;
 }
 
-}  // namespace
+}  // namespace oge
 
 extern "C" {
 
@@ -394,11 +336,7 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     OGE_CUDA_TRY(cudaEventRecord(c->ev[1], s));
     OGE_CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, s));
     OGE_CUDA_TRY(cudaStreamSynchronize(s));
-    if (c->h_counters[CNT_ERR] & DEV_ERR_BAD_RECORD)
-        return fail_msg(OGE_ERR_BAD_RECORD, "run: malformed record (block_size disagrees with offsets, or sections overrun the record)");
-    if (c->h_counters[CNT_ERR] & DEV_ERR_KEY_RANGE)
-        return fail_msg(OGE_ERR_KEY_RANGE, "run: a record's refID / unclipped coordinate / library does not fit the key layout "
-                                           "(n_ref=%d max_ref_len=%d clip_margin=%d)", c->cfg.n_ref, c->cfg.max_ref_len, c->cfg.clip_margin);
+    if ((rc = check_endbuild_errors(c))) return rc;
     const uint64_t n_frag = c->h_counters[CNT_FRAG], n_pe = c->h_counters[CNT_PAIR_ELIGIBLE];
 
     // ---- K2 mate join
@@ -451,6 +389,7 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     SelectParams sp;
     sp.dup = c->dup.p; sp.mate_of = c->mate_of.p; sp.idx_base = c->cfg.index_base; sp.n_records = n;
     sp.counters = c->counters.p; sp.kl = c->kl; sp.n_dev = nullptr;
+    sp.fm = nullptr; sp.n_fm = 0; sp.foreign_marks = nullptr; sp.foreign_cap = 0;
     E128 *sorted_pairs = c->pair.p;
     if (n_pairs) {
         if ((rc = radix_sort_128(c->pair.p, c->pair2.p, n_pairs, nullptr, c->kl.p_coord2, c->kl.p_end, c->scratch.p, s, &sorted_pairs,

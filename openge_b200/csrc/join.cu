@@ -20,12 +20,11 @@
 // One random 32-byte slot per record (two atomics); mates of a coordinate-sorted file sit a few
 // hundred records apart, so the second touch of a slot and the mate's name are L2 hits.
 #include "kernels.cuh"
+#include "pairing.cuh"
 
 namespace oge {
 
 constexpr int JOIN_THREADS = 256;
-
-__device__ __forceinline__ uint64_t slot_of(uint64_t h, uint64_t n_slots) { return __umul64hi(h, n_slots); }
 
 // ---- exact key comparison -----------------------------------------------------------------------
 // (shared with the slow path)  RG value location by the same tag walk as endbuild.cu.
@@ -109,50 +108,6 @@ __device__ int find_rg_global(const uint8_t *tags, uint32_t n, uint32_t *len) {
     return -1;
 }
 
-// ---- pair entry ---------------------------------------------------------------------------------
-// first = the record seen first in the file (the map's stored ReadEnds), second = the current one.
-__device__ __forceinline__ E128 make_pair_entry(const KeyLayout &L, const E128 &first, const E128 &second,
-                                                uint32_t *idx1_local, uint32_t *idx2_local, uint64_t idx_base) {
-    uint64_t lib = bits_get(first, L.f_lib, L.lib_bits);      // library of the first-seen end (:218)
-    uint64_t ref_f = bits_get(first, L.f_ref, L.ref_bits), ref_s = bits_get(second, L.f_ref, L.ref_bits);
-    uint64_t co_f = bits_get(first, L.f_coord, L.coord_bits), co_s = bits_get(second, L.f_coord, L.coord_bits);
-    uint64_t rev_f = bits_get(first, L.f_orient, 1), rev_s = bits_get(second, L.f_orient, 1);
-    uint64_t idx_f = bits_get(first, L.f_idx, L.idx_bits), idx_s = bits_get(second, L.f_idx, L.idx_bits);
-    uint32_t score = ((uint32_t) first.lo + (uint32_t) second.lo) & 0xFFFFu;      // short + short (:245)
-    E128 e;
-    e.lo = score;
-    e.hi = 0;
-    // second >= first in (sequence, coordinate): keep order, else flip (:229-243)
-    bool keep = ref_s > ref_f || (ref_s == ref_f && co_s >= co_f);
-    uint64_t r1 = keep ? ref_f : ref_s, c1 = keep ? co_f : co_s, v1 = keep ? rev_f : rev_s, i1 = keep ? idx_f : idx_s;
-    uint64_t r2 = keep ? ref_s : ref_f, c2 = keep ? co_s : co_f, v2 = keep ? rev_s : rev_f, i2 = keep ? idx_s : idx_f;
-    bits_or(e, L.p_idx, i1);
-    bits_or(e, L.p_coord2, c2);
-    bits_or(e, L.p_ref2, r2);
-    bits_or(e, L.p_orient, (v1 << 1) | v2);      // getOrientationByte(read1Negative, read2Negative) (:169-178)
-    bits_or(e, L.p_coord1, c1);
-    bits_or(e, L.p_ref1, r1);
-    bits_or(e, L.p_lib, lib);
-    *idx1_local = (uint32_t) (i1 - idx_base);
-    *idx2_local = (uint32_t) (i2 - idx_base);
-    return e;
-}
-
-__device__ __forceinline__ E128 ld_frag(const E128 *p) {
-    ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(p);
-    E128 e;
-    e.lo = v.x;
-    e.hi = v.y;
-    return e;
-}
-
-__device__ __forceinline__ E128 complex_entry(uint64_t h, uint32_t ordinal) {
-    E128 e;
-    e.lo = (h << 32) | ordinal;
-    e.hi = h >> 32;
-    return e;
-}
-
 // unaligned little-endian 32-bit read from global memory: two aligned words + funnel shift
 __device__ __forceinline__ uint32_t ldg_u32_unaligned(const uint8_t *p) {
     const uintptr_t a = (uintptr_t) p, wa = a & ~(uintptr_t) 3;
@@ -171,8 +126,6 @@ __device__ bool name_tails_equal(const uint8_t *pa, const uint8_t *pb, uint32_t 
         if (pa[36 + j] != pb[36 + j]) return false;
     return true;
 }
-
-constexpr uint32_t SLOT_NO_PAIR = 0xFFFFFFFFu;
 
 __global__ void __launch_bounds__(JOIN_THREADS) mate_join_kernel(JoinParams P) {
     const uint64_t i = (uint64_t) blockIdx.x * JOIN_THREADS + threadIdx.x;
@@ -236,7 +189,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) mate_join_kernel(JoinParams P) {
         if (emit) {
             pair_pos = base + __popc(m & lt);
             reinterpret_cast<ulonglong2 *>(P.pair)[pair_pos] = make_ulonglong2(ent.lo, ent.hi);
-            P.mate_of[i1] = i2;
+            P.mate_of[i1] = (uint32_t) (i2 + P.idx_base);
         }
     }
     if (emit || cplx_other) {      // what mate_fixup needs should a third record of this name turn up
@@ -330,7 +283,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) mate_complex_kernel(JoinParams P
             E128 ent = make_pair_entry(P.kl, first, second, &i1, &i2, P.idx_base);
             uint32_t pos = atomicAdd(&P.counters[CNT_PAIRS], 1u);
             reinterpret_cast<ulonglong2 *>(P.pair)[pos] = make_ulonglong2(ent.lo, ent.hi);
-            P.mate_of[i1] = i2;
+            P.mate_of[i1] = (uint32_t) (i2 + P.idx_base);
         }
     }
 }

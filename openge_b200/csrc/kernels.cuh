@@ -68,7 +68,7 @@ struct JoinParams {
     MateSlot *table;
     uint64_t n_slots;
     E128 *pair;             // output pair entries (appended; counters[CNT_PAIRS])
-    uint32_t *mate_of;      // [n] local ordinal of the pair's other record, for idx1's record
+    uint32_t *mate_of;      // [n] GLOBAL ordinal of the pair's other record, indexed by idx1's local ordinal
     E128 *cplx;             // output: (hash << 32 | local ordinal) of records for the exact path
     uint32_t *cplx_slots;   // output: slots that saw a third arrival (counters[CNT_COMPLEX_SLOTS])
     uint32_t *counters;
@@ -89,11 +89,16 @@ struct SelectParams {
     uint32_t n_max;
     const uint32_t *n_dev;      // device count (pairs) or nullptr
     uint8_t *dup;               // [n records] duplicate set, indexed by local ordinal
-    const uint32_t *mate_of;
-    uint64_t idx_base;
-    uint64_t n_records;
+    const uint32_t *mate_of;    // global ordinal of idx2, indexed by idx1's local ordinal
+    uint64_t idx_base;          // global ordinal of local record 0
+    uint64_t n_records;         // local records: ordinals outside [idx_base, idx_base + n_records) belong to other ranks
     uint32_t *counters;
     KeyLayout kl;
+    // range sharding only (null / 0 on one GPU)
+    const uint64_t *fm;         // (idx1 << 32 | idx2) sorted by idx1: mates of pair entries whose idx1 is not local
+    uint32_t n_fm;
+    uint32_t *foreign_marks;    // out: global ordinals to mark on other ranks (counters[CNT_FOREIGN_MARKS])
+    uint32_t foreign_cap;
 };
 
 int launch_select_pairs(const SelectParams &P, cudaStream_t stream, uint64_t *launches);
@@ -114,6 +119,33 @@ struct FlagParams {
 int launch_flags(const FlagParams &P, cudaStream_t stream, uint64_t *launches);
 
 // pull with remove_duplicates: compaction of the kept records
+// ---- range sharding (shard.cu) ------------------------------------------------------------------
+// What leaves a rank about one record whose name was not seen exactly twice locally.
+struct __align__(16) PubEntry {
+    E128 frag;          // its fragment end entry (global ordinal inside)
+    uint64_t hk;        // pairing-key hash
+    uint64_t rsv;
+    NameTag tag;        // read-group code + name, for the exact comparison on the receiving side
+};
+static_assert(sizeof(PubEntry) == 64, "PubEntry is 64 bytes on the wire");
+
+// An end entry handed to the rank that owns its key range.
+struct __align__(16) RouteEntry {
+    E128 e;
+    uint32_t idx2;      // pairs: global ordinal of the second record
+    uint32_t kind;      // 0 fragment, 1 pair
+    uint64_t rsv;
+};
+static_assert(sizeof(RouteEntry) == 32, "RouteEntry is 32 bytes on the wire");
+
+struct ShardParams {
+    const uint64_t *split;      // world - 1 packed keys (ref << coord_bits | biased coord): first key of ranks 1..
+    int world, rank;
+    uint64_t idx_base, n;       // local ordinal range
+    KeyLayout kl;
+    uint32_t *counters;
+};
+
 int launch_compact(const uint8_t *rec, const uint64_t *off, uint64_t n, const uint16_t *flag_out, int remove_dups,
                    uint8_t *out_rec, uint64_t *out_off, uint64_t *scratch /* n+1 + blocks */, uint32_t *counters,
                    cudaStream_t stream, uint64_t *launches);

@@ -121,7 +121,27 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(SelectParams P) {
     // run id of entry k = run_base + popc(heads & ((2 << k) - 1)) - 1   (-1: continues an earlier tile's run)
     auto run_of = [&](int k) { return (int) (run_base + __popc(heads & ((2u << k) - 1))) - 1; };
     auto score_of = [&](const E128 &v) { return (int) (int16_t) (uint16_t) (v.lo & 0xFFFFu); };
-    auto idx_of = [&](const E128 &v) { return (uint32_t) (bits_get(v, idx_pos, L.idx_bits) - P.idx_base); };
+    // global ordinals (< 2^32); [idx_base, idx_base + n_records) are this rank's records
+    auto idx_of = [&](const E128 &v) { return (uint32_t) bits_get(v, idx_pos, L.idx_bits); };
+    auto mark = [&](uint32_t g) {
+        const uint64_t l = (uint64_t) g - P.idx_base;      // wraps for ordinals below the base
+        if (l < P.n_records) P.dup[l] = 1;
+        else {
+            uint32_t at = atomicAdd(&P.counters[CNT_FOREIGN_MARKS], 1u);
+            if (at < P.foreign_cap) P.foreign_marks[at] = g;
+        }
+    };
+    auto mate_of = [&](uint32_t g1) -> uint32_t {
+        const uint64_t l = (uint64_t) g1 - P.idx_base;
+        if (l < P.n_records) return P.mate_of[l];
+        uint32_t lo = 0, hi = P.n_fm;      // first couple with idx1 >= g1
+        while (lo < hi) {
+            uint32_t mid = (lo + hi) >> 1;
+            if ((uint32_t) (P.fm[mid] >> 32) < g1) lo = mid + 1;
+            else hi = mid;
+        }
+        return (uint32_t) P.fm[lo];
+    };
     auto paired_of = [&](const E128 &v) { return PAIRS ? true : bits_get(v, L.f_paired, 1) != 0; };
 
     // ---- pass 1: max score, count, flags per run (thread-local folding of consecutive entries)
@@ -216,18 +236,17 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(SelectParams P) {
         bool is_best = score_of(v) == s_max[r] && idx_of(v) == s_best[r];
         if (PAIRS) {
             if (!is_best) {
-                uint32_t i1 = idx_of(v);
-                uint32_t i2 = P.mate_of[i1];
-                P.dup[i1] = 1;
-                P.dup[i2] = 1;
+                const uint32_t i1 = idx_of(v);
+                mark(i1);
+                mark(mate_of(i1));
                 marks += 2;
             }
         } else {
             uint32_t fl = s_flags[r];
             if (!(fl & RUN_HAS_UNPAIRED)) return;
-            bool mark = (fl & RUN_HAS_PAIRED) ? !paired_of(v) : !is_best;
-            if (mark) {
-                P.dup[idx_of(v)] = 1;
+            bool mark_it = (fl & RUN_HAS_PAIRED) ? !paired_of(v) : !is_best;
+            if (mark_it) {
+                mark(idx_of(v));
                 marks += 1;
             }
         }

@@ -1,0 +1,355 @@
+// Range-sharded dedup across GPUs: the device work between the exchanges.
+//
+// The reference has no counterpart (it is one process); what has to be preserved is that the
+// result equals its single-stream run (`openge dedup --nosplit -v`):
+//   * the pairing of ReadEndsMap (util/picard_structures.h:82-109, algorithms/mark_duplicates.cpp:209-246)
+//     is a sequential toggle over the whole file, so every name that is not a plain couple inside
+//     one shard is resolved over the union of all shards' sightings, in global file order;
+//   * a duplicate group (areComparableForDuplicates, :402-414) must be evaluated in one place, so
+//     every end entry lives on the rank that owns its key range.
+// All lists that cross ranks are small (cross-shard mates, boundary ends, marks); the exchange
+// delivers every rank's list to every rank and the receiving kernels keep what concerns them.
+#include "kernels.cuh"
+#include "pairing.cuh"
+
+namespace oge {
+
+constexpr int SH_THREADS = 256;
+
+// rank owning the key range that holds (ref, coord): number of split keys <= the packed key
+__device__ __forceinline__ int owner_of(const ShardParams &S, uint64_t packed) {
+    int o = 0;
+    for (int r = 0; r + 1 < S.world; r++) o += S.split[r] <= packed ? 1 : 0;
+    return o;
+}
+__device__ __forceinline__ uint64_t frag_packed(const KeyLayout &L, const E128 &e) { return bits_get(e, L.f_coord, L.coord_bits + L.ref_bits); }
+__device__ __forceinline__ uint64_t pair_packed(const KeyLayout &L, const E128 &e) { return bits_get(e, L.p_coord1, L.coord_bits + L.ref_bits); }
+__device__ __forceinline__ bool is_dead(const E128 &e) { return (e.lo & e.hi) == ~0ull; }
+
+// warp-aggregated append position (all lanes of the warp must call)
+__device__ __forceinline__ uint32_t warp_append(bool want, uint32_t *counter) {
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, want);
+    if (!m) return 0;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t) __popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    return base + __popc(m & ((1u << lane) - 1));
+}
+
+// ---- phase 1: who gets published -------------------------------------------------------------------
+// names seen once locally: their slot still holds one arrival
+__global__ void __launch_bounds__(SH_THREADS) sh_singletons_kernel(const MateSlot *__restrict__ table, uint64_t n_slots,
+                                                                   uint32_t *__restrict__ list, uint32_t *__restrict__ counters) {
+    const uint64_t s = (uint64_t) blockIdx.x * SH_THREADS + threadIdx.x;
+    bool want = false;
+    uint32_t ord = 0;
+    if (s < n_slots) {
+        const ulonglong2 kv = *reinterpret_cast<const ulonglong2 *>(&table[s]);      // key, val
+        want = kv.x != 0 && (kv.y >> 32) == 1;
+        ord = (uint32_t) kv.y - 1u;
+    }
+    const uint32_t at = warp_append(want, &counters[CNT_PUB]);
+    if (want) list[at] = ord;
+}
+
+// records on the exact-path list (names seen three or more times locally, hash-equal couples)
+__global__ void __launch_bounds__(SH_THREADS) sh_complex_kernel(const E128 *__restrict__ cplx, uint32_t n_cplx, uint32_t *__restrict__ list,
+                                                                uint32_t *__restrict__ counters) {
+    const uint32_t j = blockIdx.x * SH_THREADS + threadIdx.x;
+    const bool want = j < n_cplx;
+    const uint32_t at = warp_append(want, &counters[CNT_PUB]);
+    if (want) list[at] = (uint32_t) cplx[j].lo;
+}
+
+__global__ void __launch_bounds__(SH_THREADS) sh_gather_kernel(const uint32_t *__restrict__ list, uint32_t n_list, const E128 *__restrict__ frag,
+                                                               const uint64_t *__restrict__ hk, const NameTag *__restrict__ tag,
+                                                               PubEntry *__restrict__ out) {
+    const uint32_t j = blockIdx.x * SH_THREADS + threadIdx.x;
+    if (j >= n_list) return;
+    const uint32_t i = list[j];
+    PubEntry p;
+    p.frag = ld_frag(frag + i);
+    p.hk = hk[i];
+    p.rsv = 0;
+    p.tag = tag[i];
+    out[j] = p;
+}
+
+// ---- phase 2: a name published elsewhere that is a complete couple here -------------------------------
+// The couple is retracted (the sequential toggle may pair its records differently once the other
+// shards' sightings are interleaved) and both records are published in the second round.
+__global__ void __launch_bounds__(SH_THREADS) sh_probe_kernel(const PubEntry *__restrict__ pub, uint64_t n_pub, ShardParams S,
+                                                              MateSlot *__restrict__ table, uint64_t n_slots, E128 *__restrict__ pair,
+                                                              uint32_t *__restrict__ list2) {
+    const uint64_t j = (uint64_t) blockIdx.x * SH_THREADS + threadIdx.x;
+    if (j >= n_pub) return;
+    const uint64_t g = bits_get(pub[j].frag, S.kl.f_idx, S.kl.idx_bits);
+    if (g - S.idx_base < S.n) return;      // one of mine
+    const uint64_t h = pub[j].hk;
+    uint64_t s = slot_of(h, n_slots);
+    while (true) {
+        const uint64_t k = table[s].key;
+        if (k == 0) return;
+        if (k == h) break;
+        if (++s == n_slots) s = 0;
+    }
+    unsigned long long *vp = reinterpret_cast<unsigned long long *>(&table[s].val);
+    const unsigned long long v = *vp;
+    if ((v >> 32) != 2) return;                       // not a couple, or already retracted (bit 63 set)
+    if (atomicCAS(vp, v, v | (1ull << 63)) != v) return;      // another entry of the same name got here first
+    const uint32_t pos = table[s].pair_pos;
+    if (pos == SLOT_NO_PAIR) return;                  // hash-equal records with different names: published in round 1
+    reinterpret_cast<ulonglong2 *>(pair)[pos] = make_ulonglong2(~0ull, ~0ull);
+    atomicAdd(&S.counters[CNT_PAIRS_RETRACTED], 1u);
+    const uint32_t at = atomicAdd(&S.counters[CNT_PUB], 2u);
+    list2[at] = (uint32_t) (table[s].who >> 32);
+    list2[at + 1] = (uint32_t) table[s].who;
+}
+
+// ---- phase 3: replay of the published set -------------------------------------------------------------
+// sort entry: hi = key hash, lo = (global ordinal << 32) | position in the published array
+__global__ void __launch_bounds__(SH_THREADS) sh_wbuild_kernel(const PubEntry *__restrict__ w, uint32_t n_w, KeyLayout L, E128 *__restrict__ out) {
+    const uint32_t j = blockIdx.x * SH_THREADS + threadIdx.x;
+    if (j >= n_w) return;
+    E128 e;
+    e.hi = w[j].hk;
+    e.lo = (bits_get(w[j].frag, L.f_idx, L.idx_bits) << 32) | j;
+    out[j] = e;
+}
+
+// The reference's map key is the byte string RG value + ":" + name (mark_duplicates.cpp:214), so
+// ("a", ":x") and ("a:", "x") are the SAME key.  Rebuild that string from a tag: the read-group
+// value comes back out of the host-resolved @RG table, the name out of the tag words.  Name bytes
+// beyond the 29 a tag holds are not available here: two keys that agree on length, on everything
+// a tag holds and on the 64-bit hash of the whole key (they are in the same hash segment) are taken as equal.
+struct PubKey {
+    const uint8_t *rg;
+    uint32_t rg_len, name_len;
+    const NameTag *t;
+    bool opaque;      // read group not listed in the header: its bytes are unknown on this rank
+};
+__device__ __forceinline__ PubKey pub_key(const NameTag &t, const RgTable &rg) {
+    PubKey k;
+    const uint32_t code = t.w[0] & 0xFFFFu, l_name = (t.w[0] >> 16) & 0xFFu;
+    k.t = &t;
+    k.name_len = l_name ? l_name - 1 : 0;
+    k.opaque = code == RGC_UNKNOWN;
+    k.rg = rg.bytes;
+    k.rg_len = 0;
+    if (code < RGC_UNKNOWN && (int) code < rg.n) {
+        k.rg = rg.bytes + rg.off[code];
+        k.rg_len = rg.off[code + 1] - rg.off[code];
+    }
+    return k;
+}
+__device__ __forceinline__ int pub_key_byte(const PubKey &k, uint32_t i) {      // -1: beyond what the tag holds
+    if (i < k.rg_len) return k.rg[i];
+    if (i == k.rg_len) return ':';
+    const uint32_t j = i - k.rg_len - 1;
+    if (j >= NAME_TAG_BYTES) return -1;
+    return j == 0 ? (int) (k.t->w[0] >> 24) : (int) ((k.t->w[(j + 3) >> 2] >> (8 * ((j + 3) & 3))) & 0xFFu);
+}
+__device__ bool pub_keys_equal(const NameTag &ta, const NameTag &tb, const RgTable &rg) {
+    const PubKey a = pub_key(ta, rg), b = pub_key(tb, rg);
+    if (a.opaque || b.opaque) {      // fall back to the tags themselves (plus the shared hash)
+        bool same = true;
+        for (int k = 0; k < 8; k++) same = same && ta.w[k] == tb.w[k];
+        return same;
+    }
+    const uint32_t la = a.rg_len + 1 + a.name_len, lb = b.rg_len + 1 + b.name_len;
+    if (la != lb) return false;
+    for (uint32_t i = 0; i < la; i++) {
+        const int x = pub_key_byte(a, i), y = pub_key_byte(b, i);
+        if (x >= 0 && y >= 0 && x != y) return false;
+    }
+    return true;
+}
+
+// One thread per hash value: the reference's toggle (tmp.put / tmp.remove, mark_duplicates.cpp:216-223)
+// over that hash's sightings in global file order, keys compared as pub_keys_equal does.  Every rank
+// replays the same list and keeps the pairs whose key it owns.
+__global__ void __launch_bounds__(SH_THREADS) sh_replay_kernel(const E128 *__restrict__ sorted, uint32_t n_w, const PubEntry *__restrict__ w,
+                                                               uint8_t *__restrict__ state, ShardParams S, E128 *__restrict__ pair,
+                                                               uint32_t pair_cap, uint32_t *__restrict__ mate_of, uint64_t *__restrict__ fm,
+                                                               uint32_t fm_cap, RgTable rg) {
+    const uint32_t j = blockIdx.x * SH_THREADS + threadIdx.x;
+    if (j >= n_w) return;
+    const uint64_t h = sorted[j].hi;
+    if (j > 0 && sorted[j - 1].hi == h) return;      // not a segment head
+    uint32_t end = j;
+    while (end < n_w && sorted[end].hi == h) state[end++] = 0;
+    for (uint32_t a = j; a < end; a++) {
+        const PubEntry &pa = w[(uint32_t) sorted[a].lo];
+        if (a > j && sorted[a].lo >> 32 == sorted[a - 1].lo >> 32) continue;      // the same record published twice
+        int found = -1;
+        for (uint32_t b = j; b < a; b++) {
+            if (!state[b]) continue;
+            if (pub_keys_equal(pa.tag, w[(uint32_t) sorted[b].lo].tag, rg)) { found = (int) b; break; }
+        }
+        if (found < 0) { state[a] = 1; continue; }
+        state[found] = 0;
+        const PubEntry &pb = w[(uint32_t) sorted[found].lo];      // the earlier sighting
+        uint32_t i1, i2;
+        const E128 ent = make_pair_entry(S.kl, pb.frag, pa.frag, &i1, &i2, 0);      // global ordinals
+        if (owner_of(S, pair_packed(S.kl, ent)) != S.rank) continue;
+        const uint32_t pos = atomicAdd(&S.counters[CNT_PAIRS], 1u);
+        if (pos < pair_cap) reinterpret_cast<ulonglong2 *>(pair)[pos] = make_ulonglong2(ent.lo, ent.hi);
+        const uint64_t l1 = (uint64_t) i1 - S.idx_base;
+        if (l1 < S.n) mate_of[l1] = i2;
+        else {
+            const uint32_t at = atomicAdd(&S.counters[CNT_FM], 1u);
+            if (at < fm_cap) fm[at] = ((uint64_t) i1 << 32) | i2;
+        }
+    }
+}
+
+// ---- phase 4: entries whose key belongs to another rank -------------------------------------------------
+// kind 0: fragment entries, kind 1: pair entries.  Routed entries leave the local list (all-ones = dead).
+__global__ void __launch_bounds__(SH_THREADS) sh_route_kernel(E128 *__restrict__ ents, uint64_t n_ents, int kind, ShardParams S,
+                                                              const uint32_t *__restrict__ mate_of, const uint64_t *__restrict__ fm, uint32_t n_fm,
+                                                              RouteEntry *__restrict__ out, uint32_t out_cap, int dry) {
+    const uint64_t j = (uint64_t) blockIdx.x * SH_THREADS + threadIdx.x;
+    bool want = false;
+    E128 e;
+    e.lo = e.hi = 0;
+    if (j < n_ents) {
+        e = ld_frag(ents + j);
+        if (!is_dead(e)) want = owner_of(S, kind ? pair_packed(S.kl, e) : frag_packed(S.kl, e)) != S.rank;
+    }
+    const uint32_t at = warp_append(want, &S.counters[CNT_ROUTE]);
+    if (!want) return;
+    if (dry) {      // counting pass: nothing moves
+        if (kind) atomicAdd(&S.counters[CNT_SCRATCH0], 1u);
+        return;
+    }
+    RouteEntry r;
+    r.e = e;
+    r.kind = (uint32_t) kind;
+    r.idx2 = 0;
+    r.rsv = 0;
+    if (kind) {
+        const uint32_t i1 = (uint32_t) bits_get(e, S.kl.p_idx, S.kl.idx_bits);
+        const uint64_t l1 = (uint64_t) i1 - S.idx_base;
+        if (l1 < S.n) r.idx2 = mate_of[l1];
+        else if (n_fm) {
+            uint32_t lo = 0, hi = n_fm;
+            while (lo < hi) {
+                uint32_t mid = (lo + hi) >> 1;
+                if ((uint32_t) (fm[mid] >> 32) < i1) lo = mid + 1; else hi = mid;
+            }
+            r.idx2 = (uint32_t) fm[lo];
+        }
+        atomicAdd(&S.counters[CNT_SCRATCH0], 1u);      // pair entries that left
+    }
+    if (at < out_cap) out[at] = r;
+    reinterpret_cast<ulonglong2 *>(ents)[j] = make_ulonglong2(~0ull, ~0ull);
+}
+
+__global__ void __launch_bounds__(SH_THREADS) sh_receive_kernel(const RouteEntry *__restrict__ in, uint64_t n_in, ShardParams S,
+                                                                E128 *__restrict__ frag_extra, uint32_t frag_cap, E128 *__restrict__ pair,
+                                                                uint32_t pair_cap, uint32_t *__restrict__ mate_of, uint64_t *__restrict__ fm,
+                                                                uint32_t fm_cap) {
+    const uint64_t j = (uint64_t) blockIdx.x * SH_THREADS + threadIdx.x;
+    if (j >= n_in) return;
+    const RouteEntry r = in[j];
+    if (owner_of(S, r.kind ? pair_packed(S.kl, r.e) : frag_packed(S.kl, r.e)) != S.rank) return;
+    if (r.kind == 0) {
+        const uint32_t at = atomicAdd(&S.counters[CNT_FRAG_EXTRA], 1u);
+        if (at < frag_cap) reinterpret_cast<ulonglong2 *>(frag_extra)[at] = make_ulonglong2(r.e.lo, r.e.hi);
+    } else {
+        const uint32_t pos = atomicAdd(&S.counters[CNT_PAIRS], 1u);
+        if (pos < pair_cap) reinterpret_cast<ulonglong2 *>(pair)[pos] = make_ulonglong2(r.e.lo, r.e.hi);
+        const uint32_t i1 = (uint32_t) bits_get(r.e, S.kl.p_idx, S.kl.idx_bits);
+        const uint64_t l1 = (uint64_t) i1 - S.idx_base;
+        if (l1 < S.n) mate_of[l1] = r.idx2;
+        else {
+            const uint32_t at = atomicAdd(&S.counters[CNT_FM], 1u);
+            if (at < fm_cap) fm[at] = ((uint64_t) i1 << 32) | r.idx2;
+        }
+    }
+}
+
+// foreign-mate couples <-> sortable 16-byte entries (sorted by idx1 = bits [32, 64))
+__global__ void __launch_bounds__(SH_THREADS) sh_fm_pack_kernel(const uint64_t *__restrict__ fm, uint32_t n, E128 *__restrict__ out) {
+    const uint32_t j = blockIdx.x * SH_THREADS + threadIdx.x;
+    if (j < n) { E128 e; e.lo = fm[j]; e.hi = 0; out[j] = e; }
+}
+__global__ void __launch_bounds__(SH_THREADS) sh_fm_unpack_kernel(const E128 *__restrict__ in, uint32_t n, uint64_t *__restrict__ fm) {
+    const uint32_t j = blockIdx.x * SH_THREADS + threadIdx.x;
+    if (j < n) fm[j] = in[j].lo;
+}
+
+// ---- phase 6: marks decided on other ranks --------------------------------------------------------------
+__global__ void __launch_bounds__(SH_THREADS) sh_apply_marks_kernel(const uint32_t *__restrict__ marks, uint64_t n_marks, uint64_t idx_base,
+                                                                    uint64_t n, uint8_t *__restrict__ dup) {
+    const uint64_t j = (uint64_t) blockIdx.x * SH_THREADS + threadIdx.x;
+    if (j >= n_marks) return;
+    const uint64_t l = (uint64_t) marks[j] - idx_base;
+    if (l < n) dup[l] = 1;
+}
+
+// ---- launchers --------------------------------------------------------------------------------------------
+static inline uint32_t grid_for(uint64_t n) { return (uint32_t) ((n + SH_THREADS - 1) / SH_THREADS); }
+
+#define SH_LAUNCH(n, call)                          \
+    do {                                            \
+        if ((n) > 0) {                              \
+            call;                                   \
+            *launches += 1;                         \
+            OGE_CUDA_TRY(cudaGetLastError());       \
+        }                                           \
+    } while (0)
+
+int launch_sh_singletons(const MateSlot *table, uint64_t n_slots, uint32_t *list, uint32_t *counters, cudaStream_t s, uint64_t *launches) {
+    SH_LAUNCH(n_slots, (sh_singletons_kernel<<<grid_for(n_slots), SH_THREADS, 0, s>>>(table, n_slots, list, counters)));
+    return 0;
+}
+int launch_sh_complex(const E128 *cplx, uint32_t n_cplx, uint32_t *list, uint32_t *counters, cudaStream_t s, uint64_t *launches) {
+    SH_LAUNCH(n_cplx, (sh_complex_kernel<<<grid_for(n_cplx), SH_THREADS, 0, s>>>(cplx, n_cplx, list, counters)));
+    return 0;
+}
+int launch_sh_gather(const uint32_t *list, uint32_t n_list, const E128 *frag, const uint64_t *hk, const NameTag *tag, PubEntry *out,
+                     cudaStream_t s, uint64_t *launches) {
+    SH_LAUNCH(n_list, (sh_gather_kernel<<<grid_for(n_list), SH_THREADS, 0, s>>>(list, n_list, frag, hk, tag, out)));
+    return 0;
+}
+int launch_sh_probe(const PubEntry *pub, uint64_t n_pub, const ShardParams &S, MateSlot *table, uint64_t n_slots, E128 *pair, uint32_t *list2,
+                    cudaStream_t s, uint64_t *launches) {
+    SH_LAUNCH(n_pub, (sh_probe_kernel<<<grid_for(n_pub), SH_THREADS, 0, s>>>(pub, n_pub, S, table, n_slots, pair, list2)));
+    return 0;
+}
+int launch_sh_wbuild(const PubEntry *w, uint32_t n_w, const KeyLayout &L, E128 *out, cudaStream_t s, uint64_t *launches) {
+    SH_LAUNCH(n_w, (sh_wbuild_kernel<<<grid_for(n_w), SH_THREADS, 0, s>>>(w, n_w, L, out)));
+    return 0;
+}
+int launch_sh_replay(const E128 *sorted, uint32_t n_w, const PubEntry *w, uint8_t *state, const ShardParams &S, E128 *pair, uint32_t pair_cap,
+                     uint32_t *mate_of, uint64_t *fm, uint32_t fm_cap, const RgTable &rg, cudaStream_t s, uint64_t *launches) {
+    SH_LAUNCH(n_w, (sh_replay_kernel<<<grid_for(n_w), SH_THREADS, 0, s>>>(sorted, n_w, w, state, S, pair, pair_cap, mate_of, fm, fm_cap, rg)));
+    return 0;
+}
+int launch_sh_route(E128 *ents, uint64_t n_ents, int kind, const ShardParams &S, const uint32_t *mate_of, const uint64_t *fm, uint32_t n_fm,
+                    RouteEntry *out, uint32_t out_cap, int dry, cudaStream_t s, uint64_t *launches) {
+    SH_LAUNCH(n_ents, (sh_route_kernel<<<grid_for(n_ents), SH_THREADS, 0, s>>>(ents, n_ents, kind, S, mate_of, fm, n_fm, out, out_cap, dry)));
+    return 0;
+}
+int launch_sh_receive(const RouteEntry *in, uint64_t n_in, const ShardParams &S, E128 *frag_extra, uint32_t frag_cap, E128 *pair,
+                      uint32_t pair_cap, uint32_t *mate_of, uint64_t *fm, uint32_t fm_cap, cudaStream_t s, uint64_t *launches) {
+    SH_LAUNCH(n_in, (sh_receive_kernel<<<grid_for(n_in), SH_THREADS, 0, s>>>(in, n_in, S, frag_extra, frag_cap, pair, pair_cap, mate_of, fm, fm_cap)));
+    return 0;
+}
+int launch_sh_fm_pack(const uint64_t *fm, uint32_t n, E128 *out, cudaStream_t s, uint64_t *launches) {
+    SH_LAUNCH(n, (sh_fm_pack_kernel<<<grid_for(n), SH_THREADS, 0, s>>>(fm, n, out)));
+    return 0;
+}
+int launch_sh_fm_unpack(const E128 *in, uint32_t n, uint64_t *fm, cudaStream_t s, uint64_t *launches) {
+    SH_LAUNCH(n, (sh_fm_unpack_kernel<<<grid_for(n), SH_THREADS, 0, s>>>(in, n, fm)));
+    return 0;
+}
+int launch_sh_apply_marks(const uint32_t *marks, uint64_t n_marks, uint64_t idx_base, uint64_t n, uint8_t *dup, cudaStream_t s,
+                          uint64_t *launches) {
+    SH_LAUNCH(n_marks, (sh_apply_marks_kernel<<<grid_for(n_marks), SH_THREADS, 0, s>>>(marks, n_marks, idx_base, n, dup)));
+    return 0;
+}
+
+}  // namespace oge

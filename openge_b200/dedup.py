@@ -56,7 +56,8 @@ EXPORTS = ["oge_gpu_dedup_create", "oge_gpu_dedup_destroy", "oge_gpu_dedup_set_r
            "oge_gpu_dedup_reset", "oge_gpu_dedup_get_stats", "oge_gpu_dedup_debug_ends",
            "oge_gpu_dedup_device_ptrs", "oge_gpu_host_alloc", "oge_gpu_host_free", "oge_gpu_device_count",
            "oge_gpu_last_error", "oge_gpu_abi_version", "oge_gpu_debug_sort128", "oge_gpu_debug_sort_bench",
-           "oge_gpu_set_sort_variant"]
+           "oge_gpu_set_sort_variant", "oge_gpu_shard_setup", "oge_gpu_shard_begin", "oge_gpu_shard_probe",
+           "oge_gpu_shard_replay", "oge_gpu_shard_route", "oge_gpu_shard_finish", "oge_gpu_shard_apply"]
 
 
 class DedupError(RuntimeError):
@@ -99,6 +100,13 @@ def lib():
         L.oge_gpu_debug_sort_bench.argtypes = [C.c_int, u64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u64,
                                                C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.oge_gpu_set_sort_variant.argtypes = [C.c_int]
+        L.oge_gpu_shard_setup.argtypes = [vp, u64, vp, vp, vp]
+        L.oge_gpu_shard_begin.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
+        L.oge_gpu_shard_probe.argtypes = [vp, vp, u64, C.POINTER(vp), C.POINTER(u64)]
+        L.oge_gpu_shard_replay.argtypes = [vp, vp, u64]
+        L.oge_gpu_shard_route.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
+        L.oge_gpu_shard_finish.argtypes = [vp, vp, u64, C.POINTER(vp), C.POINTER(u64)]
+        L.oge_gpu_shard_apply.argtypes = [vp, vp, u64]
         for name in EXPORTS:
             getattr(L, name)
         _lib = L
@@ -251,6 +259,36 @@ class DedupContext:
         out = np.zeros(self.n, dtype=END_DTYPE)
         _check(lib().oge_gpu_dedup_debug_ends(self._h, out.ctypes.data, self.n))
         return out
+
+    # ---- range sharding (include/oge_gpu_dedup.h, oge_gpu_shard_*): device pointers in and out
+    def shard_setup(self, global_n, bases, split_ref, split_pos):
+        b = np.ascontiguousarray(bases, dtype=np.uint64)
+        r = np.ascontiguousarray(split_ref if len(split_ref) else [0], dtype=np.int32)
+        p = np.ascontiguousarray(split_pos if len(split_pos) else [0], dtype=np.int32)
+        _check(lib().oge_gpu_shard_setup(self._h, int(global_n), b.ctypes.data, r.ctypes.data, p.ctypes.data))
+
+    def _out_call(self, fn, *args):
+        ptr, cnt = C.c_void_p(), C.c_uint64()
+        _check(fn(self._h, *args, C.byref(ptr), C.byref(cnt)))
+        return ptr.value or 0, int(cnt.value)
+
+    def shard_begin(self):
+        return self._out_call(lib().oge_gpu_shard_begin)
+
+    def shard_probe(self, ptr, n):
+        return self._out_call(lib().oge_gpu_shard_probe, ptr, n)
+
+    def shard_replay(self, ptr, n):
+        _check(lib().oge_gpu_shard_replay(self._h, ptr, n))
+
+    def shard_route(self):
+        return self._out_call(lib().oge_gpu_shard_route)
+
+    def shard_finish(self, ptr, n):
+        return self._out_call(lib().oge_gpu_shard_finish, ptr, n)
+
+    def shard_apply(self, ptr, n):
+        _check(lib().oge_gpu_shard_apply(self._h, ptr, n))
 
     def device_ptrs(self):
         r, o, f = C.c_void_p(), C.c_void_p(), C.c_void_p()

@@ -1,0 +1,386 @@
+"""Range-sharded dedup over several GPUs: host orchestration.
+
+One coordinate-sorted file is cut into contiguous record ranges, one per rank.  Each rank keeps its
+records, end entries, sorts and selects on its own GPU; four small lists cross ranks per run, each
+delivered to every rank by an all-to-all (NCCL on GPUs, gloo in the CPU tests):
+
+    begin   ->  published entries, round 1   (records whose RG:name key was not seen exactly twice locally)
+    probe   ->  published entries, round 2   (local couples of names published elsewhere, retracted)
+    replay      every rank replays the published set in global file order, keeps the pairs it owns
+    route   ->  end entries whose key lies in another rank's coordinate range
+    finish  ->  marks on records of other ranks
+    apply       flag write
+
+The result equals the reference's single-stream `openge dedup --nosplit -v`, not its own
+split-by-chromosome mode.  The per-phase device work is behind `ShardEngine`;
+`CudaShardEngine` drives the C ABI (oge_gpu_shard_*), the test suite plugs in a numpy model of the
+same protocol (tests/sharded_model.py) to run the orchestration under gloo without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+
+import numpy as np
+
+PUB_BYTES, ROUTE_BYTES, MARK_BYTES = 64, 32, 4
+
+
+# --------------------------------------------------------------------------------------- ranges
+class ShardPlan:
+    """Record ranges and key ranges of a `world`-way split."""
+
+    def __init__(self, bases, split_ref, split_pos):
+        self.bases = [int(b) for b in bases]                  # world + 1 global ordinals
+        self.split_ref = [int(r) for r in split_ref]          # world - 1: refID of the first record of ranks 1..
+        self.split_pos = [int(p) for p in split_pos]
+        self.world = len(self.bases) - 1
+        self.global_n = self.bases[-1]
+
+
+def _first_key(records, offsets, i):
+    o = int(offsets[i])
+    ref, pos = np.frombuffer(records[o + 4: o + 12].tobytes(), dtype="<i4")
+    return int(ref), int(pos)
+
+
+def split_bam(bam, world: int):
+    """Cut a BamFile into `world` contiguous record ranges of (nearly) equal record count.
+    -> (ShardPlan, [(records, offsets), ...])"""
+    n = bam.n
+    cuts = [n * r // world for r in range(world + 1)]
+    shards, sref, spos = [], [], []
+    for r in range(world):
+        lo, hi = cuts[r], cuts[r + 1]
+        b0, b1 = int(bam.offsets[lo]), int(bam.offsets[hi])
+        shards.append((bam.records[b0:b1], (bam.offsets[lo: hi + 1] - bam.offsets[lo]).astype(np.uint64)))
+        if r > 0:
+            if lo < n:
+                ref, pos = _first_key(bam.records, bam.offsets, lo)
+            else:
+                ref, pos = -1, -1      # an empty tail shard owns no key
+            sref.append(ref)
+            spos.append(pos)
+    return ShardPlan(cuts, sref, spos), shards
+
+
+# --------------------------------------------------------------------------------------- engines
+class ShardEngine:
+    """Per-rank device work between the exchanges.  Lists are 1-D uint8 torch tensors on `device`."""
+    device = "cpu"
+
+    def begin(self): raise NotImplementedError
+    def probe(self, pub_all): raise NotImplementedError
+    def replay(self, w): raise NotImplementedError
+    def route(self): raise NotImplementedError
+    def finish(self, route_all): raise NotImplementedError
+    def apply(self, marks_all): raise NotImplementedError
+    def flags(self): raise NotImplementedError
+
+
+class _DevView:
+    """Borrowed device memory as a __cuda_array_interface__ object (torch.as_tensor makes a view)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class CudaShardEngine(ShardEngine):
+    """One oge_gpu_dedup_ctx driven through the sharded C ABI (include/oge_gpu_dedup.h)."""
+
+    def __init__(self, records, offsets, header_text, refs, plan: ShardPlan, rank: int, device: int = 0, pinned_ptr=None,
+                 profile_events=False):
+        import torch
+        from . import dedup
+        self.torch = torch
+        self.device = "cuda:%d" % device
+        self.rank = rank
+        self.n = len(offsets) - 1
+        max_len = max([l for _, l in refs], default=0)
+        self.ctx = dedup.DedupContext(n_ref=len(refs), max_ref_len=max_len, device=device, rank=rank, world=plan.world,
+                                      index_base=plan.bases[rank], profile_events=profile_events,
+                                      capacity_records=self.n, capacity_bytes=int(len(records)))
+        self.ctx.set_header(header_text)
+        self.ctx.shard_setup(plan.global_n, plan.bases, plan.split_ref, plan.split_pos)
+        if self.n:
+            if pinned_ptr is not None:
+                self._off_pin = dedup.PinnedBuffer(offsets.nbytes)
+                self._off_pin.array.view(np.uint64)[:] = offsets
+                self.ctx.push_async(pinned_ptr, int(len(records)), self._off_pin.ptr, self.n)
+                self.ctx.sync()
+            else:
+                self.ctx.push(records, offsets)
+
+    def _take(self, ptr, count, item):
+        torch = self.torch
+        if not count:
+            return torch.empty(0, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            t = torch.as_tensor(_DevView(ptr, count * item), device=self.device).clone()
+        return t
+
+    def _give(self, t, item):
+        torch = self.torch
+        assert t.dtype == torch.uint8 and t.numel() % item == 0
+        torch.cuda.current_stream(self.device).synchronize()      # the library works on its own stream
+        return (t.data_ptr() if t.numel() else None), t.numel() // item
+
+    def begin(self):
+        return self._take(*self.ctx.shard_begin(), PUB_BYTES)
+
+    def probe(self, pub_all):
+        return self._take(*self.ctx.shard_probe(*self._give(pub_all, PUB_BYTES)), PUB_BYTES)
+
+    def replay(self, w):
+        self.ctx.shard_replay(*self._give(w, PUB_BYTES))
+
+    def route(self):
+        return self._take(*self.ctx.shard_route(), ROUTE_BYTES)
+
+    def finish(self, route_all):
+        return self._take(*self.ctx.shard_finish(*self._give(route_all, ROUTE_BYTES)), MARK_BYTES)
+
+    def apply(self, marks_all):
+        self.ctx.shard_apply(*self._give(marks_all, MARK_BYTES))
+
+    def flags(self):
+        return self.ctx.flags()
+
+    def stats(self):
+        return self.ctx.stats()
+
+    def close(self):
+        self.ctx.close()
+
+
+# --------------------------------------------------------------------------------------- exchanges
+class LocalExchange:
+    """All ranks live in this process (several contexts on one GPU, or the numpy model): every
+    rank's list is simply concatenated in rank order."""
+
+    def __init__(self):
+        self.bytes_moved = 0
+
+    def __call__(self, lists):
+        import torch
+        self.bytes_moved += sum(int(t.numel()) for t in lists) * max(0, len(lists) - 1)
+        return torch.cat(lists) if len(lists) > 1 else lists[0]
+
+
+class AllToAllExchange:
+    """One rank per process under torch.distributed.  Every rank's list goes to every rank with
+    all_to_all_single (the path's only collective): first the byte counts, then the payload with
+    uneven splits.  Returns the lists concatenated in rank order."""
+
+    def __init__(self, dist, device, timed=False):
+        import torch
+        self.dist, self.torch, self.device = dist, torch, device
+        self.world = dist.get_world_size()
+        self.bytes_moved = 0
+        self.ms = 0.0
+        self.timed = timed and str(device).startswith("cuda")
+
+    def __call__(self, lists):
+        torch, dist, W = self.torch, self.dist, self.world
+        (mine,) = lists
+        if self.timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        n_mine = torch.full((W,), mine.numel(), dtype=torch.int64, device=self.device)
+        n_all = torch.empty(W, dtype=torch.int64, device=self.device)
+        dist.all_to_all_single(n_all, n_mine)
+        counts = [int(x) for x in n_all.tolist()]
+        out = torch.empty(sum(counts), dtype=torch.uint8, device=self.device)
+        if sum(counts) or mine.numel():
+            send = mine.repeat(W) if mine.numel() else mine
+            dist.all_to_all_single(out, send, output_split_sizes=counts, input_split_sizes=[int(mine.numel())] * W)
+        if self.timed:
+            e1.record()
+            e1.synchronize()
+            self.ms += e0.elapsed_time(e1)
+        self.bytes_moved += int(mine.numel()) * (W - 1)
+        return out
+
+
+# --------------------------------------------------------------------------------------- the protocol
+def run_phases(engines, exchange):
+    """Drive one sharded run over the local `engines` (one per process under torch.distributed, or
+    all ranks in-process).  Afterwards every engine's flags() are final."""
+    import torch
+    pub_all = exchange([e.begin() for e in engines])
+    pub2_all = exchange([e.probe(pub_all) for e in engines])
+    w = torch.cat([pub_all, pub2_all]) if pub2_all.numel() else pub_all
+    for e in engines:
+        e.replay(w)
+    route_all = exchange([e.route() for e in engines])
+    marks_all = exchange([e.finish(route_all) for e in engines])
+    for e in engines:
+        e.apply(marks_all)
+    return {"published": int(w.numel()) // PUB_BYTES, "routed": int(route_all.numel()) // ROUTE_BYTES,
+            "marks": int(marks_all.numel()) // MARK_BYTES}
+
+
+def dedup_in_process(bam, world: int, device: int = 0):
+    """All `world` ranks as contexts on ONE GPU (tests): -> (flags of the whole file, info dict)."""
+    plan, shards = split_bam(bam, world)
+    engines = [CudaShardEngine(rec, off, bam.text, bam.refs, plan, r, device=device) for r, (rec, off) in enumerate(shards)]
+    try:
+        info = run_phases(engines, LocalExchange())
+        flags = np.concatenate([e.flags() for e in engines]) if engines else np.zeros(0, np.uint16)
+        info["stats"] = [e.stats() for e in engines]
+    finally:
+        for e in engines:
+            e.close()
+    return flags, info
+
+
+# --------------------------------------------------------------------------------------- bench support
+def make_rank_shard(workload, scale, rank, world, pinned=True):
+    """Synthetic shard of rank `rank` for the weak-scaling bench: the genome is `world` copies of the
+    workload's contig set; rank r draws the workload's reads on its own copy (own seed), and every
+    rank draws the same small overlay of pairs whose mates lie on two different ranks' contigs
+    (0.5 % of the pairs, 10 % of them duplicates of each other) and merges in the overlay records that
+    fall on its contigs.  The concatenation of the shards is one coordinate-sorted file.
+    -> (records, offsets, header text, contigs, keepalive)"""
+    from . import dedup, synth
+    cfg, contigs, rgs = synth.config(workload, scale)
+    nc = len(contigs)
+    if nc * world > 256:
+        raise ValueError("contig table holds 256 entries: %d ranks x %d contigs" % (world, nc))
+    all_contigs = [("c%d_%s" % (r, name), ln) for r in range(world) for name, ln in contigs]
+    hold = {}
+
+    def alloc(tag):
+        def f(nbytes):
+            if pinned:
+                hold[tag] = dedup.PinnedBuffer(nbytes + 64)
+                return hold[tag].array[:nbytes]
+            return np.empty(nbytes + 64, dtype=np.uint8)[:nbytes]
+        return f
+
+    main = synth.restrict(cfg, all_contigs, rank * nc, (rank + 1) * nc, seed=cfg.seed * 1000 + rank, name_base=rank << 40)
+    main.cross_contig_frac = 0.0
+    rec, offs = synth.generate(main, records_out=alloc("main") if world == 1 else None)
+    if world > 1:
+        over = synth.restrict(cfg, all_contigs, 0, nc * world, seed=cfg.seed * 7919 + 17, name_base=1 << 60)
+        over.n_templates = max(16, int(cfg.n_templates * world * 0.005))
+        over.cross_contig_frac, over.dup_frac = 1.0, 0.10
+        over.single_frac = over.mate_unmapped_frac = over.unmapped_pair_frac = over.secondary_frac = over.supplementary_frac = 0.0
+        orec, ooffs = synth.generate(over)
+        keep = synth.records_on_contigs(orec, ooffs, rank * nc, (rank + 1) * nc)
+        rec, offs = synth.merge_sorted(rec, offs, orec, ooffs, keep, records_out=alloc("merged"))
+    return rec, offs, synth.header_text(all_contigs, rgs), all_contigs, hold
+
+
+def bench(args, rank, world, local_rank, rec, offs, text, contigs, metric, workload_name):
+    """bench.py's N > 1 arm: one rank per process, NCCL all-to-all exchanges, device-timed phases."""
+    import json
+    import os
+    import sys
+
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench as benchmod
+    from . import dedup
+
+    dev = torch.device("cuda", local_rank)
+    n = len(offs) - 1
+    # ranges: record counts and first keys of every rank (setup, not timed)
+    mine = torch.tensor([n] + list(_first_key(rec, offs, 0) if n else (-1, -1)), dtype=torch.int64, device=dev)
+    allv = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allv, mine)
+    counts = [int(v[0]) for v in allv]
+    bases = [0]
+    for c in counts:
+        bases.append(bases[-1] + c)
+    plan = ShardPlan(bases, [int(v[1]) for v in allv[1:]], [int(v[2]) for v in allv[1:]])
+
+    eng = CudaShardEngine(rec, offs, text, contigs, plan, rank, device=local_rank, pinned_ptr=rec.ctypes.data, profile_events=True)
+    ex = AllToAllExchange(dist, dev, timed=True)
+
+    def step():
+        ex.ms = 0.0
+        info = run_phases([eng], ex)
+        st = eng.stats()
+        return st["ms_total"] + ex.ms, st, info, ex.ms
+
+    for _ in range(args.warmup):
+        step()
+    sampler = benchmod.ClockSampler(local_rank)
+    sampler.start()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ms, pass_ms, pass_bytes, pass_launches, launches, ex_ms = [], 0.0, 0, 0, 0, 0.0
+    for _ in range(args.steps):
+        m, st, info, xm = step()
+        ms.append(m)
+        ex_ms += xm
+        pass_ms += st["ms_sort_pass_kernels"]
+        pass_bytes += st["sort_pass_bytes"]
+        pass_launches += st["sort_pass_launches"]
+        launches += st["launches"]
+    dist.barrier()
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    clocks = sampler.stop()
+
+    # max over ranks of the device-timed step (phases on the library stream + exchanges on torch's)
+    t = torch.tensor([float(np.mean(ms)), ex_ms / args.steps, float(st["n_duplicates"]), float(n), wall_ms], dtype=torch.float64, device=dev)
+    mx = t.clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    sm = t.clone()
+    dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    ms_per_step, total_reads, total_dups = float(mx[0]), int(sm[3]), int(sm[2])
+
+    # end to end from pinned host buffers: push + phases + flags back
+    flags_pin = dedup.PinnedBuffer(max(2, n * 2))
+    e2e = []
+    for it in range(1 + max(1, min(args.steps, 2))):
+        eng.ctx.reset()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        if n:
+            eng.ctx.push_async(rec.ctypes.data, int(rec.nbytes), eng._off_pin.ptr, n)
+        run_phases([eng], ex)
+        eng.ctx.flags(flags_pin.array.view(np.uint16)[:n])
+        dist.barrier()
+        e2e.append(time.perf_counter() - t1)
+    e2e_s = torch.tensor([float(np.mean(e2e[1:]))], dtype=torch.float64, device=dev)
+    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    h2d = torch.tensor([float(rec.nbytes + offs.nbytes), float(n * 2)], dtype=torch.float64, device=dev)
+    dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
+
+    if rank == 0:
+        peak, peak_src = benchmod.load_peaks()
+        achieved = (pass_bytes / 1e9) / (pass_ms * 1e-3) if pass_ms > 0 else 0.0
+        traffic = benchmod.load_traffic()
+        line = {
+            "metric": metric, "value": total_reads / (ms_per_step * 1e-3), "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64", "data": "synthetic",
+            "config": {"workload": "%s x %d ranks: every rank holds one coordinate range (a copy of the contig set) of a "
+                                   "%d-read file; 0.5%% of the pairs have their mates on two different ranks" % (workload_name, world, total_reads),
+                       "reads": total_reads, "reads_rank0": n, "l2": "inputs larger than L2",
+                       "wall_ms_per_step": float(mx[4]), "exchange_ms_per_step": float(mx[1]), "duplicates_flagged": total_dups,
+                       "published_entries": info["published"], "routed_entries": info["routed"], "marks_exchanged": info["marks"],
+                       "stage_ms_rank0": {k: st[k] for k in ("ms_endbuild", "ms_join", "ms_sort_pair", "ms_sort_frag", "ms_select", "ms_flags")},
+                       "parallelism": "range-sharded x%d, all-to-all of small lists" % world},
+            "e2e": {"value": total_reads / float(e2e_s[0]), "unit": "reads/s", "h2d_bytes_per_step": int(h2d[0]),
+                    "d2h_bytes_per_step": int(h2d[1]), "ms_per_step": float(e2e_s[0]) * 1e3},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "rs_pass_v2", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "peak_source": peak_src,
+                         "traffic": traffic.get("dram_bytes_per_launch") if traffic else None, "launches_timed": pass_launches,
+                         "avg_launch_ms": pass_ms / pass_launches if pass_launches else None,
+                         "algorithmic_bytes_per_launch": pass_bytes / pass_launches if pass_launches else None, "rank": 0},
+            "cpu_baseline": None,
+        }
+        print(json.dumps(line))
+    eng.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0

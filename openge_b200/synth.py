@@ -31,6 +31,7 @@ class SynthCfg(C.Structure):
         ("predup_frac", C.c_double), ("no_rg_frac", C.c_double), ("unknown_rg_frac", C.c_double),
         ("const_qual_frac", C.c_double), ("extra_tag_frac", C.c_double),
         ("n_rg", C.c_int32), ("hot_loci", C.c_int32), ("dup_same_rg", C.c_int32),
+        ("contig_lo", C.c_int32), ("contig_hi", C.c_int32),
     ]
 
 
@@ -47,6 +48,9 @@ def lib():
         L.oge_synth_emit.restype = C.c_int
         L.oge_synth_emit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.oge_synth_free.argtypes = [C.c_void_p]
+        L.oge_merge_sorted.restype = C.c_uint64
+        L.oge_merge_sorted.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
         L.oge_frame_records.restype = C.c_int64
         L.oge_frame_records.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
         _lib = L
@@ -143,6 +147,43 @@ def generate(cfg: SynthCfg, records_out=None, nthreads: int = 0):
     finally:
         L.oge_synth_free(h)
     return rec, offs
+
+
+def restrict(cfg: SynthCfg, all_contigs, contig_lo: int, contig_hi: int, seed: int, name_base: int = 0) -> SynthCfg:
+    """A copy of ``cfg`` over the contig table ``all_contigs`` [(name, len)] that draws its templates on
+    contigs [contig_lo, contig_hi) only (range shards of a multi-GPU run).  Names are a hash of
+    (template ordinal, seed): different seeds give disjoint name sets."""
+    c = SynthCfg.from_buffer_copy(bytes(cfg))
+    c.seed = seed
+    c.n_contigs = len(all_contigs)
+    for i, (_, ln) in enumerate(all_contigs):
+        c.contig_len[i] = ln
+    c.contig_lo, c.contig_hi = contig_lo, contig_hi
+    return c
+
+
+def records_on_contigs(rec, offs, contig_lo: int, contig_hi: int) -> np.ndarray:
+    """uint8 mask over the records: refID in [contig_lo, contig_hi)."""
+    o = offs[:-1].astype(np.int64)
+    ref = rec[o[:, None] + np.arange(4, 8)].copy().view("<i4").ravel() if len(o) else np.zeros(0, "<i4")
+    return ((ref >= contig_lo) & (ref < contig_hi)).astype(np.uint8)
+
+
+def merge_sorted(rec_a, offs_a, rec_b, offs_b, keep_b, records_out=None):
+    """Merge two coordinate-sorted record chains (B restricted to keep_b) -> (records, offsets)."""
+    L = lib()
+    rec_a, rec_b = np.ascontiguousarray(rec_a), np.ascontiguousarray(rec_b)
+    offs_a, offs_b = np.ascontiguousarray(offs_a, dtype=np.uint64), np.ascontiguousarray(offs_b, dtype=np.uint64)
+    keep_b = np.ascontiguousarray(keep_b, dtype=np.uint8)
+    na, nb = len(offs_a) - 1, len(offs_b) - 1
+    nbytes = C.c_uint64()
+    n = L.oge_merge_sorted(rec_a.ctypes.data, offs_a.ctypes.data, na, rec_b.ctypes.data, offs_b.ctypes.data, nb,
+                           keep_b.ctypes.data, None, None, C.byref(nbytes))
+    out = records_out(nbytes.value) if records_out else np.empty(nbytes.value + 16, dtype=np.uint8)[: nbytes.value]
+    offs = np.empty(n + 1, dtype=np.uint64)
+    L.oge_merge_sorted(rec_a.ctypes.data, offs_a.ctypes.data, na, rec_b.ctypes.data, offs_b.ctypes.data, nb,
+                       keep_b.ctypes.data, out.ctypes.data, offs.ctypes.data, C.byref(nbytes))
+    return out, offs
 
 
 def make(name: str, scale: float = 1.0, seed=None):

@@ -1,0 +1,213 @@
+"""TEST INFRASTRUCTURE: a numpy/python model of the range-sharded protocol (openge_b200/sharded.py,
+DESIGN.md section 6) behind the same ShardEngine interface as the CUDA engine.
+
+It exists so that the host orchestration -- ranges, exchanges, phase order -- can run under
+torch.distributed/gloo on CPU, and so that the protocol itself is checked against the single-stream
+oracle independently of the kernels.  Per-record end fields come from the C oracle
+(oracle.markdup(..., want_ends=True), i.e. buildReadEnds of mark_duplicates.cpp:147-164); the pairing,
+routing and selection below restate sections A.2.3-A.2.5 of SURVEY.md for one shard.
+Pure-python loops: small inputs only.
+"""
+import numpy as np
+import torch
+
+import oracle
+from openge_b200.sharded import ShardEngine
+
+PUB = np.dtype([("gidx", "<i8"), ("lib", "<i2"), ("ref", "<i4"), ("coord", "<i4"), ("rev", "u1"), ("paired", "u1"),
+                ("score", "<i2"), ("klen", "<i4"), ("key", "S256")])
+ROUTE = np.dtype([("kind", "u1"), ("lib", "<i2"), ("ref1", "<i4"), ("coord1", "<i4"), ("orient", "u1"), ("ref2", "<i4"),
+                  ("coord2", "<i4"), ("score", "<i2"), ("idx1", "<i8"), ("idx2", "<i8"), ("paired", "u1")])
+MARK = np.dtype("<i8")
+
+
+def _to_t(a):
+    return torch.from_numpy(np.frombuffer(a.tobytes(), dtype=np.uint8).copy()) if len(a) else torch.empty(0, dtype=torch.uint8)
+
+
+def _from_t(t, dt):
+    return np.frombuffer(t.numpy().tobytes(), dtype=dt)
+
+
+def pairing_key(rec, o0, o1):
+    """RG value + ':' + read name (mark_duplicates.cpp:210-214); tag walk as BamAlignment.cpp:270-294."""
+    p = rec[o0:o1].tobytes()
+    l_name, n_cig = p[12], int.from_bytes(p[16:18], "little")
+    l_seq = int.from_bytes(p[20:24], "little")
+    name = p[36: 36 + max(0, l_name - 1)]
+    t = 36 + l_name + 4 * n_cig + (l_seq + 1) // 2 + l_seq
+    rg = b""
+    sizes = {b"A": 1, b"c": 1, b"C": 1, b"s": 2, b"S": 2, b"i": 4, b"I": 4, b"f": 4}
+    while t + 3 <= len(p):
+        tag, ty = p[t: t + 2], p[t + 2: t + 3]
+        t += 3
+        if tag == b"RG":
+            e = p.find(b"\0", t)
+            rg = p[t: e if e >= 0 else len(p)]
+            break
+        if ty in sizes:
+            t += sizes[ty]
+        elif ty in (b"Z", b"H"):
+            e = p.find(b"\0", t)
+            t = (e if e >= 0 else len(p)) + 1
+        elif ty == b"B":
+            sub, cnt = p[t: t + 1], int.from_bytes(p[t + 1: t + 5], "little")
+            t += 5 + cnt * sizes.get(sub, 1 << 30)
+        else:
+            break
+        if t >= len(p) or p[t] == 0:
+            break
+    return rg + b":" + name
+
+
+class ModelShardEngine(ShardEngine):
+    device = "cpu"
+
+    def __init__(self, records, offsets, header_text, plan, rank):
+        self.rank, self.plan = rank, plan
+        self.base = plan.bases[rank]
+        self.n = len(offsets) - 1
+        self.records, self.offsets = records, offsets
+        if self.n:
+            _, ends, _ = oracle.markdup(records, offsets, header_text, want_ends=True)
+        else:
+            ends = np.zeros(0, dtype=oracle.END_DTYPE)
+        self.ends = ends
+        o = offsets[:-1].astype(np.int64)
+        self.flag_in = records[o[:, None] + np.arange(18, 20)].copy().view("<u2").ravel() if self.n else np.zeros(0, "<u2")
+        self.dup = np.zeros(self.n, dtype=bool)
+        self.splits = list(zip(plan.split_ref, plan.split_pos))
+
+    # rank owning the key range of (ref, coord)
+    def owner(self, ref, coord):
+        return sum(1 for (r, p) in self.splits if r >= 0 and (r, p) <= (ref, coord))
+
+    def _pub(self, i):
+        e = self.ends[i]
+        key = pairing_key(self.records, int(self.offsets[i]), int(self.offsets[i + 1]))
+        assert len(key) <= 256
+        return (self.base + i, e["lib"], e["ref"], e["coord"], 1 if e["orientation"] == 2 else 0, 1 if e["read2Sequence"] != -1 else 0,
+                e["score"], len(key), key)
+
+    @staticmethod
+    def _pair(first, second):
+        """first = earlier sighting.  Flip rule and orientation of mark_duplicates.cpp:226-243, 169-178."""
+        fs, fc, ss, sc = int(first["ref"]), int(first["coord"]), int(second["ref"]), int(second["coord"])
+        keep = ss > fs or (ss == fs and sc >= fc)
+        a, b = (first, second) if keep else (second, first)
+        orient = {(1, 1): 4, (1, 0): 6, (0, 1): 5, (0, 0): 3}[(int(a["rev"]), int(b["rev"]))]
+        score = np.array([(int(first["score"]) + int(second["score"])) & 0xFFFF], dtype=np.uint16).view(np.int16)[0]
+        return (1, first["lib"], a["ref"], a["coord"], orient, b["ref"], b["coord"], score, a["gidx"], b["gidx"], 1)
+
+    def begin(self):
+        by_key = {}
+        for i in range(self.n):
+            if self.ends[i]["pair_eligible"]:
+                by_key.setdefault(pairing_key(self.records, int(self.offsets[i]), int(self.offsets[i + 1])), []).append(i)
+        self.couples, pub = {}, []
+        for key, ids in by_key.items():
+            if len(ids) == 2:
+                self.couples[key] = ids
+            else:
+                pub += ids
+        self.pairs = []      # ROUTE-shaped tuples owned (so far) by this rank
+        return _to_t(np.array([self._pub(i) for i in pub], dtype=PUB))
+
+    def probe(self, pub_all):
+        pa = _from_t(pub_all, PUB)
+        out = []
+        for e in pa:
+            if self.base <= e["gidx"] < self.base + self.n:
+                continue
+            key = bytes(e["key"])[: e["klen"]]
+            if key in self.couples:
+                out += self.couples.pop(key)
+        return _to_t(np.array([self._pub(i) for i in out], dtype=PUB))
+
+    def replay(self, w):
+        # clean local couples first
+        for key, (i, j) in self.couples.items():
+            a = np.array([self._pub(i)], dtype=PUB)[0]
+            b = np.array([self._pub(j)], dtype=PUB)[0]
+            self.pairs.append(self._pair(a, b))
+        wa = _from_t(w, PUB)
+        groups = {}
+        seen = set()
+        for e in wa:
+            if int(e["gidx"]) in seen:
+                continue
+            seen.add(int(e["gidx"]))
+            groups.setdefault(bytes(e["key"])[: e["klen"]], []).append(e)
+        for key, es in groups.items():
+            es.sort(key=lambda e: int(e["gidx"]))
+            for k in range(0, len(es) - 1, 2):      # (1,2), (3,4), ...: the toggle of picard_structures.h:87-96
+                p = self._pair(es[k], es[k + 1])
+                if self.owner(int(p[2]), int(p[3])) == self.rank:
+                    self.pairs.append(p)
+
+    def route(self):
+        out, keep = [], []
+        for p in self.pairs:
+            (out if self.owner(int(p[2]), int(p[3])) != self.rank else keep).append(p)
+        self.pairs = keep
+        self.frags = []
+        for i in range(self.n):
+            e = self.ends[i]
+            if not e["eligible"]:
+                continue
+            f = (0, e["lib"], e["ref"], e["coord"], int(e["orientation"]), -1, -1, e["score"], self.base + i, -1,
+                 1 if e["read2Sequence"] != -1 else 0)
+            (out if self.owner(int(e["ref"]), int(e["coord"])) != self.rank else self.frags).append(f)
+        return _to_t(np.array(out, dtype=ROUTE))
+
+    def _mark(self, g, foreign):
+        if self.base <= g < self.base + self.n:
+            self.dup[g - self.base] = True
+        else:
+            foreign.append(g)
+
+    def finish(self, route_all):
+        for r in _from_t(route_all, ROUTE):
+            if self.owner(int(r["ref1"]), int(r["coord1"])) != self.rank:
+                continue
+            (self.pairs if r["kind"] == 1 else self.frags).append(tuple(r))
+        foreign = []
+        groups = {}
+        for p in self.pairs:
+            groups.setdefault((int(p[1]), int(p[2]), int(p[3]), int(p[4]), int(p[5]), int(p[6])), []).append(p)
+        for g in groups.values():      # mark_duplicates.cpp:488-507: best = max score, then smallest idx1
+            if len(g) < 2:
+                continue
+            best = min(g, key=lambda p: (-int(p[7]), int(p[8])))
+            for p in g:
+                if p is not best:
+                    self._mark(int(p[8]), foreign)
+                    self._mark(int(p[9]), foreign)
+        groups = {}
+        for f in self.frags:
+            groups.setdefault((int(f[1]), int(f[2]), int(f[3]), int(f[4])), []).append(f)
+        for g in groups.values():      # :371-390, :515-540
+            if len(g) < 2 or all(f[10] for f in g):
+                continue
+            if any(f[10] for f in g):
+                for f in g:
+                    if not f[10]:
+                        self._mark(int(f[8]), foreign)
+            else:
+                best = min(g, key=lambda f: (-int(f[7]), int(f[8])))
+                for f in g:
+                    if f is not best:
+                        self._mark(int(f[8]), foreign)
+        return _to_t(np.array(foreign, dtype=MARK))
+
+    def apply(self, marks_all):
+        for g in _from_t(marks_all, MARK):
+            if self.base <= g < self.base + self.n:
+                self.dup[int(g) - self.base] = True
+
+    def flags(self):
+        f = self.flag_in.copy()
+        prim = (f & 0x100) == 0
+        f[prim & self.dup] |= 0x400
+        f[prim & ~self.dup] &= np.uint16(~0x400 & 0xFFFF)
+        return f

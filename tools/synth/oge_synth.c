@@ -44,6 +44,7 @@ typedef struct {
     int32_t n_rg;                /* read groups rg1..rgN (ids "rg%d") */
     int32_t hot_loci;            /* >0: duplicates copy from this many hot templates, Zipf-skewed (C4) */
     int32_t dup_same_rg;         /* 1: a duplicate keeps its source's read group (else redrawn) */
+    int32_t contig_lo, contig_hi;   /* hi > lo: templates are drawn on contigs [lo, hi) only (range shards) */
 } SynthCfg;
 
 typedef struct {
@@ -130,8 +131,13 @@ static uint8_t draw_rg(const SynthCfg *c, uint64_t *s) {
 }
 
 static int32_t draw_contig(const SynthCfg *c, uint64_t *s, const double *cum) {
-    double r = urand(s) * cum[c->n_contigs - 1];
     int32_t lo = 0, hi = c->n_contigs - 1;
+    double base = 0.0, r;
+    if (c->contig_hi > c->contig_lo) {
+        lo = c->contig_lo; hi = c->contig_hi - 1;
+        base = lo ? cum[lo - 1] : 0.0;
+    }
+    r = base + urand(s) * (cum[hi] - base);
     while (lo < hi) { int32_t mid = (lo + hi) / 2; if (cum[mid] > r) hi = mid; else lo = mid + 1; }
     return lo;
 }
@@ -250,8 +256,10 @@ void *oge_synth_plan(const SynthCfg *cfg, uint64_t *n_records, uint64_t *n_bytes
                 g.contig2 = g.contig;
                 if (g.type == 0) {
                     int32_t u2 = u1 + ins - L;
-                    if (urand(&s) < c->cross_contig_frac && c->n_contigs > 1) {
-                        do g.contig2 = (int32_t) irand(&s, c->n_contigs); while (g.contig2 == g.contig);
+                    int32_t c_lo = c->contig_hi > c->contig_lo ? c->contig_lo : 0;
+                    int32_t c_n = c->contig_hi > c->contig_lo ? c->contig_hi - c->contig_lo : c->n_contigs;
+                    if (urand(&s) < c->cross_contig_frac && c_n > 1) {
+                        do g.contig2 = c_lo + (int32_t) irand(&s, (uint64_t) c_n); while (g.contig2 == g.contig);
                         span = c->contig_len[g.contig2] - 2 * L - 1200; if (span < 1) span = 1;
                         u2 = 600 + (int32_t) irand(&s, (uint64_t) span);
                     }
@@ -485,4 +493,36 @@ int64_t oge_frame_records(const uint8_t *buf, uint64_t len, uint64_t *offsets, u
         if (offsets) { if (n >= cap) return -1; offsets[n] = pos; }
     }
     return (int64_t) n;
+}
+
+/* (refID, pos) order of a coordinate-sorted file: unmapped (refID -1) last. */
+static inline uint64_t sort_key_of(const uint8_t *rec) {
+    int32_t ref, pos;
+    memcpy(&ref, rec + 4, 4);
+    memcpy(&pos, rec + 8, 4);
+    if (ref < 0) return ~0ULL;
+    return ((uint64_t)(uint32_t) ref << 32) | (uint32_t)(pos + 1);
+}
+
+/* Merge two coordinate-sorted record chains A and B' (B restricted to the records with keep[i] != 0)
+ * into out_rec / out_off (n_out + 1 offsets); ties keep A first.  With out_rec == NULL only sizes
+ * are computed.  Returns the number of records. */
+uint64_t oge_merge_sorted(const uint8_t *a, const uint64_t *a_off, uint64_t na, const uint8_t *b, const uint64_t *b_off,
+                          uint64_t nb, const uint8_t *keep, uint8_t *out_rec, uint64_t *out_off, uint64_t *out_bytes) {
+    uint64_t i = 0, j = 0, n = 0, pos = 0;
+    while (j < nb && !keep[j]) j++;
+    if (out_off) out_off[0] = 0;
+    while (i < na || j < nb) {
+        int take_a = j >= nb || (i < na && sort_key_of(a + a_off[i]) <= sort_key_of(b + b_off[j]));
+        const uint8_t *src = take_a ? a + a_off[i] : b + b_off[j];
+        uint64_t len = take_a ? a_off[i + 1] - a_off[i] : b_off[j + 1] - b_off[j];
+        if (out_rec) memcpy(out_rec + pos, src, len);
+        pos += len;
+        n++;
+        if (out_off) out_off[n] = pos;
+        if (take_a) i++;
+        else { j++; while (j < nb && !keep[j]) j++; }
+    }
+    if (out_bytes) *out_bytes = pos;
+    return n;
 }
