@@ -98,10 +98,10 @@ def make_shard(workload, scale, rank, world, pinned):
     """Synthetic records for this rank -> (records array, offsets, header text, contigs).
     world == 1: the named config.  world > 1: handled by openge_b200.sharded (range shards)."""
     from openge_b200 import synth
-    cfg, contigs, rgs = synth.config(workload, scale)
     if world > 1:
         from openge_b200 import sharded
-        return sharded.make_rank_shard(cfg, contigs, rgs, rank, world, pinned)
+        return sharded.make_rank_shard(workload, scale, rank, world, pinned)
+    cfg, contigs, rgs = synth.config(workload, scale)
     hold = {}
 
     def alloc(nbytes):
@@ -208,9 +208,8 @@ def workload_name(args):
 # --------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-    if world != args.gpus:
-        if args.gpus > 1 and world == 1:
-            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch with torch.distributed.run for --gpus > 1 (one rank per GPU)")
     from openge_b200 import dedup
     if dedup.device_count() < 1:
         raise SystemExit("bench.py needs a CUDA device: the dedup path has no CPU fallback")
