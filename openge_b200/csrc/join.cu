@@ -19,6 +19,8 @@
 //                 Hash-equal couples whose names differ take the same path.
 // One random 32-byte slot per record (two atomics); mates of a coordinate-sorted file sit a few
 // hundred records apart, so the second touch of a slot and the mate's name are L2 hits.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 #include "pairing.cuh"
 
@@ -127,98 +129,124 @@ __device__ bool name_tails_equal(const uint8_t *pa, const uint8_t *pb, uint32_t 
     return true;
 }
 
+// ITEMS records per thread, staged so that the dependent chain hash -> slot -> counter -> tags -> ends
+// of one record overlaps with the others': the kernel is bound by memory latency, not bandwidth.
+template <int ITEMS>
 __global__ void __launch_bounds__(JOIN_THREADS) mate_join_kernel(JoinParams P) {
-    const uint64_t i = (uint64_t) blockIdx.x * JOIN_THREADS + threadIdx.x;
+    const uint64_t i0 = (uint64_t) blockIdx.x * (JOIN_THREADS * ITEMS) + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1;
-    const uint64_t h = i < P.n ? P.hk[i] : 0;
 
-    bool emit = false, cplx_self = false, cplx_other = false, list_slot = false;
-    uint32_t other = 0, i1 = 0, i2 = 0;
-    uint64_t s = 0;
-    E128 ent;
-    ent.lo = ent.hi = 0;
-    if (h) {
-        s = slot_of(h, P.n_slots);
-        while (true) {      // claim or find the key's slot (a plain L2 read first: half of the arrivals find their key there)
-            unsigned long long *kp = reinterpret_cast<unsigned long long *>(&P.table[s].key);
-            unsigned long long k;
-            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(k) : "l"(kp) : "memory");
-            if (k == h) break;
-            if (k == 0) {
-                k = atomicCAS(kp, 0ull, (unsigned long long) h);
-                if (k == 0 || k == h) break;
+    uint64_t h[ITEMS], s[ITEMS];
+    unsigned long long key0[ITEMS], old[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+        const uint64_t i = i0 + (uint64_t) k * JOIN_THREADS;
+        h[k] = i < P.n ? P.hk[i] : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {      // first probe of every record in flight together
+        s[k] = slot_of(h[k], P.n_slots);
+        key0[k] = 0;
+        if (h[k]) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(key0[k]) : "l"(&P.table[s[k]].key) : "memory");
+    }
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {      // claim or find the key's slot (half of the arrivals find their key with the plain read)
+        if (!h[k]) continue;
+        unsigned long long key = key0[k];
+        while (true) {
+            if (key == h[k]) break;
+            if (key == 0) {
+                key = atomicCAS(reinterpret_cast<unsigned long long *>(&P.table[s[k]].key), 0ull, (unsigned long long) h[k]);
+                if (key == 0 || key == h[k]) break;
             }
-            if (++s == P.n_slots) s = 0;
+            if (++s[k] == P.n_slots) s[k] = 0;
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(key) : "l"(&P.table[s[k]].key) : "memory");
         }
-        const unsigned long long old =
-            atomicAdd(reinterpret_cast<unsigned long long *>(&P.table[s].val), (1ull << 32) + (uint32_t) i + 1u);
-        const uint32_t arrivals = (uint32_t) (old >> 32);
-        if (arrivals == 1) {
-            other = (uint32_t) old - 1u;
-            bool same = true;
-            if (P.verify_names) {
-                const uint4 *ta = reinterpret_cast<const uint4 *>(P.tag + i), *tb = reinterpret_cast<const uint4 *>(P.tag + other);
-                const uint4 a0 = ta[0], a1 = ta[1], b0 = tb[0], b1 = tb[1];
-                same = a0.x == b0.x && a0.y == b0.y && a0.z == b0.z && a0.w == b0.w && a1.x == b1.x && a1.y == b1.y &&
-                       a1.z == b1.z && a1.w == b1.w && (a0.x & 0xFFFFu) != RGC_UNKNOWN;
-                const uint32_t l_name = (a0.x >> 16) & 0xFFu;
-                if (same && l_name > NAME_TAG_BYTES + 1) same = name_tails_equal(P.rec + P.off[i], P.rec + P.off[other], l_name);
-            }
-            if (same) {
-                const uint32_t first = min((uint32_t) i, other), second = max((uint32_t) i, other);      // file order
-                ent = make_pair_entry(P.kl, ld_frag(P.frag + first), ld_frag(P.frag + second), &i1, &i2, P.idx_base);
-                emit = true;
-            } else {
-                cplx_self = cplx_other = true;      // two names, one hash (or read groups the header does not list)
-            }
-        } else if (arrivals >= 2) {
-            cplx_self = true;
-            list_slot = arrivals == 2;
-        }
+    }
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+        old[k] = 0;
+        if (h[k])
+            old[k] = atomicAdd(reinterpret_cast<unsigned long long *>(&P.table[s[k]].val),
+                               (1ull << 32) + (uint32_t) (i0 + (uint64_t) k * JOIN_THREADS) + 1u);
     }
 
-    // ---- warp-aggregated appends
-    uint32_t m = __ballot_sync(0xFFFFFFFFu, emit);
-    uint32_t pair_pos = SLOT_NO_PAIR;
-    if (m) {
-        int leader = __ffs(m) - 1;
-        uint32_t base = 0;
-        if (lane == leader) base = atomicAdd(&P.counters[CNT_PAIRS], (uint32_t) __popc(m));
-        base = __shfl_sync(0xFFFFFFFFu, base, leader);
-        if (emit) {
-            pair_pos = base + __popc(m & lt);
-            reinterpret_cast<ulonglong2 *>(P.pair)[pair_pos] = make_ulonglong2(ent.lo, ent.hi);
-            P.mate_of[i1] = (uint32_t) (i2 + P.idx_base);
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+        const uint64_t i = i0 + (uint64_t) k * JOIN_THREADS;
+        bool emit = false, cplx_self = false, cplx_other = false, list_slot = false;
+        uint32_t other = 0, i1 = 0, i2 = 0;
+        E128 ent;
+        ent.lo = ent.hi = 0;
+        if (h[k]) {
+            const uint32_t arrivals = (uint32_t) (old[k] >> 32);
+            if (arrivals == 1) {      // the second of its name: the sum field is the first one's ordinal
+                other = (uint32_t) old[k] - 1u;
+                bool same = true;
+                if (P.verify_names) {
+                    const uint4 *ta = reinterpret_cast<const uint4 *>(P.tag + i), *tb = reinterpret_cast<const uint4 *>(P.tag + other);
+                    const uint4 a0 = ta[0], a1 = ta[1], b0 = tb[0], b1 = tb[1];
+                    same = a0.x == b0.x && a0.y == b0.y && a0.z == b0.z && a0.w == b0.w && a1.x == b1.x && a1.y == b1.y &&
+                           a1.z == b1.z && a1.w == b1.w && (a0.x & 0xFFFFu) != RGC_UNKNOWN;
+                    const uint32_t l_name = (a0.x >> 16) & 0xFFu;
+                    if (same && l_name > NAME_TAG_BYTES + 1) same = name_tails_equal(P.rec + P.off[i], P.rec + P.off[other], l_name);
+                }
+                if (same) {
+                    const uint32_t first = min((uint32_t) i, other), second = max((uint32_t) i, other);      // file order
+                    ent = make_pair_entry(P.kl, ld_frag(P.frag + first), ld_frag(P.frag + second), &i1, &i2, P.idx_base);
+                    emit = true;
+                } else {
+                    cplx_self = cplx_other = true;      // two names, one hash (or read groups the header does not list)
+                }
+            } else if (arrivals >= 2) {
+                cplx_self = true;
+                list_slot = arrivals == 2;
+            }
         }
+
+        // ---- warp-aggregated appends
+        uint32_t m = __ballot_sync(0xFFFFFFFFu, emit);
+        uint32_t pair_pos = SLOT_NO_PAIR;
+        if (m) {
+            int leader = __ffs(m) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(&P.counters[CNT_PAIRS], (uint32_t) __popc(m));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (emit) {
+                pair_pos = base + __popc(m & lt);
+                reinterpret_cast<ulonglong2 *>(P.pair)[pair_pos] = make_ulonglong2(ent.lo, ent.hi);
+                P.mate_of[i1] = (uint32_t) (i2 + P.idx_base);
+            }
+        }
+        if (emit || cplx_other) {      // what mate_fixup needs should a third record of this name turn up
+            P.table[s[k]].who = ((uint64_t) (uint32_t) i << 32) | other;
+            P.table[s[k]].pair_pos = pair_pos;
+        }
+        uint32_t nc = (cplx_self ? 1u : 0u) + (cplx_other ? 1u : 0u);
+        uint32_t any = __ballot_sync(0xFFFFFFFFu, nc != 0);
+        if (any) {
+            uint32_t x = nc;      // exclusive prefix of nc over the warp
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+                if (lane >= o) x += y;
+            }
+            uint32_t total = __shfl_sync(0xFFFFFFFFu, x, 31);
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&P.counters[CNT_COMPLEX], total);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0) + x - nc;
+            if (cplx_self) {
+                E128 c = complex_entry(h[k], (uint32_t) i);
+                reinterpret_cast<ulonglong2 *>(P.cplx)[base++] = make_ulonglong2(c.lo, c.hi);
+            }
+            if (cplx_other) {
+                E128 c = complex_entry(h[k], other);
+                reinterpret_cast<ulonglong2 *>(P.cplx)[base] = make_ulonglong2(c.lo, c.hi);
+                atomicAdd(&P.counters[CNT_HASH_MISMATCH], 1u);
+            }
+        }
+        if (list_slot) P.cplx_slots[atomicAdd(&P.counters[CNT_COMPLEX_SLOTS], 1u)] = (uint32_t) s[k];
     }
-    if (emit || cplx_other) {      // what mate_fixup needs should a third record of this name turn up
-        P.table[s].who = ((uint64_t) (uint32_t) i << 32) | other;
-        P.table[s].pair_pos = pair_pos;
-    }
-    uint32_t nc = (cplx_self ? 1u : 0u) + (cplx_other ? 1u : 0u);
-    uint32_t any = __ballot_sync(0xFFFFFFFFu, nc != 0);
-    if (any) {
-        uint32_t x = nc;      // exclusive prefix of nc over the warp
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
-            if (lane >= o) x += y;
-        }
-        uint32_t total = __shfl_sync(0xFFFFFFFFu, x, 31);
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&P.counters[CNT_COMPLEX], total);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0) + x - nc;
-        if (cplx_self) {
-            E128 c = complex_entry(h, (uint32_t) i);
-            reinterpret_cast<ulonglong2 *>(P.cplx)[base++] = make_ulonglong2(c.lo, c.hi);
-        }
-        if (cplx_other) {
-            E128 c = complex_entry(h, other);
-            reinterpret_cast<ulonglong2 *>(P.cplx)[base] = make_ulonglong2(c.lo, c.hi);
-            atomicAdd(&P.counters[CNT_HASH_MISMATCH], 1u);
-        }
-    }
-    if (list_slot) P.cplx_slots[atomicAdd(&P.counters[CNT_COMPLEX_SLOTS], 1u)] = (uint32_t) s;
 }
 
 // One thread per slot that saw a third arrival: its first two records follow the others to the exact
@@ -290,7 +318,16 @@ __global__ void __launch_bounds__(JOIN_THREADS) mate_complex_kernel(JoinParams P
 
 int launch_mate_join(const JoinParams &P, cudaStream_t stream, uint64_t *launches) {
     if (P.n == 0) return 0;
-    mate_join_kernel<<<(uint32_t) ((P.n + JOIN_THREADS - 1) / JOIN_THREADS), JOIN_THREADS, 0, stream>>>(P);
+    static int items = -1;
+    if (items < 0) {
+        const char *e = getenv("OGE_JOIN_ITEMS");
+        items = e && *e ? atoi(e) : 1;
+    }
+    const uint64_t per_cta = (uint64_t) JOIN_THREADS * (items == 4 ? 4 : items == 1 ? 1 : 2);
+    const uint32_t grid = (uint32_t) ((P.n + per_cta - 1) / per_cta);
+    if (items == 4) mate_join_kernel<4><<<grid, JOIN_THREADS, 0, stream>>>(P);
+    else if (items == 1) mate_join_kernel<1><<<grid, JOIN_THREADS, 0, stream>>>(P);
+    else mate_join_kernel<2><<<grid, JOIN_THREADS, 0, stream>>>(P);
     *launches += 1;
     OGE_CUDA_TRY(cudaGetLastError());
     return 0;

@@ -12,12 +12,15 @@
 //   frags: runs of 2+ holding at least one unpaired end (:379); if the run also holds an end
 //          of a pair, all unpaired ends are marked (:517-522), else all but the survivor (:524-538)
 //
-// One CTA per 2048-entry tile.  Runs are delimited by head flags, numbered by a block scan
-// and reduced with shared-memory atomics (thread-local pre-folding keeps long runs cheap).
-// A run that starts in a tile is owned by that tile even when it spills into the next ones:
-// the owner keeps reading until the key changes; a tile's leading entries that continue an
-// earlier run are skipped.  HBM traffic: the sorted entries once (+ the spill) and one byte
-// per mark.
+// One CTA per 2048-entry tile, eight consecutive entries per thread.  The survivor of a run is the
+// maximum of one packed 64-bit candidate per entry, (score + 2^15) << 32 | ~index, so "greatest score,
+// then smallest index" is a single max.  Runs that lie inside one thread's eight entries (almost all of
+// them: most runs are singletons) are reduced in registers with a forward and a backward sweep; only
+// the partial runs at a thread's edges go through shared-memory atomics, into the slot of the thread
+// the run starts in (found with a block-wide max-scan of "last thread holding a run head").
+// A run that starts in a tile is owned by that tile even when it spills into the next ones: the
+// owner keeps reading until the key changes; a tile's leading entries that continue an earlier
+// run are skipped.  HBM traffic: the sorted entries once (+ the spill) and one byte per mark.
 #include "kernels.cuh"
 
 namespace oge {
@@ -26,11 +29,11 @@ constexpr int SEL_THREADS = 256;
 constexpr int SEL_ITEMS = 8;
 constexpr int SEL_TILE = SEL_THREADS * SEL_ITEMS;      // 2048
 constexpr int SEL_PAD = SEL_TILE + SEL_TILE / 8 + 2;   // one skew slot per 8 entries: conflict-free blocked reads
+constexpr int SEL_WARPS = SEL_THREADS / 32;
 
 constexpr uint32_t RUN_HAS_PAIRED = 1u, RUN_HAS_UNPAIRED = 2u;
 
-// dynamic shared memory: entries (padded) + 4 per-run arrays
-constexpr size_t SEL_SMEM = (size_t) SEL_PAD * sizeof(E128) + (size_t) SEL_TILE * 4 * 4;
+constexpr size_t SEL_SMEM = (size_t) SEL_PAD * sizeof(E128);
 
 __device__ __forceinline__ int pad_index(int j) { return j + (j >> 3); }
 
@@ -42,20 +45,31 @@ __device__ __forceinline__ E128 ldg_entry(const E128 *p) {
     return e;
 }
 
+// equal on every bit at and above key_lo?
 __device__ __forceinline__ bool key_eq(const E128 &a, const E128 &b, int key_lo) {
-    E128 x = bits_from(a, key_lo), y = bits_from(b, key_lo);
-    return x.lo == y.lo && x.hi == y.hi;
+    const uint64_t xh = a.hi ^ b.hi, xl = a.lo ^ b.lo;
+    if (key_lo >= 64) return (xh >> (key_lo - 64)) == 0;
+    return xh == 0 && (xl >> key_lo) == 0;
+}
+
+// what a run needs to know about its entries
+struct RunAgg {
+    unsigned long long cand;      // max of (score + 2^15) << 32 | ~index
+    uint32_t cnt, fl;
+};
+__device__ __forceinline__ void agg_add(RunAgg &a, unsigned long long cand, uint32_t fl) {
+    a.cand = cand > a.cand ? cand : a.cand;
+    a.cnt += 1;
+    a.fl |= fl;
 }
 
 template <bool PAIRS>
-__global__ void __launch_bounds__(SEL_THREADS) select_kernel(SelectParams P) {
+__global__ void __launch_bounds__(SEL_THREADS, 3) select_kernel(SelectParams P) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     E128 *s_e = reinterpret_cast<E128 *>(smem_raw);
-    int *s_max = reinterpret_cast<int *>(smem_raw + (size_t) SEL_PAD * sizeof(E128));
-    uint32_t *s_best = reinterpret_cast<uint32_t *>(s_max + SEL_TILE);
-    uint32_t *s_cnt = s_best + SEL_TILE;
-    uint32_t *s_flags = s_cnt + SEL_TILE;
-    __shared__ uint32_t s_wsum[SEL_THREADS / 32];
+    __shared__ unsigned long long s_cand[SEL_THREADS];
+    __shared__ uint32_t s_cnt[SEL_THREADS], s_fl[SEL_THREADS];
+    __shared__ int s_wmax[SEL_WARPS];
     __shared__ uint32_t s_ext_end;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -72,57 +86,26 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(SelectParams P) {
     for (int k = 0; k < SEL_ITEMS; k++) {
         int j = k * SEL_THREADS + tid;
         if ((uint32_t) j < count) s_e[pad_index(j) + 1] = ldg_entry(P.sorted + base + j);
-        s_max[j] = INT_MIN;
-        s_best[j] = 0xFFFFFFFFu;
-        s_cnt[j] = 0;
-        s_flags[j] = 0;
     }
+    s_cand[tid] = 0;
+    s_cnt[tid] = 0;
+    s_fl[tid] = 0;
     if (tid == 0) {
         if (base > 0) s_e[0] = ldg_entry(P.sorted + base - 1);
         s_ext_end = 0xFFFFFFFFu;
     }
     __syncthreads();
 
-    // ---- blocked view: thread t owns entries [8t, 8t+8); head flags
-    E128 e[SEL_ITEMS];
-    uint32_t heads = 0;      // bit k: entry k starts a run
-    int n_mine = 0;
-    {
-        E128 prev;
-        int j0 = tid * SEL_ITEMS;
-        if (j0 == 0) prev = s_e[0];
-        else prev = s_e[pad_index(j0 - 1) + 1];
-#pragma unroll
-        for (int k = 0; k < SEL_ITEMS; k++) {
-            int j = j0 + k;
-            if ((uint32_t) j < count) {
-                e[k] = s_e[pad_index(j) + 1];
-                bool head = (base + j == 0) || !key_eq(e[k], prev, key_lo);
-                heads |= (head ? 1u : 0u) << k;
-                prev = e[k];
-                n_mine = k + 1;
-            }
-        }
-    }
-    // ---- run ids: exclusive block scan of the head counts
-    uint32_t hc = __popc(heads), x = hc;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
-        if (lane >= o) x += y;
-    }
-    if (lane == 31) s_wsum[warp] = x;
-    __syncthreads();
-    uint32_t run_base = x - hc;
-    for (int w = 0; w < warp; w++) run_base += s_wsum[w];
-    uint32_t total_runs = 0;
-    for (int w = 0; w < SEL_THREADS / 32; w++) total_runs += s_wsum[w];
-
-    // run id of entry k = run_base + popc(heads & ((2 << k) - 1)) - 1   (-1: continues an earlier tile's run)
-    auto run_of = [&](int k) { return (int) (run_base + __popc(heads & ((2u << k) - 1))) - 1; };
-    auto score_of = [&](const E128 &v) { return (int) (int16_t) (uint16_t) (v.lo & 0xFFFFu); };
     // global ordinals (< 2^32); [idx_base, idx_base + n_records) are this rank's records
     auto idx_of = [&](const E128 &v) { return (uint32_t) bits_get(v, idx_pos, L.idx_bits); };
+    auto cand_of = [&](const E128 &v) {
+        const uint32_t sc = (uint32_t) ((int) (int16_t) (uint16_t) (v.lo & 0xFFFFu) + 32768);
+        return ((unsigned long long) sc << 32) | (uint32_t) ~idx_of(v);
+    };
+    auto flags_of = [&](const E128 &v) -> uint32_t {
+        if (PAIRS) return 0;
+        return bits_get(v, L.f_paired, 1) ? RUN_HAS_PAIRED : RUN_HAS_UNPAIRED;
+    };
     auto mark = [&](uint32_t g) {
         const uint64_t l = (uint64_t) g - P.idx_base;      // wraps for ordinals below the base
         if (l < P.n_records) P.dup[l] = 1;
@@ -142,54 +125,117 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(SelectParams P) {
         }
         return (uint32_t) P.fm[lo];
     };
-    auto paired_of = [&](const E128 &v) { return PAIRS ? true : bits_get(v, L.f_paired, 1) != 0; };
-
-    // ---- pass 1: max score, count, flags per run (thread-local folding of consecutive entries)
-    {
-        int cur = -2, mx = INT_MIN;
-        uint32_t c = 0, fl = 0;
-        auto flush = [&]() {
-            if (cur >= 0) {
-                atomicMax(&s_max[cur], mx);
-                atomicAdd(&s_cnt[cur], c);
-                if (!PAIRS) atomicOr(&s_flags[cur], fl);
+    uint32_t marks = 0;
+    // the verdict on one entry given its run's totals (mark_duplicates.cpp:488-507, 515-540)
+    auto decide = [&](const E128 &v, unsigned long long cand, const RunAgg &r) {
+        if (r.cnt < 2) return;
+        const bool is_best = cand == r.cand;
+        if (PAIRS) {
+            if (!is_best) {
+                const uint32_t i1 = idx_of(v);
+                mark(i1);
+                mark(mate_of(i1));
+                marks += 2;
             }
-        };
+        } else {
+            if (!(r.fl & RUN_HAS_UNPAIRED)) return;
+            const bool mark_it = (r.fl & RUN_HAS_PAIRED) ? !(bits_get(v, L.f_paired, 1) != 0) : !is_best;
+            if (mark_it) {
+                mark(idx_of(v));
+                marks += 1;
+            }
+        }
+    };
+
+    // ---- blocked view: thread t owns entries [8t, 8t+8); head flags
+    E128 e[SEL_ITEMS];
+    uint32_t heads = 0;      // bit k: entry k starts a run
+    int n_mine = 0;
+    {
+        E128 prev;
+        const int j0 = tid * SEL_ITEMS;
+        prev = j0 == 0 ? s_e[0] : s_e[pad_index(j0 - 1) + 1];
+#pragma unroll
+        for (int k = 0; k < SEL_ITEMS; k++) {
+            const int j = j0 + k;
+            if ((uint32_t) j < count) {
+                e[k] = s_e[pad_index(j) + 1];
+                const bool head = (base + j == 0) || !key_eq(e[k], prev, key_lo);
+                heads |= (head ? 1u : 0u) << k;
+                prev = e[k];
+                n_mine = k + 1;
+            }
+        }
+    }
+    const int first_head = heads ? __ffs(heads) - 1 : n_mine;      // entries before it continue a run from the left
+    const int last_head = heads ? 31 - __clz(heads) : -1;         // entries from it on are this thread's trailing run
+
+    // ---- slot of the run my leading entries continue: the nearest thread to the left holding a head
+    int left;
+    {
+        int v = heads ? tid : -1, x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= o) x = max(x, y);
+        }
+        if (lane == 31) s_wmax[warp] = x;
+        int prev_lane = __shfl_up_sync(0xFFFFFFFFu, x, 1);
+        __syncthreads();
+        int wprev = -1;
+        for (int w = 0; w < warp; w++) wprev = max(wprev, s_wmax[w]);
+        left = lane == 0 ? wprev : max(wprev, prev_lane);
+    }
+    int tile_last_slot = -1;      // slot of the tile's last run (-1: the whole tile continues an earlier tile's run)
+    for (int w = 0; w < SEL_WARPS; w++) tile_last_slot = max(tile_last_slot, s_wmax[w]);
+
+    // ---- forward sweep: running totals inside each run; edge partials go to shared memory
+    RunAgg F[SEL_ITEMS];
+    {
+        RunAgg cur = {0ull, 0u, 0u};
 #pragma unroll
         for (int k = 0; k < SEL_ITEMS; k++) {
             if (k < n_mine) {
-                int r = run_of(k);
-                if (r != cur) {
-                    flush();
-                    cur = r; mx = INT_MIN; c = 0; fl = 0;
-                }
-                mx = max(mx, score_of(e[k]));
-                c++;
-                fl |= paired_of(e[k]) ? RUN_HAS_PAIRED : RUN_HAS_UNPAIRED;
+                if ((heads >> k) & 1) cur = RunAgg{0ull, 0u, 0u};
+                agg_add(cur, cand_of(e[k]), flags_of(e[k]));
+                F[k] = cur;
             }
         }
-        flush();
+    }
+    // leading partial = F[first_head - 1], trailing partial = F[n_mine - 1] (when the thread holds a head)
+#pragma unroll
+    for (int k = 0; k < SEL_ITEMS; k++) {
+        if (k == first_head - 1 && left >= 0) {
+            atomicMax(&s_cand[left], F[k].cand);
+            atomicAdd(&s_cnt[left], F[k].cnt);
+            if (!PAIRS) atomicOr(&s_fl[left], F[k].fl);
+        }
+        if (k == n_mine - 1 && last_head >= 0) {
+            atomicMax(&s_cand[tid], F[k].cand);
+            atomicAdd(&s_cnt[tid], F[k].cnt);
+            if (!PAIRS) atomicOr(&s_fl[tid], F[k].fl);
+        }
     }
 
     // ---- the tile's last run may spill into the following tiles: the owner follows it
-    const bool spill_possible = count == SEL_TILE && base + SEL_TILE < n && total_runs > 0;
-    const int last_run = (int) total_runs - 1;
+    const bool spill_possible = count == SEL_TILE && base + SEL_TILE < n && tile_last_slot >= 0;
     E128 last_key_entry;
     if (spill_possible) {      // uniform over the CTA
         last_key_entry = s_e[pad_index(SEL_TILE - 1) + 1];
         uint32_t pos = base + SEL_TILE;
         while (true) {
-            uint32_t j = pos + tid;
-            bool in = j < n, match = false;
+            const uint32_t j = pos + tid;
+            const bool in = j < n;
+            bool match = false;
             E128 v;
             if (in) {
                 v = ldg_entry(P.sorted + j);
                 match = key_eq(v, last_key_entry, key_lo);
             }
             if (match) {
-                atomicMax(&s_max[last_run], score_of(v));
-                atomicAdd(&s_cnt[last_run], 1u);
-                if (!PAIRS) atomicOr(&s_flags[last_run], paired_of(v) ? RUN_HAS_PAIRED : RUN_HAS_UNPAIRED);
+                atomicMax(&s_cand[tile_last_slot], cand_of(v));
+                atomicAdd(&s_cnt[tile_last_slot], 1u);
+                if (!PAIRS) atomicOr(&s_fl[tile_last_slot], flags_of(v));
             } else {
                 // the array is sorted by key, so the matching entries are a prefix: the smallest
                 // non-matching index is the end of the run
@@ -200,66 +246,34 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(SelectParams P) {
         }
     }
     __syncthreads();
-    // first index past the tile's last run (== base + count when there is nothing to follow)
     const uint32_t ext_end = spill_possible ? s_ext_end : base + count;
 
-    // ---- pass 2: smallest index among the entries holding the run's max score
+    // ---- backward sweep: every entry learns its run's totals, then the verdict
     {
-        int cur = -2;
-        uint32_t best = 0xFFFFFFFFu;
+        RunAgg tot = {0ull, 0u, 0u};
+        const RunAgg lead = left >= 0 ? RunAgg{s_cand[left], s_cnt[left], s_fl[left]} : RunAgg{0ull, 0u, 0u};
+        const RunAgg trail = RunAgg{s_cand[tid], s_cnt[tid], s_fl[tid]};
 #pragma unroll
-        for (int k = 0; k < SEL_ITEMS; k++) {
+        for (int k = SEL_ITEMS - 1; k >= 0; k--) {
             if (k < n_mine) {
-                int r = run_of(k);
-                if (r != cur) {
-                    if (cur >= 0 && best != 0xFFFFFFFFu) atomicMin(&s_best[cur], best);
-                    cur = r; best = 0xFFFFFFFFu;
+                const bool run_ends_here = k == n_mine - 1 || ((heads >> (k + 1)) & 1);
+                if (run_ends_here) tot = F[k];
+                if (k < first_head) {
+                    if (left >= 0) decide(e[k], cand_of(e[k]), lead);      // else: owned by an earlier tile
+                } else if (k >= last_head) {
+                    decide(e[k], cand_of(e[k]), trail);
+                } else {
+                    decide(e[k], cand_of(e[k]), tot);
                 }
-                if (r >= 0 && score_of(e[k]) == s_max[r]) best = min(best, idx_of(e[k]));
             }
-        }
-        if (cur >= 0 && best != 0xFFFFFFFFu) atomicMin(&s_best[cur], best);
-        if (spill_possible) {
-            for (uint32_t j = base + SEL_TILE + tid; j < ext_end; j += SEL_THREADS) {
-                E128 v = ldg_entry(P.sorted + j);
-                if (score_of(v) == s_max[last_run]) atomicMin(&s_best[last_run], idx_of(v));
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- pass 3: mark
-    uint32_t marks = 0;
-    auto decide = [&](const E128 &v, int r) {
-        uint32_t c = s_cnt[r];
-        if (c < 2) return;
-        bool is_best = score_of(v) == s_max[r] && idx_of(v) == s_best[r];
-        if (PAIRS) {
-            if (!is_best) {
-                const uint32_t i1 = idx_of(v);
-                mark(i1);
-                mark(mate_of(i1));
-                marks += 2;
-            }
-        } else {
-            uint32_t fl = s_flags[r];
-            if (!(fl & RUN_HAS_UNPAIRED)) return;
-            bool mark_it = (fl & RUN_HAS_PAIRED) ? !paired_of(v) : !is_best;
-            if (mark_it) {
-                mark(idx_of(v));
-                marks += 1;
-            }
-        }
-    };
-#pragma unroll
-    for (int k = 0; k < SEL_ITEMS; k++) {
-        if (k < n_mine) {
-            int r = run_of(k);
-            if (r >= 0) decide(e[k], r);
         }
     }
     if (spill_possible) {
-        for (uint32_t j = base + SEL_TILE + tid; j < ext_end; j += SEL_THREADS) decide(ldg_entry(P.sorted + j), last_run);
+        const RunAgg r = RunAgg{s_cand[tile_last_slot], s_cnt[tile_last_slot], s_fl[tile_last_slot]};
+        for (uint32_t j = base + SEL_TILE + tid; j < ext_end; j += SEL_THREADS) {
+            const E128 v = ldg_entry(P.sorted + j);
+            decide(v, cand_of(v), r);
+        }
     }
     for (int o = 16; o; o >>= 1) marks += __shfl_xor_sync(0xFFFFFFFFu, marks, o);
     if (lane == 0 && marks) atomicAdd(&P.counters[CNT_MARKS], marks);
