@@ -11,7 +11,12 @@
 // key in the high bits, so that the LSD radix sort only has to walk the key's bit range.
 //
 //   frag:  [score:16][idx:idx_bits][paired:1] | key: [orient:1][coord][ref][lib]
-//   pair:  [score:16][idx1:idx_bits]          | key: [coord2][ref2][orient:2][coord1][ref1][lib]
+//   pair:  [score:16][idx1:idx_bits] ...0...  | key: [coord2][ref2][orient:2][coord1][ref1][lib]        "far"
+//          [score:16][idx1:idx_bits] ...0...  | key:        [delta][orient:2][coord1][ref1][lib]        "near"
+// Pair keys are anchored at bit 127, so lib/ref1/coord1/orient sit at the same place in both forms.
+// A pair whose ends lie on the same reference less than 2^delta_bits apart (every ordinary insert)
+// is a NEAR pair: its second end is stored as the distance, which makes the key 3 radix passes
+// shorter.  Near and far pairs live in separate lists; equal duplicate keys imply equal class.
 //
 // The key order is irrelevant (only equality defines a duplicate group, and the survivor is
 // chosen by an order-independent (score desc, index asc) reduction; picard_structures.h:56-68
@@ -32,8 +37,9 @@ struct KeyLayout {
     uint32_t lib_invalid;    // lib field value of "no entry" (all ones)
     // frag entry bit positions
     int f_idx, f_paired, f_orient, f_coord, f_ref, f_lib, f_end;   // f_orient = first key bit
-    // pair entry bit positions
-    int p_idx, p_coord2, p_ref2, p_orient, p_coord1, p_ref1, p_lib, p_end;   // p_coord2 = first key bit
+    // pair entry bit positions (keys anchored at the top: p_end == 128)
+    int p_idx, p_coord2, p_ref2, p_orient, p_coord1, p_ref1, p_lib, p_end;   // far pairs: p_coord2 = first key bit
+    int n_delta, delta_bits;                                                 // near pairs: n_delta = first key bit
 };
 
 // ---- 128-bit field helpers (positions and widths are warp-uniform) ---------------------------
@@ -90,12 +96,15 @@ enum {
     CNT_COMPLEX_SEGS,
     CNT_COMPLEX_SLOTS,  // slots that saw a third arrival
     CNT_PAIRS_RETRACTED,
+    CNT_PAIRS_FAR,      // far-pair entries emitted
+    CNT_FAR_RETRACTED,
     CNT_FOREIGN_MARKS,  // sharded: marks on records of other ranks
     CNT_PUB,            // sharded: published entries
     CNT_ROUTE,          // sharded: entries handed to their key owner
     CNT_FRAG_EXTRA,     // sharded: fragment entries received
     CNT_FM,             // sharded: foreign-mate couples
     CNT_SCRATCH0,
+    CNT_SCRATCH1,
     CNT_N = 32
 };
 

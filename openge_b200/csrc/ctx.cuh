@@ -54,7 +54,7 @@ struct ShardState {
     DevBuf<uint32_t> marks, pub_list;
     DevBuf<uint64_t> fm;                  // foreign mates: (idx1 << 32 | idx2), sorted by idx1
     DevBuf<E128> fm_sort, w_sort, w_sort2;
-    uint64_t n_frag = 0, n_pe = 0, n_pairs = 0, n_retracted = 0, n_slots = 0, n_fm = 0, n_frag_total = 0, n_w = 0;
+    uint64_t n_frag = 0, n_pe = 0, n_pairs = 0, n_retracted = 0, n_slots = 0, n_fm = 0, n_frag_total = 0, n_w = 0, n_far = 0, n_far_dead = 0;
     int phase = 0;
 };
 
@@ -83,7 +83,7 @@ struct oge_gpu_dedup_ctx {
     int16_t unknown_lib = 1;
 
     // work arrays
-    DevBuf<E128> frag, sortbuf, pair, pair2;
+    DevBuf<E128> frag, sortbuf, pair, pair2, pairf, pairf2;      // pair = near pairs, pairf = far pairs
     DevBuf<uint64_t> hk;
     DevBuf<uint16_t> flag_in, flag_out;
     DevBuf<NameTag> tag;

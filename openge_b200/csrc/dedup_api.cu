@@ -8,6 +8,7 @@
 // no device is usable.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -71,20 +72,28 @@ int compute_layout(oge_gpu_dedup_ctx *c, KeyLayout *L) {
     L->f_ref = b; b += L->ref_bits;
     L->f_lib = b; b += L->lib_bits;
     L->f_end = b;
-    b = 16;
-    L->p_idx = b; b += L->idx_bits;
-    L->p_coord2 = b; b += L->coord_bits;
-    L->p_ref2 = b; b += L->ref_bits;
-    L->p_orient = b; b += 2;
-    L->p_coord1 = b; b += L->coord_bits;
-    L->p_ref1 = b; b += L->ref_bits;
-    L->p_lib = b; b += L->lib_bits;
-    L->p_end = b;
-    if (L->f_end > 128 || L->p_end > 128)
+    L->p_idx = 16;
+    L->p_end = 128;
+    L->p_lib = 128 - L->lib_bits;
+    L->p_ref1 = L->p_lib - L->ref_bits;
+    L->p_coord1 = L->p_ref1 - L->coord_bits;
+    L->p_orient = L->p_coord1 - 2;
+    L->p_ref2 = L->p_orient - L->ref_bits;
+    L->p_coord2 = L->p_ref2 - L->coord_bits;
+    // near pairs: the distance field is sized so that the key is a whole number of 8-bit digits (>= 11 bits)
+    {
+        const int fixed = L->lib_bits + L->ref_bits + L->coord_bits + 2;
+        int d = 11;
+        while ((fixed + d) % 8) d++;
+        if (d > L->coord_bits) d = L->coord_bits;
+        L->delta_bits = d;
+        L->n_delta = L->p_orient - d;
+    }
+    if (L->f_end > 128 || L->p_coord2 < 16 + L->idx_bits)
         return fail_msg(OGE_ERR_KEY_RANGE,
                         "key layout needs %d (frag) / %d (pair) bits, more than the 128 of a 16-byte entry: "
                         "idx %d, coord %d, ref %d, lib %d bits (set max_ref_len / n_ref in the config)",
-                        L->f_end, L->p_end, L->idx_bits, L->coord_bits, L->ref_bits, L->lib_bits);
+                        L->f_end, 16 + L->idx_bits + 128 - L->p_coord2, L->idx_bits, L->coord_bits, L->ref_bits, L->lib_bits);
     return 0;
 }
 
@@ -216,7 +225,7 @@ void oge_gpu_dedup_destroy(oge_gpu_dedup_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     c->rec.release(); c->off.release(); c->rg_bytes.release(); c->rg_off.release(); c->rg_lib.release();
-    c->frag.release(); c->sortbuf.release(); c->pair.release(); c->pair2.release(); c->hk.release();
+    c->frag.release(); c->sortbuf.release(); c->pair.release(); c->pair2.release(); c->pairf.release(); c->pairf2.release(); c->hk.release();
     c->tag.release(); c->flag_in.release(); c->flag_out.release(); c->dup.release(); c->scratch.release();
     c->cplx_state.release(); c->cplx_slots.release(); c->mate_of.release(); c->counters.release(); c->table.release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -340,19 +349,21 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     const uint64_t n_frag = c->h_counters[CNT_FRAG], n_pe = c->h_counters[CNT_PAIR_ELIGIBLE];
 
     // ---- K2 mate join
-    uint64_t n_pairs = 0, n_cplx = 0, n_retracted = 0;
+    uint64_t n_pairs = 0, n_far = 0, n_cplx = 0, n_retracted = 0, n_far_retracted = 0;
     if (n_pe) {
         uint64_t n_slots = n_pe + 1024;      // two records per name: half full
         if ((rc = c->table.reserve(n_slots, false, s))) return rc;
         if ((rc = c->pair.reserve(n_pe / 2 + 1024, false, s))) return rc;
         if ((rc = c->pair2.reserve(n_pe / 2 + 1024, false, s))) return rc;
+        if ((rc = c->pairf.reserve(n_pe / 2 + 1024, false, s))) return rc;      // worst case: every pair is a far pair
+        if ((rc = c->pairf2.reserve(n_pe / 2 + 1024, false, s))) return rc;
         if ((rc = c->cplx_slots.reserve(n_pe / 3 + 1024, false, s))) return rc;
         OGE_CUDA_TRY(cudaMemsetAsync(c->table.p, 0, n_slots * sizeof(MateSlot), s));
         JoinParams jp;
         jp.rec = c->rec.p; jp.off = c->off.p; jp.n = n; jp.idx_base = c->cfg.index_base;
         jp.frag = c->frag.p; jp.hk = c->hk.p; jp.tag = c->tag.p;
         jp.table = c->table.p; jp.n_slots = n_slots;
-        jp.pair = c->pair.p; jp.mate_of = c->mate_of.p; jp.cplx = c->sortbuf.p; jp.cplx_slots = c->cplx_slots.p;
+        jp.pair = c->pair.p; jp.pair_far = c->pairf.p; jp.mate_of = c->mate_of.p; jp.cplx = c->sortbuf.p; jp.cplx_slots = c->cplx_slots.p;
         jp.counters = c->counters.p; jp.rg = rg_table(c); jp.kl = c->kl; jp.verify_names = c->cfg.verify_names;
         if ((rc = launch_mate_join(jp, s, &launches))) return rc;
         OGE_CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, s));
@@ -364,12 +375,14 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
             OGE_CUDA_TRY(cudaStreamSynchronize(s));
             n_cplx = c->h_counters[CNT_COMPLEX];
             n_retracted = c->h_counters[CNT_PAIRS_RETRACTED];
-            const uint64_t need = c->h_counters[CNT_PAIRS] + n_cplx / 2 + 1;
-            if (need > c->pair.cap) {
-                if ((rc = c->pair.reserve(need, true, s))) return rc;
-                jp.pair = c->pair.p;
-            }
+            n_far_retracted = c->h_counters[CNT_FAR_RETRACTED];
+            const uint64_t need = c->h_counters[CNT_PAIRS] + n_cplx / 2 + 1, need_far = c->h_counters[CNT_PAIRS_FAR] + n_cplx / 2 + 1;
+            if ((rc = c->pair.reserve(need, true, s))) return rc;
             if ((rc = c->pair2.reserve(need, false, s))) return rc;
+            if ((rc = c->pairf.reserve(need_far, true, s))) return rc;
+            if ((rc = c->pairf2.reserve(need_far, false, s))) return rc;
+            jp.pair = c->pair.p;
+            jp.pair_far = c->pairf.p;
             // sort (hash, ordinal), replay the toggle map per hash value.  The mate table is dead by
             // now and at least as large as the list: it is the ping-pong buffer.
             E128 *sorted = nullptr;
@@ -382,6 +395,7 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
             OGE_CUDA_TRY(cudaStreamSynchronize(s));
         }
         n_pairs = c->h_counters[CNT_PAIRS];
+        n_far = c->h_counters[CNT_PAIRS_FAR];
     }
     OGE_CUDA_TRY(cudaEventRecord(c->ev[2], s));
 
@@ -390,16 +404,26 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     sp.dup = c->dup.p; sp.mate_of = c->mate_of.p; sp.idx_base = c->cfg.index_base; sp.n_records = n;
     sp.counters = c->counters.p; sp.kl = c->kl; sp.n_dev = nullptr;
     sp.fm = nullptr; sp.n_fm = 0; sp.foreign_marks = nullptr; sp.foreign_cap = 0;
-    E128 *sorted_pairs = c->pair.p;
+    // near pairs (short key) and far pairs (full key) are separate lists: equal keys imply equal class
+    E128 *sorted_pairs = c->pair.p, *sorted_far = c->pairf.p;
     if (n_pairs) {
-        if ((rc = radix_sort_128(c->pair.p, c->pair2.p, n_pairs, nullptr, c->kl.p_coord2, c->kl.p_end, c->scratch.p, s, &sorted_pairs,
+        if ((rc = radix_sort_128(c->pair.p, c->pair2.p, n_pairs, nullptr, c->kl.n_delta, c->kl.p_end, c->scratch.p, s, &sorted_pairs,
+                                 &launches, tp)))
+            return rc;
+    }
+    if (n_far) {
+        if ((rc = radix_sort_128(c->pairf.p, c->pairf2.p, n_far, nullptr, c->kl.p_coord2, c->kl.p_end, c->scratch.p, s, &sorted_far,
                                  &launches, tp)))
             return rc;
     }
     OGE_CUDA_TRY(cudaEventRecord(c->ev[3], s));
     if (n_pairs > n_retracted) {      // retracted provisional pairs are all-ones entries: they sorted to the tail
         sp.sorted = sorted_pairs; sp.n_max = (uint32_t) (n_pairs - n_retracted);
-        if ((rc = launch_select_pairs(sp, s, &launches))) return rc;
+        if ((rc = launch_select_pairs(sp, false, s, &launches))) return rc;
+    }
+    if (n_far > n_far_retracted) {
+        sp.sorted = sorted_far; sp.n_max = (uint32_t) (n_far - n_far_retracted);
+        if ((rc = launch_select_pairs(sp, true, s, &launches))) return rc;
     }
     OGE_CUDA_TRY(cudaEventRecord(c->ev[4], s));
 
@@ -429,16 +453,20 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     if (c->cfg.debug_keep_ends && sorted_frags != c->frag.p && n_frag)
         OGE_CUDA_TRY(cudaMemcpy(c->frag.p, sorted_frags, n * sizeof(E128), cudaMemcpyDeviceToDevice));
 
+    if (getenv("OGE_DEBUG_COUNTERS"))
+        fprintf(stderr, "[oge] n=%llu frag=%llu pe=%llu near=%llu far=%llu cplx=%llu retracted=%llu/%llu\n", (unsigned long long) n,
+                (unsigned long long) n_frag, (unsigned long long) n_pe, (unsigned long long) n_pairs, (unsigned long long) n_far,
+                (unsigned long long) n_cplx, (unsigned long long) n_retracted, (unsigned long long) n_far_retracted);
     oge_gpu_dedup_stats &st = c->stats;
     st.n_frag_entries = n_frag;
-    st.n_pair_entries = n_pairs - n_retracted;
+    st.n_pair_entries = n_pairs - n_retracted + n_far - n_far_retracted;
     st.n_duplicates = c->h_counters[CNT_DUPS];
     st.n_complex_names = n_cplx;
     st.n_hash_mismatch = c->h_counters[CNT_HASH_MISMATCH];
     st.frag_key_bits = c->kl.f_end - c->kl.f_orient;
-    st.pair_key_bits = c->kl.p_end - c->kl.p_coord2;
+    st.pair_key_bits = c->kl.p_end - c->kl.n_delta;      // near pairs (far pairs: p_end - p_coord2)
     st.frag_sort_passes = make_sort_plan(c->kl.f_orient, c->kl.f_end).n_pass;
-    st.pair_sort_passes = make_sort_plan(c->kl.p_coord2, c->kl.p_end).n_pass;
+    st.pair_sort_passes = make_sort_plan(c->kl.n_delta, c->kl.p_end).n_pass;
     st.ms_total = ms_between(c->ev[0], c->ev[7]);
     st.ms_endbuild = ms_between(c->ev[0], c->ev[1]);
     st.ms_join = ms_between(c->ev[1], c->ev[2]);

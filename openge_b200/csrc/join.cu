@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) mate_join_kernel(JoinParams P) {
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) {
         const uint64_t i = i0 + (uint64_t) k * JOIN_THREADS;
-        bool emit = false, cplx_self = false, cplx_other = false, list_slot = false;
+        bool emit = false, far = false, cplx_self = false, cplx_other = false, list_slot = false;
         uint32_t other = 0, i1 = 0, i2 = 0;
         E128 ent;
         ent.lo = ent.hi = 0;
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) mate_join_kernel(JoinParams P) {
                 }
                 if (same) {
                     const uint32_t first = min((uint32_t) i, other), second = max((uint32_t) i, other);      // file order
-                    ent = make_pair_entry(P.kl, ld_frag(P.frag + first), ld_frag(P.frag + second), &i1, &i2, P.idx_base);
+                    ent = make_pair_entry(P.kl, ld_frag(P.frag + first), ld_frag(P.frag + second), &i1, &i2, P.idx_base, &far);
                     emit = true;
                 } else {
                     cplx_self = cplx_other = true;      // two names, one hash (or read groups the header does not list)
@@ -205,19 +205,26 @@ __global__ void __launch_bounds__(JOIN_THREADS) mate_join_kernel(JoinParams P) {
             }
         }
 
-        // ---- warp-aggregated appends
-        uint32_t m = __ballot_sync(0xFFFFFFFFu, emit);
+        // ---- warp-aggregated appends (near pairs; far pairs are rare and append one by one)
+        uint32_t m = __ballot_sync(0xFFFFFFFFu, emit && !far);
         uint32_t pair_pos = SLOT_NO_PAIR;
         if (m) {
             int leader = __ffs(m) - 1;
             uint32_t base = 0;
             if (lane == leader) base = atomicAdd(&P.counters[CNT_PAIRS], (uint32_t) __popc(m));
             base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            if (emit) {
+            if (emit && !far) {
                 pair_pos = base + __popc(m & lt);
                 reinterpret_cast<ulonglong2 *>(P.pair)[pair_pos] = make_ulonglong2(ent.lo, ent.hi);
-                P.mate_of[i1] = (uint32_t) (i2 + P.idx_base);
             }
+        }
+        if (emit) {
+            if (far) {
+                const uint32_t at = atomicAdd(&P.counters[CNT_PAIRS_FAR], 1u);
+                reinterpret_cast<ulonglong2 *>(P.pair_far)[at] = make_ulonglong2(ent.lo, ent.hi);
+                pair_pos = at | SLOT_PAIR_FAR;
+            }
+            P.mate_of[i1] = (uint32_t) (i2 + P.idx_base);
         }
         if (emit || cplx_other) {      // what mate_fixup needs should a third record of this name turn up
             P.table[s[k]].who = ((uint64_t) (uint32_t) i << 32) | other;
@@ -258,8 +265,9 @@ __global__ void __launch_bounds__(JOIN_THREADS) mate_fixup_kernel(JoinParams P, 
     const MateSlot &sl = P.table[P.cplx_slots[j]];
     const uint32_t a = (uint32_t) (sl.who >> 32), b = (uint32_t) sl.who;
     if (sl.pair_pos != SLOT_NO_PAIR) {      // else: a hash-mismatched couple, already on the exact path
-        reinterpret_cast<ulonglong2 *>(P.pair)[sl.pair_pos] = make_ulonglong2(~0ull, ~0ull);
-        atomicAdd(&P.counters[CNT_PAIRS_RETRACTED], 1u);
+        const bool far = (sl.pair_pos & SLOT_PAIR_FAR) != 0;
+        reinterpret_cast<ulonglong2 *>(far ? P.pair_far : P.pair)[sl.pair_pos & ~SLOT_PAIR_FAR] = make_ulonglong2(~0ull, ~0ull);
+        atomicAdd(&P.counters[far ? CNT_FAR_RETRACTED : CNT_PAIRS_RETRACTED], 1u);
         uint32_t base = atomicAdd(&P.counters[CNT_COMPLEX], 2u);
         E128 ca = complex_entry(sl.key, a), cb = complex_entry(sl.key, b);
         reinterpret_cast<ulonglong2 *>(P.cplx)[base] = make_ulonglong2(ca.lo, ca.hi);
@@ -308,9 +316,10 @@ __global__ void __launch_bounds__(JOIN_THREADS) mate_complex_kernel(JoinParams P
             uint32_t rb = (uint32_t) sorted[found].lo;
             E128 first = ld_frag(P.frag + rb), second = ld_frag(P.frag + ra);
             uint32_t i1, i2;
-            E128 ent = make_pair_entry(P.kl, first, second, &i1, &i2, P.idx_base);
-            uint32_t pos = atomicAdd(&P.counters[CNT_PAIRS], 1u);
-            reinterpret_cast<ulonglong2 *>(P.pair)[pos] = make_ulonglong2(ent.lo, ent.hi);
+            bool far;
+            E128 ent = make_pair_entry(P.kl, first, second, &i1, &i2, P.idx_base, &far);
+            uint32_t pos = atomicAdd(&P.counters[far ? CNT_PAIRS_FAR : CNT_PAIRS], 1u);
+            reinterpret_cast<ulonglong2 *>(far ? P.pair_far : P.pair)[pos] = make_ulonglong2(ent.lo, ent.hi);
             P.mate_of[i1] = (uint32_t) (i2 + P.idx_base);
         }
     }

@@ -67,7 +67,8 @@ struct JoinParams {
     const NameTag *tag;
     MateSlot *table;
     uint64_t n_slots;
-    E128 *pair;             // output pair entries (appended; counters[CNT_PAIRS])
+    E128 *pair;             // output near-pair entries (appended; counters[CNT_PAIRS])
+    E128 *pair_far;         // output far-pair entries (appended; counters[CNT_PAIRS_FAR])
     uint32_t *mate_of;      // [n] GLOBAL ordinal of the pair's other record, indexed by idx1's local ordinal
     E128 *cplx;             // output: (hash << 32 | local ordinal) of records for the exact path
     uint32_t *cplx_slots;   // output: slots that saw a third arrival (counters[CNT_COMPLEX_SLOTS])
@@ -101,7 +102,7 @@ struct SelectParams {
     uint32_t foreign_cap;
 };
 
-int launch_select_pairs(const SelectParams &P, cudaStream_t stream, uint64_t *launches);
+int launch_select_pairs(const SelectParams &P, bool far, cudaStream_t stream, uint64_t *launches);
 int launch_select_frags(const SelectParams &P, cudaStream_t stream, uint64_t *launches);
 
 // ---- K5 flag write (flags.cu) -----------------------------------------------------------------
@@ -133,7 +134,7 @@ static_assert(sizeof(PubEntry) == 64, "PubEntry is 64 bytes on the wire");
 struct __align__(16) RouteEntry {
     E128 e;
     uint32_t idx2;      // pairs: global ordinal of the second record
-    uint32_t kind;      // 0 fragment, 1 pair
+    uint32_t kind;      // 0 fragment, 1 near pair, 2 far pair
     uint64_t rsv;
 };
 static_assert(sizeof(RouteEntry) == 32, "RouteEntry is 32 bytes on the wire");

@@ -5,13 +5,14 @@
 namespace oge {
 
 constexpr uint32_t SLOT_NO_PAIR = 0xFFFFFFFFu;
+constexpr uint32_t SLOT_PAIR_FAR = 0x80000000u;      // pair_pos flag: the entry sits in the far-pair list
 
 __device__ __forceinline__ uint64_t slot_of(uint64_t h, uint64_t n_slots) { return __umul64hi(h, n_slots); }
 
 // ---- pair entry ---------------------------------------------------------------------------------
 // first = the record seen first in the file (the map's stored ReadEnds), second = the current one.
 __device__ __forceinline__ E128 make_pair_entry(const KeyLayout &L, const E128 &first, const E128 &second,
-                                                uint32_t *idx1_local, uint32_t *idx2_local, uint64_t idx_base) {
+                                                uint32_t *idx1_local, uint32_t *idx2_local, uint64_t idx_base, bool *far) {
     uint64_t lib = bits_get(first, L.f_lib, L.lib_bits);      // library of the first-seen end (:218)
     uint64_t ref_f = bits_get(first, L.f_ref, L.ref_bits), ref_s = bits_get(second, L.f_ref, L.ref_bits);
     uint64_t co_f = bits_get(first, L.f_coord, L.coord_bits), co_s = bits_get(second, L.f_coord, L.coord_bits);
@@ -26,8 +27,14 @@ __device__ __forceinline__ E128 make_pair_entry(const KeyLayout &L, const E128 &
     uint64_t r1 = keep ? ref_f : ref_s, c1 = keep ? co_f : co_s, v1 = keep ? rev_f : rev_s, i1 = keep ? idx_f : idx_s;
     uint64_t r2 = keep ? ref_s : ref_f, c2 = keep ? co_s : co_f, v2 = keep ? rev_s : rev_f, i2 = keep ? idx_s : idx_f;
     bits_or(e, L.p_idx, i1);
-    bits_or(e, L.p_coord2, c2);
-    bits_or(e, L.p_ref2, r2);
+    // same reference and a short distance (c2 >= c1 then, by the flip rule): the near form
+    *far = !(r1 == r2 && c2 - c1 < (1ull << L.delta_bits));
+    if (*far) {
+        bits_or(e, L.p_coord2, c2);
+        bits_or(e, L.p_ref2, r2);
+    } else {
+        bits_or(e, L.n_delta, c2 - c1);
+    }
     bits_or(e, L.p_orient, (v1 << 1) | v2);      // getOrientationByte(read1Negative, read2Negative) (:169-178)
     bits_or(e, L.p_coord1, c1);
     bits_or(e, L.p_ref1, r1);

@@ -63,8 +63,10 @@ __device__ __forceinline__ void agg_add(RunAgg &a, unsigned long long cand, uint
     a.fl |= fl;
 }
 
-template <bool PAIRS>
+// KIND: 0 fragment ends, 1 near pairs, 2 far pairs (they differ in where the key starts)
+template <int KIND>
 __global__ void __launch_bounds__(SEL_THREADS, 3) select_kernel(SelectParams P) {
+    constexpr bool PAIRS = KIND != 0;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     E128 *s_e = reinterpret_cast<E128 *>(smem_raw);
     __shared__ unsigned long long s_cand[SEL_THREADS];
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 3) select_kernel(SelectParams P) 
     if (base >= n) return;
     const uint32_t count = min((uint32_t) SEL_TILE, n - base);
     const KeyLayout &L = P.kl;
-    const int key_lo = PAIRS ? L.p_coord2 : L.f_orient;
+    const int key_lo = KIND == 0 ? L.f_orient : (KIND == 1 ? L.n_delta : L.p_coord2);
     const int idx_pos = PAIRS ? L.p_idx : L.f_idx;
 
     // ---- load the tile (striped, coalesced) + its predecessor into shared memory
@@ -279,23 +281,24 @@ __global__ void __launch_bounds__(SEL_THREADS, 3) select_kernel(SelectParams P) 
     if (lane == 0 && marks) atomicAdd(&P.counters[CNT_MARKS], marks);
 }
 
-static int launch_select(const SelectParams &P, bool pairs, cudaStream_t stream, uint64_t *launches) {
+template <int KIND>
+static int launch_select(const SelectParams &P, cudaStream_t stream, uint64_t *launches) {
     if (P.n_max == 0) return 0;
     static bool configured = false;
     if (!configured) {
-        OGE_CUDA_TRY(cudaFuncSetAttribute(select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SEL_SMEM));
-        OGE_CUDA_TRY(cudaFuncSetAttribute(select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SEL_SMEM));
+        OGE_CUDA_TRY(cudaFuncSetAttribute(select_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SEL_SMEM));
         configured = true;
     }
-    uint32_t grid = (P.n_max + SEL_TILE - 1) / SEL_TILE;
-    if (pairs) select_kernel<true><<<grid, SEL_THREADS, SEL_SMEM, stream>>>(P);
-    else select_kernel<false><<<grid, SEL_THREADS, SEL_SMEM, stream>>>(P);
+    const uint32_t grid = (P.n_max + SEL_TILE - 1) / SEL_TILE;
+    select_kernel<KIND><<<grid, SEL_THREADS, SEL_SMEM, stream>>>(P);
     *launches += 1;
     OGE_CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
-int launch_select_pairs(const SelectParams &P, cudaStream_t stream, uint64_t *launches) { return launch_select(P, true, stream, launches); }
-int launch_select_frags(const SelectParams &P, cudaStream_t stream, uint64_t *launches) { return launch_select(P, false, stream, launches); }
+int launch_select_pairs(const SelectParams &P, bool far, cudaStream_t stream, uint64_t *launches) {
+    return far ? launch_select<2>(P, stream, launches) : launch_select<1>(P, stream, launches);
+}
+int launch_select_frags(const SelectParams &P, cudaStream_t stream, uint64_t *launches) { return launch_select<0>(P, stream, launches); }
 
 }  // namespace oge

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(SH_THREADS) sh_gather_kernel(const uint32_t *_
 // shards' sightings are interleaved) and both records are published in the second round.
 __global__ void __launch_bounds__(SH_THREADS) sh_probe_kernel(const PubEntry *__restrict__ pub, uint64_t n_pub, ShardParams S,
                                                               MateSlot *__restrict__ table, uint64_t n_slots, E128 *__restrict__ pair,
-                                                              uint32_t *__restrict__ list2) {
+                                                              E128 *__restrict__ pair_far, uint32_t *__restrict__ list2) {
     const uint64_t j = (uint64_t) blockIdx.x * SH_THREADS + threadIdx.x;
     if (j >= n_pub) return;
     const uint64_t g = bits_get(pub[j].frag, S.kl.f_idx, S.kl.idx_bits);
@@ -100,8 +100,9 @@ __global__ void __launch_bounds__(SH_THREADS) sh_probe_kernel(const PubEntry *__
     if (atomicCAS(vp, v, v | (1ull << 63)) != v) return;      // another entry of the same name got here first
     const uint32_t pos = table[s].pair_pos;
     if (pos == SLOT_NO_PAIR) return;                  // hash-equal records with different names: published in round 1
-    reinterpret_cast<ulonglong2 *>(pair)[pos] = make_ulonglong2(~0ull, ~0ull);
-    atomicAdd(&S.counters[CNT_PAIRS_RETRACTED], 1u);
+    const bool far = (pos & SLOT_PAIR_FAR) != 0;
+    reinterpret_cast<ulonglong2 *>(far ? pair_far : pair)[pos & ~SLOT_PAIR_FAR] = make_ulonglong2(~0ull, ~0ull);
+    atomicAdd(&S.counters[far ? CNT_FAR_RETRACTED : CNT_PAIRS_RETRACTED], 1u);
     const uint32_t at = atomicAdd(&S.counters[CNT_PUB], 2u);
     list2[at] = (uint32_t) (table[s].who >> 32);
     list2[at + 1] = (uint32_t) table[s].who;
@@ -171,8 +172,9 @@ __device__ bool pub_keys_equal(const NameTag &ta, const NameTag &tb, const RgTab
 // replays the same list and keeps the pairs whose key it owns.
 __global__ void __launch_bounds__(SH_THREADS) sh_replay_kernel(const E128 *__restrict__ sorted, uint32_t n_w, const PubEntry *__restrict__ w,
                                                                uint8_t *__restrict__ state, ShardParams S, E128 *__restrict__ pair,
-                                                               uint32_t pair_cap, uint32_t *__restrict__ mate_of, uint64_t *__restrict__ fm,
-                                                               uint32_t fm_cap, RgTable rg) {
+                                                               uint32_t pair_cap, E128 *__restrict__ pair_far, uint32_t far_cap,
+                                                               uint32_t *__restrict__ mate_of, uint64_t *__restrict__ fm, uint32_t fm_cap,
+                                                               RgTable rg) {
     const uint32_t j = blockIdx.x * SH_THREADS + threadIdx.x;
     if (j >= n_w) return;
     const uint64_t h = sorted[j].hi;
@@ -191,10 +193,11 @@ __global__ void __launch_bounds__(SH_THREADS) sh_replay_kernel(const E128 *__res
         state[found] = 0;
         const PubEntry &pb = w[(uint32_t) sorted[found].lo];      // the earlier sighting
         uint32_t i1, i2;
-        const E128 ent = make_pair_entry(S.kl, pb.frag, pa.frag, &i1, &i2, 0);      // global ordinals
+        bool far;
+        const E128 ent = make_pair_entry(S.kl, pb.frag, pa.frag, &i1, &i2, 0, &far);      // global ordinals
         if (owner_of(S, pair_packed(S.kl, ent)) != S.rank) continue;
-        const uint32_t pos = atomicAdd(&S.counters[CNT_PAIRS], 1u);
-        if (pos < pair_cap) reinterpret_cast<ulonglong2 *>(pair)[pos] = make_ulonglong2(ent.lo, ent.hi);
+        const uint32_t pos = atomicAdd(&S.counters[far ? CNT_PAIRS_FAR : CNT_PAIRS], 1u);
+        if (pos < (far ? far_cap : pair_cap)) reinterpret_cast<ulonglong2 *>(far ? pair_far : pair)[pos] = make_ulonglong2(ent.lo, ent.hi);
         const uint64_t l1 = (uint64_t) i1 - S.idx_base;
         if (l1 < S.n) mate_of[l1] = i2;
         else {
@@ -205,7 +208,7 @@ __global__ void __launch_bounds__(SH_THREADS) sh_replay_kernel(const E128 *__res
 }
 
 // ---- phase 4: entries whose key belongs to another rank -------------------------------------------------
-// kind 0: fragment entries, kind 1: pair entries.  Routed entries leave the local list (all-ones = dead).
+// kind 0: fragment entries, 1: near pairs, 2: far pairs.  Routed entries leave the local list (all-ones = dead).
 __global__ void __launch_bounds__(SH_THREADS) sh_route_kernel(E128 *__restrict__ ents, uint64_t n_ents, int kind, ShardParams S,
                                                               const uint32_t *__restrict__ mate_of, const uint64_t *__restrict__ fm, uint32_t n_fm,
                                                               RouteEntry *__restrict__ out, uint32_t out_cap, int dry) {
@@ -219,10 +222,8 @@ __global__ void __launch_bounds__(SH_THREADS) sh_route_kernel(E128 *__restrict__
     }
     const uint32_t at = warp_append(want, &S.counters[CNT_ROUTE]);
     if (!want) return;
-    if (dry) {      // counting pass: nothing moves
-        if (kind) atomicAdd(&S.counters[CNT_SCRATCH0], 1u);
-        return;
-    }
+    if (kind) atomicAdd(&S.counters[kind == 1 ? CNT_SCRATCH0 : CNT_SCRATCH1], 1u);      // pair entries that leave
+    if (dry) return;                                                                    // counting pass: nothing moves
     RouteEntry r;
     r.e = e;
     r.kind = (uint32_t) kind;
@@ -240,7 +241,6 @@ __global__ void __launch_bounds__(SH_THREADS) sh_route_kernel(E128 *__restrict__
             }
             r.idx2 = (uint32_t) fm[lo];
         }
-        atomicAdd(&S.counters[CNT_SCRATCH0], 1u);      // pair entries that left
     }
     if (at < out_cap) out[at] = r;
     reinterpret_cast<ulonglong2 *>(ents)[j] = make_ulonglong2(~0ull, ~0ull);
@@ -248,8 +248,8 @@ __global__ void __launch_bounds__(SH_THREADS) sh_route_kernel(E128 *__restrict__
 
 __global__ void __launch_bounds__(SH_THREADS) sh_receive_kernel(const RouteEntry *__restrict__ in, uint64_t n_in, ShardParams S,
                                                                 E128 *__restrict__ frag_extra, uint32_t frag_cap, E128 *__restrict__ pair,
-                                                                uint32_t pair_cap, uint32_t *__restrict__ mate_of, uint64_t *__restrict__ fm,
-                                                                uint32_t fm_cap) {
+                                                                uint32_t pair_cap, E128 *__restrict__ pair_far, uint32_t far_cap,
+                                                                uint32_t *__restrict__ mate_of, uint64_t *__restrict__ fm, uint32_t fm_cap) {
     const uint64_t j = (uint64_t) blockIdx.x * SH_THREADS + threadIdx.x;
     if (j >= n_in) return;
     const RouteEntry r = in[j];
@@ -258,8 +258,9 @@ __global__ void __launch_bounds__(SH_THREADS) sh_receive_kernel(const RouteEntry
         const uint32_t at = atomicAdd(&S.counters[CNT_FRAG_EXTRA], 1u);
         if (at < frag_cap) reinterpret_cast<ulonglong2 *>(frag_extra)[at] = make_ulonglong2(r.e.lo, r.e.hi);
     } else {
-        const uint32_t pos = atomicAdd(&S.counters[CNT_PAIRS], 1u);
-        if (pos < pair_cap) reinterpret_cast<ulonglong2 *>(pair)[pos] = make_ulonglong2(r.e.lo, r.e.hi);
+        const bool far = r.kind == 2;
+        const uint32_t pos = atomicAdd(&S.counters[far ? CNT_PAIRS_FAR : CNT_PAIRS], 1u);
+        if (pos < (far ? far_cap : pair_cap)) reinterpret_cast<ulonglong2 *>(far ? pair_far : pair)[pos] = make_ulonglong2(r.e.lo, r.e.hi);
         const uint32_t i1 = (uint32_t) bits_get(r.e, S.kl.p_idx, S.kl.idx_bits);
         const uint64_t l1 = (uint64_t) i1 - S.idx_base;
         if (l1 < S.n) mate_of[l1] = r.idx2;
@@ -314,9 +315,9 @@ int launch_sh_gather(const uint32_t *list, uint32_t n_list, const E128 *frag, co
     SH_LAUNCH(n_list, (sh_gather_kernel<<<grid_for(n_list), SH_THREADS, 0, s>>>(list, n_list, frag, hk, tag, out)));
     return 0;
 }
-int launch_sh_probe(const PubEntry *pub, uint64_t n_pub, const ShardParams &S, MateSlot *table, uint64_t n_slots, E128 *pair, uint32_t *list2,
-                    cudaStream_t s, uint64_t *launches) {
-    SH_LAUNCH(n_pub, (sh_probe_kernel<<<grid_for(n_pub), SH_THREADS, 0, s>>>(pub, n_pub, S, table, n_slots, pair, list2)));
+int launch_sh_probe(const PubEntry *pub, uint64_t n_pub, const ShardParams &S, MateSlot *table, uint64_t n_slots, E128 *pair, E128 *pair_far,
+                    uint32_t *list2, cudaStream_t s, uint64_t *launches) {
+    SH_LAUNCH(n_pub, (sh_probe_kernel<<<grid_for(n_pub), SH_THREADS, 0, s>>>(pub, n_pub, S, table, n_slots, pair, pair_far, list2)));
     return 0;
 }
 int launch_sh_wbuild(const PubEntry *w, uint32_t n_w, const KeyLayout &L, E128 *out, cudaStream_t s, uint64_t *launches) {
@@ -324,8 +325,10 @@ int launch_sh_wbuild(const PubEntry *w, uint32_t n_w, const KeyLayout &L, E128 *
     return 0;
 }
 int launch_sh_replay(const E128 *sorted, uint32_t n_w, const PubEntry *w, uint8_t *state, const ShardParams &S, E128 *pair, uint32_t pair_cap,
-                     uint32_t *mate_of, uint64_t *fm, uint32_t fm_cap, const RgTable &rg, cudaStream_t s, uint64_t *launches) {
-    SH_LAUNCH(n_w, (sh_replay_kernel<<<grid_for(n_w), SH_THREADS, 0, s>>>(sorted, n_w, w, state, S, pair, pair_cap, mate_of, fm, fm_cap, rg)));
+                     E128 *pair_far, uint32_t far_cap, uint32_t *mate_of, uint64_t *fm, uint32_t fm_cap, const RgTable &rg, cudaStream_t s,
+                     uint64_t *launches) {
+    SH_LAUNCH(n_w, (sh_replay_kernel<<<grid_for(n_w), SH_THREADS, 0, s>>>(sorted, n_w, w, state, S, pair, pair_cap, pair_far, far_cap, mate_of,
+                                                                           fm, fm_cap, rg)));
     return 0;
 }
 int launch_sh_route(E128 *ents, uint64_t n_ents, int kind, const ShardParams &S, const uint32_t *mate_of, const uint64_t *fm, uint32_t n_fm,
@@ -334,8 +337,10 @@ int launch_sh_route(E128 *ents, uint64_t n_ents, int kind, const ShardParams &S,
     return 0;
 }
 int launch_sh_receive(const RouteEntry *in, uint64_t n_in, const ShardParams &S, E128 *frag_extra, uint32_t frag_cap, E128 *pair,
-                      uint32_t pair_cap, uint32_t *mate_of, uint64_t *fm, uint32_t fm_cap, cudaStream_t s, uint64_t *launches) {
-    SH_LAUNCH(n_in, (sh_receive_kernel<<<grid_for(n_in), SH_THREADS, 0, s>>>(in, n_in, S, frag_extra, frag_cap, pair, pair_cap, mate_of, fm, fm_cap)));
+                      uint32_t pair_cap, E128 *pair_far, uint32_t far_cap, uint32_t *mate_of, uint64_t *fm, uint32_t fm_cap, cudaStream_t s,
+                      uint64_t *launches) {
+    SH_LAUNCH(n_in, (sh_receive_kernel<<<grid_for(n_in), SH_THREADS, 0, s>>>(in, n_in, S, frag_extra, frag_cap, pair, pair_cap, pair_far,
+                                                                            far_cap, mate_of, fm, fm_cap)));
     return 0;
 }
 int launch_sh_fm_pack(const uint64_t *fm, uint32_t n, E128 *out, cudaStream_t s, uint64_t *launches) {

@@ -18,15 +18,17 @@ int launch_sh_singletons(const MateSlot *table, uint64_t n_slots, uint32_t *list
 int launch_sh_complex(const E128 *cplx, uint32_t n_cplx, uint32_t *list, uint32_t *counters, cudaStream_t s, uint64_t *launches);
 int launch_sh_gather(const uint32_t *list, uint32_t n_list, const E128 *frag, const uint64_t *hk, const NameTag *tag, PubEntry *out,
                      cudaStream_t s, uint64_t *launches);
-int launch_sh_probe(const PubEntry *pub, uint64_t n_pub, const ShardParams &S, MateSlot *table, uint64_t n_slots, E128 *pair, uint32_t *list2,
-                    cudaStream_t s, uint64_t *launches);
+int launch_sh_probe(const PubEntry *pub, uint64_t n_pub, const ShardParams &S, MateSlot *table, uint64_t n_slots, E128 *pair, E128 *pair_far,
+                    uint32_t *list2, cudaStream_t s, uint64_t *launches);
 int launch_sh_wbuild(const PubEntry *w, uint32_t n_w, const KeyLayout &L, E128 *out, cudaStream_t s, uint64_t *launches);
 int launch_sh_replay(const E128 *sorted, uint32_t n_w, const PubEntry *w, uint8_t *state, const ShardParams &S, E128 *pair, uint32_t pair_cap,
-                     uint32_t *mate_of, uint64_t *fm, uint32_t fm_cap, const RgTable &rg, cudaStream_t s, uint64_t *launches);
+                     E128 *pair_far, uint32_t far_cap, uint32_t *mate_of, uint64_t *fm, uint32_t fm_cap, const RgTable &rg, cudaStream_t s,
+                     uint64_t *launches);
 int launch_sh_route(E128 *ents, uint64_t n_ents, int kind, const ShardParams &S, const uint32_t *mate_of, const uint64_t *fm, uint32_t n_fm,
                     RouteEntry *out, uint32_t out_cap, int dry, cudaStream_t s, uint64_t *launches);
 int launch_sh_receive(const RouteEntry *in, uint64_t n_in, const ShardParams &S, E128 *frag_extra, uint32_t frag_cap, E128 *pair,
-                      uint32_t pair_cap, uint32_t *mate_of, uint64_t *fm, uint32_t fm_cap, cudaStream_t s, uint64_t *launches);
+                      uint32_t pair_cap, E128 *pair_far, uint32_t far_cap, uint32_t *mate_of, uint64_t *fm, uint32_t fm_cap, cudaStream_t s,
+                      uint64_t *launches);
 int launch_sh_fm_pack(const uint64_t *fm, uint32_t n, E128 *out, cudaStream_t s, uint64_t *launches);
 int launch_sh_fm_unpack(const E128 *in, uint32_t n, uint64_t *fm, cudaStream_t s, uint64_t *launches);
 int launch_sh_apply_marks(const uint32_t *marks, uint64_t n_marks, uint64_t idx_base, uint64_t n, uint8_t *dup, cudaStream_t s,
@@ -139,7 +141,7 @@ int oge_gpu_shard_begin(oge_gpu_dedup_ctx *c, void **pub_dev, uint64_t *n_pub) {
     }
     OGE_CUDA_TRY(cudaEventRecord(c->copy_done, c->copy_stream));
     OGE_CUDA_TRY(cudaStreamWaitEvent(s, c->copy_done, 0));
-    sh.n_frag = sh.n_pe = sh.n_pairs = sh.n_retracted = sh.n_slots = sh.n_fm = 0;
+    sh.n_frag = sh.n_pe = sh.n_pairs = sh.n_retracted = sh.n_far = sh.n_far_dead = sh.n_slots = sh.n_fm = 0;
     if (n) {
         if ((rc = ensure_work(c))) return rc;
         PhaseClock clk(c, &c->stats.ms_endbuild);
@@ -166,6 +168,8 @@ int oge_gpu_shard_begin(oge_gpu_dedup_ctx *c, void **pub_dev, uint64_t *n_pub) {
         if ((rc = c->table.reserve(sh.n_slots, false, s))) return rc;
         if ((rc = c->pair.reserve(n_pe / 2 + 1024, false, s))) return rc;
         if ((rc = c->pair2.reserve(n_pe / 2 + 1024, false, s))) return rc;
+        if ((rc = c->pairf.reserve(n_pe / 2 + 1024, false, s))) return rc;
+        if ((rc = c->pairf2.reserve(n_pe / 2 + 1024, false, s))) return rc;
         if ((rc = c->cplx_slots.reserve(n_pe / 3 + 1024, false, s))) return rc;
         if ((rc = sh.pub_list.reserve(n_pe + 16, false, s))) return rc;
         OGE_CUDA_TRY(cudaMemsetAsync(c->table.p, 0, sh.n_slots * sizeof(MateSlot), s));
@@ -173,7 +177,7 @@ int oge_gpu_shard_begin(oge_gpu_dedup_ctx *c, void **pub_dev, uint64_t *n_pub) {
         jp.rec = c->rec.p; jp.off = c->off.p; jp.n = n; jp.idx_base = c->cfg.index_base;
         jp.frag = c->frag.p; jp.hk = c->hk.p; jp.tag = c->tag.p;
         jp.table = c->table.p; jp.n_slots = sh.n_slots;
-        jp.pair = c->pair.p; jp.mate_of = c->mate_of.p; jp.cplx = c->sortbuf.p; jp.cplx_slots = c->cplx_slots.p;
+        jp.pair = c->pair.p; jp.pair_far = c->pairf.p; jp.mate_of = c->mate_of.p; jp.cplx = c->sortbuf.p; jp.cplx_slots = c->cplx_slots.p;
         jp.counters = c->counters.p; jp.rg = rg_table(c); jp.kl = c->kl; jp.verify_names = c->cfg.verify_names;
         if ((rc = launch_mate_join(jp, s, &launches))) return rc;
         if ((rc = read_counters(c))) return rc;
@@ -188,6 +192,8 @@ int oge_gpu_shard_begin(oge_gpu_dedup_ctx *c, void **pub_dev, uint64_t *n_pub) {
         n_list = c->h_counters[CNT_PUB];
         sh.n_pairs = c->h_counters[CNT_PAIRS];
         sh.n_retracted = c->h_counters[CNT_PAIRS_RETRACTED];
+        sh.n_far = c->h_counters[CNT_PAIRS_FAR];
+        sh.n_far_dead = c->h_counters[CNT_FAR_RETRACTED];
         c->stats.n_complex_names = c->h_counters[CNT_COMPLEX];
         if ((rc = sh.pub.reserve(n_list + 1, false, s))) return rc;
         if ((rc = launch_sh_gather(sh.pub_list.p, (uint32_t) n_list, c->frag.p, c->hk.p, c->tag.p, sh.pub.p, s, &launches))) return rc;
@@ -210,12 +216,13 @@ int oge_gpu_shard_probe(oge_gpu_dedup_ctx *c, const void *pub_all_dev, uint64_t 
     if (sh.n_pe && n_all) {
         PhaseClock clk(c, &c->stats.ms_join);
         if ((rc = zero_counter(c, CNT_PUB))) return rc;
-        if ((rc = launch_sh_probe((const PubEntry *) pub_all_dev, n_all, shard_params(c), c->table.p, sh.n_slots, c->pair.p, sh.pub_list.p, s,
+        if ((rc = launch_sh_probe((const PubEntry *) pub_all_dev, n_all, shard_params(c), c->table.p, sh.n_slots, c->pair.p, c->pairf.p, sh.pub_list.p, s,
                                   &launches)))
             return rc;
         if ((rc = read_counters(c))) return rc;
         n2 = c->h_counters[CNT_PUB];
         sh.n_retracted = c->h_counters[CNT_PAIRS_RETRACTED];
+        sh.n_far_dead = c->h_counters[CNT_FAR_RETRACTED];
         if ((rc = sh.pub2.reserve(n2 + 1, false, s))) return rc;
         if ((rc = launch_sh_gather(sh.pub_list.p, (uint32_t) n2, c->frag.p, c->hk.p, c->tag.p, sh.pub2.p, s, &launches))) return rc;
         clk.stop();
@@ -238,9 +245,11 @@ int oge_gpu_shard_replay(oge_gpu_dedup_ctx *c, const void *w_dev, uint64_t n_w) 
     sh.n_w = n_w;
     if (n_w) {
         PhaseClock clk(c, &c->stats.ms_join);
-        const uint64_t pair_cap = sh.n_pairs + n_w / 2 + 16;
+        const uint64_t pair_cap = sh.n_pairs + n_w / 2 + 16, far_cap = sh.n_far + n_w / 2 + 16;
         if ((rc = c->pair.reserve(pair_cap, true, s))) return rc;
         if ((rc = c->pair2.reserve(pair_cap, false, s))) return rc;
+        if ((rc = c->pairf.reserve(far_cap, true, s))) return rc;
+        if ((rc = c->pairf2.reserve(far_cap, false, s))) return rc;
         if ((rc = sh.fm.reserve(n_w / 2 + 16, false, s))) return rc;
         if ((rc = sh.w_sort.reserve(n_w, false, s))) return rc;
         if ((rc = sh.w_sort2.reserve(n_w, false, s))) return rc;
@@ -251,10 +260,11 @@ int oge_gpu_shard_replay(oge_gpu_dedup_ctx *c, const void *w_dev, uint64_t n_w) 
         E128 *sorted = nullptr;
         if ((rc = radix_sort_128(sh.w_sort.p, sh.w_sort2.p, n_w, nullptr, 32, 128, c->scratch.p, s, &sorted, &launches))) return rc;
         if ((rc = launch_sh_replay(sorted, (uint32_t) n_w, (const PubEntry *) w_dev, c->cplx_state.p, shard_params(c), c->pair.p,
-                                   (uint32_t) c->pair.cap, c->mate_of.p, sh.fm.p, (uint32_t) sh.fm.cap, rg_table(c), s, &launches)))
+                                   (uint32_t) c->pair.cap, c->pairf.p, (uint32_t) c->pairf.cap, c->mate_of.p, sh.fm.p, (uint32_t) sh.fm.cap, rg_table(c), s, &launches)))
             return rc;
         if ((rc = read_counters(c))) return rc;
         sh.n_pairs = c->h_counters[CNT_PAIRS];
+        sh.n_far = c->h_counters[CNT_PAIRS_FAR];
         sh.n_fm = c->h_counters[CNT_FM];
         clk.stop();
     }
@@ -271,16 +281,19 @@ int oge_gpu_shard_route(oge_gpu_dedup_ctx *c, void **route_dev, uint64_t *n_rout
     ShardState &sh = c->sh;
     uint64_t launches = 0, n_out = 0;
     sh.n_frag_total = c->n;
-    if (c->cfg.world > 1 && (c->n || sh.n_pairs)) {
+    if (c->cfg.world > 1 && (c->n || sh.n_pairs || sh.n_far)) {
         PhaseClock clk(c, &c->stats.ms_select);
         const ShardParams S = shard_params(c);
         // count first (nothing is removed), then move
         for (int dry = 1; dry >= 0; dry--) {
-            if ((rc = zero_counter(c, CNT_ROUTE)) || (rc = zero_counter(c, CNT_SCRATCH0))) return rc;
+            if ((rc = zero_counter(c, CNT_ROUTE)) || (rc = zero_counter(c, CNT_SCRATCH0)) || (rc = zero_counter(c, CNT_SCRATCH1))) return rc;
             if ((rc = launch_sh_route(c->frag.p, c->n, 0, S, c->mate_of.p, sh.fm.p, 0, sh.route.p, dry ? 0u : (uint32_t) sh.route.cap, dry, s,
                                       &launches)))
                 return rc;
             if ((rc = launch_sh_route(c->pair.p, sh.n_pairs, 1, S, c->mate_of.p, sh.fm.p, 0, sh.route.p, dry ? 0u : (uint32_t) sh.route.cap,
+                                      dry, s, &launches)))
+                return rc;
+            if ((rc = launch_sh_route(c->pairf.p, sh.n_far, 2, S, c->mate_of.p, sh.fm.p, 0, sh.route.p, dry ? 0u : (uint32_t) sh.route.cap,
                                       dry, s, &launches)))
                 return rc;
             if ((rc = read_counters(c))) return rc;
@@ -290,9 +303,10 @@ int oge_gpu_shard_route(oge_gpu_dedup_ctx *c, void **route_dev, uint64_t *n_rout
                 if ((rc = sh.route.reserve(n_out, false, s))) return rc;
             }
         }
-        const uint64_t routed_pairs = n_out ? c->h_counters[CNT_SCRATCH0] : 0;
-        sh.n_retracted += routed_pairs;                 // dead pair entries, whatever the reason
-        sh.n_frag -= n_out - routed_pairs;
+        const uint64_t routed_near = n_out ? c->h_counters[CNT_SCRATCH0] : 0, routed_far = n_out ? c->h_counters[CNT_SCRATCH1] : 0;
+        sh.n_retracted += routed_near;                  // dead pair entries, whatever the reason
+        sh.n_far_dead += routed_far;
+        sh.n_frag -= n_out - routed_near - routed_far;
         clk.stop();
     }
     c->stats.launches += launches;
@@ -319,16 +333,19 @@ int oge_gpu_shard_finish(oge_gpu_dedup_ctx *c, const void *route_all_dev, uint64
         if ((rc = c->sortbuf.reserve(n + n_all, false, s))) return rc;
         if ((rc = c->pair.reserve(sh.n_pairs + n_all, true, s))) return rc;
         if ((rc = c->pair2.reserve(sh.n_pairs + n_all, false, s))) return rc;
+        if ((rc = c->pairf.reserve(sh.n_far + n_all, true, s))) return rc;
+        if ((rc = c->pairf2.reserve(sh.n_far + n_all, false, s))) return rc;
         if ((rc = sh.fm.reserve(sh.n_fm + n_all, true, s))) return rc;
-        if ((rc = c->scratch.reserve(std::max(sort_scratch_bytes(std::max(n + n_all, sh.n_pairs + n_all)), c->scratch.cap), true, s))) return rc;
+        if ((rc = c->scratch.reserve(std::max(sort_scratch_bytes(std::max(std::max(n + n_all, sh.n_pairs + n_all), sh.n_far + n_all)), c->scratch.cap), true, s))) return rc;
         if (n == 0 && (rc = c->mate_of.reserve(1, false, s))) return rc;
         if ((rc = zero_counter(c, CNT_FRAG_EXTRA))) return rc;
         if ((rc = launch_sh_receive((const RouteEntry *) route_all_dev, n_all, shard_params(c), c->frag.p + n, (uint32_t) n_all, c->pair.p,
-                                    (uint32_t) c->pair.cap, c->mate_of.p, sh.fm.p, (uint32_t) sh.fm.cap, s, &launches)))
+                                    (uint32_t) c->pair.cap, c->pairf.p, (uint32_t) c->pairf.cap, c->mate_of.p, sh.fm.p, (uint32_t) sh.fm.cap, s, &launches)))
             return rc;
         if ((rc = read_counters(c))) return rc;
         extra = c->h_counters[CNT_FRAG_EXTRA];
         sh.n_pairs = c->h_counters[CNT_PAIRS];
+        sh.n_far = c->h_counters[CNT_PAIRS_FAR];
         sh.n_fm = c->h_counters[CNT_FM];
         clk.stop();
     }
@@ -352,19 +369,20 @@ int oge_gpu_shard_finish(oge_gpu_dedup_ctx *c, const void *route_all_dev, uint64
     sp.counters = c->counters.p; sp.kl = c->kl; sp.n_dev = nullptr;
     sp.fm = sh.fm.p; sp.n_fm = (uint32_t) sh.n_fm; sp.foreign_marks = sh.marks.p; sp.foreign_cap = (uint32_t) sh.marks.cap;
     const uint64_t n_pairs = sh.n_pairs, n_dead = sh.n_retracted;
-    if (n_pairs) {
-        E128 *sorted_pairs = c->pair.p;
+    for (int far = 0; far < 2; far++) {      // near pairs (short key), then far pairs
+        const uint64_t cnt = far ? sh.n_far : n_pairs, dead = far ? sh.n_far_dead : n_dead;
+        if (!cnt) continue;
+        E128 *a = far ? c->pairf.p : c->pair.p, *b = far ? c->pairf2.p : c->pair2.p, *sorted = a;
         {
             PhaseClock clk(c, &c->stats.ms_sort_pair);
-            if ((rc = radix_sort_128(c->pair.p, c->pair2.p, n_pairs, nullptr, c->kl.p_coord2, c->kl.p_end, c->scratch.p, s, &sorted_pairs,
-                                     &launches, tp)))
+            if ((rc = radix_sort_128(a, b, cnt, nullptr, far ? c->kl.p_coord2 : c->kl.n_delta, c->kl.p_end, c->scratch.p, s, &sorted, &launches, tp)))
                 return rc;
             clk.stop();
         }
-        if (n_pairs > n_dead) {
+        if (cnt > dead) {
             PhaseClock clk(c, &c->stats.ms_select);
-            sp.sorted = sorted_pairs; sp.n_max = (uint32_t) (n_pairs - n_dead);
-            if ((rc = launch_select_pairs(sp, s, &launches))) return rc;
+            sp.sorted = sorted; sp.n_max = (uint32_t) (cnt - dead);
+            if ((rc = launch_select_pairs(sp, far != 0, s, &launches))) return rc;
             clk.stop();
         }
     }
@@ -389,7 +407,7 @@ int oge_gpu_shard_finish(oge_gpu_dedup_ctx *c, const void *route_all_dev, uint64
                                                   (unsigned long long) n_foreign, (unsigned long long) sh.marks.cap);
     c->stats.launches += launches;
     c->stats.n_frag_entries = n_frag_valid;
-    c->stats.n_pair_entries = n_pairs - n_dead;
+    c->stats.n_pair_entries = n_pairs - n_dead + sh.n_far - sh.n_far_dead;
     for (int i = 0; i < timer.used; i++) c->stats.ms_sort_pass_kernels += ms_between(c->pass_ev[2 * i], c->pass_ev[2 * i + 1]);
     c->stats.sort_pass_launches = timer.used;
     c->stats.sort_pass_bytes = timer.bytes;
@@ -419,9 +437,9 @@ int oge_gpu_shard_apply(oge_gpu_dedup_ctx *c, const void *marks_all_dev, uint64_
     c->stats.launches += launches;
     c->stats.n_hash_mismatch = c->h_counters[CNT_HASH_MISMATCH];
     c->stats.frag_key_bits = c->kl.f_end - c->kl.f_orient;
-    c->stats.pair_key_bits = c->kl.p_end - c->kl.p_coord2;
+    c->stats.pair_key_bits = c->kl.p_end - c->kl.n_delta;
     c->stats.frag_sort_passes = make_sort_plan(c->kl.f_orient, c->kl.f_end).n_pass;
-    c->stats.pair_sort_passes = make_sort_plan(c->kl.p_coord2, c->kl.p_end).n_pass;
+    c->stats.pair_sort_passes = make_sort_plan(c->kl.n_delta, c->kl.p_end).n_pass;
     c->ran = true;
     c->sh.phase = 0;
     return OGE_OK;
