@@ -59,7 +59,7 @@ def build_gpu(force=False, verbose=False):
             if os.path.exists(GPU_LIB):
                 return GPU_LIB
             raise RuntimeError("nvcc not found and %s is missing" % GPU_LIB)
-        flags = list(NVCC_FLAGS)
+        flags = list(NVCC_FLAGS) + os.environ.get("OGE_NVCC_EXTRA", "").split()
         if verbose:
             flags += ["-Xptxas", "-v"]
         out = _run(["nvcc"] + flags + ["-I", os.path.join(ROOT, "include"), "-I", CSRC] + cu +

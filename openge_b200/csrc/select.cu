@@ -12,7 +12,7 @@
 //   frags: runs of 2+ holding at least one unpaired end (:379); if the run also holds an end
 //          of a pair, all unpaired ends are marked (:517-522), else all but the survivor (:524-538)
 //
-// One CTA per 2048-entry tile, eight consecutive entries per thread.  The survivor of a run is the
+// One CTA per 1024-entry tile, four consecutive entries per thread (eight were measured: slower, 80 registers).  The survivor of a run is the
 // maximum of one packed 64-bit candidate per entry, (score + 2^15) << 32 | ~index, so "greatest score,
 // then smallest index" is a single max.  Runs that lie inside one thread's eight entries (almost all of
 // them: most runs are singletons) are reduced in registers with a forward and a backward sweep; only
@@ -26,7 +26,10 @@
 namespace oge {
 
 constexpr int SEL_THREADS = 256;
-constexpr int SEL_ITEMS = 8;
+#ifndef OGE_SEL_ITEMS
+#define OGE_SEL_ITEMS 4
+#endif
+constexpr int SEL_ITEMS = OGE_SEL_ITEMS;
 constexpr int SEL_TILE = SEL_THREADS * SEL_ITEMS;      // 2048
 constexpr int SEL_PAD = SEL_TILE + SEL_TILE / 8 + 2;   // one skew slot per 8 entries: conflict-free blocked reads
 constexpr int SEL_WARPS = SEL_THREADS / 32;
@@ -52,6 +55,26 @@ __device__ __forceinline__ bool key_eq(const E128 &a, const E128 &b, int key_lo)
     return xh == 0 && (xl >> key_lo) == 0;
 }
 
+// the rare path (an entry that is a duplicate): kept out of line so the common path stays small
+__device__ __noinline__ void mark_record(uint8_t *dup, uint64_t idx_base, uint64_t n_records, uint32_t *foreign_counter,
+                                         uint32_t *foreign_marks, uint32_t foreign_cap, uint32_t g) {
+    const uint64_t l = (uint64_t) g - idx_base;      // wraps for ordinals below the base
+    if (l < n_records) dup[l] = 1;
+    else {
+        uint32_t at = atomicAdd(foreign_counter, 1u);
+        if (at < foreign_cap) foreign_marks[at] = g;
+    }
+}
+__device__ __noinline__ uint32_t foreign_mate(const uint64_t *fm, uint32_t n_fm, uint32_t g1) {
+    uint32_t lo = 0, hi = n_fm;      // first couple with idx1 >= g1
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if ((uint32_t) (fm[mid] >> 32) < g1) lo = mid + 1;
+        else hi = mid;
+    }
+    return (uint32_t) fm[lo];
+}
+
 // what a run needs to know about its entries
 struct RunAgg {
     unsigned long long cand;      // max of (score + 2^15) << 32 | ~index
@@ -65,7 +88,7 @@ __device__ __forceinline__ void agg_add(RunAgg &a, unsigned long long cand, uint
 
 // KIND: 0 fragment ends, 1 near pairs, 2 far pairs (they differ in where the key starts)
 template <int KIND>
-__global__ void __launch_bounds__(SEL_THREADS, 3) select_kernel(SelectParams P) {
+__global__ void __launch_bounds__(SEL_THREADS, SEL_ITEMS == 8 ? 3 : 5) select_kernel(SelectParams P) {
     constexpr bool PAIRS = KIND != 0;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     E128 *s_e = reinterpret_cast<E128 *>(smem_raw);
@@ -108,25 +131,6 @@ __global__ void __launch_bounds__(SEL_THREADS, 3) select_kernel(SelectParams P) 
         if (PAIRS) return 0;
         return bits_get(v, L.f_paired, 1) ? RUN_HAS_PAIRED : RUN_HAS_UNPAIRED;
     };
-    auto mark = [&](uint32_t g) {
-        const uint64_t l = (uint64_t) g - P.idx_base;      // wraps for ordinals below the base
-        if (l < P.n_records) P.dup[l] = 1;
-        else {
-            uint32_t at = atomicAdd(&P.counters[CNT_FOREIGN_MARKS], 1u);
-            if (at < P.foreign_cap) P.foreign_marks[at] = g;
-        }
-    };
-    auto mate_of = [&](uint32_t g1) -> uint32_t {
-        const uint64_t l = (uint64_t) g1 - P.idx_base;
-        if (l < P.n_records) return P.mate_of[l];
-        uint32_t lo = 0, hi = P.n_fm;      // first couple with idx1 >= g1
-        while (lo < hi) {
-            uint32_t mid = (lo + hi) >> 1;
-            if ((uint32_t) (P.fm[mid] >> 32) < g1) lo = mid + 1;
-            else hi = mid;
-        }
-        return (uint32_t) P.fm[lo];
-    };
     uint32_t marks = 0;
     // the verdict on one entry given its run's totals (mark_duplicates.cpp:488-507, 515-540)
     auto decide = [&](const E128 &v, unsigned long long cand, const RunAgg &r) {
@@ -134,16 +138,18 @@ __global__ void __launch_bounds__(SEL_THREADS, 3) select_kernel(SelectParams P) 
         const bool is_best = cand == r.cand;
         if (PAIRS) {
             if (!is_best) {
-                const uint32_t i1 = idx_of(v);
-                mark(i1);
-                mark(mate_of(i1));
+                const uint32_t g1 = idx_of(v);
+                const uint64_t l1 = (uint64_t) g1 - P.idx_base;
+                const uint32_t g2 = l1 < P.n_records ? P.mate_of[l1] : foreign_mate(P.fm, P.n_fm, g1);
+                mark_record(P.dup, P.idx_base, P.n_records, &P.counters[CNT_FOREIGN_MARKS], P.foreign_marks, P.foreign_cap, g1);
+                mark_record(P.dup, P.idx_base, P.n_records, &P.counters[CNT_FOREIGN_MARKS], P.foreign_marks, P.foreign_cap, g2);
                 marks += 2;
             }
         } else {
             if (!(r.fl & RUN_HAS_UNPAIRED)) return;
             const bool mark_it = (r.fl & RUN_HAS_PAIRED) ? !(bits_get(v, L.f_paired, 1) != 0) : !is_best;
             if (mark_it) {
-                mark(idx_of(v));
+                mark_record(P.dup, P.idx_base, P.n_records, &P.counters[CNT_FOREIGN_MARKS], P.foreign_marks, P.foreign_cap, idx_of(v));
                 marks += 1;
             }
         }
@@ -260,13 +266,12 @@ __global__ void __launch_bounds__(SEL_THREADS, 3) select_kernel(SelectParams P) 
             if (k < n_mine) {
                 const bool run_ends_here = k == n_mine - 1 || ((heads >> (k + 1)) & 1);
                 if (run_ends_here) tot = F[k];
-                if (k < first_head) {
-                    if (left >= 0) decide(e[k], cand_of(e[k]), lead);      // else: owned by an earlier tile
-                } else if (k >= last_head) {
-                    decide(e[k], cand_of(e[k]), trail);
-                } else {
-                    decide(e[k], cand_of(e[k]), tot);
-                }
+                const bool leading = k < first_head, trailing = k >= last_head && last_head >= 0;
+                RunAgg r = tot;
+                if (leading) r = lead;
+                if (trailing) r = trail;
+                // (a leading entry with no head to its left in this tile is owned by an earlier tile)
+                if (r.cnt >= 2 && !(leading && left < 0)) decide(e[k], cand_of(e[k]), r);
             }
         }
     }
