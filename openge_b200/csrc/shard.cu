@@ -221,9 +221,8 @@ __global__ void __launch_bounds__(SH_THREADS) sh_route_kernel(E128 *__restrict__
         if (!is_dead(e)) want = owner_of(S, kind ? pair_packed(S.kl, e) : frag_packed(S.kl, e)) != S.rank;
     }
     const uint32_t at = warp_append(want, &S.counters[CNT_ROUTE]);
-    if (!want) return;
+    if (!want || dry || at >= out_cap) return;      // no room: the entry stays and is picked up by the next sweep
     if (kind) atomicAdd(&S.counters[kind == 1 ? CNT_SCRATCH0 : CNT_SCRATCH1], 1u);      // pair entries that leave
-    if (dry) return;                                                                    // counting pass: nothing moves
     RouteEntry r;
     r.e = e;
     r.kind = (uint32_t) kind;
@@ -242,7 +241,7 @@ __global__ void __launch_bounds__(SH_THREADS) sh_route_kernel(E128 *__restrict__
             r.idx2 = (uint32_t) fm[lo];
         }
     }
-    if (at < out_cap) out[at] = r;
+    out[at] = r;
     reinterpret_cast<ulonglong2 *>(ents)[j] = make_ulonglong2(~0ull, ~0ull);
 }
 

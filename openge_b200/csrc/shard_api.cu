@@ -9,6 +9,7 @@
 //   route   end entries whose key range belongs to another rank leave
 //   finish  (all ranks' routed entries) K3 + K4 on what this rank owns; marks for other ranks' records
 //   apply   (all ranks' marks) K5
+#include <stdlib.h>
 #include <string.h>
 
 #include "ctx.cuh"
@@ -284,24 +285,27 @@ int oge_gpu_shard_route(oge_gpu_dedup_ctx *c, void **route_dev, uint64_t *n_rout
     if (c->cfg.world > 1 && (c->n || sh.n_pairs || sh.n_far)) {
         PhaseClock clk(c, &c->stats.ms_select);
         const ShardParams S = shard_params(c);
-        // count first (nothing is removed), then move
-        for (int dry = 1; dry >= 0; dry--) {
-            if ((rc = zero_counter(c, CNT_ROUTE)) || (rc = zero_counter(c, CNT_SCRATCH0)) || (rc = zero_counter(c, CNT_SCRATCH1))) return rc;
-            if ((rc = launch_sh_route(c->frag.p, c->n, 0, S, c->mate_of.p, sh.fm.p, 0, sh.route.p, dry ? 0u : (uint32_t) sh.route.cap, dry, s,
-                                      &launches)))
-                return rc;
-            if ((rc = launch_sh_route(c->pair.p, sh.n_pairs, 1, S, c->mate_of.p, sh.fm.p, 0, sh.route.p, dry ? 0u : (uint32_t) sh.route.cap,
-                                      dry, s, &launches)))
-                return rc;
-            if ((rc = launch_sh_route(c->pairf.p, sh.n_far, 2, S, c->mate_of.p, sh.fm.p, 0, sh.route.p, dry ? 0u : (uint32_t) sh.route.cap,
-                                      dry, s, &launches)))
-                return rc;
+        // one sweep over the entries into a buffer sized for the usual case (boundary entries are a tiny
+        // fraction); entries that found no room stay in place and a second sweep collects them
+        {
+            const char *e = getenv("OGE_ROUTE_CAP");      // test hook: force the second sweep
+            const uint64_t want = e && *e ? (uint64_t) atoll(e) : std::max<uint64_t>(1u << 16, (c->n + sh.n_pairs + sh.n_far) / 64);
+            if (e && *e) sh.route.release();
+            if ((rc = sh.route.reserve(std::max<uint64_t>(want, 1), false, s))) return rc;
+        }
+        if ((rc = zero_counter(c, CNT_ROUTE)) || (rc = zero_counter(c, CNT_SCRATCH0)) || (rc = zero_counter(c, CNT_SCRATCH1))) return rc;
+        for (int sweep = 0; sweep < 2; sweep++) {
+            const uint32_t cap = (uint32_t) sh.route.cap;
+            if ((rc = launch_sh_route(c->frag.p, c->n, 0, S, c->mate_of.p, sh.fm.p, 0, sh.route.p, cap, 0, s, &launches))) return rc;
+            if ((rc = launch_sh_route(c->pair.p, sh.n_pairs, 1, S, c->mate_of.p, sh.fm.p, 0, sh.route.p, cap, 0, s, &launches))) return rc;
+            if ((rc = launch_sh_route(c->pairf.p, sh.n_far, 2, S, c->mate_of.p, sh.fm.p, 0, sh.route.p, cap, 0, s, &launches))) return rc;
             if ((rc = read_counters(c))) return rc;
             n_out = c->h_counters[CNT_ROUTE];
-            if (dry) {
-                if (n_out == 0) break;
-                if ((rc = sh.route.reserve(n_out, false, s))) return rc;
-            }
+            if (n_out <= cap) break;
+            if (sweep == 1) return fail_msg(OGE_ERR_STATE, "shard_route: entry count changed between sweeps");
+            if ((rc = sh.route.reserve(n_out, true, s))) return rc;
+            OGE_CUDA_TRY(cudaMemcpyAsync(c->counters.p + CNT_ROUTE, &cap, 4, cudaMemcpyHostToDevice, s));      // continue behind what is stored
+            OGE_CUDA_TRY(cudaStreamSynchronize(s));
         }
         const uint64_t routed_near = n_out ? c->h_counters[CNT_SCRATCH0] : 0, routed_far = n_out ? c->h_counters[CNT_SCRATCH1] : 0;
         sh.n_retracted += routed_near;                  // dead pair entries, whatever the reason

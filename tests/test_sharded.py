@@ -156,6 +156,16 @@ def test_cuda_shards_in_process_equal_oracle(case, world):
 
 
 @pytest.mark.gpu
+def test_cuda_route_overflow_sweep(monkeypatch):
+    """A routing buffer that is too small: the entries that found no room are collected by a second sweep."""
+    monkeypatch.setenv("OGE_ROUTE_CAP", "1")
+    bam = straddle_fixture()
+    want = oracle.markdup(bam.records, bam.offsets, bam.text)
+    got, info = sharded.dedup_in_process(bam, 2)
+    assert np.array_equal(got, want) and info["routed"] >= 2
+
+
+@pytest.mark.gpu
 def test_cuda_shards_larger_synthetic():
     bam = synth.make("C3", 0.05, seed=21)
     want = oracle.markdup(bam.records, bam.offsets, bam.text)
