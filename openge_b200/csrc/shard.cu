@@ -109,7 +109,9 @@ __global__ void __launch_bounds__(SH_THREADS) sh_probe_kernel(const PubEntry *__
 }
 
 // ---- phase 3: replay of the published set -------------------------------------------------------------
-// sort entry: hi = key hash, lo = (global ordinal << 32) | position in the published array
+// sort entry: hi = key hash, lo = (global ordinal << 32) | position in the published array; sorted on bits
+// [32, 96): by the low half of the hash, then by file order.  A segment of equal low halves may mix
+// several hashes; the replay compares whole keys (and whole hashes), so that only costs comparisons.
 __global__ void __launch_bounds__(SH_THREADS) sh_wbuild_kernel(const PubEntry *__restrict__ w, uint32_t n_w, KeyLayout L, E128 *__restrict__ out) {
     const uint32_t j = blockIdx.x * SH_THREADS + threadIdx.x;
     if (j >= n_w) return;
@@ -177,17 +179,17 @@ __global__ void __launch_bounds__(SH_THREADS) sh_replay_kernel(const E128 *__res
                                                                RgTable rg) {
     const uint32_t j = blockIdx.x * SH_THREADS + threadIdx.x;
     if (j >= n_w) return;
-    const uint64_t h = sorted[j].hi;
-    if (j > 0 && sorted[j - 1].hi == h) return;      // not a segment head
+    const uint32_t h = (uint32_t) sorted[j].hi;
+    if (j > 0 && (uint32_t) sorted[j - 1].hi == h) return;      // not a segment head
     uint32_t end = j;
-    while (end < n_w && sorted[end].hi == h) state[end++] = 0;
+    while (end < n_w && (uint32_t) sorted[end].hi == h) state[end++] = 0;
     for (uint32_t a = j; a < end; a++) {
         const PubEntry &pa = w[(uint32_t) sorted[a].lo];
         if (a > j && sorted[a].lo >> 32 == sorted[a - 1].lo >> 32) continue;      // the same record published twice
         int found = -1;
         for (uint32_t b = j; b < a; b++) {
             if (!state[b]) continue;
-            if (pub_keys_equal(pa.tag, w[(uint32_t) sorted[b].lo].tag, rg)) { found = (int) b; break; }
+            if (sorted[b].hi == sorted[a].hi && pub_keys_equal(pa.tag, w[(uint32_t) sorted[b].lo].tag, rg)) { found = (int) b; break; }
         }
         if (found < 0) { state[a] = 1; continue; }
         state[found] = 0;

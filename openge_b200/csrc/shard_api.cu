@@ -259,7 +259,7 @@ int oge_gpu_shard_replay(oge_gpu_dedup_ctx *c, const void *w_dev, uint64_t n_w) 
         if (c->n == 0 && (rc = c->mate_of.reserve(1, false, s))) return rc;
         if ((rc = launch_sh_wbuild((const PubEntry *) w_dev, (uint32_t) n_w, c->kl, sh.w_sort.p, s, &launches))) return rc;
         E128 *sorted = nullptr;
-        if ((rc = radix_sort_128(sh.w_sort.p, sh.w_sort2.p, n_w, nullptr, 32, 128, c->scratch.p, s, &sorted, &launches))) return rc;
+        if ((rc = radix_sort_128(sh.w_sort.p, sh.w_sort2.p, n_w, nullptr, 32, 96, c->scratch.p, s, &sorted, &launches))) return rc;
         if ((rc = launch_sh_replay(sorted, (uint32_t) n_w, (const PubEntry *) w_dev, c->cplx_state.p, shard_params(c), c->pair.p,
                                    (uint32_t) c->pair.cap, c->pairf.p, (uint32_t) c->pairf.cap, c->mate_of.p, sh.fm.p, (uint32_t) sh.fm.cap, rg_table(c), s, &launches)))
             return rc;
