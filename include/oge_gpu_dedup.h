@@ -151,25 +151,27 @@ int oge_gpu_debug_sort128(int device, void *entries, uint64_t n, int bit_lo, int
  * The reference is a single process; these entry points exist so that G ranks, each holding a contiguous
  * record range of one coordinate-sorted file, produce exactly the flags of its single-stream run
  * (`openge dedup --nosplit -v`; the reference's own split mode, command_dedup.cpp:71-95, does not: SURVEY F2).
- * Between the calls the host delivers every rank's output list to every rank (all-to-all over NCCL); all
- * pointers are DEVICE pointers, lists are arrays of 64-byte (published), 32-byte (routed) or 4-byte
- * (marks) items, valid until the next call on the context.  Order: setup, then per run
- * begin -> probe -> replay -> route -> finish -> apply; afterwards oge_gpu_dedup_flags / _pull / _get_stats. */
+ * Between the calls the host delivers every rank's output lists to every rank (all-to-all over NCCL): three
+ * exchanges per run.  All pointers are DEVICE pointers; lists are arrays of 64-byte (published), 32-byte
+ * (routed) or 4-byte (marks) items, valid until the next call on the context.  Order: setup once, then per
+ * run begin -> probe -> finish -> apply; afterwards oge_gpu_dedup_flags / _pull / _get_stats. */
 int oge_gpu_shard_setup(oge_gpu_dedup_ctx *ctx, uint64_t global_n, const uint64_t *bases /* world + 1 */,
                         const int32_t *split_ref, const int32_t *split_pos /* world - 1: first record of ranks 1.. */);
-/* K1 + local mate join (mark_duplicates.cpp:192-256 on the shard); publishes the records whose RG:name key was
- * not seen exactly twice on this rank. */
-int oge_gpu_shard_begin(oge_gpu_dedup_ctx *ctx, void **pub_dev, uint64_t *n_pub);
-/* in: round-1 entries of all ranks.  A local couple of a name published elsewhere is retracted and published. */
-int oge_gpu_shard_probe(oge_gpu_dedup_ctx *ctx, const void *pub_all_dev, uint64_t n_all, void **pub2_dev, uint64_t *n_pub2);
-/* in: every entry of both rounds.  Replays ReadEndsMap's toggle (picard_structures.h:87-96) over them in global
- * file order and keeps the pairs whose key range this rank owns. */
-int oge_gpu_shard_replay(oge_gpu_dedup_ctx *ctx, const void *w_dev, uint64_t n_w);
-/* out: end entries whose (refID, unclipped coordinate) lies in another rank's range. */
-int oge_gpu_shard_route(oge_gpu_dedup_ctx *ctx, void **route_dev, uint64_t *n_route);
-/* in: routed entries of all ranks.  K3 + K4 (mark_duplicates.cpp:262-271, 326-400) on what this rank owns;
- * out: global ordinals to mark that belong to other ranks. */
-int oge_gpu_shard_finish(oge_gpu_dedup_ctx *ctx, const void *route_all_dev, uint64_t n_all, void **marks_dev, uint64_t *n_marks);
+/* K1 + local mate join (mark_duplicates.cpp:192-256 on the shard).  out: the records whose RG:name key was not
+ * seen exactly twice on this rank (published, round 1), and copies of the fragment ends whose (refID,
+ * unclipped coordinate) lies in another rank's key range. */
+int oge_gpu_shard_begin(oge_gpu_dedup_ctx *ctx, void **pub_dev, uint64_t *n_pub, void **frag_route_dev, uint64_t *n_frag_route);
+/* in: round-1 entries and routed fragment ends of all ranks.  A local couple of a name published elsewhere is
+ * retracted and published (round 2); the fragment K3 + K4 (mark_duplicates.cpp:262-271, 371-390) start on a
+ * side stream; out also: pair ends whose key lies in another rank's range. */
+int oge_gpu_shard_probe(oge_gpu_dedup_ctx *ctx, const void *pub_all_dev, uint64_t n_pub_all, const void *frag_route_all_dev,
+                        uint64_t n_frag_route_all, void **pub2_dev, uint64_t *n_pub2, void **pair_route_dev, uint64_t *n_pair_route);
+/* in: every published entry of both rounds and the routed pair ends of all ranks.  Replays ReadEndsMap's toggle
+ * (picard_structures.h:87-96) over the published set in global file order, keeps the pairs whose key range this
+ * rank owns, pair K3 + K4 (:336-355, 488-507).  out: global ordinals to mark that belong to other ranks
+ * (two lists: from pairs, from fragments). */
+int oge_gpu_shard_finish(oge_gpu_dedup_ctx *ctx, const void *pub_both_dev, uint64_t n_pub_both, const void *pair_route_all_dev,
+                         uint64_t n_pair_route_all, void **marks_dev, uint64_t *n_marks, void **marks_frag_dev, uint64_t *n_marks_frag);
 /* in: marks of all ranks.  K5 (mark_duplicates.cpp:443-465). */
 int oge_gpu_shard_apply(oge_gpu_dedup_ctx *ctx, const void *marks_all_dev, uint64_t n_all);
 

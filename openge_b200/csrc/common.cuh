@@ -103,6 +103,8 @@ enum {
     CNT_ROUTE,          // sharded: entries handed to their key owner
     CNT_FRAG_EXTRA,     // sharded: fragment entries received
     CNT_FM,             // sharded: foreign-mate couples
+    CNT_FRAG_VALID,     // sharded: fragment entries to select over (device-side count)
+    CNT_FOREIGN_MARKS_FRAG,
     CNT_SCRATCH0,
     CNT_SCRATCH1,
     CNT_N = 32

@@ -50,8 +50,13 @@ struct ShardState {
     std::vector<uint64_t> split_keys;     // world - 1 packed (ref << coord_bits | biased coord): first key of ranks 1..
     DevBuf<uint64_t> d_split;
     DevBuf<PubEntry> pub, pub2;           // published entries, rounds 1 and 2
-    DevBuf<RouteEntry> route;
-    DevBuf<uint32_t> marks, pub_list;
+    DevBuf<RouteEntry> route, froute;
+    DevBuf<uint32_t> marks, marks_frag, pub_list;
+    DevBuf<uint8_t> scratch2;             // sort scratch of the side stream
+    cudaEvent_t ev_main = nullptr, ev_side[3] = {nullptr, nullptr, nullptr};
+    bool frag_busy = false;
+    int side_pass_used = 0;
+    uint64_t side_pass_bytes = 0, n_froute_all = 0;
     DevBuf<uint64_t> fm;                  // foreign mates: (idx1 << 32 | idx2), sorted by idx1
     DevBuf<E128> fm_sort, w_sort, w_sort2;
     uint64_t n_frag = 0, n_pe = 0, n_pairs = 0, n_retracted = 0, n_slots = 0, n_fm = 0, n_frag_total = 0, n_w = 0, n_far = 0, n_far_dead = 0;
@@ -65,7 +70,7 @@ using namespace oge;      // internal header: only this library's .cu files incl
 struct oge_gpu_dedup_ctx {
     oge_gpu_dedup_config cfg;
     int sms = 148;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, side_stream = nullptr;
     cudaEvent_t copy_done = nullptr;
     cudaEvent_t ev[10];
     cudaEvent_t pass_ev[2 * 48];      // profile_events: one pair per radix-sort pass launch

@@ -196,6 +196,10 @@ int oge_gpu_dedup_create(const oge_gpu_dedup_config *cfg, oge_gpu_dedup_ctx **ou
     do {
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->sh.ev_main, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreate(&c->sh.ev_side[0]) != cudaSuccess || cudaEventCreate(&c->sh.ev_side[1]) != cudaSuccess ||
+            cudaEventCreate(&c->sh.ev_side[2]) != cudaSuccess ||
             cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming) != cudaSuccess) {
             rc = fail_cuda(cudaGetLastError(), "stream/event create", __FILE__, __LINE__);
             break;
@@ -224,6 +228,7 @@ void oge_gpu_dedup_destroy(oge_gpu_dedup_ctx *c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    if (c->side_stream) cudaStreamSynchronize(c->side_stream);
     c->rec.release(); c->off.release(); c->rg_bytes.release(); c->rg_off.release(); c->rg_lib.release();
     c->frag.release(); c->sortbuf.release(); c->pair.release(); c->pair2.release(); c->pairf.release(); c->pairf2.release(); c->hk.release();
     c->tag.release(); c->flag_in.release(); c->flag_out.release(); c->dup.release(); c->scratch.release();
@@ -234,6 +239,12 @@ void oge_gpu_dedup_destroy(oge_gpu_dedup_ctx *c) {
     if (c->copy_done) cudaEventDestroy(c->copy_done);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->side_stream) cudaStreamDestroy(c->side_stream);
+    if (c->sh.ev_main) cudaEventDestroy(c->sh.ev_main);
+    for (auto &e : c->sh.ev_side) if (e) cudaEventDestroy(e);
+    c->sh.d_split.release(); c->sh.pub.release(); c->sh.pub2.release(); c->sh.route.release(); c->sh.froute.release();
+    c->sh.marks.release(); c->sh.marks_frag.release(); c->sh.pub_list.release(); c->sh.fm.release(); c->sh.fm_sort.release();
+    c->sh.w_sort.release(); c->sh.w_sort2.release(); c->sh.scratch2.release();
     delete c;
 }
 
@@ -403,7 +414,8 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     SelectParams sp;
     sp.dup = c->dup.p; sp.mate_of = c->mate_of.p; sp.idx_base = c->cfg.index_base; sp.n_records = n;
     sp.counters = c->counters.p; sp.kl = c->kl; sp.n_dev = nullptr;
-    sp.fm = nullptr; sp.n_fm = 0; sp.foreign_marks = nullptr; sp.foreign_cap = 0;
+    sp.fm = nullptr; sp.n_fm = 0; sp.foreign_marks = nullptr; sp.foreign_cap = 0; sp.foreign_counter = c->counters.p + CNT_FOREIGN_MARKS;
+    sp.split = nullptr; sp.world = 1; sp.rank = 0;
     // near pairs (short key) and far pairs (full key) are separate lists: equal keys imply equal class
     E128 *sorted_pairs = c->pair.p, *sorted_far = c->pairf.p;
     if (n_pairs) {

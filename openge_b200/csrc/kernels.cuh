@@ -98,8 +98,11 @@ struct SelectParams {
     // range sharding only (null / 0 on one GPU)
     const uint64_t *fm;         // (idx1 << 32 | idx2) sorted by idx1: mates of pair entries whose idx1 is not local
     uint32_t n_fm;
-    uint32_t *foreign_marks;    // out: global ordinals to mark on other ranks (counters[CNT_FOREIGN_MARKS])
+    uint32_t *foreign_marks;    // out: global ordinals to mark on other ranks
     uint32_t foreign_cap;
+    uint32_t *foreign_counter;  // how many of them
+    const uint64_t *split;      // world - 1 packed first keys of ranks 1.. (fragment ends whose key another rank owns are left alone)
+    int world, rank;
 };
 
 int launch_select_pairs(const SelectParams &P, bool far, cudaStream_t stream, uint64_t *launches);

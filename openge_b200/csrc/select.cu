@@ -141,15 +141,21 @@ __global__ void __launch_bounds__(SEL_THREADS, SEL_ITEMS == 8 ? 3 : 5) select_ke
                 const uint32_t g1 = idx_of(v);
                 const uint64_t l1 = (uint64_t) g1 - P.idx_base;
                 const uint32_t g2 = l1 < P.n_records ? P.mate_of[l1] : foreign_mate(P.fm, P.n_fm, g1);
-                mark_record(P.dup, P.idx_base, P.n_records, &P.counters[CNT_FOREIGN_MARKS], P.foreign_marks, P.foreign_cap, g1);
-                mark_record(P.dup, P.idx_base, P.n_records, &P.counters[CNT_FOREIGN_MARKS], P.foreign_marks, P.foreign_cap, g2);
+                mark_record(P.dup, P.idx_base, P.n_records, P.foreign_counter, P.foreign_marks, P.foreign_cap, g1);
+                mark_record(P.dup, P.idx_base, P.n_records, P.foreign_counter, P.foreign_marks, P.foreign_cap, g2);
                 marks += 2;
             }
         } else {
             if (!(r.fl & RUN_HAS_UNPAIRED)) return;
+            if (P.world > 1) {      // range shards: a run whose key another rank owns is judged there (its entries were copied over)
+                const uint64_t packed = bits_get(v, L.f_coord, L.coord_bits + L.ref_bits);
+                int owner = 0;
+                for (int q = 0; q + 1 < P.world; q++) owner += P.split[q] <= packed ? 1 : 0;
+                if (owner != P.rank) return;
+            }
             const bool mark_it = (r.fl & RUN_HAS_PAIRED) ? !(bits_get(v, L.f_paired, 1) != 0) : !is_best;
             if (mark_it) {
-                mark_record(P.dup, P.idx_base, P.n_records, &P.counters[CNT_FOREIGN_MARKS], P.foreign_marks, P.foreign_cap, idx_of(v));
+                mark_record(P.dup, P.idx_base, P.n_records, P.foreign_counter, P.foreign_marks, P.foreign_cap, idx_of(v));
                 marks += 1;
             }
         }

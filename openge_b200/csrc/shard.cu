@@ -210,7 +210,8 @@ __global__ void __launch_bounds__(SH_THREADS) sh_replay_kernel(const E128 *__res
 }
 
 // ---- phase 4: entries whose key belongs to another rank -------------------------------------------------
-// kind 0: fragment entries, 1: near pairs, 2: far pairs.  Routed entries leave the local list (all-ones = dead).
+// kind 0: fragment entries, 1: near pairs, 2: far pairs.  dry 0: routed entries leave the local list (all-ones =
+// dead); 1: count only; 2: a copy leaves (fragment ends: K4 skips the runs whose key another rank owns).
 __global__ void __launch_bounds__(SH_THREADS) sh_route_kernel(E128 *__restrict__ ents, uint64_t n_ents, int kind, ShardParams S,
                                                               const uint32_t *__restrict__ mate_of, const uint64_t *__restrict__ fm, uint32_t n_fm,
                                                               RouteEntry *__restrict__ out, uint32_t out_cap, int dry) {
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(SH_THREADS) sh_route_kernel(E128 *__restrict__
         if (!is_dead(e)) want = owner_of(S, kind ? pair_packed(S.kl, e) : frag_packed(S.kl, e)) != S.rank;
     }
     const uint32_t at = warp_append(want, &S.counters[CNT_ROUTE]);
-    if (!want || dry || at >= out_cap) return;      // no room: the entry stays and is picked up by the next sweep
+    if (!want || dry == 1 || at >= out_cap) return;      // no room: the entry stays and is picked up by the next sweep
     if (kind) atomicAdd(&S.counters[kind == 1 ? CNT_SCRATCH0 : CNT_SCRATCH1], 1u);      // pair entries that leave
     RouteEntry r;
     r.e = e;
@@ -244,16 +245,17 @@ __global__ void __launch_bounds__(SH_THREADS) sh_route_kernel(E128 *__restrict__
         }
     }
     out[at] = r;
-    reinterpret_cast<ulonglong2 *>(ents)[j] = make_ulonglong2(~0ull, ~0ull);
+    if (dry == 0) reinterpret_cast<ulonglong2 *>(ents)[j] = make_ulonglong2(~0ull, ~0ull);      // dry == 2: a copy leaves, the entry stays
 }
 
-__global__ void __launch_bounds__(SH_THREADS) sh_receive_kernel(const RouteEntry *__restrict__ in, uint64_t n_in, ShardParams S,
+__global__ void __launch_bounds__(SH_THREADS) sh_receive_kernel(const RouteEntry *__restrict__ in, uint64_t n_in, ShardParams S, uint32_t kinds,
                                                                 E128 *__restrict__ frag_extra, uint32_t frag_cap, E128 *__restrict__ pair,
                                                                 uint32_t pair_cap, E128 *__restrict__ pair_far, uint32_t far_cap,
                                                                 uint32_t *__restrict__ mate_of, uint64_t *__restrict__ fm, uint32_t fm_cap) {
     const uint64_t j = (uint64_t) blockIdx.x * SH_THREADS + threadIdx.x;
     if (j >= n_in) return;
     const RouteEntry r = in[j];
+    if (!((kinds >> r.kind) & 1u)) return;      // not in this call
     if (owner_of(S, r.kind ? pair_packed(S.kl, r.e) : frag_packed(S.kl, r.e)) != S.rank) return;
     if (r.kind == 0) {
         const uint32_t at = atomicAdd(&S.counters[CNT_FRAG_EXTRA], 1u);
@@ -337,10 +339,10 @@ int launch_sh_route(E128 *ents, uint64_t n_ents, int kind, const ShardParams &S,
     SH_LAUNCH(n_ents, (sh_route_kernel<<<grid_for(n_ents), SH_THREADS, 0, s>>>(ents, n_ents, kind, S, mate_of, fm, n_fm, out, out_cap, dry)));
     return 0;
 }
-int launch_sh_receive(const RouteEntry *in, uint64_t n_in, const ShardParams &S, E128 *frag_extra, uint32_t frag_cap, E128 *pair,
+int launch_sh_receive(const RouteEntry *in, uint64_t n_in, const ShardParams &S, uint32_t kinds, E128 *frag_extra, uint32_t frag_cap, E128 *pair,
                       uint32_t pair_cap, E128 *pair_far, uint32_t far_cap, uint32_t *mate_of, uint64_t *fm, uint32_t fm_cap, cudaStream_t s,
                       uint64_t *launches) {
-    SH_LAUNCH(n_in, (sh_receive_kernel<<<grid_for(n_in), SH_THREADS, 0, s>>>(in, n_in, S, frag_extra, frag_cap, pair, pair_cap, pair_far,
+    SH_LAUNCH(n_in, (sh_receive_kernel<<<grid_for(n_in), SH_THREADS, 0, s>>>(in, n_in, S, kinds, frag_extra, frag_cap, pair, pair_cap, pair_far,
                                                                             far_cap, mate_of, fm, fm_cap)));
     return 0;
 }

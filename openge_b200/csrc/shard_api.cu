@@ -27,7 +27,7 @@ int launch_sh_replay(const E128 *sorted, uint32_t n_w, const PubEntry *w, uint8_
                      uint64_t *launches);
 int launch_sh_route(E128 *ents, uint64_t n_ents, int kind, const ShardParams &S, const uint32_t *mate_of, const uint64_t *fm, uint32_t n_fm,
                     RouteEntry *out, uint32_t out_cap, int dry, cudaStream_t s, uint64_t *launches);
-int launch_sh_receive(const RouteEntry *in, uint64_t n_in, const ShardParams &S, E128 *frag_extra, uint32_t frag_cap, E128 *pair,
+int launch_sh_receive(const RouteEntry *in, uint64_t n_in, const ShardParams &S, uint32_t kinds, E128 *frag_extra, uint32_t frag_cap, E128 *pair,
                       uint32_t pair_cap, E128 *pair_far, uint32_t far_cap, uint32_t *mate_of, uint64_t *fm, uint32_t fm_cap, cudaStream_t s,
                       uint64_t *launches);
 int launch_sh_fm_pack(const uint64_t *fm, uint32_t n, E128 *out, cudaStream_t s, uint64_t *launches);
@@ -110,10 +110,50 @@ int oge_gpu_shard_setup(oge_gpu_dedup_ctx *c, uint64_t global_n, const uint64_t 
     return OGE_OK;
 }
 
-int oge_gpu_shard_begin(oge_gpu_dedup_ctx *c, void **pub_dev, uint64_t *n_pub) {
+// sweep `ents` for entries owned by other ranks into sh.route (appending behind `have` stored entries)
+static int route_sweep(oge_gpu_dedup_ctx *c, int n_lists, E128 *const *lists, const uint64_t *counts, const int *kinds, int mode,
+                       uint64_t *n_out, uint64_t *launches) {
+    cudaStream_t s = c->stream;
+    ShardState &sh = c->sh;
+    const ShardParams S = shard_params(c);
+    int rc;
+    uint64_t total = 0;
+    for (int i = 0; i < n_lists; i++) total += counts[i];
+    {
+        const char *e = getenv("OGE_ROUTE_CAP");      // test hook: force the second sweep
+        const uint64_t want = e && *e ? (uint64_t) atoll(e) : std::max<uint64_t>(1u << 16, total / 64);
+        if (e && *e) sh.route.release();
+        if ((rc = sh.route.reserve(std::max<uint64_t>(want, 1), false, s))) return rc;
+    }
+    if ((rc = zero_counter(c, CNT_ROUTE)) || (rc = zero_counter(c, CNT_SCRATCH0)) || (rc = zero_counter(c, CNT_SCRATCH1))) return rc;
+    *n_out = 0;
+    for (int sweep = 0; sweep < 2; sweep++) {      // entries that found no room stay in place: a second sweep collects them
+        const uint32_t cap = (uint32_t) sh.route.cap;
+        for (int i = 0; i < n_lists; i++)
+            if ((rc = launch_sh_route(lists[i], counts[i], kinds[i], S, c->mate_of.p, sh.fm.p, 0, sh.route.p, cap, mode, s, launches))) return rc;
+        if ((rc = read_counters(c))) return rc;
+        *n_out = c->h_counters[CNT_ROUTE];
+        if (*n_out <= cap) break;
+        if (sweep == 1) return fail_msg(OGE_ERR_STATE, "shard route: entry count changed between sweeps");
+        if ((rc = sh.route.reserve(*n_out, mode == 0, s))) return rc;
+        // moving sweep: continue behind what is stored; copying sweep: nothing left the lists, start over
+        const uint32_t restart = mode == 0 ? cap : 0u;
+        OGE_CUDA_TRY(cudaMemcpyAsync(c->counters.p + CNT_ROUTE, &restart, 4, cudaMemcpyHostToDevice, s));
+        OGE_CUDA_TRY(cudaStreamSynchronize(s));
+        if (mode != 0 && ((rc = zero_counter(c, CNT_SCRATCH0)) || (rc = zero_counter(c, CNT_SCRATCH1)))) return rc;
+    }
+    return 0;
+}
+
+__global__ void sh_add_counter_kernel(uint32_t *dst, uint32_t base, const uint32_t *counter, uint32_t cap) {
+    uint32_t v = base + min(*counter, cap);
+    *dst = v;
+}
+
+int oge_gpu_shard_begin(oge_gpu_dedup_ctx *c, void **pub_dev, uint64_t *n_pub, void **froute_dev, uint64_t *n_froute) {
     int rc = need_phase(c, c ? c->sh.phase : 0, "shard_begin");
     if (rc) return rc;
-    if (!pub_dev || !n_pub) return fail_msg(OGE_ERR_INVALID_ARG, "shard_begin: null argument");
+    if (!pub_dev || !n_pub || !froute_dev || !n_froute) return fail_msg(OGE_ERR_INVALID_ARG, "shard_begin: null argument");
     if (c->sh.bases[c->cfg.rank + 1] - c->sh.bases[c->cfg.rank] != c->n)
         return fail_msg(OGE_ERR_INVALID_ARG, "shard_begin: the context holds %llu records, the ranges say %llu", (unsigned long long) c->n,
                         (unsigned long long) (c->sh.bases[c->cfg.rank + 1] - c->sh.bases[c->cfg.rank]));
@@ -122,8 +162,8 @@ int oge_gpu_shard_begin(oge_gpu_dedup_ctx *c, void **pub_dev, uint64_t *n_pub) {
     memset(&c->stats, 0, sizeof(c->stats));
     c->stats.n_records = c->n;
     c->ran = false;
-    *pub_dev = nullptr;
-    *n_pub = 0;
+    *pub_dev = *froute_dev = nullptr;
+    *n_pub = *n_froute = 0;
     if ((rc = compute_layout(c, &c->kl))) return rc;
     const uint64_t n = c->n;
     uint64_t launches = 0;
@@ -142,11 +182,12 @@ int oge_gpu_shard_begin(oge_gpu_dedup_ctx *c, void **pub_dev, uint64_t *n_pub) {
     }
     OGE_CUDA_TRY(cudaEventRecord(c->copy_done, c->copy_stream));
     OGE_CUDA_TRY(cudaStreamWaitEvent(s, c->copy_done, 0));
-    sh.n_frag = sh.n_pe = sh.n_pairs = sh.n_retracted = sh.n_far = sh.n_far_dead = sh.n_slots = sh.n_fm = 0;
+    sh.n_frag = sh.n_pe = sh.n_pairs = sh.n_retracted = sh.n_far = sh.n_far_dead = sh.n_slots = sh.n_fm = sh.n_froute_all = 0;
+    OGE_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, CNT_N * 4, s));
+    uint64_t n_fr = 0;
     if (n) {
         if ((rc = ensure_work(c))) return rc;
         PhaseClock clk(c, &c->stats.ms_endbuild);
-        OGE_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, CNT_N * 4, s));
         OGE_CUDA_TRY(cudaMemsetAsync(c->dup.p, 0, n, s));
         EndbuildParams eb;
         eb.rec = c->rec.p; eb.off = c->off.p; eb.n = n; eb.idx_base = c->cfg.index_base;
@@ -158,8 +199,6 @@ int oge_gpu_shard_begin(oge_gpu_dedup_ctx *c, void **pub_dev, uint64_t *n_pub) {
         if ((rc = check_endbuild_errors(c))) return rc;
         sh.n_frag = c->h_counters[CNT_FRAG];
         sh.n_pe = c->h_counters[CNT_PAIR_ELIGIBLE];
-    } else {
-        OGE_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, CNT_N * 4, s));
     }
     uint64_t n_list = 0;
     if (sh.n_pe) {
@@ -200,25 +239,47 @@ int oge_gpu_shard_begin(oge_gpu_dedup_ctx *c, void **pub_dev, uint64_t *n_pub) {
         if ((rc = launch_sh_gather(sh.pub_list.p, (uint32_t) n_list, c->frag.p, c->hk.p, c->tag.p, sh.pub.p, s, &launches))) return rc;
         clk.stop();
     }
+    // copies of the fragment ends whose key lies in another rank's range leave now: they travel with
+    // the first exchange, so that the fragment sort can overlap the pair exchanges (the originals stay:
+    // K4 leaves runs alone whose key another rank owns)
+    if (n && c->cfg.world > 1) {
+        PhaseClock clk(c, &c->stats.ms_select);
+        E128 *lists[1] = {c->frag.p};
+        const uint64_t counts[1] = {n};
+        const int kinds[1] = {0};
+        if ((rc = route_sweep(c, 1, lists, counts, kinds, 2, &n_fr, &launches))) return rc;
+        if ((rc = sh.froute.reserve(n_fr + 1, false, s))) return rc;
+        if (n_fr) OGE_CUDA_TRY(cudaMemcpyAsync(sh.froute.p, sh.route.p, n_fr * sizeof(RouteEntry), cudaMemcpyDeviceToDevice, s));
+        OGE_CUDA_TRY(cudaStreamSynchronize(s));
+        clk.stop();
+    }
     c->stats.launches += launches;
     *pub_dev = sh.pub.p;
     *n_pub = n_list;
+    *froute_dev = sh.froute.p;
+    *n_froute = n_fr;
     sh.phase = 1;
     return OGE_OK;
 }
 
-int oge_gpu_shard_probe(oge_gpu_dedup_ctx *c, const void *pub_all_dev, uint64_t n_all, void **pub2_dev, uint64_t *n_pub2) {
+int oge_gpu_shard_probe(oge_gpu_dedup_ctx *c, const void *pub_all_dev, uint64_t n_all, const void *froute_all_dev, uint64_t n_fr_all,
+                        void **pub2_dev, uint64_t *n_pub2, void **proute_dev, uint64_t *n_proute) {
     int rc = need_phase(c, 1, "shard_probe");
     if (rc) return rc;
-    if (!pub2_dev || !n_pub2 || (n_all && !pub_all_dev)) return fail_msg(OGE_ERR_INVALID_ARG, "shard_probe: null argument");
-    cudaStream_t s = c->stream;
+    if (!pub2_dev || !n_pub2 || !proute_dev || !n_proute || (n_all && !pub_all_dev) || (n_fr_all && !froute_all_dev))
+        return fail_msg(OGE_ERR_INVALID_ARG, "shard_probe: null argument");
+    cudaStream_t s = c->stream, s2 = c->side_stream;
     ShardState &sh = c->sh;
-    uint64_t launches = 0, n2 = 0;
+    uint64_t launches = 0, n2 = 0, n_pr = 0;
+    const uint64_t n = c->n;
+
+    // ---- local couples of names published elsewhere are retracted and published (this reads the fragment
+    //      array, so it comes before the fragment sort starts moving it)
     if (sh.n_pe && n_all) {
         PhaseClock clk(c, &c->stats.ms_join);
         if ((rc = zero_counter(c, CNT_PUB))) return rc;
-        if ((rc = launch_sh_probe((const PubEntry *) pub_all_dev, n_all, shard_params(c), c->table.p, sh.n_slots, c->pair.p, c->pairf.p, sh.pub_list.p, s,
-                                  &launches)))
+        if ((rc = launch_sh_probe((const PubEntry *) pub_all_dev, n_all, shard_params(c), c->table.p, sh.n_slots, c->pair.p, c->pairf.p,
+                                  sh.pub_list.p, s, &launches)))
             return rc;
         if ((rc = read_counters(c))) return rc;
         n2 = c->h_counters[CNT_PUB];
@@ -228,135 +289,123 @@ int oge_gpu_shard_probe(oge_gpu_dedup_ctx *c, const void *pub_all_dev, uint64_t 
         if ((rc = launch_sh_gather(sh.pub_list.p, (uint32_t) n2, c->frag.p, c->hk.p, c->tag.p, sh.pub2.p, s, &launches))) return rc;
         clk.stop();
     }
+    // ---- side stream: the fragment ends are complete once the routed copies are in -> K3 + K4 on them,
+    //      concurrently with the pair routing, the second exchange and the replay on the main stream
+    sh.n_froute_all = n_fr_all;
+    sh.frag_busy = false;
+    if (n + n_fr_all) {
+        if ((rc = c->frag.reserve(n + n_fr_all, true, s))) return rc;
+        if ((rc = c->sortbuf.reserve(n + n_fr_all, false, s))) return rc;
+        if ((rc = sh.scratch2.reserve(sort_scratch_bytes(n + n_fr_all), false, s))) return rc;
+        if ((rc = sh.marks_frag.reserve(n_fr_all + 16, false, s))) return rc;
+        if (n == 0 && (rc = c->mate_of.reserve(1, false, s))) return rc;
+        if (n == 0 && (rc = c->dup.reserve(1, false, s))) return rc;
+        OGE_CUDA_TRY(cudaEventRecord(sh.ev_main, s));
+        OGE_CUDA_TRY(cudaStreamWaitEvent(s2, sh.ev_main, 0));
+        OGE_CUDA_TRY(cudaEventRecord(sh.ev_side[0], s2));
+        if (n_fr_all) {
+            OGE_CUDA_TRY(cudaMemsetAsync(c->frag.p + n, 0xFF, n_fr_all * sizeof(E128), s2));      // unused tail slots are dead entries
+            if ((rc = launch_sh_receive((const RouteEntry *) froute_all_dev, n_fr_all, shard_params(c), 1u, c->frag.p + n, (uint32_t) n_fr_all,
+                                        nullptr, 0, nullptr, 0, nullptr, nullptr, 0, s2, &launches)))
+                return rc;
+        }
+        sh_add_counter_kernel<<<1, 1, 0, s2>>>(c->counters.p + CNT_FRAG_VALID, (uint32_t) sh.n_frag, c->counters.p + CNT_FRAG_EXTRA, (uint32_t) n_fr_all);
+        PassTimer timer2{c->pass_ev + 48, 24, 0, 0};
+        E128 *sorted_frags = c->frag.p;
+        if ((rc = radix_sort_128(c->frag.p, c->sortbuf.p, n + n_fr_all, nullptr, c->kl.f_orient, c->kl.f_end, sh.scratch2.p, s2, &sorted_frags,
+                                 &launches, c->cfg.profile_events ? &timer2 : nullptr)))
+            return rc;
+        sh.side_pass_used = timer2.used;
+        sh.side_pass_bytes = timer2.bytes;
+        OGE_CUDA_TRY(cudaEventRecord(sh.ev_side[1], s2));
+        SelectParams sp;
+        sp.dup = c->dup.p; sp.mate_of = c->mate_of.p; sp.idx_base = c->cfg.index_base; sp.n_records = n;
+        sp.counters = c->counters.p; sp.kl = c->kl;
+        sp.fm = nullptr; sp.n_fm = 0; sp.foreign_marks = sh.marks_frag.p; sp.foreign_cap = (uint32_t) sh.marks_frag.cap;
+        sp.foreign_counter = c->counters.p + CNT_FOREIGN_MARKS_FRAG;
+        sp.split = sh.d_split.p; sp.world = c->cfg.world; sp.rank = c->cfg.rank;
+        sp.sorted = sorted_frags; sp.n_max = (uint32_t) (n + n_fr_all); sp.n_dev = c->counters.p + CNT_FRAG_VALID;
+        if ((rc = launch_select_frags(sp, s2, &launches))) return rc;
+        OGE_CUDA_TRY(cudaEventRecord(sh.ev_side[2], s2));
+        sh.frag_busy = true;
+    }
+
+    // ---- the remaining local couples whose key lies in another rank's range leave
+    if (c->cfg.world > 1 && (sh.n_pairs || sh.n_far)) {
+        PhaseClock clk(c, &c->stats.ms_select);
+        E128 *lists[2] = {c->pair.p, c->pairf.p};
+        const uint64_t counts[2] = {sh.n_pairs, sh.n_far};
+        const int kinds[2] = {1, 2};
+        if ((rc = route_sweep(c, 2, lists, counts, kinds, 0, &n_pr, &launches))) return rc;
+        sh.n_retracted += n_pr ? c->h_counters[CNT_SCRATCH0] : 0;      // dead pair entries, whatever the reason
+        sh.n_far_dead += n_pr ? c->h_counters[CNT_SCRATCH1] : 0;
+        clk.stop();
+    }
     c->stats.launches += launches;
     *pub2_dev = sh.pub2.p;
     *n_pub2 = n2;
+    *proute_dev = sh.route.p;
+    *n_proute = n_pr;
     sh.phase = 2;
     return OGE_OK;
 }
 
-int oge_gpu_shard_replay(oge_gpu_dedup_ctx *c, const void *w_dev, uint64_t n_w) {
-    int rc = need_phase(c, 2, "shard_replay");
+int oge_gpu_shard_finish(oge_gpu_dedup_ctx *c, const void *w_dev, uint64_t n_w, const void *proute_all_dev, uint64_t n_all, void **marks_dev,
+                         uint64_t *n_marks, void **marks_frag_dev, uint64_t *n_marks_frag) {
+    int rc = need_phase(c, 2, "shard_finish");
     if (rc) return rc;
-    if (n_w && !w_dev) return fail_msg(OGE_ERR_INVALID_ARG, "shard_replay: null argument");
-    if (n_w >= (1ull << 30)) return fail_msg(OGE_ERR_TOO_LARGE, "shard_replay: published set too large");
-    cudaStream_t s = c->stream;
-    ShardState &sh = c->sh;
-    uint64_t launches = 0;
-    sh.n_w = n_w;
-    if (n_w) {
-        PhaseClock clk(c, &c->stats.ms_join);
-        const uint64_t pair_cap = sh.n_pairs + n_w / 2 + 16, far_cap = sh.n_far + n_w / 2 + 16;
-        if ((rc = c->pair.reserve(pair_cap, true, s))) return rc;
-        if ((rc = c->pair2.reserve(pair_cap, false, s))) return rc;
-        if ((rc = c->pairf.reserve(far_cap, true, s))) return rc;
-        if ((rc = c->pairf2.reserve(far_cap, false, s))) return rc;
-        if ((rc = sh.fm.reserve(n_w / 2 + 16, false, s))) return rc;
-        if ((rc = sh.w_sort.reserve(n_w, false, s))) return rc;
-        if ((rc = sh.w_sort2.reserve(n_w, false, s))) return rc;
-        if ((rc = c->cplx_state.reserve(n_w, false, s))) return rc;
-        if ((rc = c->scratch.reserve(std::max(sort_scratch_bytes(n_w), c->scratch.cap), true, s))) return rc;
-        if (c->n == 0 && (rc = c->mate_of.reserve(1, false, s))) return rc;
-        if ((rc = launch_sh_wbuild((const PubEntry *) w_dev, (uint32_t) n_w, c->kl, sh.w_sort.p, s, &launches))) return rc;
-        E128 *sorted = nullptr;
-        if ((rc = radix_sort_128(sh.w_sort.p, sh.w_sort2.p, n_w, nullptr, 32, 96, c->scratch.p, s, &sorted, &launches))) return rc;
-        if ((rc = launch_sh_replay(sorted, (uint32_t) n_w, (const PubEntry *) w_dev, c->cplx_state.p, shard_params(c), c->pair.p,
-                                   (uint32_t) c->pair.cap, c->pairf.p, (uint32_t) c->pairf.cap, c->mate_of.p, sh.fm.p, (uint32_t) sh.fm.cap, rg_table(c), s, &launches)))
-            return rc;
-        if ((rc = read_counters(c))) return rc;
-        sh.n_pairs = c->h_counters[CNT_PAIRS];
-        sh.n_far = c->h_counters[CNT_PAIRS_FAR];
-        sh.n_fm = c->h_counters[CNT_FM];
-        clk.stop();
-    }
-    c->stats.launches += launches;
-    sh.phase = 3;
-    return OGE_OK;
-}
-
-int oge_gpu_shard_route(oge_gpu_dedup_ctx *c, void **route_dev, uint64_t *n_route) {
-    int rc = need_phase(c, 3, "shard_route");
-    if (rc) return rc;
-    if (!route_dev || !n_route) return fail_msg(OGE_ERR_INVALID_ARG, "shard_route: null argument");
-    cudaStream_t s = c->stream;
-    ShardState &sh = c->sh;
-    uint64_t launches = 0, n_out = 0;
-    sh.n_frag_total = c->n;
-    if (c->cfg.world > 1 && (c->n || sh.n_pairs || sh.n_far)) {
-        PhaseClock clk(c, &c->stats.ms_select);
-        const ShardParams S = shard_params(c);
-        // one sweep over the entries into a buffer sized for the usual case (boundary entries are a tiny
-        // fraction); entries that found no room stay in place and a second sweep collects them
-        {
-            const char *e = getenv("OGE_ROUTE_CAP");      // test hook: force the second sweep
-            const uint64_t want = e && *e ? (uint64_t) atoll(e) : std::max<uint64_t>(1u << 16, (c->n + sh.n_pairs + sh.n_far) / 64);
-            if (e && *e) sh.route.release();
-            if ((rc = sh.route.reserve(std::max<uint64_t>(want, 1), false, s))) return rc;
-        }
-        if ((rc = zero_counter(c, CNT_ROUTE)) || (rc = zero_counter(c, CNT_SCRATCH0)) || (rc = zero_counter(c, CNT_SCRATCH1))) return rc;
-        for (int sweep = 0; sweep < 2; sweep++) {
-            const uint32_t cap = (uint32_t) sh.route.cap;
-            if ((rc = launch_sh_route(c->frag.p, c->n, 0, S, c->mate_of.p, sh.fm.p, 0, sh.route.p, cap, 0, s, &launches))) return rc;
-            if ((rc = launch_sh_route(c->pair.p, sh.n_pairs, 1, S, c->mate_of.p, sh.fm.p, 0, sh.route.p, cap, 0, s, &launches))) return rc;
-            if ((rc = launch_sh_route(c->pairf.p, sh.n_far, 2, S, c->mate_of.p, sh.fm.p, 0, sh.route.p, cap, 0, s, &launches))) return rc;
-            if ((rc = read_counters(c))) return rc;
-            n_out = c->h_counters[CNT_ROUTE];
-            if (n_out <= cap) break;
-            if (sweep == 1) return fail_msg(OGE_ERR_STATE, "shard_route: entry count changed between sweeps");
-            if ((rc = sh.route.reserve(n_out, true, s))) return rc;
-            OGE_CUDA_TRY(cudaMemcpyAsync(c->counters.p + CNT_ROUTE, &cap, 4, cudaMemcpyHostToDevice, s));      // continue behind what is stored
-            OGE_CUDA_TRY(cudaStreamSynchronize(s));
-        }
-        const uint64_t routed_near = n_out ? c->h_counters[CNT_SCRATCH0] : 0, routed_far = n_out ? c->h_counters[CNT_SCRATCH1] : 0;
-        sh.n_retracted += routed_near;                  // dead pair entries, whatever the reason
-        sh.n_far_dead += routed_far;
-        sh.n_frag -= n_out - routed_near - routed_far;
-        clk.stop();
-    }
-    c->stats.launches += launches;
-    *route_dev = sh.route.p;
-    *n_route = n_out;
-    sh.phase = 4;
-    return OGE_OK;
-}
-
-int oge_gpu_shard_finish(oge_gpu_dedup_ctx *c, const void *route_all_dev, uint64_t n_all, void **marks_dev, uint64_t *n_marks) {
-    int rc = need_phase(c, 4, "shard_finish");
-    if (rc) return rc;
-    if (!marks_dev || !n_marks || (n_all && !route_all_dev)) return fail_msg(OGE_ERR_INVALID_ARG, "shard_finish: null argument");
+    if (!marks_dev || !n_marks || !marks_frag_dev || !n_marks_frag || (n_w && !w_dev) || (n_all && !proute_all_dev))
+        return fail_msg(OGE_ERR_INVALID_ARG, "shard_finish: null argument");
+    if (n_w >= (1ull << 30)) return fail_msg(OGE_ERR_TOO_LARGE, "shard_finish: published set too large");
     cudaStream_t s = c->stream;
     ShardState &sh = c->sh;
     uint64_t launches = 0;
     const uint64_t n = c->n;
     PassTimer timer{c->pass_ev, 48, 0, 0};
     PassTimer *tp = c->cfg.profile_events ? &timer : nullptr;
-    uint64_t extra = 0;
-    if (n_all) {
-        PhaseClock clk(c, &c->stats.ms_select);
-        if ((rc = c->frag.reserve(n + n_all, true, s))) return rc;
-        if ((rc = c->sortbuf.reserve(n + n_all, false, s))) return rc;
-        if ((rc = c->pair.reserve(sh.n_pairs + n_all, true, s))) return rc;
-        if ((rc = c->pair2.reserve(sh.n_pairs + n_all, false, s))) return rc;
-        if ((rc = c->pairf.reserve(sh.n_far + n_all, true, s))) return rc;
-        if ((rc = c->pairf2.reserve(sh.n_far + n_all, false, s))) return rc;
-        if ((rc = sh.fm.reserve(sh.n_fm + n_all, true, s))) return rc;
-        if ((rc = c->scratch.reserve(std::max(sort_scratch_bytes(std::max(std::max(n + n_all, sh.n_pairs + n_all), sh.n_far + n_all)), c->scratch.cap), true, s))) return rc;
+    sh.n_w = n_w;
+
+    // ---- replay of the published set: the pairs whose key this rank owns
+    if (n_w || n_all) {
+        const uint64_t pair_cap = sh.n_pairs + n_w / 2 + n_all + 16, far_cap = sh.n_far + n_w / 2 + n_all + 16;
+        if ((rc = c->pair.reserve(pair_cap, true, s))) return rc;
+        if ((rc = c->pair2.reserve(pair_cap, false, s))) return rc;
+        if ((rc = c->pairf.reserve(far_cap, true, s))) return rc;
+        if ((rc = c->pairf2.reserve(far_cap, false, s))) return rc;
+        if ((rc = sh.fm.reserve(n_w / 2 + n_all + 16, false, s))) return rc;
+        if ((rc = c->scratch.reserve(std::max(sort_scratch_bytes(std::max(std::max(n_w, pair_cap), far_cap)), c->scratch.cap), true, s))) return rc;
         if (n == 0 && (rc = c->mate_of.reserve(1, false, s))) return rc;
-        if ((rc = zero_counter(c, CNT_FRAG_EXTRA))) return rc;
-        if ((rc = launch_sh_receive((const RouteEntry *) route_all_dev, n_all, shard_params(c), c->frag.p + n, (uint32_t) n_all, c->pair.p,
-                                    (uint32_t) c->pair.cap, c->pairf.p, (uint32_t) c->pairf.cap, c->mate_of.p, sh.fm.p, (uint32_t) sh.fm.cap, s, &launches)))
+    }
+    if (n_w) {
+        PhaseClock clk(c, &c->stats.ms_join);
+        if ((rc = sh.w_sort.reserve(n_w, false, s))) return rc;
+        if ((rc = sh.w_sort2.reserve(n_w, false, s))) return rc;
+        if ((rc = c->cplx_state.reserve(n_w, false, s))) return rc;
+        if ((rc = launch_sh_wbuild((const PubEntry *) w_dev, (uint32_t) n_w, c->kl, sh.w_sort.p, s, &launches))) return rc;
+        E128 *sorted = nullptr;
+        if ((rc = radix_sort_128(sh.w_sort.p, sh.w_sort2.p, n_w, nullptr, 32, 96, c->scratch.p, s, &sorted, &launches))) return rc;
+        if ((rc = launch_sh_replay(sorted, (uint32_t) n_w, (const PubEntry *) w_dev, c->cplx_state.p, shard_params(c), c->pair.p,
+                                   (uint32_t) c->pair.cap, c->pairf.p, (uint32_t) c->pairf.cap, c->mate_of.p, sh.fm.p, (uint32_t) sh.fm.cap,
+                                   rg_table(c), s, &launches)))
             return rc;
-        if ((rc = read_counters(c))) return rc;
-        extra = c->h_counters[CNT_FRAG_EXTRA];
-        sh.n_pairs = c->h_counters[CNT_PAIRS];
-        sh.n_far = c->h_counters[CNT_PAIRS_FAR];
-        sh.n_fm = c->h_counters[CNT_FM];
         clk.stop();
     }
+    if (n_all) {
+        PhaseClock clk(c, &c->stats.ms_select);
+        if ((rc = launch_sh_receive((const RouteEntry *) proute_all_dev, n_all, shard_params(c), 6u, nullptr, 0, c->pair.p, (uint32_t) c->pair.cap,
+                                    c->pairf.p, (uint32_t) c->pairf.cap, c->mate_of.p, sh.fm.p, (uint32_t) sh.fm.cap, s, &launches)))
+            return rc;
+        clk.stop();
+    }
+    if ((rc = read_counters(c))) return rc;
+    sh.n_pairs = c->h_counters[CNT_PAIRS];
+    sh.n_far = c->h_counters[CNT_PAIRS_FAR];
+    sh.n_fm = c->h_counters[CNT_FM];
+    if (sh.n_pairs > c->pair.cap || sh.n_far > c->pairf.cap || sh.n_fm > sh.fm.cap)
+        return fail_msg(OGE_ERR_STATE, "shard_finish: pair lists overran their buffers");
     if (sh.n_fm > 1) {      // foreign mates sorted by idx1 for the binary search in K4
         PhaseClock clk(c, &c->stats.ms_select);
         if ((rc = sh.fm_sort.reserve(2 * sh.n_fm, false, s))) return rc;
-        if ((rc = c->scratch.reserve(std::max(sort_scratch_bytes(sh.n_fm), c->scratch.cap), true, s))) return rc;
         if ((rc = launch_sh_fm_pack(sh.fm.p, (uint32_t) sh.n_fm, sh.fm_sort.p, s, &launches))) return rc;
         E128 *sorted = nullptr;
         if ((rc = radix_sort_128(sh.fm_sort.p, sh.fm_sort.p + sh.n_fm, sh.n_fm, nullptr, 32, 64, c->scratch.p, s, &sorted, &launches))) return rc;
@@ -365,16 +414,16 @@ int oge_gpu_shard_finish(oge_gpu_dedup_ctx *c, const void *route_all_dev, uint64
     }
     // marks on other ranks' records can only come from entries that crossed ranks: pairs formed by the
     // replay (at most one per two published entries) and routed entries
-    if ((rc = sh.marks.reserve(sh.n_w + 2 * n_all + 1024, false, s))) return rc;
-    if ((rc = zero_counter(c, CNT_FOREIGN_MARKS))) return rc;
+    if ((rc = sh.marks.reserve(n_w + 2 * n_all + 1024, false, s))) return rc;
 
     SelectParams sp;
     sp.dup = c->dup.p; sp.mate_of = c->mate_of.p; sp.idx_base = c->cfg.index_base; sp.n_records = n;
     sp.counters = c->counters.p; sp.kl = c->kl; sp.n_dev = nullptr;
     sp.fm = sh.fm.p; sp.n_fm = (uint32_t) sh.n_fm; sp.foreign_marks = sh.marks.p; sp.foreign_cap = (uint32_t) sh.marks.cap;
-    const uint64_t n_pairs = sh.n_pairs, n_dead = sh.n_retracted;
+    sp.foreign_counter = c->counters.p + CNT_FOREIGN_MARKS;
+    sp.split = sh.d_split.p; sp.world = c->cfg.world; sp.rank = c->cfg.rank;
     for (int far = 0; far < 2; far++) {      // near pairs (short key), then far pairs
-        const uint64_t cnt = far ? sh.n_far : n_pairs, dead = far ? sh.n_far_dead : n_dead;
+        const uint64_t cnt = far ? sh.n_far : sh.n_pairs, dead = far ? sh.n_far_dead : sh.n_retracted;
         if (!cnt) continue;
         E128 *a = far ? c->pairf.p : c->pair.p, *b = far ? c->pairf2.p : c->pair2.p, *sorted = a;
         {
@@ -390,33 +439,35 @@ int oge_gpu_shard_finish(oge_gpu_dedup_ctx *c, const void *route_all_dev, uint64
             clk.stop();
         }
     }
-    const uint64_t n_frag_valid = sh.n_frag + extra;
-    if (n_frag_valid) {
-        E128 *sorted_frags = c->frag.p;
-        {
-            PhaseClock clk(c, &c->stats.ms_sort_frag);
-            if ((rc = radix_sort_128(c->frag.p, c->sortbuf.p, n + extra, nullptr, c->kl.f_orient, c->kl.f_end, c->scratch.p, s, &sorted_frags,
-                                     &launches, tp)))
-                return rc;
-            clk.stop();
-        }
-        PhaseClock clk(c, &c->stats.ms_select);
-        sp.sorted = sorted_frags; sp.n_max = (uint32_t) n_frag_valid;
-        if ((rc = launch_select_frags(sp, s, &launches))) return rc;
+    // ---- join the side stream: the fragment verdicts
+    uint64_t extra = 0;
+    if (sh.frag_busy) {
+        PhaseClock clk(c, nullptr);      // whatever of the fragment work the pair work did not hide
+        OGE_CUDA_TRY(cudaStreamWaitEvent(s, sh.ev_side[2], 0));
         clk.stop();
+        sh.frag_busy = false;
     }
     if ((rc = read_counters(c))) return rc;
-    const uint64_t n_foreign = c->h_counters[CNT_FOREIGN_MARKS];
-    if (n_foreign > sh.marks.cap) return fail_msg(OGE_ERR_STATE, "shard_finish: %llu marks for other ranks, room for %llu",
-                                                  (unsigned long long) n_foreign, (unsigned long long) sh.marks.cap);
+    if (sh.n_froute_all || n) {
+        extra = std::min<uint64_t>(c->h_counters[CNT_FRAG_EXTRA], sh.n_froute_all);
+        c->stats.ms_sort_frag = ms_between(sh.ev_side[0], sh.ev_side[1]);
+        c->stats.ms_select += ms_between(sh.ev_side[1], sh.ev_side[2]);
+    }
+    const uint64_t n_foreign = c->h_counters[CNT_FOREIGN_MARKS], n_foreign_frag = c->h_counters[CNT_FOREIGN_MARKS_FRAG];
+    if (n_foreign > sh.marks.cap || n_foreign_frag > sh.marks_frag.cap)
+        return fail_msg(OGE_ERR_STATE, "shard_finish: %llu + %llu marks for other ranks, room for %llu + %llu", (unsigned long long) n_foreign,
+                        (unsigned long long) n_foreign_frag, (unsigned long long) sh.marks.cap, (unsigned long long) sh.marks_frag.cap);
     c->stats.launches += launches;
-    c->stats.n_frag_entries = n_frag_valid;
-    c->stats.n_pair_entries = n_pairs - n_dead + sh.n_far - sh.n_far_dead;
+    c->stats.n_frag_entries = sh.n_frag + extra;
+    c->stats.n_pair_entries = sh.n_pairs - sh.n_retracted + sh.n_far - sh.n_far_dead;
     for (int i = 0; i < timer.used; i++) c->stats.ms_sort_pass_kernels += ms_between(c->pass_ev[2 * i], c->pass_ev[2 * i + 1]);
-    c->stats.sort_pass_launches = timer.used;
-    c->stats.sort_pass_bytes = timer.bytes;
+    for (int i = 0; i < sh.side_pass_used; i++) c->stats.ms_sort_pass_kernels += ms_between(c->pass_ev[48 + 2 * i], c->pass_ev[48 + 2 * i + 1]);
+    c->stats.sort_pass_launches = timer.used + sh.side_pass_used;
+    c->stats.sort_pass_bytes = timer.bytes + sh.side_pass_bytes;
     *marks_dev = sh.marks.p;
     *n_marks = n_foreign;
+    *marks_frag_dev = sh.marks_frag.p;
+    *n_marks_frag = n_foreign_frag;
     sh.phase = 5;
     return OGE_OK;
 }

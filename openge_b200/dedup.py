@@ -57,7 +57,7 @@ EXPORTS = ["oge_gpu_dedup_create", "oge_gpu_dedup_destroy", "oge_gpu_dedup_set_r
            "oge_gpu_dedup_device_ptrs", "oge_gpu_host_alloc", "oge_gpu_host_free", "oge_gpu_device_count",
            "oge_gpu_last_error", "oge_gpu_abi_version", "oge_gpu_debug_sort128", "oge_gpu_debug_sort_bench",
            "oge_gpu_set_sort_variant", "oge_gpu_shard_setup", "oge_gpu_shard_begin", "oge_gpu_shard_probe",
-           "oge_gpu_shard_replay", "oge_gpu_shard_route", "oge_gpu_shard_finish", "oge_gpu_shard_apply"]
+           "oge_gpu_shard_finish", "oge_gpu_shard_apply"]
 
 
 class DedupError(RuntimeError):
@@ -101,11 +101,9 @@ def lib():
                                                C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.oge_gpu_set_sort_variant.argtypes = [C.c_int]
         L.oge_gpu_shard_setup.argtypes = [vp, u64, vp, vp, vp]
-        L.oge_gpu_shard_begin.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
-        L.oge_gpu_shard_probe.argtypes = [vp, vp, u64, C.POINTER(vp), C.POINTER(u64)]
-        L.oge_gpu_shard_replay.argtypes = [vp, vp, u64]
-        L.oge_gpu_shard_route.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
-        L.oge_gpu_shard_finish.argtypes = [vp, vp, u64, C.POINTER(vp), C.POINTER(u64)]
+        L.oge_gpu_shard_begin.argtypes = [vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(vp), C.POINTER(u64)]
+        L.oge_gpu_shard_probe.argtypes = [vp, vp, u64, vp, u64, C.POINTER(vp), C.POINTER(u64), C.POINTER(vp), C.POINTER(u64)]
+        L.oge_gpu_shard_finish.argtypes = [vp, vp, u64, vp, u64, C.POINTER(vp), C.POINTER(u64), C.POINTER(vp), C.POINTER(u64)]
         L.oge_gpu_shard_apply.argtypes = [vp, vp, u64]
         for name in EXPORTS:
             getattr(L, name)
@@ -267,25 +265,22 @@ class DedupContext:
         p = np.ascontiguousarray(split_pos if len(split_pos) else [0], dtype=np.int32)
         _check(lib().oge_gpu_shard_setup(self._h, int(global_n), b.ctypes.data, r.ctypes.data, p.ctypes.data))
 
-    def _out_call(self, fn, *args):
-        ptr, cnt = C.c_void_p(), C.c_uint64()
-        _check(fn(self._h, *args, C.byref(ptr), C.byref(cnt)))
-        return ptr.value or 0, int(cnt.value)
+    def _out2_call(self, fn, *args):
+        p1, c1, p2, c2 = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_uint64()
+        _check(fn(self._h, *args, C.byref(p1), C.byref(c1), C.byref(p2), C.byref(c2)))
+        return (p1.value or 0, int(c1.value)), (p2.value or 0, int(c2.value))
 
     def shard_begin(self):
-        return self._out_call(lib().oge_gpu_shard_begin)
+        """-> (published round 1, routed fragment ends): each a (device pointer, item count)."""
+        return self._out2_call(lib().oge_gpu_shard_begin)
 
-    def shard_probe(self, ptr, n):
-        return self._out_call(lib().oge_gpu_shard_probe, ptr, n)
+    def shard_probe(self, pub_ptr, n_pub, fr_ptr, n_fr):
+        """-> (published round 2, routed pair ends)"""
+        return self._out2_call(lib().oge_gpu_shard_probe, pub_ptr, n_pub, fr_ptr, n_fr)
 
-    def shard_replay(self, ptr, n):
-        _check(lib().oge_gpu_shard_replay(self._h, ptr, n))
-
-    def shard_route(self):
-        return self._out_call(lib().oge_gpu_shard_route)
-
-    def shard_finish(self, ptr, n):
-        return self._out_call(lib().oge_gpu_shard_finish, ptr, n)
+    def shard_finish(self, w_ptr, n_w, pr_ptr, n_pr):
+        """-> (marks from pairs, marks from fragments)"""
+        return self._out2_call(lib().oge_gpu_shard_finish, w_ptr, n_w, pr_ptr, n_pr)
 
     def shard_apply(self, ptr, n):
         _check(lib().oge_gpu_shard_apply(self._h, ptr, n))

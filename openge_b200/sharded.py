@@ -1,14 +1,17 @@
 """Range-sharded dedup over several GPUs: host orchestration.
 
 One coordinate-sorted file is cut into contiguous record ranges, one per rank.  Each rank keeps its
-records, end entries, sorts and selects on its own GPU; four small lists cross ranks per run, each
-delivered to every rank by an all-to-all (NCCL on GPUs, gloo in the CPU tests):
+records, end entries, sorts and selects on its own GPU; small lists cross ranks in three exchanges per
+run, each delivering every rank's lists to every rank with an all-to-all (NCCL on GPUs, gloo in the
+CPU tests):
 
     begin   ->  published entries, round 1   (records whose RG:name key was not seen exactly twice locally)
+                + copies of the fragment ends whose key lies in another rank's coordinate range
     probe   ->  published entries, round 2   (local couples of names published elsewhere, retracted)
-    replay      every rank replays the published set in global file order, keeps the pairs it owns
-    route   ->  end entries whose key lies in another rank's coordinate range
-    finish  ->  marks on records of other ranks
+                + pair ends whose key lies in another rank's range; the fragment sort/select start on a
+                side stream and overlap the second exchange
+    finish  ->  every rank replays the published set in global file order and keeps the pairs it owns;
+                pair sort/select; marks on records of other ranks
     apply       flag write
 
 The result equals the reference's single-stream `openge dedup --nosplit -v`, not its own
@@ -69,11 +72,9 @@ class ShardEngine:
     """Per-rank device work between the exchanges.  Lists are 1-D uint8 torch tensors on `device`."""
     device = "cpu"
 
-    def begin(self): raise NotImplementedError
-    def probe(self, pub_all): raise NotImplementedError
-    def replay(self, w): raise NotImplementedError
-    def route(self): raise NotImplementedError
-    def finish(self, route_all): raise NotImplementedError
+    def begin(self): raise NotImplementedError                          # -> (pub, frag_route)
+    def probe(self, pub_all, frag_route_all): raise NotImplementedError  # -> (pub2, pair_route)
+    def finish(self, pub_both, pair_route_all): raise NotImplementedError  # -> (marks, marks_frag)
     def apply(self, marks_all): raise NotImplementedError
     def flags(self): raise NotImplementedError
 
@@ -126,19 +127,16 @@ class CudaShardEngine(ShardEngine):
         return (t.data_ptr() if t.numel() else None), t.numel() // item
 
     def begin(self):
-        return self._take(*self.ctx.shard_begin(), PUB_BYTES)
+        pub, fr = self.ctx.shard_begin()
+        return self._take(*pub, PUB_BYTES), self._take(*fr, ROUTE_BYTES)
 
-    def probe(self, pub_all):
-        return self._take(*self.ctx.shard_probe(*self._give(pub_all, PUB_BYTES)), PUB_BYTES)
+    def probe(self, pub_all, frag_route_all):
+        pub2, pr = self.ctx.shard_probe(*self._give(pub_all, PUB_BYTES), *self._give(frag_route_all, ROUTE_BYTES))
+        return self._take(*pub2, PUB_BYTES), self._take(*pr, ROUTE_BYTES)
 
-    def replay(self, w):
-        self.ctx.shard_replay(*self._give(w, PUB_BYTES))
-
-    def route(self):
-        return self._take(*self.ctx.shard_route(), ROUTE_BYTES)
-
-    def finish(self, route_all):
-        return self._take(*self.ctx.shard_finish(*self._give(route_all, ROUTE_BYTES)), MARK_BYTES)
+    def finish(self, pub_both, pair_route_all):
+        m, mf = self.ctx.shard_finish(*self._give(pub_both, PUB_BYTES), *self._give(pair_route_all, ROUTE_BYTES))
+        return self._take(*m, MARK_BYTES), self._take(*mf, MARK_BYTES)
 
     def apply(self, marks_all):
         self.ctx.shard_apply(*self._give(marks_all, MARK_BYTES))
@@ -156,21 +154,22 @@ class CudaShardEngine(ShardEngine):
 # --------------------------------------------------------------------------------------- exchanges
 class LocalExchange:
     """All ranks live in this process (several contexts on one GPU, or the numpy model): every
-    rank's list is simply concatenated in rank order."""
+    rank's lists are simply concatenated in rank order.  `outs` = one tuple of lists per rank."""
 
     def __init__(self):
         self.bytes_moved = 0
 
-    def __call__(self, lists):
+    def __call__(self, outs):
         import torch
-        self.bytes_moved += sum(int(t.numel()) for t in lists) * max(0, len(lists) - 1)
-        return torch.cat(lists) if len(lists) > 1 else lists[0]
+        k = len(outs[0])
+        self.bytes_moved += sum(int(t.numel()) for o in outs for t in o) * max(0, len(outs) - 1)
+        return tuple(torch.cat([o[j] for o in outs]) if len(outs) > 1 else outs[0][j] for j in range(k))
 
 
 class AllToAllExchange:
-    """One rank per process under torch.distributed.  Every rank's list goes to every rank with
-    all_to_all_single (the path's only collective): first the byte counts, then the payload with
-    uneven splits.  Returns the lists concatenated in rank order."""
+    """One rank per process under torch.distributed.  Every rank's lists go to every rank with
+    all_to_all_single (the path's only collective): first the byte counts of the lists, then one payload
+    with uneven splits.  Returns, per list, the ranks' contributions concatenated in rank order."""
 
     def __init__(self, dist, device, timed=False):
         import torch
@@ -180,43 +179,54 @@ class AllToAllExchange:
         self.ms = 0.0
         self.timed = timed and str(device).startswith("cuda")
 
-    def __call__(self, lists):
+    def __call__(self, outs):
         torch, dist, W = self.torch, self.dist, self.world
-        (mine,) = lists
+        (mine,) = outs
+        k = len(mine)
         if self.timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        n_mine = torch.full((W,), mine.numel(), dtype=torch.int64, device=self.device)
-        n_all = torch.empty(W, dtype=torch.int64, device=self.device)
-        dist.all_to_all_single(n_all, n_mine)
-        counts = [int(x) for x in n_all.tolist()]
-        out = torch.empty(sum(counts), dtype=torch.uint8, device=self.device)
-        if sum(counts) or mine.numel():
-            send = mine.repeat(W) if mine.numel() else mine
-            dist.all_to_all_single(out, send, output_split_sizes=counts, input_split_sizes=[int(mine.numel())] * W)
+        sizes = torch.tensor([int(t.numel()) for t in mine] * W, dtype=torch.int64, device=self.device)
+        sizes_all = torch.empty(W * k, dtype=torch.int64, device=self.device)
+        dist.all_to_all_single(sizes_all, sizes)
+        per = sizes_all.view(W, k).tolist()                      # per[r][j] = bytes of rank r's list j
+        recv = [sum(p) for p in per]
+        payload = torch.cat(list(mine)) if k > 1 else mine[0]
+        out = torch.empty(sum(recv), dtype=torch.uint8, device=self.device)
+        if sum(recv) or payload.numel():
+            send = payload.repeat(W) if payload.numel() else payload
+            dist.all_to_all_single(out, send, output_split_sizes=recv, input_split_sizes=[int(payload.numel())] * W)
+        res, starts, pos = [], [], 0
+        for r in range(W):
+            starts.append(pos)
+            pos += recv[r]
+        for j in range(k):
+            parts = []
+            for r in range(W):
+                o = starts[r] + sum(per[r][:j])
+                parts.append(out[o: o + per[r][j]])
+            res.append(torch.cat(parts) if W > 1 else parts[0])
         if self.timed:
             e1.record()
             e1.synchronize()
             self.ms += e0.elapsed_time(e1)
-        self.bytes_moved += int(mine.numel()) * (W - 1)
-        return out
+        self.bytes_moved += int(payload.numel()) * (W - 1)
+        return tuple(res)
 
 
 # --------------------------------------------------------------------------------------- the protocol
 def run_phases(engines, exchange):
     """Drive one sharded run over the local `engines` (one per process under torch.distributed, or
-    all ranks in-process).  Afterwards every engine's flags() are final."""
+    all ranks in-process): three exchanges.  Afterwards every engine's flags() are final."""
     import torch
-    pub_all = exchange([e.begin() for e in engines])
-    pub2_all = exchange([e.probe(pub_all) for e in engines])
+    pub_all, frag_route_all = exchange([e.begin() for e in engines])
+    pub2_all, pair_route_all = exchange([e.probe(pub_all, frag_route_all) for e in engines])
     w = torch.cat([pub_all, pub2_all]) if pub2_all.numel() else pub_all
-    for e in engines:
-        e.replay(w)
-    route_all = exchange([e.route() for e in engines])
-    marks_all = exchange([e.finish(route_all) for e in engines])
+    marks_a, marks_b = exchange([e.finish(w, pair_route_all) for e in engines])
+    marks_all = torch.cat([marks_a, marks_b]) if marks_b.numel() else marks_a
     for e in engines:
         e.apply(marks_all)
-    return {"published": int(w.numel()) // PUB_BYTES, "routed": int(route_all.numel()) // ROUTE_BYTES,
+    return {"published": int(w.numel()) // PUB_BYTES, "routed": (int(frag_route_all.numel()) + int(pair_route_all.numel())) // ROUTE_BYTES,
             "marks": int(marks_all.numel()) // MARK_BYTES}
 
 
@@ -299,11 +309,18 @@ def bench(args, rank, world, local_rank, rec, offs, text, contigs, metric, workl
     eng = CudaShardEngine(rec, offs, text, contigs, plan, rank, device=local_rank, pinned_ptr=rec.ctypes.data, profile_events=True)
     ex = AllToAllExchange(dist, dev, timed=True)
 
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
     def step():
+        # every phase ends with a host-side sync on the library's streams, so events on torch's stream
+        # around the whole step see all of it: device phases, exchanges, and whatever overlaps them
         ex.ms = 0.0
+        e0.record()
         info = run_phases([eng], ex)
+        e1.record()
+        e1.synchronize()
         st = eng.stats()
-        return st["ms_total"] + ex.ms, st, info, ex.ms
+        return e0.elapsed_time(e1), st, info, ex.ms
 
     for _ in range(args.warmup):
         step()
@@ -326,7 +343,7 @@ def bench(args, rank, world, local_rank, rec, offs, text, contigs, metric, workl
     wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     clocks = sampler.stop()
 
-    # max over ranks of the device-timed step (phases on the library stream + exchanges on torch's)
+    # max over ranks of the event-timed step
     t = torch.tensor([float(np.mean(ms)), ex_ms / args.steps, float(st["n_duplicates"]), float(n), wall_ms], dtype=torch.float64, device=dev)
     mx = t.clone()
     dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -364,7 +381,9 @@ def bench(args, rank, world, local_rank, rec, offs, text, contigs, metric, workl
             "config": {"workload": "%s x %d ranks: every rank holds one coordinate range (a copy of the contig set) of a "
                                    "%d-read file; 0.5%% of the pairs have their mates on two different ranks" % (workload_name, world, total_reads),
                        "reads": total_reads, "reads_rank0": n, "l2": "inputs larger than L2",
-                       "wall_ms_per_step": float(mx[4]), "exchange_ms_per_step": float(mx[1]), "duplicates_flagged": total_dups,
+                       "wall_ms_per_step": float(mx[4]), "exchange_ms_per_step": float(mx[1]), "device_phase_ms_rank0": st["ms_total"],
+                       "timing": "CUDA events around each step (phases sync the library streams before returning), max over ranks",
+                       "duplicates_flagged": total_dups,
                        "published_entries": info["published"], "routed_entries": info["routed"], "marks_exchanged": info["marks"],
                        "stage_ms_rank0": {k: st[k] for k in ("ms_endbuild", "ms_join", "ms_sort_pair", "ms_sort_frag", "ms_select", "ms_flags")},
                        "parallelism": "range-sharded x%d, all-to-all of small lists" % world},

@@ -99,6 +99,11 @@ class ModelShardEngine(ShardEngine):
         score = np.array([(int(first["score"]) + int(second["score"])) & 0xFFFF], dtype=np.uint16).view(np.int16)[0]
         return (1, first["lib"], a["ref"], a["coord"], orient, b["ref"], b["coord"], score, a["gidx"], b["gidx"], 1)
 
+    def _frag(self, i):
+        e = self.ends[i]
+        return (0, e["lib"], e["ref"], e["coord"], int(e["orientation"]), -1, -1, e["score"], self.base + i, -1,
+                1 if e["read2Sequence"] != -1 else 0)
+
     def begin(self):
         by_key = {}
         for i in range(self.n):
@@ -111,9 +116,12 @@ class ModelShardEngine(ShardEngine):
             else:
                 pub += ids
         self.pairs = []      # ROUTE-shaped tuples owned (so far) by this rank
-        return _to_t(np.array([self._pub(i) for i in pub], dtype=PUB))
+        # copies of the fragment ends another rank owns leave; the originals stay and are skipped at selection
+        self.frags = [self._frag(i) for i in range(self.n) if self.ends[i]["eligible"]]
+        out = [f for f in self.frags if self.owner(int(f[2]), int(f[3])) != self.rank]
+        return _to_t(np.array([self._pub(i) for i in pub], dtype=PUB)), _to_t(np.array(out, dtype=ROUTE))
 
-    def probe(self, pub_all):
+    def probe(self, pub_all, frag_route_all):
         pa = _from_t(pub_all, PUB)
         out = []
         for e in pa:
@@ -122,14 +130,25 @@ class ModelShardEngine(ShardEngine):
             key = bytes(e["key"])[: e["klen"]]
             if key in self.couples:
                 out += self.couples.pop(key)
-        return _to_t(np.array([self._pub(i) for i in out], dtype=PUB))
-
-    def replay(self, w):
-        # clean local couples first
+        for r in _from_t(frag_route_all, ROUTE):
+            if self.owner(int(r["ref1"]), int(r["coord1"])) == self.rank and not (self.base <= r["idx1"] < self.base + self.n):
+                self.frags.append(tuple(r))
+        # the remaining local couples: those whose key another rank owns leave
+        route = []
         for key, (i, j) in self.couples.items():
             a = np.array([self._pub(i)], dtype=PUB)[0]
             b = np.array([self._pub(j)], dtype=PUB)[0]
-            self.pairs.append(self._pair(a, b))
+            p = self._pair(a, b)
+            (route if self.owner(int(p[2]), int(p[3])) != self.rank else self.pairs).append(p)
+        return _to_t(np.array([self._pub(i) for i in out], dtype=PUB)), _to_t(np.array(route, dtype=ROUTE))
+
+    def _mark(self, g, foreign):
+        if self.base <= g < self.base + self.n:
+            self.dup[g - self.base] = True
+        else:
+            foreign.append(g)
+
+    def finish(self, w, pair_route_all):
         wa = _from_t(w, PUB)
         groups = {}
         seen = set()
@@ -144,33 +163,9 @@ class ModelShardEngine(ShardEngine):
                 p = self._pair(es[k], es[k + 1])
                 if self.owner(int(p[2]), int(p[3])) == self.rank:
                     self.pairs.append(p)
-
-    def route(self):
-        out, keep = [], []
-        for p in self.pairs:
-            (out if self.owner(int(p[2]), int(p[3])) != self.rank else keep).append(p)
-        self.pairs = keep
-        self.frags = []
-        for i in range(self.n):
-            e = self.ends[i]
-            if not e["eligible"]:
-                continue
-            f = (0, e["lib"], e["ref"], e["coord"], int(e["orientation"]), -1, -1, e["score"], self.base + i, -1,
-                 1 if e["read2Sequence"] != -1 else 0)
-            (out if self.owner(int(e["ref"]), int(e["coord"])) != self.rank else self.frags).append(f)
-        return _to_t(np.array(out, dtype=ROUTE))
-
-    def _mark(self, g, foreign):
-        if self.base <= g < self.base + self.n:
-            self.dup[g - self.base] = True
-        else:
-            foreign.append(g)
-
-    def finish(self, route_all):
-        for r in _from_t(route_all, ROUTE):
-            if self.owner(int(r["ref1"]), int(r["coord1"])) != self.rank:
-                continue
-            (self.pairs if r["kind"] == 1 else self.frags).append(tuple(r))
+        for r in _from_t(pair_route_all, ROUTE):
+            if self.owner(int(r["ref1"]), int(r["coord1"])) == self.rank:
+                self.pairs.append(tuple(r))
         foreign = []
         groups = {}
         for p in self.pairs:
@@ -186,8 +181,8 @@ class ModelShardEngine(ShardEngine):
         groups = {}
         for f in self.frags:
             groups.setdefault((int(f[1]), int(f[2]), int(f[3]), int(f[4])), []).append(f)
-        for g in groups.values():      # :371-390, :515-540
-            if len(g) < 2 or all(f[10] for f in g):
+        for key, g in groups.items():      # :371-390, :515-540
+            if len(g) < 2 or all(f[10] for f in g) or self.owner(key[1], key[2]) != self.rank:
                 continue
             if any(f[10] for f in g):
                 for f in g:
@@ -198,7 +193,7 @@ class ModelShardEngine(ShardEngine):
                 for f in g:
                     if f is not best:
                         self._mark(int(f[8]), foreign)
-        return _to_t(np.array(foreign, dtype=MARK))
+        return _to_t(np.array(foreign, dtype=MARK)), torch.empty(0, dtype=torch.uint8)
 
     def apply(self, marks_all):
         for g in _from_t(marks_all, MARK):
