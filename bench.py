@@ -215,6 +215,9 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the dedup path has no CPU fallback")
     dist = None
     if world > 1:
+        # NCCL prints its version banner to stdout at some debug levels: the bench prints ONE JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
