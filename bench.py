@@ -288,9 +288,11 @@ def run_ours(args):
     peak, peak_src = load_peaks()
     achieved = (pass_bytes / 1e9) / (pass_ms * 1e-3) if pass_ms > 0 else 0.0
     traffic = load_traffic()
-    roofline = {"bound": "hbm", "kernel": "rs_onesweep_pass", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "rs_pass_v2 (onesweep radix-sort pass)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_source": peak_src,
-                "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+                "traffic": (traffic["ratio"] * pass_bytes / pass_launches) if traffic and pass_launches else None,
+                "traffic_source": ("profiles/roofline_traffic.json: dram bytes / algorithmic bytes = %.3f over the ncu --set full "
+                                   "capture of the same kernel at C2 size, applied to this run's bytes per launch" % traffic["ratio"]) if traffic else None,
                 "launches_timed": pass_launches,
                 "avg_launch_ms": pass_ms / pass_launches if pass_launches else None,
                 "algorithmic_bytes_per_launch": pass_bytes / pass_launches if pass_launches else None}

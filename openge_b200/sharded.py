@@ -393,7 +393,9 @@ def bench(args, rank, world, local_rank, rec, offs, text, contigs, metric, workl
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "rs_pass_v2", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src,
-                         "traffic": traffic.get("dram_bytes_per_launch") if traffic else None, "launches_timed": pass_launches,
+                         "traffic": (traffic["ratio"] * pass_bytes / pass_launches) if traffic and pass_launches else None,
+                "traffic_source": ("profiles/roofline_traffic.json: dram bytes / algorithmic bytes = %.3f over the ncu --set full "
+                                   "capture of the same kernel at C2 size, applied to this run's bytes per launch" % traffic["ratio"]) if traffic else None, "launches_timed": pass_launches,
                          "avg_launch_ms": pass_ms / pass_launches if pass_launches else None,
                          "algorithmic_bytes_per_launch": pass_bytes / pass_launches if pass_launches else None, "rank": 0},
             "cpu_baseline": None,
