@@ -234,3 +234,46 @@ def test_size_independent_properties_at_scale():
     assert np.array_equal(flags, want)
     # mates of a duplicate pair are flagged together
     assert st["n_duplicates"] % 2 == 0
+
+
+def long_name_bam():
+    """Names far longer than the 29 characters a name tag holds, identical up to their last character;
+    a 254-character name; a read close to the reference's 10 000-byte record limit."""
+    text = "@HD\tVN:1.4\tSO:coordinate\n@SQ\tSN:chr1\tLN:100000\n@RG\tID:rg1\tLB:libA\tSM:s\n"
+    rg = bamio.tag_z("RG", "rg1")
+    stem = "instrument:run:flowcell:lane:tile:" + "x" * 30 + ":"
+    recs = []
+
+    def pair(name, p1, p2, q):
+        recs.append((p1, bamio.build_record(name, 99, 0, p1, 60, "100M", 0, p2, 0, "ACGT" * 25, q, rg)))
+        recs.append((p2, bamio.build_record(name, 147, 0, p2, 60, "100M", 0, p1, 0, "ACGT" * 25, q, rg)))
+
+    for k in range(40):                       # 40 duplicate pairs whose names differ only in the tail
+        pair(stem + "%04d" % k, 1000, 1300, 20 + (k % 20))
+    pair("n" * 254, 5000, 5300, 30)           # the longest name BAM allows
+    pair("m" * 253 + "z", 5000, 5300, 35)
+    big = 4800                                # 4800 bases: 36 + name + 8 + 2400 + 4800 + tags < 10 000
+    recs.append((9000, bamio.build_record("big1", 0, 0, 9000, 60, "%dM" % big, -1, -1, 0, "A" * big, 40, rg)))
+    recs.append((9000, bamio.build_record("big2", 0, 0, 9000, 60, "10S%dM" % (big - 10), -1, -1, 0, "A" * big, 41, rg)))
+    recs.append((8990, bamio.build_record("big3", 0, 0, 8990, 60, "%dM" % big, -1, -1, 0, "A" * big, 42, rg)))
+    recs.sort(key=lambda t: t[0])
+    records, offsets = bamio.concat_records([r for _, r in recs])
+    return bamio.BamFile(text=text, refs=[("chr1", 100000)], records=records, offsets=offsets)
+
+
+def test_long_names_and_large_records():
+    bam = long_name_bam()
+    want = oracle.markdup(bam.records, bam.offsets, bam.text)
+    got, st = gpu_flags(bam)
+    assert np.array_equal(got, want)
+    assert int(((want & 0x400) != 0).sum()) == 2 * 39 + 2 + 1      # all but the best pair of each group, and big1 (big2's unclipped start is 8990)
+    assert st["n_hash_mismatch"] == 0
+
+
+def test_long_names_across_shards():
+    from openge_b200 import sharded
+    bam = long_name_bam()
+    want = oracle.markdup(bam.records, bam.offsets, bam.text)
+    for world in (2, 3):
+        got, _ = sharded.dedup_in_process(bam, world)
+        assert np.array_equal(got, want)
