@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define OGE_GPU_DEDUP_ABI_VERSION 1
+#define OGE_GPU_DEDUP_ABI_VERSION 2
 
 enum {
     OGE_OK = 0,
@@ -65,6 +65,8 @@ typedef struct oge_gpu_dedup_config {
     int32_t rank;
     int32_t world;
     uint64_t index_base;            /* global ordinal of this shard's first record */
+    int32_t debug_full_frag_sort;   /* 1: always sort every fragment end (measurement / A-B of the reduced fragment pass) */
+    int32_t reserved;
 } oge_gpu_dedup_config;
 
 /* Per-run counters (the reference prints the analogous numbers under -v, mark_duplicates.cpp:261,433). */

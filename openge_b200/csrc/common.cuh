@@ -86,6 +86,8 @@ enum : uint32_t {
 enum {
     CNT_ERR = 0,
     CNT_FRAG,           // eligible records (fragSort.size())
+    CNT_UNPAIRED,       // eligible records that are not an end of a pair (the only ones the fragment pass can mark)
+    CNT_UFRAG,          // fragment entries collected for the reduced fragment sort
     CNT_PAIR_ELIGIBLE,  // records that enter the mate map
     CNT_PAIRS,          // pair entries emitted (pairSort.size())
     CNT_COMPLEX,        // half-pair entries sent to the exact slow path

@@ -89,6 +89,8 @@ struct oge_gpu_dedup_ctx {
 
     // work arrays
     DevBuf<E128> frag, sortbuf, pair, pair2, pairf, pairf2;      // pair = near pairs, pairf = far pairs
+    DevBuf<E128> ufrag, ufrag2;                                  // reduced fragment pass: the entries that can matter
+    DevBuf<unsigned long long> uset;                             // keys of the unpaired ends
     DevBuf<uint64_t> hk;
     DevBuf<uint16_t> flag_in, flag_out;
     DevBuf<NameTag> tag;
@@ -96,6 +98,7 @@ struct oge_gpu_dedup_ctx {
     DevBuf<uint32_t> mate_of, counters, cplx_slots;
     DevBuf<MateSlot> table;
     uint32_t *h_counters = nullptr;      // pinned
+    uint64_t h_counters_k1_unpaired = 0;
 
     KeyLayout kl;
     bool ran = false;

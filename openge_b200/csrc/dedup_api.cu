@@ -230,7 +230,7 @@ void oge_gpu_dedup_destroy(oge_gpu_dedup_ctx *c) {
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->side_stream) cudaStreamSynchronize(c->side_stream);
     c->rec.release(); c->off.release(); c->rg_bytes.release(); c->rg_off.release(); c->rg_lib.release();
-    c->frag.release(); c->sortbuf.release(); c->pair.release(); c->pair2.release(); c->pairf.release(); c->pairf2.release(); c->hk.release();
+    c->frag.release(); c->sortbuf.release(); c->pair.release(); c->pair2.release(); c->pairf.release(); c->pairf2.release(); c->ufrag.release(); c->ufrag2.release(); c->uset.release(); c->hk.release();
     c->tag.release(); c->flag_in.release(); c->flag_out.release(); c->dup.release(); c->scratch.release();
     c->cplx_state.release(); c->cplx_slots.release(); c->mate_of.release(); c->counters.release(); c->table.release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -358,6 +358,7 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     OGE_CUDA_TRY(cudaStreamSynchronize(s));
     if ((rc = check_endbuild_errors(c))) return rc;
     const uint64_t n_frag = c->h_counters[CNT_FRAG], n_pe = c->h_counters[CNT_PAIR_ELIGIBLE];
+    c->h_counters_k1_unpaired = c->h_counters[CNT_UNPAIRED];
 
     // ---- K2 mate join
     uint64_t n_pairs = 0, n_far = 0, n_cplx = 0, n_retracted = 0, n_far_retracted = 0;
@@ -439,16 +440,47 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     }
     OGE_CUDA_TRY(cudaEventRecord(c->ev[4], s));
 
-    // ---- K3 + K4 on the fragments (ineligible records carry the all-ones key and sort last)
+    // ---- K3 + K4 on the fragments.  Only an end that is not part of a pair can be marked here, and an end
+    //      of a pair only matters when it shares its key with such an end (fragfilter.cu): sort that subset
+    //      when unpaired ends are rare (none at all on clean paired-end data), everything otherwise
+    //      (ineligible records carry the all-ones key and sort last).
+    const uint64_t n_unp = c->h_counters_k1_unpaired;
     E128 *sorted_frags = c->frag.p;
-    if (n_frag) {
+    uint64_t n_fsel = 0;
+    int frag_mode = 2;      // 0 nothing to do, 1 reduced, 2 full
+    if (n_frag == 0) frag_mode = 0;
+    else if (c->cfg.debug_full_frag_sort) frag_mode = 2;
+    else if (n_unp == 0) frag_mode = 0;
+    else if (n_unp <= n_frag / 16 && c->kl.f_end - c->kl.f_orient <= 63) frag_mode = 1;
+    if (frag_mode == 1) {
+        const uint64_t ucap = std::max<uint64_t>(n_frag / 4, 4 * n_unp) + 1024;
+        uint64_t n_slots = 1024;
+        while (n_slots < 4 * n_unp) n_slots <<= 1;
+        if ((rc = c->ufrag.reserve(ucap, false, s))) return rc;
+        if ((rc = c->ufrag2.reserve(ucap, false, s))) return rc;
+        if ((rc = c->uset.reserve(n_slots, false, s))) return rc;
+        OGE_CUDA_TRY(cudaMemsetAsync(c->uset.p, 0, n_slots * 8, s));
+        OGE_CUDA_TRY(cudaMemsetAsync(c->counters.p + CNT_UFRAG, 0, 4, s));
+        if ((rc = launch_ff_collect(c->frag.p, n, c->kl, c->ufrag.p, (uint32_t) ucap, c->counters.p, s, &launches))) return rc;
+        if ((rc = launch_ff_set_build(c->ufrag.p, c->counters.p + CNT_UFRAG, (uint32_t) n_unp, c->kl, c->uset.p, n_slots, s, &launches))) return rc;
+        if ((rc = launch_ff_filter(c->frag.p, n, c->kl, c->uset.p, n_slots, c->ufrag.p, (uint32_t) ucap, c->counters.p, s, &launches))) return rc;
+        OGE_CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, s));
+        OGE_CUDA_TRY(cudaStreamSynchronize(s));
+        n_fsel = c->h_counters[CNT_UFRAG];
+        if (n_fsel > ucap) frag_mode = 2;      // more paired ends share keys with unpaired ones than expected: sort everything
+        else if ((rc = radix_sort_128(c->ufrag.p, c->ufrag2.p, n_fsel, nullptr, c->kl.f_orient, c->kl.f_end, c->scratch.p, s, &sorted_frags,
+                                      &launches, tp)))
+            return rc;
+    }
+    if (frag_mode == 2) {
+        n_fsel = n_frag;
         if ((rc = radix_sort_128(c->frag.p, c->sortbuf.p, n, nullptr, c->kl.f_orient, c->kl.f_end, c->scratch.p, s, &sorted_frags,
                                  &launches, tp)))
             return rc;
     }
     OGE_CUDA_TRY(cudaEventRecord(c->ev[5], s));
-    if (n_frag) {
-        sp.sorted = sorted_frags; sp.n_max = (uint32_t) n_frag;
+    if (frag_mode && n_fsel) {
+        sp.sorted = sorted_frags; sp.n_max = (uint32_t) n_fsel;
         if ((rc = launch_select_frags(sp, s, &launches))) return rc;
     }
     OGE_CUDA_TRY(cudaEventRecord(c->ev[6], s));
@@ -462,7 +494,7 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     OGE_CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, s));
     OGE_CUDA_TRY(cudaStreamSynchronize(s));
     // the fragment sort moved the end entries: keep them findable for debug_ends
-    if (c->cfg.debug_keep_ends && sorted_frags != c->frag.p && n_frag)
+    if (c->cfg.debug_keep_ends && frag_mode == 2 && sorted_frags != c->frag.p && n_frag)
         OGE_CUDA_TRY(cudaMemcpy(c->frag.p, sorted_frags, n * sizeof(E128), cudaMemcpyDeviceToDevice));
 
     if (getenv("OGE_DEBUG_COUNTERS"))

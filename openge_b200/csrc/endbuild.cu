@@ -235,12 +235,12 @@ struct RgSmem {
 // ---------------------------------------------------------------- one record
 template <class Rd>
 __device__ __forceinline__ void build_end(const EndbuildParams &P, const RgSmem &rgt, const Rd &r, uint32_t rec_len, uint64_t i,
-                                          uint32_t &err, bool &is_frag, bool &is_pe) {
+                                          uint32_t &err, bool &is_frag, bool &is_pe, bool &is_unpaired) {
     E128 ent;
     ent.lo = ent.hi = ~0ull;
     uint64_t hk = 0;
     uint32_t rgc = RGC_ABSENT, flag = 0;
-    is_frag = is_pe = false;
+    is_frag = is_pe = is_unpaired = false;
 
     bool ok = rec_len >= 36;
     uint32_t l_name = 0, n_cig = 0, l_seq = 0, o_cig = 0, o_qual = 0, o_tags = 0;
@@ -338,6 +338,7 @@ __device__ __forceinline__ void build_end(const EndbuildParams &P, const RgSmem 
                 bits_or(ent, L.f_coord, (uint64_t) sc);
                 bits_or(ent, L.f_ref, (uint64_t) ref | ((uint64_t) lib << L.ref_bits));                  // f_lib = f_ref + ref_bits
                 is_frag = true;
+                is_unpaired = !paired;      // only these can be marked by the fragment pass (mark_duplicates.cpp:379, 517-538)
                 if (pe) {
                     KeyHasher h;
                     h.init();
@@ -431,7 +432,7 @@ __global__ void __launch_bounds__(EB_THREADS) endbuild_kernel(EndbuildParams P, 
 
     if (tid == 0 && blockIdx.x < n_tiles) issue(blockIdx.x, P.off[(uint64_t) blockIdx.x * EB_THREADS], P.off[tile_end(blockIdx.x)]);
 
-    uint32_t err = 0, n_frag = 0, n_pe = 0, k = 0;
+    uint32_t err = 0, n_frag = 0, n_pe = 0, n_unp = 0, k = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, k++) {
         // byte range of this CTA's next tile: requested now, needed after the parse
         const uint32_t nt = tile + gridDim.x;
@@ -444,7 +445,7 @@ __global__ void __launch_bounds__(EB_THREADS) endbuild_kernel(EndbuildParams P, 
         const uint64_t r = (uint64_t) tile * EB_THREADS + tid;
         if (r < P.n) {
             const uint64_t o0 = s_off[tid], o1 = s_off[tid + 1];
-            bool f = false, pe = false;
+            bool f = false, pe = false, unp = false;
             if (o1 < o0 || o1 - o0 > 0xFFFFFFFFull) {
                 err |= DEV_ERR_BAD_RECORD;
                 reinterpret_cast<ulonglong2 *>(P.frag)[r] = make_ulonglong2(~0ull, ~0ull);
@@ -452,13 +453,14 @@ __global__ void __launch_bounds__(EB_THREADS) endbuild_kernel(EndbuildParams P, 
                 P.flag_in[r] = 0;
             } else if (s_direct) {
                 GlobalRd rd{P.rec + o0};
-                build_end(P, rgt, rd, (uint32_t) (o1 - o0), r, err, f, pe);
+                build_end(P, rgt, rd, (uint32_t) (o1 - o0), r, err, f, pe, unp);
             } else {
                 SharedRd rd{stage_addr + (uint32_t) (o0 - s_a0)};
-                build_end(P, rgt, rd, (uint32_t) (o1 - o0), r, err, f, pe);
+                build_end(P, rgt, rd, (uint32_t) (o1 - o0), r, err, f, pe, unp);
             }
             n_frag += f;
             n_pe += pe;
+            n_unp += unp;
         }
         __syncthreads();      // everyone is done with the stage
         if (tid == 0 && nt < n_tiles) issue(nt, nb0, nb1);
@@ -468,10 +470,12 @@ __global__ void __launch_bounds__(EB_THREADS) endbuild_kernel(EndbuildParams P, 
     for (int o = 16; o; o >>= 1) {
         n_frag += __shfl_xor_sync(0xFFFFFFFFu, n_frag, o);
         n_pe += __shfl_xor_sync(0xFFFFFFFFu, n_pe, o);
+        n_unp += __shfl_xor_sync(0xFFFFFFFFu, n_unp, o);
         err |= __shfl_xor_sync(0xFFFFFFFFu, err, o);
     }
     if ((tid & 31) == 0) {
         if (n_frag) atomicAdd(&P.counters[CNT_FRAG], n_frag);
+        if (n_unp) atomicAdd(&P.counters[CNT_UNPAIRED], n_unp);
         if (n_pe) atomicAdd(&P.counters[CNT_PAIR_ELIGIBLE], n_pe);
         if (err) atomicOr(&P.counters[CNT_ERR], err);
     }

@@ -108,6 +108,14 @@ struct SelectParams {
 int launch_select_pairs(const SelectParams &P, bool far, cudaStream_t stream, uint64_t *launches);
 int launch_select_frags(const SelectParams &P, cudaStream_t stream, uint64_t *launches);
 
+// ---- reduced fragment pass (fragfilter.cu): only unpaired ends and the paired ends sharing a key with one matter
+int launch_ff_collect(const E128 *frag, uint64_t n, const KeyLayout &L, E128 *out, uint32_t cap, uint32_t *counters, cudaStream_t s,
+                      uint64_t *launches);
+int launch_ff_set_build(const E128 *list, const uint32_t *n_dev, uint32_t n_max, const KeyLayout &L, unsigned long long *set, uint64_t n_slots,
+                        cudaStream_t s, uint64_t *launches);
+int launch_ff_filter(const E128 *frag, uint64_t n, const KeyLayout &L, const unsigned long long *set, uint64_t n_slots, E128 *out, uint32_t cap,
+                     uint32_t *counters, cudaStream_t s, uint64_t *launches);
+
 // ---- K5 flag write (flags.cu) -----------------------------------------------------------------
 struct FlagParams {
     uint8_t *rec;

@@ -19,7 +19,7 @@ import numpy as np
 from . import _build, header as _header
 from .bamio import BamFile
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 OGE_OK = 0
 ERRORS = {-1: "OGE_ERR_INVALID_ARG", -2: "OGE_ERR_CUDA", -3: "OGE_ERR_NOMEM", -4: "OGE_ERR_KEY_RANGE",
@@ -31,7 +31,8 @@ class Config(C.Structure):
                 ("clip_margin", C.c_int32), ("remove_duplicates", C.c_int32), ("verify_names", C.c_int32),
                 ("compat_quiet_index_bug", C.c_int32), ("debug_keep_ends", C.c_int32), ("profile_events", C.c_int32),
                 ("capacity_records", C.c_uint64), ("capacity_bytes", C.c_uint64),
-                ("rank", C.c_int32), ("world", C.c_int32), ("index_base", C.c_uint64)]
+                ("rank", C.c_int32), ("world", C.c_int32), ("index_base", C.c_uint64),
+                ("debug_full_frag_sort", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -171,13 +172,13 @@ class DedupContext:
 
     def __init__(self, n_ref=0, max_ref_len=0, device=0, remove_duplicates=False, verify_names=True,
                  compat_quiet_index_bug=False, debug_keep_ends=False, clip_margin=0, capacity_records=0,
-                 capacity_bytes=0, index_base=0, rank=0, world=1, profile_events=False):
+                 capacity_bytes=0, index_base=0, rank=0, world=1, profile_events=False, full_frag_sort=False):
         self._h = C.c_void_p()
         cfg = Config(abi_version=ABI_VERSION, device=device, n_ref=n_ref, max_ref_len=max_ref_len, clip_margin=clip_margin,
                      remove_duplicates=int(remove_duplicates), verify_names=int(verify_names),
                      compat_quiet_index_bug=int(compat_quiet_index_bug), debug_keep_ends=int(debug_keep_ends),
                      profile_events=int(profile_events), capacity_records=capacity_records, capacity_bytes=capacity_bytes, rank=rank, world=world,
-                     index_base=index_base)
+                     index_base=index_base, debug_full_frag_sort=int(full_frag_sort))
         _check(lib().oge_gpu_dedup_create(C.byref(cfg), C.byref(self._h)))
         self.n = 0
         self.nbytes = 0

@@ -28,7 +28,7 @@ def test_header_symbols_exported():
 def test_abi_version_and_struct_sizes():
     L = dedup.lib()
     assert L.oge_gpu_abi_version() == dedup.ABI_VERSION
-    assert C.sizeof(dedup.Config) == 72
+    assert C.sizeof(dedup.Config) == 80
     assert C.sizeof(dedup.Stats) == 120
     assert dedup.END_DTYPE.itemsize == 28
 
