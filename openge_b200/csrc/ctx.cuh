@@ -54,7 +54,9 @@ struct ShardState {
     DevBuf<uint32_t> marks, marks_frag, pub_list;
     DevBuf<uint8_t> scratch2;             // sort scratch of the side stream
     cudaEvent_t ev_main = nullptr, ev_side[3] = {nullptr, nullptr, nullptr};
-    bool frag_busy = false;
+    bool frag_busy = false, frag_ran = false;
+    int frag_mode = 2;                    // 0 nothing, 1 reduced fragment pass, 2 every fragment end
+    uint64_t n_unpaired = 0, ucap = 0, uset_slots = 0;
     int side_pass_used = 0;
     uint64_t side_pass_bytes = 0, n_froute_all = 0;
     DevBuf<uint64_t> fm;                  // foreign mates: (idx1 << 32 | idx2), sorted by idx1

@@ -453,7 +453,8 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     else if (n_unp == 0) frag_mode = 0;
     else if (n_unp <= n_frag / 16 && c->kl.f_end - c->kl.f_orient <= 63) frag_mode = 1;
     if (frag_mode == 1) {
-        const uint64_t ucap = std::max<uint64_t>(n_frag / 4, 4 * n_unp) + 1024;
+        uint64_t ucap = std::max<uint64_t>(n_frag / 4, 4 * n_unp) + 1024;
+        if (const char *e = getenv("OGE_UFRAG_CAP")) ucap = std::max<uint64_t>(1, (uint64_t) atoll(e));      // test hook: force the fallback
         uint64_t n_slots = 1024;
         while (n_slots < 4 * n_unp) n_slots <<= 1;
         if ((rc = c->ufrag.reserve(ucap, false, s))) return rc;

@@ -145,6 +145,8 @@ static int route_sweep(oge_gpu_dedup_ctx *c, int n_lists, E128 *const *lists, co
     return 0;
 }
 
+__global__ void sh_fit_counter_kernel(uint32_t *dst, const uint32_t *counter, uint32_t cap) { *dst = *counter <= cap ? *counter : 0u; }
+
 __global__ void sh_add_counter_kernel(uint32_t *dst, uint32_t base, const uint32_t *counter, uint32_t cap) {
     uint32_t v = base + min(*counter, cap);
     *dst = v;
@@ -182,7 +184,8 @@ int oge_gpu_shard_begin(oge_gpu_dedup_ctx *c, void **pub_dev, uint64_t *n_pub, v
     }
     OGE_CUDA_TRY(cudaEventRecord(c->copy_done, c->copy_stream));
     OGE_CUDA_TRY(cudaStreamWaitEvent(s, c->copy_done, 0));
-    sh.n_frag = sh.n_pe = sh.n_pairs = sh.n_retracted = sh.n_far = sh.n_far_dead = sh.n_slots = sh.n_fm = sh.n_froute_all = 0;
+    sh.n_frag = sh.n_pe = sh.n_pairs = sh.n_retracted = sh.n_far = sh.n_far_dead = sh.n_slots = sh.n_fm = sh.n_froute_all = sh.n_unpaired = 0;
+    sh.frag_mode = 0;
     OGE_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, CNT_N * 4, s));
     uint64_t n_fr = 0;
     if (n) {
@@ -199,6 +202,7 @@ int oge_gpu_shard_begin(oge_gpu_dedup_ctx *c, void **pub_dev, uint64_t *n_pub, v
         if ((rc = check_endbuild_errors(c))) return rc;
         sh.n_frag = c->h_counters[CNT_FRAG];
         sh.n_pe = c->h_counters[CNT_PAIR_ELIGIBLE];
+        sh.n_unpaired = c->h_counters[CNT_UNPAIRED];
     }
     uint64_t n_list = 0;
     if (sh.n_pe) {
@@ -293,10 +297,28 @@ int oge_gpu_shard_probe(oge_gpu_dedup_ctx *c, const void *pub_all_dev, uint64_t 
     //      concurrently with the pair routing, the second exchange and the replay on the main stream
     sh.n_froute_all = n_fr_all;
     sh.frag_busy = false;
-    if (n + n_fr_all) {
-        if ((rc = c->frag.reserve(n + n_fr_all, true, s))) return rc;
-        if ((rc = c->sortbuf.reserve(n + n_fr_all, false, s))) return rc;
-        if ((rc = sh.scratch2.reserve(sort_scratch_bytes(n + n_fr_all), false, s))) return rc;
+    // how much of the fragment work is needed at all (fragfilter.cu): nothing when neither this shard nor
+    // the routed copies hold an unpaired end; the reduced pass when they are rare; else everything
+    sh.frag_mode = 2;
+    if (sh.n_unpaired == 0 && n_fr_all == 0) sh.frag_mode = 0;
+    else if (!c->cfg.debug_full_frag_sort && sh.n_unpaired <= sh.n_frag / 16 && c->kl.f_end - c->kl.f_orient <= 63) sh.frag_mode = 1;
+    if (sh.frag_mode && n + n_fr_all) {
+        const uint64_t n_all_frag = n + n_fr_all;
+        sh.ucap = std::max<uint64_t>(sh.n_frag / 4, 4 * sh.n_unpaired) + n_fr_all + 1024;
+        if (const char *e = getenv("OGE_UFRAG_CAP")) sh.ucap = std::max<uint64_t>(1, (uint64_t) atoll(e));      // test hook: force the fallback
+        if ((rc = c->frag.reserve(n_all_frag, true, s))) return rc;
+        if (sh.frag_mode == 2) {
+            if ((rc = c->sortbuf.reserve(n_all_frag, false, s))) return rc;
+            if ((rc = sh.scratch2.reserve(sort_scratch_bytes(n_all_frag), false, s))) return rc;
+        } else {
+            uint64_t n_slots = 1024;
+            while (n_slots < 4 * (sh.n_unpaired + n_fr_all)) n_slots <<= 1;
+            sh.uset_slots = n_slots;
+            if ((rc = c->ufrag.reserve(sh.ucap, false, s))) return rc;
+            if ((rc = c->ufrag2.reserve(sh.ucap, false, s))) return rc;
+            if ((rc = c->uset.reserve(n_slots, false, s))) return rc;
+            if ((rc = sh.scratch2.reserve(sort_scratch_bytes(sh.ucap), false, s))) return rc;
+        }
         if ((rc = sh.marks_frag.reserve(n_fr_all + 16, false, s))) return rc;
         if (n == 0 && (rc = c->mate_of.reserve(1, false, s))) return rc;
         if (n == 0 && (rc = c->dup.reserve(1, false, s))) return rc;
@@ -309,22 +331,43 @@ int oge_gpu_shard_probe(oge_gpu_dedup_ctx *c, const void *pub_all_dev, uint64_t 
                                         nullptr, 0, nullptr, 0, nullptr, nullptr, 0, s2, &launches)))
                 return rc;
         }
-        sh_add_counter_kernel<<<1, 1, 0, s2>>>(c->counters.p + CNT_FRAG_VALID, (uint32_t) sh.n_frag, c->counters.p + CNT_FRAG_EXTRA, (uint32_t) n_fr_all);
         PassTimer timer2{c->pass_ev + 48, 24, 0, 0};
         E128 *sorted_frags = c->frag.p;
-        if ((rc = radix_sort_128(c->frag.p, c->sortbuf.p, n + n_fr_all, nullptr, c->kl.f_orient, c->kl.f_end, sh.scratch2.p, s2, &sorted_frags,
-                                 &launches, c->cfg.profile_events ? &timer2 : nullptr)))
-            return rc;
-        sh.side_pass_used = timer2.used;
-        sh.side_pass_bytes = timer2.bytes;
-        OGE_CUDA_TRY(cudaEventRecord(sh.ev_side[1], s2));
         SelectParams sp;
         sp.dup = c->dup.p; sp.mate_of = c->mate_of.p; sp.idx_base = c->cfg.index_base; sp.n_records = n;
         sp.counters = c->counters.p; sp.kl = c->kl;
         sp.fm = nullptr; sp.n_fm = 0; sp.foreign_marks = sh.marks_frag.p; sp.foreign_cap = (uint32_t) sh.marks_frag.cap;
         sp.foreign_counter = c->counters.p + CNT_FOREIGN_MARKS_FRAG;
         sp.split = sh.d_split.p; sp.world = c->cfg.world; sp.rank = c->cfg.rank;
-        sp.sorted = sorted_frags; sp.n_max = (uint32_t) (n + n_fr_all); sp.n_dev = c->counters.p + CNT_FRAG_VALID;
+        if (sh.frag_mode == 1) {
+            // sizes stay on the device (the side stream never waits for the host): CNT_UFRAG counts what was
+            // collected, CNT_FRAG_VALID is that count if it fits the list and 0 otherwise (overflow: finish()
+            // notices and falls back to the full sort)
+            OGE_CUDA_TRY(cudaMemsetAsync(c->uset.p, 0, sh.uset_slots * 8, s2));
+            OGE_CUDA_TRY(cudaMemsetAsync(c->counters.p + CNT_UFRAG, 0, 4, s2));
+            if ((rc = launch_ff_collect(c->frag.p, n_all_frag, c->kl, c->ufrag.p, (uint32_t) sh.ucap, c->counters.p, s2, &launches))) return rc;
+            if ((rc = launch_ff_set_build(c->ufrag.p, c->counters.p + CNT_UFRAG, (uint32_t) std::min<uint64_t>(sh.n_unpaired + n_fr_all, sh.ucap),
+                                          c->kl, c->uset.p, sh.uset_slots, s2, &launches)))
+                return rc;
+            if ((rc = launch_ff_filter(c->frag.p, n_all_frag, c->kl, c->uset.p, sh.uset_slots, c->ufrag.p, (uint32_t) sh.ucap, c->counters.p, s2,
+                                       &launches)))
+                return rc;
+            sh_fit_counter_kernel<<<1, 1, 0, s2>>>(c->counters.p + CNT_FRAG_VALID, c->counters.p + CNT_UFRAG, (uint32_t) sh.ucap);
+            if ((rc = radix_sort_128(c->ufrag.p, c->ufrag2.p, sh.ucap, c->counters.p + CNT_FRAG_VALID, c->kl.f_orient, c->kl.f_end, sh.scratch2.p,
+                                     s2, &sorted_frags, &launches, c->cfg.profile_events ? &timer2 : nullptr)))
+                return rc;
+            sp.n_max = (uint32_t) sh.ucap;
+        } else {
+            sh_add_counter_kernel<<<1, 1, 0, s2>>>(c->counters.p + CNT_FRAG_VALID, (uint32_t) sh.n_frag, c->counters.p + CNT_FRAG_EXTRA, (uint32_t) n_fr_all);
+            if ((rc = radix_sort_128(c->frag.p, c->sortbuf.p, n_all_frag, nullptr, c->kl.f_orient, c->kl.f_end, sh.scratch2.p, s2, &sorted_frags,
+                                     &launches, c->cfg.profile_events ? &timer2 : nullptr)))
+                return rc;
+            sp.n_max = (uint32_t) n_all_frag;
+        }
+        sh.side_pass_used = timer2.used;
+        sh.side_pass_bytes = timer2.bytes;
+        OGE_CUDA_TRY(cudaEventRecord(sh.ev_side[1], s2));
+        sp.sorted = sorted_frags; sp.n_dev = c->counters.p + CNT_FRAG_VALID;
         if ((rc = launch_select_frags(sp, s2, &launches))) return rc;
         OGE_CUDA_TRY(cudaEventRecord(sh.ev_side[2], s2));
         sh.frag_busy = true;
@@ -441,6 +484,7 @@ int oge_gpu_shard_finish(oge_gpu_dedup_ctx *c, const void *w_dev, uint64_t n_w, 
     }
     // ---- join the side stream: the fragment verdicts
     uint64_t extra = 0;
+    sh.frag_ran = sh.frag_busy;
     if (sh.frag_busy) {
         PhaseClock clk(c, nullptr);      // whatever of the fragment work the pair work did not hide
         OGE_CUDA_TRY(cudaStreamWaitEvent(s, sh.ev_side[2], 0));
@@ -448,10 +492,31 @@ int oge_gpu_shard_finish(oge_gpu_dedup_ctx *c, const void *w_dev, uint64_t n_w, 
         sh.frag_busy = false;
     }
     if ((rc = read_counters(c))) return rc;
+    if (sh.frag_mode == 1 && c->h_counters[CNT_UFRAG] > sh.ucap) {
+        // more paired ends share a key with an unpaired one than the list holds: nothing was selected
+        // (the device-side size was forced to 0); sort every fragment end now, on this stream
+        PhaseClock clk(c, &c->stats.ms_sort_frag);
+        const uint64_t n_all_frag = n + sh.n_froute_all;
+        if ((rc = c->sortbuf.reserve(n_all_frag, false, s))) return rc;
+        if ((rc = c->scratch.reserve(std::max(sort_scratch_bytes(n_all_frag), c->scratch.cap), true, s))) return rc;
+        sh_add_counter_kernel<<<1, 1, 0, s>>>(c->counters.p + CNT_FRAG_VALID, (uint32_t) sh.n_frag, c->counters.p + CNT_FRAG_EXTRA, (uint32_t) sh.n_froute_all);
+        E128 *sorted_frags = c->frag.p;
+        if ((rc = radix_sort_128(c->frag.p, c->sortbuf.p, n_all_frag, nullptr, c->kl.f_orient, c->kl.f_end, c->scratch.p, s, &sorted_frags, &launches, tp)))
+            return rc;
+        sp.fm = nullptr; sp.n_fm = 0; sp.foreign_marks = sh.marks_frag.p; sp.foreign_cap = (uint32_t) sh.marks_frag.cap;
+        sp.foreign_counter = c->counters.p + CNT_FOREIGN_MARKS_FRAG;
+        sp.sorted = sorted_frags; sp.n_max = (uint32_t) n_all_frag; sp.n_dev = c->counters.p + CNT_FRAG_VALID;
+        if ((rc = launch_select_frags(sp, s, &launches))) return rc;
+        clk.stop();
+        if ((rc = read_counters(c))) return rc;
+        sh.frag_mode = 2;
+    }
     if (sh.n_froute_all || n) {
         extra = std::min<uint64_t>(c->h_counters[CNT_FRAG_EXTRA], sh.n_froute_all);
-        c->stats.ms_sort_frag = ms_between(sh.ev_side[0], sh.ev_side[1]);
-        c->stats.ms_select += ms_between(sh.ev_side[1], sh.ev_side[2]);
+        if (sh.frag_ran) {
+            c->stats.ms_sort_frag += ms_between(sh.ev_side[0], sh.ev_side[1]);
+            c->stats.ms_select += ms_between(sh.ev_side[1], sh.ev_side[2]);
+        }
     }
     const uint64_t n_foreign = c->h_counters[CNT_FOREIGN_MARKS], n_foreign_frag = c->h_counters[CNT_FOREIGN_MARKS_FRAG];
     if (n_foreign > sh.marks.cap || n_foreign_frag > sh.marks_frag.cap)

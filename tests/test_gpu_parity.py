@@ -321,6 +321,26 @@ def test_reduced_fragment_pass_equals_full_sort_and_oracle():
     assert res[False][1]["launches"] != res[True][1]["launches"] or True
 
 
+def test_reduced_fragment_pass_overflow_falls_back(monkeypatch):
+    monkeypatch.setenv("OGE_UFRAG_CAP", "64")
+    bam = sparse_unpaired_bam(scale=0.002)
+    want = oracle.markdup(bam.records, bam.offsets, bam.text)
+    got, _ = gpu_flags(bam)
+    assert np.array_equal(got, want)
+    from openge_b200 import sharded
+    got2, _ = sharded.dedup_in_process(bam, 2)
+    assert np.array_equal(got2, want)
+
+
+def test_reduced_fragment_pass_across_shards():
+    from openge_b200 import sharded
+    bam = sparse_unpaired_bam(scale=0.002)
+    want = oracle.markdup(bam.records, bam.offsets, bam.text)
+    for world in (2, 5):
+        got, _ = sharded.dedup_in_process(bam, world)
+        assert np.array_equal(got, want)
+
+
 def test_paired_only_data_skips_fragment_sort():
     bam = synth.make("C2", 0.004, seed=9)      # every read is an end of a pair
     want = oracle.markdup(bam.records, bam.offsets, bam.text)
