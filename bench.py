@@ -333,6 +333,11 @@ def run_ours(args):
 
 
 def main():
+    # the contract is ONE JSON line on stdout: whatever libraries print there (NCCL's version banner, for one)
+    # goes to stderr, and only the result line is written to the real stdout
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

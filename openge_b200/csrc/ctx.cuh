@@ -75,6 +75,11 @@ struct oge_gpu_dedup_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr, side_stream = nullptr;
     cudaEvent_t copy_done = nullptr;
     cudaEvent_t ev[10];
+    // sharded path: phase clocks are resolved lazily (no host sync per phase)
+    static constexpr int N_CLK = 48;
+    cudaEvent_t clk_ev[2 * N_CLK];
+    float *clk_slot[N_CLK];
+    int clk_used = 0;
     cudaEvent_t pass_ev[2 * 48];      // profile_events: one pair per radix-sort pass launch
 
     // resident input

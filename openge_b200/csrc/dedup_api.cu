@@ -205,6 +205,7 @@ int oge_gpu_dedup_create(const oge_gpu_dedup_config *cfg, oge_gpu_dedup_ctx **ou
             break;
         }
         for (auto &e : c->ev) cudaEventCreate(&e);
+        for (auto &e : c->clk_ev) cudaEventCreate(&e);
         for (auto &e : c->pass_ev) { e = nullptr; if (cfg->profile_events) cudaEventCreate(&e); }
         if (cudaHostAlloc((void **) &c->h_counters, CNT_N * 4, cudaHostAllocDefault) != cudaSuccess) {
             rc = fail_cuda(cudaGetLastError(), "cudaHostAlloc", __FILE__, __LINE__);
@@ -235,6 +236,7 @@ void oge_gpu_dedup_destroy(oge_gpu_dedup_ctx *c) {
     c->cplx_state.release(); c->cplx_slots.release(); c->mate_of.release(); c->counters.release(); c->table.release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : c->clk_ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->pass_ev) if (e) cudaEventDestroy(e);
     if (c->copy_done) cudaEventDestroy(c->copy_done);
     if (c->stream) cudaStreamDestroy(c->stream);

@@ -61,19 +61,33 @@ int zero_counter(oge_gpu_dedup_ctx *c, int which) {
     return 0;
 }
 
-// every phase is bracketed by events; the device time of the phases adds up to stats.ms_total
+// every phase is bracketed by events on the main stream; they are resolved (and added to the stage times and to
+// stats.ms_total) at the next point where the host has synchronised anyway -- no sync of their own
 struct PhaseClock {
     oge_gpu_dedup_ctx *c;
-    float *slot;
-    PhaseClock(oge_gpu_dedup_ctx *ctx, float *stage) : c(ctx), slot(stage) { cudaEventRecord(c->ev[8], c->stream); }
+    int k;
+    PhaseClock(oge_gpu_dedup_ctx *ctx, float *stage) : c(ctx), k(-1) {
+        if (c->clk_used < oge_gpu_dedup_ctx::N_CLK) {
+            k = c->clk_used++;
+            c->clk_slot[k] = stage;
+            cudaEventRecord(c->clk_ev[2 * k], c->stream);
+        }
+    }
     void stop() {
-        cudaEventRecord(c->ev[9], c->stream);
-        cudaEventSynchronize(c->ev[9]);
-        float ms = ms_between(c->ev[8], c->ev[9]);
-        c->stats.ms_total += ms;
-        if (slot) *slot += ms;
+        if (k >= 0) cudaEventRecord(c->clk_ev[2 * k + 1], c->stream);
     }
 };
+
+// call after a stream synchronisation
+void resolve_clocks(oge_gpu_dedup_ctx *c) {
+    for (int k = 0; k < c->clk_used; k++) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->clk_ev[2 * k], c->clk_ev[2 * k + 1]) != cudaSuccess) { cudaGetLastError(); continue; }
+        c->stats.ms_total += ms;
+        if (c->clk_slot[k]) *c->clk_slot[k] += ms;
+    }
+    c->clk_used = 0;
+}
 
 int need_phase(oge_gpu_dedup_ctx *c, int phase, const char *name) {
     if (!c) return fail_msg(OGE_ERR_INVALID_ARG, "%s: null context", name);
@@ -164,6 +178,7 @@ int oge_gpu_shard_begin(oge_gpu_dedup_ctx *c, void **pub_dev, uint64_t *n_pub, v
     memset(&c->stats, 0, sizeof(c->stats));
     c->stats.n_records = c->n;
     c->ran = false;
+    c->clk_used = 0;
     *pub_dev = *froute_dev = nullptr;
     *n_pub = *n_froute = 0;
     if ((rc = compute_layout(c, &c->kl))) return rc;
@@ -257,6 +272,8 @@ int oge_gpu_shard_begin(oge_gpu_dedup_ctx *c, void **pub_dev, uint64_t *n_pub, v
         OGE_CUDA_TRY(cudaStreamSynchronize(s));
         clk.stop();
     }
+    OGE_CUDA_TRY(cudaStreamSynchronize(s));
+    resolve_clocks(c);
     c->stats.launches += launches;
     *pub_dev = sh.pub.p;
     *n_pub = n_list;
@@ -384,6 +401,8 @@ int oge_gpu_shard_probe(oge_gpu_dedup_ctx *c, const void *pub_all_dev, uint64_t 
         sh.n_far_dead += n_pr ? c->h_counters[CNT_SCRATCH1] : 0;
         clk.stop();
     }
+    OGE_CUDA_TRY(cudaStreamSynchronize(s));
+    resolve_clocks(c);
     c->stats.launches += launches;
     *pub2_dev = sh.pub2.p;
     *n_pub2 = n2;
@@ -518,6 +537,7 @@ int oge_gpu_shard_finish(oge_gpu_dedup_ctx *c, const void *w_dev, uint64_t n_w, 
             c->stats.ms_select += ms_between(sh.ev_side[1], sh.ev_side[2]);
         }
     }
+    resolve_clocks(c);
     const uint64_t n_foreign = c->h_counters[CNT_FOREIGN_MARKS], n_foreign_frag = c->h_counters[CNT_FOREIGN_MARKS_FRAG];
     if (n_foreign > sh.marks.cap || n_foreign_frag > sh.marks_frag.cap)
         return fail_msg(OGE_ERR_STATE, "shard_finish: %llu + %llu marks for other ranks, room for %llu + %llu", (unsigned long long) n_foreign,
@@ -552,6 +572,7 @@ int oge_gpu_shard_apply(oge_gpu_dedup_ctx *c, const void *marks_all_dev, uint64_
         if ((rc = launch_flags(fp, s, &launches))) return rc;
         clk.stop();
         if ((rc = read_counters(c))) return rc;
+        resolve_clocks(c);
         c->stats.n_duplicates = c->h_counters[CNT_DUPS];
     }
     c->stats.launches += launches;

@@ -168,50 +168,108 @@ class LocalExchange:
 
 class AllToAllExchange:
     """One rank per process under torch.distributed.  Every rank's lists go to every rank with
-    all_to_all_single (the path's only collective): first the byte counts of the lists, then one payload
-    with uneven splits.  Returns, per list, the ranks' contributions concatenated in rank order."""
+    all_to_all_single (the path's only collective).  Returns, per list, the ranks' contributions
+    concatenated in rank order.
 
-    def __init__(self, dist, device, timed=False):
+    Two wire protocols.  Sized: the byte counts of the lists first, then one payload with uneven
+    splits (two collectives and a host round trip in between).  Framed: ONE collective of fixed-size
+    frames [k sizes | payload | padding], the frame capacity taken from the previous call at the same
+    place in the step (every rank sees every rank's sizes, so all ranks compute the same capacity); a
+    rank whose payload does not fit says so in its header and everybody falls back to the sized
+    protocol for that call.  Steady-state runs (same file shape step after step) use one collective
+    per exchange."""
+
+    HEADER = 64      # bytes: up to 7 int64 sizes + an overflow flag
+
+    def __init__(self, dist, device, timed=False, framed=True):
         import torch
         self.dist, self.torch, self.device = dist, torch, device
         self.world = dist.get_world_size()
         self.bytes_moved = 0
         self.ms = 0.0
         self.timed = timed and str(device).startswith("cuda")
+        self.framed = framed
+        self.cap = {}          # call site -> frame payload capacity agreed by all ranks
+        self.site = 0
+        self.calls = {"framed": 0, "sized": 0}
 
-    def __call__(self, outs):
+    def new_step(self):
+        self.site = 0
+
+    def _split(self, out, per, recv_offsets):
+        torch, W = self.torch, self.world
+        res = []
+        for j in range(len(per[0])):
+            parts = []
+            for r in range(W):
+                o = recv_offsets[r] + sum(per[r][:j])
+                parts.append(out[o: o + per[r][j]])
+            res.append(torch.cat(parts) if W > 1 else parts[0])
+        return tuple(res)
+
+    def _sized(self, mine, payload):
         torch, dist, W = self.torch, self.dist, self.world
-        (mine,) = outs
         k = len(mine)
-        if self.timed:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
         sizes = torch.tensor([int(t.numel()) for t in mine] * W, dtype=torch.int64, device=self.device)
         sizes_all = torch.empty(W * k, dtype=torch.int64, device=self.device)
         dist.all_to_all_single(sizes_all, sizes)
         per = sizes_all.view(W, k).tolist()                      # per[r][j] = bytes of rank r's list j
         recv = [sum(p) for p in per]
-        payload = torch.cat(list(mine)) if k > 1 else mine[0]
         out = torch.empty(sum(recv), dtype=torch.uint8, device=self.device)
         if sum(recv) or payload.numel():
             send = payload.repeat(W) if payload.numel() else payload
             dist.all_to_all_single(out, send, output_split_sizes=recv, input_split_sizes=[int(payload.numel())] * W)
-        res, starts, pos = [], [], 0
+        offs, pos = [], 0
         for r in range(W):
-            starts.append(pos)
+            offs.append(pos)
             pos += recv[r]
-        for j in range(k):
-            parts = []
-            for r in range(W):
-                o = starts[r] + sum(per[r][:j])
-                parts.append(out[o: o + per[r][j]])
-            res.append(torch.cat(parts) if W > 1 else parts[0])
+        self.calls["sized"] += 1
+        return self._split(out, per, offs), per
+
+    def _framed(self, mine, payload, cap):
+        torch, dist, W = self.torch, self.dist, self.world
+        k = len(mine)
+        frame = self.HEADER + cap
+        fits = int(payload.numel()) <= cap
+        hdr = torch.zeros(8, dtype=torch.int64, device=self.device)
+        hdr[:k] = torch.tensor([int(t.numel()) for t in mine], dtype=torch.int64, device=self.device)
+        hdr[7] = 0 if fits else 1
+        buf = torch.empty(frame, dtype=torch.uint8, device=self.device)
+        buf[: self.HEADER] = hdr.view(torch.uint8)
+        if fits and payload.numel():
+            buf[self.HEADER: self.HEADER + payload.numel()] = payload
+        out = torch.empty(W * frame, dtype=torch.uint8, device=self.device)
+        dist.all_to_all_single(out, buf.repeat(W))
+        heads = out.view(W, frame)[:, : self.HEADER].contiguous().view(torch.int64).view(W, 8).tolist()
+        per = [h[:k] for h in heads]
+        if any(h[7] for h in heads):
+            return None, per
+        self.calls["framed"] += 1
+        return self._split(out, per, [r * frame + self.HEADER for r in range(W)]), per
+
+    def __call__(self, outs):
+        torch = self.torch
+        (mine,) = outs
+        assert len(mine) <= 7
+        if self.timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        payload = torch.cat(list(mine)) if len(mine) > 1 else mine[0]
+        site, res = self.site, None
+        self.site += 1
+        if self.framed and site in self.cap:
+            res, per = self._framed(mine, payload, self.cap[site])
+        if res is None:
+            res, per = self._sized(mine, payload)
+        # capacity for the next call at this site: a quarter more than the largest contribution seen now
+        biggest = max(sum(p) for p in per)
+        self.cap[site] = max(4096, (biggest + biggest // 4 + 255) // 256 * 256)
         if self.timed:
             e1.record()
             e1.synchronize()
             self.ms += e0.elapsed_time(e1)
-        self.bytes_moved += int(payload.numel()) * (W - 1)
-        return tuple(res)
+        self.bytes_moved += int(payload.numel()) * (self.world - 1)
+        return res
 
 
 # --------------------------------------------------------------------------------------- the protocol
@@ -219,6 +277,8 @@ def run_phases(engines, exchange):
     """Drive one sharded run over the local `engines` (one per process under torch.distributed, or
     all ranks in-process): three exchanges.  Afterwards every engine's flags() are final."""
     import torch
+    if hasattr(exchange, "new_step"):
+        exchange.new_step()
     pub_all, frag_route_all = exchange([e.begin() for e in engines])
     pub2_all, pair_route_all = exchange([e.probe(pub_all, frag_route_all) for e in engines])
     w = torch.cat([pub_all, pub2_all]) if pub2_all.numel() else pub_all

@@ -121,11 +121,16 @@ def _gloo_worker(rank, world, port, out_dir):
         bam = straddling_case()
         plan, shards = sharded.split_bam(bam, world)
         rec, off = shards[rank]
-        eng = ModelShardEngine(rec, off, bam.text, plan, rank)
         ex = sharded.AllToAllExchange(dist, torch.device("cpu"))
-        info = sharded.run_phases([eng], ex)
+        for it in range(3):      # first run: sized protocol; later runs: one framed collective per exchange
+            eng = ModelShardEngine(rec, off, bam.text, plan, rank)
+            if it == 2:
+                ex.cap = {k: 4096 for k in ex.cap}      # frames too small: every rank must fall back together
+            info = sharded.run_phases([eng], ex)
+            np.save(os.path.join(out_dir, "flags%d_%d.npy" % (rank, it)), eng.flags())
         np.save(os.path.join(out_dir, "flags%d.npy" % rank), eng.flags())
-        np.save(os.path.join(out_dir, "info%d.npy" % rank), np.array([info["published"], info["routed"], info["marks"], ex.bytes_moved]))
+        np.save(os.path.join(out_dir, "info%d.npy" % rank), np.array([info["published"], info["routed"], info["marks"], ex.bytes_moved,
+                                                                      ex.calls["framed"], ex.calls["sized"]]))
     finally:
         dist.destroy_process_group()
 
@@ -138,8 +143,12 @@ def test_orchestration_under_gloo_world2(tmp_path):
     want = oracle.markdup(bam.records, bam.offsets, bam.text)
     got = np.concatenate([np.load(tmp_path / ("flags%d.npy" % r)) for r in range(world)])
     assert np.array_equal(got, want)
+    for it in range(3):
+        got = np.concatenate([np.load(tmp_path / ("flags%d_%d.npy" % (r, it))) for r in range(world)])
+        assert np.array_equal(got, want)
     i0, i1 = np.load(tmp_path / "info0.npy"), np.load(tmp_path / "info1.npy")
     assert np.array_equal(i0[:3], i1[:3]) and i0[0] > 0      # both ranks saw the same exchanged lists
+    assert i0[4] >= 3 and i0[5] >= 4 and np.array_equal(i0[4:], i1[4:])      # framed calls happened; so did the joint fall-backs
 
 
 # ------------------------------------------------------------------------------------------- GPU
