@@ -183,7 +183,7 @@ int oge_gpu_shard_apply(oge_gpu_dedup_ctx *ctx, const void *marks_all_dev, uint6
  * device (no key inversion on [bit_lo, bit_hi), order-independent checksums unchanged). */
 int oge_gpu_debug_sort_bench(int device, uint64_t n, int bit_lo, int bit_hi, int variant, int mode, int reps, uint64_t seed,
                              float *ms_pass_avg, float *ms_sort_avg, int *n_pass, int *verified);
-/* Tuning hook: pass-kernel variant (bit 0: match.any ranking; bit 1: 4096-entry tiles; -1: first-generation kernel). */
+/* Tuning hook: pass-kernel variant (0: 2048-entry tiles of 256 threads; 2: 4096-entry tiles of 512 threads, default). */
 int oge_gpu_set_sort_variant(int variant);
 
 /* Pinned host memory for push/pull buffers. */

@@ -727,8 +727,8 @@ extern "C" int oge_gpu_debug_sort_bench(int device, uint64_t n, int bit_lo, int 
     int rc = radix_sort_init();
     if (rc) return rc;
     const int saved = radix_sort_get_variant();
-    radix_sort_set_variant(variant < 0 ? variant : (variant & 0xFF));
-    radix_sort_set_prefetch(variant < 0 ? 0 : variant >> 8);
+    radix_sort_set_variant(variant & 0xFF);
+    radix_sort_set_prefetch(variant >> 8);
     DevBuf<E128> a, b;
     DevBuf<uint8_t> scratch;
     DevBuf<unsigned long long> chk;
@@ -778,8 +778,8 @@ extern "C" int oge_gpu_debug_sort_bench(int device, uint64_t n, int bit_lo, int 
 }
 
 extern "C" int oge_gpu_set_sort_variant(int variant) {
-    if (variant < -1 || variant > 0xFFFFFF) return fail_msg(OGE_ERR_INVALID_ARG, "set_sort_variant: %d", variant);
-    radix_sort_set_variant(variant < 0 ? variant : (variant & 0xFF));
-    radix_sort_set_prefetch(variant < 0 ? 0 : variant >> 8);
+    if (variant < 0 || variant > 0xFFFFFF) return fail_msg(OGE_ERR_INVALID_ARG, "set_sort_variant: %d", variant);
+    radix_sort_set_variant(variant & 0xFF);
+    radix_sort_set_prefetch(variant >> 8);
     return OGE_OK;
 }

@@ -132,7 +132,7 @@ __device__ bool name_tails_equal(const uint8_t *pa, const uint8_t *pb, uint32_t 
 // ITEMS records per thread, staged so that the dependent chain hash -> slot -> counter -> tags -> ends
 // of one record overlaps with the others': the kernel is bound by memory latency, not bandwidth.
 template <int ITEMS>
-__global__ void __launch_bounds__(JOIN_THREADS) mate_join_kernel(JoinParams P) {
+__global__ void __launch_bounds__(JOIN_THREADS, ITEMS == 1 ? 8 : 4) mate_join_kernel(JoinParams P) {
     const uint64_t i0 = (uint64_t) blockIdx.x * (JOIN_THREADS * ITEMS) + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1;
@@ -151,25 +151,33 @@ __global__ void __launch_bounds__(JOIN_THREADS) mate_join_kernel(JoinParams P) {
         if (h[k]) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(key0[k]) : "l"(&P.table[s[k]].key) : "memory");
     }
 #pragma unroll
-    for (int k = 0; k < ITEMS; k++) {      // claim or find the key's slot (half of the arrivals find their key with the plain read)
+    for (int k = 0; k < ITEMS; k++) {      // claim or find the key's slot and count this arrival
+        old[k] = 0;
         if (!h[k]) continue;
+        const unsigned long long inc = (1ull << 32) + (uint32_t) (i0 + (uint64_t) k * JOIN_THREADS) + 1u;
         unsigned long long key = key0[k];
         while (true) {
-            if (key == h[k]) break;
             if (key == 0) {
-                key = atomicCAS(reinterpret_cast<unsigned long long *>(&P.table[s[k]].key), 0ull, (unsigned long long) h[k]);
-                if (key == 0 || key == h[k]) break;
+                // an empty slot: claim it and count the arrival with ONE 16-byte compare-and-swap of (key, val);
+                // the L2 atomic units are what bounds this kernel, so the first arrival of a name costs one
+                // atomic instead of a claim plus an add
+                unsigned long long ok, ov;
+                asm volatile(
+                    "{\n .reg .b128 cmp, nv, ov;\n mov.b128 cmp, {%2, %3};\n mov.b128 nv, {%4, %5};\n"
+                    " atom.global.relaxed.gpu.cas.b128 ov, [%6], cmp, nv;\n mov.b128 {%0, %1}, ov;\n}\n"
+                    : "=l"(ok), "=l"(ov)
+                    : "l"(0ull), "l"(0ull), "l"((unsigned long long) h[k]), "l"(inc), "l"(&P.table[s[k]])
+                    : "memory");
+                if (ok == 0 && ov == 0) break;      // claimed: first arrival, old[k] stays 0
+                key = ok;                           // somebody was faster: their key is in the slot now
+            }
+            if (key == h[k]) {
+                old[k] = atomicAdd(reinterpret_cast<unsigned long long *>(&P.table[s[k]].val), inc);
+                break;
             }
             if (++s[k] == P.n_slots) s[k] = 0;
             asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(key) : "l"(&P.table[s[k]].key) : "memory");
         }
-    }
-#pragma unroll
-    for (int k = 0; k < ITEMS; k++) {
-        old[k] = 0;
-        if (h[k])
-            old[k] = atomicAdd(reinterpret_cast<unsigned long long *>(&P.table[s[k]].val),
-                               (1ull << 32) + (uint32_t) (i0 + (uint64_t) k * JOIN_THREADS) + 1u);
     }
 
 #pragma unroll

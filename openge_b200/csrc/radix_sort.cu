@@ -8,7 +8,7 @@
 // Structure (one read of the input for all histograms, then one read + one write per pass):
 //   rs_histogram      every pass's 256-bin digit histogram in one sweep (shared-memory bins)
 //   rs_scan           exclusive scan of each histogram -> global digit offsets
-//   rs_onesweep_pass  per 2048-entry tile: 128-bit coalesced loads, warp-private digit counters
+//   rs_pass_v2        per 4096-entry tile: 128-bit coalesced loads, warp-private digit counters
 //                     ranked with match.any, chained-scan (decoupled look-back) across tiles,
 //                     reorder through shared memory, coalesced 128-bit stores
 // The sort is stable per pass (warp-striped tile order + tile-ordered look-back), which LSD needs.
@@ -147,158 +147,15 @@ __device__ __forceinline__ uint32_t match_digit(uint32_t d, int bits) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// One scatter pass.  Dynamic shared memory: [sorted: RS_TILE * 16 B][warp counters: RS_WARPS * 256 * 4 B]
-constexpr size_t PASS_SMEM = (size_t) RS_TILE * sizeof(E128) + (size_t) RS_WARPS * RS_RADIX * 4;
-
-__global__ void __launch_bounds__(RS_THREADS, 4)
-rs_onesweep_pass(const E128 *__restrict__ in, E128 *__restrict__ out, uint32_t n_max, const uint32_t *__restrict__ n_dev,
-                 int shift, int bits, const uint32_t *__restrict__ digit_offset, uint32_t *__restrict__ status,
-                 uint32_t *__restrict__ tile_counter) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    E128 *s_sorted = reinterpret_cast<E128 *>(smem_raw);
-    uint32_t *s_warp_cnt = reinterpret_cast<uint32_t *>(smem_raw + (size_t) RS_TILE * sizeof(E128));
-    __shared__ uint32_t s_tile_base[RS_RADIX];
-    __shared__ long long s_delta[RS_RADIX];
-    __shared__ uint32_t s_scan[RS_WARPS];
-    __shared__ uint32_t s_tile;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t n = n_dev ? min(*n_dev, n_max) : n_max;
-    const uint32_t n_tiles = (n + RS_TILE - 1) / RS_TILE;
-    const uint32_t mask = (1u << bits) - 1;
-
-    // tile ids are handed out in launch order so that every predecessor of a tile is already
-    // running (or done): the look-back below can never wait on a CTA that has not started
-    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
-    for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) s_warp_cnt[i] = 0;
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    if (tile >= n_tiles) return;
-    const uint32_t base = tile * RS_TILE;
-
-    // ---- load: warp-striped, 16 B per lane, 512 B contiguous per warp instruction
-    E128 e[RS_ITEMS];
-    const uint32_t wbase = base + warp * (32 * RS_ITEMS) + lane;
-#pragma unroll
-    for (int k = 0; k < RS_ITEMS; k++) {
-        uint32_t i = wbase + k * 32;
-        if (i < n) e[k] = ld_entry(in + i);
-    }
-
-    // ---- rank inside the warp: match.any groups equal digits; the group's highest lane owns the
-    //      warp-private counter update, so no atomics are needed
-    uint32_t rank[RS_ITEMS];
-    uint32_t *wc = s_warp_cnt + warp * RS_RADIX;
-    const uint32_t lt_mask = (1u << lane) - 1;
-#pragma unroll
-    for (int k = 0; k < RS_ITEMS; k++) {
-        uint32_t d = (wbase + k * 32 < n) ? digit_of(e[k], shift, mask) : 0xFFFFFFFFu;
-        uint32_t peers = match_digit(d, bits);
-        int leader = 31 - __clz(peers);
-        uint32_t old = 0;
-        if (lane == leader && d != 0xFFFFFFFFu) {
-            old = wc[d];
-            wc[d] = old + __popc(peers);
-        }
-        old = __shfl_sync(0xFFFFFFFFu, old, leader);
-        rank[k] = old + __popc(peers & lt_mask);
-        __syncwarp();
-    }
-    __syncthreads();
-
-    // ---- per digit: exclusive scan over warps, tile total, publish, block scan, look-back
-    uint32_t total = 0;
-    if (tid < RS_RADIX) {
-#pragma unroll
-        for (int w = 0; w < RS_WARPS; w++) {
-            uint32_t c = s_warp_cnt[w * RS_RADIX + tid];
-            s_warp_cnt[w * RS_RADIX + tid] = total;
-            total += c;
-        }
-        uint32_t word = (tile == 0 ? LB_FLAG_INC : LB_FLAG_AGG) | total;
-        asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(status + (size_t) tile * RS_RADIX + tid), "r"(word) : "memory");
-    }
-    // block-wide exclusive scan of `total` over the 256 digit threads (other threads carry 0)
-    uint32_t x = total;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
-        if (lane >= o) x += y;
-    }
-    if (lane == 31) s_scan[warp] = x;
-    __syncthreads();
-    if (tid < RS_RADIX) {
-        uint32_t wprefix = 0;
-        for (int i = 0; i < warp; i++) wprefix += s_scan[i];
-        uint32_t tile_base = wprefix + x - total;
-
-        uint32_t excl = 0;
-        if (tile > 0) {
-            // decoupled look-back, LB_WINDOW predecessors per round trip: the status words of
-            // tiles t-1 .. t-W are independent loads, so the chain costs one L2 latency per W tiles
-            long long p = (long long) tile - 1;
-            bool done = false;
-            while (!done) {
-                uint32_t s[LB_WINDOW];
-#pragma unroll
-                for (int j = 0; j < LB_WINDOW; j++) {
-                    long long q = p - j;
-                    s[j] = 0;
-                    if (q >= 0)
-                        asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(s[j]) : "l"(status + (size_t) q * RS_RADIX + tid) : "memory");
-                }
-#pragma unroll
-                for (int j = 0; j < LB_WINDOW; j++) {
-                    if (done) break;
-                    uint32_t f = s[j] >> 30;
-                    if (f == 0) break;          // not published yet: poll again from this tile
-                    excl += s[j] & LB_VALUE_MASK;
-                    p--;
-                    if (f == 2) done = true;
-                }
-            }
-            uint32_t word = LB_FLAG_INC | (excl + total);
-            asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(status + (size_t) tile * RS_RADIX + tid), "r"(word) : "memory");
-        }
-        s_tile_base[tid] = tile_base;
-        s_delta[tid] = (long long) digit_offset[tid] + (long long) excl - (long long) tile_base;
-    }
-    __syncthreads();
-
-    // ---- reorder through shared memory
-#pragma unroll
-    for (int k = 0; k < RS_ITEMS; k++) {
-        if (wbase + k * 32 < n) {
-            uint32_t d = digit_of(e[k], shift, mask);
-            uint32_t pos = s_tile_base[d] + wc[d] + rank[k];
-            st_entry(s_sorted + pos, e[k]);
-        }
-    }
-    __syncthreads();
-
-    // ---- store: consecutive threads write consecutive sorted slots; runs of one digit are
-    //      contiguous in the output
-    const uint32_t count = min((uint32_t) RS_TILE, n - base);
-#pragma unroll
-    for (int k = 0; k < RS_ITEMS; k++) {
-        uint32_t j = k * RS_THREADS + tid;
-        if (j < count) {
-            E128 v = s_sorted[j];
-            uint32_t d = digit_of(v, shift, mask);
-            st_entry(out + (long long) j + s_delta[d], v);
-        }
-    }
-}
-
-
-// ------------------------------------------------------------------------------------------------
-// Second-generation pass kernel.  The first one was issue-bound (ncu: 60 % issue slots busy, ~2000
+// The pass kernel (second generation; the first one, one 2048-entry tile per 256-thread CTA with 128-bit variable
+// shifts, is in the history of this file and in profiles/r1_first_generation_kernels.txt).  It was issue-bound (ncu: 60 % issue slots busy, ~2000
 // warp instructions per warp and tile, dram at 25 %), so this one is written for instruction count:
 //   * the digit comes out of a 32-bit word pair chosen at compile time (WORD = shift / 32):
 //     one funnel shift + one AND instead of a 128-bit variable shift, and it is computed once
 //   * full tiles take a path without any bounds predicate
-//   * the warp ranking is either eight ballots or one match.any per entry (MATCH); the group
-//     leader bumps the warp-private counter with a single shared-memory atomic
+//   * the warp ranking is eight ballots per entry (one match.any per entry was measured: 2.55 vs 3.07 TB/s,
+//     profiles/r1_sort_variants_ab.json); the group leader bumps the warp-private counter with a single
+//     shared-memory atomic
 //   * 32-bit scatter deltas
 //   * THREADS = 256 or 512: tile = THREADS * 8 entries; a larger tile halves the look-backs per
 //     entry and doubles the length of the contiguous runs written to HBM
@@ -313,9 +170,7 @@ __device__ __forceinline__ uint32_t digit_word(const E128 &e, int sh, uint32_t m
 }
 
 // lanes of the warp holding the same 8-bit digit (all lanes valid)
-template <int MATCH>
 __device__ __forceinline__ uint32_t peers_of(uint32_t d) {
-    if (MATCH) return __match_any_sync(0xFFFFFFFFu, d);
     uint32_t peers = 0xFFFFFFFFu;
 #pragma unroll
     for (int b = 0; b < RS_RADIX_BITS; b++) {
@@ -337,7 +192,7 @@ struct PassCfg {
     static constexpr int CTAS_PER_SM = THREADS == 256 ? 4 : 2;
 };
 
-template <int THREADS, int WORD, int MATCH>
+template <int THREADS, int WORD>
 __global__ void __launch_bounds__(THREADS, PassCfg<THREADS>::CTAS_PER_SM)
 rs_pass_v2(const E128 *__restrict__ in, E128 *__restrict__ out, uint32_t n_max, const uint32_t *__restrict__ n_dev, int shift,
            int bits, const uint32_t *__restrict__ digit_offset, uint32_t *__restrict__ status, uint32_t *__restrict__ status_next,
@@ -411,7 +266,7 @@ rs_pass_v2(const E128 *__restrict__ in, E128 *__restrict__ out, uint32_t n_max, 
 #pragma unroll
     for (int k = 0; k < RS_ITEMS; k++) {
         uint32_t peers;
-        if (MATCH || full) peers = peers_of<MATCH>(d[k]);
+        if (full) peers = peers_of(d[k]);
         else peers = match_digit(d[k], RS_RADIX_BITS);
         const int leader = 31 - __clz(peers);
         uint32_t old = 0;
@@ -516,43 +371,40 @@ rs_pass_v2(const E128 *__restrict__ in, E128 *__restrict__ out, uint32_t n_max, 
     }
 }
 
-// variant: bit 0 = match.any ranking, bit 1 = 512-thread tiles; -1 = the first-generation kernel
+// variant: 0 = 256-thread CTAs (2048-entry tiles), 2 = 512-thread CTAs (4096-entry tiles, default)
 static int g_sort_variant = 2;
 static int g_sort_prefetch = 0;      // tiles ahead (0 = one wave)
 void radix_sort_set_prefetch(int tiles) { g_sort_prefetch = tiles; }
 void radix_sort_set_variant(int v) { g_sort_variant = v; }
 int radix_sort_get_variant() { return g_sort_variant; }
 
-template <int THREADS, int MATCH>
+template <int THREADS>
 static cudaError_t launch_pass_v2(int word, uint32_t grid, cudaStream_t stream, const E128 *src, E128 *dst, uint32_t n,
                                   const uint32_t *n_dev, int shift, int bits, const uint32_t *goff, uint32_t *status, uint32_t *status_next, uint32_t *tc,
                                   int dbg) {
     const size_t smem = PassCfg<THREADS>::SMEM;
     switch (word) {
-        case 0: rs_pass_v2<THREADS, 0, MATCH><<<grid, THREADS, smem, stream>>>(src, dst, n, n_dev, shift, bits, goff, status, status_next, tc, dbg); break;
-        case 1: rs_pass_v2<THREADS, 1, MATCH><<<grid, THREADS, smem, stream>>>(src, dst, n, n_dev, shift, bits, goff, status, status_next, tc, dbg); break;
-        case 2: rs_pass_v2<THREADS, 2, MATCH><<<grid, THREADS, smem, stream>>>(src, dst, n, n_dev, shift, bits, goff, status, status_next, tc, dbg); break;
-        default: rs_pass_v2<THREADS, 3, MATCH><<<grid, THREADS, smem, stream>>>(src, dst, n, n_dev, shift, bits, goff, status, status_next, tc, dbg); break;
+        case 0: rs_pass_v2<THREADS, 0><<<grid, THREADS, smem, stream>>>(src, dst, n, n_dev, shift, bits, goff, status, status_next, tc, dbg); break;
+        case 1: rs_pass_v2<THREADS, 1><<<grid, THREADS, smem, stream>>>(src, dst, n, n_dev, shift, bits, goff, status, status_next, tc, dbg); break;
+        case 2: rs_pass_v2<THREADS, 2><<<grid, THREADS, smem, stream>>>(src, dst, n, n_dev, shift, bits, goff, status, status_next, tc, dbg); break;
+        default: rs_pass_v2<THREADS, 3><<<grid, THREADS, smem, stream>>>(src, dst, n, n_dev, shift, bits, goff, status, status_next, tc, dbg); break;
     }
     return cudaGetLastError();
 }
 
-template <int THREADS, int MATCH>
+template <int THREADS>
 static cudaError_t init_pass_v2() {
     const int smem = (int) PassCfg<THREADS>::SMEM;
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(rs_pass_v2<THREADS, 0, MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(rs_pass_v2<THREADS, 1, MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(rs_pass_v2<THREADS, 2, MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-    return cudaFuncSetAttribute(rs_pass_v2<THREADS, 3, MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if ((e = cudaFuncSetAttribute(rs_pass_v2<THREADS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(rs_pass_v2<THREADS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(rs_pass_v2<THREADS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(rs_pass_v2<THREADS, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
 int radix_sort_init() {
-    OGE_CUDA_TRY(cudaFuncSetAttribute(rs_onesweep_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) PASS_SMEM));
-    OGE_CUDA_TRY((init_pass_v2<256, 0>()));
-    OGE_CUDA_TRY((init_pass_v2<256, 1>()));
-    OGE_CUDA_TRY((init_pass_v2<512, 0>()));
-    OGE_CUDA_TRY((init_pass_v2<512, 1>()));
+    OGE_CUDA_TRY((init_pass_v2<256>()));
+    OGE_CUDA_TRY((init_pass_v2<512>()));
     return 0;
 }
 
@@ -580,30 +432,23 @@ int radix_sort_128(E128 *a, E128 *b, uint64_t n, const uint32_t *n_dev, int bit_
 
     E128 *src = a, *dst = b;
     // dbg bits 0-2 are measurement knobs (bits 0, 1 give wrong results); bits 8.. = prefetch distance in tiles
-    int dbg = g_sort_variant >= 0 ? ((g_sort_variant >> 4) & 15) : 0;
-    const int variant = g_sort_variant >= 0 ? (g_sort_variant & 15) : -1;
-    const uint64_t vtiles = variant >= 0 && (variant & 2) ? (n + PassCfg<512>::TILE - 1) / PassCfg<512>::TILE : tiles;
+    int dbg = (g_sort_variant >> 4) & 15;
+    const int variant = g_sort_variant & 2;
+    const uint64_t vtiles = variant ? (n + PassCfg<512>::TILE - 1) / PassCfg<512>::TILE : tiles;
     {
-        int pf = g_sort_prefetch > 0 ? g_sort_prefetch : sms * (variant >= 0 && (variant & 2) ? 2 : 4);
+        int pf = g_sort_prefetch > 0 ? g_sort_prefetch : sms * (variant ? 2 : 4);
         dbg |= pf << 8;
     }
     for (int p = 0; p < plan.n_pass; p++) {
         uint32_t *st = status + (size_t) (p & 1) * tiles * RS_RADIX, *st_next = status + (size_t) ((p + 1) & 1) * tiles * RS_RADIX;
-        if (p == 0 || variant < 0) OGE_CUDA_TRY(cudaMemsetAsync(st, 0, (size_t) tiles * RS_RADIX * 4, stream));
+        if (p == 0) OGE_CUDA_TRY(cudaMemsetAsync(st, 0, (size_t) tiles * RS_RADIX * 4, stream));
         const bool timed = timer && timer->used < timer->cap;
         if (timed) cudaEventRecord(timer->pool[2 * timer->used], stream);
         const int shift = plan.shift[p], bits = plan.bits[p];
         uint32_t *tc = tile_counters + p;
         const uint32_t *go = goff + p * RS_RADIX;
-        switch (variant) {
-            case 0: OGE_CUDA_TRY((launch_pass_v2<256, 0>(shift >> 5, (uint32_t) vtiles, stream, src, dst, (uint32_t) n, n_dev, shift, bits, go, st, st_next, tc, dbg))); break;
-            case 1: OGE_CUDA_TRY((launch_pass_v2<256, 1>(shift >> 5, (uint32_t) vtiles, stream, src, dst, (uint32_t) n, n_dev, shift, bits, go, st, st_next, tc, dbg))); break;
-            case 2: OGE_CUDA_TRY((launch_pass_v2<512, 0>(shift >> 5, (uint32_t) vtiles, stream, src, dst, (uint32_t) n, n_dev, shift, bits, go, st, st_next, tc, dbg))); break;
-            case 3: OGE_CUDA_TRY((launch_pass_v2<512, 1>(shift >> 5, (uint32_t) vtiles, stream, src, dst, (uint32_t) n, n_dev, shift, bits, go, st, st_next, tc, dbg))); break;
-            default:
-                rs_onesweep_pass<<<(uint32_t) tiles, RS_THREADS, PASS_SMEM, stream>>>(src, dst, (uint32_t) n, n_dev, shift, bits, go, st, tc);
-                break;
-        }
+        if (variant) OGE_CUDA_TRY((launch_pass_v2<512>(shift >> 5, (uint32_t) vtiles, stream, src, dst, (uint32_t) n, n_dev, shift, bits, go, st, st_next, tc, dbg)));
+        else OGE_CUDA_TRY((launch_pass_v2<256>(shift >> 5, (uint32_t) vtiles, stream, src, dst, (uint32_t) n, n_dev, shift, bits, go, st, st_next, tc, dbg)));
         if (timed) {
             cudaEventRecord(timer->pool[2 * timer->used + 1], stream);
             timer->used++;

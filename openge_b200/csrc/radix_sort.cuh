@@ -40,8 +40,8 @@ int radix_sort_128(E128 *a, E128 *b, uint64_t n, const uint32_t *n_dev, int bit_
 
 int radix_sort_init();   // one-time function attributes
 
-// Pass-kernel variant (tuning / A-B measurement): bit 0 = match.any ranking instead of ballots,
-// bit 1 = 512-thread CTAs (4096-entry tiles); -1 = first-generation kernel.
+// Pass-kernel variant (tuning / A-B measurement): 0 = 256-thread CTAs (2048-entry tiles), 2 = 512-thread CTAs
+// (4096-entry tiles, the default); bits 4-6 are measurement knobs (radix_sort.cu), bits 8.. the L2 prefetch distance.
 void radix_sort_set_variant(int v);
 int radix_sort_get_variant();
 void radix_sort_set_prefetch(int tiles);

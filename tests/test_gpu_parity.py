@@ -41,7 +41,7 @@ def test_radix_sort_matches_numpy(n, lo, hi):
     assert all(k_out[i] <= k_out[i + 1] for i in range(n - 1))
 
 
-@pytest.mark.parametrize("variant", [-1, 0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 2])
 @pytest.mark.parametrize("n,lo,hi", [(2048, 0, 8), (4099, 30, 41), (1_000_003, 42, 112)])
 def test_radix_sort_variants_stable(variant, n, lo, hi):
     """Every pass-kernel variant is a stable sort on the bit range (LSD needs per-pass stability)."""
@@ -64,7 +64,7 @@ def test_radix_sort_variants_stable(variant, n, lo, hi):
     assert np.array_equal(out, e[order])
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 2])
 def test_sort_bench_hook_verifies(variant):
     r = dedup.debug_sort_bench(3_000_001, 43, 79, variant=variant, mode=1, reps=1)
     assert r["verified"] and r["passes"] == 5

@@ -8,7 +8,7 @@ sys.path.insert(0, ROOT)
 from openge_b200 import dedup  # noqa: E402
 
 out = []
-variants = [int(v) for v in (sys.argv[1].split(",") if len(sys.argv) > 1 else "-1,0,1,2,3".split(","))]
+variants = [int(v) for v in (sys.argv[1].split(",") if len(sys.argv) > 1 else "0,2".split(","))]
 for n, lo, hi in [(25_000_000, 42, 112), (50_000_000, 43, 79)]:
     for mode in (0, 1):
         for v in variants:
