@@ -51,6 +51,24 @@ def gpu_sources():
     return out
 
 
+class _BuildLock:
+    """One builder at a time (several ranks of one torchrun may import the package together)."""
+
+    def __init__(self, path):
+        self.path = path
+
+    def __enter__(self):
+        import fcntl
+        self.f = open(self.path, "w")
+        fcntl.flock(self.f, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *a):
+        import fcntl
+        fcntl.flock(self.f, fcntl.LOCK_UN)
+        self.f.close()
+
+
 def build_gpu(force=False, verbose=False):
     srcs = gpu_sources()
     cu = [s for s in srcs if s.endswith(".cu")]
@@ -59,13 +77,16 @@ def build_gpu(force=False, verbose=False):
             if os.path.exists(GPU_LIB):
                 return GPU_LIB
             raise RuntimeError("nvcc not found and %s is missing" % GPU_LIB)
-        flags = list(NVCC_FLAGS) + os.environ.get("OGE_NVCC_EXTRA", "").split()
-        if verbose:
-            flags += ["-Xptxas", "-v"]
-        out = _run(["nvcc"] + flags + ["-I", os.path.join(ROOT, "include"), "-I", CSRC] + cu +
-                   ["-o", GPU_LIB, "-lcudart"])
-        if verbose:
-            print(out)
+        with _BuildLock(GPU_LIB + ".lock"):
+            if force or _stale(GPU_LIB, srcs):      # somebody else may have built it while we waited
+                flags = list(NVCC_FLAGS) + os.environ.get("OGE_NVCC_EXTRA", "").split()
+                if verbose:
+                    flags += ["-Xptxas", "-v"]
+                tmp = GPU_LIB + ".tmp.%d" % os.getpid()
+                out = _run(["nvcc"] + flags + ["-I", os.path.join(ROOT, "include"), "-I", CSRC] + cu + ["-o", tmp, "-lcudart"])
+                os.replace(tmp, GPU_LIB)      # readers never see a half-written library
+                if verbose:
+                    print(out)
     return GPU_LIB
 
 
