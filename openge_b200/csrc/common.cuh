@@ -109,6 +109,7 @@ enum {
     CNT_FOREIGN_MARKS_FRAG,
     CNT_SCRATCH0,
     CNT_SCRATCH1,
+    CNT_SCRATCH2,
     CNT_N = 32
 };
 

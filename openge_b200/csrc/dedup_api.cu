@@ -465,8 +465,8 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
         OGE_CUDA_TRY(cudaMemsetAsync(c->uset.p, 0, n_slots * 8, s));
         OGE_CUDA_TRY(cudaMemsetAsync(c->counters.p + CNT_UFRAG, 0, 4, s));
         if ((rc = launch_ff_collect(c->frag.p, n, c->kl, c->ufrag.p, (uint32_t) ucap, c->counters.p, s, &launches))) return rc;
-        if ((rc = launch_ff_set_build(c->ufrag.p, c->counters.p + CNT_UFRAG, (uint32_t) n_unp, c->kl, c->uset.p, n_slots, s, &launches))) return rc;
-        if ((rc = launch_ff_filter(c->frag.p, n, c->kl, c->uset.p, n_slots, c->ufrag.p, (uint32_t) ucap, c->counters.p, s, &launches))) return rc;
+        if ((rc = launch_ff_set_build(c->ufrag.p, c->counters.p + CNT_UFRAG, (uint32_t) std::min(n_unp, ucap), c->kl, c->uset.p, n_slots, s, &launches))) return rc;
+        if ((rc = launch_ff_filter(c->frag.p, n, c->kl, c->uset.p, n_slots, c->ufrag.p, (uint32_t) ucap, c->counters.p, nullptr, s, &launches))) return rc;
         OGE_CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, s));
         OGE_CUDA_TRY(cudaStreamSynchronize(s));
         n_fsel = c->h_counters[CNT_UFRAG];

@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(FF_THREADS) ff_set_build_kernel(const E128 *__
 
 __global__ void __launch_bounds__(FF_THREADS) ff_filter_kernel(const E128 *__restrict__ frag, uint64_t n, KeyLayout L,
                                                                const unsigned long long *__restrict__ set, uint64_t mask, E128 *__restrict__ out,
-                                                               uint32_t cap, uint32_t *__restrict__ counters) {
+                                                               uint32_t cap, uint32_t *__restrict__ counters, const uint32_t *__restrict__ n_set) {
+    if (n_set && *n_set == 0) return;      // no unpaired end anywhere: nothing can share a key with one
     const uint64_t i = (uint64_t) blockIdx.x * FF_THREADS + threadIdx.x;
     bool want = false;
     E128 e;
@@ -117,9 +118,9 @@ int launch_ff_set_build(const E128 *list, const uint32_t *n_dev, uint32_t n_max,
     return 0;
 }
 int launch_ff_filter(const E128 *frag, uint64_t n, const KeyLayout &L, const unsigned long long *set, uint64_t n_slots, E128 *out, uint32_t cap,
-                     uint32_t *counters, cudaStream_t s, uint64_t *launches) {
+                     uint32_t *counters, const uint32_t *n_set, cudaStream_t s, uint64_t *launches) {
     if (!n) return 0;
-    ff_filter_kernel<<<ff_grid(n), FF_THREADS, 0, s>>>(frag, n, L, set, n_slots - 1, out, cap, counters);
+    ff_filter_kernel<<<ff_grid(n), FF_THREADS, 0, s>>>(frag, n, L, set, n_slots - 1, out, cap, counters, n_set);
     *launches += 1;
     OGE_CUDA_TRY(cudaGetLastError());
     return 0;

@@ -114,7 +114,7 @@ int launch_ff_collect(const E128 *frag, uint64_t n, const KeyLayout &L, E128 *ou
 int launch_ff_set_build(const E128 *list, const uint32_t *n_dev, uint32_t n_max, const KeyLayout &L, unsigned long long *set, uint64_t n_slots,
                         cudaStream_t s, uint64_t *launches);
 int launch_ff_filter(const E128 *frag, uint64_t n, const KeyLayout &L, const unsigned long long *set, uint64_t n_slots, E128 *out, uint32_t cap,
-                     uint32_t *counters, cudaStream_t s, uint64_t *launches);
+                     uint32_t *counters, const uint32_t *n_set /* device: entries in the set, or null */, cudaStream_t s, uint64_t *launches);
 
 // ---- K5 flag write (flags.cu) -----------------------------------------------------------------
 struct FlagParams {

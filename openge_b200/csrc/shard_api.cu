@@ -362,12 +362,15 @@ int oge_gpu_shard_probe(oge_gpu_dedup_ctx *c, const void *pub_all_dev, uint64_t 
             // notices and falls back to the full sort)
             OGE_CUDA_TRY(cudaMemsetAsync(c->uset.p, 0, sh.uset_slots * 8, s2));
             OGE_CUDA_TRY(cudaMemsetAsync(c->counters.p + CNT_UFRAG, 0, 4, s2));
-            if ((rc = launch_ff_collect(c->frag.p, n_all_frag, c->kl, c->ufrag.p, (uint32_t) sh.ucap, c->counters.p, s2, &launches))) return rc;
+            // unpaired ends: the local ones (none on clean paired-end data: the host knows from K1) and the routed copies
+            if (sh.n_unpaired && (rc = launch_ff_collect(c->frag.p, n, c->kl, c->ufrag.p, (uint32_t) sh.ucap, c->counters.p, s2, &launches))) return rc;
+            if ((rc = launch_ff_collect(c->frag.p + n, n_fr_all, c->kl, c->ufrag.p, (uint32_t) sh.ucap, c->counters.p, s2, &launches))) return rc;
+            OGE_CUDA_TRY(cudaMemcpyAsync(c->counters.p + CNT_SCRATCH2, c->counters.p + CNT_UFRAG, 4, cudaMemcpyDeviceToDevice, s2));      // size of the set
             if ((rc = launch_ff_set_build(c->ufrag.p, c->counters.p + CNT_UFRAG, (uint32_t) std::min<uint64_t>(sh.n_unpaired + n_fr_all, sh.ucap),
                                           c->kl, c->uset.p, sh.uset_slots, s2, &launches)))
                 return rc;
-            if ((rc = launch_ff_filter(c->frag.p, n_all_frag, c->kl, c->uset.p, sh.uset_slots, c->ufrag.p, (uint32_t) sh.ucap, c->counters.p, s2,
-                                       &launches)))
+            if ((rc = launch_ff_filter(c->frag.p, n_all_frag, c->kl, c->uset.p, sh.uset_slots, c->ufrag.p, (uint32_t) sh.ucap, c->counters.p,
+                                       c->counters.p + CNT_SCRATCH2, s2, &launches)))
                 return rc;
             sh_fit_counter_kernel<<<1, 1, 0, s2>>>(c->counters.p + CNT_FRAG_VALID, c->counters.p + CNT_UFRAG, (uint32_t) sh.ucap);
             if ((rc = radix_sort_128(c->ufrag.p, c->ufrag2.p, sh.ucap, c->counters.p + CNT_FRAG_VALID, c->kl.f_orient, c->kl.f_end, sh.scratch2.p,
