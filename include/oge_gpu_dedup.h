@@ -141,6 +141,10 @@ int oge_gpu_dedup_reset(oge_gpu_dedup_ctx *ctx);
 int oge_gpu_dedup_get_stats(oge_gpu_dedup_ctx *ctx, oge_gpu_dedup_stats *out);
 int oge_gpu_dedup_debug_ends(oge_gpu_dedup_ctx *ctx, oge_gpu_end *out, uint64_t n);
 
+/* Device-to-device copy on the context's stream, completed on return: how a caller takes a list that one of the
+ * oge_gpu_shard_* calls handed out (valid only until the next call) into its own exchange buffer. */
+int oge_gpu_copy_d2d(oge_gpu_dedup_ctx *ctx, void *dst, const void *src, uint64_t nbytes);
+
 /* Device pointers of the resident arrays, for callers that keep working on the GPU
  * (and for bench.py's device-resident timing): records, offsets (u64, n+1), flags (u16, n). */
 int oge_gpu_dedup_device_ptrs(oge_gpu_dedup_ctx *ctx, void **records, void **offsets, void **flags);

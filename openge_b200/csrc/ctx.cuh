@@ -53,7 +53,7 @@ struct ShardState {
     DevBuf<RouteEntry> route, froute;
     DevBuf<uint32_t> marks, marks_frag, pub_list;
     DevBuf<uint8_t> scratch2;             // sort scratch of the side stream
-    cudaEvent_t ev_main = nullptr, ev_side[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_main = nullptr, ev_far = nullptr, ev_side[3] = {nullptr, nullptr, nullptr};
     bool frag_busy = false, frag_ran = false;
     int frag_mode = 2;                    // 0 nothing, 1 reduced fragment pass, 2 every fragment end
     uint64_t n_unpaired = 0, ucap = 0, uset_slots = 0;

@@ -198,6 +198,7 @@ int oge_gpu_dedup_create(const oge_gpu_dedup_config *cfg, oge_gpu_dedup_ctx **ou
             cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&c->sh.ev_main, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->sh.ev_far, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreate(&c->sh.ev_side[0]) != cudaSuccess || cudaEventCreate(&c->sh.ev_side[1]) != cudaSuccess ||
             cudaEventCreate(&c->sh.ev_side[2]) != cudaSuccess ||
             cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming) != cudaSuccess) {
@@ -243,6 +244,7 @@ void oge_gpu_dedup_destroy(oge_gpu_dedup_ctx *c) {
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
     if (c->sh.ev_main) cudaEventDestroy(c->sh.ev_main);
+    if (c->sh.ev_far) cudaEventDestroy(c->sh.ev_far);
     for (auto &e : c->sh.ev_side) if (e) cudaEventDestroy(e);
     c->sh.d_split.release(); c->sh.pub.release(); c->sh.pub2.release(); c->sh.route.release(); c->sh.froute.release();
     c->sh.marks.release(); c->sh.marks_frag.release(); c->sh.pub_list.release(); c->sh.fm.release(); c->sh.fm_sort.release();
@@ -643,6 +645,15 @@ int oge_gpu_debug_sort128(int device, void *entries, uint64_t n, int bit_lo, int
     if (!rc && cudaMemcpy(entries, res, n * sizeof(E128), cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail_cuda(cudaGetLastError(), "sort d2h", __FILE__, __LINE__);
     a.release(); b.release(); scratch.release();
     return rc;
+}
+
+int oge_gpu_copy_d2d(oge_gpu_dedup_ctx *c, void *dst, const void *src, uint64_t nbytes) {
+    if (!c || (nbytes && (!dst || !src))) return fail_msg(OGE_ERR_INVALID_ARG, "copy_d2d: null argument");
+    if (!nbytes) return OGE_OK;
+    OGE_CUDA_TRY(cudaSetDevice(c->cfg.device));
+    OGE_CUDA_TRY(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, c->stream));
+    OGE_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return OGE_OK;
 }
 
 int oge_gpu_dedup_device_ptrs(oge_gpu_dedup_ctx *c, void **records, void **offsets, void **flags) {

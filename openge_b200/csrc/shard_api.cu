@@ -201,6 +201,8 @@ int oge_gpu_shard_begin(oge_gpu_dedup_ctx *c, void **pub_dev, uint64_t *n_pub, v
     OGE_CUDA_TRY(cudaStreamWaitEvent(s, c->copy_done, 0));
     sh.n_frag = sh.n_pe = sh.n_pairs = sh.n_retracted = sh.n_far = sh.n_far_dead = sh.n_slots = sh.n_fm = sh.n_froute_all = sh.n_unpaired = 0;
     sh.frag_mode = 0;
+    sh.side_pass_used = 0;
+    sh.side_pass_bytes = 0;
     OGE_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, CNT_N * 4, s));
     uint64_t n_fr = 0;
     if (n) {
@@ -326,7 +328,7 @@ int oge_gpu_shard_probe(oge_gpu_dedup_ctx *c, const void *pub_all_dev, uint64_t 
         if ((rc = c->frag.reserve(n_all_frag, true, s))) return rc;
         if (sh.frag_mode == 2) {
             if ((rc = c->sortbuf.reserve(n_all_frag, false, s))) return rc;
-            if ((rc = sh.scratch2.reserve(sort_scratch_bytes(n_all_frag), false, s))) return rc;
+            if ((rc = sh.scratch2.reserve(sort_scratch_bytes(std::max<uint64_t>(n_all_frag, sh.n_pe / 2 + n_all + 1024)), false, s))) return rc;
         } else {
             uint64_t n_slots = 1024;
             while (n_slots < 4 * (sh.n_unpaired + n_fr_all)) n_slots <<= 1;
@@ -334,7 +336,7 @@ int oge_gpu_shard_probe(oge_gpu_dedup_ctx *c, const void *pub_all_dev, uint64_t 
             if ((rc = c->ufrag.reserve(sh.ucap, false, s))) return rc;
             if ((rc = c->ufrag2.reserve(sh.ucap, false, s))) return rc;
             if ((rc = c->uset.reserve(n_slots, false, s))) return rc;
-            if ((rc = sh.scratch2.reserve(sort_scratch_bytes(sh.ucap), false, s))) return rc;
+            if ((rc = sh.scratch2.reserve(sort_scratch_bytes(std::max<uint64_t>(sh.ucap, sh.n_pe / 2 + n_all + 1024)), false, s))) return rc;
         }
         if ((rc = sh.marks_frag.reserve(n_fr_all + 16, false, s))) return rc;
         if (n == 0 && (rc = c->mate_of.reserve(1, false, s))) return rc;
@@ -487,10 +489,38 @@ int oge_gpu_shard_finish(oge_gpu_dedup_ctx *c, const void *w_dev, uint64_t n_w, 
     sp.fm = sh.fm.p; sp.n_fm = (uint32_t) sh.n_fm; sp.foreign_marks = sh.marks.p; sp.foreign_cap = (uint32_t) sh.marks.cap;
     sp.foreign_counter = c->counters.p + CNT_FOREIGN_MARKS;
     sp.split = sh.d_split.p; sp.world = c->cfg.world; sp.rank = c->cfg.rank;
-    for (int far = 0; far < 2; far++) {      // near pairs (short key), then far pairs
+    // far pairs (cross-contig / huge inserts: a short list, 9 launch-bound passes) go to the side stream, behind
+    // whatever fragment work is still queued there, and run concurrently with the near-pair sort
+    bool far_on_side = false;
+    if (sh.n_far) {
+        const size_t need = sort_scratch_bytes(sh.n_far);
+        if (sh.scratch2.cap >= need || !sh.frag_busy) {
+            if (sh.scratch2.cap < need && (rc = sh.scratch2.reserve(need, false, s))) return rc;
+            far_on_side = true;
+        }
+    }
+    for (int far = 1; far >= 0; far--) {      // far pairs first (queued on the side stream), then near pairs (short key)
         const uint64_t cnt = far ? sh.n_far : sh.n_pairs, dead = far ? sh.n_far_dead : sh.n_retracted;
         if (!cnt) continue;
+        const bool side = far && far_on_side;
+        cudaStream_t st = side ? c->side_stream : s;
         E128 *a = far ? c->pairf.p : c->pair.p, *b = far ? c->pairf2.p : c->pair2.p, *sorted = a;
+        if (side) {
+            OGE_CUDA_TRY(cudaEventRecord(sh.ev_main, s));      // the lists, the mate table and the foreign mates are final
+            OGE_CUDA_TRY(cudaStreamWaitEvent(st, sh.ev_main, 0));
+            PassTimer timer3{c->pass_ev + 48 + 2 * sh.side_pass_used, 24 - sh.side_pass_used, 0, 0};
+            if ((rc = radix_sort_128(a, b, cnt, nullptr, c->kl.p_coord2, c->kl.p_end, sh.scratch2.p, st, &sorted, &launches,
+                                     c->cfg.profile_events ? &timer3 : nullptr)))
+                return rc;
+            sh.side_pass_used += timer3.used;
+            sh.side_pass_bytes += timer3.bytes;
+            if (cnt > dead) {
+                sp.sorted = sorted; sp.n_max = (uint32_t) (cnt - dead);
+                if ((rc = launch_select_pairs(sp, true, st, &launches))) return rc;
+            }
+            OGE_CUDA_TRY(cudaEventRecord(sh.ev_far, st));
+            continue;
+        }
         {
             PhaseClock clk(c, &c->stats.ms_sort_pair);
             if ((rc = radix_sort_128(a, b, cnt, nullptr, far ? c->kl.p_coord2 : c->kl.n_delta, c->kl.p_end, c->scratch.p, s, &sorted, &launches, tp)))
@@ -503,6 +533,11 @@ int oge_gpu_shard_finish(oge_gpu_dedup_ctx *c, const void *w_dev, uint64_t n_w, 
             if ((rc = launch_select_pairs(sp, far != 0, s, &launches))) return rc;
             clk.stop();
         }
+    }
+    if (far_on_side) {
+        PhaseClock clk(c, &c->stats.ms_sort_pair);      // whatever of the far-pair work the near-pair work did not hide
+        OGE_CUDA_TRY(cudaStreamWaitEvent(s, sh.ev_far, 0));
+        clk.stop();
     }
     // ---- join the side stream: the fragment verdicts
     uint64_t extra = 0;

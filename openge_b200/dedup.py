@@ -58,7 +58,7 @@ EXPORTS = ["oge_gpu_dedup_create", "oge_gpu_dedup_destroy", "oge_gpu_dedup_set_r
            "oge_gpu_dedup_device_ptrs", "oge_gpu_host_alloc", "oge_gpu_host_free", "oge_gpu_device_count",
            "oge_gpu_last_error", "oge_gpu_abi_version", "oge_gpu_debug_sort128", "oge_gpu_debug_sort_bench",
            "oge_gpu_set_sort_variant", "oge_gpu_shard_setup", "oge_gpu_shard_begin", "oge_gpu_shard_probe",
-           "oge_gpu_shard_finish", "oge_gpu_shard_apply"]
+           "oge_gpu_shard_finish", "oge_gpu_shard_apply", "oge_gpu_copy_d2d"]
 
 
 class DedupError(RuntimeError):
@@ -101,6 +101,7 @@ def lib():
         L.oge_gpu_debug_sort_bench.argtypes = [C.c_int, u64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u64,
                                                C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.oge_gpu_set_sort_variant.argtypes = [C.c_int]
+        L.oge_gpu_copy_d2d.argtypes = [vp, vp, vp, u64]
         L.oge_gpu_shard_setup.argtypes = [vp, u64, vp, vp, vp]
         L.oge_gpu_shard_begin.argtypes = [vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(vp), C.POINTER(u64)]
         L.oge_gpu_shard_probe.argtypes = [vp, vp, u64, vp, u64, C.POINTER(vp), C.POINTER(u64), C.POINTER(vp), C.POINTER(u64)]
@@ -282,6 +283,9 @@ class DedupContext:
     def shard_finish(self, w_ptr, n_w, pr_ptr, n_pr):
         """-> (marks from pairs, marks from fragments)"""
         return self._out2_call(lib().oge_gpu_shard_finish, w_ptr, n_w, pr_ptr, n_pr)
+
+    def copy_d2d(self, dst_ptr, src_ptr, nbytes):
+        _check(lib().oge_gpu_copy_d2d(self._h, dst_ptr, src_ptr, nbytes))
 
     def shard_apply(self, ptr, n):
         _check(lib().oge_gpu_shard_apply(self._h, ptr, n))

@@ -86,6 +86,32 @@ class _DevView:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
 
+class DevChunk:
+    """A list a shard call handed out: device pointer + size, valid until the next call on that context.
+    Quacks like the 1-D uint8 tensor the exchanges expect (numel, copy into a tensor slice)."""
+
+    def __init__(self, engine, ptr, nbytes):
+        self.engine, self.ptr, self.nbytes = engine, ptr, int(nbytes)
+
+    def numel(self):
+        return self.nbytes
+
+    def copy_into(self, dst):      # dst: uint8 tensor slice of the same length on the engine's device
+        if self.nbytes:
+            self.engine.ctx.copy_d2d(dst.data_ptr(), self.ptr, self.nbytes)
+
+    def tensor(self):
+        torch = self.engine.torch
+        if not self.nbytes:
+            return torch.empty(0, dtype=torch.uint8, device=self.engine.device)
+        with torch.cuda.device(self.engine.device):
+            return torch.as_tensor(_DevView(self.ptr, self.nbytes), device=self.engine.device).clone()
+
+
+def as_tensor(x):
+    return x.tensor() if isinstance(x, DevChunk) else x
+
+
 class CudaShardEngine(ShardEngine):
     """One oge_gpu_dedup_ctx driven through the sharded C ABI (include/oge_gpu_dedup.h)."""
 
@@ -113,12 +139,7 @@ class CudaShardEngine(ShardEngine):
                 self.ctx.push(records, offsets)
 
     def _take(self, ptr, count, item):
-        torch = self.torch
-        if not count:
-            return torch.empty(0, dtype=torch.uint8, device=self.device)
-        with torch.cuda.device(self.device):
-            t = torch.as_tensor(_DevView(ptr, count * item), device=self.device).clone()
-        return t
+        return DevChunk(self, ptr, count * item)
 
     def _give(self, t, item):
         torch = self.torch
@@ -161,6 +182,7 @@ class LocalExchange:
 
     def __call__(self, outs):
         import torch
+        outs = [tuple(as_tensor(t) for t in o) for o in outs]
         k = len(outs[0])
         self.bytes_moved += sum(int(t.numel()) for o in outs for t in o) * max(0, len(outs) - 1)
         return tuple(torch.cat([o[j] for o in outs]) if len(outs) > 1 else outs[0][j] for j in range(k))
@@ -250,6 +272,7 @@ class AllToAllExchange:
     def __call__(self, outs):
         torch = self.torch
         (mine,) = outs
+        mine = tuple(as_tensor(t) for t in mine)
         assert len(mine) <= 7
         if self.timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -270,6 +293,100 @@ class AllToAllExchange:
             self.ms += e0.elapsed_time(e1)
         self.bytes_moved += int(payload.numel()) * (self.world - 1)
         return res
+
+
+class GatherExchange:
+    """The same delivery (every rank's lists to every rank) as the all-gather it is: one
+    all_gather_into_tensor of fixed-size frames [sizes | payload | padding] per exchange, the frame
+    capacity agreed from the previous call at the same place in the step; the first call at a site, and
+    any call where some rank's payload outgrew the frame, gathers the sizes first and then frames of the
+    exact maximum.  No per-peer replication of the send buffer, persistent staging buffers."""
+
+    HEADER = 64
+
+    def __init__(self, dist, device, timed=False):
+        import torch
+        self.dist, self.torch, self.device = dist, torch, device
+        self.world = dist.get_world_size()
+        self.bytes_moved = 0
+        self.ms = 0.0
+        self.timed = timed and str(device).startswith("cuda")
+        self.cap, self.site = {}, 0
+        self.calls = {"framed": 0, "sized": 0}
+        self._send, self._recv = {}, {}
+
+    def new_step(self):
+        self.site = 0
+
+    def _buffers(self, site, frame):
+        torch = self.torch
+        if site not in self._send or self._send[site].numel() != frame:
+            self._send[site] = torch.empty(frame, dtype=torch.uint8, device=self.device)
+            self._recv[site] = torch.empty(self.world * frame, dtype=torch.uint8, device=self.device)
+        return self._send[site], self._recv[site]
+
+    def _gather(self, site, mine, payload, cap, flag):
+        torch, dist, W, H = self.torch, self.dist, self.world, self.HEADER
+        frame = H + cap
+        buf, out = self._buffers(site, frame)
+        hdr = torch.tensor([int(t.numel()) for t in mine] + [0] * (7 - len(mine)) + [flag], dtype=torch.int64)
+        buf[:H] = hdr.view(torch.uint8).to(self.device, non_blocking=True)
+        if not flag:
+            pos = H
+            for t in mine:      # straight into the frame: no intermediate tensors
+                n = int(t.numel())
+                if n:
+                    if isinstance(t, DevChunk):
+                        t.copy_into(buf[pos: pos + n])
+                    else:
+                        buf[pos: pos + n] = t
+                pos += n
+        dist.all_gather_into_tensor(out, buf)
+        heads = out.view(W, frame)[:, :H].contiguous().view(torch.int64).view(W, 8).cpu().tolist()
+        return out, heads, frame
+
+    def __call__(self, outs):
+        torch, W, H = self.torch, self.world, self.HEADER
+        (mine,) = outs
+        k = len(mine)
+        assert k <= 7
+        if self.timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        total = sum(int(t.numel()) for t in mine)
+        payload = None
+        site = self.site
+        self.site += 1
+        out = None
+        if site in self.cap:
+            cap = self.cap[site]
+            fits = total <= cap
+            out, heads, frame = self._gather(site, mine, payload, cap, 0 if fits else 1)
+            if any(h[7] for h in heads):
+                out = None
+            else:
+                self.calls["framed"] += 1
+        if out is None:      # sizes first (a frame without payload), then frames of the exact maximum
+            _, heads, _ = self._gather(("sz", site), mine, payload, 0, 1)
+            cap = max(256, (max(sum(h[:k]) for h in heads) + 255) // 256 * 256)
+            out, heads, frame = self._gather(site, mine, payload, cap, 0)
+            self.calls["sized"] += 1
+        per = [h[:k] for h in heads]
+        res = []
+        for j in range(k):
+            parts = []
+            for r in range(W):
+                o = r * frame + H + sum(per[r][:j])
+                parts.append(out[o: o + per[r][j]])
+            res.append(torch.cat(parts))      # a copy: `out` is reused by the next step
+        biggest = max(sum(p) for p in per)
+        self.cap[site] = max(4096, (biggest + biggest // 4 + 255) // 256 * 256)
+        if self.timed:
+            e1.record()
+            e1.synchronize()
+            self.ms += e0.elapsed_time(e1)
+        self.bytes_moved += total * (W - 1)
+        return tuple(res)
 
 
 # --------------------------------------------------------------------------------------- the protocol
@@ -367,7 +484,7 @@ def bench(args, rank, world, local_rank, rec, offs, text, contigs, metric, workl
     plan = ShardPlan(bases, [int(v[1]) for v in allv[1:]], [int(v[2]) for v in allv[1:]])
 
     eng = CudaShardEngine(rec, offs, text, contigs, plan, rank, device=local_rank, pinned_ptr=rec.ctypes.data, profile_events=True)
-    ex = AllToAllExchange(dist, dev, timed=True)
+    ex = (AllToAllExchange if os.environ.get("OGE_EXCHANGE") == "alltoall" else GatherExchange)(dist, dev, timed=True)
 
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
@@ -446,7 +563,7 @@ def bench(args, rank, world, local_rank, rec, offs, text, contigs, metric, workl
                        "duplicates_flagged": total_dups,
                        "published_entries": info["published"], "routed_entries": info["routed"], "marks_exchanged": info["marks"],
                        "stage_ms_rank0": {k: st[k] for k in ("ms_endbuild", "ms_join", "ms_sort_pair", "ms_sort_frag", "ms_select", "ms_flags")},
-                       "parallelism": "range-sharded x%d, all-to-all of small lists" % world},
+                       "parallelism": "range-sharded x%d, three exchanges of small lists per step (%s)" % (world, type(ex).__name__)},
             "e2e": {"value": total_reads / float(e2e_s[0]), "unit": "reads/s", "h2d_bytes_per_step": int(h2d[0]),
                     "d2h_bytes_per_step": int(h2d[1]), "ms_per_step": float(e2e_s[0]) * 1e3},
             "gpu_launches": int(launches),

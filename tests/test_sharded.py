@@ -113,7 +113,7 @@ def _free_port():
     return p
 
 
-def _gloo_worker(rank, world, port, out_dir):
+def _gloo_worker(rank, world, port, out_dir, kind="alltoall"):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -121,7 +121,7 @@ def _gloo_worker(rank, world, port, out_dir):
         bam = straddling_case()
         plan, shards = sharded.split_bam(bam, world)
         rec, off = shards[rank]
-        ex = sharded.AllToAllExchange(dist, torch.device("cpu"))
+        ex = (sharded.GatherExchange if kind == "gather" else sharded.AllToAllExchange)(dist, torch.device("cpu"))
         for it in range(3):      # first run: sized protocol; later runs: one framed collective per exchange
             eng = ModelShardEngine(rec, off, bam.text, plan, rank)
             if it == 2:
@@ -135,10 +135,11 @@ def _gloo_worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
-def test_orchestration_under_gloo_world2(tmp_path):
+@pytest.mark.parametrize("kind", ["alltoall", "gather"])
+def test_orchestration_under_gloo_world2(tmp_path, kind):
     import torch.multiprocessing as mp
     world, port = 2, _free_port()
-    mp.spawn(_gloo_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_gloo_worker, args=(world, port, str(tmp_path), kind), nprocs=world, join=True)
     bam = straddling_case()
     want = oracle.markdup(bam.records, bam.offsets, bam.text)
     got = np.concatenate([np.load(tmp_path / ("flags%d.npy" % r)) for r in range(world)])
