@@ -323,7 +323,9 @@ int oge_gpu_shard_probe(oge_gpu_dedup_ctx *c, const void *pub_all_dev, uint64_t 
     else if (!c->cfg.debug_full_frag_sort && sh.n_unpaired <= sh.n_frag / 16 && c->kl.f_end - c->kl.f_orient <= 63) sh.frag_mode = 1;
     if (sh.frag_mode && n + n_fr_all) {
         const uint64_t n_all_frag = n + n_fr_all;
-        sh.ucap = std::max<uint64_t>(sh.n_frag / 4, 4 * sh.n_unpaired) + n_fr_all + 1024;
+        // room for the unpaired ends and the paired ends sharing their keys; with no local unpaired end only the
+        // few routed copies can matter, and small capacities keep the (mostly empty) launches of the sort small
+        sh.ucap = (sh.n_unpaired ? std::max<uint64_t>(sh.n_frag / 4, 4 * sh.n_unpaired) : 0) + 64 * n_fr_all + 1024;
         if (const char *e = getenv("OGE_UFRAG_CAP")) sh.ucap = std::max<uint64_t>(1, (uint64_t) atoll(e));      // test hook: force the fallback
         if ((rc = c->frag.reserve(n_all_frag, true, s))) return rc;
         if (sh.frag_mode == 2) {
