@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define OGE_GPU_DEDUP_ABI_VERSION 2
+#define OGE_GPU_DEDUP_ABI_VERSION 3
 
 enum {
     OGE_OK = 0,
@@ -134,6 +134,17 @@ int oge_gpu_dedup_flags(oge_gpu_dedup_ctx *ctx, uint16_t *out, uint64_t n);
  * out_offsets (optional) receives out_nrec+1 offsets. */
 int oge_gpu_dedup_pull(oge_gpu_dedup_ctx *ctx, uint8_t *out_records, uint64_t cap_bytes,
                        uint64_t *out_offsets, uint64_t cap_records, uint64_t *out_bytes, uint64_t *out_nrec);
+
+/* The counters of the reference's Statistics module (algorithms/statistics.cpp:77-162: what `openge stats` prints,
+ * and what a Statistics stage placed behind MarkDuplicates would count) over the resident records and their
+ * flag words after the run, as device reductions; `sorted` is the "Sorted:" verdict (:89-101), including the
+ * reference's exemption of the first record of every contig. */
+typedef struct oge_gpu_flagstats {
+    uint64_t n_reads, n_mapped, n_forward_strand, n_reverse_strand, n_failed_qc, n_duplicates;
+    uint64_t n_paired, n_proper_pair, n_both_mates_mapped, n_first_mate, n_second_mate, n_singletons;
+    uint64_t sorted;                /* 1 = "Yes", 0 = "No" */
+} oge_gpu_flagstats;
+int oge_gpu_dedup_flagstats(oge_gpu_dedup_ctx *ctx, oge_gpu_flagstats *out);
 
 /* Forget the pushed records (keeps allocations); a context can then take the next file. */
 int oge_gpu_dedup_reset(oge_gpu_dedup_ctx *ctx);

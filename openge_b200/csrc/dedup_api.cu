@@ -589,6 +589,23 @@ int oge_gpu_dedup_pull(oge_gpu_dedup_ctx *c, uint8_t *out_records, uint64_t cap_
     return OGE_OK;
 }
 
+int oge_gpu_dedup_flagstats(oge_gpu_dedup_ctx *c, oge_gpu_flagstats *out) {
+    if (!c || !out) return fail_msg(OGE_ERR_INVALID_ARG, "flagstats: null argument");
+    if (!c->ran) return fail_msg(OGE_ERR_STATE, "flagstats: call oge_gpu_dedup_run first");
+    static_assert(sizeof(oge_gpu_flagstats) == FS_N_OUT * sizeof(uint64_t), "oge_gpu_flagstats mirrors the FS_* order");
+    OGE_CUDA_TRY(cudaSetDevice(c->cfg.device));
+    DevBuf<uint8_t> tmp;
+    int rc = tmp.reserve(flagstat_scratch_bytes(c->n), false, c->stream);
+    if (rc) return rc;
+    uint64_t launches = 0;
+    rc = launch_flagstats(c->rec.p, c->off.p, c->flag_out.p, c->n, tmp.p, c->sms, c->stream, &launches);
+    if (!rc && cudaMemcpyAsync(out, tmp.p, sizeof(*out), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+        rc = fail_cuda(cudaGetLastError(), "flagstats copy", __FILE__, __LINE__);
+    if (!rc && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail_cuda(cudaGetLastError(), "flagstats sync", __FILE__, __LINE__);
+    tmp.release();
+    return rc;
+}
+
 int oge_gpu_dedup_get_stats(oge_gpu_dedup_ctx *c, oge_gpu_dedup_stats *out) {
     if (!c || !out) return fail_msg(OGE_ERR_INVALID_ARG, "get_stats: null argument");
     *out = c->stats;

@@ -130,6 +130,22 @@ struct FlagParams {
 
 int launch_flags(const FlagParams &P, cudaStream_t stream, uint64_t *launches);
 
+// ---- flag statistics (flagstat.cu): Statistics::runInternal's counters over the resident records
+enum {
+    FS_READS = 0, FS_MAPPED, FS_FORWARD, FS_REVERSE, FS_FAILED_QC, FS_DUPLICATES, FS_PAIRED, FS_PROPER_PAIR,
+    FS_BOTH_MAPPED, FS_FIRST_MATE, FS_SECOND_MATE, FS_SINGLETONS,
+    FS_N_COUNTERS,
+    FS_SORTED = FS_N_COUNTERS,
+    FS_N_OUT
+};
+struct SortTile {      // what a 1024-record tile tells the seam check about its considered records
+    int32_t n_valid, bad;      // 0, 1, 2 (= two or more)
+    int32_t first_ref, first_pos, second_ref, second_pos, last2_ref, last2_pos, last_ref, last_pos;
+};
+size_t flagstat_scratch_bytes(uint64_t n);
+int launch_flagstats(const uint8_t *rec, const uint64_t *off, const uint16_t *flags, uint64_t n, void *scratch, int sms,
+                     cudaStream_t stream, uint64_t *launches);
+
 // pull with remove_duplicates: compaction of the kept records
 // ---- range sharding (shard.cu) ------------------------------------------------------------------
 // What leaves a rank about one record whose name was not seen exactly twice locally.

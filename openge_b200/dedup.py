@@ -19,7 +19,7 @@ import numpy as np
 from . import _build, header as _header
 from .bamio import BamFile
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 OGE_OK = 0
 ERRORS = {-1: "OGE_ERR_INVALID_ARG", -2: "OGE_ERR_CUDA", -3: "OGE_ERR_NOMEM", -4: "OGE_ERR_KEY_RANGE",
@@ -49,12 +49,16 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+FLAGSTAT_FIELDS = ("reads", "mapped", "forward", "reverse", "failed_qc", "duplicates", "paired", "proper_pair",
+                   "both_mapped", "first_mate", "second_mate", "singletons", "sorted")      # oge_gpu_flagstats, in order
+
+
 END_DTYPE = np.dtype([("eligible", "<i4"), ("pair_eligible", "<i4"), ("ref", "<i4"), ("coord", "<i4"),
                       ("orientation", "<i4"), ("read2Sequence", "<i4"), ("score", "<i2"), ("lib", "<i2")])
 
 EXPORTS = ["oge_gpu_dedup_create", "oge_gpu_dedup_destroy", "oge_gpu_dedup_set_readgroups", "oge_gpu_dedup_push",
            "oge_gpu_dedup_sync", "oge_gpu_dedup_run", "oge_gpu_dedup_flags", "oge_gpu_dedup_pull",
-           "oge_gpu_dedup_reset", "oge_gpu_dedup_get_stats", "oge_gpu_dedup_debug_ends",
+           "oge_gpu_dedup_reset", "oge_gpu_dedup_flagstats", "oge_gpu_dedup_get_stats", "oge_gpu_dedup_debug_ends",
            "oge_gpu_dedup_device_ptrs", "oge_gpu_host_alloc", "oge_gpu_host_free", "oge_gpu_device_count",
            "oge_gpu_last_error", "oge_gpu_abi_version", "oge_gpu_debug_sort128", "oge_gpu_debug_sort_bench",
            "oge_gpu_set_sort_variant", "oge_gpu_shard_setup", "oge_gpu_shard_begin", "oge_gpu_shard_probe",
@@ -90,6 +94,7 @@ def lib():
         L.oge_gpu_dedup_pull.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64), C.POINTER(u64)]
         L.oge_gpu_dedup_reset.argtypes = [vp]
         L.oge_gpu_dedup_get_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.oge_gpu_dedup_flagstats.argtypes = [vp, vp]
         L.oge_gpu_dedup_debug_ends.argtypes = [vp, vp, u64]
         L.oge_gpu_dedup_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
         L.oge_gpu_host_alloc.argtypes = [C.c_size_t]
@@ -254,6 +259,13 @@ class DedupContext:
         st = Stats()
         _check(lib().oge_gpu_dedup_get_stats(self._h, C.byref(st)))
         return st.as_dict()
+
+    def flagstats(self) -> dict:
+        """The reference's Statistics counters (algorithms/statistics.cpp:77-162) over the records and their flag
+        words after the run, reduced on the device."""
+        out = np.zeros(len(FLAGSTAT_FIELDS), dtype=np.uint64)
+        _check(lib().oge_gpu_dedup_flagstats(self._h, out.ctypes.data))
+        return dict(zip(FLAGSTAT_FIELDS, (int(x) for x in out)))
 
     def ends(self) -> np.ndarray:
         out = np.zeros(self.n, dtype=END_DTYPE)

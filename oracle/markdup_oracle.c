@@ -478,3 +478,47 @@ int oge_oracle_markdup(const uint8_t *records, const uint64_t *offsets, uint64_t
     free(pair_sort.v); free(frag_sort.v); free(tmp.s); free(dup);
     return 0;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Flag statistics: the counting loop of Statistics::runInternal (algorithms/statistics.cpp:77-162),
+ * over framed records.  `flags` (optional) overrides the flag word of the records (the dedup
+ * output); out[0..11] = numReads, numMapped, numForwardStrand, numReverseStrand, numFailedQC,
+ * numDuplicates, numPaired, numProperPair, numBothMatesMapped, numFirstMate, numSecondMate,
+ * numSingletons; out[12] = the "Sorted:" verdict (1 Yes / 0 No).
+ * Flag predicates: util/bamtools/BamAlignment.cpp:444-516 (bit tests of BamConstants.h:35-45).
+ */
+int oge_oracle_flagstats(const uint8_t *records, const uint64_t *offsets, uint64_t n, const uint16_t *flags, uint64_t *out) {
+    uint64_t i;
+    int sorted = 1, last_rid = -1, last_position = -1;          /* statistics.cpp:82-84 */
+    memset(out, 0, 13 * sizeof(uint64_t));
+    for (i = 0; i < n; i++) {
+        const uint8_t *p = records + offsets[i];
+        const int32_t rid = rd_i32(p + 4), pos = rd_i32(p + 8);
+        const uint32_t f = flags ? flags[i] : rd_u16(p + 18);
+        if (sorted && rid != -1 && pos != -1) {                  /* :89-101 */
+            if (last_rid > rid) sorted = 0;
+            else if (last_rid < rid) { last_rid = rid; last_position = -1; }
+            else {
+                if (last_position > pos) sorted = 0;
+                else last_position = pos;
+            }
+        }
+        out[0]++;                                                /* :104 */
+        if (f & 0x400) out[5]++;                                 /* :107 IsDuplicate */
+        if (f & 0x200) out[4]++;                                 /* :108 IsFailedQC */
+        if (!(f & 0x4)) out[1]++;                                /* :109 IsMapped */
+        if (f & 0x10) out[3]++; else out[2]++;                   /* :112-115 */
+        if (f & 0x1) {                                           /* :118 IsPaired */
+            out[6]++;
+            if (f & 0x40) out[9]++;                              /* :124 */
+            if (f & 0x80) out[10]++;                             /* :125 */
+            if (!(f & 0x4)) {                                    /* :128-135 */
+                if (!(f & 0x8)) out[8]++;
+                else out[11]++;
+            }
+            if (f & 0x2) out[7]++;                               /* :138 */
+        }
+    }
+    out[12] = (uint64_t) sorted;
+    return 0;
+}

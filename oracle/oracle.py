@@ -38,8 +38,29 @@ def lib():
         L.oge_oracle_markdup.restype = C.c_int
         L.oge_oracle_markdup.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_char_p), C.c_void_p,
                                          C.c_int32, C.c_int16, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oge_oracle_flagstats.restype = C.c_int
+        L.oge_oracle_flagstats.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
+
+
+FLAGSTAT_FIELDS = ("reads", "mapped", "forward", "reverse", "failed_qc", "duplicates", "paired", "proper_pair",
+                   "both_mapped", "first_mate", "second_mate", "singletons", "sorted")
+
+
+def flagstats(records: np.ndarray, offsets: np.ndarray, flags: np.ndarray | None = None) -> dict:
+    """Statistics::runInternal's counters (statistics.cpp:77-162) over framed records; `flags` overrides the
+    records' flag words (the dedup output)."""
+    L = lib()
+    records = np.ascontiguousarray(records)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(offsets) - 1
+    out = np.zeros(13, dtype=np.uint64)
+    fl = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint16)
+    rc = L.oge_oracle_flagstats(records.ctypes.data, offsets.ctypes.data, n, None if fl is None else fl.ctypes.data, out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("oracle failed")
+    return dict(zip(FLAGSTAT_FIELDS, (int(x) for x in out)))
 
 
 def markdup(records: np.ndarray, offsets: np.ndarray, text: str, compat_quiet: bool = False, want_ends: bool = False):
@@ -142,3 +163,38 @@ def ref_time_mem(bam, reps=1, threads=None, tmpdir=None, timeout=900):
         if r.returncode != 0:
             raise RuntimeError("reference failed")
         return json.loads(r.stdout.decode().strip().splitlines()[-1])
+
+
+_STAT_LABELS = {"Total reads": "reads", "Mapped reads": "mapped", "Forward strand": "forward", "Reverse strand": "reverse",
+                "Failed QC": "failed_qc", "Duplicates": "duplicates", "Paired-end reads": "paired", "'Proper-pairs'": "proper_pair",
+                "Both pairs mapped": "both_mapped", "Read 1": "first_mate", "Read 2": "second_mate", "Singletons": "singletons",
+                "Sorted": "sorted"}
+
+
+def ref_stats(bam, tmpdir=None, timeout=60) -> dict:
+    """The compiled reference's own Statistics module (algorithms/statistics.cpp) run behind its MarkDuplicates
+    (`--nosplit -v --stats`): the printed report parsed into the FLAGSTAT_FIELDS dict.  Lines the reference omits
+    when there are no paired reads (statistics.cpp:165-171) come back as 0."""
+    exe = _build.ensure_ref()
+    if exe is None:
+        raise RuntimeError("oracle/_ref/oge_ref_dedup not built")
+    base = tmpdir or ("/dev/shm" if os.path.isdir("/dev/shm") else None)
+    with tempfile.TemporaryDirectory(dir=base) as d:
+        inp, out = os.path.join(d, "in.rawbam"), os.path.join(d, "out.rawbam")
+        bamio.write_bam(inp, bam, raw=True)
+        cmd = [exe, "-T", d, "-F", "rawbam", "-v", "--nosplit", "--stats", inp, out]
+        for attempt in range(4):
+            try:
+                r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout)
+            except subprocess.TimeoutExpired:
+                continue
+            if r.returncode != 0:
+                raise RuntimeError("reference failed: %s" % r.stderr.decode()[-2000:])
+            res = {k: 0 for k in FLAGSTAT_FIELDS}
+            for line in r.stdout.decode().splitlines():
+                label, _, rest = line.partition(":")
+                if label in _STAT_LABELS and rest.strip():
+                    tok = rest.split()[0]
+                    res[_STAT_LABELS[label]] = {"Yes": 1, "No": 0}.get(tok, None) if tok in ("Yes", "No") else int(tok)
+            return res
+        raise RefHang("reference did not terminate in %d s (4 attempts)" % timeout)

@@ -14,12 +14,16 @@
 //                    MemorySource -> MarkDuplicates -> CountingSink   (records in, flags out)
 //                    i.e. exactly MarkDuplicates::runInternal with host buffers on both sides.
 //                    Prints one JSON line with seconds per repetition.
+//   --stats:         (single chain only) puts the reference's Statistics module (algorithms/statistics.cpp,
+//                    what `openge stats` runs, command_stats.cpp) between MarkDuplicates and the writer:
+//                    its report goes to stdout.
 #include "algorithms/algorithm_module.h"
 #include "algorithms/file_reader.h"
 #include "algorithms/file_writer.h"
 #include "algorithms/mark_duplicates.h"
 #include "algorithms/sorted_merge.h"
 #include "algorithms/split_by_chromosome.h"
+#include "algorithms/statistics.h"
 #include "util/read_stream_reader.h"
 
 #include <sys/time.h>
@@ -72,12 +76,12 @@ protected:
 
 static void usage() {
     fprintf(stderr,
-        "usage: oge_ref_dedup [-v] [--nosplit] [-r] [-t N] [-T tmpdir] [-F fmt] [-c lvl] [--mem [--reps K] [--flags out.u16]] in out\n");
+        "usage: oge_ref_dedup [-v] [--nosplit] [-r] [-t N] [-T tmpdir] [-F fmt] [-c lvl] [--stats] [--mem [--reps K] [--flags out.u16]] in out\n");
     exit(2);
 }
 
 int main(int argc, char ** argv) {
-    bool verbose = false, nosplit = false, remove_dups = false, mem = false;
+    bool verbose = false, nosplit = false, remove_dups = false, mem = false, stats = false;
     int threads = ThreadPool::availableCores();
     int level = 6, reps = 1;
     string tmpdir = "/tmp", format, flags_out;
@@ -88,6 +92,7 @@ int main(int argc, char ** argv) {
         else if (a == "--nosplit") nosplit = true;
         else if (a == "-r") remove_dups = true;
         else if (a == "--mem") mem = true;
+        else if (a == "--stats") stats = true;
         else if (a == "-t" && i + 1 < argc) threads = atoi(argv[++i]);
         else if (a == "-T" && i + 1 < argc) tmpdir = argv[++i];
         else if (a == "-F" && i + 1 < argc) format = argv[++i];
@@ -143,9 +148,16 @@ int main(int argc, char ** argv) {
         FileReader reader;
         MarkDuplicates mark_duplicates(tmpdir);
         FileWriter writer;
+        Statistics statistics;
         reader.addSink(&mark_duplicates);
         if (!format.empty()) writer.setFormat(format);
-        mark_duplicates.addSink(&writer);
+        if (stats) {
+            statistics.showReadLengthSummary(false);      // the member is left uninitialised by the constructor (statistics.cpp:32-48)
+            mark_duplicates.addSink(&statistics);
+            statistics.addSink(&writer);
+        } else {
+            mark_duplicates.addSink(&writer);
+        }
         mark_duplicates.removeDuplicates = remove_dups;
         reader.addFile(pos[0]);
         writer.setFilename(pos[1]);

@@ -135,3 +135,50 @@ def edge_cases():
     add("unm", 4, 1, 100, "*", -1, 0)
     records, offsets = bamio.concat_records(recs)
     return bamio.BamFile(text=text, refs=[("chr1", 100000), ("chr2", 5000)], records=records, offsets=offsets)
+
+
+def sortedness_cases():
+    """Small single-end BAMs exercising the "Sorted:" verdict of the reference's Statistics module
+    (algorithms/statistics.cpp:89-101), including its quirk: the first record of every contig is exempt
+    from the position comparison (last_position is reset to -1 and not set by that record).
+    -> dict name -> BamFile"""
+    text = ("@HD\tVN:1.4\tSO:unsorted\n@SQ\tSN:chr1\tLN:100000\n@SQ\tSN:chr2\tLN:100000\n@SQ\tSN:chr3\tLN:100000\n"
+            "@RG\tID:rg1\tLB:libA\tSM:s\n")
+    refs = [("chr1", 100000), ("chr2", 100000), ("chr3", 100000)]
+
+    def mk(rows):
+        recs = []
+        for k, (ref, pos1, flag) in enumerate(rows):
+            if flag & 4:
+                recs.append(bamio.build_record("r%03d" % k, flag, ref, pos1 - 1, 0, "*", -1, -1, 0, SEQ100, 30, bamio.tag_z("RG", "rg1")))
+            else:
+                recs.append(_rec("r%03d" % k, flag, ref, pos1, "100M", -1, 0, "I"))
+        records, offsets = bamio.concat_records(recs)
+        return bamio.BamFile(text=text, refs=refs, records=records, offsets=offsets)
+
+    cases = {
+        "sorted_plain": [(0, 100, 0), (0, 200, 16), (1, 50, 0), (1, 50, 0), (2, 10, 0)],
+        "first_of_contig_exempt": [(0, 500, 0), (0, 100, 0), (0, 200, 0), (1, 900, 0), (1, 10, 16), (1, 20, 0)],   # still "Yes"
+        "pos_drop_third": [(0, 500, 0), (0, 600, 0), (0, 100, 0)],                                               # "No"
+        "contig_drop": [(0, 100, 0), (1, 100, 0), (0, 200, 0)],                                                  # "No"
+        "unplaced_skipped": [(0, 100, 0), (0, 300, 0), (-1, 0, 4), (0, 200, 0)],                                 # "No": -1/-1 records are skipped
+        "unplaced_between_ok": [(0, 100, 0), (-1, 0, 4), (0, 100, 0), (-1, 0, 4), (-1, 0, 4), (1, 5, 0), (-1, 0, 4), (1, 1, 0), (1, 1, 0)],
+        "only_unplaced": [(-1, 0, 4), (-1, 0, 4)],
+        "single": [(2, 77, 16)],
+    }
+    rng = np.random.default_rng(5)
+    big = []
+    for ref in range(3):      # 3000 sorted records spanning several 1024-record tiles, one violation deep inside
+        pos = np.sort(rng.integers(1, 90000, size=1000))
+        big += [(ref, int(p), int(rng.integers(0, 2)) * 16) for p in pos]
+    cases["big_sorted"] = list(big)
+    bad = list(big)
+    bad[2049] = (bad[2049][0], 1, 0)
+    cases["big_one_violation"] = bad
+    edge = list(big)
+    edge[1024] = (edge[1024][0], 1, 0)      # first record of the second 1024-tile
+    cases["big_violation_at_tile_start"] = edge
+    edge2 = list(big)
+    edge2[1025] = (edge2[1025][0], 1, 0)    # second record of a tile: its predecessor's predecessor is in the previous tile
+    cases["big_violation_second_of_tile"] = edge2
+    return {k: mk(v) for k, v in cases.items()}

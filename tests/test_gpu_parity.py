@@ -355,3 +355,67 @@ def test_paired_only_data_skips_fragment_sort():
     assert np.array_equal(got, want) and np.array_equal(got_full, want)
     assert st["sort_pass_launches"] == st["pair_sort_passes"]                                  # near pairs only
     assert st_full["sort_pass_launches"] == st["pair_sort_passes"] + st["frag_sort_passes"]
+
+
+# ---- flag statistics: oge_gpu_dedup_flagstats against the numbers printed by the compiled
+# reference's own Statistics module (tests/golden/flagstats.npz) and against the oracle restatement
+def _flagstats_golden():
+    import os
+    from conftest import GOLDEN
+    return dict(np.load(os.path.join(GOLDEN, "flagstats.npz")))
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_flagstats_match_reference_statistics(case):
+    bam, _ = load_golden(case)
+    want = _flagstats_golden()[case]
+    with dedup.context_for(bam) as ctx:
+        ctx.push(bam.records, bam.offsets)
+        ctx.run()
+        got = ctx.flagstats()
+    assert [got[k] for k in dedup.FLAGSTAT_FIELDS] == [int(x) for x in want]
+
+
+def test_flagstats_sorted_verdict_matches_reference_statistics():
+    import fixtures
+    gold = _flagstats_golden()
+    for name, bam in fixtures.sortedness_cases().items():
+        with dedup.context_for(bam) as ctx:
+            ctx.push(bam.records, bam.offsets)
+            ctx.run()
+            got = ctx.flagstats()
+        assert [got[k] for k in dedup.FLAGSTAT_FIELDS] == [int(x) for x in gold["sortedness_" + name]], name
+
+
+def test_flagstats_vs_oracle_at_size_and_unsorted():
+    bam = synth.make("C3", 0.3, seed=77)      # ~3 M records: thousands of sortedness tiles
+    with dedup.context_for(bam) as ctx:
+        ctx.push(bam.records, bam.offsets)
+        ctx.run()
+        got, flags = ctx.flagstats(), ctx.flags()
+    assert got == oracle.flagstats(bam.records, bam.offsets, flags)
+    assert got["sorted"] == 1 and got["duplicates"] == int(((flags & 0x400) != 0).sum())
+    # the same records with two far-apart blocks swapped: unsorted, every other counter unchanged
+    sizes = np.diff(bam.offsets.astype(np.int64))
+    order = np.arange(bam.n)
+    a, b = bam.n // 3, 2 * bam.n // 3
+    order[a:a + 1000], order[b:b + 1000] = np.arange(b, b + 1000), np.arange(a, a + 1000)
+    starts = bam.offsets[:-1].astype(np.int64)[order]
+    new_off = np.concatenate([[0], np.cumsum(sizes[order])]).astype(np.uint64)
+    gather = np.repeat(starts - new_off[:-1].astype(np.int64), sizes[order]) + np.arange(int(new_off[-1]), dtype=np.int64)
+    rec2 = bam.records[gather]
+    with dedup.context_for(bam) as ctx:
+        ctx.push(rec2, new_off)
+        ctx.run()
+        got2, flags2 = ctx.flagstats(), ctx.flags()
+    assert got2 == oracle.flagstats(rec2, new_off, flags2)
+    assert got2["sorted"] == 0
+
+
+def test_flagstats_before_run_is_a_state_error():
+    bam, _ = load_golden("a3_fixture1")
+    with dedup.context_for(bam) as ctx:
+        ctx.push(bam.records, bam.offsets)
+        with pytest.raises(dedup.DedupError) as e:
+            ctx.flagstats()
+        assert e.value.code == -5

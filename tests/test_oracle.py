@@ -87,3 +87,27 @@ def test_oracle_vs_live_reference(name, scale, seed):
 def test_empty_input():
     flags = oracle.markdup(np.zeros(0, np.uint8), np.zeros(1, np.uint64), "@HD\tVN:1.4\tSO:coordinate\n")
     assert len(flags) == 0
+
+
+# ---- flag statistics: the oracle restatement of Statistics::runInternal against the
+# numbers printed by the compiled reference's own Statistics module (tests/golden/make_flagstats_golden.py)
+def _flagstats_golden():
+    import os
+    from conftest import GOLDEN
+    return dict(np.load(os.path.join(GOLDEN, "flagstats.npz")))
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_oracle_flagstats_match_reference_statistics(case):
+    bam, g = load_golden(case)
+    want = _flagstats_golden()[case]
+    got = oracle.flagstats(bam.records, bam.offsets, g["flags_nosplit_v"])
+    assert [got[k] for k in oracle.FLAGSTAT_FIELDS] == [int(x) for x in want]
+
+
+def test_oracle_sorted_verdict_matches_reference_statistics():
+    gold = _flagstats_golden()
+    for name, bam in fixtures.sortedness_cases().items():
+        flags = oracle.markdup(bam.records, bam.offsets, bam.text)
+        got = oracle.flagstats(bam.records, bam.offsets, flags)
+        assert [got[k] for k in oracle.FLAGSTAT_FIELDS] == [int(x) for x in gold["sortedness_" + name]], name
