@@ -1,6 +1,8 @@
 """In-tree builds of the native pieces (no JIT cache: the .so files travel with the repo).
 
   libopenge_b200.so   CUDA kernels + C-ABI   (nvcc, sm_100a)      openge_b200/csrc/
+  liboge_bamhost.so   host BAM streaming layer (g++, zlib; no CUDA)   openge_b200/host/bam_host.cpp
+  host/_build/oge_dedup_fused   BAM file -> GPU dedup -> BAM file (g++; links both libraries)
   libogesynth.so      synthetic workloads    (gcc)                tools/synth/
   liboge_oracle.so    TEST-ONLY CPU oracle   (gcc)                oracle/
   oracle/_ref/...     the reference itself   (g++, only where /root/reference exists)
@@ -17,6 +19,8 @@ SYNTH_LIB = os.path.join(ROOT, "tools", "synth", "libogesynth.so")
 ORACLE_LIB = os.path.join(ROOT, "oracle", "liboge_oracle.so")
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "oge_ref_dedup")
 HOST_BIN = os.path.join(ROOT, "openge_b200", "host", "_build", "oge_dedup_gpu")
+BAMHOST_LIB = os.path.join(ROOT, "openge_b200", "liboge_bamhost.so")
+FUSED_BIN = os.path.join(ROOT, "openge_b200", "host", "_build", "oge_dedup_fused")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--use_fast_math", "-Xcompiler", "-fPIC", "-shared"]
@@ -127,10 +131,43 @@ def ensure_host(force=False):
     return HOST_BIN if os.path.exists(HOST_BIN) else None
 
 
+def ensure_bamhost(force=False):
+    """The host-side BAM streaming layer (include/oge_bam_host.h): parallel BGZF codec, header model, framing."""
+    src = os.path.join(ROOT, "openge_b200", "host", "bam_host.cpp")
+    hdr = os.path.join(ROOT, "include", "oge_bam_host.h")
+    if force or _stale(BAMHOST_LIB, [src, hdr]):
+        with _BuildLock(BAMHOST_LIB + ".lock"):
+            if force or _stale(BAMHOST_LIB, [src, hdr]):
+                tmp = BAMHOST_LIB + ".tmp.%d" % os.getpid()
+                _run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-pthread", "-I", os.path.join(ROOT, "include"), src, "-o", tmp, "-lz"])
+                os.replace(tmp, BAMHOST_LIB)
+    return BAMHOST_LIB
+
+
+def ensure_fused(force=False):
+    """`openge dedup` as one fused path: oge_bam_load -> libopenge_b200.so -> oge_bam_store.  Needs no reference sources."""
+    d = os.path.join(ROOT, "openge_b200", "host")
+    srcs = [os.path.join(d, "dedup_fused_main.cpp"), os.path.join(d, "bam_host.cpp")]
+    deps = srcs + [os.path.join(ROOT, "include", "oge_bam_host.h"), os.path.join(ROOT, "include", "oge_gpu_dedup.h"), GPU_LIB]
+    if force or _stale(FUSED_BIN, deps):
+        if not _have("g++"):
+            return FUSED_BIN if os.path.exists(FUSED_BIN) else None
+        os.makedirs(os.path.dirname(FUSED_BIN), exist_ok=True)
+        with _BuildLock(os.path.join(ROOT, "openge_b200", "liboge_fused.lock")):
+            if force or _stale(FUSED_BIN, deps):
+                tmp = FUSED_BIN + ".tmp.%d" % os.getpid()
+                _run(["g++", "-std=c++17", "-O2", "-pthread", "-I", os.path.join(ROOT, "include")] + srcs +
+                     ["-o", tmp, "-L", os.path.join(ROOT, "openge_b200"), "-lopenge_b200", "-Wl,-rpath,$ORIGIN/../..", "-lz"])
+                os.replace(tmp, FUSED_BIN)
+    return FUSED_BIN
+
+
 def build_all(verbose=False):
     ensure_synth()
     ensure_oracle()
     ensure_ref()
     lib = build_gpu(verbose=verbose)
+    ensure_bamhost()
+    ensure_fused()
     ensure_host()
     return lib

@@ -1,0 +1,216 @@
+"""ctypes binding of liboge_bamhost.so (include/oge_bam_host.h): the host-side BAM streaming layer around the
+GPU dedup path -- parallel BGZF inflate into one buffer, header model, record framing, flag/bin rewrite, parallel
+BGZF deflate with the reference's exact block layout.  No CUDA in here; the duplicate flags come from
+openge_b200.dedup (libopenge_b200.so).
+
+``dedup_file`` is `openge dedup in.bam -o out.bam` (reference: commands/command_dedup.cpp:37-114) as one fused
+path: load -> push/run/flags on the GPU -> apply_flags -> store.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _build
+
+ERRORS = {-1: "OGE_BAM_ERR_IO", -2: "OGE_BAM_ERR_FORMAT", -3: "OGE_BAM_ERR_NOMEM", -4: "OGE_BAM_ERR_ARG"}
+
+EXPORTS = ["oge_bam_load", "oge_bam_close", "oge_bam_header_text", "oge_bam_n_ref", "oge_bam_ref_name", "oge_bam_ref_len",
+           "oge_bam_records", "oge_bam_records_bytes", "oge_bam_offsets", "oge_bam_n_records", "oge_bam_library_table",
+           "oge_bam_apply_flags", "oge_bam_store", "oge_bam_timings", "oge_bgzf_decompress", "oge_bgzf_compress",
+           "oge_bam_header_render", "oge_bam_buffer_free", "oge_bam_last_error"]
+
+
+class BamHostError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("%s (%d): %s" % (ERRORS.get(code, "error"), code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = _build.ensure_bamhost()
+        if not os.path.exists(path):
+            raise ImportError("liboge_bamhost.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(path)
+        vp, u64 = C.c_void_p, C.c_uint64
+        L.oge_bam_load.argtypes = [C.c_char_p, C.c_int, vp, vp, C.POINTER(vp)]
+        L.oge_bam_close.argtypes = [vp]
+        L.oge_bam_close.restype = None
+        L.oge_bam_header_text.argtypes = [vp]
+        L.oge_bam_header_text.restype = C.c_char_p
+        L.oge_bam_n_ref.argtypes = [vp]
+        L.oge_bam_n_ref.restype = C.c_int32
+        L.oge_bam_ref_name.argtypes = [vp, C.c_int32]
+        L.oge_bam_ref_name.restype = C.c_char_p
+        L.oge_bam_ref_len.argtypes = [vp, C.c_int32]
+        L.oge_bam_ref_len.restype = C.c_int32
+        L.oge_bam_records.argtypes = [vp]
+        L.oge_bam_records.restype = vp
+        L.oge_bam_records_bytes.argtypes = [vp]
+        L.oge_bam_records_bytes.restype = u64
+        L.oge_bam_offsets.argtypes = [vp]
+        L.oge_bam_offsets.restype = vp
+        L.oge_bam_n_records.argtypes = [vp]
+        L.oge_bam_n_records.restype = u64
+        L.oge_bam_library_table.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int32), C.POINTER(C.c_int16), C.POINTER(C.c_int32)]
+        L.oge_bam_apply_flags.argtypes = [vp, vp, C.c_int, C.c_int]
+        L.oge_bam_store.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int]
+        L.oge_bam_timings.argtypes = [vp, C.POINTER(C.c_double), C.c_int]
+        L.oge_bgzf_decompress.argtypes = [vp, C.c_size_t, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
+        L.oge_bgzf_compress.argtypes = [vp, C.c_size_t, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
+        L.oge_bam_header_render.argtypes = [C.c_char_p, C.POINTER(vp)]
+        L.oge_bam_buffer_free.argtypes = [vp]
+        L.oge_bam_buffer_free.restype = None
+        L.oge_bam_last_error.restype = C.c_char_p
+        for name in EXPORTS:
+            getattr(L, name)
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise BamHostError(rc, lib().oge_bam_last_error().decode("utf-8", "replace"))
+
+
+def _take(ptr, n) -> bytes:
+    try:
+        return C.string_at(ptr.value, n) if n else b""
+    finally:
+        lib().oge_bam_buffer_free(ptr)
+
+
+def bgzf_decompress(data: bytes, threads: int = 0) -> bytes:
+    out, n = C.c_void_p(), C.c_size_t()
+    buf = np.frombuffer(data, dtype=np.uint8)
+    _check(lib().oge_bgzf_decompress(buf.ctypes.data if len(buf) else None, len(buf), threads, C.byref(out), C.byref(n)))
+    return _take(out, n.value)
+
+
+def bgzf_compress(raw: bytes, level: int = 6, threads: int = 0) -> bytes:
+    """The reference's BgzfOutputStream (util/bgzf_output_stream.cpp) block for block, compressed in parallel."""
+    out, n = C.c_void_p(), C.c_size_t()
+    buf = np.frombuffer(raw, dtype=np.uint8)
+    _check(lib().oge_bgzf_compress(buf.ctypes.data if len(buf) else None, len(buf), level, threads, C.byref(out), C.byref(n)))
+    return _take(out, n.value)
+
+
+def header_render(text: str) -> str:
+    """BamHeader(text).toString() of the reference (util/bam_header.cpp:107-262)."""
+    out = C.c_void_p()
+    _check(lib().oge_bam_header_render(text.encode(), C.byref(out)))
+    try:
+        return C.string_at(out.value).decode()
+    finally:
+        lib().oge_bam_buffer_free(out)
+
+
+class HostBam:
+    """One loaded BAM file (oge_bam_file): inflated, framed, header parsed."""
+
+    def __init__(self, path: str, threads: int = 0, pinned: bool = False):
+        self._h = C.c_void_p()
+        alloc = free = None
+        if pinned:      # the inflated stream lands in page-locked memory so that push() is one DMA
+            from . import dedup
+            g = dedup.lib()
+            alloc = C.cast(g.oge_gpu_host_alloc, C.c_void_p)
+            free = C.cast(g.oge_gpu_host_free, C.c_void_p)
+        _check(lib().oge_bam_load(os.fsencode(path), threads, alloc, free, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().oge_bam_close(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def n(self) -> int:
+        return int(lib().oge_bam_n_records(self._h))
+
+    @property
+    def text(self) -> str:
+        return lib().oge_bam_header_text(self._h).decode()
+
+    @property
+    def refs(self):
+        L = lib()
+        return [(L.oge_bam_ref_name(self._h, i).decode(), int(L.oge_bam_ref_len(self._h, i))) for i in range(L.oge_bam_n_ref(self._h))]
+
+    @property
+    def records(self) -> np.ndarray:
+        """A VIEW of the resident record bytes (valid until close / apply_flags with remove_duplicates)."""
+        nb = int(lib().oge_bam_records_bytes(self._h))
+        if nb == 0:
+            return np.zeros(0, dtype=np.uint8)
+        return np.ctypeslib.as_array((C.c_uint8 * nb).from_address(lib().oge_bam_records(self._h)))
+
+    @property
+    def offsets(self) -> np.ndarray:
+        return np.ctypeslib.as_array((C.c_uint64 * (self.n + 1)).from_address(lib().oge_bam_offsets(self._h)))
+
+    def records_ptr(self):
+        return lib().oge_bam_records(self._h), int(lib().oge_bam_records_bytes(self._h)), lib().oge_bam_offsets(self._h)
+
+    def library_table(self):
+        ids, libs, n, unk, nl = C.c_void_p(), C.c_void_p(), C.c_int32(), C.c_int16(), C.c_int32()
+        _check(lib().oge_bam_library_table(self._h, C.byref(ids), C.byref(libs), C.byref(n), C.byref(unk), C.byref(nl)))
+        names = [C.cast(ids.value, C.POINTER(C.c_char_p))[i] for i in range(n.value)]
+        lib_ids = [C.cast(libs.value, C.POINTER(C.c_int16))[i] for i in range(n.value)]
+        return names, lib_ids, int(unk.value), int(nl.value)
+
+    def apply_flags(self, flags: np.ndarray, remove_duplicates: bool = False, threads: int = 0):
+        flags = np.ascontiguousarray(flags, dtype=np.uint16)
+        if len(flags) != self.n:
+            raise ValueError("flags: %d values for %d records" % (len(flags), self.n))
+        _check(lib().oge_bam_apply_flags(self._h, flags.ctypes.data, int(remove_duplicates), threads))
+
+    def store(self, path: str, format: str | None = None, level: int = 6, pg_command_line: str | None = None,
+              pg_version: str = "0.3-b200", threads: int = 0):
+        _check(lib().oge_bam_store(self._h, os.fsencode(path), format.encode() if format else None, level,
+                                   pg_command_line.encode() if pg_command_line else None, pg_version.encode(), threads))
+
+    def timings(self) -> dict:
+        t = (C.c_double * 6)()
+        _check(lib().oge_bam_timings(self._h, t, 6))
+        return dict(zip(("read", "scan", "inflate", "frame", "apply_flags", "store"), (float(x) for x in t)))
+
+
+def dedup_file(in_path: str, out_path: str, remove_duplicates: bool = False, level: int = 6, format: str | None = None,
+               pg_command_line: str | None = None, threads: int = 0, device: int = 0) -> dict:
+    """`openge dedup in.bam -o out.bam` on the GPU, file to file.  -> stats (dedup counters, flag statistics, timings)."""
+    from . import dedup
+    with HostBam(in_path, threads=threads, pinned=True) as bam:
+        refs = bam.refs
+        ctx = dedup.DedupContext(n_ref=len(refs), max_ref_len=max([l for _, l in refs], default=0), device=device,
+                                 remove_duplicates=remove_duplicates)
+        with ctx:
+            ctx.set_header(bam.text)
+            ptr, nbytes, off_ptr = bam.records_ptr()
+            ctx.push_async(ptr, nbytes, off_ptr, bam.n)
+            ctx.run()
+            flags = ctx.flags()
+            out = {"dedup": ctx.stats(), "flagstats": ctx.flagstats()}
+        bam.apply_flags(flags, remove_duplicates, threads)
+        bam.store(out_path, format, level, pg_command_line, threads=threads)
+        out["timings"] = bam.timings()
+        out["n_out"] = bam.n
+    return out

@@ -1,0 +1,160 @@
+// `openge dedup` as one fused host path around the GPU: BAM file in, BAM file out, no per-record objects.
+//
+//   reference (commands/command_dedup.cpp:37-114)                 here
+//   FileReader -> MarkDuplicates -> FileWriter, one OGERead        oge_bam_load (parallel BGZF inflate into a pinned buffer,
+//   per record on three pipeline threads, temp-file spill            framing) -> oge_gpu_dedup_push / _run / _flags (the CUDA
+//                                                                    path) -> oge_bam_apply_flags -> oge_bam_store (parallel
+//                                                                    BGZF deflate, byte-identical blocks)
+//
+// Same flags as the reference's command (commands/commands.cpp:117-132, command_dedup.cpp:29-35):
+//   openge dedup [in.bam] -o out.bam [-r] [-v] [-t N] [-c level] [-F bam|rawbam] [--nopg] [--nosplit] [-T dir] [-d]
+// --nosplit, -T and -d are accepted and have no effect: the result is always that of the canonical single-chain run
+// (`--nosplit -v`), nothing is spilled to disk, and there is one pipeline.  --stats prints the report of
+// the reference's Statistics module (algorithms/statistics.cpp:150-174) for the output stream, counted on the device.
+// Errors: message on stderr, exit(-1), as everywhere in the reference.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <chrono>
+#include <string>
+#include <vector>
+
+#include "oge_bam_host.h"
+#include "oge_gpu_dedup.h"
+
+#ifndef OGE_VERSION_STRING
+#define OGE_VERSION_STRING "0.3-b200"
+#endif
+
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+static void die(const char *what, const char *msg) {
+    fprintf(stderr, "%s: %s Aborting.\n", what, msg);
+    exit(-1);
+}
+
+static void usage() {
+    fprintf(stderr,
+            "usage: oge_dedup_fused [dedup] in.bam -o out.bam [-r] [-v] [-t threads] [-c level] [-F bam|rawbam] [--nopg] [--stats]\n"
+            "                       [--device N] [--nosplit] [-T tmpdir] [-d]\n");
+    exit(-1);
+}
+
+int main(int argc, char **argv) {
+    std::string in, out, format;
+    bool remove_dups = false, verbose = false, nopg = false, stats = false;
+    int threads = 0, level = 6, device = 0;
+    std::string command_line = "openge ";      // commands/commands.cpp:36-40
+    for (int i = 1; i < argc; i++) {
+        command_line += argv[i];
+        command_line += " ";
+    }
+    for (int i = 1; i < argc; i++) {
+        const std::string a = argv[i];
+        auto need = [&]() -> const char * {
+            if (i + 1 >= argc) usage();
+            return argv[++i];
+        };
+        if (a == "dedup" && i == 1) continue;
+        else if (a == "-o" || a == "--out") out = need();
+        else if (a == "-r" || a == "--remove") remove_dups = true;
+        else if (a == "-v" || a == "--verbose") verbose = true;
+        else if (a == "-t" || a == "--threads") threads = atoi(need());
+        else if (a == "-c" || a == "--compression") level = atoi(need());
+        else if (a == "-F" || a == "--format") format = need();
+        else if (a == "-T" || a == "--tmpdir") need();
+        else if (a == "--nopg") nopg = true;
+        else if (a == "--nosplit" || a == "-d" || a == "--nothreads") continue;
+        else if (a == "--stats") stats = true;
+        else if (a == "--device") device = atoi(need());
+        else if (!a.empty() && a[0] == '-') usage();
+        else if (in.empty()) in = a;
+        else if (out.empty()) out = a;
+        else die("oge_dedup_fused", "one input file only (merge inputs with `openge mergesort` first).");
+    }
+    if (in.empty() || out.empty()) usage();
+
+    const double t_start = now_s();
+    oge_bam_file *bam = NULL;
+    if (oge_gpu_device_count() < 1) die("MarkDuplicates (GPU)", "no CUDA device: this path has no CPU fallback.");
+    int rc = oge_bam_load(in.c_str(), threads, oge_gpu_host_alloc, oge_gpu_host_free, &bam);
+    if (rc) die("Error reading BAM", oge_bam_last_error());
+    const uint64_t n = oge_bam_n_records(bam);
+    const double t_loaded = now_s();
+    if (verbose) fprintf(stderr, "Read %llu records.\n", (unsigned long long) n);
+
+    oge_gpu_dedup_config cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.abi_version = OGE_GPU_DEDUP_ABI_VERSION;
+    cfg.device = device;
+    cfg.n_ref = oge_bam_n_ref(bam);
+    for (int32_t i = 0; i < cfg.n_ref; i++)
+        if (oge_bam_ref_len(bam, i) > cfg.max_ref_len) cfg.max_ref_len = oge_bam_ref_len(bam, i);
+    cfg.remove_duplicates = remove_dups ? 1 : 0;
+    cfg.verify_names = -1;
+    cfg.capacity_records = n;
+    cfg.capacity_bytes = oge_bam_records_bytes(bam);
+    oge_gpu_dedup_ctx *ctx = NULL;
+    if ((rc = oge_gpu_dedup_create(&cfg, &ctx))) die("MarkDuplicates (GPU): oge_gpu_dedup_create", oge_gpu_last_error());
+    {
+        const char *const *ids;
+        const int16_t *libs;
+        int32_t n_rg, n_libs;
+        int16_t unknown;
+        oge_bam_library_table(bam, &ids, &libs, &n_rg, &unknown, &n_libs);
+        if ((rc = oge_gpu_dedup_set_readgroups(ctx, ids, libs, n_rg, unknown, n_libs))) die("MarkDuplicates (GPU): set_readgroups", oge_gpu_last_error());
+    }
+    if ((rc = oge_gpu_dedup_push(ctx, oge_bam_records(bam), oge_bam_records_bytes(bam), oge_bam_offsets(bam), n))) die("MarkDuplicates (GPU): push", oge_gpu_last_error());
+    if ((rc = oge_gpu_dedup_run(ctx))) die("MarkDuplicates (GPU): run", oge_gpu_last_error());
+    std::vector<uint16_t> flags(n ? n : 1);
+    if ((rc = oge_gpu_dedup_flags(ctx, flags.data(), n))) die("MarkDuplicates (GPU): flags", oge_gpu_last_error());
+    oge_gpu_dedup_stats st;
+    oge_gpu_dedup_get_stats(ctx, &st);
+    oge_gpu_flagstats fs;
+    memset(&fs, 0, sizeof(fs));
+    if (stats && (rc = oge_gpu_dedup_flagstats(ctx, &fs))) die("Statistics (GPU)", oge_gpu_last_error());
+    oge_gpu_dedup_destroy(ctx);
+    const double t_gpu = now_s();
+    if (verbose) {
+        fprintf(stderr, "Sorted %llu pair ends and %llu fragment ends on the GPU in %.3f ms (%llu kernel launches).\n",
+                (unsigned long long) st.n_pair_entries, (unsigned long long) st.n_frag_entries, st.ms_total, (unsigned long long) st.launches);
+        fprintf(stderr, "Marking %llu records as duplicates.\n", (unsigned long long) st.n_duplicates);
+    }
+
+    if ((rc = oge_bam_apply_flags(bam, flags.data(), remove_dups ? 1 : 0, threads))) die("Error rewriting records", oge_bam_last_error());
+    if ((rc = oge_bam_store(bam, out.c_str(), format.empty() ? NULL : format.c_str(), level, nopg ? NULL : command_line.c_str(),
+                            OGE_VERSION_STRING, threads)))
+        die("Error writing BAM", oge_bam_last_error());
+    const double t_end = now_s();
+
+    if (stats) {      // the report of algorithms/statistics.cpp:150-174 (with -r the reference's Statistics stage would sit
+                      // behind the filter; this one counts before it)
+        const double nr = fs.n_reads ? (double) fs.n_reads : 1.0, np = fs.n_paired ? (double) fs.n_paired : 1.0;
+        printf("Total reads:       %10llu\n", (unsigned long long) fs.n_reads);
+        printf("Mapped reads:      %10llu (%5.1f%%)\n", (unsigned long long) fs.n_mapped, (float) fs.n_mapped / nr * 100);
+        printf("Forward strand:    %10llu (%5.1f%%)\n", (unsigned long long) fs.n_forward_strand, (float) fs.n_forward_strand / nr * 100);
+        printf("Reverse strand:    %10llu (%5.1f%%)\n", (unsigned long long) fs.n_reverse_strand, (float) fs.n_reverse_strand / nr * 100);
+        printf("Failed QC:         %10llu (%5.1f%%)\n", (unsigned long long) fs.n_failed_qc, (float) fs.n_failed_qc / nr * 100);
+        printf("Duplicates:        %10llu (%5.1f%%)\n", (unsigned long long) fs.n_duplicates, (float) fs.n_duplicates / nr * 100);
+        printf("Paired-end reads:  %10llu (%5.1f%%)\n", (unsigned long long) fs.n_paired, (float) fs.n_paired / nr * 100);
+        if (fs.n_paired) {
+            printf("'Proper-pairs':    %10llu (%5.1f%%)\n", (unsigned long long) fs.n_proper_pair, (float) fs.n_proper_pair / np * 100);
+            printf("Both pairs mapped: %10llu (%5.1f%%)\n", (unsigned long long) fs.n_both_mates_mapped, (float) fs.n_both_mates_mapped / np * 100);
+            printf("Read 1:            %10llu\n", (unsigned long long) fs.n_first_mate);
+            printf("Read 2:            %10llu\n", (unsigned long long) fs.n_second_mate);
+            printf("Singletons:        %10llu (%5.1f%%)\n", (unsigned long long) fs.n_singletons, (float) fs.n_singletons / np * 100);
+        }
+        printf("Sorted:            %10s\n", fs.sorted ? "Yes" : "No");
+    }
+    if (verbose) {
+        double t[6];
+        oge_bam_timings(bam, t, 6);
+        fprintf(stderr, "Written %llu records.\n", (unsigned long long) oge_bam_n_records(bam));
+        fprintf(stderr,
+                "Timing: load %.3f s (read %.3f, scan %.3f, inflate %.3f, frame %.3f) | gpu %.3f s (device %.3f ms) | rewrite %.3f s | store %.3f s | total %.3f s\n",
+                t_loaded - t_start, t[0], t[1], t[2], t[3], t_gpu - t_loaded, st.ms_total, t[4], t[5], t_end - t_start);
+    }
+    oge_bam_close(bam);
+    return 0;
+}

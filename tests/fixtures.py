@@ -182,3 +182,26 @@ def sortedness_cases():
     edge2[1025] = (edge2[1025][0], 1, 0)    # second record of a tile: its predecessor's predecessor is in the previous tile
     cases["big_violation_second_of_tile"] = edge2
     return {k: mk(v) for k, v in cases.items()}
+
+
+def header_cases():
+    """BAMs whose header text is NOT in the reference's canonical form: what its writer emits for them is defined
+    by BamHeader(text).toString() (util/bam_header.cpp:107-262).  -> dict name -> BamFile (records of fixture1)"""
+    b1, _ = fixture1()
+    sq = "@SQ\tSN:chr1\tLN:100000\n@SQ\tSN:chr2\tLN:100000\n"
+    texts = {
+        # fields out of the reference's print order, fields it does not know (dropped), KS printed twice
+        "reordered_fields": ("@HD\tVN:1.0\tSO:coordinate\tGO:none\n"
+                             "@SQ\tUR:file:/x.fa\tSN:chr1\tM5:abc\tLN:100000\tAS:hg0\tSP:human\n@SQ\tSN:chr2\tLN:0100000\n"
+                             "@RG\tSM:s\tID:rg1\tLB:libA\tKS:ACGT\tPL:ILLUMINA\tXX:zz\tCN:c\tDS:d\tDT:t\tFO:f\tPG:p\tPI:300\tPU:u\n"
+                             "@RG\tID:rg2\tLB:libB\n"
+                             "@PG\tVN:1\tID:bwa\tPN:bwa\tCL:bwa mem x\tPP:prev\n@PG\tID:openge\n"
+                             "@CO\tfree text\twith a tab\n"),
+        # lines in another order: the reference regroups them HD, SQ, RG, PG, CO
+        "regrouped_lines": "@CO\tfirst\n@RG\tID:rg1\tLB:libA\n" + sq + "@HD\tVN:1.4\tSO:queryname\n@RG\tID:rg2\tLB:libB\n",
+        # no @HD: VN 1.4 / SO unknown is supplied
+        "no_hd": sq + "@RG\tID:rg1\tLB:libA\n@RG\tID:rg2\tLB:libB\n",
+        # the last line has no newline: the reference drops it
+        "unterminated_last_line": "@HD\tVN:1.4\tSO:unsorted\n" + sq + "@RG\tID:rg1\tLB:libA\n@RG\tID:rg2\tLB:libB\n@CO\tdropped",
+    }
+    return {k: bamio.BamFile(text=t, refs=list(b1.refs), records=b1.records, offsets=b1.offsets) for k, t in texts.items()}

@@ -1,0 +1,75 @@
+"""File-to-file throughput of `openge dedup` on the GPU box: the fused path (oge_dedup_fused) next to the compiled
+reference binary, same input file, same flags (--nosplit -v, compression level from --level).
+
+    python tools/bench/fused_file.py --config C2 --scale 0.2 --level 1 [--ref-scale 0.02]
+
+Prints one JSON line: reads/s of both, the fused path's phase split, and whether the two output files are identical
+(checked on the reference-sized sample).  The input BAM is written with the host layer's own parallel BGZF writer."""
+import argparse
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from openge_b200 import _build, bamhost, bamio, synth  # noqa: E402
+
+
+def write_input(path, name, scale, seed):
+    bam = synth.make(name, scale, seed=seed)
+    raw = bamio.serialize_bam_stream(bam)
+    with open(path, "wb") as f:
+        f.write(bamhost.bgzf_compress(raw, 1))
+    return bam.n, len(raw)
+
+
+def run(cmd, timeout):
+    t0 = time.time()
+    r = subprocess.run(cmd, capture_output=True, timeout=timeout)
+    return time.time() - t0, r
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="C2")
+    ap.add_argument("--scale", type=float, default=0.2)
+    ap.add_argument("--ref-scale", type=float, default=0.02)
+    ap.add_argument("--level", type=int, default=6)
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--seed", type=int, default=2)
+    a = ap.parse_args()
+    fused = _build.ensure_fused()
+    ref = _build.REF_BIN if os.path.exists(_build.REF_BIN) else None
+    out = {"config": a.config, "level": a.level, "host_threads": a.threads or os.cpu_count()}
+    with tempfile.TemporaryDirectory(dir="/dev/shm") as d:
+        inp = os.path.join(d, "in.bam")
+        n, raw_bytes = write_input(inp, a.config, a.scale, a.seed)
+        o1 = os.path.join(d, "fused.bam")
+        cmd = [fused, "dedup", inp, "-o", o1, "-v", "--nopg", "-c", str(a.level)] + (["-t", str(a.threads)] if a.threads else [])
+        run(cmd, 1800)      # warm-up: CUDA context, page cache
+        secs, r = run(cmd, 1800)
+        assert r.returncode == 0, r.stderr.decode()[-2000:]
+        timing = [l for l in r.stderr.decode().splitlines() if l.startswith("Timing:")]
+        out["fused"] = {"reads": n, "raw_bytes": raw_bytes, "file_bytes": os.path.getsize(inp), "seconds": secs,
+                        "reads_per_s": n / secs, "phases": timing[-1] if timing else None}
+        if ref:
+            inp2 = os.path.join(d, "in2.bam")
+            n2, _ = write_input(inp2, a.config, a.ref_scale, a.seed)
+            o2, o3 = os.path.join(d, "ref.bam"), os.path.join(d, "fused2.bam")
+            secs2, r2 = run([ref, "-T", d, "--nosplit", "-v", "-c", str(a.level), inp2, o2] + (["-t", str(a.threads)] if a.threads else []), 1800)
+            assert r2.returncode == 0, r2.stderr.decode()[-2000:]
+            _, r3 = run([fused, "dedup", inp2, "-o", o3, "--nopg", "-c", str(a.level)], 1800)
+            assert r3.returncode == 0
+            same = hashlib.sha256(open(o2, "rb").read()).digest() == hashlib.sha256(open(o3, "rb").read()).digest()
+            out["reference"] = {"reads": n2, "seconds": secs2, "reads_per_s": n2 / secs2, "output_files_identical": same}
+            out["speedup_file_to_file"] = out["fused"]["reads_per_s"] / out["reference"]["reads_per_s"]
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
