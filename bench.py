@@ -46,6 +46,11 @@ def env_int(name, default):
 
 # --------------------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region.  The timed region of this bench is tens of milliseconds,
+    which `nvidia-smi -lms` cannot resolve (its first line arrives after the region has ended), so the samples come from
+    NVML in-process on a thread, about one per millisecond; `nvidia-smi` is the fall-back when NVML cannot be loaded.
+    start() begins sampling (call it before the warm-up so that the thread is already running); mark_begin()/mark_end()
+    bracket the timed region and only samples between them are reported."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
@@ -54,43 +59,113 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.samples = []      # (t, sm_mhz, reasons bitmask)
+        self.max_mhz = None
+        self.t_begin = self.t_end = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+
+    def _visible_index(self):
+        # NVML enumerates physical devices; CUDA_VISIBLE_DEVICES remaps the ordinals torch / the library use
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "").strip()
+        if vis:
+            parts = [x.strip() for x in vis.split(",") if x.strip()]
+            if self.gpu < len(parts) and parts[self.gpu].isdigit():
+                return int(parts[self.gpu])
+        return self.gpu
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+            import pynvml
+            pynvml.nvmlInit()
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self._visible_index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+            self._nvml = pynvml
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
+            return
+        except Exception:
+            self._nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self._visible_index()), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        nv = self._nvml
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                mask = int(reasons_fn(self._h))
+                self.samples.append((time.perf_counter(), mhz, mask))
+            except Exception:
+                pass
+            time.sleep(0.0005)
+
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
 
     def stop(self):
+        if self.t_end is None:
+            self.mark_end()
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=2)
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=5)
             except Exception:
                 self.proc.kill()
+        lo = self.t_begin if self.t_begin is not None else -1.0
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 8:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+        if self._nvml is not None:
+            nv = self._nvml
+            bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            inside = [x for x in self.samples if lo <= x[0] <= self.t_end]
+            if not inside and self.samples:      # a region shorter than one poll: the nearest sample
+                inside = [min(self.samples, key=lambda x: abs(x[0] - self.t_end))]
+            for _, mhz, mask in inside:
+                sm.append(mhz)
+                for name, b in bits.items():
+                    if mask & b:
+                        reasons.add(name)
+            mx = [self.max_mhz] if self.max_mhz else []
+            source = "nvml"
+        else:
+            for t, ln in self.lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 8 or not (lo <= t <= self.t_end + 0.05):
+                    continue
+                try:
+                    sm.append(float(f[0]))
+                    mx.append(float(f[1]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            source = "nvidia-smi"
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": source}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm), "source": source}
 
 
 # --------------------------------------------------------------------------------------- workload
@@ -246,12 +321,13 @@ def run_ours(args):
     # ---- device-resident timing
     push_all()
     ctx.sync()
-    for _ in range(args.warmup):
-        ctx.run()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    for _ in range(args.warmup):
+        ctx.run()
     ctx.sync()
     dev_ms, pass_ms, pass_bytes, pass_launches, launches = [], 0.0, 0, 0, 0
+    sampler.mark_begin()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         ctx.run()
@@ -263,6 +339,7 @@ def run_ours(args):
         launches += st["launches"]
     ctx.sync()
     wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    sampler.mark_end()
     clocks = sampler.stop()
     ms_per_step = float(np.mean(dev_ms))
     value = n / (ms_per_step * 1e-3)

@@ -499,12 +499,13 @@ def bench(args, rank, world, local_rank, rec, offs, text, contigs, metric, workl
         st = eng.stats()
         return e0.elapsed_time(e1), st, info, ex.ms
 
-    for _ in range(args.warmup):
-        step()
     sampler = benchmod.ClockSampler(local_rank)
     sampler.start()
+    for _ in range(args.warmup):
+        step()
     dist.barrier()
     torch.cuda.synchronize()
+    sampler.mark_begin()
     t0 = time.perf_counter()
     ms, pass_ms, pass_bytes, pass_launches, launches, ex_ms = [], 0.0, 0, 0, 0, 0.0
     for _ in range(args.steps):
@@ -518,6 +519,7 @@ def bench(args, rank, world, local_rank, rec, offs, text, contigs, metric, workl
     dist.barrier()
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    sampler.mark_end()
     clocks = sampler.stop()
 
     # max over ranks of the event-timed step
