@@ -58,6 +58,22 @@ typedef void (*oge_bam_free_fn)(void *);
 int oge_bam_load(const char *path, int threads, oge_bam_alloc_fn alloc_fn, oge_bam_free_fn free_fn, oge_bam_file **out);
 void oge_bam_close(oge_bam_file *f);
 
+/* Two-stage open for a caller that inflates elsewhere -- the GPU, oge_gpu_dedup_push_bgzf (oge_gpu_dedup.h):
+ *   oge_bam_open_bgzf      reads the file, indexes its BGZF blocks and inflates only the leading block(s) on the host,
+ *                          as far as the header reaches: header text, reference list and the stream offset of the
+ *                          first record are known afterwards (everything below except records/offsets works);
+ *   oge_bam_bgzf_index     the compressed bytes and the block table to hand to the inflater; header_bytes = inflated
+ *                          bytes in front of the first record;
+ *   oge_bam_records_buffer the (alloc_fn) buffer that has to receive the inflated bytes from header_bytes on
+ *                          (total inflated size - header_bytes of them);
+ *   oge_bam_frame_records  frames the record chain in that buffer (BamDeserializer::read, :144-172) and frees the
+ *                          compressed copy.  From here on the object is the same as after oge_bam_load. */
+int oge_bam_open_bgzf(const char *path, int threads, oge_bam_alloc_fn alloc_fn, oge_bam_free_fn free_fn, oge_bam_file **out);
+int oge_bam_bgzf_index(const oge_bam_file *f, const uint8_t **comp, uint64_t *comp_bytes, const uint64_t **block_in_off,
+                       const uint32_t **block_csize, const uint32_t **block_isize, uint64_t *n_blocks, uint64_t *header_bytes);
+uint8_t *oge_bam_records_buffer(oge_bam_file *f);
+int oge_bam_frame_records(oge_bam_file *f);
+
 const char *oge_bam_header_text(const oge_bam_file *f);        /* as stored in the file */
 int32_t oge_bam_n_ref(const oge_bam_file *f);
 const char *oge_bam_ref_name(const oge_bam_file *f, int32_t i);

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define OGE_GPU_DEDUP_ABI_VERSION 3
+#define OGE_GPU_DEDUP_ABI_VERSION 4
 
 enum {
     OGE_OK = 0,
@@ -86,6 +86,10 @@ typedef struct oge_gpu_dedup_stats {
     float ms_sort_pass_kernels;     /* summed duration of the pass launches of the last run */
     uint32_t sort_pass_launches;
     uint64_t sort_pass_bytes;       /* algorithmic bytes of those launches: 32 per entry (16 read + 16 written) */
+    /* oge_gpu_dedup_push_bgzf: the inflate kernel on its own (CUDA events around the launch) */
+    float ms_inflate;
+    uint32_t reserved0;
+    uint64_t inflate_blocks, inflate_bytes_in, inflate_bytes_out;
 } oge_gpu_dedup_stats;
 
 /* Per-record view of the end-building kernel (buildReadEnds, mark_duplicates.cpp:147-164). */
@@ -120,6 +124,21 @@ int oge_gpu_dedup_set_readgroups(oge_gpu_dedup_ctx *ctx, const char *const *ids,
 int oge_gpu_dedup_push(oge_gpu_dedup_ctx *ctx, const uint8_t *records, uint64_t nbytes,
                        const uint64_t *offsets, uint64_t nrec);
 int oge_gpu_dedup_sync(oge_gpu_dedup_ctx *ctx);
+
+/* The same input side for a BGZF-compressed BAM file, with the inflate on the device: stands in for
+ * BgzfInputStream::BgzfBlock::decompress (util/bgzf_input_stream.cpp:65-142; one zlib call per block, raw deflate,
+ * window 15; like there the inflated size is checked and the CRC is not) for every block of the file at once, one
+ * warp per block.  comp = the whole file in host memory; the block table comes from the file's block headers
+ * (oge_bam_bgzf_index in oge_bam_host.h: offset, BSIZE + 1 and ISIZE of every block); header_bytes = inflated bytes in
+ * front of the first record (magic, header text, reference list), which stay out of the record array.  host_copy
+ * (optional) receives the inflated record bytes (total ISIZE - header_bytes) for the host side of the pipeline
+ * (framing, the output file).  Synchronous.  Must be the only push of the context, followed by ONE
+ * oge_gpu_dedup_set_offsets with the record chain framed from those bytes (BamDeserializer::read,
+ * util/bam_deserializer.h:144-172). */
+int oge_gpu_dedup_push_bgzf(oge_gpu_dedup_ctx *ctx, const uint8_t *comp, uint64_t comp_bytes, const uint64_t *block_in_off,
+                            const uint32_t *block_csize, const uint32_t *block_isize, uint64_t n_blocks, uint64_t header_bytes,
+                            uint8_t *host_copy);
+int oge_gpu_dedup_set_offsets(oge_gpu_dedup_ctx *ctx, const uint64_t *offsets, uint64_t nrec);
 
 /* buildSortedReadEndLists + generateDuplicateIndexes + the flag rewrite of runInternal
  * (mark_duplicates.cpp:185-279, 326-400, 443-465) over everything pushed so far.  Idempotent:

@@ -17,7 +17,7 @@ from . import _build
 
 ERRORS = {-1: "OGE_BAM_ERR_IO", -2: "OGE_BAM_ERR_FORMAT", -3: "OGE_BAM_ERR_NOMEM", -4: "OGE_BAM_ERR_ARG"}
 
-EXPORTS = ["oge_bam_load", "oge_bam_close", "oge_bam_header_text", "oge_bam_n_ref", "oge_bam_ref_name", "oge_bam_ref_len",
+EXPORTS = ["oge_bam_load", "oge_bam_open_bgzf", "oge_bam_bgzf_index", "oge_bam_records_buffer", "oge_bam_frame_records", "oge_bam_close", "oge_bam_header_text", "oge_bam_n_ref", "oge_bam_ref_name", "oge_bam_ref_len",
            "oge_bam_records", "oge_bam_records_bytes", "oge_bam_offsets", "oge_bam_n_records", "oge_bam_library_table",
            "oge_bam_apply_flags", "oge_bam_store", "oge_bam_timings", "oge_bgzf_decompress", "oge_bgzf_compress",
            "oge_bam_header_render", "oge_bam_buffer_free", "oge_bam_last_error"]
@@ -41,6 +41,11 @@ def lib():
         L = C.CDLL(path)
         vp, u64 = C.c_void_p, C.c_uint64
         L.oge_bam_load.argtypes = [C.c_char_p, C.c_int, vp, vp, C.POINTER(vp)]
+        L.oge_bam_open_bgzf.argtypes = [C.c_char_p, C.c_int, vp, vp, C.POINTER(vp)]
+        L.oge_bam_bgzf_index.argtypes = [vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]
+        L.oge_bam_records_buffer.argtypes = [vp]
+        L.oge_bam_records_buffer.restype = vp
+        L.oge_bam_frame_records.argtypes = [vp]
         L.oge_bam_close.argtypes = [vp]
         L.oge_bam_close.restype = None
         L.oge_bam_header_text.argtypes = [vp]
@@ -115,7 +120,9 @@ def header_render(text: str) -> str:
 class HostBam:
     """One loaded BAM file (oge_bam_file): inflated, framed, header parsed."""
 
-    def __init__(self, path: str, threads: int = 0, pinned: bool = False):
+    def __init__(self, path: str, threads: int = 0, pinned: bool = False, defer_inflate: bool = False):
+        """defer_inflate: two-stage open (oge_bam_open_bgzf) -- only the header is inflated here; the caller inflates
+        the blocks of bgzf_index() into records_buffer() (the GPU does: DedupContext.push_bgzf) and calls frame_records()."""
         self._h = C.c_void_p()
         alloc = free = None
         if pinned:      # the inflated stream lands in page-locked memory so that push() is one DMA
@@ -123,7 +130,23 @@ class HostBam:
             g = dedup.lib()
             alloc = C.cast(g.oge_gpu_host_alloc, C.c_void_p)
             free = C.cast(g.oge_gpu_host_free, C.c_void_p)
-        _check(lib().oge_bam_load(os.fsencode(path), threads, alloc, free, C.byref(self._h)))
+        fn = lib().oge_bam_open_bgzf if defer_inflate else lib().oge_bam_load
+        _check(fn(os.fsencode(path), threads, alloc, free, C.byref(self._h)))
+
+    def bgzf_index(self) -> dict:
+        comp, nb, io, cs, isz, n, hb = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint64(), C.c_uint64()
+        _check(lib().oge_bam_bgzf_index(self._h, C.byref(comp), C.byref(nb), C.byref(io), C.byref(cs), C.byref(isz), C.byref(n), C.byref(hb)))
+        return {"comp": comp.value, "comp_bytes": int(nb.value), "in_off": io.value, "csize": cs.value, "isize": isz.value,
+                "n_blocks": int(n.value), "header_bytes": int(hb.value)}
+
+    def records_buffer(self) -> int:
+        p = lib().oge_bam_records_buffer(self._h)
+        if not p:
+            _check(-3)
+        return p
+
+    def frame_records(self):
+        _check(lib().oge_bam_frame_records(self._h))
 
     def close(self):
         if self._h:
@@ -195,20 +218,33 @@ class HostBam:
 
 
 def dedup_file(in_path: str, out_path: str, remove_duplicates: bool = False, level: int = 6, format: str | None = None,
-               pg_command_line: str | None = None, threads: int = 0, device: int = 0) -> dict:
-    """`openge dedup in.bam -o out.bam` on the GPU, file to file.  -> stats (dedup counters, flag statistics, timings)."""
+               pg_command_line: str | None = None, threads: int = 0, device: int = 0, gpu_inflate: bool = True,
+               pinned: bool = False) -> dict:
+    """`openge dedup in.bam -o out.bam` on the GPU, file to file.  -> stats (dedup counters, flag statistics, timings).
+    gpu_inflate: the BGZF blocks are inflated on the device (DedupContext.push_bgzf), else by the host threads."""
     from . import dedup
-    with HostBam(in_path, threads=threads, pinned=True) as bam:
+    with open(in_path, "rb") as fh:
+        is_bgzf = fh.read(2) == b"\x1f\x8b"
+    gpu_inflate = gpu_inflate and is_bgzf
+    with HostBam(in_path, threads=threads, pinned=pinned, defer_inflate=gpu_inflate) as bam:
         refs = bam.refs
         ctx = dedup.DedupContext(n_ref=len(refs), max_ref_len=max([l for _, l in refs], default=0), device=device,
                                  remove_duplicates=remove_duplicates)
         with ctx:
             ctx.set_header(bam.text)
-            ptr, nbytes, off_ptr = bam.records_ptr()
-            ctx.push_async(ptr, nbytes, off_ptr, bam.n)
+            if gpu_inflate:
+                ix = bam.bgzf_index()
+                ctx.push_bgzf(ix["comp"], ix["comp_bytes"], ix["in_off"], ix["csize"], ix["isize"], ix["n_blocks"], ix["header_bytes"],
+                              bam.records_buffer())
+                bam.frame_records()
+                ptr, nbytes, off_ptr = bam.records_ptr()
+                ctx.set_offsets(off_ptr, bam.n, nbytes)
+            else:
+                ptr, nbytes, off_ptr = bam.records_ptr()
+                ctx.push_async(ptr, nbytes, off_ptr, bam.n)
             ctx.run()
             flags = ctx.flags()
-            out = {"dedup": ctx.stats(), "flagstats": ctx.flagstats()}
+            out = {"dedup": ctx.stats(), "flagstats": ctx.flagstats(), "gpu_inflate": gpu_inflate}
         bam.apply_flags(flags, remove_duplicates, threads)
         bam.store(out_path, format, level, pg_command_line, threads=threads)
         out["timings"] = bam.timings()

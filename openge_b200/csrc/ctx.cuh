@@ -86,6 +86,8 @@ struct oge_gpu_dedup_ctx {
     DevBuf<uint8_t> rec;
     DevBuf<uint64_t> off;
     uint64_t n = 0, rec_bytes = 0;
+    uint64_t rec_lead = 0;      // records start at rec.p + rec_lead (non-zero after push_bgzf: the BAM header sits in front)
+    uint8_t *recs() const { return rec.p + rec_lead; }
 
     // read-group table
     DevBuf<uint8_t> rg_bytes;

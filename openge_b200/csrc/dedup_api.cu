@@ -283,9 +283,93 @@ int oge_gpu_dedup_set_readgroups(oge_gpu_dedup_ctx *c, const char *const *ids, c
     return OGE_OK;
 }
 
+int oge_gpu_dedup_push_bgzf(oge_gpu_dedup_ctx *c, const uint8_t *comp, uint64_t comp_bytes, const uint64_t *block_in_off,
+                            const uint32_t *block_csize, const uint32_t *block_isize, uint64_t n_blocks, uint64_t header_bytes,
+                            uint8_t *host_copy) {
+    if (!c || !comp || !block_in_off || !block_csize || !block_isize) return fail_msg(OGE_ERR_INVALID_ARG, "push_bgzf: null argument");
+    if (c->n || c->rec_bytes) return fail_msg(OGE_ERR_STATE, "push_bgzf: the context already holds records (oge_gpu_dedup_reset first)");
+    OGE_CUDA_TRY(cudaSetDevice(c->cfg.device));
+    std::vector<uint64_t> out_off(n_blocks + 1);
+    uint64_t total = 0;
+    for (uint64_t b = 0; b < n_blocks; b++) {
+        if (block_csize[b] < 26 || block_isize[b] > 65536 || block_in_off[b] + block_csize[b] > comp_bytes)
+            return fail_msg(OGE_ERR_BAD_RECORD, "push_bgzf: block %llu does not fit the file or inflates to more than 65536 bytes", (unsigned long long) b);
+        out_off[b] = total;
+        total += block_isize[b];
+    }
+    out_off[n_blocks] = total;
+    if (header_bytes > total) return fail_msg(OGE_ERR_INVALID_ARG, "push_bgzf: header_bytes beyond the inflated stream");
+    const uint64_t rec_bytes = total - header_bytes;
+    const uint64_t lead = (header_bytes + 255) & ~255ull;      // the first record lands on a 256-byte boundary of the buffer
+    cudaStream_t s = c->stream;
+    int rc;
+    if ((rc = c->rec.reserve(lead + rec_bytes, false, s))) return rc;
+    DevBuf<uint8_t> zcomp;
+    DevBuf<uint64_t> zoff;       // in_off[n_blocks], out_off[n_blocks + 1]
+    DevBuf<uint32_t> zcs;        // csize[n_blocks], err[2]
+    auto done = [&](int code) {
+        zcomp.release();
+        zoff.release();
+        zcs.release();
+        return code;
+    };
+    if ((rc = zcomp.reserve(comp_bytes + 64, false, s)) || (rc = zoff.reserve(2 * n_blocks + 1, false, s)) || (rc = zcs.reserve(n_blocks + 2, false, s)))
+        return done(rc);
+    cudaEvent_t e0 = c->ev[8], e1 = c->ev[9];
+    cudaError_t e = cudaMemsetAsync(zcomp.p + comp_bytes, 0, 64, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(zcomp.p, comp, comp_bytes, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(zoff.p, block_in_off, n_blocks * 8, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(zoff.p + n_blocks, out_off.data(), (n_blocks + 1) * 8, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(zcs.p, block_csize, n_blocks * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(zcs.p + n_blocks, 0, 8, s);
+    if (e == cudaSuccess) e = cudaEventRecord(e0, s);
+    if (e != cudaSuccess) return done(fail_cuda(e, "push_bgzf upload", __FILE__, __LINE__));
+    BgzfParams P;
+    P.comp = zcomp.p;
+    P.in_off = zoff.p;
+    P.out_off = zoff.p + n_blocks;
+    P.csize = zcs.p;
+    P.n_blocks = n_blocks;
+    P.out = c->rec.p + (lead - header_bytes);
+    P.err = zcs.p + n_blocks;
+    uint64_t launches = 0;
+    if ((rc = launch_bgzf_inflate(P, c->sms, s, &launches))) return done(rc);
+    uint32_t err[2] = {0, 0};
+    e = cudaEventRecord(e1, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(err, zcs.p + n_blocks, 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && host_copy && rec_bytes) e = cudaMemcpyAsync(host_copy, c->rec.p + lead, rec_bytes, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return done(fail_cuda(e, "push_bgzf inflate", __FILE__, __LINE__));
+    if (err[0]) return done(fail_msg(OGE_ERR_BAD_RECORD, "Zlib inflate failed (BGZF block %u, code %u).", err[1], err[0]));
+    c->stats.ms_inflate = ms_between(e0, e1);
+    c->stats.inflate_blocks = n_blocks;
+    c->stats.inflate_bytes_in = comp_bytes;
+    c->stats.inflate_bytes_out = total;
+    c->rec_lead = lead;
+    c->rec_bytes = rec_bytes;
+    c->n = 0;
+    c->ran = false;
+    return done(OGE_OK);
+}
+
+int oge_gpu_dedup_set_offsets(oge_gpu_dedup_ctx *c, const uint64_t *offsets, uint64_t nrec) {
+    if (!c || !offsets) return fail_msg(OGE_ERR_INVALID_ARG, "set_offsets: null argument");
+    if (c->n || !c->rec_lead) return fail_msg(OGE_ERR_STATE, "set_offsets: follows oge_gpu_dedup_push_bgzf, once");
+    if (offsets[0] != 0 || offsets[nrec] != c->rec_bytes) return fail_msg(OGE_ERR_BAD_RECORD, "set_offsets: offsets[0] must be 0 and offsets[nrec] the inflated record bytes");
+    if (nrec >= (1ull << 30)) return fail_msg(OGE_ERR_TOO_LARGE, "set_offsets: more than 2^30-1 records in one context");
+    OGE_CUDA_TRY(cudaSetDevice(c->cfg.device));
+    int rc;
+    if ((rc = c->off.reserve(nrec + 1, false, c->copy_stream))) return rc;
+    OGE_CUDA_TRY(cudaMemcpyAsync(c->off.p, offsets, (nrec + 1) * 8, cudaMemcpyHostToDevice, c->copy_stream));
+    c->n = nrec;
+    c->ran = false;
+    return OGE_OK;
+}
+
 int oge_gpu_dedup_push(oge_gpu_dedup_ctx *c, const uint8_t *records, uint64_t nbytes, const uint64_t *offsets, uint64_t nrec) {
     if (!c || (nrec && (!records || !offsets))) return fail_msg(OGE_ERR_INVALID_ARG, "push: null argument");
     if (nrec == 0) return OGE_OK;
+    if (c->rec_lead) return fail_msg(OGE_ERR_STATE, "push: the context holds an inflated BGZF file (oge_gpu_dedup_reset first)");
     if (offsets[0] != 0 || offsets[nrec] != nbytes) return fail_msg(OGE_ERR_BAD_RECORD, "push: offsets[0] must be 0 and offsets[nrec] == nbytes");
     if (c->n + nrec >= (1ull << 30)) return fail_msg(OGE_ERR_TOO_LARGE, "push: more than 2^30-1 records in one context");
     OGE_CUDA_TRY(cudaSetDevice(c->cfg.device));
@@ -321,6 +405,7 @@ int oge_gpu_dedup_reset(oge_gpu_dedup_ctx *c) {
     if (rc) return rc;
     c->n = 0;
     c->rec_bytes = 0;
+    c->rec_lead = 0;
     c->ran = false;
     return OGE_OK;
 }
@@ -353,7 +438,7 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
 
     // ---- K1 end-build
     EndbuildParams eb;
-    eb.rec = c->rec.p; eb.off = c->off.p; eb.n = n; eb.idx_base = c->cfg.index_base;
+    eb.rec = c->recs(); eb.off = c->off.p; eb.n = n; eb.idx_base = c->cfg.index_base;
     eb.frag = c->frag.p; eb.hk = c->hk.p; eb.tag = c->tag.p; eb.flag_in = c->flag_in.p;
     eb.counters = c->counters.p; eb.rg = rg_table(c); eb.kl = c->kl;
     if ((rc = launch_endbuild(eb, (uint32_t) (c->rec_bytes / n), c->sms, s, &launches))) return rc;
@@ -376,7 +461,7 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
         if ((rc = c->cplx_slots.reserve(n_pe / 3 + 1024, false, s))) return rc;
         OGE_CUDA_TRY(cudaMemsetAsync(c->table.p, 0, n_slots * sizeof(MateSlot), s));
         JoinParams jp;
-        jp.rec = c->rec.p; jp.off = c->off.p; jp.n = n; jp.idx_base = c->cfg.index_base;
+        jp.rec = c->recs(); jp.off = c->off.p; jp.n = n; jp.idx_base = c->cfg.index_base;
         jp.frag = c->frag.p; jp.hk = c->hk.p; jp.tag = c->tag.p;
         jp.table = c->table.p; jp.n_slots = n_slots;
         jp.pair = c->pair.p; jp.pair_far = c->pairf.p; jp.mate_of = c->mate_of.p; jp.cplx = c->sortbuf.p; jp.cplx_slots = c->cplx_slots.p;
@@ -492,7 +577,7 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
 
     // ---- K5 flag write
     FlagParams fp;
-    fp.rec = c->rec.p; fp.off = c->off.p; fp.n = n; fp.flag_in = c->flag_in.p; fp.flag_out = c->flag_out.p;
+    fp.rec = c->recs(); fp.off = c->off.p; fp.n = n; fp.flag_in = c->flag_in.p; fp.flag_out = c->flag_out.p;
     fp.dup = c->dup.p; fp.counters = c->counters.p; fp.quiet_index_bug = c->cfg.compat_quiet_index_bug;
     if ((rc = launch_flags(fp, s, &launches))) return rc;
     OGE_CUDA_TRY(cudaEventRecord(c->ev[7], s));
@@ -557,7 +642,7 @@ int oge_gpu_dedup_pull(oge_gpu_dedup_ctx *c, uint8_t *out_records, uint64_t cap_
     if (!c->cfg.remove_duplicates) {
         if (cap_bytes < c->rec_bytes || !out_records) return fail_msg(OGE_ERR_INVALID_ARG, "pull: need %llu bytes", (unsigned long long) c->rec_bytes);
         if (out_offsets && cap_records < c->n + 1) return fail_msg(OGE_ERR_INVALID_ARG, "pull: need %llu offsets", (unsigned long long) c->n + 1);
-        OGE_CUDA_TRY(cudaMemcpyAsync(out_records, c->rec.p, c->rec_bytes, cudaMemcpyDeviceToHost, s));
+        OGE_CUDA_TRY(cudaMemcpyAsync(out_records, c->recs(), c->rec_bytes, cudaMemcpyDeviceToHost, s));
         if (out_offsets) OGE_CUDA_TRY(cudaMemcpyAsync(out_offsets, c->off.p, (c->n + 1) * 8, cudaMemcpyDeviceToHost, s));
         OGE_CUDA_TRY(cudaStreamSynchronize(s));
         *out_bytes = c->rec_bytes;
@@ -571,7 +656,7 @@ int oge_gpu_dedup_pull(oge_gpu_dedup_ctx *c, uint8_t *out_records, uint64_t cap_
     uint64_t launches = 0;
     if ((rc = tmp_rec.reserve(c->rec_bytes, false, s))) return rc;
     if ((rc = tmp_off.reserve(c->n + 1, false, s))) { tmp_rec.release(); return rc; }
-    rc = launch_compact(c->rec.p, c->off.p, c->n, c->flag_out.p, 1, tmp_rec.p, tmp_off.p, reinterpret_cast<uint64_t *>(c->scratch.p),
+    rc = launch_compact(c->recs(), c->off.p, c->n, c->flag_out.p, 1, tmp_rec.p, tmp_off.p, reinterpret_cast<uint64_t *>(c->scratch.p),
                         c->counters.p, s, &launches);
     uint64_t totals[2] = {0, 0};
     if (!rc && cudaMemcpyAsync(totals, c->scratch.p, 16, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = fail_cuda(cudaGetLastError(), "pull totals", __FILE__, __LINE__);
@@ -598,7 +683,7 @@ int oge_gpu_dedup_flagstats(oge_gpu_dedup_ctx *c, oge_gpu_flagstats *out) {
     int rc = tmp.reserve(flagstat_scratch_bytes(c->n), false, c->stream);
     if (rc) return rc;
     uint64_t launches = 0;
-    rc = launch_flagstats(c->rec.p, c->off.p, c->flag_out.p, c->n, tmp.p, c->sms, c->stream, &launches);
+    rc = launch_flagstats(c->recs(), c->off.p, c->flag_out.p, c->n, tmp.p, c->sms, c->stream, &launches);
     if (!rc && cudaMemcpyAsync(out, tmp.p, sizeof(*out), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
         rc = fail_cuda(cudaGetLastError(), "flagstats copy", __FILE__, __LINE__);
     if (!rc && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail_cuda(cudaGetLastError(), "flagstats sync", __FILE__, __LINE__);
@@ -675,7 +760,7 @@ int oge_gpu_copy_d2d(oge_gpu_dedup_ctx *c, void *dst, const void *src, uint64_t 
 
 int oge_gpu_dedup_device_ptrs(oge_gpu_dedup_ctx *c, void **records, void **offsets, void **flags) {
     if (!c) return fail_msg(OGE_ERR_INVALID_ARG, "device_ptrs: null context");
-    if (records) *records = c->rec.p;
+    if (records) *records = c->recs();
     if (offsets) *offsets = c->off.p;
     if (flags) *flags = c->flag_out.p;
     return OGE_OK;

@@ -130,6 +130,18 @@ struct FlagParams {
 
 int launch_flags(const FlagParams &P, cudaStream_t stream, uint64_t *launches);
 
+// ---- BGZF inflate (bgzf_inflate.cu): one warp per block
+struct BgzfParams {
+    const uint8_t *comp;        // the compressed file
+    const uint64_t *in_off;     // [n_blocks] byte offset of every block in comp
+    const uint32_t *csize;      // [n_blocks] BSIZE + 1
+    const uint64_t *out_off;    // [n_blocks + 1] byte offset of every block's payload in the inflated stream
+    uint64_t n_blocks;
+    uint8_t *out;               // where byte 0 of the inflated stream goes
+    uint32_t *err;              // [2]: first inflate error code, block index
+};
+int launch_bgzf_inflate(const BgzfParams &P, int sms, cudaStream_t stream, uint64_t *launches);
+
 // ---- flag statistics (flagstat.cu): Statistics::runInternal's counters over the resident records
 enum {
     FS_READS = 0, FS_MAPPED, FS_FORWARD, FS_REVERSE, FS_FAILED_QC, FS_DUPLICATES, FS_PAIRED, FS_PROPER_PAIR,

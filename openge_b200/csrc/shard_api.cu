@@ -210,7 +210,7 @@ int oge_gpu_shard_begin(oge_gpu_dedup_ctx *c, void **pub_dev, uint64_t *n_pub, v
         PhaseClock clk(c, &c->stats.ms_endbuild);
         OGE_CUDA_TRY(cudaMemsetAsync(c->dup.p, 0, n, s));
         EndbuildParams eb;
-        eb.rec = c->rec.p; eb.off = c->off.p; eb.n = n; eb.idx_base = c->cfg.index_base;
+        eb.rec = c->recs(); eb.off = c->off.p; eb.n = n; eb.idx_base = c->cfg.index_base;
         eb.frag = c->frag.p; eb.hk = c->hk.p; eb.tag = c->tag.p; eb.flag_in = c->flag_in.p;
         eb.counters = c->counters.p; eb.rg = rg_table(c); eb.kl = c->kl;
         if ((rc = launch_endbuild(eb, (uint32_t) (c->rec_bytes / n), c->sms, s, &launches))) return rc;
@@ -235,7 +235,7 @@ int oge_gpu_shard_begin(oge_gpu_dedup_ctx *c, void **pub_dev, uint64_t *n_pub, v
         if ((rc = sh.pub_list.reserve(n_pe + 16, false, s))) return rc;
         OGE_CUDA_TRY(cudaMemsetAsync(c->table.p, 0, sh.n_slots * sizeof(MateSlot), s));
         JoinParams jp;
-        jp.rec = c->rec.p; jp.off = c->off.p; jp.n = n; jp.idx_base = c->cfg.index_base;
+        jp.rec = c->recs(); jp.off = c->off.p; jp.n = n; jp.idx_base = c->cfg.index_base;
         jp.frag = c->frag.p; jp.hk = c->hk.p; jp.tag = c->tag.p;
         jp.table = c->table.p; jp.n_slots = sh.n_slots;
         jp.pair = c->pair.p; jp.pair_far = c->pairf.p; jp.mate_of = c->mate_of.p; jp.cplx = c->sortbuf.p; jp.cplx_slots = c->cplx_slots.p;
@@ -607,7 +607,7 @@ int oge_gpu_shard_apply(oge_gpu_dedup_ctx *c, const void *marks_all_dev, uint64_
         PhaseClock clk(c, &c->stats.ms_flags);
         if ((rc = launch_sh_apply_marks((const uint32_t *) marks_all_dev, n_all, c->cfg.index_base, c->n, c->dup.p, s, &launches))) return rc;
         FlagParams fp;
-        fp.rec = c->rec.p; fp.off = c->off.p; fp.n = c->n; fp.flag_in = c->flag_in.p; fp.flag_out = c->flag_out.p;
+        fp.rec = c->recs(); fp.off = c->off.p; fp.n = c->n; fp.flag_in = c->flag_in.p; fp.flag_out = c->flag_out.p;
         fp.dup = c->dup.p; fp.counters = c->counters.p; fp.quiet_index_bug = 0;
         if ((rc = launch_flags(fp, s, &launches))) return rc;
         clk.stop();

@@ -19,7 +19,7 @@ import numpy as np
 from . import _build, header as _header
 from .bamio import BamFile
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 OGE_OK = 0
 ERRORS = {-1: "OGE_ERR_INVALID_ARG", -2: "OGE_ERR_CUDA", -3: "OGE_ERR_NOMEM", -4: "OGE_ERR_KEY_RANGE",
@@ -43,7 +43,9 @@ class Stats(C.Structure):
                 ("ms_total", C.c_float), ("ms_endbuild", C.c_float), ("ms_join", C.c_float),
                 ("ms_sort_frag", C.c_float), ("ms_sort_pair", C.c_float), ("ms_select", C.c_float),
                 ("ms_flags", C.c_float), ("launches", C.c_uint64),
-                ("ms_sort_pass_kernels", C.c_float), ("sort_pass_launches", C.c_uint32), ("sort_pass_bytes", C.c_uint64)]
+                ("ms_sort_pass_kernels", C.c_float), ("sort_pass_launches", C.c_uint32), ("sort_pass_bytes", C.c_uint64),
+                ("ms_inflate", C.c_float), ("reserved0", C.c_uint32), ("inflate_blocks", C.c_uint64),
+                ("inflate_bytes_in", C.c_uint64), ("inflate_bytes_out", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -57,6 +59,7 @@ END_DTYPE = np.dtype([("eligible", "<i4"), ("pair_eligible", "<i4"), ("ref", "<i
                       ("orientation", "<i4"), ("read2Sequence", "<i4"), ("score", "<i2"), ("lib", "<i2")])
 
 EXPORTS = ["oge_gpu_dedup_create", "oge_gpu_dedup_destroy", "oge_gpu_dedup_set_readgroups", "oge_gpu_dedup_push",
+           "oge_gpu_dedup_push_bgzf", "oge_gpu_dedup_set_offsets",
            "oge_gpu_dedup_sync", "oge_gpu_dedup_run", "oge_gpu_dedup_flags", "oge_gpu_dedup_pull",
            "oge_gpu_dedup_reset", "oge_gpu_dedup_flagstats", "oge_gpu_dedup_get_stats", "oge_gpu_dedup_debug_ends",
            "oge_gpu_dedup_device_ptrs", "oge_gpu_host_alloc", "oge_gpu_host_free", "oge_gpu_device_count",
@@ -89,6 +92,8 @@ def lib():
         L.oge_gpu_dedup_set_readgroups.argtypes = [vp, C.POINTER(C.c_char_p), vp, C.c_int32, C.c_int16, C.c_int32]
         L.oge_gpu_dedup_push.argtypes = [vp, vp, u64, vp, u64]
         L.oge_gpu_dedup_sync.argtypes = [vp]
+        L.oge_gpu_dedup_push_bgzf.argtypes = [vp, vp, u64, vp, vp, vp, u64, u64, vp]
+        L.oge_gpu_dedup_set_offsets.argtypes = [vp, vp, u64]
         L.oge_gpu_dedup_run.argtypes = [vp]
         L.oge_gpu_dedup_flags.argtypes = [vp, vp, u64]
         L.oge_gpu_dedup_pull.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64), C.POINTER(u64)]
@@ -227,6 +232,15 @@ class DedupContext:
         _check(lib().oge_gpu_dedup_push(self._h, records_ptr, nbytes, offsets_ptr, nrec))
         self.n += nrec
         self.nbytes += nbytes
+
+    def push_bgzf(self, comp_ptr, comp_bytes, in_off_ptr, csize_ptr, isize_ptr, n_blocks, header_bytes, host_copy_ptr=None):
+        """Inflate a whole BGZF file on the device (one warp per block); records land in HBM, and in host_copy."""
+        _check(lib().oge_gpu_dedup_push_bgzf(self._h, comp_ptr, comp_bytes, in_off_ptr, csize_ptr, isize_ptr, n_blocks, header_bytes, host_copy_ptr))
+
+    def set_offsets(self, offsets_ptr, nrec, nbytes):
+        _check(lib().oge_gpu_dedup_set_offsets(self._h, offsets_ptr, nrec))
+        self.n = nrec
+        self.nbytes = nbytes
 
     def sync(self):
         _check(lib().oge_gpu_dedup_sync(self._h))

@@ -441,7 +441,127 @@ struct oge_bam_file {
     int16_t unknown_lib = 1;
     int32_t n_libs = 1;
     double t[6] = {0, 0, 0, 0, 0, 0};
+    // two-stage open (oge_bam_open_bgzf): the compressed file and its block index, until the records are framed
+    uint8_t *comp = nullptr;
+    uint64_t comp_bytes = 0;
+    BlockIndex ix;
 };
+
+namespace {
+
+constexpr int NEED_MORE = 1;      // parse_stream_header: the bytes seen so far end inside the header
+
+int read_whole_file(const char *path, int threads, uint8_t **out, size_t *out_n) {
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(OGE_BAM_ERR_IO, "cannot open %s: %s", path, strerror(errno));
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); return fail(OGE_BAM_ERR_IO, "cannot stat %s", path); }
+    const size_t fsize = (size_t) st.st_size;
+    uint8_t *comp = (uint8_t *) malloc(fsize + 64);
+    if (!comp) { close(fd); return fail(OGE_BAM_ERR_NOMEM, "cannot allocate %zu bytes for %s", fsize, path); }
+    memset(comp + fsize, 0, 64);
+    // parallel pread: one range per worker
+    const int rt = (int) std::min<size_t>(threads, std::max<size_t>(1, fsize >> 26));
+    const size_t chunk = (fsize + rt - 1) / rt;
+    const int rc = parallel_run(rt, [&](int w) -> int {
+        size_t at = (size_t) w * chunk;
+        const size_t end = std::min(fsize, at + chunk);
+        while (at < end) {
+            const ssize_t r = pread(fd, comp + at, end - at, (off_t) at);
+            if (r <= 0) return fail(OGE_BAM_ERR_IO, "read error on %s", path);
+            at += (size_t) r;
+        }
+        return 0;
+    });
+    close(fd);
+    if (rc) { free(comp); return rc; }
+    *out = comp;
+    *out_n = fsize;
+    return 0;
+}
+
+// BamDeserializer::open (util/bam_deserializer.h:40-135) over the first n bytes of the inflated stream.
+// complete = these are ALL the bytes of the stream; otherwise running out of bytes returns NEED_MORE.
+int parse_stream_header(oge_bam_file *f, const uint8_t *s, uint64_t n, bool complete) {
+    auto short_of = [&](const char *msg) { return complete ? fail(OGE_BAM_ERR_FORMAT, "%s", msg) : NEED_MORE; };
+    if (n < 12) return short_of("Error reading BAM stream header magic bytes.");
+    if (memcmp(s, "BAM\1", 4) != 0) return fail(OGE_BAM_ERR_FORMAT, "Error reading BAM stream header magic bytes.");
+    const int32_t l_text = rd_i32(s + 4);
+    if (l_text < 0) return fail(OGE_BAM_ERR_FORMAT, "Error reading BAM stream header text.");
+    if (8ull + (uint64_t) l_text + 4 > n) return short_of("Error reading BAM stream header text.");
+    f->text.assign((const char *) s + 8, (size_t) l_text);
+    {   // the reference builds the header from a C string: it ends at the first NUL
+        const size_t z = f->text.find('\0');
+        if (z != std::string::npos) f->text.resize(z);
+    }
+    f->header = HeaderModel();
+    f->refs.clear();
+    int rc = f->header.parse(f->text);
+    if (rc) return rc;
+    uint64_t pos = 8 + (uint64_t) l_text;
+    const int32_t n_ref = rd_i32(s + pos);
+    pos += 4;
+    if (n_ref < 0) return fail(OGE_BAM_ERR_FORMAT, "Error reading BAM stream reference count.");
+    if ((size_t) n_ref != f->header.sq.size())
+        return fail(OGE_BAM_ERR_FORMAT, "BAM header text sequence data count doesn't match reference sequence list. Is this file corrupted?");
+    for (int32_t i = 0; i < n_ref; i++) {
+        if (pos + 4 > n) return short_of("Error reading BAM stream reference sequence name length.");
+        const int32_t l_name = rd_i32(s + pos);
+        pos += 4;
+        if (l_name < 1) return fail(OGE_BAM_ERR_FORMAT, "Error reading BAM stream reference sequence.");
+        if (pos + (uint64_t) l_name + 4 > n) return short_of("Error reading BAM stream reference sequence.");
+        std::string name((const char *) s + pos, (size_t) l_name - 1);
+        pos += (uint64_t) l_name;
+        const int32_t len = rd_i32(s + pos);
+        pos += 4;
+        if (name != f->header.sq[i].name || (long long) len != f->header.sq[i].length)      // :127-131
+            return fail(OGE_BAM_ERR_FORMAT, "BAM header text doesn't match sequence information. Is this file corrupted?");
+        f->refs.emplace_back(name, len);
+    }
+    f->first_record = pos;
+    return 0;
+}
+
+// The record chain: BamDeserializer::read (util/bam_deserializer.h:144-172) over stream[first_record, stream_bytes).
+int frame_chain(oge_bam_file *f) {
+    const uint8_t *s = f->stream;
+    const uint64_t n = f->stream_bytes, base = f->first_record;
+    uint64_t pos = base;
+    f->offsets.reserve((size_t) ((n - pos) / 160 + 16));
+    while (pos < n) {
+        if (pos + 4 > n) return fail(OGE_BAM_ERR_FORMAT, "Expected more bytes reading BAM core. Is this file truncated or corrupted?");
+        __builtin_prefetch(s + pos + 2048);      // the walk is a dependent chain with a stride the hardware prefetcher cannot guess
+        const uint32_t bs = rd_u32(s + pos);
+        if (bs < 32 || bs > 10000) return fail(OGE_BAM_ERR_FORMAT, "Invalid BAM block size(%u).", bs);
+        if (pos + 4 + bs > n) return fail(OGE_BAM_ERR_FORMAT, "Expected more bytes reading BAM core. Is this file truncated or corrupted?");
+        f->offsets.push_back(pos - base);
+        pos += 4 + (uint64_t) bs;
+    }
+    f->offsets.push_back(pos - base);
+    f->rec_bytes = pos - base;
+    return 0;
+}
+
+// library ids (what mark_duplicates.cpp:282-318 resolves per read; only equality of ids matters)
+void build_library_table(oge_bam_file *f) {
+    std::map<std::string, int16_t> ids;
+    int16_t next_id = 1;
+    ids["Unknown Library"] = next_id++;
+    f->rg_ids.clear();
+    f->rg_libs.clear();
+    f->rg_id_ptrs.clear();
+    for (const RgRec &r : f->header.rg) {
+        const std::string lib = r.lb.empty() ? std::string("Unknown Library") : r.lb;
+        if (!ids.count(lib)) ids[lib] = next_id++;
+        f->rg_ids.push_back(r.id);
+        f->rg_libs.push_back(ids[lib]);
+    }
+    for (const std::string &id : f->rg_ids) f->rg_id_ptrs.push_back(id.c_str());
+    f->unknown_lib = 1;
+    f->n_libs = (int32_t) ids.size();
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -452,6 +572,7 @@ void oge_bam_buffer_free(void *p) { free(p); }
 void oge_bam_close(oge_bam_file *f) {
     if (!f) return;
     if (f->stream) (f->free_fn ? f->free_fn : free)(f->stream);
+    free(f->comp);
     delete f;
 }
 
@@ -461,28 +582,11 @@ int oge_bam_load(const char *path, int threads, oge_bam_alloc_fn alloc_fn, oge_b
     threads = clamp_threads(threads);
     *out = nullptr;
     double t0 = now_s();
-    const int fd = open(path, O_RDONLY);
-    if (fd < 0) return fail(OGE_BAM_ERR_IO, "cannot open %s: %s", path, strerror(errno));
-    struct stat st;
-    if (fstat(fd, &st) != 0) { close(fd); return fail(OGE_BAM_ERR_IO, "cannot stat %s", path); }
-    const size_t fsize = (size_t) st.st_size;
-    uint8_t *comp = (uint8_t *) malloc(fsize + 1);
-    if (!comp) { close(fd); return fail(OGE_BAM_ERR_NOMEM, "cannot allocate %zu bytes for %s", fsize, path); }
-    {   // parallel pread: one range per worker
-        const int rt = (int) std::min<size_t>(threads, std::max<size_t>(1, fsize >> 26));
-        const size_t chunk = (fsize + rt - 1) / rt;
-        const int rc = parallel_run(rt, [&](int w) -> int {
-            size_t at = (size_t) w * chunk;
-            const size_t end = std::min(fsize, at + chunk);
-            while (at < end) {
-                const ssize_t r = pread(fd, comp + at, end - at, (off_t) at);
-                if (r <= 0) return fail(OGE_BAM_ERR_IO, "read error on %s", path);
-                at += (size_t) r;
-            }
-            return 0;
-        });
-        close(fd);
-        if (rc) { free(comp); return rc; }
+    uint8_t *comp = nullptr;
+    size_t fsize = 0;
+    {
+        const int rc = read_whole_file(path, threads, &comp, &fsize);
+        if (rc) return rc;
     }
     oge_bam_file *f = new oge_bam_file();
     f->alloc_fn = alloc_fn;
@@ -518,73 +622,104 @@ int oge_bam_load(const char *path, int threads, oge_bam_alloc_fn alloc_fn, oge_b
     comp = nullptr;
     memset(f->stream + f->stream_bytes, 0, 256);
 
-    // ---- header: BamDeserializer::open (util/bam_deserializer.h:40-135)
     t0 = now_s();
-    const uint8_t *s = f->stream;
-    const uint64_t n = f->stream_bytes;
-    if (n < 12 || memcmp(s, "BAM\1", 4) != 0) return bail(fail(OGE_BAM_ERR_FORMAT, "Error reading BAM stream header magic bytes."));
-    const int32_t l_text = rd_i32(s + 4);
-    if (l_text < 0 || 8ull + (uint64_t) l_text + 4 > n) return bail(fail(OGE_BAM_ERR_FORMAT, "Error reading BAM stream header text."));
-    f->text.assign((const char *) s + 8, (size_t) l_text);
-    {   // the reference builds the header from a C string: it ends at the first NUL (:65-79 pass text.c_str()-like data)
-        const size_t z = f->text.find('\0');
-        if (z != std::string::npos) f->text.resize(z);
-    }
-    int rc = f->header.parse(f->text);
+    int rc = parse_stream_header(f, f->stream, f->stream_bytes, true);
     if (rc) return bail(rc);
-    uint64_t pos = 8 + (uint64_t) l_text;
-    const int32_t n_ref = rd_i32(s + pos);
-    pos += 4;
-    if (n_ref < 0) return bail(fail(OGE_BAM_ERR_FORMAT, "Error reading BAM stream reference count."));
-    if ((size_t) n_ref != f->header.sq.size())
-        return bail(fail(OGE_BAM_ERR_FORMAT, "BAM header text sequence data count doesn't match reference sequence list. Is this file corrupted?"));
-    for (int32_t i = 0; i < n_ref; i++) {
-        if (pos + 4 > n) return bail(fail(OGE_BAM_ERR_FORMAT, "Error reading BAM stream reference sequence name length."));
-        const int32_t l_name = rd_i32(s + pos);
-        pos += 4;
-        if (l_name < 1 || pos + (uint64_t) l_name + 4 > n) return bail(fail(OGE_BAM_ERR_FORMAT, "Error reading BAM stream reference sequence."));
-        std::string name((const char *) s + pos, (size_t) l_name - 1);
-        pos += (uint64_t) l_name;
-        const int32_t len = rd_i32(s + pos);
-        pos += 4;
-        if (name != f->header.sq[i].name || (long long) len != f->header.sq[i].length)      // :127-131
-            return bail(fail(OGE_BAM_ERR_FORMAT, "BAM header text doesn't match sequence information. Is this file corrupted?"));
-        f->refs.emplace_back(name, len);
-    }
-    f->first_record = pos;
-
-    // ---- record chain: BamDeserializer::read (:144-172)
-    f->offsets.reserve((size_t) ((n - pos) / 160 + 16));
-    const uint64_t base = pos;
-    while (pos < n) {
-        if (pos + 4 > n) return bail(fail(OGE_BAM_ERR_FORMAT, "Expected more bytes reading BAM core. Is this file truncated or corrupted?"));
-        const uint32_t bs = rd_u32(s + pos);
-        if (bs < 32 || bs > 10000) return bail(fail(OGE_BAM_ERR_FORMAT, "Invalid BAM block size(%u).", bs));
-        if (pos + 4 + bs > n) return bail(fail(OGE_BAM_ERR_FORMAT, "Expected more bytes reading BAM core. Is this file truncated or corrupted?"));
-        f->offsets.push_back(pos - base);
-        pos += 4 + (uint64_t) bs;
-    }
-    f->offsets.push_back(pos - base);
-    f->rec_bytes = pos - base;
-
-    // ---- library ids (what mark_duplicates.cpp:282-318 resolves per read; only equality of ids matters)
-    {
-        std::map<std::string, int16_t> ids;
-        int16_t next_id = 1;
-        ids["Unknown Library"] = next_id++;
-        for (const RgRec &r : f->header.rg) {
-            const std::string lib = r.lb.empty() ? std::string("Unknown Library") : r.lb;
-            if (!ids.count(lib)) ids[lib] = next_id++;
-            f->rg_ids.push_back(r.id);
-            f->rg_libs.push_back(ids[lib]);
-        }
-        for (const std::string &id : f->rg_ids) f->rg_id_ptrs.push_back(id.c_str());
-        f->unknown_lib = 1;
-        f->n_libs = (int32_t) ids.size();
-    }
+    rc = frame_chain(f);
+    if (rc) return bail(rc);
+    build_library_table(f);
     f->t[3] = now_s() - t0;
     *out = f;
     return 0;
+}
+
+// ---- two-stage open for callers that inflate elsewhere (the GPU: oge_gpu_dedup_push_bgzf) -------------------------
+int oge_bam_open_bgzf(const char *path, int threads, oge_bam_alloc_fn alloc_fn, oge_bam_free_fn free_fn, oge_bam_file **out) {
+    if (!path || !out) return fail(OGE_BAM_ERR_ARG, "open_bgzf: null argument");
+    if ((alloc_fn == nullptr) != (free_fn == nullptr)) return fail(OGE_BAM_ERR_ARG, "open_bgzf: alloc_fn and free_fn go together");
+    threads = clamp_threads(threads);
+    *out = nullptr;
+    double t0 = now_s();
+    uint8_t *comp = nullptr;
+    size_t fsize = 0;
+    int rc = read_whole_file(path, threads, &comp, &fsize);
+    if (rc) return rc;
+    oge_bam_file *f = new oge_bam_file();
+    f->alloc_fn = alloc_fn;
+    f->free_fn = free_fn;
+    f->comp = comp;
+    f->comp_bytes = fsize;
+    f->t[0] = now_s() - t0;
+    auto bail = [&](int code) {
+        oge_bam_close(f);
+        return code;
+    };
+    if (fsize >= 4 && memcmp(comp, "BAM\1", 4) == 0) return bail(fail(OGE_BAM_ERR_FORMAT, "open_bgzf: %s is an uncompressed BAM stream (use oge_bam_load)", path));
+    t0 = now_s();
+    if ((rc = bgzf_scan(comp, fsize, f->ix))) return bail(rc);
+    f->t[1] = now_s() - t0;
+    f->stream_bytes = f->ix.out_off.back();
+    // the header decides where the records start: inflate leading blocks on the host until it is complete
+    t0 = now_s();
+    std::vector<uint8_t> head;
+    size_t nb = 0;
+    while (true) {
+        rc = parse_stream_header(f, head.data(), head.size(), nb == f->ix.in_off.size());
+        if (rc == 0) break;
+        if (rc != NEED_MORE) return bail(rc);
+        // next block
+        const size_t b = nb++;
+        const size_t at = head.size();
+        head.resize(at + f->ix.isize[b] + 8);
+        BlockIndex one;
+        one.in_off.push_back(f->ix.in_off[b]);
+        one.csize.push_back(f->ix.csize[b]);
+        one.isize.push_back(f->ix.isize[b]);
+        one.out_off.push_back(0);
+        one.out_off.push_back(f->ix.isize[b]);
+        if ((rc = bgzf_inflate(comp, one, head.data() + at, 1))) return bail(rc);
+        head.resize(at + f->ix.isize[b]);
+    }
+    f->rec_bytes = f->stream_bytes - f->first_record;
+    build_library_table(f);
+    f->t[3] = now_s() - t0;
+    *out = f;
+    return 0;
+}
+
+int oge_bam_bgzf_index(const oge_bam_file *f, const uint8_t **comp, uint64_t *comp_bytes, const uint64_t **block_in_off,
+                       const uint32_t **block_csize, const uint32_t **block_isize, uint64_t *n_blocks, uint64_t *header_bytes) {
+    if (!f || !f->comp) return fail(OGE_BAM_ERR_ARG, "bgzf_index: the file was not opened with oge_bam_open_bgzf");
+    if (comp) *comp = f->comp;
+    if (comp_bytes) *comp_bytes = f->comp_bytes;
+    if (block_in_off) *block_in_off = f->ix.in_off.data();
+    if (block_csize) *block_csize = f->ix.csize.data();
+    if (block_isize) *block_isize = f->ix.isize.data();
+    if (n_blocks) *n_blocks = f->ix.in_off.size();
+    if (header_bytes) *header_bytes = f->first_record;
+    return 0;
+}
+
+uint8_t *oge_bam_records_buffer(oge_bam_file *f) {
+    if (!f || !f->comp) { fail(OGE_BAM_ERR_ARG, "records_buffer: the file was not opened with oge_bam_open_bgzf"); return nullptr; }
+    if (!f->stream) {
+        // laid out like a loaded file (header region left unused) so that every other entry point works unchanged
+        f->stream = (uint8_t *) (f->alloc_fn ? f->alloc_fn(f->stream_bytes + 256) : malloc(f->stream_bytes + 256));
+        if (!f->stream) { fail(OGE_BAM_ERR_NOMEM, "cannot allocate %llu bytes", (unsigned long long) f->stream_bytes + 256); return nullptr; }
+    }
+    return f->stream + f->first_record;
+}
+
+int oge_bam_frame_records(oge_bam_file *f) {
+    if (!f || !f->comp || !f->stream) return fail(OGE_BAM_ERR_ARG, "frame_records: call oge_bam_open_bgzf and fill oge_bam_records_buffer first");
+    const double t0 = now_s();
+    memset(f->stream + f->stream_bytes, 0, 256);
+    free(f->comp);      // the compressed bytes are not needed any more
+    f->comp = nullptr;
+    f->offsets.clear();
+    const int rc = frame_chain(f);
+    f->t[3] += now_s() - t0;
+    return rc;
 }
 
 const char *oge_bam_header_text(const oge_bam_file *f) { return f ? f->text.c_str() : ""; }
@@ -594,7 +729,7 @@ int32_t oge_bam_ref_len(const oge_bam_file *f, int32_t i) { return f && i >= 0 &
 uint8_t *oge_bam_records(oge_bam_file *f) { return f ? f->stream + f->first_record : nullptr; }
 uint64_t oge_bam_records_bytes(const oge_bam_file *f) { return f ? f->rec_bytes : 0; }
 const uint64_t *oge_bam_offsets(const oge_bam_file *f) { return f ? f->offsets.data() : nullptr; }
-uint64_t oge_bam_n_records(const oge_bam_file *f) { return f ? f->offsets.size() - 1 : 0; }
+uint64_t oge_bam_n_records(const oge_bam_file *f) { return f && !f->offsets.empty() ? f->offsets.size() - 1 : 0; }
 
 int oge_bam_library_table(oge_bam_file *f, const char *const **ids, const int16_t **lib_ids, int32_t *n, int16_t *unknown_lib_id,
                           int32_t *n_libs) {
@@ -611,6 +746,7 @@ int oge_bam_apply_flags(oge_bam_file *f, const uint16_t *flags, int remove_dupli
     if (!f || (!flags && oge_bam_n_records(f))) return fail(OGE_BAM_ERR_ARG, "apply_flags: null argument");
     threads = clamp_threads(threads);
     const double t0 = now_s();
+    if (f->offsets.empty()) return fail(OGE_BAM_ERR_ARG, "apply_flags: the records have not been framed yet");
     const uint64_t n = f->offsets.size() - 1;
     uint8_t *rec = f->stream + f->first_record;
     const uint64_t *off = f->offsets.data();

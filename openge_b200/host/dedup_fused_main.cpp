@@ -8,6 +8,9 @@
 //
 // Same flags as the reference's command (commands/commands.cpp:117-132, command_dedup.cpp:29-35):
 //   openge dedup [in.bam] -o out.bam [-r] [-v] [-t N] [-c level] [-F bam|rawbam] [--nopg] [--nosplit] [-T dir] [-d]
+// BGZF input is inflated ON THE GPU (oge_gpu_dedup_push_bgzf: one warp per block; the compressed file crosses PCIe and the
+// records are born in HBM); --cpu-inflate keeps the inflate on the host threads (oge_bam_load).  --pinned puts the host
+// copy of the records in page-locked memory.
 // --nosplit, -T and -d are accepted and have no effect: the result is always that of the canonical single-chain run
 // (`--nosplit -v`), nothing is spilled to disk, and there is one pipeline.  --stats prints the report of
 // the reference's Statistics module (algorithms/statistics.cpp:150-174) for the output stream, counted on the device.
@@ -37,13 +40,13 @@ static void die(const char *what, const char *msg) {
 static void usage() {
     fprintf(stderr,
             "usage: oge_dedup_fused [dedup] in.bam -o out.bam [-r] [-v] [-t threads] [-c level] [-F bam|rawbam] [--nopg] [--stats]\n"
-            "                       [--device N] [--nosplit] [-T tmpdir] [-d]\n");
+            "                       [--device N] [--cpu-inflate] [--pinned] [--nosplit] [-T tmpdir] [-d]\n");
     exit(-1);
 }
 
 int main(int argc, char **argv) {
     std::string in, out, format;
-    bool remove_dups = false, verbose = false, nopg = false, stats = false;
+    bool remove_dups = false, verbose = false, nopg = false, stats = false, cpu_inflate = false, pinned = false;
     int threads = 0, level = 6, device = 0;
     std::string command_line = "openge ";      // commands/commands.cpp:36-40
     for (int i = 1; i < argc; i++) {
@@ -67,6 +70,8 @@ int main(int argc, char **argv) {
         else if (a == "--nopg") nopg = true;
         else if (a == "--nosplit" || a == "-d" || a == "--nothreads") continue;
         else if (a == "--stats") stats = true;
+        else if (a == "--cpu-inflate") cpu_inflate = true;
+        else if (a == "--pinned") pinned = true;
         else if (a == "--device") device = atoi(need());
         else if (!a.empty() && a[0] == '-') usage();
         else if (in.empty()) in = a;
@@ -78,11 +83,18 @@ int main(int argc, char **argv) {
     const double t_start = now_s();
     oge_bam_file *bam = NULL;
     if (oge_gpu_device_count() < 1) die("MarkDuplicates (GPU)", "no CUDA device: this path has no CPU fallback.");
-    int rc = oge_bam_load(in.c_str(), threads, oge_gpu_host_alloc, oge_gpu_host_free, &bam);
-    if (rc) die("Error reading BAM", oge_bam_last_error());
-    const uint64_t n = oge_bam_n_records(bam);
+    oge_bam_alloc_fn alloc_fn = pinned ? oge_gpu_host_alloc : NULL;
+    oge_bam_free_fn free_fn = pinned ? oge_gpu_host_free : NULL;
+    // BGZF input: open in two stages and let the GPU inflate; an uncompressed stream (or --cpu-inflate) loads on the host
+    bool gpu_inflate = !cpu_inflate;
+    int rc = 0;
+    if (gpu_inflate) {
+        rc = oge_bam_open_bgzf(in.c_str(), threads, alloc_fn, free_fn, &bam);
+        if (rc == OGE_BAM_ERR_FORMAT && strstr(oge_bam_last_error(), "uncompressed BAM stream")) gpu_inflate = false;
+        else if (rc) die("Error reading BAM", oge_bam_last_error());
+    }
+    if (!gpu_inflate && (rc = oge_bam_load(in.c_str(), threads, alloc_fn, free_fn, &bam))) die("Error reading BAM", oge_bam_last_error());
     const double t_loaded = now_s();
-    if (verbose) fprintf(stderr, "Read %llu records.\n", (unsigned long long) n);
 
     oge_gpu_dedup_config cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -93,8 +105,10 @@ int main(int argc, char **argv) {
         if (oge_bam_ref_len(bam, i) > cfg.max_ref_len) cfg.max_ref_len = oge_bam_ref_len(bam, i);
     cfg.remove_duplicates = remove_dups ? 1 : 0;
     cfg.verify_names = -1;
-    cfg.capacity_records = n;
-    cfg.capacity_bytes = oge_bam_records_bytes(bam);
+    if (!gpu_inflate) {
+        cfg.capacity_records = oge_bam_n_records(bam);
+        cfg.capacity_bytes = oge_bam_records_bytes(bam);
+    }
     oge_gpu_dedup_ctx *ctx = NULL;
     if ((rc = oge_gpu_dedup_create(&cfg, &ctx))) die("MarkDuplicates (GPU): oge_gpu_dedup_create", oge_gpu_last_error());
     {
@@ -105,7 +119,27 @@ int main(int argc, char **argv) {
         oge_bam_library_table(bam, &ids, &libs, &n_rg, &unknown, &n_libs);
         if ((rc = oge_gpu_dedup_set_readgroups(ctx, ids, libs, n_rg, unknown, n_libs))) die("MarkDuplicates (GPU): set_readgroups", oge_gpu_last_error());
     }
-    if ((rc = oge_gpu_dedup_push(ctx, oge_bam_records(bam), oge_bam_records_bytes(bam), oge_bam_offsets(bam), n))) die("MarkDuplicates (GPU): push", oge_gpu_last_error());
+    double t_inflated = t_loaded, t_framed = t_loaded;
+    if (gpu_inflate) {
+        const uint8_t *comp;
+        const uint64_t *in_off;
+        const uint32_t *csize, *isize;
+        uint64_t comp_bytes, n_blocks, header_bytes;
+        oge_bam_bgzf_index(bam, &comp, &comp_bytes, &in_off, &csize, &isize, &n_blocks, &header_bytes);
+        uint8_t *host_records = oge_bam_records_buffer(bam);
+        if (!host_records) die("Error reading BAM", oge_bam_last_error());
+        if ((rc = oge_gpu_dedup_push_bgzf(ctx, comp, comp_bytes, in_off, csize, isize, n_blocks, header_bytes, host_records)))
+            die("Error reading BAM", oge_gpu_last_error());
+        t_inflated = now_s();
+        if ((rc = oge_bam_frame_records(bam))) die("Error reading BAM", oge_bam_last_error());
+        t_framed = now_s();
+        if ((rc = oge_gpu_dedup_set_offsets(ctx, oge_bam_offsets(bam), oge_bam_n_records(bam)))) die("MarkDuplicates (GPU): set_offsets", oge_gpu_last_error());
+    } else {
+        if ((rc = oge_gpu_dedup_push(ctx, oge_bam_records(bam), oge_bam_records_bytes(bam), oge_bam_offsets(bam), oge_bam_n_records(bam))))
+            die("MarkDuplicates (GPU): push", oge_gpu_last_error());
+    }
+    const uint64_t n = oge_bam_n_records(bam);
+    if (verbose) fprintf(stderr, "Read %llu records.\n", (unsigned long long) n);
     if ((rc = oge_gpu_dedup_run(ctx))) die("MarkDuplicates (GPU): run", oge_gpu_last_error());
     std::vector<uint16_t> flags(n ? n : 1);
     if ((rc = oge_gpu_dedup_flags(ctx, flags.data(), n))) die("MarkDuplicates (GPU): flags", oge_gpu_last_error());
@@ -151,9 +185,17 @@ int main(int argc, char **argv) {
         double t[6];
         oge_bam_timings(bam, t, 6);
         fprintf(stderr, "Written %llu records.\n", (unsigned long long) oge_bam_n_records(bam));
-        fprintf(stderr,
-                "Timing: load %.3f s (read %.3f, scan %.3f, inflate %.3f, frame %.3f) | gpu %.3f s (device %.3f ms) | rewrite %.3f s | store %.3f s | total %.3f s\n",
-                t_loaded - t_start, t[0], t[1], t[2], t[3], t_gpu - t_loaded, st.ms_total, t[4], t[5], t_end - t_start);
+        if (gpu_inflate)
+            fprintf(stderr,
+                    "Timing: open %.3f s (read %.3f, scan %.3f, header %.3f) | gpu inflate + copy back %.3f s (kernel %.3f ms, %.1f GB/s out) | frame %.3f s | "
+                    "gpu dedup %.3f s (device %.3f ms) | rewrite %.3f s | store %.3f s | total %.3f s\n",
+                    t_loaded - t_start, t[0], t[1], t[3] - (t_framed - t_inflated), t_inflated - t_loaded, st.ms_inflate,
+                    st.ms_inflate > 0 ? st.inflate_bytes_out / 1e6 / st.ms_inflate : 0.0, t_framed - t_inflated, t_gpu - t_framed, st.ms_total, t[4], t[5],
+                    t_end - t_start);
+        else
+            fprintf(stderr,
+                    "Timing: load %.3f s (read %.3f, scan %.3f, inflate %.3f, frame %.3f) | gpu %.3f s (device %.3f ms) | rewrite %.3f s | store %.3f s | total %.3f s\n",
+                    t_loaded - t_start, t[0], t[1], t[2], t[3], t_gpu - t_loaded, st.ms_total, t[4], t[5], t_end - t_start);
     }
     oge_bam_close(bam);
     return 0;

@@ -65,6 +65,34 @@ def test_load_frames_like_the_python_reader(tmp):
             assert [libs.index(x) for x in libs] == [list(libs2).index(x) for x in libs2]
 
 
+def test_two_stage_open_equals_load(tmp):
+    """oge_bam_open_bgzf / records_buffer / frame_records (the GPU-inflate entry): here the buffer is filled by the host codec."""
+    b1, _ = fixtures.fixture1()
+    big_text = "@HD\tVN:1.4\tSO:coordinate\n" + "".join("@SQ\tSN:contig%05d\tLN:%d\n" % (i, 1000 + i) for i in range(9000)) + "@RG\tID:rg1\tLB:libA\n@RG\tID:rg2\tLB:libB\n"
+    wide = bamio.BamFile(text=big_text, refs=[("contig%05d" % i, 1000 + i) for i in range(9000)], records=b1.records, offsets=b1.offsets)
+    for bam in (synth.make("C3", 0.005, seed=4), wide):      # the second header spans several BGZF blocks
+        p = os.path.join(tmp, "x.bam")
+        bamio.write_bam(p, bam)
+        with bamhost.HostBam(p, defer_inflate=True) as h:
+            assert h.text == bam.text and h.refs == bam.refs and h.n == 0
+            ix = h.bgzf_index()
+            raw = bamhost.bgzf_decompress(open(p, "rb").read())
+            assert ix["header_bytes"] == len(raw) - len(bam.records) and ix["comp_bytes"] == os.path.getsize(p)
+            isize = np.ctypeslib.as_array((C.c_uint32 * ix["n_blocks"]).from_address(ix["isize"]))
+            assert int(isize.sum()) == len(raw)
+            C.memmove(h.records_buffer(), raw[ix["header_bytes"]:], len(raw) - ix["header_bytes"])
+            h.frame_records()
+            assert h.n == bam.n and np.array_equal(h.records, bam.records) and np.array_equal(h.offsets, bam.offsets)
+            h.apply_flags(bam.flags())
+            h.store(os.path.join(tmp, "y.rawbam"), "rawbam")
+        assert bamio.read_bam(os.path.join(tmp, "y.rawbam")).n == bam.n
+    p = os.path.join(tmp, "raw.bam")
+    bamio.write_bam(p, bam, raw=True)
+    with pytest.raises(bamhost.BamHostError) as e:
+        bamhost.HostBam(p, defer_inflate=True)
+    assert "uncompressed BAM stream" in str(e.value)
+
+
 def test_bgzf_codec_round_trip_and_block_layout():
     rng = np.random.default_rng(1)
     for n in (0, 1, 65535, 65536, 65537, 3 * 65536, 1_000_003):

@@ -1,0 +1,155 @@
+"""GPU suite: BGZF inflate on the device (oge_gpu_dedup_push_bgzf, one warp per block) against zlib, and the fused
+file path with it against the reference's output files."""
+import ctypes as C
+import hashlib
+import os
+import subprocess
+import tempfile
+import zlib
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN, load_golden
+from openge_b200 import _build, bamhost, bamio, dedup, synth
+
+pytestmark = pytest.mark.gpu
+
+GOLD = dict(np.load(os.path.join(GOLDEN, "bamfile.npz")))
+
+
+@pytest.fixture()
+def tmp():
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    with tempfile.TemporaryDirectory(dir=base) as d:
+        yield d
+
+
+def bgzf_blocks(raw: bytes, level: int, strategy=zlib.Z_DEFAULT_STRATEGY, block=65536) -> bytes:
+    """A BGZF file cut into `block`-byte payloads, every block compressed with the given zlib level and strategy."""
+    out = []
+    for k in list(range(0, len(raw), block)) + [len(raw)]:
+        chunk = raw[k:k + block] if k < len(raw) else b""
+        co = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
+        z = co.compress(chunk) + co.flush()
+        if len(z) + 26 > 65536:      # incompressible: store it
+            co = zlib.compressobj(0, zlib.DEFLATED, -15)
+            z = co.compress(chunk) + co.flush()
+        out.append(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + (len(z) + 25).to_bytes(2, "little") + z +
+                   zlib.crc32(chunk).to_bytes(4, "little") + len(chunk).to_bytes(4, "little"))
+    return b"".join(out)
+
+
+def gpu_inflate_file(path):
+    """-> (records bytes as inflated on the device and copied back, HostBam) via the two-stage open."""
+    h = bamhost.HostBam(path, defer_inflate=True)
+    refs = h.refs
+    ctx = dedup.DedupContext(n_ref=len(refs), max_ref_len=max([l for _, l in refs], default=0))
+    ix = h.bgzf_index()
+    ctx.push_bgzf(ix["comp"], ix["comp_bytes"], ix["in_off"], ix["csize"], ix["isize"], ix["n_blocks"], ix["header_bytes"], h.records_buffer())
+    h.frame_records()
+    return ctx, h
+
+
+@pytest.mark.parametrize("level,strategy,block", [(6, zlib.Z_DEFAULT_STRATEGY, 65536), (1, zlib.Z_DEFAULT_STRATEGY, 65280),
+                                                  (9, zlib.Z_DEFAULT_STRATEGY, 30000), (0, zlib.Z_DEFAULT_STRATEGY, 65000),
+                                                  (6, zlib.Z_FIXED, 40000), (6, zlib.Z_HUFFMAN_ONLY, 50000), (6, zlib.Z_RLE, 777)])
+def test_device_inflate_matches_zlib(tmp, level, strategy, block):
+    bam = synth.make("C3", 0.02, seed=31)
+    raw = bamio.serialize_bam_stream(bam)
+    p = os.path.join(tmp, "x.bam")
+    open(p, "wb").write(bgzf_blocks(raw, level, strategy, block))
+    ctx, h = gpu_inflate_file(p)
+    with ctx, h:
+        assert h.n == bam.n and h.text == bam.text
+        assert np.array_equal(h.records, bam.records) and np.array_equal(h.offsets, bam.offsets)      # the D2H copy
+        st = ctx.stats()
+        assert st["inflate_bytes_out"] == len(raw) and st["ms_inflate"] > 0
+        # and what stayed in HBM is the same: run the dedup on it
+        ptr, nbytes, off_ptr = h.records_ptr()
+        ctx.set_header(h.text)
+        ctx.set_offsets(off_ptr, h.n, nbytes)
+        ctx.run()
+        assert np.array_equal(ctx.flags(), oracle.markdup(bam.records, bam.offsets, bam.text))
+        rec, off = ctx.pull()
+        want = bam.records.copy()
+        f = ctx.flags()
+        o = bam.offsets[:-1].astype(np.int64)
+        want[o + 18] = (f & 0xFF).astype(np.uint8)
+        want[o + 19] = (f >> 8).astype(np.uint8)
+        assert np.array_equal(rec, want) and np.array_equal(off, bam.offsets)
+
+
+def test_device_inflate_other_writers_and_large_headers(tmp):
+    # python zlib at level 1 through bamio (its own block size), the host layer's writer, and a header spanning several blocks
+    bam = synth.make("C1", 0.01, seed=8)
+    big_text = "@HD\tVN:1.4\tSO:coordinate\n" + "".join("@SQ\tSN:contig%05d\tLN:%d\n" % (i, 1000 + i) for i in range(9000)) + "@RG\tID:rg1\tLB:lib1\n"
+    refs = [("contig%05d" % i, 1000 + i) for i in range(9000)]
+    b2 = bamio.BamFile(text=big_text, refs=refs, records=bam.records, offsets=bam.offsets)
+    for k, (b, writer) in enumerate([(bam, "bamio"), (bam, "host"), (b2, "host")]):
+        p = os.path.join(tmp, "w%d.bam" % k)
+        if writer == "bamio":
+            bamio.write_bam(p, b)
+        else:
+            open(p, "wb").write(bamhost.bgzf_compress(bamio.serialize_bam_stream(b), 6))
+        ctx, h = gpu_inflate_file(p)
+        with ctx, h:
+            assert h.text == b.text and h.refs == b.refs
+            assert np.array_equal(h.records, b.records) and np.array_equal(h.offsets, b.offsets)
+
+
+def test_device_inflate_rejects_corrupt_blocks(tmp):
+    bam = synth.make("C1", 0.01, seed=9)
+    z = bytearray(bamhost.bgzf_compress(bamio.serialize_bam_stream(bam), 6))
+    bs0 = int.from_bytes(z[16:18], "little") + 1
+    for k in range(bs0 + 600, bs0 + 640):      # scramble the middle of the second block's deflate stream
+        z[k] ^= 0xA5
+    p = os.path.join(tmp, "bad.bam")
+    open(p, "wb").write(bytes(z))
+    with bamhost.HostBam(p, defer_inflate=True) as h, dedup.DedupContext(n_ref=len(h.refs), max_ref_len=100000000) as ctx:
+        ix = h.bgzf_index()
+        with pytest.raises(dedup.DedupError) as e:
+            ctx.push_bgzf(ix["comp"], ix["comp_bytes"], ix["in_off"], ix["csize"], ix["isize"], ix["n_blocks"], ix["header_bytes"], h.records_buffer())
+        assert e.value.code == -7 and "BGZF block 1" in str(e.value)
+        # state errors: offsets before a successful push_bgzf; plain push after one
+    with dedup.DedupContext(n_ref=1, max_ref_len=1000) as ctx:
+        with pytest.raises(dedup.DedupError) as e:
+            ctx.set_offsets(np.zeros(1, np.uint64).ctypes.data, 0, 0)
+        assert e.value.code == -5
+
+
+@pytest.mark.parametrize("name,scale,seed,level,remove", [("C3", 0.01, 99, 6, False), ("C3", 0.01, 99, 6, True), ("C4", 0.004, 6, 9, False)])
+def test_fused_file_with_device_inflate_is_byte_identical_to_the_reference_output(tmp, name, scale, seed, level, remove):
+    bam = synth.make(name, scale, seed=seed)
+    inp, out = os.path.join(tmp, "in.bam"), os.path.join(tmp, "out.bam")
+    bamio.write_bam(inp, bam)
+    st = bamhost.dedup_file(inp, out, remove_duplicates=remove, level=level, gpu_inflate=True)
+    assert st["gpu_inflate"] and st["dedup"]["inflate_blocks"] > 0
+    key = "%s_%g_%d_c%d%s" % (name, scale, seed, level, "_r" if remove else "")
+    assert hashlib.sha256(open(out, "rb").read()).hexdigest() == str(GOLD[key])
+    out2 = os.path.join(tmp, "out2.bam")
+    st2 = bamhost.dedup_file(inp, out2, remove_duplicates=remove, level=level, gpu_inflate=False)
+    assert not st2["gpu_inflate"] and open(out2, "rb").read() == open(out, "rb").read()
+
+
+def test_fused_binary_inflate_modes_agree(tmp):
+    exe = _build.ensure_fused()
+    bam, g = load_golden("synth_C3")
+    inp = os.path.join(tmp, "in.bam")
+    bamio.write_bam(inp, bam)
+    outs = []
+    for extra in ([], ["--cpu-inflate"], ["--pinned"]):
+        out = os.path.join(tmp, "o%d.rawbam" % len(outs))
+        r = subprocess.run([exe, inp, "-o", out, "-F", "rawbam", "--nopg", "-v"] + extra, capture_output=True, timeout=300)
+        assert r.returncode == 0, r.stderr.decode()[-2000:]
+        assert (b"gpu inflate" in r.stderr) == ("--cpu-inflate" not in extra)
+        outs.append(open(out, "rb").read())
+    assert outs[0] == outs[1] == outs[2]
+    assert np.array_equal(bamio.parse_bam_stream(outs[0]).flags(), g["flags_nosplit_v"])
+    # an uncompressed input falls back to the host loader
+    raw_in = os.path.join(tmp, "in.rawbam")
+    bamio.write_bam(raw_in, bam, raw=True)
+    out = os.path.join(tmp, "o_raw.rawbam")
+    r = subprocess.run([exe, raw_in, "-o", out, "-F", "rawbam", "--nopg"], capture_output=True, timeout=300)
+    assert r.returncode == 0 and open(out, "rb").read() == outs[0]

@@ -1,0 +1,98 @@
+"""CPU suite: the product's DEFLATE decoder (openge_b200/csrc/inflate_core.cuh, the body of the GPU BGZF inflate kernel)
+compiled for the host with one lane (tests/native/inflate_host.cpp) against zlib.  The warp-parallel execution of the same
+source is covered by tests/test_gpu_inflate.py."""
+import ctypes as C
+import os
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+@pytest.fixture(scope="module")
+def lib():
+    out_dir = os.path.join(ROOT, "tests", "native", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "liboge_inflate_host.so")
+    src = os.path.join(ROOT, "tests", "native", "inflate_host.cpp")
+    core = os.path.join(ROOT, "openge_b200", "csrc", "inflate_core.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core)):
+        subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-I", os.path.join(ROOT, "openge_b200", "csrc"), src, "-o", so], check=True)
+    L = C.CDLL(so)
+    L.oge_test_inflate_block.argtypes = [C.c_char_p, C.c_uint, C.c_void_p, C.c_uint]
+    return L
+
+
+def inflate(L, z, n):
+    out = np.zeros(max(1, n), dtype=np.uint8)
+    rc = L.oge_test_inflate_block(z, len(z), out.ctypes.data, n)
+    return rc, out[:n].tobytes()
+
+
+def payloads():
+    rng = np.random.default_rng(0)
+    yield b""
+    yield b"a"
+    yield b"hello hello hello hello"
+    yield bytes(65536)                                                      # one long run: overlapping matches, distance 1
+    yield bytes(rng.integers(0, 256, 65536, dtype=np.uint8))                # incompressible: stored blocks at every level
+    yield bytes(rng.integers(65, 69, 65536, dtype=np.uint8))                # 2 bits of entropy per byte
+    yield (b"ACGT" * 100 + bytes(rng.integers(0, 256, 50, dtype=np.uint8))) * 100
+    for n in (1, 2, 3, 100, 1000, 30000, 65536):
+        yield bytes(rng.integers(0, 40, n, dtype=np.uint8) + 33)            # quality-like
+    p = np.array([2.0 ** -(i / 6) for i in range(256)])
+    yield bytes(rng.choice(256, size=65536, p=p / p.sum()).astype(np.uint8))  # skewed: codes longer than the 10-bit primary table
+    from openge_b200 import bamio, synth
+    raw = bamio.serialize_bam_stream(synth.make("C3", 0.002, seed=5))
+    for k in range(0, min(len(raw), 4 * 65536), 65536):
+        yield raw[k:k + 65536]                                              # real BAM bytes
+
+
+def test_tables_fit_the_shared_memory_budget(lib):
+    assert lib.oge_test_inflate_tables_bytes() * 8 <= 48 * 1024      # 8 warps per CTA, static shared memory
+
+
+def test_decoder_matches_zlib_on_every_block_type(lib):
+    n = 0
+    for data in payloads():
+        for level in (0, 1, 6, 9):
+            for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FILTERED):
+                co = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
+                z = co.compress(data) + co.flush()
+                rc, out = inflate(lib, z, len(data))
+                assert rc == 0 and out == data, (len(data), level, strategy, rc)
+                n += 1
+    assert n > 300
+
+
+def test_multi_block_streams_with_sync_flushes(lib):
+    rng = np.random.default_rng(3)
+    data = bytes(rng.integers(0, 8, 40000, dtype=np.uint8))
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    z = b""
+    for k in range(0, len(data), 7000):      # Z_SYNC_FLUSH puts an empty stored block between Huffman blocks
+        z += co.compress(data[k:k + 7000]) + co.flush(zlib.Z_SYNC_FLUSH)
+    z += co.flush()
+    rc, out = inflate(lib, z, len(data))
+    assert rc == 0 and out == data
+
+
+def test_corrupt_streams_are_rejected_not_overrun(lib):
+    rng = np.random.default_rng(4)
+    data = bytes(rng.integers(0, 40, 20000, dtype=np.uint8))
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    z = co.compress(data) + co.flush()
+    assert inflate(lib, z, len(data) - 1)[0] != 0          # ISIZE too small: output overrun detected
+    assert inflate(lib, z, len(data) + 1)[0] != 0          # ISIZE too large: short stream
+    assert inflate(lib, z[: len(z) // 2], len(data))[0] != 0
+    assert inflate(lib, b"\x07" + z[1:], len(data))[0] != 0      # BTYPE 3
+    bad = 0
+    for k in range(200):      # random corruption never crashes; it is either detected or decodes to other bytes
+        zz = bytearray(z)
+        zz[int(rng.integers(0, len(zz)))] ^= 1 << int(rng.integers(0, 8))
+        rc, out = inflate(lib, bytes(zz), len(data))
+        bad += rc != 0 or out != data
+    assert bad >= 190

@@ -50,13 +50,20 @@ def main():
         inp = os.path.join(d, "in.bam")
         n, raw_bytes = write_input(inp, a.config, a.scale, a.seed)
         o1 = os.path.join(d, "fused.bam")
-        cmd = [fused, "dedup", inp, "-o", o1, "-v", "--nopg", "-c", str(a.level)] + (["-t", str(a.threads)] if a.threads else [])
-        run(cmd, 1800)      # warm-up: CUDA context, page cache
-        secs, r = run(cmd, 1800)
-        assert r.returncode == 0, r.stderr.decode()[-2000:]
-        timing = [l for l in r.stderr.decode().splitlines() if l.startswith("Timing:")]
-        out["fused"] = {"reads": n, "raw_bytes": raw_bytes, "file_bytes": os.path.getsize(inp), "seconds": secs,
-                        "reads_per_s": n / secs, "phases": timing[-1] if timing else None}
+        base = [fused, "dedup", inp, "-o", o1, "-v", "--nopg", "-c", str(a.level)] + (["-t", str(a.threads)] if a.threads else [])
+        run(base, 1800)      # warm-up: CUDA context, page cache
+        digests = set()
+        for mode, extra in (("gpu_inflate", []), ("gpu_inflate_pinned", ["--pinned"]), ("cpu_inflate", ["--cpu-inflate"]),
+                            ("cpu_inflate_pinned", ["--cpu-inflate", "--pinned"]), ("gpu_inflate_rawbam_out", ["-F", "rawbam"])):
+            secs, r = run(base + extra, 1800)
+            assert r.returncode == 0, r.stderr.decode()[-2000:]
+            timing = [l for l in r.stderr.decode().splitlines() if l.startswith("Timing:")]
+            out["fused" if mode == "gpu_inflate" else "fused_" + mode] = {
+                "reads": n, "raw_bytes": raw_bytes, "file_bytes": os.path.getsize(inp), "seconds": secs,
+                "reads_per_s": n / secs, "phases": timing[-1] if timing else None}
+            if "rawbam" not in mode:
+                digests.add(hashlib.sha256(open(o1, "rb").read()).hexdigest())
+        out["all_modes_same_output"] = len(digests) == 1
         if ref:
             inp2 = os.path.join(d, "in2.bam")
             n2, _ = write_input(inp2, a.config, a.ref_scale, a.seed)
