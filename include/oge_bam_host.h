@@ -73,6 +73,8 @@ int oge_bam_bgzf_index(const oge_bam_file *f, const uint8_t **comp, uint64_t *co
                        const uint32_t **block_csize, const uint32_t **block_isize, uint64_t *n_blocks, uint64_t *header_bytes);
 uint8_t *oge_bam_records_buffer(oge_bam_file *f);
 int oge_bam_frame_records(oge_bam_file *f);
+/* ... or take the offsets from whoever framed the records already (oge_gpu_dedup_frame + oge_gpu_dedup_offsets). */
+int oge_bam_adopt_offsets(oge_bam_file *f, const uint64_t *offsets, uint64_t nrec);
 
 const char *oge_bam_header_text(const oge_bam_file *f);        /* as stored in the file */
 int32_t oge_bam_n_ref(const oge_bam_file *f);

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define OGE_GPU_DEDUP_ABI_VERSION 4
+#define OGE_GPU_DEDUP_ABI_VERSION 5
 
 enum {
     OGE_OK = 0,
@@ -88,8 +88,10 @@ typedef struct oge_gpu_dedup_stats {
     uint64_t sort_pass_bytes;       /* algorithmic bytes of those launches: 32 per entry (16 read + 16 written) */
     /* oge_gpu_dedup_push_bgzf: the inflate kernel on its own (CUDA events around the launch) */
     float ms_inflate;
-    uint32_t reserved0;
+    float ms_frame;                 /* oge_gpu_dedup_frame: guess + walk + proof + offsets write */
     uint64_t inflate_blocks, inflate_bytes_in, inflate_bytes_out;
+    uint64_t frame_repairs;         /* chunks whose guessed entry the proof replaced */
+    float ms_inflate_h2d, ms_inflate_d2h;   /* push_bgzf: upload of the compressed file, copy-back of the records (0 without host_copy) */
 } oge_gpu_dedup_stats;
 
 /* Per-record view of the end-building kernel (buildReadEnds, mark_duplicates.cpp:147-164). */
@@ -139,6 +141,14 @@ int oge_gpu_dedup_push_bgzf(oge_gpu_dedup_ctx *ctx, const uint8_t *comp, uint64_
                             const uint32_t *block_csize, const uint32_t *block_isize, uint64_t n_blocks, uint64_t header_bytes,
                             uint8_t *host_copy);
 int oge_gpu_dedup_set_offsets(oge_gpu_dedup_ctx *ctx, const uint64_t *offsets, uint64_t nrec);
+/* ... or frame them on the device, in place of oge_gpu_dedup_set_offsets: BamDeserializer::read's chain walk
+ * (util/bam_deserializer.h:144-172; same limits 32 <= block_size <= 10000, same messages) done speculatively in parallel
+ * over 64 KB chunks and then proven -- every chunk must have been entered exactly where its predecessor's walk left,
+ * chunk 0 at byte 0; chunks whose guess was wrong are re-walked from the proven position -- so the result is the
+ * sequential chain, not a heuristic.  With this the host needs no copy of the records before the dedup runs
+ * (host_copy may be NULL in push_bgzf).  oge_gpu_dedup_offsets downloads the n + 1 offsets. */
+int oge_gpu_dedup_frame(oge_gpu_dedup_ctx *ctx, uint64_t *nrec_out);
+int oge_gpu_dedup_offsets(oge_gpu_dedup_ctx *ctx, uint64_t *out, uint64_t n_plus_1);
 
 /* buildSortedReadEndLists + generateDuplicateIndexes + the flag rewrite of runInternal
  * (mark_duplicates.cpp:185-279, 326-400, 443-465) over everything pushed so far.  Idempotent:

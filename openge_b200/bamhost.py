@@ -17,7 +17,7 @@ from . import _build
 
 ERRORS = {-1: "OGE_BAM_ERR_IO", -2: "OGE_BAM_ERR_FORMAT", -3: "OGE_BAM_ERR_NOMEM", -4: "OGE_BAM_ERR_ARG"}
 
-EXPORTS = ["oge_bam_load", "oge_bam_open_bgzf", "oge_bam_bgzf_index", "oge_bam_records_buffer", "oge_bam_frame_records", "oge_bam_close", "oge_bam_header_text", "oge_bam_n_ref", "oge_bam_ref_name", "oge_bam_ref_len",
+EXPORTS = ["oge_bam_load", "oge_bam_open_bgzf", "oge_bam_bgzf_index", "oge_bam_records_buffer", "oge_bam_frame_records", "oge_bam_adopt_offsets", "oge_bam_close", "oge_bam_header_text", "oge_bam_n_ref", "oge_bam_ref_name", "oge_bam_ref_len",
            "oge_bam_records", "oge_bam_records_bytes", "oge_bam_offsets", "oge_bam_n_records", "oge_bam_library_table",
            "oge_bam_apply_flags", "oge_bam_store", "oge_bam_timings", "oge_bgzf_decompress", "oge_bgzf_compress",
            "oge_bam_header_render", "oge_bam_buffer_free", "oge_bam_last_error"]
@@ -46,6 +46,7 @@ def lib():
         L.oge_bam_records_buffer.argtypes = [vp]
         L.oge_bam_records_buffer.restype = vp
         L.oge_bam_frame_records.argtypes = [vp]
+        L.oge_bam_adopt_offsets.argtypes = [vp, vp, u64]
         L.oge_bam_close.argtypes = [vp]
         L.oge_bam_close.restype = None
         L.oge_bam_header_text.argtypes = [vp]
@@ -148,6 +149,10 @@ class HostBam:
     def frame_records(self):
         _check(lib().oge_bam_frame_records(self._h))
 
+    def adopt_offsets(self, offsets: np.ndarray):
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        _check(lib().oge_bam_adopt_offsets(self._h, offsets.ctypes.data, len(offsets) - 1))
+
     def close(self):
         if self._h:
             lib().oge_bam_close(self._h)
@@ -228,22 +233,27 @@ def dedup_file(in_path: str, out_path: str, remove_duplicates: bool = False, lev
     gpu_inflate = gpu_inflate and is_bgzf
     with HostBam(in_path, threads=threads, pinned=pinned, defer_inflate=gpu_inflate) as bam:
         refs = bam.refs
-        ctx = dedup.DedupContext(n_ref=len(refs), max_ref_len=max([l for _, l in refs], default=0), device=device,
-                                 remove_duplicates=remove_duplicates)
-        with ctx:
+        ctx = dedup.DedupContext(n_ref=len(refs), max_ref_len=max([l for _, l in refs], default=0), device=device)
+        with ctx:      # -r is applied by the host layer (apply_flags), so pull() returns every record
             ctx.set_header(bam.text)
             if gpu_inflate:
+                # compressed bytes up, inflate + framing + dedup on the device, ONE copy of the (flag-patched) records back
                 ix = bam.bgzf_index()
-                ctx.push_bgzf(ix["comp"], ix["comp_bytes"], ix["in_off"], ix["csize"], ix["isize"], ix["n_blocks"], ix["header_bytes"],
-                              bam.records_buffer())
-                bam.frame_records()
-                ptr, nbytes, off_ptr = bam.records_ptr()
-                ctx.set_offsets(off_ptr, bam.n, nbytes)
+                ctx.push_bgzf(ix["comp"], ix["comp_bytes"], ix["in_off"], ix["csize"], ix["isize"], ix["n_blocks"], ix["header_bytes"], None)
+                total = int(np.ctypeslib.as_array((C.c_uint32 * ix["n_blocks"]).from_address(ix["isize"])).sum()) if ix["n_blocks"] else 0
+                ctx.frame(total - ix["header_bytes"])
+                ctx.run()
+                flags = ctx.flags()
+                nb, nr = C.c_uint64(), C.c_uint64()
+                offs = np.empty(ctx.n + 1, dtype=np.uint64)
+                from .dedup import _check as _gcheck, lib as _glib
+                _gcheck(_glib().oge_gpu_dedup_pull(ctx._h, bam.records_buffer(), ctx.nbytes, offs.ctypes.data, len(offs), C.byref(nb), C.byref(nr)))
+                bam.adopt_offsets(offs)
             else:
                 ptr, nbytes, off_ptr = bam.records_ptr()
                 ctx.push_async(ptr, nbytes, off_ptr, bam.n)
-            ctx.run()
-            flags = ctx.flags()
+                ctx.run()
+                flags = ctx.flags()
             out = {"dedup": ctx.stats(), "flagstats": ctx.flagstats(), "gpu_inflate": gpu_inflate}
         bam.apply_flags(flags, remove_duplicates, threads)
         bam.store(out_path, format, level, pg_command_line, threads=threads)

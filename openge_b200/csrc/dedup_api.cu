@@ -315,8 +315,9 @@ int oge_gpu_dedup_push_bgzf(oge_gpu_dedup_ctx *c, const uint8_t *comp, uint64_t 
     };
     if ((rc = zcomp.reserve(comp_bytes + 64, false, s)) || (rc = zoff.reserve(2 * n_blocks + 1, false, s)) || (rc = zcs.reserve(n_blocks + 2, false, s)))
         return done(rc);
-    cudaEvent_t e0 = c->ev[8], e1 = c->ev[9];
-    cudaError_t e = cudaMemsetAsync(zcomp.p + comp_bytes, 0, 64, s);
+    cudaEvent_t e0 = c->ev[8], e1 = c->ev[9], eu = c->ev[0], ed = c->ev[1];
+    cudaError_t e = cudaEventRecord(eu, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(zcomp.p + comp_bytes, 0, 64, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(zcomp.p, comp, comp_bytes, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(zoff.p, block_in_off, n_blocks * 8, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(zoff.p + n_blocks, out_off.data(), (n_blocks + 1) * 8, cudaMemcpyHostToDevice, s);
@@ -338,10 +339,15 @@ int oge_gpu_dedup_push_bgzf(oge_gpu_dedup_ctx *c, const uint8_t *comp, uint64_t 
     e = cudaEventRecord(e1, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(err, zcs.p + n_blocks, 8, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess && host_copy && rec_bytes) e = cudaMemcpyAsync(host_copy, c->rec.p + lead, rec_bytes, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaEventRecord(ed, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return done(fail_cuda(e, "push_bgzf inflate", __FILE__, __LINE__));
     if (err[0]) return done(fail_msg(OGE_ERR_BAD_RECORD, "Zlib inflate failed (BGZF block %u, code %u).", err[1], err[0]));
     c->stats.ms_inflate = ms_between(e0, e1);
+    c->stats.ms_inflate_h2d = ms_between(eu, e0);
+    c->stats.ms_inflate_d2h = ms_between(e1, ed);
+    c->stats.ms_frame = 0;
+    c->stats.frame_repairs = 0;
     c->stats.inflate_blocks = n_blocks;
     c->stats.inflate_bytes_in = comp_bytes;
     c->stats.inflate_bytes_out = total;
@@ -350,6 +356,108 @@ int oge_gpu_dedup_push_bgzf(oge_gpu_dedup_ctx *c, const uint8_t *comp, uint64_t 
     c->n = 0;
     c->ran = false;
     return done(OGE_OK);
+}
+
+int oge_gpu_dedup_frame(oge_gpu_dedup_ctx *c, uint64_t *nrec_out) {
+    if (!c || !nrec_out) return fail_msg(OGE_ERR_INVALID_ARG, "frame: null argument");
+    if (c->n || !c->rec_lead) return fail_msg(OGE_ERR_STATE, "frame: follows oge_gpu_dedup_push_bgzf, once");
+    OGE_CUDA_TRY(cudaSetDevice(c->cfg.device));
+    cudaStream_t s = c->stream;
+    *nrec_out = 0;
+    if (c->rec_bytes == 0) {
+        int rc0 = c->off.reserve(1, false, s);
+        if (rc0) return rc0;
+        OGE_CUDA_TRY(cudaMemsetAsync(c->off.p, 0, 8, s));
+        OGE_CUDA_TRY(cudaStreamSynchronize(s));
+        return OGE_OK;
+    }
+    FrameParams P;
+    P.rec = c->recs();
+    P.total = c->rec_bytes;
+    P.chunk = 1 << 16;
+    P.n_chunks = (P.total + P.chunk - 1) / P.chunk;
+    P.n_ref = c->cfg.n_ref;
+    const uint64_t nc = P.n_chunks;
+    DevBuf<uint64_t> w;      // entry, exit, count, base
+    DevBuf<uint32_t> wb;
+    int rc;
+    auto done = [&](int code) {
+        w.release();
+        wb.release();
+        return code;
+    };
+    if ((rc = w.reserve(4 * nc, false, s)) || (rc = wb.reserve(nc, false, s))) return done(rc);
+    P.entry = w.p;
+    P.exit_ = w.p + nc;
+    P.count = w.p + 2 * nc;
+    uint64_t *d_base = w.p + 3 * nc;
+    P.base = d_base;
+    P.bad = wb.p;
+    P.off = nullptr;
+    uint64_t launches = 0;
+    cudaEvent_t e0 = c->ev[8], e1 = c->ev[9];
+    cudaError_t e = cudaEventRecord(e0, s);
+    if (e != cudaSuccess) return done(fail_cuda(e, "frame", __FILE__, __LINE__));
+    if ((rc = launch_frame_guess(P, s, &launches)) || (rc = launch_frame_walk(P, 0, nc, 0, s, &launches))) return done(rc);
+    std::vector<uint64_t> h(3 * nc);
+    std::vector<uint32_t> hb(nc);
+    e = cudaMemcpyAsync(h.data(), w.p, 3 * nc * 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hb.data(), wb.p, nc * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return done(fail_cuda(e, "frame walk", __FILE__, __LINE__));
+    uint64_t *entry = h.data(), *exit_ = h.data() + nc, *count = h.data() + 2 * nc;
+    // ---- the proof: every chunk must have been entered where its predecessor left; repair the ones that were not
+    uint64_t repairs = 0;
+    for (uint64_t k = 0; k < nc; k++) {
+        const uint64_t want = k ? exit_[k - 1] : 0;
+        if (entry[k] != want) {
+            repairs++;
+            e = cudaMemcpyAsync(w.p + k, &want, 8, cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) return done(fail_cuda(e, "frame repair", __FILE__, __LINE__));
+            if ((rc = launch_frame_walk(P, k, 1, 0, s, &launches))) return done(rc);
+            e = cudaMemcpyAsync(&exit_[k], w.p + nc + k, 8, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(&count[k], w.p + 2 * nc + k, 8, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(&hb[k], wb.p + k, 4, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) return done(fail_cuda(e, "frame repair", __FILE__, __LINE__));
+            entry[k] = want;
+        }
+        if (hb[k]) {      // the TRUE chain breaks here: the reference's messages (util/bam_deserializer.h:155-170)
+            if ((hb[k] & 3) == 2) return done(fail_msg(OGE_ERR_BAD_RECORD, "Invalid BAM block size(%u).", hb[k] >> 2));
+            return done(fail_msg(OGE_ERR_BAD_RECORD, "Expected more bytes reading BAM core. Is this file truncated or corrupted?"));
+        }
+    }
+    std::vector<uint64_t> base(nc);
+    uint64_t n = 0;
+    for (uint64_t k = 0; k < nc; k++) {
+        base[k] = n;
+        n += count[k];
+    }
+    if (n >= (1ull << 30)) return done(fail_msg(OGE_ERR_TOO_LARGE, "frame: more than 2^30-1 records in one context"));
+    if ((rc = c->off.reserve(n + 1, false, s))) return done(rc);
+    e = cudaMemcpyAsync(d_base, base.data(), nc * 8, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return done(fail_cuda(e, "frame bases", __FILE__, __LINE__));
+    P.off = c->off.p;
+    if ((rc = launch_frame_walk(P, 0, nc, 1, s, &launches))) return done(rc);
+    e = cudaEventRecord(e1, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return done(fail_cuda(e, "frame write", __FILE__, __LINE__));
+    c->stats.ms_frame = ms_between(e0, e1);
+    c->stats.frame_repairs = repairs;
+    c->n = n;
+    c->ran = false;
+    *nrec_out = n;
+    return done(OGE_OK);
+}
+
+int oge_gpu_dedup_offsets(oge_gpu_dedup_ctx *c, uint64_t *out, uint64_t n_plus_1) {
+    if (!c || !out) return fail_msg(OGE_ERR_INVALID_ARG, "offsets: null argument");
+    if (n_plus_1 != c->n + 1) return fail_msg(OGE_ERR_INVALID_ARG, "offsets: the context holds %llu records", (unsigned long long) c->n);
+    OGE_CUDA_TRY(cudaSetDevice(c->cfg.device));
+    OGE_CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+    OGE_CUDA_TRY(cudaMemcpyAsync(out, c->off.p, n_plus_1 * 8, cudaMemcpyDeviceToHost, c->stream));
+    OGE_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return OGE_OK;
 }
 
 int oge_gpu_dedup_set_offsets(oge_gpu_dedup_ctx *c, const uint64_t *offsets, uint64_t nrec) {
@@ -414,7 +522,18 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     if (!c) return fail_msg(OGE_ERR_INVALID_ARG, "run: null context");
     OGE_CUDA_TRY(cudaSetDevice(c->cfg.device));
     cudaStream_t s = c->stream;
-    memset(&c->stats, 0, sizeof(c->stats));
+    {   // the input-side figures (push_bgzf / frame) describe the resident records, not a run: they survive
+        const oge_gpu_dedup_stats keep = c->stats;
+        memset(&c->stats, 0, sizeof(c->stats));
+        c->stats.ms_inflate = keep.ms_inflate;
+        c->stats.inflate_blocks = keep.inflate_blocks;
+        c->stats.inflate_bytes_in = keep.inflate_bytes_in;
+        c->stats.inflate_bytes_out = keep.inflate_bytes_out;
+        c->stats.ms_frame = keep.ms_frame;
+        c->stats.frame_repairs = keep.frame_repairs;
+        c->stats.ms_inflate_h2d = keep.ms_inflate_h2d;
+        c->stats.ms_inflate_d2h = keep.ms_inflate_d2h;
+    }
     c->stats.n_records = c->n;
     if (c->n == 0) {
         c->ran = true;

@@ -142,6 +142,23 @@ struct BgzfParams {
 };
 int launch_bgzf_inflate(const BgzfParams &P, int sms, cudaStream_t stream, uint64_t *launches);
 
+// ---- record framing on the device (frame.cu): speculative parallel chain walk + proof
+struct FrameParams {
+    const uint8_t *rec;         // first record
+    uint64_t total;             // record bytes
+    uint64_t chunk;             // bytes per chunk
+    uint64_t n_chunks;
+    int32_t n_ref;
+    uint64_t *entry;            // [n_chunks] first record start at or after the chunk start (guess, then proven)
+    uint64_t *exit_;            // [n_chunks] first record start at or after the chunk end, walking from entry
+    uint64_t *count;            // [n_chunks] records starting inside the chunk
+    uint32_t *bad;              // [n_chunks] 0, 1 = truncated, 2 | block_size << 2 = invalid block size
+    const uint64_t *base;       // [n_chunks] rank of the chunk's first record (write pass)
+    uint64_t *off;              // offsets out
+};
+int launch_frame_guess(const FrameParams &P, cudaStream_t s, uint64_t *launches);
+int launch_frame_walk(const FrameParams &P, uint64_t first_chunk, uint64_t n_walk, int write, cudaStream_t s, uint64_t *launches);
+
 // ---- flag statistics (flagstat.cu): Statistics::runInternal's counters over the resident records
 enum {
     FS_READS = 0, FS_MAPPED, FS_FORWARD, FS_REVERSE, FS_FAILED_QC, FS_DUPLICATES, FS_PAIRED, FS_PROPER_PAIR,

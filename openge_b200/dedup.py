@@ -19,7 +19,7 @@ import numpy as np
 from . import _build, header as _header
 from .bamio import BamFile
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 OGE_OK = 0
 ERRORS = {-1: "OGE_ERR_INVALID_ARG", -2: "OGE_ERR_CUDA", -3: "OGE_ERR_NOMEM", -4: "OGE_ERR_KEY_RANGE",
@@ -44,8 +44,9 @@ class Stats(C.Structure):
                 ("ms_sort_frag", C.c_float), ("ms_sort_pair", C.c_float), ("ms_select", C.c_float),
                 ("ms_flags", C.c_float), ("launches", C.c_uint64),
                 ("ms_sort_pass_kernels", C.c_float), ("sort_pass_launches", C.c_uint32), ("sort_pass_bytes", C.c_uint64),
-                ("ms_inflate", C.c_float), ("reserved0", C.c_uint32), ("inflate_blocks", C.c_uint64),
-                ("inflate_bytes_in", C.c_uint64), ("inflate_bytes_out", C.c_uint64)]
+                ("ms_inflate", C.c_float), ("ms_frame", C.c_float), ("inflate_blocks", C.c_uint64),
+                ("inflate_bytes_in", C.c_uint64), ("inflate_bytes_out", C.c_uint64), ("frame_repairs", C.c_uint64),
+                ("ms_inflate_h2d", C.c_float), ("ms_inflate_d2h", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -59,7 +60,7 @@ END_DTYPE = np.dtype([("eligible", "<i4"), ("pair_eligible", "<i4"), ("ref", "<i
                       ("orientation", "<i4"), ("read2Sequence", "<i4"), ("score", "<i2"), ("lib", "<i2")])
 
 EXPORTS = ["oge_gpu_dedup_create", "oge_gpu_dedup_destroy", "oge_gpu_dedup_set_readgroups", "oge_gpu_dedup_push",
-           "oge_gpu_dedup_push_bgzf", "oge_gpu_dedup_set_offsets",
+           "oge_gpu_dedup_push_bgzf", "oge_gpu_dedup_set_offsets", "oge_gpu_dedup_frame", "oge_gpu_dedup_offsets",
            "oge_gpu_dedup_sync", "oge_gpu_dedup_run", "oge_gpu_dedup_flags", "oge_gpu_dedup_pull",
            "oge_gpu_dedup_reset", "oge_gpu_dedup_flagstats", "oge_gpu_dedup_get_stats", "oge_gpu_dedup_debug_ends",
            "oge_gpu_dedup_device_ptrs", "oge_gpu_host_alloc", "oge_gpu_host_free", "oge_gpu_device_count",
@@ -94,6 +95,8 @@ def lib():
         L.oge_gpu_dedup_sync.argtypes = [vp]
         L.oge_gpu_dedup_push_bgzf.argtypes = [vp, vp, u64, vp, vp, vp, u64, u64, vp]
         L.oge_gpu_dedup_set_offsets.argtypes = [vp, vp, u64]
+        L.oge_gpu_dedup_frame.argtypes = [vp, C.POINTER(u64)]
+        L.oge_gpu_dedup_offsets.argtypes = [vp, vp, u64]
         L.oge_gpu_dedup_run.argtypes = [vp]
         L.oge_gpu_dedup_flags.argtypes = [vp, vp, u64]
         L.oge_gpu_dedup_pull.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64), C.POINTER(u64)]
@@ -241,6 +244,19 @@ class DedupContext:
         _check(lib().oge_gpu_dedup_set_offsets(self._h, offsets_ptr, nrec))
         self.n = nrec
         self.nbytes = nbytes
+
+    def frame(self, nbytes=0) -> int:
+        """Frame the inflated records on the device (speculative parallel chain walk + proof) -> record count."""
+        n = C.c_uint64()
+        _check(lib().oge_gpu_dedup_frame(self._h, C.byref(n)))
+        self.n = int(n.value)
+        self.nbytes = nbytes
+        return self.n
+
+    def offsets(self) -> np.ndarray:
+        out = np.empty(self.n + 1, dtype=np.uint64)
+        _check(lib().oge_gpu_dedup_offsets(self._h, out.ctypes.data, self.n + 1))
+        return out
 
     def sync(self):
         _check(lib().oge_gpu_dedup_sync(self._h))

@@ -701,13 +701,38 @@ int oge_bam_bgzf_index(const oge_bam_file *f, const uint8_t **comp, uint64_t *co
 }
 
 uint8_t *oge_bam_records_buffer(oge_bam_file *f) {
-    if (!f || !f->comp) { fail(OGE_BAM_ERR_ARG, "records_buffer: the file was not opened with oge_bam_open_bgzf"); return nullptr; }
+    if (!f || (!f->comp && !f->stream)) { fail(OGE_BAM_ERR_ARG, "records_buffer: the file was not opened with oge_bam_open_bgzf"); return nullptr; }
     if (!f->stream) {
         // laid out like a loaded file (header region left unused) so that every other entry point works unchanged
         f->stream = (uint8_t *) (f->alloc_fn ? f->alloc_fn(f->stream_bytes + 256) : malloc(f->stream_bytes + 256));
         if (!f->stream) { fail(OGE_BAM_ERR_NOMEM, "cannot allocate %llu bytes", (unsigned long long) f->stream_bytes + 256); return nullptr; }
+        if (!f->alloc_fn) {
+            // fresh pageable memory: fault the pages in with all threads now (callers overlap this with the GPU's work),
+            // not one by one under the device-to-host copy
+            const uint64_t total = f->stream_bytes + 256;
+            const int th = clamp_threads(0);
+            const uint64_t per = (total / th + 4096) & ~4095ull;
+            uint8_t *base = f->stream;
+            parallel_run(th, [&](int w) -> int {
+                for (uint64_t at = (uint64_t) w * per; at < std::min(total, (uint64_t) (w + 1) * per); at += 4096) base[at] = 0;
+                return 0;
+            });
+        }
     }
     return f->stream + f->first_record;
+}
+
+int oge_bam_adopt_offsets(oge_bam_file *f, const uint64_t *offsets, uint64_t nrec) {
+    if (!f || !offsets || !f->stream) return fail(OGE_BAM_ERR_ARG, "adopt_offsets: fill oge_bam_records_buffer first");
+    if (offsets[0] != 0 || offsets[nrec] != f->stream_bytes - f->first_record) return fail(OGE_BAM_ERR_ARG, "adopt_offsets: offsets do not span the record bytes");
+    const double t0 = now_s();
+    memset(f->stream + f->stream_bytes, 0, 256);
+    free(f->comp);
+    f->comp = nullptr;
+    f->offsets.assign(offsets, offsets + nrec + 1);
+    f->rec_bytes = offsets[nrec];
+    f->t[3] += now_s() - t0;
+    return 0;
 }
 
 int oge_bam_frame_records(oge_bam_file *f) {

@@ -21,6 +21,7 @@
 
 #include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "oge_bam_host.h"
@@ -103,7 +104,7 @@ int main(int argc, char **argv) {
     cfg.n_ref = oge_bam_n_ref(bam);
     for (int32_t i = 0; i < cfg.n_ref; i++)
         if (oge_bam_ref_len(bam, i) > cfg.max_ref_len) cfg.max_ref_len = oge_bam_ref_len(bam, i);
-    cfg.remove_duplicates = remove_dups ? 1 : 0;
+    cfg.remove_duplicates = 0;      // -r is applied by oge_bam_apply_flags: oge_gpu_dedup_pull returns every record
     cfg.verify_names = -1;
     if (!gpu_inflate) {
         cfg.capacity_records = oge_bam_n_records(bam);
@@ -120,29 +121,49 @@ int main(int argc, char **argv) {
         if ((rc = oge_gpu_dedup_set_readgroups(ctx, ids, libs, n_rg, unknown, n_libs))) die("MarkDuplicates (GPU): set_readgroups", oge_gpu_last_error());
     }
     double t_inflated = t_loaded, t_framed = t_loaded;
+    uint64_t n = 0;
+    std::vector<uint16_t> flags;
     if (gpu_inflate) {
+        // compressed bytes up; inflate, framing and dedup on the device; ONE copy of the flag-patched records back
         const uint8_t *comp;
         const uint64_t *in_off;
         const uint32_t *csize, *isize;
         uint64_t comp_bytes, n_blocks, header_bytes;
         oge_bam_bgzf_index(bam, &comp, &comp_bytes, &in_off, &csize, &isize, &n_blocks, &header_bytes);
-        uint8_t *host_records = oge_bam_records_buffer(bam);
-        if (!host_records) die("Error reading BAM", oge_bam_last_error());
-        if ((rc = oge_gpu_dedup_push_bgzf(ctx, comp, comp_bytes, in_off, csize, isize, n_blocks, header_bytes, host_records)))
+        uint8_t *host_records = NULL;
+        std::thread prefault([&] { host_records = oge_bam_records_buffer(bam); });      // page the host buffer in meanwhile
+        if ((rc = oge_gpu_dedup_push_bgzf(ctx, comp, comp_bytes, in_off, csize, isize, n_blocks, header_bytes, NULL))) {
+            prefault.join();
             die("Error reading BAM", oge_gpu_last_error());
+        }
         t_inflated = now_s();
-        if ((rc = oge_bam_frame_records(bam))) die("Error reading BAM", oge_bam_last_error());
+        if ((rc = oge_gpu_dedup_frame(ctx, &n))) {
+            prefault.join();
+            die("Error reading BAM", oge_gpu_last_error());
+        }
         t_framed = now_s();
-        if ((rc = oge_gpu_dedup_set_offsets(ctx, oge_bam_offsets(bam), oge_bam_n_records(bam)))) die("MarkDuplicates (GPU): set_offsets", oge_gpu_last_error());
+        if (verbose) fprintf(stderr, "Read %llu records.\n", (unsigned long long) n);
+        if ((rc = oge_gpu_dedup_run(ctx))) die("MarkDuplicates (GPU): run", oge_gpu_last_error());
+        flags.resize(n ? n : 1);
+        if ((rc = oge_gpu_dedup_flags(ctx, flags.data(), n))) die("MarkDuplicates (GPU): flags", oge_gpu_last_error());
+        prefault.join();
+        if (!host_records) die("Error reading BAM", oge_bam_last_error());
+        std::vector<uint64_t> offs(n + 1);
+        uint64_t got_bytes = 0, got_n = 0;
+        uint64_t total = 0;
+        for (uint64_t b = 0; b < n_blocks; b++) total += isize[b];
+        if ((rc = oge_gpu_dedup_pull(ctx, host_records, total - header_bytes, offs.data(), n + 1, &got_bytes, &got_n))) die("MarkDuplicates (GPU): pull", oge_gpu_last_error());
+        if (n == 0) offs[0] = 0;
+        if ((rc = oge_bam_adopt_offsets(bam, offs.data(), n))) die("Error reading BAM", oge_bam_last_error());
     } else {
-        if ((rc = oge_gpu_dedup_push(ctx, oge_bam_records(bam), oge_bam_records_bytes(bam), oge_bam_offsets(bam), oge_bam_n_records(bam))))
+        n = oge_bam_n_records(bam);
+        if (verbose) fprintf(stderr, "Read %llu records.\n", (unsigned long long) n);
+        if ((rc = oge_gpu_dedup_push(ctx, oge_bam_records(bam), oge_bam_records_bytes(bam), oge_bam_offsets(bam), n)))
             die("MarkDuplicates (GPU): push", oge_gpu_last_error());
+        if ((rc = oge_gpu_dedup_run(ctx))) die("MarkDuplicates (GPU): run", oge_gpu_last_error());
+        flags.resize(n ? n : 1);
+        if ((rc = oge_gpu_dedup_flags(ctx, flags.data(), n))) die("MarkDuplicates (GPU): flags", oge_gpu_last_error());
     }
-    const uint64_t n = oge_bam_n_records(bam);
-    if (verbose) fprintf(stderr, "Read %llu records.\n", (unsigned long long) n);
-    if ((rc = oge_gpu_dedup_run(ctx))) die("MarkDuplicates (GPU): run", oge_gpu_last_error());
-    std::vector<uint16_t> flags(n ? n : 1);
-    if ((rc = oge_gpu_dedup_flags(ctx, flags.data(), n))) die("MarkDuplicates (GPU): flags", oge_gpu_last_error());
     oge_gpu_dedup_stats st;
     oge_gpu_dedup_get_stats(ctx, &st);
     oge_gpu_flagstats fs;
@@ -187,11 +208,11 @@ int main(int argc, char **argv) {
         fprintf(stderr, "Written %llu records.\n", (unsigned long long) oge_bam_n_records(bam));
         if (gpu_inflate)
             fprintf(stderr,
-                    "Timing: open %.3f s (read %.3f, scan %.3f, header %.3f) | gpu inflate + copy back %.3f s (kernel %.3f ms, %.1f GB/s out) | frame %.3f s | "
-                    "gpu dedup %.3f s (device %.3f ms) | rewrite %.3f s | store %.3f s | total %.3f s\n",
-                    t_loaded - t_start, t[0], t[1], t[3] - (t_framed - t_inflated), t_inflated - t_loaded, st.ms_inflate,
-                    st.ms_inflate > 0 ? st.inflate_bytes_out / 1e6 / st.ms_inflate : 0.0, t_framed - t_inflated, t_gpu - t_framed, st.ms_total, t[4], t[5],
-                    t_end - t_start);
+                    "Timing: open %.3f s (read %.3f, scan %.3f) | gpu inflate %.3f s (upload %.1f ms, kernel %.3f ms = %.1f GB/s out) | gpu frame %.3f s "
+                    "(device %.3f ms, %llu repairs) | gpu dedup + copy back %.3f s (device %.3f ms) | rewrite %.3f s | store %.3f s | total %.3f s\n",
+                    t_loaded - t_start, t[0], t[1], t_inflated - t_loaded, st.ms_inflate_h2d, st.ms_inflate,
+                    st.ms_inflate > 0 ? st.inflate_bytes_out / 1e6 / st.ms_inflate : 0.0, t_framed - t_inflated, st.ms_frame,
+                    (unsigned long long) st.frame_repairs, t_gpu - t_framed, st.ms_total, t[4], t[5], t_end - t_start);
         else
             fprintf(stderr,
                     "Timing: load %.3f s (read %.3f, scan %.3f, inflate %.3f, frame %.3f) | gpu %.3f s (device %.3f ms) | rewrite %.3f s | store %.3f s | total %.3f s\n",

@@ -29,7 +29,7 @@ def test_abi_version_and_struct_sizes():
     L = dedup.lib()
     assert L.oge_gpu_abi_version() == dedup.ABI_VERSION
     assert C.sizeof(dedup.Config) == 80
-    assert C.sizeof(dedup.Stats) == 152
+    assert C.sizeof(dedup.Stats) == 168
     assert dedup.END_DTYPE.itemsize == 28
 
 

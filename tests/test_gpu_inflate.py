@@ -153,3 +153,91 @@ def test_fused_binary_inflate_modes_agree(tmp):
     out = os.path.join(tmp, "o_raw.rawbam")
     r = subprocess.run([exe, raw_in, "-o", out, "-F", "rawbam", "--nopg"], capture_output=True, timeout=300)
     assert r.returncode == 0 and open(out, "rb").read() == outs[0]
+
+
+# ---- record framing on the device (oge_gpu_dedup_frame): speculative parallel chain walk + proof
+def device_frame(path):
+    h = bamhost.HostBam(path, defer_inflate=True)
+    ctx = dedup.DedupContext(n_ref=len(h.refs), max_ref_len=max([l for _, l in h.refs], default=0))
+    ix = h.bgzf_index()
+    ctx.push_bgzf(ix["comp"], ix["comp_bytes"], ix["in_off"], ix["csize"], ix["isize"], ix["n_blocks"], ix["header_bytes"], None)
+    return ctx, h
+
+
+@pytest.mark.parametrize("name,scale", [("C3", 0.05), ("C1", 0.02), ("C4", 0.004)])
+def test_device_framing_equals_the_sequential_chain(tmp, name, scale):
+    bam = synth.make(name, scale, seed=17)
+    p = os.path.join(tmp, "x.bam")
+    open(p, "wb").write(bamhost.bgzf_compress(bamio.serialize_bam_stream(bam), 1))
+    ctx, h = device_frame(p)
+    with ctx, h:
+        assert ctx.frame(len(bam.records)) == bam.n
+        assert np.array_equal(ctx.offsets(), bam.offsets)
+        assert ctx.stats()["ms_frame"] > 0
+        ctx.set_header(h.text)
+        ctx.run()
+        assert np.array_equal(ctx.flags(), oracle.markdup(bam.records, bam.offsets, bam.text))
+
+
+def test_device_framing_is_proven_not_guessed(tmp):
+    """A record whose tag bytes hold a perfectly plausible chain of fake records, placed so that it is the first thing a
+    64 KB chunk sees: the guess takes the bait, the proof (entry == predecessor's exit) replaces it."""
+    import fixtures
+    text = "@HD\tVN:1.4\tSO:coordinate\n@SQ\tSN:chr1\tLN:100000\n@RG\tID:rg1\tLB:libA\n"
+    small = [fixtures._rec("r%05d" % i, 0, 0, 100 + i, "100M", -1, 0, "I") for i in range(1200)]
+    fake_chain = b"".join(fixtures._rec("fake%d" % i, 0, 0, 5 + i, "100M", -1, 0, "I") for i in range(4))
+    recs, pos = [], 0
+    i = 0
+    while pos < 65536 - 2500:
+        recs.append(small[i]); pos += len(small[i]); i += 1
+    # the carrier: core + name + cigar + seq + qual come first; then RG and a B:C array: [0xFF padding][fake chain][0xFF padding]
+    probe = bamio.build_record("carrier", 0, 0, 100 + i, 60, "100M", -1, -1, 0, fixtures.SEQ100, 40, bamio.tag_z("RG", "rg1") + b"XBBC" + (0).to_bytes(4, "little"))
+    data_at = pos + len(probe)                      # stream offset of the first array byte
+    pad_front = (65536 - data_at) + 3               # the fake chain starts 3 bytes into chunk 1
+    assert 0 < pad_front < 4000
+    arr = b"\xff" * pad_front + fake_chain + b"\xff" * 200
+    carrier = bamio.build_record("carrier", 0, 0, 100 + i, 60, "100M", -1, -1, 0, fixtures.SEQ100, 40,
+                                 bamio.tag_z("RG", "rg1") + b"XBBC" + len(arr).to_bytes(4, "little") + arr)
+    recs.append(carrier)
+    assert pos + len(carrier) > 65536 + 3 + len(fake_chain)
+    recs += small[i:]
+    records, offsets = bamio.concat_records(recs)
+    bam = bamio.BamFile(text=text, refs=[("chr1", 100000)], records=records, offsets=offsets)
+    assert bytes(records[65539:65539 + len(fake_chain)]) == fake_chain
+    p = os.path.join(tmp, "trap.bam")
+    open(p, "wb").write(bamhost.bgzf_compress(bamio.serialize_bam_stream(bam), 6))
+    ctx, h = device_frame(p)
+    with ctx, h:
+        assert ctx.frame(len(records)) == bam.n
+        assert np.array_equal(ctx.offsets(), bam.offsets)
+        assert ctx.stats()["frame_repairs"] >= 1
+        ctx.set_header(h.text)
+        ctx.run()
+        assert np.array_equal(ctx.flags(), oracle.markdup(bam.records, bam.offsets, bam.text))
+
+
+def test_device_framing_reports_broken_chains_like_the_reference(tmp):
+    bam = synth.make("C1", 0.01, seed=3)
+    raw = bytearray(bamio.serialize_bam_stream(bam))
+    first = len(raw) - len(bam.records)
+    k = int(bam.offsets[len(bam.offsets) // 2])
+    bad = bytearray(raw)
+    bad[first + k: first + k + 4] = (20000).to_bytes(4, "little")
+    for data, msg in ((bytes(bad), "Invalid BAM block size(20000)"), (bytes(raw[:-7]), "Expected more bytes reading BAM core")):
+        p = os.path.join(tmp, "b.bam")
+        open(p, "wb").write(bamhost.bgzf_compress(data, 1))
+        ctx, h = device_frame(p)
+        with ctx, h:
+            with pytest.raises(dedup.DedupError) as e:
+                ctx.frame(0)
+            assert e.value.code == -7 and msg in str(e.value)
+
+
+def test_device_framing_empty_file(tmp):
+    import fixtures
+    b1, _ = fixtures.fixture1()
+    empty = bamio.BamFile(text=b1.text, refs=list(b1.refs), records=np.zeros(0, np.uint8), offsets=np.zeros(1, np.uint64))
+    inp, out = os.path.join(tmp, "e.bam"), os.path.join(tmp, "o.bam")
+    bamio.write_bam(inp, empty)
+    st = bamhost.dedup_file(inp, out)
+    assert st["n_out"] == 0 and bamio.read_bam(out).n == 0
