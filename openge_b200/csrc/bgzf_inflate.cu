@@ -1,37 +1,97 @@
 // BGZF inflate on the device (the part the reference does in util/bgzf_input_stream.cpp:65-142 with one
-// zlib call per block behind a 50 ms-polled job queue).  BGZF blocks are independent deflate streams of at most 64 KB,
-// so a file is inflated by one warp per block: the decoder (inflate_core.cuh) keeps its bit-reader state redundantly in
-// all 32 lanes, reads compressed words and table entries as warp broadcasts, and copies matches with all lanes.  The
-// compressed file crosses PCIe (a third to a quarter of the inflated bytes) and the records are born in HBM, where
-// the dedup path wants them; nothing is staged through host zlib.
+// zlib call per block behind a 50 ms-polled job queue).  BGZF blocks are independent deflate streams of at most 64 KB.
+// The compressed file crosses PCIe (a third to a quarter of the inflated bytes) and the records are born in HBM, where
+// the dedup path wants them; nothing is staged through host zlib.  Two kernels over the same decoder (inflate_core.cuh):
+//
+//   bgzf_inflate_threads (default)  one THREAD per block: a warp decodes 32 streams in SIMT lockstep.  The two hot lookup
+//       tables of a stream (9-bit literal/length, 7-bit distance: 1.25 KB) sit in shared memory at an odd word stride, so
+//       that lanes reading the same index hit different banks; the cold arrays (code lengths, canonical symbol order,
+//       counts) are thread-local.  160 streams per SM.
+//   bgzf_inflate_warps (OGE_INFLATE_KERNEL=warp)  one WARP per block, decode state redundant in all lanes, matches copied by
+//       32 lanes.  First version: correct, but measured issue-bound at 24 GB/s -- 31 of 32 lanes repeat the same ~40
+//       instructions per literal (profiles/r1_inflate_*.txt) -- which is why the thread form exists.
+#include <stdlib.h>
+#include <string.h>
+
 #include "inflate_core.cuh"
 #include "kernels.cuh"
 
 namespace oge {
 
+// ---------------------------------------------------------------------------------------------- warp per block
 constexpr int INF_WARPS = 8;      // warps per CTA; 8 x 3.9 KB of tables = 31 KB of static shared memory
 
-__global__ void __launch_bounds__(INF_WARPS * 32, 4) bgzf_inflate_kernel(BgzfParams P) {
+__global__ void __launch_bounds__(INF_WARPS * 32, 4) bgzf_inflate_warps(BgzfParams P) {
     __shared__ oge_inflate::Tables tables[INF_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const oge_inflate::TablesRef T = oge_inflate::tables_ref(&tables[warp]);
     for (uint64_t b = (uint64_t) blockIdx.x * INF_WARPS + warp; b < P.n_blocks; b += (uint64_t) gridDim.x * INF_WARPS) {
         const uint64_t o0 = P.out_off[b], o1 = P.out_off[b + 1];
         if (o1 == o0) continue;      // the empty end-of-file block
-        const int rc = oge_inflate::inflate_block(P.comp + P.in_off[b] + 18, P.csize[b] - 26, P.out + o0, (uint32_t) (o1 - o0), &tables[warp], lane);
+        const int rc = oge_inflate::inflate_block<32, oge_inflate::LIT_BITS, oge_inflate::DIST_BITS>(
+            P.comp + P.in_off[b] + 18, P.csize[b] - 26, P.out + o0, (uint32_t) (o1 - o0), T, lane);
         if (rc && lane == 0 && atomicCAS(&P.err[0], 0u, (uint32_t) rc) == 0u) P.err[1] = (uint32_t) b;
         __syncwarp();
     }
 }
 
+// ---------------------------------------------------------------------------------------------- thread per block
+constexpr int INT_THREADS = 160;                      // streams per CTA, one CTA per SM
+constexpr int INT_LB = 9, INT_DB = 7;                 // primary table widths
+constexpr int INT_HOT_U16 = (1 << INT_LB) + (1 << INT_DB) + 2;      // + 2: odd number of 32-bit words per stream
+static_assert(((INT_HOT_U16 / 2) & 1) == 1, "an odd word stride spreads equal indices of the 32 lanes over the 32 banks");
+
+struct ColdTables {      // thread-local: touched when a deflate block starts and on the rare long codes
+    uint16_t cl_tab[1 << oge_inflate::CL_BITS];
+    uint16_t lit_sym[288], dist_sym[32], cl_sym[20];
+    uint16_t lit_cnt[16], dist_cnt[16], cl_cnt[16];
+    uint8_t lens[320];
+    int32_t status;
+};
+
+__global__ void __launch_bounds__(INT_THREADS, 1) bgzf_inflate_threads(BgzfParams P) {
+    extern __shared__ uint16_t hot[];      // [INT_THREADS][INT_HOT_U16]
+    ColdTables cold;
+    oge_inflate::TablesRef T;
+    T.lit_tab = hot + (size_t) threadIdx.x * INT_HOT_U16;
+    T.dist_tab = T.lit_tab + (1 << INT_LB);
+    T.cl_tab = cold.cl_tab;
+    T.lit_sym = cold.lit_sym; T.dist_sym = cold.dist_sym; T.cl_sym = cold.cl_sym;
+    T.lit_cnt = cold.lit_cnt; T.dist_cnt = cold.dist_cnt; T.cl_cnt = cold.cl_cnt;
+    T.lens = cold.lens;
+    T.status = &cold.status;
+    const uint64_t stride = (uint64_t) gridDim.x * INT_THREADS;
+    // consecutive lanes take consecutive blocks: similar sizes, so the 32 streams of a warp finish close together
+    for (uint64_t b = (uint64_t) blockIdx.x * INT_THREADS + threadIdx.x; b < P.n_blocks; b += stride) {
+        const uint64_t o0 = P.out_off[b], o1 = P.out_off[b + 1];
+        if (o1 == o0) continue;
+        const int rc = oge_inflate::inflate_block<1, INT_LB, INT_DB>(P.comp + P.in_off[b] + 18, P.csize[b] - 26, P.out + o0, (uint32_t) (o1 - o0), T, 0);
+        if (rc && atomicCAS(&P.err[0], 0u, (uint32_t) rc) == 0u) P.err[1] = (uint32_t) b;
+    }
+}
+
 int launch_bgzf_inflate(const BgzfParams &P, int sms, cudaStream_t stream, uint64_t *launches) {
     if (P.n_blocks == 0) return 0;
-    const uint64_t want = (P.n_blocks + INF_WARPS - 1) / INF_WARPS;
-    static int per_sm = 0;      // resident CTAs per SM: one wave, blocks are taken with a grid stride
-    if (!per_sm) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgzf_inflate_kernel, INF_WARPS * 32, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+    static int mode = -1;      // 0 threads (default), 1 warps
+    if (mode < 0) {
+        const char *e = getenv("OGE_INFLATE_KERNEL");
+        mode = e && !strcmp(e, "warp") ? 1 : 0;
     }
-    const uint64_t cap = (uint64_t) sms * per_sm;
-    bgzf_inflate_kernel<<<(uint32_t) (want < cap ? want : cap), INF_WARPS * 32, 0, stream>>>(P);
+    if (mode == 1) {
+        static int per_sm = 0;      // resident CTAs per SM: one wave, blocks are taken with a grid stride
+        if (!per_sm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgzf_inflate_warps, INF_WARPS * 32, 0) != cudaSuccess || per_sm < 1)) per_sm = 2;
+        const uint64_t want = (P.n_blocks + INF_WARPS - 1) / INF_WARPS, cap = (uint64_t) sms * per_sm;
+        bgzf_inflate_warps<<<(uint32_t) (want < cap ? want : cap), INF_WARPS * 32, 0, stream>>>(P);
+    } else {
+        const size_t smem = (size_t) INT_THREADS * INT_HOT_U16 * sizeof(uint16_t);
+        static bool configured = false;
+        if (!configured) {
+            OGE_CUDA_TRY(cudaFuncSetAttribute(bgzf_inflate_threads, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            configured = true;
+        }
+        const uint64_t want = (P.n_blocks + INT_THREADS - 1) / INT_THREADS;
+        bgzf_inflate_threads<<<(uint32_t) (want < (uint64_t) sms ? want : (uint64_t) sms), INT_THREADS, smem, stream>>>(P);
+    }
     *launches += 1;
     OGE_CUDA_TRY(cudaGetLastError());
     return 0;

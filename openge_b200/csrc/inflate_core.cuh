@@ -7,28 +7,34 @@
 // raw inflate, window 15, whole block in one call).  Like the reference, the CRC of the block is not checked; the
 // inflated length is (:137).
 //
-// The same source compiles for the host with ONE lane (OGE_INFLATE_LANES == 1): tests/native/inflate_host.cpp runs it
+// LANES is a template parameter.  LANES == 32: the warp-cooperative form described above.  LANES == 1: one THREAD per
+// block -- 32 independent streams per warp in SIMT lockstep, every lane doing useful decoding work; this is the form the
+// device uses by default (bgzf_inflate.cu: the warp-cooperative kernel turned out to be issue-bound, 31 of 32 lanes
+// repeating the same decode), and also the form that compiles for the host: tests/native/inflate_host.cpp runs it
 // against zlib on the CPU, so the decoding logic is checked without a GPU.
 #pragma once
 #include <stdint.h>
 
-#if defined(__CUDA_ARCH__)
-#define OGE_INFLATE_LANES 32
-#define OGE_INFLATE_SYNC() __syncwarp()
-#define OGE_HD __device__ __forceinline__
-#define OGE_HD_NOINLINE __device__ __noinline__
+#if defined(__CUDACC__)
+#define OGE_HD __host__ __device__ __forceinline__
+#define OGE_HD_NOINLINE __host__ __device__ __noinline__
 #else
-#define OGE_INFLATE_LANES 1
-#define OGE_INFLATE_SYNC() ((void) 0)
 #define OGE_HD static inline
 #define OGE_HD_NOINLINE static
 #endif
 
 namespace oge_inflate {
 
-constexpr int LIT_BITS = 10;      // primary table widths: codes up to this length decode with one lookup,
+constexpr int LIT_BITS = 10;      // primary table widths (warp form): codes up to this length decode with one lookup,
 constexpr int DIST_BITS = 8;      // longer ones (rare) walk the canonical code bit by bit
 constexpr int CL_BITS = 7;
+
+template <int LANES>
+OGE_HD void sync_lanes() {
+#if defined(__CUDA_ARCH__)
+    if (LANES > 1) __syncwarp();
+#endif
+}
 
 enum {
     INF_OK = 0,
@@ -51,6 +57,26 @@ struct Tables {
     uint8_t lens[320];
     int32_t status;      // scratch for lane 0's verdicts
 };
+
+// Where a decoder's tables live (one contiguous Tables block per warp, or hot tables in shared memory and the rest
+// in thread-local memory for the thread-per-block form).
+struct TablesRef {
+    uint16_t *lit_tab, *dist_tab, *cl_tab;
+    uint16_t *lit_sym, *dist_sym, *cl_sym;
+    uint16_t *lit_cnt, *dist_cnt, *cl_cnt;
+    uint8_t *lens;        // 320
+    int32_t *status;
+};
+
+OGE_HD TablesRef tables_ref(Tables *T) {
+    TablesRef R;
+    R.lit_tab = T->lit_tab; R.dist_tab = T->dist_tab; R.cl_tab = T->cl_tab;
+    R.lit_sym = T->lit_sym; R.dist_sym = T->dist_sym; R.cl_sym = T->cl_sym;
+    R.lit_cnt = T->lit_cnt; R.dist_cnt = T->dist_cnt; R.cl_cnt = T->cl_cnt;
+    R.lens = T->lens;
+    R.status = &T->status;
+    return R;
+}
 
 struct BitReader {
     const uint32_t *wp;      // next aligned word
@@ -95,8 +121,9 @@ OGE_HD uint32_t bit_reverse(uint32_t v, int n) {
 // canonical order; tab[] = primary lookup on the next `bits` stream bits: symbol | length << 9, or 0 for "longer
 // than `bits`, or no such code".  Lane 0 counts and orders, all lanes fill the lookup table.
 // Returns (in every lane) 0, or INF_ERR_LENGTHS for an over-subscribed set.
+template <int LANES>
 OGE_HD_NOINLINE int build_tables(const uint8_t *lens, int n, int bits, uint16_t *tab, uint16_t *sym, uint16_t *cnt, int32_t *status, int lane) {
-    OGE_INFLATE_SYNC();
+    sync_lanes<LANES>();
     if (lane == 0) {
         for (int l = 0; l < 16; l++) cnt[l] = 0;
         for (int i = 0; i < n; i++) cnt[lens[i]]++;
@@ -113,8 +140,8 @@ OGE_HD_NOINLINE int build_tables(const uint8_t *lens, int n, int bits, uint16_t 
             if (lens[i]) sym[offs[lens[i]]++] = (uint16_t) i;
         *status = bad ? INF_ERR_LENGTHS : 0;
     }
-    for (int k = lane; k < (1 << bits); k += OGE_INFLATE_LANES) tab[k] = 0;
-    OGE_INFLATE_SYNC();
+    for (int k = lane; k < (1 << bits); k += LANES) tab[k] = 0;
+    sync_lanes<LANES>();
     if (*status) return *status;
     // first code and first canonical index of every length
     uint32_t first_code[16], first_idx[16];
@@ -130,7 +157,7 @@ OGE_HD_NOINLINE int build_tables(const uint8_t *lens, int n, int bits, uint16_t 
     }
     int total = 0;
     for (int l = 1; l < 16; l++) total += cnt[l];
-    for (int i = lane; i < total; i += OGE_INFLATE_LANES) {
+    for (int i = lane; i < total; i += LANES) {
         const uint32_t s = sym[i];
         const int l = lens[s];
         if (l > bits) continue;
@@ -138,7 +165,7 @@ OGE_HD_NOINLINE int build_tables(const uint8_t *lens, int n, int bits, uint16_t 
         const uint16_t e = (uint16_t) (s | ((uint32_t) l << 9));
         for (uint32_t k = bit_reverse(code, l); k < (1u << bits); k += 1u << l) tab[k] = e;
     }
-    OGE_INFLATE_SYNC();
+    sync_lanes<LANES>();
     return 0;
 }
 
@@ -178,7 +205,9 @@ OGE_HD int cl_order(int i) {
 // Inflates one raw deflate stream of `in_len` bytes (a BGZF block's payload) into exactly `out_len` bytes.
 // Called by all lanes of a warp with identical arguments (or by one host thread).  Readable slack: up to 12 bytes
 // past in + in_len (the gzip footer and the next block header are there).
-OGE_HD_NOINLINE int inflate_block(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_len, Tables *T, int lane) {
+template <int LANES, int LB, int DB>
+OGE_HD_NOINLINE int inflate_block(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_len, const TablesRef &TR, int lane) {
+    const TablesRef *T = &TR;
     BitReader r;
     br_init(r, in, in_len);
     uint32_t pos = 0;
@@ -197,14 +226,14 @@ OGE_HD_NOINLINE int inflate_block(const uint8_t *in, uint32_t in_len, uint8_t *o
             // byte position of the reader: words consumed minus the bytes still buffered
             const uint8_t *src = reinterpret_cast<const uint8_t *>(r.wp) - (r.cnt >> 3);
             if (src + len > in + in_len) return INF_ERR_OVERRUN;
-            for (uint32_t j = lane; j < len; j += OGE_INFLATE_LANES) out[pos + j] = src[j];
+            for (uint32_t j = lane; j < len; j += LANES) out[pos + j] = src[j];
             pos += len;
             br_init(r, src + len, (uint32_t) (in + in_len - (src + len)));
         } else if (type == 1 || type == 2) {
             int n_lit, n_dist;
             if (type == 1) {      // fixed code (RFC 1951 3.2.6)
-                for (int i = lane; i < 288; i += OGE_INFLATE_LANES) T->lens[i] = i < 144 ? 8 : (i < 256 ? 9 : (i < 280 ? 7 : 8));
-                for (int i = lane; i < 30; i += OGE_INFLATE_LANES) T->lens[288 + i] = 5;
+                for (int i = lane; i < 288; i += LANES) T->lens[i] = i < 144 ? 8 : (i < 256 ? 9 : (i < 280 ? 7 : 8));
+                for (int i = lane; i < 30; i += LANES) T->lens[288 + i] = 5;
                 n_lit = 288;
                 n_dist = 30;
             } else {              // dynamic code (3.2.7)
@@ -214,15 +243,15 @@ OGE_HD_NOINLINE int inflate_block(const uint8_t *in, uint32_t in_len, uint8_t *o
                 const int n_cl = (int) br_take(r, 4) + 4;
                 if (n_lit > 286 || n_dist > 30) return INF_ERR_LENGTHS;
                 uint8_t *cl = T->lens + 300;      // 19 code-length code lengths, parked at the end of lens[]
-                OGE_INFLATE_SYNC();
-                for (int i = lane; i < 19; i += OGE_INFLATE_LANES) cl[i] = 0;
-                OGE_INFLATE_SYNC();
+                sync_lanes<LANES>();
+                for (int i = lane; i < 19; i += LANES) cl[i] = 0;
+                sync_lanes<LANES>();
                 for (int i = 0; i < n_cl; i++) {
                     br_refill(r);
                     const uint32_t v = br_take(r, 3);
                     if (lane == 0) cl[cl_order(i)] = (uint8_t) v;
                 }
-                int rc = build_tables(cl, 19, CL_BITS, T->cl_tab, T->cl_sym, T->cl_cnt, &T->status, lane);
+                int rc = build_tables<LANES>(cl, 19, CL_BITS, T->cl_tab, T->cl_sym, T->cl_cnt, T->status, lane);
                 if (rc) return rc;
                 int i = 0;
                 uint32_t prev = 0;
@@ -248,32 +277,32 @@ OGE_HD_NOINLINE int inflate_block(const uint8_t *in, uint32_t in_len, uint8_t *o
                             rep = 11 + (int) br_take(r, 7);
                         }
                         if (i + rep > n_lit + n_dist) return INF_ERR_LENGTHS;
-                        for (int k = lane; k < rep; k += OGE_INFLATE_LANES) T->lens[i + k] = (uint8_t) v;
+                        for (int k = lane; k < rep; k += LANES) T->lens[i + k] = (uint8_t) v;
                         i += rep;
                         if (s != 16) prev = 0;
                     }
                 }
-                OGE_INFLATE_SYNC();
+                sync_lanes<LANES>();
                 if (T->lens[256] == 0) return INF_ERR_LENGTHS;      // no end-of-block code
                 // distance lengths follow the literal/length ones in the stream; give them their own start
                 if (n_lit < 288) {
-                    OGE_INFLATE_SYNC();
+                    sync_lanes<LANES>();
                     uint8_t d[32];
                     for (int k = 0; k < n_dist; k++) d[k] = T->lens[n_lit + k];
-                    OGE_INFLATE_SYNC();
-                    for (int k = lane; k < n_dist; k += OGE_INFLATE_LANES) T->lens[288 + k] = d[k];
-                    OGE_INFLATE_SYNC();
+                    sync_lanes<LANES>();
+                    for (int k = lane; k < n_dist; k += LANES) T->lens[288 + k] = d[k];
+                    sync_lanes<LANES>();
                 }
             }
-            int rc = build_tables(T->lens, n_lit, LIT_BITS, T->lit_tab, T->lit_sym, T->lit_cnt, &T->status, lane);
+            int rc = build_tables<LANES>(T->lens, n_lit, LB, T->lit_tab, T->lit_sym, T->lit_cnt, T->status, lane);
             if (rc) return rc;
-            rc = build_tables(T->lens + 288, n_dist, DIST_BITS, T->dist_tab, T->dist_sym, T->dist_cnt, &T->status, lane);
+            rc = build_tables<LANES>(T->lens + 288, n_dist, DB, T->dist_tab, T->dist_sym, T->dist_cnt, T->status, lane);
             if (rc) return rc;
 
             // ---- the symbol loop
             while (true) {
                 br_refill(r);
-                int s = decode_symbol(r, T->lit_tab, LIT_BITS, T->lit_sym, T->lit_cnt);
+                int s = decode_symbol(r, T->lit_tab, LB, T->lit_sym, T->lit_cnt);
                 if (s < 256) {
                     if (s < 0) return INF_ERR_SYMBOL;
                     if (pos >= out_len) return INF_ERR_OVERRUN;
@@ -293,7 +322,7 @@ OGE_HD_NOINLINE int inflate_block(const uint8_t *in, uint32_t in_len, uint8_t *o
                     len = ((4u + (uint32_t) ((s - 261) & 3)) << e) + 3 + br_take(r, e);
                 }
                 br_refill(r);
-                const int ds = decode_symbol(r, T->dist_tab, DIST_BITS, T->dist_sym, T->dist_cnt);
+                const int ds = decode_symbol(r, T->dist_tab, DB, T->dist_sym, T->dist_cnt);
                 if (ds < 0 || ds > 29) return INF_ERR_SYMBOL;
                 uint32_t dist;
                 br_refill(r);
@@ -304,11 +333,11 @@ OGE_HD_NOINLINE int inflate_block(const uint8_t *in, uint32_t in_len, uint8_t *o
                 }
                 if (dist > pos) return INF_ERR_DISTANCE;
                 if (pos + len > out_len) return INF_ERR_OVERRUN;
-                OGE_INFLATE_SYNC();      // the bytes this match copies may have been written by other lanes
-                if (dist >= len) {
-                    for (uint32_t j = lane; j < len; j += OGE_INFLATE_LANES) out[pos + j] = out[pos - dist + j];
+                sync_lanes<LANES>();      // the bytes this match copies may have been written by other lanes
+                if (LANES == 1 || dist >= len) {      // one lane copies front to back, which is the definition of an overlapping match
+                    for (uint32_t j = lane; j < len; j += LANES) out[pos + j] = out[pos - dist + j];
                 } else {                 // overlapping: the source repeats with period dist
-                    for (uint32_t j = lane; j < len; j += OGE_INFLATE_LANES) out[pos + j] = out[pos - dist + (j % dist)];
+                    for (uint32_t j = lane; j < len; j += LANES) out[pos + j] = out[pos - dist + (j % dist)];
                 }
                 pos += len;
                 if (r.wp > in_stop) return INF_ERR_OVERRUN;
@@ -319,7 +348,7 @@ OGE_HD_NOINLINE int inflate_block(const uint8_t *in, uint32_t in_len, uint8_t *o
         if (last) break;
         if (r.wp > in_stop) return INF_ERR_OVERRUN;
     }
-    OGE_INFLATE_SYNC();
+    sync_lanes<LANES>();
     return pos == out_len ? INF_OK : INF_ERR_SHORT;
 }
 

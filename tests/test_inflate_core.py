@@ -22,13 +22,16 @@ def lib():
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core)):
         subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-I", os.path.join(ROOT, "openge_b200", "csrc"), src, "-o", so], check=True)
     L = C.CDLL(so)
-    L.oge_test_inflate_block.argtypes = [C.c_char_p, C.c_uint, C.c_void_p, C.c_uint]
+    L.oge_test_inflate_block2.argtypes = [C.c_char_p, C.c_uint, C.c_void_p, C.c_uint, C.c_int]
     return L
+
+
+SMALL = [0]      # 1: the table widths of the thread-per-block kernel (9 / 7 bits)
 
 
 def inflate(L, z, n):
     out = np.zeros(max(1, n), dtype=np.uint8)
-    rc = L.oge_test_inflate_block(z, len(z), out.ctypes.data, n)
+    rc = L.oge_test_inflate_block2(z, len(z), out.ctypes.data, n, SMALL[0])
     return rc, out[:n].tobytes()
 
 
@@ -55,7 +58,9 @@ def test_tables_fit_the_shared_memory_budget(lib):
     assert lib.oge_test_inflate_tables_bytes() * 8 <= 48 * 1024      # 8 warps per CTA, static shared memory
 
 
-def test_decoder_matches_zlib_on_every_block_type(lib):
+@pytest.mark.parametrize("small", [0, 1])
+def test_decoder_matches_zlib_on_every_block_type(lib, small):
+    SMALL[0] = small
     n = 0
     for data in payloads():
         for level in (0, 1, 6, 9):
@@ -66,6 +71,7 @@ def test_decoder_matches_zlib_on_every_block_type(lib):
                 assert rc == 0 and out == data, (len(data), level, strategy, rc)
                 n += 1
     assert n > 300
+    SMALL[0] = 0
 
 
 def test_multi_block_streams_with_sync_flushes(lib):
