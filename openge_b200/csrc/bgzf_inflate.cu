@@ -3,13 +3,16 @@
 // The compressed file crosses PCIe (a third to a quarter of the inflated bytes) and the records are born in HBM, where
 // the dedup path wants them; nothing is staged through host zlib.  Two kernels over the same decoder (inflate_core.cuh):
 //
-//   bgzf_inflate_threads (default)  one THREAD per block: a warp decodes 32 streams in SIMT lockstep.  The two hot lookup
-//       tables of a stream (9-bit literal/length, 7-bit distance: 1.25 KB) sit in shared memory at an odd word stride, so
-//       that lanes reading the same index hit different banks; the cold arrays (code lengths, canonical symbol order,
-//       counts) are thread-local.  160 streams per SM.
-//   bgzf_inflate_warps (OGE_INFLATE_KERNEL=warp)  one WARP per block, decode state redundant in all lanes, matches copied by
-//       32 lanes.  First version: correct, but measured issue-bound at 24 GB/s -- 31 of 32 lanes repeat the same ~40
-//       instructions per literal (profiles/r1_inflate_*.txt) -- which is why the thread form exists.
+//   bgzf_inflate_warps    one WARP per block, decode state redundant in all lanes, matches copied by 32 lanes.  Correct and
+//       simple, but issue-bound: 31 of 32 lanes repeat the same ~40 instructions per literal (79 % issue slots busy,
+//       21-23 GB/s of inflated bytes; profiles/r1_inflate_kernels.txt).
+//   bgzf_inflate_threads  one THREAD per block: a warp decodes 32 streams, each lane doing useful work, as a state machine
+//       that keeps the lanes converged (inflate_lockstep).  The two hot lookup tables of a stream (9-bit literal/length,
+//       7-bit distance: 1.25 KB) sit in shared memory at an odd word stride, so that lanes reading the same index hit
+//       different banks; the cold arrays (code lengths, canonical symbol order, counts) are thread-local.  160 streams
+//       per SM.  (Its first version ran inflate_block<1> per lane: the lanes drifted apart at the first data-dependent
+//       branch and the warp executed one lane at a time -- 4.4-5.2 GB/s.)
+// OGE_INFLATE_KERNEL=warp|threads picks one; the default is the one that measured faster.
 #include <stdlib.h>
 #include <string.h>
 
@@ -61,21 +64,27 @@ __global__ void __launch_bounds__(INT_THREADS, 1) bgzf_inflate_threads(BgzfParam
     T.lens = cold.lens;
     T.status = &cold.status;
     const uint64_t stride = (uint64_t) gridDim.x * INT_THREADS;
-    // consecutive lanes take consecutive blocks: similar sizes, so the 32 streams of a warp finish close together
-    for (uint64_t b = (uint64_t) blockIdx.x * INT_THREADS + threadIdx.x; b < P.n_blocks; b += stride) {
-        const uint64_t o0 = P.out_off[b], o1 = P.out_off[b + 1];
-        if (o1 == o0) continue;
-        const int rc = oge_inflate::inflate_block<1, INT_LB, INT_DB>(P.comp + P.in_off[b] + 18, P.csize[b] - 26, P.out + o0, (uint32_t) (o1 - o0), T, 0);
+    // consecutive lanes take consecutive blocks: similar sizes, so the 32 streams of a warp finish close together.
+    // The trip count is warp-uniform (lanes past the end keep the others company inside inflate_lockstep).
+    for (uint64_t b = (uint64_t) blockIdx.x * INT_THREADS + threadIdx.x; __any_sync(0xFFFFFFFFu, b < P.n_blocks); b += stride) {
+        uint64_t o0 = 0, o1 = 0;
+        if (b < P.n_blocks) {
+            o0 = P.out_off[b];
+            o1 = P.out_off[b + 1];
+        }
+        const bool active = o1 > o0;      // not past the end, not the empty end-of-file block
+        const int rc = oge_inflate::inflate_lockstep<INT_LB, INT_DB>(active ? P.comp + P.in_off[b] + 18 : nullptr, active ? P.csize[b] - 26 : 0,
+                                                                     P.out + o0, (uint32_t) (o1 - o0), T, active);
         if (rc && atomicCAS(&P.err[0], 0u, (uint32_t) rc) == 0u) P.err[1] = (uint32_t) b;
     }
 }
 
 int launch_bgzf_inflate(const BgzfParams &P, int sms, cudaStream_t stream, uint64_t *launches) {
     if (P.n_blocks == 0) return 0;
-    static int mode = -1;      // 0 threads (default), 1 warps
+    static int mode = -1;      // 0 threads, 1 warps (default)
     if (mode < 0) {
         const char *e = getenv("OGE_INFLATE_KERNEL");
-        mode = e && !strcmp(e, "warp") ? 1 : 0;
+        mode = e && !strcmp(e, "threads") ? 0 : 1;
     }
     if (mode == 1) {
         static int per_sm = 0;      // resident CTAs per SM: one wave, blocks are taken with a grid stride

@@ -202,107 +202,154 @@ OGE_HD int cl_order(int i) {
     return (int) ((i < 12 ? lo >> (5 * i) : hi >> (5 * (i - 12))) & 31u);
 }
 
-// Inflates one raw deflate stream of `in_len` bytes (a BGZF block's payload) into exactly `out_len` bytes.
-// Called by all lanes of a warp with identical arguments (or by one host thread).  Readable slack: up to 12 bytes
-// past in + in_len (the gzip footer and the next block header are there).
+// One deflate block header (RFC 1951 3.2.3): BFINAL, BTYPE; a stored block is copied here and then; for a Huffman
+// block the code lengths are read (3.2.6 / 3.2.7) and the lookup tables built.  *huff = a symbol stream follows.
+// (Inlined on purpose: taken by reference into a real call, the bit reader would live in local memory and every
+// symbol of the hot loop would pay for it -- measured: 750 M local loads, 22 GB of DRAM reads for a 1 GB file.)
 template <int LANES, int LB, int DB>
-OGE_HD_NOINLINE int inflate_block(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_len, const TablesRef &TR, int lane) {
-    const TablesRef *T = &TR;
+OGE_HD int block_header(BitReader &r, const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_len, uint32_t &pos,
+                                 const TablesRef TR, int lane, uint32_t *last_out, bool *huff) {
+    br_refill(r);
+    const uint32_t last = br_take(r, 1), type = br_take(r, 2);
+    *last_out = last;
+    *huff = false;
+    if (type == 0) {      // stored
+        br_drop(r, r.cnt & 7);
+        br_refill(r);
+        const uint32_t len = br_take(r, 16);
+        br_refill(r);
+        const uint32_t nlen = br_take(r, 16);
+        if ((len ^ nlen) != 0xFFFFu) return INF_ERR_STORED;
+        if (pos + len > out_len) return INF_ERR_OVERRUN;
+        // byte position of the reader: words consumed minus the bytes still buffered
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(r.wp) - (r.cnt >> 3);
+        if (src + len > in + in_len) return INF_ERR_OVERRUN;
+        for (uint32_t j = lane; j < len; j += LANES) out[pos + j] = src[j];
+        pos += len;
+        br_init(r, src + len, (uint32_t) (in + in_len - (src + len)));
+        return INF_OK;
+    }
+    if (type == 3) return INF_ERR_BTYPE;
+    int n_lit, n_dist;
+    if (type == 1) {      // fixed code (RFC 1951 3.2.6)
+        for (int i = lane; i < 288; i += LANES) TR.lens[i] = i < 144 ? 8 : (i < 256 ? 9 : (i < 280 ? 7 : 8));
+        for (int i = lane; i < 30; i += LANES) TR.lens[288 + i] = 5;
+        n_lit = 288;
+        n_dist = 30;
+    } else {              // dynamic code (3.2.7)
+        br_refill(r);
+        n_lit = (int) br_take(r, 5) + 257;
+        n_dist = (int) br_take(r, 5) + 1;
+        const int n_cl = (int) br_take(r, 4) + 4;
+        if (n_lit > 286 || n_dist > 30) return INF_ERR_LENGTHS;
+        uint8_t *cl = TR.lens + 300;      // 19 code-length code lengths, parked at the end of lens[]
+        sync_lanes<LANES>();
+        for (int i = lane; i < 19; i += LANES) cl[i] = 0;
+        sync_lanes<LANES>();
+        for (int i = 0; i < n_cl; i++) {
+            br_refill(r);
+            const uint32_t v = br_take(r, 3);
+            if (lane == 0) cl[cl_order(i)] = (uint8_t) v;
+        }
+        int rc = build_tables<LANES>(cl, 19, CL_BITS, TR.cl_tab, TR.cl_sym, TR.cl_cnt, TR.status, lane);
+        if (rc) return rc;
+        int i = 0;
+        uint32_t prev = 0;
+        while (i < n_lit + n_dist) {
+            br_refill(r);
+            const int s = decode_symbol(r, TR.cl_tab, CL_BITS, TR.cl_sym, TR.cl_cnt);
+            if (s < 0) return INF_ERR_SYMBOL;
+            if (s < 16) {
+                if (lane == 0) TR.lens[i] = (uint8_t) s;
+                prev = (uint32_t) s;
+                i++;
+            } else {
+                uint32_t v = 0;
+                int rep;
+                br_refill(r);
+                if (s == 16) {
+                    if (i == 0) return INF_ERR_LENGTHS;
+                    v = prev;
+                    rep = 3 + (int) br_take(r, 2);
+                } else if (s == 17) {
+                    rep = 3 + (int) br_take(r, 3);
+                } else {
+                    rep = 11 + (int) br_take(r, 7);
+                }
+                if (i + rep > n_lit + n_dist) return INF_ERR_LENGTHS;
+                for (int k = lane; k < rep; k += LANES) TR.lens[i + k] = (uint8_t) v;
+                i += rep;
+                if (s != 16) prev = 0;
+            }
+        }
+        sync_lanes<LANES>();
+        if (TR.lens[256] == 0) return INF_ERR_LENGTHS;      // no end-of-block code
+        // distance lengths follow the literal/length ones in the stream; give them their own start
+        if (n_lit < 288) {
+            sync_lanes<LANES>();
+            uint8_t d[32];
+            for (int k = 0; k < n_dist; k++) d[k] = TR.lens[n_lit + k];
+            sync_lanes<LANES>();
+            for (int k = lane; k < n_dist; k += LANES) TR.lens[288 + k] = d[k];
+            sync_lanes<LANES>();
+        }
+    }
+    int rc = build_tables<LANES>(TR.lens, n_lit, LB, TR.lit_tab, TR.lit_sym, TR.lit_cnt, TR.status, lane);
+    if (rc) return rc;
+    rc = build_tables<LANES>(TR.lens + 288, n_dist, DB, TR.dist_tab, TR.dist_sym, TR.dist_cnt, TR.status, lane);
+    if (rc) return rc;
+    *huff = true;
+    return INF_OK;
+}
+
+// Length and distance of a match whose literal/length symbol s (257..285) has been decoded (RFC 1951 3.2.5: bases and
+// extra bits by formula).  Returns 0 or an error.
+template <int DB>
+OGE_HD int match_params(BitReader &r, int s, const TablesRef T, uint32_t *len_out, uint32_t *dist_out) {
+    if (s > 285) return INF_ERR_SYMBOL;
+    uint32_t len;
+    br_refill(r);
+    if (s < 265) len = (uint32_t) s - 254;
+    else if (s == 285) len = 258;
+    else {
+        const int e = (s - 261) >> 2;
+        len = ((4u + (uint32_t) ((s - 261) & 3)) << e) + 3 + br_take(r, e);
+    }
+    br_refill(r);
+    const int ds = decode_symbol(r, T.dist_tab, DB, T.dist_sym, T.dist_cnt);
+    if (ds < 0 || ds > 29) return INF_ERR_SYMBOL;
+    uint32_t dist;
+    br_refill(r);
+    if (ds < 4) dist = (uint32_t) ds + 1;
+    else {
+        const int e = (ds >> 1) - 1;
+        dist = ((2u + (uint32_t) (ds & 1)) << e) + 1 + br_take(r, e);
+    }
+    *len_out = len;
+    *dist_out = dist;
+    return INF_OK;
+}
+
+// Inflates one raw deflate stream of `in_len` bytes (a BGZF block's payload) into exactly `out_len` bytes.
+// Called by all lanes of a warp with identical arguments (LANES == 32), or by one thread (LANES == 1).  Readable slack:
+// up to 12 bytes past in + in_len (the gzip footer and the next block header are there).
+template <int LANES, int LB, int DB>
+OGE_HD_NOINLINE int inflate_block(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_len, const TablesRef TR, int lane) {
+    // the table pointers by value, in registers: reached through a reference they would be reloaded from local memory
+    // for every symbol (the byte stores to `out` could alias them as far as the compiler knows)
     BitReader r;
     br_init(r, in, in_len);
     uint32_t pos = 0;
     const uint32_t *in_stop = r.end + 3;      // reading zeros beyond the data means the stream is broken
     while (true) {
-        br_refill(r);
-        const uint32_t last = br_take(r, 1), type = br_take(r, 2);
-        if (type == 0) {      // stored
-            br_drop(r, r.cnt & 7);
-            br_refill(r);
-            const uint32_t len = br_take(r, 16);
-            br_refill(r);
-            const uint32_t nlen = br_take(r, 16);
-            if ((len ^ nlen) != 0xFFFFu) return INF_ERR_STORED;
-            if (pos + len > out_len) return INF_ERR_OVERRUN;
-            // byte position of the reader: words consumed minus the bytes still buffered
-            const uint8_t *src = reinterpret_cast<const uint8_t *>(r.wp) - (r.cnt >> 3);
-            if (src + len > in + in_len) return INF_ERR_OVERRUN;
-            for (uint32_t j = lane; j < len; j += LANES) out[pos + j] = src[j];
-            pos += len;
-            br_init(r, src + len, (uint32_t) (in + in_len - (src + len)));
-        } else if (type == 1 || type == 2) {
-            int n_lit, n_dist;
-            if (type == 1) {      // fixed code (RFC 1951 3.2.6)
-                for (int i = lane; i < 288; i += LANES) T->lens[i] = i < 144 ? 8 : (i < 256 ? 9 : (i < 280 ? 7 : 8));
-                for (int i = lane; i < 30; i += LANES) T->lens[288 + i] = 5;
-                n_lit = 288;
-                n_dist = 30;
-            } else {              // dynamic code (3.2.7)
+        uint32_t last;
+        bool huff;
+        const int hrc = block_header<LANES, LB, DB>(r, in, in_len, out, out_len, pos, TR, lane, &last, &huff);
+        if (hrc) return hrc;
+        if (huff) {
+            while (true) {      // ---- the symbol loop
                 br_refill(r);
-                n_lit = (int) br_take(r, 5) + 257;
-                n_dist = (int) br_take(r, 5) + 1;
-                const int n_cl = (int) br_take(r, 4) + 4;
-                if (n_lit > 286 || n_dist > 30) return INF_ERR_LENGTHS;
-                uint8_t *cl = T->lens + 300;      // 19 code-length code lengths, parked at the end of lens[]
-                sync_lanes<LANES>();
-                for (int i = lane; i < 19; i += LANES) cl[i] = 0;
-                sync_lanes<LANES>();
-                for (int i = 0; i < n_cl; i++) {
-                    br_refill(r);
-                    const uint32_t v = br_take(r, 3);
-                    if (lane == 0) cl[cl_order(i)] = (uint8_t) v;
-                }
-                int rc = build_tables<LANES>(cl, 19, CL_BITS, T->cl_tab, T->cl_sym, T->cl_cnt, T->status, lane);
-                if (rc) return rc;
-                int i = 0;
-                uint32_t prev = 0;
-                while (i < n_lit + n_dist) {
-                    br_refill(r);
-                    const int s = decode_symbol(r, T->cl_tab, CL_BITS, T->cl_sym, T->cl_cnt);
-                    if (s < 0) return INF_ERR_SYMBOL;
-                    if (s < 16) {
-                        if (lane == 0) T->lens[i] = (uint8_t) s;
-                        prev = (uint32_t) s;
-                        i++;
-                    } else {
-                        uint32_t v = 0;
-                        int rep;
-                        br_refill(r);
-                        if (s == 16) {
-                            if (i == 0) return INF_ERR_LENGTHS;
-                            v = prev;
-                            rep = 3 + (int) br_take(r, 2);
-                        } else if (s == 17) {
-                            rep = 3 + (int) br_take(r, 3);
-                        } else {
-                            rep = 11 + (int) br_take(r, 7);
-                        }
-                        if (i + rep > n_lit + n_dist) return INF_ERR_LENGTHS;
-                        for (int k = lane; k < rep; k += LANES) T->lens[i + k] = (uint8_t) v;
-                        i += rep;
-                        if (s != 16) prev = 0;
-                    }
-                }
-                sync_lanes<LANES>();
-                if (T->lens[256] == 0) return INF_ERR_LENGTHS;      // no end-of-block code
-                // distance lengths follow the literal/length ones in the stream; give them their own start
-                if (n_lit < 288) {
-                    sync_lanes<LANES>();
-                    uint8_t d[32];
-                    for (int k = 0; k < n_dist; k++) d[k] = T->lens[n_lit + k];
-                    sync_lanes<LANES>();
-                    for (int k = lane; k < n_dist; k += LANES) T->lens[288 + k] = d[k];
-                    sync_lanes<LANES>();
-                }
-            }
-            int rc = build_tables<LANES>(T->lens, n_lit, LB, T->lit_tab, T->lit_sym, T->lit_cnt, T->status, lane);
-            if (rc) return rc;
-            rc = build_tables<LANES>(T->lens + 288, n_dist, DB, T->dist_tab, T->dist_sym, T->dist_cnt, T->status, lane);
-            if (rc) return rc;
-
-            // ---- the symbol loop
-            while (true) {
-                br_refill(r);
-                int s = decode_symbol(r, T->lit_tab, LB, T->lit_sym, T->lit_cnt);
+                int s = decode_symbol(r, TR.lit_tab, LB, TR.lit_sym, TR.lit_cnt);
                 if (s < 256) {
                     if (s < 0) return INF_ERR_SYMBOL;
                     if (pos >= out_len) return INF_ERR_OVERRUN;
@@ -311,26 +358,9 @@ OGE_HD_NOINLINE int inflate_block(const uint8_t *in, uint32_t in_len, uint8_t *o
                     continue;
                 }
                 if (s == 256) break;
-                if (s > 285) return INF_ERR_SYMBOL;
-                // length: base and extra bits by formula (RFC 1951 3.2.5)
-                uint32_t len;
-                br_refill(r);
-                if (s < 265) len = (uint32_t) s - 254;
-                else if (s == 285) len = 258;
-                else {
-                    const int e = (s - 261) >> 2;
-                    len = ((4u + (uint32_t) ((s - 261) & 3)) << e) + 3 + br_take(r, e);
-                }
-                br_refill(r);
-                const int ds = decode_symbol(r, T->dist_tab, DB, T->dist_sym, T->dist_cnt);
-                if (ds < 0 || ds > 29) return INF_ERR_SYMBOL;
-                uint32_t dist;
-                br_refill(r);
-                if (ds < 4) dist = (uint32_t) ds + 1;
-                else {
-                    const int e = (ds >> 1) - 1;
-                    dist = ((2u + (uint32_t) (ds & 1)) << e) + 1 + br_take(r, e);
-                }
+                uint32_t len, dist;
+                const int mrc = match_params<DB>(r, s, TR, &len, &dist);
+                if (mrc) return mrc;
                 if (dist > pos) return INF_ERR_DISTANCE;
                 if (pos + len > out_len) return INF_ERR_OVERRUN;
                 sync_lanes<LANES>();      // the bytes this match copies may have been written by other lanes
@@ -342,14 +372,77 @@ OGE_HD_NOINLINE int inflate_block(const uint8_t *in, uint32_t in_len, uint8_t *o
                 pos += len;
                 if (r.wp > in_stop) return INF_ERR_OVERRUN;
             }
-        } else {
-            return INF_ERR_BTYPE;
         }
         if (last) break;
         if (r.wp > in_stop) return INF_ERR_OVERRUN;
     }
     sync_lanes<LANES>();
     return pos == out_len ? INF_OK : INF_ERR_SHORT;
+}
+
+// The same decoder for 32 INDEPENDENT streams held by the 32 lanes of a warp, written as a state machine so that the
+// lanes stay converged: every trip of the loop, every lane that still has work does ONE step of its own stream (a
+// literal, a match, or a block header) and all lanes meet again at the end of the trip.  Written the obvious way (each
+// lane running inflate_block<1> on its own) the lanes drift apart after the first data-dependent branch and the warp
+// executes one lane at a time: measured, 64 G warp-instructions for 1.5 GB -- as many as the warp-cooperative form.
+// `active` = this lane has a stream; lanes without one only keep the others company.
+template <int LB, int DB>
+OGE_HD_NOINLINE int inflate_lockstep(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_len, const TablesRef TR, bool active) {
+    enum { ST_HEADER = 0, ST_DECODE = 1, ST_DONE = 2 };
+    BitReader r;
+    r.wp = r.end = nullptr;
+    r.buf = 0;
+    r.cnt = 0;
+    const uint32_t *in_stop = nullptr;
+    uint32_t pos = 0, last = 0;
+    int rc = INF_OK, state = ST_DONE;
+    if (active) {
+        br_init(r, in, in_len);
+        in_stop = r.end + 3;
+        state = ST_HEADER;
+    }
+    while (true) {
+#if defined(__CUDA_ARCH__)
+        if (!__any_sync(0xFFFFFFFFu, state != ST_DONE)) break;
+#else
+        if (state == ST_DONE) break;
+#endif
+        if (state == ST_DECODE) {
+            br_refill(r);
+            const int s = decode_symbol(r, TR.lit_tab, LB, TR.lit_sym, TR.lit_cnt);
+            if (s < 256) {
+                if (s < 0) { rc = INF_ERR_SYMBOL; state = ST_DONE; }
+                else if (pos >= out_len) { rc = INF_ERR_OVERRUN; state = ST_DONE; }
+                else out[pos++] = (uint8_t) s;
+            } else if (s == 256) {
+                state = last ? ST_DONE : ST_HEADER;
+                if (r.wp > in_stop) { rc = INF_ERR_OVERRUN; state = ST_DONE; }
+            } else {
+                uint32_t len = 0, dist = 0;
+                rc = match_params<DB>(r, s, TR, &len, &dist);
+                if (!rc && dist > pos) rc = INF_ERR_DISTANCE;
+                if (!rc && pos + len > out_len) rc = INF_ERR_OVERRUN;
+                if (!rc && r.wp > in_stop) rc = INF_ERR_OVERRUN;
+                if (rc) state = ST_DONE;
+                else {
+                    for (uint32_t j = 0; j < len; j++) out[pos + j] = out[pos - dist + j];      // front to back: overlap-safe
+                    pos += len;
+                }
+            }
+        } else if (state == ST_HEADER) {
+            bool huff = false;
+            rc = block_header<1, LB, DB>(r, in, in_len, out, out_len, pos, TR, 0, &last, &huff);
+            if (rc) state = ST_DONE;
+            else if (huff) state = ST_DECODE;
+            else state = last ? ST_DONE : ST_HEADER;
+            if (!rc && r.wp > in_stop) { rc = INF_ERR_OVERRUN; state = ST_DONE; }
+        }
+#if defined(__CUDA_ARCH__)
+        __syncwarp();
+#endif
+    }
+    if (active && rc == INF_OK && pos != out_len) rc = INF_ERR_SHORT;
+    return rc;
 }
 
 }  // namespace oge_inflate

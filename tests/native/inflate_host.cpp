@@ -11,7 +11,9 @@ extern "C" int oge_test_inflate_block2(const unsigned char *in, unsigned in_len,
     unsigned char *padded = (unsigned char *) calloc(1, (size_t) in_len + 32);
     memcpy(padded, in, in_len);
     int rc;
-    if (small_tables)      // the widths the thread-per-block kernel uses
+    if (small_tables == 2)      // the state-machine form of the thread-per-block kernel, with its table widths
+        rc = oge_inflate::inflate_lockstep<9, 7>(padded, in_len, out, out_len, oge_inflate::tables_ref(T), true);
+    else if (small_tables)
         rc = oge_inflate::inflate_block<1, 9, 7>(padded, in_len, out, out_len, oge_inflate::tables_ref(T), 0);
     else
         rc = oge_inflate::inflate_block<1, oge_inflate::LIT_BITS, oge_inflate::DIST_BITS>(padded, in_len, out, out_len, oge_inflate::tables_ref(T), 0);

@@ -26,7 +26,7 @@ def lib():
     return L
 
 
-SMALL = [0]      # 1: the table widths of the thread-per-block kernel (9 / 7 bits)
+SMALL = [0]      # 1: the table widths of the thread-per-block kernel (9 / 7 bits); 2: its state-machine form
 
 
 def inflate(L, z, n):
@@ -58,7 +58,7 @@ def test_tables_fit_the_shared_memory_budget(lib):
     assert lib.oge_test_inflate_tables_bytes() * 8 <= 48 * 1024      # 8 warps per CTA, static shared memory
 
 
-@pytest.mark.parametrize("small", [0, 1])
+@pytest.mark.parametrize("small", [0, 1, 2])
 def test_decoder_matches_zlib_on_every_block_type(lib, small):
     SMALL[0] = small
     n = 0
@@ -74,7 +74,14 @@ def test_decoder_matches_zlib_on_every_block_type(lib, small):
     SMALL[0] = 0
 
 
-def test_multi_block_streams_with_sync_flushes(lib):
+@pytest.mark.parametrize("small", [0, 2])
+def test_multi_block_streams_with_sync_flushes(lib, small):
+    SMALL[0] = small
+    _multi(lib)
+    SMALL[0] = 0
+
+
+def _multi(lib):
     rng = np.random.default_rng(3)
     data = bytes(rng.integers(0, 8, 40000, dtype=np.uint8))
     co = zlib.compressobj(6, zlib.DEFLATED, -15)
@@ -86,7 +93,14 @@ def test_multi_block_streams_with_sync_flushes(lib):
     assert rc == 0 and out == data
 
 
-def test_corrupt_streams_are_rejected_not_overrun(lib):
+@pytest.mark.parametrize("small", [0, 2])
+def test_corrupt_streams_are_rejected_not_overrun(lib, small):
+    SMALL[0] = small
+    _corrupt(lib)
+    SMALL[0] = 0
+
+
+def _corrupt(lib):
     rng = np.random.default_rng(4)
     data = bytes(rng.integers(0, 40, 20000, dtype=np.uint8))
     co = zlib.compressobj(6, zlib.DEFLATED, -15)
