@@ -230,6 +230,10 @@ int oge_gpu_debug_sort_bench(int device, uint64_t n, int bit_lo, int bit_hi, int
 /* Tuning hook: pass-kernel variant (0: 2048-entry tiles of 256 threads; 2: 4096-entry tiles of 512 threads, default). */
 int oge_gpu_set_sort_variant(int variant);
 
+/* Tuning hook: which BGZF inflate kernel oge_gpu_dedup_push_bgzf launches (1: one warp per block, default; 0: one thread
+ * per block, 32 streams per warp as a converged state machine).  Also settable with OGE_INFLATE_KERNEL=warp|threads. */
+int oge_gpu_set_inflate_kernel(int kernel);
+
 /* Pinned host memory for push/pull buffers. */
 void *oge_gpu_host_alloc(size_t nbytes);
 void oge_gpu_host_free(void *p);

@@ -79,13 +79,17 @@ __global__ void __launch_bounds__(INT_THREADS, 1) bgzf_inflate_threads(BgzfParam
     }
 }
 
+static int g_inflate_mode = -1;      // 0 threads, 1 warps (default); -1 = not chosen yet (OGE_INFLATE_KERNEL decides)
+
+void set_inflate_kernel(int mode) { g_inflate_mode = mode == 0 ? 0 : 1; }
+
 int launch_bgzf_inflate(const BgzfParams &P, int sms, cudaStream_t stream, uint64_t *launches) {
     if (P.n_blocks == 0) return 0;
-    static int mode = -1;      // 0 threads, 1 warps (default)
-    if (mode < 0) {
+    if (g_inflate_mode < 0) {
         const char *e = getenv("OGE_INFLATE_KERNEL");
-        mode = e && !strcmp(e, "threads") ? 0 : 1;
+        g_inflate_mode = e && !strcmp(e, "threads") ? 0 : 1;
     }
+    const int mode = g_inflate_mode;
     if (mode == 1) {
         static int per_sm = 0;      // resident CTAs per SM: one wave, blocks are taken with a grid stride
         if (!per_sm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgzf_inflate_warps, INF_WARPS * 32, 0) != cudaSuccess || per_sm < 1)) per_sm = 2;

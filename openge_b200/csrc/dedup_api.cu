@@ -1009,6 +1009,12 @@ extern "C" int oge_gpu_debug_sort_bench(int device, uint64_t n, int bit_lo, int 
     return OGE_OK;
 }
 
+extern "C" int oge_gpu_set_inflate_kernel(int kernel) {
+    if (kernel != 0 && kernel != 1) return fail_msg(OGE_ERR_INVALID_ARG, "set_inflate_kernel: 0 (thread per block) or 1 (warp per block)");
+    oge::set_inflate_kernel(kernel);
+    return OGE_OK;
+}
+
 extern "C" int oge_gpu_set_sort_variant(int variant) {
     if (variant < 0 || variant > 0xFFFFFF) return fail_msg(OGE_ERR_INVALID_ARG, "set_sort_variant: %d", variant);
     radix_sort_set_variant(variant & 0xFF);

@@ -141,6 +141,7 @@ struct BgzfParams {
     uint32_t *err;              // [2]: first inflate error code, block index
 };
 int launch_bgzf_inflate(const BgzfParams &P, int sms, cudaStream_t stream, uint64_t *launches);
+void set_inflate_kernel(int mode);      // 0: thread per block, 1: warp per block
 
 // ---- record framing on the device (frame.cu): speculative parallel chain walk + proof
 struct FrameParams {

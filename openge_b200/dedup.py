@@ -65,7 +65,7 @@ EXPORTS = ["oge_gpu_dedup_create", "oge_gpu_dedup_destroy", "oge_gpu_dedup_set_r
            "oge_gpu_dedup_reset", "oge_gpu_dedup_flagstats", "oge_gpu_dedup_get_stats", "oge_gpu_dedup_debug_ends",
            "oge_gpu_dedup_device_ptrs", "oge_gpu_host_alloc", "oge_gpu_host_free", "oge_gpu_device_count",
            "oge_gpu_last_error", "oge_gpu_abi_version", "oge_gpu_debug_sort128", "oge_gpu_debug_sort_bench",
-           "oge_gpu_set_sort_variant", "oge_gpu_shard_setup", "oge_gpu_shard_begin", "oge_gpu_shard_probe",
+           "oge_gpu_set_sort_variant", "oge_gpu_set_inflate_kernel", "oge_gpu_shard_setup", "oge_gpu_shard_begin", "oge_gpu_shard_probe",
            "oge_gpu_shard_finish", "oge_gpu_shard_apply", "oge_gpu_copy_d2d"]
 
 
@@ -114,6 +114,7 @@ def lib():
         L.oge_gpu_debug_sort_bench.argtypes = [C.c_int, u64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u64,
                                                C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.oge_gpu_set_sort_variant.argtypes = [C.c_int]
+        L.oge_gpu_set_inflate_kernel.argtypes = [C.c_int]
         L.oge_gpu_copy_d2d.argtypes = [vp, vp, vp, u64]
         L.oge_gpu_shard_setup.argtypes = [vp, u64, vp, vp, vp]
         L.oge_gpu_shard_begin.argtypes = [vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(vp), C.POINTER(u64)]
@@ -145,6 +146,11 @@ def debug_sort128(entries: np.ndarray, bit_lo: int, bit_hi: int, device: int = 0
 def set_sort_variant(variant: int):
     """Tuning hook: which onesweep pass kernel runs (see radix_sort.cuh)."""
     _check(lib().oge_gpu_set_sort_variant(variant))
+
+
+def set_inflate_kernel(kernel: str):
+    """Tuning hook: "warp" (one warp per BGZF block, default) or "threads" (one thread per block)."""
+    _check(lib().oge_gpu_set_inflate_kernel({"threads": 0, "warp": 1}[kernel]))
 
 
 def debug_sort_bench(n, bit_lo, bit_hi, variant=0, mode=0, reps=3, seed=1, device=0) -> dict:

@@ -52,10 +52,18 @@ def gpu_inflate_file(path):
     return ctx, h
 
 
+@pytest.fixture(params=["warp", "threads"])
+def inflate_kernel(request):
+    """Both device decoders: one warp per block (default) and one thread per block."""
+    dedup.set_inflate_kernel(request.param)
+    yield request.param
+    dedup.set_inflate_kernel("warp")
+
+
 @pytest.mark.parametrize("level,strategy,block", [(6, zlib.Z_DEFAULT_STRATEGY, 65536), (1, zlib.Z_DEFAULT_STRATEGY, 65280),
                                                   (9, zlib.Z_DEFAULT_STRATEGY, 30000), (0, zlib.Z_DEFAULT_STRATEGY, 65000),
                                                   (6, zlib.Z_FIXED, 40000), (6, zlib.Z_HUFFMAN_ONLY, 50000), (6, zlib.Z_RLE, 777)])
-def test_device_inflate_matches_zlib(tmp, level, strategy, block):
+def test_device_inflate_matches_zlib(tmp, inflate_kernel, level, strategy, block):
     bam = synth.make("C3", 0.02, seed=31)
     raw = bamio.serialize_bam_stream(bam)
     p = os.path.join(tmp, "x.bam")
@@ -81,7 +89,7 @@ def test_device_inflate_matches_zlib(tmp, level, strategy, block):
         assert np.array_equal(rec, want) and np.array_equal(off, bam.offsets)
 
 
-def test_device_inflate_other_writers_and_large_headers(tmp):
+def test_device_inflate_other_writers_and_large_headers(tmp, inflate_kernel):
     # python zlib at level 1 through bamio (its own block size), the host layer's writer, and a header spanning several blocks
     bam = synth.make("C1", 0.01, seed=8)
     big_text = "@HD\tVN:1.4\tSO:coordinate\n" + "".join("@SQ\tSN:contig%05d\tLN:%d\n" % (i, 1000 + i) for i in range(9000)) + "@RG\tID:rg1\tLB:lib1\n"
@@ -99,7 +107,7 @@ def test_device_inflate_other_writers_and_large_headers(tmp):
             assert np.array_equal(h.records, b.records) and np.array_equal(h.offsets, b.offsets)
 
 
-def test_device_inflate_rejects_corrupt_blocks(tmp):
+def test_device_inflate_rejects_corrupt_blocks(tmp, inflate_kernel):
     bam = synth.make("C1", 0.01, seed=9)
     z = bytearray(bamhost.bgzf_compress(bamio.serialize_bam_stream(bam), 6))
     bs0 = int.from_bytes(z[16:18], "little") + 1
