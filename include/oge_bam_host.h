@@ -26,8 +26,8 @@
  * inflated records are pinned).  Nothing here computes duplicate flags -- that is libopenge_b200.so's job.
  * Conventions as in oge_gpu_dedup.h: 0 on success, negative on failure, oge_bam_last_error() has the message
  * (the reference prints a message and exit(-1)s on every one of these conditions; the CLI maps back to that).
- * Not rebuilt: SAM/FASTQ output, stdin/stdout streams, the .bai index the reference's BAM writer emits next to a
- * coordinate-sorted output (util/bam_index.cpp).
+ * Not rebuilt: SAM/FASTQ output, stdin/stdout streams.  (No .bai either -- and none in the reference: its BAM writer
+ * collects index data for coordinate-sorted output, but BamIndex::writeFile returns before writing, util/bam_index.cpp:243.)
  */
 #ifndef OGE_BAM_HOST_H
 #define OGE_BAM_HOST_H
