@@ -53,6 +53,14 @@ def main():
             key = "%s_%g_%d_c%d%s" % (name, scale, seed, level, "_r" if remove else "")
             out[key] = np.array(hashlib.sha256(data).hexdigest())
             print(key, len(data), out[key])
+        # real data: the reference's own test file (test/data/208.yhet.bam, stored in yhet208.npz), whose header is not canonical
+        from conftest import load_golden
+        for case in ("yhet208", "edge_cases"):
+            bam, _ = load_golden(case)
+            for level in (6, 1):
+                data = ref_file(bam, level, False, d)
+                out["%s_c%d" % (case, level)] = np.array(hashlib.sha256(data).hexdigest())
+                print(case, level, len(data))
         for name, bam in fixtures.header_cases().items():
             data = ref_file(bam, 6, False, d, fmt="rawbam")
             got = bamio.parse_bam_stream(data)

@@ -121,6 +121,14 @@ def test_output_file_is_byte_identical_to_the_reference_golden(tmp, name, scale,
     assert hashlib.sha256(data).hexdigest() == str(GOLD[key])
 
 
+@pytest.mark.parametrize("case,level", [("yhet208", 6), ("yhet208", 1), ("edge_cases", 6), ("edge_cases", 1)])
+def test_real_data_output_file_is_byte_identical_to_the_reference_golden(tmp, case, level):
+    """test/data/208.yhet.bam of the reference (real reads, a header that is not in canonical form) and the edge-case records."""
+    bam, _ = load_golden(case)
+    data = host_dedup_with_oracle_flags(bam, tmp, level, threads=4)
+    assert hashlib.sha256(data).hexdigest() == str(GOLD["%s_c%d" % (case, level)])
+
+
 @pytest.mark.parametrize("case", ["reordered_fields", "regrouped_lines", "no_hd", "unterminated_last_line"])
 def test_header_is_rendered_like_the_reference(tmp, case):
     bam = fixtures.header_cases()[case]

@@ -45,6 +45,15 @@ def test_dedup_file_is_byte_identical_to_the_reference_output(tmp, name, scale, 
     assert st["dedup"]["launches"] > 0 and st["flagstats"]["reads"] == bam.n
 
 
+@pytest.mark.parametrize("case,level", [("yhet208", 6), ("edge_cases", 1)])
+def test_dedup_file_on_real_data_is_byte_identical_to_the_reference_output(tmp, case, level):
+    bam, _ = load_golden(case)
+    inp, out = os.path.join(tmp, "in.bam"), os.path.join(tmp, "out.bam")
+    bamio.write_bam(inp, bam)
+    bamhost.dedup_file(inp, out, level=level)
+    assert hashlib.sha256(open(out, "rb").read()).hexdigest() == str(GOLD["%s_c%d" % (case, level)])
+
+
 @pytest.mark.parametrize("case", ["a3_fixture1", "a3_fixture2", "edge_cases", "yhet208", "synth_C2", "synth_C5"])
 def test_fused_binary_matches_golden_flags(tmp, fused_exe, case):
     bam, g = load_golden(case)
