@@ -203,5 +203,10 @@ def header_cases():
         "no_hd": sq + "@RG\tID:rg1\tLB:libA\n@RG\tID:rg2\tLB:libB\n",
         # the last line has no newline: the reference drops it
         "unterminated_last_line": "@HD\tVN:1.4\tSO:unsorted\n" + sq + "@RG\tID:rg1\tLB:libA\n@RG\tID:rg2\tLB:libB\n@CO\tdropped",
+        # a read group listed twice (the first one wins for the library look-up), one without LB, SO:unknown, an empty @CO
+        "repeated_rg_and_no_lb": "@HD\tVN:1.5\tSO:unknown\n" + sq + "@RG\tID:rg1\tLB:libA\n@RG\tID:rg1\tLB:libZ\tSM:x\n@RG\tID:rg2\n@CO\t\n",
+        # carriage returns stay inside the last field of a line; numbers are re-printed through atoi; fields may repeat (last one wins)
+        "crlf_and_numbers": "@HD\tVN:1.4\tSO:coordinate\r\n".replace("\r", "") + "@SQ\tSN:chr1\tLN:+100000\tAS:a\tAS:b\n@SQ\tSN:chr2\tLN:100000\n"
+                            "@RG\tID:rg1\tLB:libA\tPL:x\r\n@RG\tID:rg2\tLB:libB\n@PG\tID:p1\tPN:n\n@PG\tID:p2\tPP:p1\tCL:a b c\n",
     }
     return {k: bamio.BamFile(text=t, refs=list(b1.refs), records=b1.records, offsets=b1.offsets) for k, t in texts.items()}

@@ -129,7 +129,7 @@ def test_real_data_output_file_is_byte_identical_to_the_reference_golden(tmp, ca
     assert hashlib.sha256(data).hexdigest() == str(GOLD["%s_c%d" % (case, level)])
 
 
-@pytest.mark.parametrize("case", ["reordered_fields", "regrouped_lines", "no_hd", "unterminated_last_line"])
+@pytest.mark.parametrize("case", ["reordered_fields", "regrouped_lines", "no_hd", "unterminated_last_line", "repeated_rg_and_no_lb", "crlf_and_numbers"])
 def test_header_is_rendered_like_the_reference(tmp, case):
     bam = fixtures.header_cases()[case]
     assert bamhost.header_render(bam.text) == str(GOLD["header_" + case])
@@ -215,6 +215,10 @@ def test_errors_are_reported(tmp):
     with pytest.raises(bamhost.BamHostError) as e:
         bamhost.header_render(bad)
     assert "wasn't CO RG SQ PG or HD" in str(e.value)
+    # a field shorter than "XX:" makes the reference die in substr (std::out_of_range, util/bam_header.cpp:44-46); here: an error
+    with pytest.raises(bamhost.BamHostError) as e:
+        bamhost.header_render(bam.text + "@PG\tID:p2\tCL:a b\tc\n")
+    assert "too short" in str(e.value)
     with bamhost.HostBam(_write(tmp, bam)) as h:
         with pytest.raises(ValueError):
             h.apply_flags(np.zeros(3, np.uint16))

@@ -116,3 +116,45 @@ def _corrupt(lib):
         rc, out = inflate(lib, bytes(zz), len(data))
         bad += rc != 0 or out != data
     assert bad >= 190
+
+
+def test_decoder_fuzz_against_zlib(lib):
+    """Randomised structure: runs, repeats at every distance class, literals of varying entropy, all levels/strategies,
+    window sizes and mem levels, every decoder form.  A few thousand streams; any mismatch prints its seed."""
+    rng = np.random.default_rng(2024)
+    forms = (0, 1, 2)
+    n_cases = 0
+    for case in range(400):
+        parts = []
+        size = int(rng.integers(0, 65536))
+        while sum(len(p) for p in parts) < size:
+            kind = int(rng.integers(0, 5))
+            if kind == 0:      # literals over an alphabet of random width
+                parts.append(rng.integers(0, int(rng.integers(1, 257)), int(rng.integers(1, 4000)), dtype=np.uint8).tobytes())
+            elif kind == 1:    # a run
+                parts.append(bytes([int(rng.integers(0, 256))]) * int(rng.integers(1, 3000)))
+            elif kind == 2 and parts:      # copy from earlier output at a random distance (up to the 32 KB window and beyond)
+                prev = b"".join(parts)
+                d = int(rng.integers(1, min(len(prev), 40000) + 1))
+                l = int(rng.integers(3, 600))
+                parts.append((prev[-d:] * (l // d + 1))[:l])
+            elif kind == 3:    # geometric symbol distribution: long codes
+                p = np.array([2.0 ** -(i / float(rng.integers(2, 12))) for i in range(256)])
+                parts.append(rng.choice(256, size=int(rng.integers(1, 5000)), p=p / p.sum()).astype(np.uint8).tobytes())
+            else:              # text-like
+                words = [b"chr1", b"ACGT", b"read", b"\x00\x01\x02", b"IIIIIIII", b"RG:Z:rg1"]
+                parts.append(b"".join(words[int(x)] for x in rng.integers(0, len(words), int(rng.integers(1, 300)))))
+        data = b"".join(parts)[:65536]
+        level = int(rng.integers(0, 10))
+        strategy = [zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED][int(rng.integers(0, 5))]
+        wbits = -int(rng.integers(9, 16))
+        mem = int(rng.integers(1, 10))
+        co = zlib.compressobj(level, zlib.DEFLATED, wbits, mem, strategy)
+        z = co.compress(data) + co.flush()
+        for form in forms:
+            SMALL[0] = form
+            rc, out = inflate(lib, z, len(data))
+            assert rc == 0 and out == data, ("case", case, "form", form, len(data), level, strategy, wbits, mem, rc)
+            n_cases += 1
+    SMALL[0] = 0
+    assert n_cases == 1200
