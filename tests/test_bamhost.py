@@ -211,6 +211,19 @@ def test_errors_are_reported(tmp):
     with pytest.raises(bamhost.BamHostError) as e:
         bamhost.HostBam(p)
     assert "Invalid BAM block size(20000)" in str(e.value)
+    # a gzip member whose extra field is not the 6-byte BC subfield: rejected like the reference does
+    # (util/bgzf_input_stream.cpp:84-98: "BGZF GZ extra field is incorrect"), e.g. plain gzip output
+    import gzip
+    open(p, "wb").write(gzip.compress(bytes(raw[:1000])))
+    with pytest.raises(bamhost.BamHostError) as e:
+        bamhost.HostBam(p)
+    assert e.value.code == -2 and ("unexpected flags" in str(e.value) or "extra field" in str(e.value))
+    xl = bytearray(good)
+    xl[10:12] = (8).to_bytes(2, "little")      # XLEN = 8
+    open(p, "wb").write(bytes(xl))
+    with pytest.raises(bamhost.BamHostError) as e:
+        bamhost.HostBam(p)
+    assert "extra field is incorrect" in str(e.value)
     bad = bam.text.replace("@RG\tID:rg1", "@XX\tID:rg1")
     with pytest.raises(bamhost.BamHostError) as e:
         bamhost.header_render(bad)
