@@ -522,3 +522,70 @@ int oge_oracle_flagstats(const uint8_t *records, const uint64_t *offsets, uint64
     out[12] = (uint64_t) sorted;
     return 0;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Coordinate order: the order `openge mergesort` puts records in before MarkDuplicates
+ * (algorithms/read_sorter.cpp: runs sorted with Sort::ByPosition, merged through a multiset of the same
+ * comparator, util/read_stream_reader.h:88-106).  ByPosition (util/bamtools/Sort.h) compares refID (-1 after
+ * everything else), position, strand (forward first), name (std::string order), flag, and finally the ADDRESSES
+ * of the two objects; records with refID -1 are all equivalent.  So the reference's order is defined only up to
+ * permutations inside groups that tie on the five fields and inside the unplaced tail; this restatement breaks
+ * those ties by input order (which is what a stable sort would do) and tests compare accordingly.
+ * perm[k] = input ordinal of the record at output position k.
+ */
+typedef struct {
+    const uint8_t *p;      /* record */
+    uint32_t idx;
+} SortItem;
+
+static int by_position(const void *pa, const void *pb) {
+    const SortItem *a = (const SortItem *) pa, *b = (const SortItem *) pb;
+    const int32_t ra = rd_i32(a->p + 4), rb = rd_i32(b->p + 4);
+    if (ra == -1 || rb == -1) {
+        if (ra == -1 && rb == -1) return a->idx < b->idx ? -1 : 1;
+        return ra == -1 ? 1 : -1;
+    }
+    if (ra != rb) return ra < rb ? -1 : 1;
+    const int32_t qa = rd_i32(a->p + 8), qb = rd_i32(b->p + 8);
+    if (qa != qb) return qa < qb ? -1 : 1;
+    const uint32_t fa = rd_u16(a->p + 18), fb = rd_u16(b->p + 18);
+    if ((fa & 0x10) != (fb & 0x10)) return (fa & 0x10) ? 1 : -1;
+    {   /* names without their terminating NUL, std::string::compare */
+        const uint32_t la = a->p[12] ? a->p[12] - 1u : 0, lb = b->p[12] ? b->p[12] - 1u : 0;
+        const int c = memcmp(a->p + 36, b->p + 36, la < lb ? la : lb);
+        if (c) return c < 0 ? -1 : 1;
+        if (la != lb) return la < lb ? -1 : 1;
+    }
+    if (fa != fb) return fa < fb ? -1 : 1;
+    return a->idx < b->idx ? -1 : (a->idx > b->idx ? 1 : 0);
+}
+
+int oge_oracle_coordinate_order(const uint8_t *records, const uint64_t *offsets, uint64_t n, uint32_t *perm, uint8_t *tied) {
+    uint64_t i;
+    SortItem *it = (SortItem *) malloc((n ? n : 1) * sizeof(SortItem));
+    if (!it) return -1;
+    for (i = 0; i < n; i++) {
+        it[i].p = records + offsets[i];
+        it[i].idx = (uint32_t) i;
+    }
+    qsort(it, n, sizeof(SortItem), by_position);
+    for (i = 0; i < n; i++) perm[i] = it[i].idx;
+    if (tied) {      /* tied[k] = 1: output position k belongs to a group whose internal order the reference does not define */
+        for (i = 0; i < n; i++) {
+            int t = rd_i32(it[i].p + 4) == -1;
+            if (!t && i > 0) {
+                SortItem x = it[i - 1], y = it[i];
+                x.idx = y.idx = 0;
+                t = by_position(&x, &y) == 0;
+            }
+            if (!t && i + 1 < n) {
+                SortItem x = it[i], y = it[i + 1];
+                x.idx = y.idx = 0;
+                t = by_position(&x, &y) == 0;
+            }
+            tied[i] = (uint8_t) t;
+        }
+    }
+    free(it);
+    return 0;
+}

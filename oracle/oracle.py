@@ -38,10 +38,48 @@ def lib():
         L.oge_oracle_markdup.restype = C.c_int
         L.oge_oracle_markdup.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_char_p), C.c_void_p,
                                          C.c_int32, C.c_int16, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oge_oracle_coordinate_order.restype = C.c_int
+        L.oge_oracle_coordinate_order.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         L.oge_oracle_flagstats.restype = C.c_int
         L.oge_oracle_flagstats.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
+
+
+def coordinate_order(records: np.ndarray, offsets: np.ndarray):
+    """The order `openge mergesort` gives the records (read_sorter.cpp + Sort::ByPosition), ties and the unplaced tail in
+    input order.  -> (perm, tied): perm[k] = input ordinal at output position k; tied[k] = the reference does not define
+    the order inside the group position k belongs to."""
+    L = lib()
+    records = np.ascontiguousarray(records)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(offsets) - 1
+    perm = np.zeros(max(1, n), dtype=np.uint32)
+    tied = np.zeros(max(1, n), dtype=np.uint8)
+    if L.oge_oracle_coordinate_order(records.ctypes.data, offsets.ctypes.data, n, perm.ctypes.data, tied.ctypes.data) != 0:
+        raise RuntimeError("oracle failed")
+    return perm[:n], tied[:n].astype(bool)
+
+
+def ref_sort(bam, dedup=False, per_tempfile=200000, tmpdir=None, timeout=120):
+    """The compiled reference's ReadSorter chain (`openge mergesort [-M]`, command_mergesort.cpp:70-113) -> output BamFile."""
+    exe = _build.ensure_ref()
+    if exe is None:
+        raise RuntimeError("oracle/_ref/oge_ref_dedup not built")
+    base = tmpdir or ("/dev/shm" if os.path.isdir("/dev/shm") else None)
+    with tempfile.TemporaryDirectory(dir=base) as d:
+        inp, out = os.path.join(d, "in.rawbam"), os.path.join(d, "out.rawbam")
+        bamio.write_bam(inp, bam, raw=True)
+        cmd = [exe, "-T", d, "--sort", "-v", "-F", "rawbam", "-n", str(per_tempfile)] + ([] if dedup else ["--nodedup"]) + [inp, out]
+        for attempt in range(4):
+            try:
+                r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout)
+            except subprocess.TimeoutExpired:
+                continue
+            if r.returncode != 0:
+                raise RuntimeError("reference failed: %s" % r.stderr.decode()[-2000:])
+            return bamio.read_bam(out)
+        raise RefHang("reference did not terminate in %d s (4 attempts)" % timeout)
 
 
 FLAGSTAT_FIELDS = ("reads", "mapped", "forward", "reverse", "failed_qc", "duplicates", "paired", "proper_pair",

@@ -14,6 +14,9 @@
 //                    MemorySource -> MarkDuplicates -> CountingSink   (records in, flags out)
 //                    i.e. exactly MarkDuplicates::runInternal with host buffers on both sides.
 //                    Prints one JSON line with seconds per repetition.
+//   --sort:          (single chain only) `openge mergesort [-M]` (commands/command_mergesort.cpp:70-113): the reference's
+//                    ReadSorter (algorithms/read_sorter.cpp, coordinate order) in front; --nodedup leaves MarkDuplicates out;
+//                    -n N = alignments per temp file (default 200000 as there)
 //   --stats:         (single chain only) puts the reference's Statistics module (algorithms/statistics.cpp,
 //                    what `openge stats` runs, command_stats.cpp) between MarkDuplicates and the writer:
 //                    its report goes to stdout.
@@ -24,6 +27,7 @@
 #include "algorithms/sorted_merge.h"
 #include "algorithms/split_by_chromosome.h"
 #include "algorithms/statistics.h"
+#include "algorithms/read_sorter.h"
 #include "util/read_stream_reader.h"
 
 #include <sys/time.h>
@@ -81,7 +85,8 @@ static void usage() {
 }
 
 int main(int argc, char ** argv) {
-    bool verbose = false, nosplit = false, remove_dups = false, mem = false, stats = false;
+    bool verbose = false, nosplit = false, remove_dups = false, mem = false, stats = false, sort = false, nodedup = false;
+    int per_tempfile = 200000;
     int threads = ThreadPool::availableCores();
     int level = 6, reps = 1;
     string tmpdir = "/tmp", format, flags_out;
@@ -93,6 +98,9 @@ int main(int argc, char ** argv) {
         else if (a == "-r") remove_dups = true;
         else if (a == "--mem") mem = true;
         else if (a == "--stats") stats = true;
+        else if (a == "--sort") sort = true;
+        else if (a == "--nodedup") nodedup = true;
+        else if (a == "-n" && i + 1 < argc) per_tempfile = atoi(argv[++i]);
         else if (a == "-t" && i + 1 < argc) threads = atoi(argv[++i]);
         else if (a == "-T" && i + 1 < argc) tmpdir = argv[++i];
         else if (a == "-F" && i + 1 < argc) format = argv[++i];
@@ -144,6 +152,27 @@ int main(int argc, char ** argv) {
             }
         }
         printf("], \"duplicates\": %zu}\n", dups);
+    } else if (sort) {
+        FileReader reader;
+        ReadSorter sort_reads(tmpdir);
+        MarkDuplicates mark_duplicates(tmpdir);
+        FileWriter writer;
+        reader.addSink(&sort_reads);
+        if (!nodedup) {
+            sort_reads.addSink(&mark_duplicates);
+            mark_duplicates.addSink(&writer);
+            mark_duplicates.removeDuplicates = remove_dups;
+        } else {
+            sort_reads.addSink(&writer);
+        }
+        sort_reads.setSortBy(BamHeader::SORT_COORDINATE);
+        sort_reads.setCompressTempFiles(false);
+        sort_reads.setAlignmentsPerTempfile(per_tempfile);
+        if (!format.empty()) writer.setFormat(format);
+        reader.addFile(pos[0]);
+        writer.setFilename(pos[1]);
+        writer.setCompressionLevel(level);
+        ret = writer.runChain();
     } else if (nosplit || num_chains <= 1) {
         FileReader reader;
         MarkDuplicates mark_duplicates(tmpdir);

@@ -210,3 +210,12 @@ def header_cases():
                             "@RG\tID:rg1\tLB:libA\tPL:x\r\n@RG\tID:rg2\tLB:libB\n@PG\tID:p1\tPN:n\n@PG\tID:p2\tPP:p1\tCL:a b c\n",
     }
     return {k: bamio.BamFile(text=t, refs=list(b1.refs), records=b1.records, offsets=b1.offsets) for k, t in texts.items()}
+
+
+def shuffled(bam, seed):
+    """The same records in a seeded random order (header marked unsorted): input for the coordinate sort."""
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(bam.n)
+    recs = [bam.records[int(bam.offsets[i]):int(bam.offsets[i + 1])].tobytes() for i in perm]
+    r, o = bamio.concat_records(recs)
+    return bamio.BamFile(text=bam.text.replace("SO:coordinate", "SO:unsorted"), refs=list(bam.refs), records=r, offsets=o)

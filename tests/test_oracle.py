@@ -111,3 +111,35 @@ def test_oracle_sorted_verdict_matches_reference_statistics():
         flags = oracle.markdup(bam.records, bam.offsets, bam.text)
         got = oracle.flagstats(bam.records, bam.offsets, flags)
         assert [got[k] for k in oracle.FLAGSTAT_FIELDS] == [int(x) for x in gold["sortedness_" + name]], name
+
+
+# ---- coordinate order: the oracle restatement of ReadSorter + Sort::ByPosition against the compiled
+# reference's own sorter (tests/golden/make_sort_golden.py).  Only the positions whose order the reference defines are compared
+# in order (its comparator ends on object addresses); all records are compared as a multiset.
+@pytest.mark.parametrize("name,scale,seed", [("C3", 0.01, 5), ("C4", 0.003, 6), ("C1", 0.02, 7), ("C3", 0.004, 8)])
+def test_oracle_coordinate_order_matches_reference_sorter(name, scale, seed):
+    import os
+    import sys
+    from conftest import GOLDEN
+    from openge_b200 import synth
+    sys.path.insert(0, GOLDEN)
+    from make_sort_golden import digests
+    gold = dict(np.load(os.path.join(GOLDEN, "sort_order.npz")))
+    bam = fixtures.shuffled(synth.make(name, scale, seed=seed), seed)
+    perm, tied = oracle.coordinate_order(bam.records, bam.offsets)
+    assert sorted(perm.tolist()) == list(range(bam.n))
+    d, n_def, ms = digests(bam.records, bam.offsets, perm, tied)
+    key = "%s_%g_%d" % (name, scale, seed)
+    assert n_def == int(gold[key + "_n_defined"]) and ms == str(gold[key + "_multiset"])
+    assert d == str(gold[key + "_defined"])
+    # feeding the sorted stream to MarkDuplicates is `openge mergesort -M`: the dedup oracle runs on the oracle's order
+    o = bam.offsets.astype(np.int64)
+    recs = [bam.records[o[i]:o[i + 1]].tobytes() for i in perm]
+    from openge_b200 import bamio
+    r, off = bamio.concat_records(recs)
+    flags = oracle.markdup(r, off, bam.text)
+    want = gold[key + "_dedup_flags"]
+    assert np.array_equal(gold[key + "_tied"], tied)
+    assert np.array_equal(flags[~tied], want[~tied])
+    if not tied.any():
+        assert np.array_equal(flags, want)
