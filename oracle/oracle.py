@@ -203,6 +203,34 @@ def ref_time_mem(bam, reps=1, threads=None, tmpdir=None, timeout=900):
         return json.loads(r.stdout.decode().strip().splitlines()[-1])
 
 
+def ref_flags_mem(bam, threads=None, tmpdir=None, timeout=1800):
+    """The compiled reference's MarkDuplicates::runInternal over records preloaded in RAM (`--mem -v --flags F`):
+    -> the output flag word of every record.  No file writer behind it, so it scales to millions of records."""
+    exe = _build.ensure_ref()
+    if exe is None:
+        raise RuntimeError("oracle/_ref/oge_ref_dedup not built")
+    base = tmpdir or ("/dev/shm" if os.path.isdir("/dev/shm") else None)
+    with tempfile.TemporaryDirectory(dir=base) as d:
+        inp, out = os.path.join(d, "in.rawbam"), os.path.join(d, "flags.u16")
+        bamio.write_bam(inp, bam, raw=True)
+        cmd = [exe, "--mem", "-v", "-T", d, "--reps", "1", "--flags", out]
+        if threads:
+            cmd += ["-t", str(threads)]
+        cmd.append(inp)
+        for attempt in range(3):
+            try:
+                r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=timeout)
+            except subprocess.TimeoutExpired:
+                continue
+            if r.returncode != 0:
+                raise RuntimeError("reference failed")
+            f = np.fromfile(out, dtype=np.uint16)
+            if len(f) != bam.n:
+                raise RuntimeError("reference returned %d flag words for %d records" % (len(f), bam.n))
+            return f
+        raise RefHang("reference did not terminate in %d s (3 attempts)" % timeout)
+
+
 _STAT_LABELS = {"Total reads": "reads", "Mapped reads": "mapped", "Forward strand": "forward", "Reverse strand": "reverse",
                 "Failed QC": "failed_qc", "Duplicates": "duplicates", "Paired-end reads": "paired", "'Proper-pairs'": "proper_pair",
                 "Both pairs mapped": "both_mapped", "Read 1": "first_mate", "Read 2": "second_mate", "Singletons": "singletons",

@@ -39,3 +39,19 @@ def has_cuda():
         return torch.cuda.is_available()
     except Exception:
         return False
+
+
+LARGE_PIN_CASES = ["C1", "C2", "C3", "C4", "C5"]
+
+
+def load_large_pin(name):
+    """-> (BamFile regenerated from its seed, duplicate bit per record, sha256 of the reference's flag array):
+    the compiled reference's own run on inputs of 1-5 M records (tests/golden/make_large_golden.py)."""
+    import hashlib
+    from openge_b200 import synth
+    g = np.load(os.path.join(GOLDEN, "large_pins.npz"), allow_pickle=False)
+    bam = synth.make(name, float(g[name + "_scale"]))
+    assert bam.n == int(g[name + "_n"])
+    assert hashlib.sha256(bam.records.tobytes()).hexdigest() == str(g[name + "_records_sha256"]), "synthetic generator drifted"
+    dup = np.unpackbits(g[name + "_dupbits"])[: bam.n].astype(bool)
+    return bam, dup, str(g[name + "_flags_sha256"])

@@ -11,7 +11,7 @@ import pytest
 
 import fixtures
 import oracle
-from conftest import GOLDEN_CASES, load_golden
+from conftest import GOLDEN_CASES, LARGE_PIN_CASES, load_golden, load_large_pin
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES)
@@ -143,3 +143,14 @@ def test_oracle_coordinate_order_matches_reference_sorter(name, scale, seed):
     assert np.array_equal(flags[~tied], want[~tied])
     if not tied.any():
         assert np.array_equal(flags, want)
+
+
+@pytest.mark.parametrize("name", LARGE_PIN_CASES)
+def test_oracle_matches_reference_at_millions_of_records(name):
+    """The restatement against the compiled reference's own flags (`--mem -v --flags`) on 1-5 M-record inputs:
+    C1 at its full size, a 5 M-read C2 slice, 2 M-record C3/C4/C5 slices (tests/golden/large_pins.npz)."""
+    import hashlib
+    bam, dup, sha = load_large_pin(name)
+    got = oracle.markdup(bam.records, bam.offsets, bam.text)
+    assert np.array_equal((got & 0x400) != 0, dup)
+    assert hashlib.sha256(got.tobytes()).hexdigest() == sha
