@@ -366,7 +366,7 @@ def run_ours(args):
 
     max_len = max(l for _, l in contigs)
     ctx = dedup.DedupContext(n_ref=len(contigs), max_ref_len=max_len, device=local_rank, profile_events=True,
-                             capacity_records=n, capacity_bytes=rec.nbytes)
+                             capacity_records=n, capacity_bytes=rec.nbytes, legacy_join=args.legacy_join)
     ctx.set_header(text)
     offs_pin = dedup.PinnedBuffer(offs.nbytes)
     offs_pin.array.view(np.uint64)[:] = offs
@@ -490,6 +490,7 @@ def main():
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--legacy-join", action="store_true", help="A/B: separate end-build and whole-file hash join instead of the fused form")
     ap.add_argument("--no-bgzf", action="store_true", help="skip the extra end-to-end measurement from a BGZF-compressed BAM in host memory")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define OGE_GPU_DEDUP_ABI_VERSION 5
+#define OGE_GPU_DEDUP_ABI_VERSION 6
 
 enum {
     OGE_OK = 0,
@@ -66,7 +66,8 @@ typedef struct oge_gpu_dedup_config {
     int32_t world;
     uint64_t index_base;            /* global ordinal of this shard's first record */
     int32_t debug_full_frag_sort;   /* 1: always sort every fragment end (measurement / A-B of the reduced fragment pass) */
-    int32_t reserved;
+    int32_t debug_legacy_join;      /* 1: separate end-build and whole-file hash join (the form the range-sharded path uses) instead of
+                                       the end-build fused with the in-CTA join (measurement / A-B) */
 } oge_gpu_dedup_config;
 
 /* Per-run counters (the reference prints the analogous numbers under -v, mark_duplicates.cpp:261,433). */

@@ -1,6 +1,7 @@
 """In-tree builds of the native pieces (no JIT cache: the .so files travel with the repo).
 
   libopenge_b200.so   CUDA kernels + C-ABI   (nvcc, sm_100a)      openge_b200/csrc/
+  libopenge_b200_testing.so   the same with -DOGE_TESTING (test hooks compiled in; loaded by tests only)
   liboge_bamhost.so   host BAM streaming layer (g++, zlib; no CUDA)   openge_b200/host/bam_host.cpp
   host/_build/oge_dedup_fused   BAM file -> GPU dedup -> BAM file (g++; links both libraries)
   libogesynth.so      synthetic workloads    (gcc)                tools/synth/
@@ -73,25 +74,51 @@ class _BuildLock:
         self.f.close()
 
 
-def build_gpu(force=False, verbose=False):
+GPU_TESTING_LIB = os.path.join(ROOT, "openge_b200", "libopenge_b200_testing.so")
+
+
+def _nvcc_objects(cu, flags, objdir, verbose):
+    """One nvcc -c per .cu, all at once; -> object paths (compiler output printed when verbose)."""
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(objdir, exist_ok=True)
+    inc = ["-I", os.path.join(ROOT, "include"), "-I", CSRC]
+
+    def one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        return obj, _run(["nvcc"] + flags + inc + ["-c", src, "-o", obj])
+
+    with ThreadPoolExecutor(max_workers=min(len(cu), os.cpu_count() or 4)) as ex:
+        res = list(ex.map(one, cu))
+    if verbose:
+        for _, out in res:
+            print(out)
+    return [o for o, _ in res]
+
+
+def build_gpu(force=False, verbose=False, testing=False):
+    """libopenge_b200.so, or (testing=True) libopenge_b200_testing.so: the same sources with -DOGE_TESTING, which
+    compiles in the test hooks (forced-overflow capacities from the environment, measurement knobs of the sort) that
+    the product library does not carry."""
+    target = GPU_TESTING_LIB if testing else GPU_LIB
     srcs = gpu_sources()
     cu = [s for s in srcs if s.endswith(".cu")]
-    if force or _stale(GPU_LIB, srcs):
+    if force or _stale(target, srcs):
         if not _have("nvcc"):
-            if os.path.exists(GPU_LIB):
-                return GPU_LIB
-            raise RuntimeError("nvcc not found and %s is missing" % GPU_LIB)
-        with _BuildLock(GPU_LIB + ".lock"):
-            if force or _stale(GPU_LIB, srcs):      # somebody else may have built it while we waited
-                flags = list(NVCC_FLAGS) + os.environ.get("OGE_NVCC_EXTRA", "").split()
+            if os.path.exists(target):
+                return target
+            raise RuntimeError("nvcc not found and %s is missing" % target)
+        with _BuildLock(target + ".lock"):
+            if force or _stale(target, srcs):      # somebody else may have built it while we waited
+                flags = [f for f in NVCC_FLAGS if f != "-shared"] + os.environ.get("OGE_NVCC_EXTRA", "").split()
+                if testing:
+                    flags.append("-DOGE_TESTING=1")
                 if verbose:
                     flags += ["-Xptxas", "-v"]
-                tmp = GPU_LIB + ".tmp.%d" % os.getpid()
-                out = _run(["nvcc"] + flags + ["-I", os.path.join(ROOT, "include"), "-I", CSRC] + cu + ["-o", tmp, "-lcudart"])
-                os.replace(tmp, GPU_LIB)      # readers never see a half-written library
-                if verbose:
-                    print(out)
-    return GPU_LIB
+                objs = _nvcc_objects(cu, flags, os.path.join(CSRC, "_obj", "testing" if testing else "product"), verbose)
+                tmp = target + ".tmp.%d" % os.getpid()
+                _run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", tmp, "-lcudart"])
+                os.replace(tmp, target)      # readers never see a half-written library
+    return target
 
 
 def ensure_synth(force=False):
@@ -167,6 +194,7 @@ def build_all(verbose=False):
     ensure_oracle()
     ensure_ref()
     lib = build_gpu(verbose=verbose)
+    build_gpu(verbose=verbose, testing=True)
     ensure_bamhost()
     ensure_fused()
     ensure_host()

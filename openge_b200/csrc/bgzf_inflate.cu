@@ -91,17 +91,14 @@ int launch_bgzf_inflate(const BgzfParams &P, int sms, cudaStream_t stream, uint6
     }
     const int mode = g_inflate_mode;
     if (mode == 1) {
-        static int per_sm = 0;      // resident CTAs per SM: one wave, blocks are taken with a grid stride
-        if (!per_sm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgzf_inflate_warps, INF_WARPS * 32, 0) != cudaSuccess || per_sm < 1)) per_sm = 2;
+        int per_sm = 0;      // resident CTAs per SM: one wave, blocks are taken with a grid stride
+        if ((cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgzf_inflate_warps, INF_WARPS * 32, 0) != cudaSuccess || per_sm < 1)) per_sm = 2;
         const uint64_t want = (P.n_blocks + INF_WARPS - 1) / INF_WARPS, cap = (uint64_t) sms * per_sm;
         bgzf_inflate_warps<<<(uint32_t) (want < cap ? want : cap), INF_WARPS * 32, 0, stream>>>(P);
     } else {
         const size_t smem = (size_t) INT_THREADS * INT_HOT_U16 * sizeof(uint16_t);
-        static bool configured = false;
-        if (!configured) {
-            OGE_CUDA_TRY(cudaFuncSetAttribute(bgzf_inflate_threads, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-            configured = true;
-        }
+        // per device and per call: the attribute belongs to the current device's copy of the function
+        OGE_CUDA_TRY(cudaFuncSetAttribute(bgzf_inflate_threads, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         const uint64_t want = (P.n_blocks + INT_THREADS - 1) / INT_THREADS;
         bgzf_inflate_threads<<<(uint32_t) (want < (uint64_t) sms ? want : (uint64_t) sms), INT_THREADS, smem, stream>>>(P);
     }

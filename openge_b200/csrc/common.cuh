@@ -80,6 +80,7 @@ __host__ __device__ __forceinline__ uint32_t digit_of(const E128 &e, int shift, 
 enum : uint32_t {
     DEV_ERR_KEY_RANGE = 1u,      // refID / coordinate / library outside the configured key layout
     DEV_ERR_BAD_RECORD = 2u,     // record sections overrun block_size, or offsets disagree with block_size
+    DEV_ERR_CAPACITY = 4u,       // an output list overran its capacity (internal sizing error)
 };
 
 // ---- counters block (one u32 array per context) ----------------------------------------------
@@ -110,6 +111,7 @@ enum {
     CNT_SCRATCH0,
     CNT_SCRATCH1,
     CNT_SCRATCH2,
+    CNT_LEFT,           // fused end-build: records handed to the global join
     CNT_N = 32
 };
 

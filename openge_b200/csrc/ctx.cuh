@@ -100,7 +100,9 @@ struct oge_gpu_dedup_ctx {
     DevBuf<E128> frag, sortbuf, pair, pair2, pairf, pairf2;      // pair = near pairs, pairf = far pairs
     DevBuf<E128> ufrag, ufrag2;                                  // reduced fragment pass: the entries that can matter
     DevBuf<unsigned long long> uset;                             // keys of the unpaired ends
-    DevBuf<uint64_t> hk;
+    DevBuf<uint64_t> hk, pair_hk, pairf_hk;                      // pair_hk: key hash of the pairs formed inside the CTAs of the fused end-build
+    DevBuf<uint32_t> left;                                       // fused end-build: records handed to the global join
+    DevBuf<E128> cplx_sort;                                      // ping-pong buffer of the exact path's sort
     DevBuf<uint16_t> flag_in, flag_out;
     DevBuf<NameTag> tag;
     DevBuf<uint8_t> dup, scratch, cplx_state;

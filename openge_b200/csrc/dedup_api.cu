@@ -134,6 +134,8 @@ int check_endbuild_errors(oge_gpu_dedup_ctx *c) {
     if (c->h_counters[CNT_ERR] & DEV_ERR_KEY_RANGE)
         return fail_msg(OGE_ERR_KEY_RANGE, "run: a record's refID / unclipped coordinate / library does not fit the key layout "
                                            "(n_ref=%d max_ref_len=%d clip_margin=%d)", c->cfg.n_ref, c->cfg.max_ref_len, c->cfg.clip_margin);
+    if (c->h_counters[CNT_ERR] & DEV_ERR_CAPACITY)
+        return fail_msg(OGE_ERR_STATE, "run: internal error, a pair list overran its capacity");
     if ((c->cfg.index_base + c->n > (1ull << 32)) || c->sh.global_n > (1ull << 32))
         return fail_msg(OGE_ERR_TOO_LARGE, "run: global record ordinals must stay below 2^32");
     return 0;
@@ -234,7 +236,7 @@ void oge_gpu_dedup_destroy(oge_gpu_dedup_ctx *c) {
     c->rec.release(); c->off.release(); c->rg_bytes.release(); c->rg_off.release(); c->rg_lib.release();
     c->frag.release(); c->sortbuf.release(); c->pair.release(); c->pair2.release(); c->pairf.release(); c->pairf2.release(); c->ufrag.release(); c->ufrag2.release(); c->uset.release(); c->hk.release();
     c->tag.release(); c->flag_in.release(); c->flag_out.release(); c->dup.release(); c->scratch.release();
-    c->cplx_state.release(); c->cplx_slots.release(); c->mate_of.release(); c->counters.release(); c->table.release();
+    c->cplx_state.release(); c->cplx_slots.release(); c->cplx_sort.release(); c->pair_hk.release(); c->pairf_hk.release(); c->left.release(); c->mate_of.release(); c->counters.release(); c->table.release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->clk_ev) if (e) cudaEventDestroy(e);
@@ -555,37 +557,74 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     OGE_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, CNT_N * 4, s));
     OGE_CUDA_TRY(cudaMemsetAsync(c->dup.p, 0, n, s));
 
-    // ---- K1 end-build
+    // ---- K1 end-build (+ the in-CTA mate join in the fused form) and K2 mate join
     EndbuildParams eb;
     eb.rec = c->recs(); eb.off = c->off.p; eb.n = n; eb.idx_base = c->cfg.index_base;
     eb.frag = c->frag.p; eb.hk = c->hk.p; eb.tag = c->tag.p; eb.flag_in = c->flag_in.p;
     eb.counters = c->counters.p; eb.rg = rg_table(c); eb.kl = c->kl;
-    if ((rc = launch_endbuild(eb, (uint32_t) (c->rec_bytes / n), c->sms, s, &launches))) return rc;
+    // debug_keep_ends wants hk[] of every record; the fused kernel only writes the leftovers'
+    const bool fused = !c->cfg.debug_keep_ends && !c->cfg.debug_legacy_join;
+    uint64_t n_pairs = 0, n_far = 0, n_cplx = 0, n_retracted = 0, n_far_retracted = 0, n_left = 0, n_pe = 0;
+    JoinParams jp;
+    jp.rec = c->recs(); jp.off = c->off.p; jp.n = n; jp.idx_base = c->cfg.index_base;
+    jp.frag = c->frag.p; jp.hk = c->hk.p; jp.tag = c->tag.p;
+    jp.mate_of = c->mate_of.p; jp.cplx = c->sortbuf.p;
+    jp.counters = c->counters.p; jp.rg = rg_table(c); jp.kl = c->kl; jp.verify_names = c->cfg.verify_names;
+    jp.list = nullptr; jp.n_list = 0;
+    if (fused) {
+        const uint64_t pair_cap = n / 2 + 3ull * LJ_PAIR_BLOCK * endbuild_join_max_grid(c->sms) + 1024, far_cap = n / 2 + 1024;
+        if ((rc = c->pair.reserve(pair_cap, false, s)) || (rc = c->pair2.reserve(pair_cap, false, s)) ||
+            (rc = c->pairf.reserve(far_cap, false, s)) || (rc = c->pairf2.reserve(far_cap, false, s)) ||
+            (rc = c->pair_hk.reserve(pair_cap, false, s)) || (rc = c->pairf_hk.reserve(far_cap, false, s)) ||
+            (rc = c->left.reserve(n, false, s)))
+            return rc;
+        LocalJoinParams lj;
+        lj.pair = c->pair.p; lj.pair_far = c->pairf.p; lj.pair_hk = c->pair_hk.p; lj.pair_far_hk = c->pairf_hk.p;
+        lj.pair_cap = (uint32_t) std::min<uint64_t>(pair_cap, 0xFFFFFFFFull); lj.far_cap = (uint32_t) far_cap;
+        lj.mate_of = c->mate_of.p; lj.left = c->left.p; lj.n_buckets = 0; lj.tiles_per_cta = 0;
+        uint32_t grid = 0;
+        if ((rc = launch_endbuild_join(eb, lj, (uint32_t) (c->rec_bytes / n), c->sms, s, &launches, &grid))) return rc;
+    } else {
+        if ((rc = launch_endbuild(eb, (uint32_t) (c->rec_bytes / n), c->sms, s, &launches))) return rc;
+    }
     OGE_CUDA_TRY(cudaEventRecord(c->ev[1], s));
     OGE_CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, s));
     OGE_CUDA_TRY(cudaStreamSynchronize(s));
     if ((rc = check_endbuild_errors(c))) return rc;
-    const uint64_t n_frag = c->h_counters[CNT_FRAG], n_pe = c->h_counters[CNT_PAIR_ELIGIBLE];
+    const uint64_t n_frag = c->h_counters[CNT_FRAG];
+    n_pe = c->h_counters[CNT_PAIR_ELIGIBLE];
     c->h_counters_k1_unpaired = c->h_counters[CNT_UNPAIRED];
+    n_left = c->h_counters[CNT_LEFT];
 
-    // ---- K2 mate join
-    uint64_t n_pairs = 0, n_far = 0, n_cplx = 0, n_retracted = 0, n_far_retracted = 0;
-    if (n_pe) {
-        uint64_t n_slots = n_pe + 1024;      // two records per name: half full
+    // ---- K2 mate join: every map-eligible record (legacy form), or what the CTAs could not settle (fused form)
+    const uint64_t n_join = fused ? n_left : n_pe;
+    const uint32_t n_loc = fused ? c->h_counters[CNT_PAIRS] : 0u, n_loc_far = fused ? c->h_counters[CNT_PAIRS_FAR] : 0u;
+    if (n_join) {
+        // open addressing with linear probing: at most half full whatever the input (all-singleton names included)
+        const uint64_t n_slots = 2 * n_join + 1024;
         if ((rc = c->table.reserve(n_slots, false, s))) return rc;
-        if ((rc = c->pair.reserve(n_pe / 2 + 1024, false, s))) return rc;
-        if ((rc = c->pair2.reserve(n_pe / 2 + 1024, false, s))) return rc;
-        if ((rc = c->pairf.reserve(n_pe / 2 + 1024, false, s))) return rc;      // worst case: every pair is a far pair
-        if ((rc = c->pairf2.reserve(n_pe / 2 + 1024, false, s))) return rc;
-        if ((rc = c->cplx_slots.reserve(n_pe / 3 + 1024, false, s))) return rc;
+        if (!fused) {
+            if ((rc = c->pair.reserve(n_pe / 2 + 1024, false, s))) return rc;
+            if ((rc = c->pair2.reserve(n_pe / 2 + 1024, false, s))) return rc;
+            if ((rc = c->pairf.reserve(n_pe / 2 + 1024, false, s))) return rc;      // worst case: every pair is a far pair
+            if ((rc = c->pairf2.reserve(n_pe / 2 + 1024, false, s))) return rc;
+        } else {
+            // pairs the global join adds behind the CTAs' reservations
+            const uint64_t need = (uint64_t) n_loc + n_join / 2 + 1, need_far = (uint64_t) n_loc_far + n_join / 2 + 1;
+            if ((rc = c->pair.reserve(need, true, s)) || (rc = c->pair2.reserve(need, false, s)) ||
+                (rc = c->pairf.reserve(need_far, true, s)) || (rc = c->pairf2.reserve(need_far, false, s)))
+                return rc;
+        }
+        if ((rc = c->cplx_slots.reserve(n_join + 1024, false, s))) return rc;
         OGE_CUDA_TRY(cudaMemsetAsync(c->table.p, 0, n_slots * sizeof(MateSlot), s));
-        JoinParams jp;
-        jp.rec = c->recs(); jp.off = c->off.p; jp.n = n; jp.idx_base = c->cfg.index_base;
-        jp.frag = c->frag.p; jp.hk = c->hk.p; jp.tag = c->tag.p;
         jp.table = c->table.p; jp.n_slots = n_slots;
-        jp.pair = c->pair.p; jp.pair_far = c->pairf.p; jp.mate_of = c->mate_of.p; jp.cplx = c->sortbuf.p; jp.cplx_slots = c->cplx_slots.p;
-        jp.counters = c->counters.p; jp.rg = rg_table(c); jp.kl = c->kl; jp.verify_names = c->cfg.verify_names;
+        jp.pair = c->pair.p; jp.pair_far = c->pairf.p; jp.cplx_slots = c->cplx_slots.p;
+        if (fused) { jp.list = c->left.p; jp.n_list = (uint32_t) n_left; }
         if ((rc = launch_mate_join(jp, s, &launches))) return rc;
+        if (fused) {
+            if ((rc = launch_pair_check(jp, c->pair_hk.p, n_loc, false, s, &launches))) return rc;
+            if ((rc = launch_pair_check(jp, c->pairf_hk.p, n_loc_far, true, s, &launches))) return rc;
+        }
         OGE_CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, s));
         OGE_CUDA_TRY(cudaStreamSynchronize(s));
         if (c->h_counters[CNT_COMPLEX]) {
@@ -594,8 +633,6 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
             OGE_CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, s));
             OGE_CUDA_TRY(cudaStreamSynchronize(s));
             n_cplx = c->h_counters[CNT_COMPLEX];
-            n_retracted = c->h_counters[CNT_PAIRS_RETRACTED];
-            n_far_retracted = c->h_counters[CNT_FAR_RETRACTED];
             const uint64_t need = c->h_counters[CNT_PAIRS] + n_cplx / 2 + 1, need_far = c->h_counters[CNT_PAIRS_FAR] + n_cplx / 2 + 1;
             if ((rc = c->pair.reserve(need, true, s))) return rc;
             if ((rc = c->pair2.reserve(need, false, s))) return rc;
@@ -603,20 +640,21 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
             if ((rc = c->pairf2.reserve(need_far, false, s))) return rc;
             jp.pair = c->pair.p;
             jp.pair_far = c->pairf.p;
-            // sort (hash, ordinal), replay the toggle map per hash value.  The mate table is dead by
-            // now and at least as large as the list: it is the ping-pong buffer.
+            // sort (hash, ordinal), replay the toggle map per hash value
             E128 *sorted = nullptr;
-            if ((rc = radix_sort_128(c->sortbuf.p, reinterpret_cast<E128 *>(c->table.p), n_cplx, nullptr, 0, 96, c->scratch.p, s,
-                                     &sorted, &launches)))
+            if ((rc = c->cplx_sort.reserve(n_cplx, false, s))) return rc;
+            if ((rc = radix_sort_128(c->sortbuf.p, c->cplx_sort.p, n_cplx, nullptr, 0, 96, c->scratch.p, s, &sorted, &launches)))
                 return rc;
             if ((rc = c->cplx_state.reserve(n_cplx, false, s))) return rc;
             if ((rc = launch_mate_complex(jp, sorted, (uint32_t) n_cplx, c->cplx_state.p, s, &launches))) return rc;
             OGE_CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, s));
             OGE_CUDA_TRY(cudaStreamSynchronize(s));
         }
-        n_pairs = c->h_counters[CNT_PAIRS];
-        n_far = c->h_counters[CNT_PAIRS_FAR];
     }
+    n_pairs = c->h_counters[CNT_PAIRS];
+    n_far = c->h_counters[CNT_PAIRS_FAR];
+    n_retracted = c->h_counters[CNT_PAIRS_RETRACTED];      // fused form: includes the reserved positions the CTAs did not use
+    n_far_retracted = c->h_counters[CNT_FAR_RETRACTED];
     OGE_CUDA_TRY(cudaEventRecord(c->ev[2], s));
 
     // ---- K3 + K4 on the pairs
@@ -662,7 +700,9 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     else if (n_unp <= n_frag / 16 && c->kl.f_end - c->kl.f_orient <= 63) frag_mode = 1;
     if (frag_mode == 1) {
         uint64_t ucap = std::max<uint64_t>(n_frag / 4, 4 * n_unp) + 1024;
+#ifdef OGE_TESTING
         if (const char *e = getenv("OGE_UFRAG_CAP")) ucap = std::max<uint64_t>(1, (uint64_t) atoll(e));      // test hook: force the fallback
+#endif
         uint64_t n_slots = 1024;
         while (n_slots < 4 * n_unp) n_slots <<= 1;
         if ((rc = c->ufrag.reserve(ucap, false, s))) return rc;
@@ -706,10 +746,12 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     if (c->cfg.debug_keep_ends && frag_mode == 2 && sorted_frags != c->frag.p && n_frag)
         OGE_CUDA_TRY(cudaMemcpy(c->frag.p, sorted_frags, n * sizeof(E128), cudaMemcpyDeviceToDevice));
 
+#ifdef OGE_TESTING
     if (getenv("OGE_DEBUG_COUNTERS"))
         fprintf(stderr, "[oge] n=%llu frag=%llu pe=%llu near=%llu far=%llu cplx=%llu retracted=%llu/%llu\n", (unsigned long long) n,
                 (unsigned long long) n_frag, (unsigned long long) n_pe, (unsigned long long) n_pairs, (unsigned long long) n_far,
                 (unsigned long long) n_cplx, (unsigned long long) n_retracted, (unsigned long long) n_far_retracted);
+#endif
     oge_gpu_dedup_stats &st = c->stats;
     st.n_frag_entries = n_frag;
     st.n_pair_entries = n_pairs - n_retracted + n_far - n_far_retracted;
@@ -1017,6 +1059,11 @@ extern "C" int oge_gpu_set_inflate_kernel(int kernel) {
 
 extern "C" int oge_gpu_set_sort_variant(int variant) {
     if (variant < 0 || variant > 0xFFFFFF) return fail_msg(OGE_ERR_INVALID_ARG, "set_sort_variant: %d", variant);
+#ifndef OGE_TESTING
+    // the product library only selects between its two (equally correct) pass kernels; the measurement knobs in
+    // bits 4-7 exist in the -DOGE_TESTING build alone
+    if ((variant & 0xFF) != 0 && (variant & 0xFF) != 2) return fail_msg(OGE_ERR_INVALID_ARG, "set_sort_variant: 0 or 2 (+ prefetch distance << 8)");
+#endif
     radix_sort_set_variant(variant & 0xFF);
     radix_sort_set_prefetch(variant >> 8);
     return OGE_OK;

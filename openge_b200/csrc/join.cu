@@ -110,13 +110,6 @@ __device__ int find_rg_global(const uint8_t *tags, uint32_t n, uint32_t *len) {
     return -1;
 }
 
-// unaligned little-endian 32-bit read from global memory: two aligned words + funnel shift
-__device__ __forceinline__ uint32_t ldg_u32_unaligned(const uint8_t *p) {
-    const uintptr_t a = (uintptr_t) p, wa = a & ~(uintptr_t) 3;
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(wa);
-    return __funnelshift_r(w[0], w[1], (uint32_t) (a & 3) * 8);
-}
-
 // name bytes from NAME_TAG_BYTES on (the part the tags do not cover) of records a and b equal?
 // l_name is known equal.  Reads past the name stay inside the record buffer (cigar/bases/quals follow).
 __device__ bool name_tails_equal(const uint8_t *pa, const uint8_t *pb, uint32_t l_name) {
@@ -131,18 +124,22 @@ __device__ bool name_tails_equal(const uint8_t *pa, const uint8_t *pb, uint32_t 
 
 // ITEMS records per thread, staged so that the dependent chain hash -> slot -> counter -> tags -> ends
 // of one record overlaps with the others': the kernel is bound by memory latency, not bandwidth.
-template <int ITEMS>
+// LIST: the records to join are P.list[0 .. n_list) (what the fused end-build could not settle inside its CTAs).
+template <int ITEMS, bool LIST>
 __global__ void __launch_bounds__(JOIN_THREADS, ITEMS == 1 ? 8 : 4) mate_join_kernel(JoinParams P) {
     const uint64_t i0 = (uint64_t) blockIdx.x * (JOIN_THREADS * ITEMS) + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1;
 
     uint64_t h[ITEMS], s[ITEMS];
+    uint32_t rec_i[ITEMS];
     unsigned long long key0[ITEMS], old[ITEMS];
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) {
-        const uint64_t i = i0 + (uint64_t) k * JOIN_THREADS;
-        h[k] = i < P.n ? P.hk[i] : 0;
+        const uint64_t j = i0 + (uint64_t) k * JOIN_THREADS;
+        const bool valid = j < (LIST ? (uint64_t) P.n_list : P.n);
+        rec_i[k] = valid ? (LIST ? P.list[j] : (uint32_t) j) : 0u;
+        h[k] = valid ? P.hk[rec_i[k]] : 0;
     }
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) {      // first probe of every record in flight together
@@ -154,7 +151,7 @@ __global__ void __launch_bounds__(JOIN_THREADS, ITEMS == 1 ? 8 : 4) mate_join_ke
     for (int k = 0; k < ITEMS; k++) {      // claim or find the key's slot and count this arrival
         old[k] = 0;
         if (!h[k]) continue;
-        const unsigned long long inc = (1ull << 32) + (uint32_t) (i0 + (uint64_t) k * JOIN_THREADS) + 1u;
+        const unsigned long long inc = (1ull << 32) + rec_i[k] + 1u;
         unsigned long long key = key0[k];
         while (true) {
             if (key == 0) {
@@ -182,7 +179,7 @@ __global__ void __launch_bounds__(JOIN_THREADS, ITEMS == 1 ? 8 : 4) mate_join_ke
 
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) {
-        const uint64_t i = i0 + (uint64_t) k * JOIN_THREADS;
+        const uint64_t i = rec_i[k];
         bool emit = false, far = false, cplx_self = false, cplx_other = false, list_slot = false;
         uint32_t other = 0, i1 = 0, i2 = 0;
         E128 ent;
@@ -334,17 +331,63 @@ __global__ void __launch_bounds__(JOIN_THREADS) mate_complex_kernel(JoinParams P
 }
 
 int launch_mate_join(const JoinParams &P, cudaStream_t stream, uint64_t *launches) {
-    if (P.n == 0) return 0;
-    static int items = -1;
-    if (items < 0) {
-        const char *e = getenv("OGE_JOIN_ITEMS");
-        items = e && *e ? atoi(e) : 1;
+    const uint64_t count = P.list ? (uint64_t) P.n_list : P.n;
+    if (count == 0) return 0;
+    // one record per thread: two and four were measured and do not help
+    const uint32_t grid = (uint32_t) ((count + JOIN_THREADS - 1) / JOIN_THREADS);
+    if (P.list) mate_join_kernel<1, true><<<grid, JOIN_THREADS, 0, stream>>>(P);
+    else mate_join_kernel<1, false><<<grid, JOIN_THREADS, 0, stream>>>(P);
+    *launches += 1;
+    OGE_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ---- fused form: the check pass -----------------------------------------------------------------
+// A pair formed inside a CTA of the fused end-build is final iff no other record of its key exists
+// among the leftovers, i.e. iff its hash is not in the mate table the global join has just built.
+// A hit retracts the pair (all-ones entry: sorts behind every key; counted) and sends its two records
+// to the exact path, together with whatever the slot held: a lone record (arrivals == 1: pushed here),
+// a couple (arrivals == 2: the slot is listed for mate_fixup, which retracts their pair and pushes
+// them), or a name the join itself found complex (arrivals >= 3: already there).  Every hit adds two
+// to the slot's arrival count, so that exactly one visitor does that.
+__global__ void __launch_bounds__(JOIN_THREADS) pair_check_kernel(JoinParams P, const uint64_t *__restrict__ pair_hk, uint32_t n_pairs,
+                                                                  int far) {
+    const uint32_t pos = blockIdx.x * JOIN_THREADS + threadIdx.x;
+    if (pos >= n_pairs) return;
+    const uint64_t h = pair_hk[pos];
+    if (!h) return;
+    uint64_t s = slot_of(h, P.n_slots);
+    while (true) {
+        unsigned long long key;
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(key) : "l"(&P.table[s].key) : "memory");
+        if (key == 0) return;      // no leftover of this name: the pair stands
+        if (key == h) break;
+        if (++s == P.n_slots) s = 0;
     }
-    const uint64_t per_cta = (uint64_t) JOIN_THREADS * (items == 4 ? 4 : items == 1 ? 1 : 2);
-    const uint32_t grid = (uint32_t) ((P.n + per_cta - 1) / per_cta);
-    if (items == 4) mate_join_kernel<4><<<grid, JOIN_THREADS, 0, stream>>>(P);
-    else if (items == 1) mate_join_kernel<1><<<grid, JOIN_THREADS, 0, stream>>>(P);
-    else mate_join_kernel<2><<<grid, JOIN_THREADS, 0, stream>>>(P);
+    const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long *>(&P.table[s].val), 2ull << 32);
+    const uint32_t arrivals = (uint32_t) (old >> 32);
+    E128 *list = far ? P.pair_far : P.pair;
+    const E128 ent = ld_frag(list + pos);
+    const uint32_t i1 = (uint32_t) (bits_get(ent, P.kl.p_idx, P.kl.idx_bits) - P.idx_base);
+    const uint32_t i2 = (uint32_t) (P.mate_of[i1] - P.idx_base);
+    reinterpret_cast<ulonglong2 *>(list)[pos] = make_ulonglong2(~0ull, ~0ull);
+    atomicAdd(&P.counters[far ? CNT_FAR_RETRACTED : CNT_PAIRS_RETRACTED], 1u);
+    const uint32_t extra = arrivals == 1 ? 1u : 0u;
+    uint32_t base = atomicAdd(&P.counters[CNT_COMPLEX], 2u + extra);
+    E128 c = complex_entry(h, i1);
+    reinterpret_cast<ulonglong2 *>(P.cplx)[base++] = make_ulonglong2(c.lo, c.hi);
+    c = complex_entry(h, i2);
+    reinterpret_cast<ulonglong2 *>(P.cplx)[base++] = make_ulonglong2(c.lo, c.hi);
+    if (extra) {
+        c = complex_entry(h, (uint32_t) old - 1u);
+        reinterpret_cast<ulonglong2 *>(P.cplx)[base] = make_ulonglong2(c.lo, c.hi);
+    }
+    if (arrivals == 2) P.cplx_slots[atomicAdd(&P.counters[CNT_COMPLEX_SLOTS], 1u)] = (uint32_t) s;
+}
+
+int launch_pair_check(const JoinParams &P, const uint64_t *pair_hk, uint32_t n_pairs, bool far, cudaStream_t stream, uint64_t *launches) {
+    if (n_pairs == 0) return 0;
+    pair_check_kernel<<<(n_pairs + JOIN_THREADS - 1) / JOIN_THREADS, JOIN_THREADS, 0, stream>>>(P, pair_hk, n_pairs, far ? 1 : 0);
     *launches += 1;
     OGE_CUDA_TRY(cudaGetLastError());
     return 0;

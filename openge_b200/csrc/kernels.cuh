@@ -48,6 +48,35 @@ struct EndbuildParams {
 
 int launch_endbuild(const EndbuildParams &P, uint32_t avg_rec_bytes, int sms, cudaStream_t stream, uint64_t *launches);
 
+// ---- K1 with the in-CTA mate join (endbuild.cu, fused form) ---------------
+// A coordinate-sorted file keeps the two reads of a pair a few (to a few hundred) records apart, so a
+// CTA that walks a CONTIGUOUS range of tiles can pair them in a small shared-memory table while the
+// records are on the SM anyway: no hash/tag arrays, no global table sector per record.  What the
+// CTA cannot settle (mate in another CTA's range or further than LJ_HORIZON records away, table
+// overflow, a name seen three times at once) is handed to the global join (join.cu) as a list of
+// record ordinals; a pair formed here is final iff its key hash is not among those leftovers,
+// which the check pass of join.cu establishes.
+constexpr int LJ_WAYS = 8;                   // ways per bucket of the in-CTA table
+constexpr int LJ_ENTRY_BYTES = 4 + 24;       // key word + payload
+constexpr uint32_t LJ_PAIR_BLOCK = 256;      // pair-list positions a CTA reserves at a time (>= 2 * EB_THREADS)
+constexpr uint32_t LJ_HORIZON = 4096;        // an entry unmatched for this many records leaves for the global join
+constexpr uint32_t LJ_SWEEP_TILES = 8;       // how often the table is swept for such entries
+
+struct LocalJoinParams {
+    E128 *pair, *pair_far;              // pair lists (counters[CNT_PAIRS], counters[CNT_PAIRS_FAR])
+    uint64_t *pair_hk, *pair_far_hk;    // key hash of every pair entry, by list position (0 = no entry)
+    uint32_t pair_cap, far_cap;
+    uint32_t *mate_of;                  // [n] GLOBAL ordinal of the pair's other record, indexed by idx1's local ordinal
+    uint32_t *left;                     // [n] local ordinals handed to the global join (counters[CNT_LEFT])
+    uint32_t n_buckets;                 // per CTA
+    uint32_t tiles_per_cta;
+};
+
+// hk[] and tag[] of P are written only for the records on the `left` list.
+int launch_endbuild_join(const EndbuildParams &P, LocalJoinParams J, uint32_t avg_rec_bytes, int sms, cudaStream_t stream,
+                         uint64_t *launches, uint32_t *grid_out);
+uint32_t endbuild_join_max_grid(int sms);
+
 // ---- K2 mate join (join.cu) -------------------------------------------------------------------
 struct __align__(32) MateSlot {      // one 32-byte sector
     uint64_t key;       // 64-bit hash of RG + ":" + name; 0 = empty
@@ -72,6 +101,8 @@ struct JoinParams {
     uint32_t *mate_of;      // [n] GLOBAL ordinal of the pair's other record, indexed by idx1's local ordinal
     E128 *cplx;             // output: (hash << 32 | local ordinal) of records for the exact path
     uint32_t *cplx_slots;   // output: slots that saw a third arrival (counters[CNT_COMPLEX_SLOTS])
+    const uint32_t *list = nullptr;   // when not null: the records to join are list[0 .. n_list) (local ordinals), not 0 .. n
+    uint32_t n_list = 0;
     uint32_t *counters;
     RgTable rg;
     KeyLayout kl;
@@ -79,6 +110,9 @@ struct JoinParams {
 };
 
 int launch_mate_join(const JoinParams &P, cudaStream_t stream, uint64_t *launches);
+// fused form: is the key hash of a pair formed inside a CTA among the records the global join has seen?  Then the pair
+// is retracted and its two records (with whatever the slot held) go to the exact path.
+int launch_pair_check(const JoinParams &P, const uint64_t *pair_hk, uint32_t n_pairs, bool far, cudaStream_t stream, uint64_t *launches);
 int launch_mate_fixup(const JoinParams &P, uint32_t n_slots_listed, cudaStream_t stream, uint64_t *launches);
 // exact path over the sorted complex list (sorted by hash then ordinal); state = n_cplx bytes of scratch
 int launch_mate_complex(const JoinParams &P, const E128 *sorted_cplx, uint32_t n_cplx, uint8_t *state, cudaStream_t stream,

@@ -52,6 +52,46 @@ __device__ __forceinline__ E128 ld_frag(const E128 *p) {
     return e;
 }
 
+// unaligned little-endian 32-bit read from global memory: two aligned words + funnel shift
+__device__ __forceinline__ uint32_t ldg_u32_unaligned(const uint8_t *p) {
+    const uintptr_t a = (uintptr_t) p, wa = a & ~(uintptr_t) 3;
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(wa);
+    return __funnelshift_r(w[0], w[1], (uint32_t) (a & 3) * 8);
+}
+
+// n bytes at a and at b equal?  (global memory; reads past the n bytes stay inside the record buffer and are masked)
+__device__ __forceinline__ bool bytes_equal_global(const uint8_t *a, const uint8_t *b, uint32_t n) {
+    uint32_t j = 0;
+    for (; j + 4 <= n; j += 4)
+        if (ldg_u32_unaligned(a + j) != ldg_u32_unaligned(b + j)) return false;
+    if (j < n) {
+        const uint32_t m = (1u << (8 * (n - j))) - 1;
+        if ((ldg_u32_unaligned(a + j) ^ ldg_u32_unaligned(b + j)) & m) return false;
+    }
+    return true;
+}
+
+// the pairing-key tag of a record (kernels.cuh: NameTag), rebuilt from the record in global memory
+__device__ __forceinline__ void make_tag_global(const uint8_t *rec, uint32_t rgc, uint32_t l_name, NameTag *out) {
+    const uint32_t nlen = l_name ? l_name - 1 : 0;
+    uint32_t w[8];
+    w[0] = rgc | (l_name << 16) | (nlen ? ((uint32_t) rec[36] << 24) : 0u);
+#pragma unroll
+    for (int k = 1; k < 8; k++) {
+        const uint32_t first = 4 * k - 3;      // name bytes [first, first + 4)
+        uint32_t v = 0;
+        if (first < nlen) {
+            v = ldg_u32_unaligned(rec + 36 + first);
+            const uint32_t have = nlen - first;
+            if (have < 4) v &= (1u << (8 * have)) - 1;
+        }
+        w[k] = v;
+    }
+    uint4 *t = reinterpret_cast<uint4 *>(out);
+    t[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    t[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
 __device__ __forceinline__ E128 complex_entry(uint64_t h, uint32_t ordinal) {
     E128 e;
     e.lo = (h << 32) | ordinal;

@@ -431,8 +431,12 @@ int radix_sort_128(E128 *a, E128 *b, uint64_t n, const uint32_t *n_dev, int bit_
     *launches += 2;
 
     E128 *src = a, *dst = b;
-    // dbg bits 0-2 are measurement knobs (bits 0, 1 give wrong results); bits 8.. = prefetch distance in tiles
+    // dbg bits 0-2 are measurement knobs (bits 0, 1 give wrong results: -DOGE_TESTING builds only); bits 8.. = prefetch distance in tiles
+#ifdef OGE_TESTING
     int dbg = (g_sort_variant >> 4) & 15;
+#else
+    int dbg = 0;
+#endif
     const int variant = g_sort_variant & 2;
     const uint64_t vtiles = variant ? (n + PassCfg<512>::TILE - 1) / PassCfg<512>::TILE : tiles;
     {

@@ -295,11 +295,8 @@ __global__ void __launch_bounds__(SEL_THREADS, SEL_ITEMS == 8 ? 3 : 5) select_ke
 template <int KIND>
 static int launch_select(const SelectParams &P, cudaStream_t stream, uint64_t *launches) {
     if (P.n_max == 0) return 0;
-    static bool configured = false;
-    if (!configured) {
-        OGE_CUDA_TRY(cudaFuncSetAttribute(select_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SEL_SMEM));
-        configured = true;
-    }
+    // per device and per call: the attribute belongs to the current device's copy of the function
+    OGE_CUDA_TRY(cudaFuncSetAttribute(select_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SEL_SMEM));
     const uint32_t grid = (P.n_max + SEL_TILE - 1) / SEL_TILE;
     select_kernel<KIND><<<grid, SEL_THREADS, SEL_SMEM, stream>>>(P);
     *launches += 1;

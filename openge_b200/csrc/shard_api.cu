@@ -134,7 +134,11 @@ static int route_sweep(oge_gpu_dedup_ctx *c, int n_lists, E128 *const *lists, co
     uint64_t total = 0;
     for (int i = 0; i < n_lists; i++) total += counts[i];
     {
+#ifdef OGE_TESTING
         const char *e = getenv("OGE_ROUTE_CAP");      // test hook: force the second sweep
+#else
+        const char *e = nullptr;
+#endif
         const uint64_t want = e && *e ? (uint64_t) atoll(e) : std::max<uint64_t>(1u << 16, total / 64);
         if (e && *e) sh.route.release();
         if ((rc = sh.route.reserve(std::max<uint64_t>(want, 1), false, s))) return rc;
@@ -225,7 +229,7 @@ int oge_gpu_shard_begin(oge_gpu_dedup_ctx *c, void **pub_dev, uint64_t *n_pub, v
     if (sh.n_pe) {
         PhaseClock clk(c, &c->stats.ms_join);
         const uint64_t n_pe = sh.n_pe;
-        sh.n_slots = n_pe + 1024;
+        sh.n_slots = 2 * n_pe + 1024;      // at most half full whatever the input (mates of most names may sit on other ranks)
         if ((rc = c->table.reserve(sh.n_slots, false, s))) return rc;
         if ((rc = c->pair.reserve(n_pe / 2 + 1024, false, s))) return rc;
         if ((rc = c->pair2.reserve(n_pe / 2 + 1024, false, s))) return rc;
@@ -326,7 +330,9 @@ int oge_gpu_shard_probe(oge_gpu_dedup_ctx *c, const void *pub_all_dev, uint64_t 
         // room for the unpaired ends and the paired ends sharing their keys; with no local unpaired end only the
         // few routed copies can matter, and small capacities keep the (mostly empty) launches of the sort small
         sh.ucap = (sh.n_unpaired ? std::max<uint64_t>(sh.n_frag / 4, 4 * sh.n_unpaired) : 0) + 64 * n_fr_all + 1024;
+#ifdef OGE_TESTING
         if (const char *e = getenv("OGE_UFRAG_CAP")) sh.ucap = std::max<uint64_t>(1, (uint64_t) atoll(e));      // test hook: force the fallback
+#endif
         if ((rc = c->frag.reserve(n_all_frag, true, s))) return rc;
         if (sh.frag_mode == 2) {
             if ((rc = c->sortbuf.reserve(n_all_frag, false, s))) return rc;

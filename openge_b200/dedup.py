@@ -19,7 +19,7 @@ import numpy as np
 from . import _build, header as _header
 from .bamio import BamFile
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 OGE_OK = 0
 ERRORS = {-1: "OGE_ERR_INVALID_ARG", -2: "OGE_ERR_CUDA", -3: "OGE_ERR_NOMEM", -4: "OGE_ERR_KEY_RANGE",
@@ -32,7 +32,7 @@ class Config(C.Structure):
                 ("compat_quiet_index_bug", C.c_int32), ("debug_keep_ends", C.c_int32), ("profile_events", C.c_int32),
                 ("capacity_records", C.c_uint64), ("capacity_bytes", C.c_uint64),
                 ("rank", C.c_int32), ("world", C.c_int32), ("index_base", C.c_uint64),
-                ("debug_full_frag_sort", C.c_int32), ("reserved", C.c_int32)]
+                ("debug_full_frag_sort", C.c_int32), ("debug_legacy_join", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -76,15 +76,42 @@ class DedupError(RuntimeError):
 
 
 _lib = None
+_testing_lib = None
+_use_testing = False
+
+
+class testing_library:
+    """Tests only: inside the `with` block every call goes to libopenge_b200_testing.so, the same sources compiled
+    with -DOGE_TESTING (forced-overflow capacities read from the environment, measurement knobs of the sort).  The
+    product library carries none of these hooks.  Contexts must be created and closed inside the block."""
+
+    def __enter__(self):
+        global _use_testing
+        self._prev, _use_testing = _use_testing, True
+        lib()
+        return self
+
+    def __exit__(self, *a):
+        global _use_testing
+        _use_testing = self._prev
 
 
 def lib():
     """Load (building if a compiler is present and sources are newer) the CUDA library."""
-    global _lib
+    global _lib, _testing_lib
+    if _use_testing:
+        if _testing_lib is None:
+            _testing_lib = _load(_build.build_gpu(testing=True))
+        return _testing_lib
     if _lib is None:
-        path = _build.build_gpu()
+        _lib = _load(_build.build_gpu())
+    return _lib
+
+
+def _load(path):
+    if True:
         if not os.path.exists(path):
-            raise ImportError("libopenge_b200.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+            raise ImportError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'`" % os.path.basename(path))
         L = C.CDLL(path)
         vp, u64 = C.c_void_p, C.c_uint64
         L.oge_gpu_dedup_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
@@ -123,8 +150,7 @@ def lib():
         L.oge_gpu_shard_apply.argtypes = [vp, vp, u64]
         for name in EXPORTS:
             getattr(L, name)
-        _lib = L
-    return _lib
+    return L
 
 
 def _check(rc):
@@ -192,13 +218,13 @@ class DedupContext:
 
     def __init__(self, n_ref=0, max_ref_len=0, device=0, remove_duplicates=False, verify_names=True,
                  compat_quiet_index_bug=False, debug_keep_ends=False, clip_margin=0, capacity_records=0,
-                 capacity_bytes=0, index_base=0, rank=0, world=1, profile_events=False, full_frag_sort=False):
+                 capacity_bytes=0, index_base=0, rank=0, world=1, profile_events=False, full_frag_sort=False, legacy_join=False):
         self._h = C.c_void_p()
         cfg = Config(abi_version=ABI_VERSION, device=device, n_ref=n_ref, max_ref_len=max_ref_len, clip_margin=clip_margin,
                      remove_duplicates=int(remove_duplicates), verify_names=int(verify_names),
                      compat_quiet_index_bug=int(compat_quiet_index_bug), debug_keep_ends=int(debug_keep_ends),
                      profile_events=int(profile_events), capacity_records=capacity_records, capacity_bytes=capacity_bytes, rank=rank, world=world,
-                     index_base=index_base, debug_full_frag_sort=int(full_frag_sort))
+                     index_base=index_base, debug_full_frag_sort=int(full_frag_sort), debug_legacy_join=int(legacy_join))
         _check(lib().oge_gpu_dedup_create(C.byref(cfg), C.byref(self._h)))
         self.n = 0
         self.nbytes = 0

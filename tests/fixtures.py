@@ -219,3 +219,50 @@ def shuffled(bam, seed):
     recs = [bam.records[int(bam.offsets[i]):int(bam.offsets[i + 1])].tobytes() for i in perm]
     r, o = bamio.concat_records(recs)
     return bamio.BamFile(text=bam.text.replace("SO:coordinate", "SO:unsorted"), refs=list(bam.refs), records=r, offsets=o)
+
+
+def name_soup(n=60000, seed=7, pool_div=2.5, n_pos=400, long_names=True, span=2_000_000):
+    """Adversarial input for the mate join: names drawn from a small pool, so that a name is seen one to eight times
+    anywhere in the file (the reference's map pairs its sightings (1,2), (3,4), ... in FILE order,
+    util/picard_structures.h:87-96 + mark_duplicates.cpp:209-246), mates far apart, few distinct positions (long
+    duplicate runs), several read groups incl. one the header does not list and reads without RG, names longer than the
+    29 bytes a name tag holds that differ only behind them, single-end and mate-unmapped reads in between.  Sorted by
+    coordinate; ties keep generation order."""
+    rng = np.random.default_rng(seed)
+    text = ("@HD\tVN:1.4\tSO:coordinate\n@SQ\tSN:chr1\tLN:%d\n@SQ\tSN:chr2\tLN:%d\n"
+            "@RG\tID:rg1\tLB:libA\tSM:s\n@RG\tID:rg2\tLB:libB\tSM:s\n@RG\tID:rg3\tLB:libA\tSM:s\n" % (span + 10000, span + 10000))
+    n_names = max(1, int(n / pool_div))
+    positions = np.sort(rng.integers(1, span, size=n_pos))
+    rows = []
+    flags = [99, 147, 83, 163, 65, 129, 97, 145, 73, 0, 16, 1, 1024 | 99]
+    rgs = ["rg1", "rg1", "rg1", "rg2", "rg3", "rgX", "rgY", None]
+    stem = "instrument:run:flowcell:lane:tile:"          # 34 bytes: longer than a name tag
+    for i in range(n):
+        k = int(rng.integers(0, n_names))
+        name = (stem + "%07d" % k) if (long_names and k % 3 == 0) else "q%d" % k
+        flag = flags[int(rng.integers(0, len(flags)))]
+        ref = int(rng.integers(0, 2))
+        pos = int(positions[int(rng.integers(0, n_pos))])
+        mref = ref if rng.random() < 0.8 else 1 - ref
+        mpos = int(positions[int(rng.integers(0, n_pos))])
+        l = int(rng.integers(20, 37))
+        clip = int(rng.integers(0, 4))
+        cigar = ("%dS%dM" % (clip, l - clip)) if clip else "%dM" % l
+        q = int(rng.integers(10, 41))
+        rg = rgs[k % len(rgs)] if rng.random() < 0.97 else rgs[int(rng.integers(0, len(rgs)))]
+        rows.append((ref, pos, i, name, flag, cigar, mref, mpos, l, q, rg))
+    rows.sort(key=lambda t: (t[0], t[1], t[2]))
+    recs = [_rec(nm, f, r, p, c, mr, mp, q, rg, seq=("ACGT" * 10)[:l]) for r, p, _, nm, f, c, mr, mp, l, q, rg in rows]
+    records, offsets = bamio.concat_records(recs)
+    return bamio.BamFile(text=text, refs=[("chr1", span + 10000), ("chr2", span + 10000)], records=records, offsets=offsets)
+
+
+def one_name(n=3000, name="*", seed=3):
+    """Every record carries the same name (stripped names): the map toggles on one key, pairing records (1,2), (3,4), ..."""
+    rng = np.random.default_rng(seed)
+    text = "@HD\tVN:1.4\tSO:coordinate\n@SQ\tSN:chr1\tLN:1000000\n@RG\tID:rg1\tLB:libA\tSM:s\n"
+    pos = np.sort(rng.integers(1, 5000, size=n))
+    recs = [_rec(name, 99 if rng.random() < 0.5 else 147, 0, int(p), "30M", 0, int(pos[int(rng.integers(0, n))]), int(rng.integers(20, 41)),
+                 seq=("ACGT" * 10)[:30]) for p in pos]
+    records, offsets = bamio.concat_records(recs)
+    return bamio.BamFile(text=text, refs=[("chr1", 1000000)], records=records, offsets=offsets)

@@ -322,14 +322,15 @@ def test_reduced_fragment_pass_equals_full_sort_and_oracle():
 
 
 def test_reduced_fragment_pass_overflow_falls_back(monkeypatch):
-    monkeypatch.setenv("OGE_UFRAG_CAP", "64")
+    monkeypatch.setenv("OGE_UFRAG_CAP", "64")      # read by the -DOGE_TESTING build only
     bam = sparse_unpaired_bam(scale=0.002)
     want = oracle.markdup(bam.records, bam.offsets, bam.text)
-    got, _ = gpu_flags(bam)
-    assert np.array_equal(got, want)
-    from openge_b200 import sharded
-    got2, _ = sharded.dedup_in_process(bam, 2)
-    assert np.array_equal(got2, want)
+    with dedup.testing_library():
+        got, _ = gpu_flags(bam)
+        assert np.array_equal(got, want)
+        from openge_b200 import sharded
+        got2, _ = sharded.dedup_in_process(bam, 2)
+        assert np.array_equal(got2, want)
 
 
 def test_reduced_fragment_pass_across_shards():
