@@ -359,6 +359,75 @@ static void mark_frags(ReadEnds **list, uint64_t cnt, int contains_pairs, uint8_
  *   stats_out       : optional [4]: frag entries, pair entries, addIndexAsDuplicate calls, unmatched
  * returns 0, or -1 on allocation failure.
  */
+
+/* ---------------------------------------------------------------------------------------------
+ * Header side of getLibraryName / getLibraryId (mark_duplicates.cpp:282-318), restated from the
+ * reference's own header model so that the oracle does not lean on the product's header code:
+ *   BamHeader::BamHeader(text)        util/bam_header.cpp:107-180: getline() until the stream is no
+ *                                     longer good -- a final line without '\n' is never seen;
+ *                                     "@RG\t" lines become BamReadGroupRecords in file order
+ *   BamReadGroupRecord(line)          util/bam_header.cpp:81-106: tab-split segments, tag = first two
+ *                                     characters, data from the fourth; a later ID / LB on the line
+ *                                     overwrites an earlier one
+ *   BamReadGroupRecords::operator[]   util/bam_header.h:216-241: the FIRST record with the ID
+ *   library ids                       handed out per distinct library NAME (:282-294); an RG without
+ *                                     LB, an unknown ID or no RG tag give "Unknown Library" (:301-318)
+ * out: ids[i] points into `text` (length id_len[i]); lib[i] = 1-based id of that read group's library
+ * name; *unknown = id of "Unknown Library".  Returns the number of read groups, or -1.
+ */
+#define ORACLE_MAX_RG 4096
+static int parse_read_groups(const char *text, const char **ids, uint32_t *id_len, int16_t *lib, int16_t *unknown) {
+    static const char UNK[] = "Unknown Library";
+    const char *names[ORACLE_MAX_RG + 1];
+    uint32_t name_len[ORACLE_MAX_RG + 1];
+    int n_names = 0, n_rg = 0;
+    const char *p = text;
+    names[0] = UNK; name_len[0] = (uint32_t) strlen(UNK); n_names = 1;
+    *unknown = 1;
+    while (*p) {
+        const char *eol = strchr(p, '\n');
+        if (!eol) break;                                   /* unterminated last line: dropped (:111-116) */
+        if (eol - p >= 4 && p[0] == '@' && p[1] == 'R' && p[2] == 'G' && p[3] == '\t') {
+            const char *seg = p + 4, *id = NULL, *lb = NULL;
+            uint32_t idl = 0, lbl = 0;
+            while (seg <= eol) {
+                const char *end = memchr(seg, '\t', (size_t)(eol - seg));
+                if (!end) end = eol;
+                if (end - seg >= 3) {
+                    if (seg[0] == 'I' && seg[1] == 'D') { id = seg + 3; idl = (uint32_t)(end - seg - 3); }
+                    else if (seg[0] == 'L' && seg[1] == 'B') { lb = seg + 3; lbl = (uint32_t)(end - seg - 3); }
+                } else if (end - seg == 2) {               /* "ID" with no data: substr(3) would throw; treat as empty */
+                    if (seg[0] == 'I' && seg[1] == 'D') { id = seg + 2; idl = 0; }
+                    else if (seg[0] == 'L' && seg[1] == 'B') { lb = seg + 2; lbl = 0; }
+                }
+                if (end == eol) break;
+                seg = end + 1;
+            }
+            if (id && n_rg < ORACLE_MAX_RG) {
+                int dup = 0, i, k = -1;
+                for (i = 0; i < n_rg; i++)
+                    if (id_len[i] == idl && !memcmp(ids[i], id, idl)) { dup = 1; break; }   /* first record with the ID wins */
+                if (!dup) {
+                    if (!lb || lbl == 0) k = 0;
+                    else {
+                        for (i = 0; i < n_names; i++)
+                            if (name_len[i] == lbl && !memcmp(names[i], lb, lbl)) { k = i; break; }
+                        if (k < 0) { names[n_names] = lb; name_len[n_names] = lbl; k = n_names++; }
+                    }
+                    ids[n_rg] = id; id_len[n_rg] = idl; lib[n_rg] = (int16_t)(k + 1);
+                    n_rg++;
+                }
+            }
+        }
+        p = eol + 1;
+    }
+    return n_rg;
+}
+
+/* The whole path from the header TEXT: what tests and bench use. */
+int oge_oracle_markdup_text(const uint8_t *records, const uint64_t *offsets, uint64_t n, const char *header_text,
+                            int compat_quiet, uint16_t *flags_out, OracleEnd *ends_out, uint64_t *stats_out);
+
 int oge_oracle_markdup(const uint8_t *records, const uint64_t *offsets, uint64_t n,
                        const char *const *rg_ids, const int16_t *rg_lib, int32_t n_rg, int16_t unknown_lib,
                        int compat_quiet, uint16_t *flags_out, OracleEnd *ends_out, uint64_t *stats_out) {
@@ -477,6 +546,24 @@ int oge_oracle_markdup(const uint8_t *records, const uint64_t *offsets, uint64_t
     for (i = 0; i < tmp.cap; i++) if (tmp.s[i].val) free(tmp.s[i].val);   /* :274-278 */
     free(pair_sort.v); free(frag_sort.v); free(tmp.s); free(dup);
     return 0;
+}
+
+int oge_oracle_markdup_text(const uint8_t *records, const uint64_t *offsets, uint64_t n, const char *header_text,
+                            int compat_quiet, uint16_t *flags_out, OracleEnd *ends_out, uint64_t *stats_out) {
+    const char *ids[ORACLE_MAX_RG];
+    uint32_t id_len[ORACLE_MAX_RG];
+    int16_t lib[ORACLE_MAX_RG], unknown = 1;
+    char *idz[ORACLE_MAX_RG];
+    int n_rg = parse_read_groups(header_text, ids, id_len, lib, &unknown), i, rc;
+    if (n_rg < 0) return -1;
+    for (i = 0; i < n_rg; i++) {                            /* NUL-terminated copies for the table */
+        idz[i] = (char *) malloc(id_len[i] + 1);
+        memcpy(idz[i], ids[i], id_len[i]);
+        idz[i][id_len[i]] = 0;
+    }
+    rc = oge_oracle_markdup(records, offsets, n, (const char *const *) idz, lib, n_rg, unknown, compat_quiet, flags_out, ends_out, stats_out);
+    for (i = 0; i < n_rg; i++) free(idz[i]);
+    return rc;
 }
 
 /* ---------------------------------------------------------------------------------------------

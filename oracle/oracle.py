@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from openge_b200 import _build, bamio, header  # noqa: E402
+from openge_b200 import _build, bamio  # noqa: E402  (build recipes and file I/O only: no product logic)
 
 
 class OracleEnd(C.Structure):
@@ -38,6 +38,8 @@ def lib():
         L.oge_oracle_markdup.restype = C.c_int
         L.oge_oracle_markdup.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_char_p), C.c_void_p,
                                          C.c_int32, C.c_int16, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oge_oracle_markdup_text.restype = C.c_int
+        L.oge_oracle_markdup_text.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oge_oracle_coordinate_order.restype = C.c_int
         L.oge_oracle_coordinate_order.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         L.oge_oracle_flagstats.restype = C.c_int
@@ -104,18 +106,15 @@ def flagstats(records: np.ndarray, offsets: np.ndarray, flags: np.ndarray | None
 def markdup(records: np.ndarray, offsets: np.ndarray, text: str, compat_quiet: bool = False, want_ends: bool = False):
     """CPU oracle over framed records -> flags (u16 per record) [, ends, stats]."""
     L = lib()
-    rg_ids, lib_ids, unknown, _ = header.library_table(text)
     n = len(offsets) - 1
-    ids = (C.c_char_p * max(1, len(rg_ids)))(*rg_ids)
-    libs = np.asarray(lib_ids if lib_ids else [0], dtype=np.int16)
     flags = np.zeros(n, dtype=np.uint16)
     ends = np.zeros(n, dtype=END_DTYPE) if want_ends else None
     stats = np.zeros(4, dtype=np.uint64)
     records = np.ascontiguousarray(records)
     offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
-    rc = L.oge_oracle_markdup(records.ctypes.data, offsets.ctypes.data, n, ids, libs.ctypes.data, len(rg_ids),
-                              unknown, int(compat_quiet), flags.ctypes.data,
-                              ends.ctypes.data if want_ends else None, stats.ctypes.data)
+    # the @RG -> LB -> library id resolution is the oracle's own (parse_read_groups in markdup_oracle.c)
+    rc = L.oge_oracle_markdup_text(records.ctypes.data, offsets.ctypes.data, n, text.encode("latin-1"), int(compat_quiet),
+                                   flags.ctypes.data, ends.ctypes.data if want_ends else None, stats.ctypes.data)
     if rc != 0:
         raise RuntimeError("oracle failed")
     if want_ends:

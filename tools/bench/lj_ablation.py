@@ -1,0 +1,53 @@
+"""Measurement only: the fused end-build + in-CTA join kernel with parts switched off (OGE_LJ_DBG, read by the
+-DOGE_TESTING build; most settings give wrong results).  One JSON line per setting.
+
+    python tools/bench/lj_ablation.py [--scale 0.4] [--steps 3] [--dbg 0,1,2,4,8,12]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from openge_b200 import dedup, synth  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--scale", type=float, default=0.4)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--dbg", default="0,1,2,4,8,12")
+    ap.add_argument("--product", action="store_true", help="use the product library (dbg is ignored there)")
+    a = ap.parse_args()
+    bam = synth.make(a.workload, a.scale)
+
+    def run_all():
+        for legacy in (False, True):
+            for d in ([0] if legacy or a.product else [int(x) for x in a.dbg.split(",")]):
+                os.environ["OGE_LJ_DBG"] = str(d)
+                with dedup.context_for(bam, legacy_join=legacy) as ctx:
+                    ctx.push(bam.records, bam.offsets)
+                    ms = []
+                    for i in range(a.steps + 2):
+                        ctx.run()
+                        st = ctx.stats()
+                        if i >= 2:
+                            ms.append((st["ms_endbuild"], st["ms_join"], st["ms_total"]))
+                    m = np.mean(np.asarray(ms), axis=0)
+                    print(json.dumps({"workload": a.workload, "reads": bam.n, "legacy": legacy, "dbg": d, "ms_endbuild": float(m[0]),
+                                      "ms_join": float(m[1]), "ms_total": float(m[2]), "dups": int(st["n_duplicates"])}), flush=True)
+
+    if a.product:
+        run_all()
+    else:
+        with dedup.testing_library():
+            run_all()
+
+
+if __name__ == "__main__":
+    main()
