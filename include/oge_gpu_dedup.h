@@ -93,6 +93,9 @@ typedef struct oge_gpu_dedup_stats {
     uint64_t inflate_blocks, inflate_bytes_in, inflate_bytes_out;
     uint64_t frame_repairs;         /* chunks whose guessed entry the proof replaced */
     float ms_inflate_h2d, ms_inflate_d2h;   /* push_bgzf: upload of the compressed file, copy-back of the records (0 without host_copy) */
+    /* fused end-build + in-CTA join: pairs settled inside the CTAs, records handed to the global join, local pairs the
+     * check pass retracted (their names had leftovers) */
+    uint64_t n_local_pairs, n_join_leftovers, n_local_retracted;
 } oge_gpu_dedup_stats;
 
 /* Per-record view of the end-building kernel (buildReadEnds, mark_duplicates.cpp:147-164). */

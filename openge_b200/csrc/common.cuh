@@ -40,6 +40,7 @@ struct KeyLayout {
     // pair entry bit positions (keys anchored at the top: p_end == 128)
     int p_idx, p_coord2, p_ref2, p_orient, p_coord1, p_ref1, p_lib, p_end;   // far pairs: p_coord2 = first key bit
     int n_delta, delta_bits;                                                 // near pairs: n_delta = first key bit
+    int fast;      // 1: field widths allow the 64-bit word form of the pair-entry builder (pairing.cuh); set by compute_layout
 };
 
 // ---- 128-bit field helpers (positions and widths are warp-uniform) ---------------------------

@@ -16,7 +16,8 @@ struct DevBuf {
     size_t cap = 0;      // elements
     int reserve(size_t n, bool keep, cudaStream_t s) {
         if (n <= cap) return 0;
-        size_t want = keep && cap ? std::max(n, cap + cap / 2) : n;
+        // grow with slack: sizes that follow data-dependent (and race-dependent) counts must not reallocate on every run
+        size_t want = keep && cap ? std::max(n, cap + cap / 2) : (cap ? n + n / 8 + 4096 : n);
         T *q = nullptr;
         cudaError_t e = cudaMalloc((void **) &q, want * sizeof(T) + 256);
         if (e != cudaSuccess && want > n) {
@@ -101,7 +102,8 @@ struct oge_gpu_dedup_ctx {
     DevBuf<E128> ufrag, ufrag2;                                  // reduced fragment pass: the entries that can matter
     DevBuf<unsigned long long> uset;                             // keys of the unpaired ends
     DevBuf<uint64_t> hk, pair_hk, pairf_hk;                      // pair_hk: key hash of the pairs formed inside the CTAs of the fused end-build
-    DevBuf<uint32_t> left;                                       // fused end-build: records handed to the global join
+    DevBuf<uint32_t> left, couple_count;                         // windowed join: records handed to the global join; couples per CTA
+    DevBuf<uint4> couples;                                       // windowed join: (taker, entry, hash) of every couple matched inside a CTA
     DevBuf<E128> cplx_sort;                                      // ping-pong buffer of the exact path's sort
     DevBuf<uint16_t> flag_in, flag_out;
     DevBuf<NameTag> tag;

@@ -89,6 +89,17 @@ int compute_layout(oge_gpu_dedup_ctx *c, KeyLayout *L) {
         L->delta_bits = d;
         L->n_delta = L->p_orient - d;
     }
+    {
+        // the 64-bit word form of the pair-entry builder (pairing.cuh: make_pair_entry) needs: the [coord][ref][lib] block
+        // of a fragment entry reachable with one two-word shift and at most 62 bits wide, the ordinal inside the low word, the
+        // near key inside the high word, far fields that do not overlap the payload
+        const int block = L->coord_bits + L->ref_bits + L->lib_bits;
+        L->fast = L->f_coord > 0 && L->f_coord < 64 && L->f_orient < 64 && block <= 62 && 16 + L->idx_bits <= 64 &&
+                  block + 2 + L->delta_bits <= 64 && L->n_delta >= 64 && L->coord_bits + L->ref_bits <= 62;
+#ifdef OGE_TESTING
+        if (getenv("OGE_GENERIC_PAIR_ENTRY")) L->fast = 0;      // test hook: the field-by-field form
+#endif
+    }
     if (L->f_end > 128 || L->p_coord2 < 16 + L->idx_bits)
         return fail_msg(OGE_ERR_KEY_RANGE,
                         "key layout needs %d (frag) / %d (pair) bits, more than the 128 of a 16-byte entry: "
@@ -236,7 +247,7 @@ void oge_gpu_dedup_destroy(oge_gpu_dedup_ctx *c) {
     c->rec.release(); c->off.release(); c->rg_bytes.release(); c->rg_off.release(); c->rg_lib.release();
     c->frag.release(); c->sortbuf.release(); c->pair.release(); c->pair2.release(); c->pairf.release(); c->pairf2.release(); c->ufrag.release(); c->ufrag2.release(); c->uset.release(); c->hk.release();
     c->tag.release(); c->flag_in.release(); c->flag_out.release(); c->dup.release(); c->scratch.release();
-    c->cplx_state.release(); c->cplx_slots.release(); c->cplx_sort.release(); c->pair_hk.release(); c->pairf_hk.release(); c->left.release(); c->mate_of.release(); c->counters.release(); c->table.release();
+    c->cplx_state.release(); c->cplx_slots.release(); c->cplx_sort.release(); c->pair_hk.release(); c->pairf_hk.release(); c->left.release(); c->couples.release(); c->couple_count.release(); c->mate_of.release(); c->counters.release(); c->table.release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->clk_ev) if (e) cudaEventDestroy(e);
@@ -562,8 +573,7 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     eb.rec = c->recs(); eb.off = c->off.p; eb.n = n; eb.idx_base = c->cfg.index_base;
     eb.frag = c->frag.p; eb.hk = c->hk.p; eb.tag = c->tag.p; eb.flag_in = c->flag_in.p;
     eb.counters = c->counters.p; eb.rg = rg_table(c); eb.kl = c->kl;
-    // debug_keep_ends wants hk[] of every record; the fused kernel only writes the leftovers'
-    const bool fused = !c->cfg.debug_keep_ends && !c->cfg.debug_legacy_join;
+    const bool fused = !c->cfg.debug_legacy_join;      // windowed join (default) or the whole-file hash join
     uint64_t n_pairs = 0, n_far = 0, n_cplx = 0, n_retracted = 0, n_far_retracted = 0, n_left = 0, n_pe = 0;
     JoinParams jp;
     jp.rec = c->recs(); jp.off = c->off.p; jp.n = n; jp.idx_base = c->cfg.index_base;
@@ -571,23 +581,28 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     jp.mate_of = c->mate_of.p; jp.cplx = c->sortbuf.p;
     jp.counters = c->counters.p; jp.rg = rg_table(c); jp.kl = c->kl; jp.verify_names = c->cfg.verify_names;
     jp.list = nullptr; jp.n_list = 0;
+    if ((rc = launch_endbuild(eb, (uint32_t) (c->rec_bytes / n), c->sms, s, &launches))) return rc;
+    OGE_CUDA_TRY(cudaEventRecord(c->ev[1], s));
     if (fused) {
-        const uint64_t pair_cap = n / 2 + 3ull * LJ_PAIR_BLOCK * endbuild_join_max_grid(c->sms) + 1024, far_cap = n / 2 + 1024;
+        // windowed join: every CTA pairs the reads of its contiguous record range in shared memory (no sizes needed from K1:
+        // no host round trip in between); what it cannot settle is listed for the global join below
+        const uint64_t pair_cap = n / 2 + 1024, far_cap = n / 2 + 1024;
         if ((rc = c->pair.reserve(pair_cap, false, s)) || (rc = c->pair2.reserve(pair_cap, false, s)) ||
             (rc = c->pairf.reserve(far_cap, false, s)) || (rc = c->pairf2.reserve(far_cap, false, s)) ||
             (rc = c->pair_hk.reserve(pair_cap, false, s)) || (rc = c->pairf_hk.reserve(far_cap, false, s)) ||
             (rc = c->left.reserve(n, false, s)))
             return rc;
+        uint32_t lj_grid = 0, lj_tpc = 0;
+        local_join_shape(n, c->sms, &lj_grid, &lj_tpc);
+        if ((rc = c->couples.reserve((uint64_t) lj_grid * lj_tpc * (LJ_TILE / 2), false, s)) || (rc = c->couple_count.reserve(lj_grid, false, s))) return rc;
         LocalJoinParams lj;
+        lj.couples = c->couples.p; lj.couple_count = c->couple_count.p; lj.couples_per_cta = 0;
         lj.pair = c->pair.p; lj.pair_far = c->pairf.p; lj.pair_hk = c->pair_hk.p; lj.pair_far_hk = c->pairf_hk.p;
-        lj.pair_cap = (uint32_t) std::min<uint64_t>(pair_cap, 0xFFFFFFFFull); lj.far_cap = (uint32_t) far_cap;
+        lj.pair_cap = (uint32_t) pair_cap; lj.far_cap = (uint32_t) far_cap;
         lj.mate_of = c->mate_of.p; lj.left = c->left.p; lj.n_buckets = 0; lj.tiles_per_cta = 0;
-        uint32_t grid = 0;
-        if ((rc = launch_endbuild_join(eb, lj, (uint32_t) (c->rec_bytes / n), c->sms, s, &launches, &grid))) return rc;
-    } else {
-        if ((rc = launch_endbuild(eb, (uint32_t) (c->rec_bytes / n), c->sms, s, &launches))) return rc;
+        jp.table = nullptr; jp.n_slots = 0; jp.pair = c->pair.p; jp.pair_far = c->pairf.p; jp.cplx_slots = nullptr;
+        if ((rc = launch_local_join(jp, lj, c->sms, s, &launches))) return rc;
     }
-    OGE_CUDA_TRY(cudaEventRecord(c->ev[1], s));
     OGE_CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, s));
     OGE_CUDA_TRY(cudaStreamSynchronize(s));
     if ((rc = check_endbuild_errors(c))) return rc;
@@ -595,6 +610,7 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     n_pe = c->h_counters[CNT_PAIR_ELIGIBLE];
     c->h_counters_k1_unpaired = c->h_counters[CNT_UNPAIRED];
     n_left = c->h_counters[CNT_LEFT];
+    const uint64_t n_dead_k1 = 0;
 
     // ---- K2 mate join: every map-eligible record (legacy form), or what the CTAs could not settle (fused form)
     const uint64_t n_join = fused ? n_left : n_pe;
@@ -757,6 +773,9 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     st.n_pair_entries = n_pairs - n_retracted + n_far - n_far_retracted;
     st.n_duplicates = c->h_counters[CNT_DUPS];
     st.n_complex_names = n_cplx;
+    st.n_local_pairs = fused ? (uint64_t) n_loc - n_dead_k1 + n_loc_far : 0;
+    st.n_join_leftovers = n_left;
+    st.n_local_retracted = fused ? n_retracted + n_far_retracted - n_dead_k1 : 0;
     st.n_hash_mismatch = c->h_counters[CNT_HASH_MISMATCH];
     st.frag_key_bits = c->kl.f_end - c->kl.f_orient;
     st.pair_key_bits = c->kl.p_end - c->kl.n_delta;      // near pairs (far pairs: p_end - p_coord2)

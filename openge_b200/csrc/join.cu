@@ -393,6 +393,254 @@ int launch_pair_check(const JoinParams &P, const uint64_t *pair_hk, uint32_t n_p
     return 0;
 }
 
+
+// ---- the windowed join -----------------------------------------------------------------------------
+// A coordinate-sorted file keeps the two reads of a pair a few (to a few hundred) records apart, so the join does
+// not need a table over the whole file: every CTA walks a CONTIGUOUS range of records in tiles and keeps the
+// reads whose mate it has not met yet in a shared-memory table (8-way buckets: a key word per way = low hash word,
+// 12 bytes of payload).  Per tile:
+//   phase 1   every map-eligible record scans its bucket: its key word is there -> FOUND that way; else it
+//             claims the first empty way with a shared-memory CAS (a failed CAS that returns its own key
+//             word is a FOUND as well: the mate got there first) and writes its payload -> INSERTED
+//   phase 2   a FOUND record takes the entry (first taker only) and confirms the match by comparing the two
+//             32-byte name tags (and the name tails in the records for names longer than a tag); it builds
+//             the pair entry exactly as the global join does (flip rule mark_duplicates.cpp:226-243,
+//             orientation :169-178, score :245), appends it (warp-aggregated) and frees the way.
+// Everything else -- bucket full, a second taker (name seen three times at once), equal hash but different key
+// bytes, entries nobody came for within LJ_HORIZON records or by the end of the CTA's range -- goes on the
+// `left` list, which the global join above takes as its input (LIST form).  Pairing here is by arrival, not by
+// file order, which is only right for names seen exactly twice; that is what pair_check_kernel establishes
+// afterwards (a name with any record on the `left` list has its pairs retracted and is replayed in file order by
+// the exact path).  Within one CTA an entry is always the most recent unmatched sighting of its name, so names
+// without leftovers and without a double take were paired as the reference's toggle map pairs them
+// (util/picard_structures.h:87-96).
+// HBM traffic: the hash of every record once (8 B), tag and end entry of every paired record once (48 B), the
+// pair entry and its hash (24 B per pair): about 70 B per record, streamed; the table never leaves the SM.
+struct __align__(4) LjPay {
+    uint32_t h_hi, ord, cnt;      // high hash word, local ordinal, takers so far
+};
+static_assert(sizeof(LjPay) + 4 == LJ_ENTRY_BYTES, "LJ_ENTRY_BYTES");
+
+__device__ __forceinline__ void lj_leftover(uint32_t *counter, uint32_t *left, uint32_t ord) {
+    const uint32_t act = __activemask(), lane = threadIdx.x & 31;
+    const int leader = __ffs(act) - 1;
+    uint32_t base = 0;
+    if ((int) lane == leader) base = atomicAdd(counter, (uint32_t) __popc(act));
+    base = __shfl_sync(act, base, leader);
+    left[base + __popc(act & ((1u << lane) - 1))] = ord;
+}
+
+// K2a: phases 1 and 2 (take) over the hashes alone.  A taker writes the couple (its ordinal, the entry's ordinal,
+// the key hash) into the CTA's own stretch of the couple list -- both records lie in the CTA's range, so the
+// stretch never holds more than half the range's records and needs no cross-CTA counter.  Nothing but hk[] is read
+// from global memory: one latency per tile, small register footprint, six CTAs per SM.
+__global__ void __launch_bounds__(LJ_THREADS, LJ_CTAS_PER_SM) local_match_kernel(const __grid_constant__ JoinParams P,
+                                                                                 const __grid_constant__ LocalJoinParams J) {
+    extern __shared__ __align__(16) uint8_t lj_smem[];      // [key words: n_entries][payloads: n_entries]
+    __shared__ uint32_t s_couples;
+    const int tid = threadIdx.x;
+    const uint32_t n_entries = J.n_buckets * LJ_WAYS;
+    uint32_t *keys = reinterpret_cast<uint32_t *>(lj_smem);
+    LjPay *pay = reinterpret_cast<LjPay *>(keys + n_entries);
+    for (uint32_t j = tid; j < n_entries; j += LJ_THREADS) keys[j] = 0;
+    if (tid == 0) s_couples = 0;
+    const uint64_t t0 = (uint64_t) blockIdx.x * J.tiles_per_cta;
+    const uint64_t n_tiles = (P.n + LJ_TILE - 1) / LJ_TILE;
+    const uint64_t t1 = t0 + J.tiles_per_cta < n_tiles ? t0 + J.tiles_per_cta : n_tiles;
+    uint4 *couples = J.couples + (uint64_t) blockIdx.x * J.couples_per_cta;
+    __syncthreads();
+
+    uint32_t k = 0;
+    uint64_t h_next[LJ_ITEMS];      // the next tile's hashes are requested one tile ahead
+#pragma unroll
+    for (int q = 0; q < LJ_ITEMS; q++) {
+        const uint64_t i = t0 * LJ_TILE + (uint64_t) q * LJ_THREADS + tid;
+        h_next[q] = t0 < t1 && i < P.n ? P.hk[i] : 0ull;
+    }
+    for (uint64_t tile = t0; tile < t1; tile++, k++) {
+        const uint64_t r0 = tile * LJ_TILE;
+        uint64_t h[LJ_ITEMS];
+        int way[LJ_ITEMS];            // FOUND: the way; INSERTED: -2; overflow: -3; not in the map: -1
+        uint32_t slot0[LJ_ITEMS];
+#pragma unroll
+        for (int q = 0; q < LJ_ITEMS; q++) {
+            h[q] = h_next[q];
+            const uint64_t i = r0 + LJ_TILE + (uint64_t) q * LJ_THREADS + tid;
+            h_next[q] = tile + 1 < t1 && i < P.n ? P.hk[i] : 0ull;
+        }
+        // ---- phase 1: find the mate's entry, or leave one
+#pragma unroll
+        for (int q = 0; q < LJ_ITEMS; q++) {
+            way[q] = -1;
+            slot0[q] = 0;
+            if (!h[q]) continue;
+            const uint32_t k32 = (uint32_t) h[q], h_hi = (uint32_t) (h[q] >> 32);
+            const uint32_t ord = (uint32_t) (r0 + (uint64_t) q * LJ_THREADS + tid);
+            slot0[q] = __umulhi(h_hi, J.n_buckets) * LJ_WAYS;
+            const uint4 ka = *reinterpret_cast<const uint4 *>(keys + slot0[q]), kb = *reinterpret_cast<const uint4 *>(keys + slot0[q] + 4);
+            const uint32_t kk[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
+            int first_empty = -1, w_found = -1;
+#pragma unroll
+            for (int w = 7; w >= 0; w--) {
+                if (kk[w] == k32) w_found = w;
+                if (kk[w] == 0) first_empty = w;
+            }
+            if (w_found >= 0) { way[q] = w_found; continue; }
+            way[q] = -3;
+            for (int w = first_empty; w >= 0 && w < LJ_WAYS; w++) {
+                const uint32_t cur = *reinterpret_cast<volatile uint32_t *>(keys + slot0[q] + w);
+                if (cur == k32) { way[q] = w; break; }
+                if (cur != 0) continue;
+                const uint32_t old = atomicCAS(keys + slot0[q] + w, 0u, k32);
+                if (old == 0) {
+                    LjPay &e = pay[slot0[q] + w];
+                    e.h_hi = h_hi; e.ord = ord; e.cnt = 0;
+                    way[q] = -2;
+                    break;
+                }
+                if (old == k32) { way[q] = w; break; }
+            }
+        }
+        __syncthreads();      // payloads of this tile's insertions are visible
+
+        // ---- phase 2: take the entry (first taker only); the names are compared by K2b
+#pragma unroll
+        for (int q = 0; q < LJ_ITEMS; q++) {
+            if (!h[q] || way[q] == -2) continue;
+            const uint32_t i = (uint32_t) (r0 + (uint64_t) q * LJ_THREADS + tid);
+            bool took = false;
+            if (way[q] >= 0) {
+                LjPay &e = pay[slot0[q] + way[q]];
+                if (e.h_hi == (uint32_t) (h[q] >> 32) && atomicAdd(&e.cnt, 1u) == 0) {
+                    const uint32_t other = e.ord;
+                    keys[slot0[q] + way[q]] = 0;      // the way is free again (nobody reads key words before the next barrier)
+                    couples[atomicAdd(&s_couples, 1u)] = make_uint4(i, other, (uint32_t) h[q], (uint32_t) (h[q] >> 32));
+                    took = true;
+                }
+            }
+            if (!took) lj_leftover(P.counters + CNT_LEFT, J.left, i);
+        }
+
+        // ---- entries nobody came for leave for the global join
+        if ((k % LJ_SWEEP_TILES) == LJ_SWEEP_TILES - 1) {
+            __syncthreads();
+            for (uint32_t j = tid; j < n_entries; j += LJ_THREADS) {
+                if (keys[j] && (uint32_t) r0 - pay[j].ord > LJ_HORIZON) {
+                    keys[j] = 0;
+                    lj_leftover(P.counters + CNT_LEFT, J.left, pay[j].ord);
+                }
+            }
+        }
+        __syncthreads();      // phase 2 (and the sweep) are complete before the next tile's phase 1
+    }
+    // ---- end of the CTA's range: whatever is still waiting leaves
+    for (uint32_t j = tid; j < n_entries; j += LJ_THREADS)
+        if (keys[j]) lj_leftover(P.counters + CNT_LEFT, J.left, pay[j].ord);
+    if (tid == 0) J.couple_count[blockIdx.x] = s_couples;
+}
+
+// K2b: one thread per couple.  Confirms the match by comparing the two 32-byte name tags (and the name tails in
+// the records for names longer than a tag), builds the pair entry and appends it (warp-aggregated); a couple that
+// fails the comparison -- one hash, two keys, or read groups the header does not list -- goes to the global join.
+__global__ void __launch_bounds__(JOIN_THREADS) local_emit_kernel(const __grid_constant__ JoinParams P, const __grid_constant__ LocalJoinParams J,
+                                                                  uint32_t n_ctas) {
+    const uint64_t j = (uint64_t) blockIdx.x * JOIN_THREADS + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1;
+    const uint32_t cta = (uint32_t) (j / J.couples_per_cta);
+    const bool live = cta < n_ctas && (uint32_t) (j - (uint64_t) cta * J.couples_per_cta) < J.couple_count[cta];
+    bool emit = false, far = false;
+    uint32_t i1 = 0, i2 = 0;
+    uint64_t h = 0;
+    E128 ent;
+    ent.lo = ent.hi = 0;
+    if (live) {
+        const uint4 c = J.couples[j];
+        const uint32_t i = c.x, other = c.y;
+        h = ((uint64_t) c.w << 32) | c.z;
+        const uint4 *ta = reinterpret_cast<const uint4 *>(P.tag + i), *tb = reinterpret_cast<const uint4 *>(P.tag + other);
+        const uint4 a0 = ta[0], a1 = ta[1], b0 = tb[0], b1 = tb[1];
+        const E128 fa = ld_frag(P.frag + i), fb = ld_frag(P.frag + other);
+        bool same = a0.x == b0.x && a0.y == b0.y && a0.z == b0.z && a0.w == b0.w && a1.x == b1.x && a1.y == b1.y &&
+                    a1.z == b1.z && a1.w == b1.w && (a0.x & 0xFFFFu) != RGC_UNKNOWN;
+        const uint32_t l_name = (a0.x >> 16) & 0xFFu;
+        if (same && l_name > NAME_TAG_BYTES + 1) same = name_tails_equal(P.rec + P.off[i], P.rec + P.off[other], l_name);
+        if (same) {
+            const bool self_first = i < other;      // file order
+            ent = make_pair_entry(P.kl, self_first ? fa : fb, self_first ? fb : fa, &i1, &i2, P.idx_base, &far);
+            emit = true;
+        } else {
+            lj_leftover(P.counters + CNT_LEFT, J.left, i);
+            lj_leftover(P.counters + CNT_LEFT, J.left, other);
+        }
+    }
+    // ---- CTA-aggregated append: one reservation in the near-pair list per CTA (a counter at one address serves about
+    //      one atomic per nanosecond; per warp that was a third of this kernel's time).  Far pairs are rare and append one by one.
+    __shared__ uint32_t s_warp_cnt[JOIN_THREADS / 32], s_base;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, emit && !far);
+    if (lane == 0) s_warp_cnt[threadIdx.x >> 5] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < JOIN_THREADS / 32; w++) {
+            const uint32_t c = s_warp_cnt[w];
+            s_warp_cnt[w] = total;
+            total += c;
+        }
+        s_base = total ? atomicAdd(&P.counters[CNT_PAIRS], total) : 0u;
+    }
+    __syncthreads();
+    if (emit && !far) {
+        const uint32_t at = s_base + s_warp_cnt[threadIdx.x >> 5] + __popc(m & lt);
+        if (at < J.pair_cap) {
+            reinterpret_cast<ulonglong2 *>(J.pair)[at] = make_ulonglong2(ent.lo, ent.hi);
+            J.pair_hk[at] = h;
+        } else atomicOr(&P.counters[CNT_ERR], DEV_ERR_CAPACITY);
+    }
+    if (emit) {
+        if (far) {
+            const uint32_t at = atomicAdd(&P.counters[CNT_PAIRS_FAR], 1u);
+            if (at < J.far_cap) {
+                reinterpret_cast<ulonglong2 *>(J.pair_far)[at] = make_ulonglong2(ent.lo, ent.hi);
+                J.pair_far_hk[at] = h;
+            } else atomicOr(&P.counters[CNT_ERR], DEV_ERR_CAPACITY);
+        }
+        J.mate_of[i1] = (uint32_t) (i2 + P.idx_base);
+    }
+}
+
+uint32_t local_join_max_grid(int sms) { return (uint32_t) sms * LJ_CTAS_PER_SM; }
+
+// tiles per CTA and grid for n records on `sms` SMs: contiguous tile ranges, at least 8 tiles each (pairs across a
+// range boundary go through the global join)
+void local_join_shape(uint64_t n, int sms, uint32_t *grid_out, uint32_t *tiles_per_cta) {
+    const uint64_t n_tiles = (n + LJ_TILE - 1) / LJ_TILE;
+    uint64_t grid = local_join_max_grid(sms);
+    if (grid > (n_tiles + 7) / 8) grid = (n_tiles + 7) / 8;
+    if (grid < 1) grid = 1;
+    const uint64_t tpc = (n_tiles + grid - 1) / grid;
+    grid = (n_tiles + tpc - 1) / tpc;
+    *grid_out = (uint32_t) grid;
+    *tiles_per_cta = (uint32_t) tpc;
+}
+
+int launch_local_join(const JoinParams &P, LocalJoinParams J, int sms, cudaStream_t stream, uint64_t *launches) {
+    if (P.n == 0) return 0;
+    uint32_t grid = 0, tpc = 0;
+    local_join_shape(P.n, sms, &grid, &tpc);
+    J.n_buckets = LJ_BUCKETS;
+    J.tiles_per_cta = tpc;
+    J.couples_per_cta = tpc * (LJ_TILE / 2);
+    const size_t smem = (size_t) LJ_BUCKETS * LJ_WAYS * LJ_ENTRY_BYTES;
+    OGE_CUDA_TRY(cudaFuncSetAttribute(local_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    local_match_kernel<<<grid, LJ_THREADS, smem, stream>>>(P, J);
+    const uint64_t slots = (uint64_t) grid * J.couples_per_cta;
+    local_emit_kernel<<<(uint32_t) ((slots + JOIN_THREADS - 1) / JOIN_THREADS), JOIN_THREADS, 0, stream>>>(P, J, grid);
+    *launches += 2;
+    OGE_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 int launch_mate_fixup(const JoinParams &P, uint32_t n_slots_listed, cudaStream_t stream, uint64_t *launches) {
     if (n_slots_listed == 0) return 0;
     mate_fixup_kernel<<<(n_slots_listed + JOIN_THREADS - 1) / JOIN_THREADS, JOIN_THREADS, 0, stream>>>(P, n_slots_listed);

@@ -48,34 +48,30 @@ struct EndbuildParams {
 
 int launch_endbuild(const EndbuildParams &P, uint32_t avg_rec_bytes, int sms, cudaStream_t stream, uint64_t *launches);
 
-// ---- K1 with the in-CTA mate join (endbuild.cu, fused form) ---------------
-// A coordinate-sorted file keeps the two reads of a pair a few (to a few hundred) records apart, so a
-// CTA that walks a CONTIGUOUS range of tiles can pair them in a small shared-memory table while the
-// records are on the SM anyway: no hash/tag arrays, no global table sector per record.  What the
-// CTA cannot settle (mate in another CTA's range or further than LJ_HORIZON records away, table
-// overflow, a name seen three times at once) is handed to the global join (join.cu) as a list of
-// record ordinals; a pair formed here is final iff its key hash is not among those leftovers,
-// which the check pass of join.cu establishes.
+// ---- K2, windowed form (join.cu: local_join_kernel) -------------------------
 constexpr int LJ_WAYS = 8;                   // ways per bucket of the in-CTA table
-constexpr int LJ_ENTRY_BYTES = 4 + 24;       // key word + payload
-constexpr uint32_t LJ_PAIR_BLOCK = 256;      // pair-list positions a CTA reserves at a time (>= 2 * EB_THREADS)
-constexpr uint32_t LJ_HORIZON = 4096;        // an entry unmatched for this many records leaves for the global join
-constexpr uint32_t LJ_SWEEP_TILES = 8;       // how often the table is swept for such entries
+constexpr int LJ_ENTRY_BYTES = 4 + 12;       // key word + payload
+constexpr int LJ_CTAS_PER_SM = 6;
+constexpr int LJ_BUCKETS = 256;              // 2048 entries = 32 KB of shared memory per CTA
+constexpr int LJ_THREADS = 256;
+constexpr int LJ_ITEMS = 4;
+constexpr int LJ_TILE = LJ_THREADS * LJ_ITEMS;
+constexpr uint32_t LJ_HORIZON = 16384;       // an entry unmatched for this many records leaves for the global join
+constexpr uint32_t LJ_SWEEP_TILES = 4;       // how often the table is swept for such entries
 
 struct LocalJoinParams {
     E128 *pair, *pair_far;              // pair lists (counters[CNT_PAIRS], counters[CNT_PAIRS_FAR])
-    uint64_t *pair_hk, *pair_far_hk;    // key hash of every pair entry, by list position (0 = no entry)
+    uint64_t *pair_hk, *pair_far_hk;    // key hash of every pair entry, by list position
     uint32_t pair_cap, far_cap;
     uint32_t *mate_of;                  // [n] GLOBAL ordinal of the pair's other record, indexed by idx1's local ordinal
     uint32_t *left;                     // [n] local ordinals handed to the global join (counters[CNT_LEFT])
+    uint4 *couples;                     // (taker, entry, hash lo, hash hi): CTA b owns [b * couples_per_cta, + couple_count[b])
+    uint32_t *couple_count;             // [grid]
+    uint32_t couples_per_cta;
     uint32_t n_buckets;                 // per CTA
     uint32_t tiles_per_cta;
 };
-
-// hk[] and tag[] of P are written only for the records on the `left` list.
-int launch_endbuild_join(const EndbuildParams &P, LocalJoinParams J, uint32_t avg_rec_bytes, int sms, cudaStream_t stream,
-                         uint64_t *launches, uint32_t *grid_out);
-uint32_t endbuild_join_max_grid(int sms);
+void local_join_shape(uint64_t n, int sms, uint32_t *grid_out, uint32_t *tiles_per_cta);
 
 // ---- K2 mate join (join.cu) -------------------------------------------------------------------
 struct __align__(32) MateSlot {      // one 32-byte sector
@@ -110,6 +106,8 @@ struct JoinParams {
 };
 
 int launch_mate_join(const JoinParams &P, cudaStream_t stream, uint64_t *launches);
+// windowed form: pairs settled inside the CTAs' contiguous record ranges; the rest goes on J.left
+int launch_local_join(const JoinParams &P, LocalJoinParams J, int sms, cudaStream_t stream, uint64_t *launches);
 // fused form: is the key hash of a pair formed inside a CTA among the records the global join has seen?  Then the pair
 // is retracted and its two records (with whatever the slot held) go to the exact path.
 int launch_pair_check(const JoinParams &P, const uint64_t *pair_hk, uint32_t n_pairs, bool far, cudaStream_t stream, uint64_t *launches);

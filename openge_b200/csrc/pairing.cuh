@@ -11,8 +11,9 @@ __device__ __forceinline__ uint64_t slot_of(uint64_t h, uint64_t n_slots) { retu
 
 // ---- pair entry ---------------------------------------------------------------------------------
 // first = the record seen first in the file (the map's stored ReadEnds), second = the current one.
-__device__ __forceinline__ E128 make_pair_entry(const KeyLayout &L, const E128 &first, const E128 &second,
-                                                uint32_t *idx1_local, uint32_t *idx2_local, uint64_t idx_base, bool *far) {
+// Generic form: field by field, any widths.
+static __device__ __noinline__ E128 make_pair_entry_generic(const KeyLayout &L, const E128 &first, const E128 &second,
+                                                     uint32_t *idx1_local, uint32_t *idx2_local, uint64_t idx_base, bool *far) {
     uint64_t lib = bits_get(first, L.f_lib, L.lib_bits);      // library of the first-seen end (:218)
     uint64_t ref_f = bits_get(first, L.f_ref, L.ref_bits), ref_s = bits_get(second, L.f_ref, L.ref_bits);
     uint64_t co_f = bits_get(first, L.f_coord, L.coord_bits), co_s = bits_get(second, L.f_coord, L.coord_bits);
@@ -39,6 +40,43 @@ __device__ __forceinline__ E128 make_pair_entry(const KeyLayout &L, const E128 &
     bits_or(e, L.p_coord1, c1);
     bits_or(e, L.p_ref1, r1);
     bits_or(e, L.p_lib, lib);
+    *idx1_local = (uint32_t) (i1 - idx_base);
+    *idx2_local = (uint32_t) (i2 - idx_base);
+    return e;
+}
+
+// Word form, for layouts with L.fast (every human-sized file): in a fragment entry [coord][ref][lib] is one
+// contiguous block above bit f_coord (0 < f_coord < 64), and the pair key holds the same block [coord1][ref1][lib]
+// in the same order, so it moves as a whole; (ref, coord) compares as the integer [coord][ref]; and the near key
+// (block + orientation + distance) is at most 64 bits wide and, anchored at bit 127, lies in the high word.
+__device__ __forceinline__ E128 make_pair_entry(const KeyLayout &L, const E128 &first, const E128 &second,
+                                                uint32_t *idx1_local, uint32_t *idx2_local, uint64_t idx_base, bool *far) {
+    if (!L.fast) return make_pair_entry_generic(L, first, second, idx1_local, idx2_local, idx_base, far);
+    const int fc = L.f_coord, cr = L.coord_bits + L.ref_bits;
+    const uint64_t blk_f = (first.lo >> fc) | (first.hi << (64 - fc)), blk_s = (second.lo >> fc) | (second.hi << (64 - fc));
+    const uint64_t cr_mask = (1ull << cr) - 1;
+    const uint64_t pos_f = blk_f & cr_mask, pos_s = blk_s & cr_mask;      // [coord][ref] as one number
+    const bool keep = pos_s >= pos_f;                                      // (:229-243)
+    const uint64_t p1 = keep ? pos_f : pos_s, p2 = keep ? pos_s : pos_f;
+    const uint64_t lo1 = keep ? first.lo : second.lo, lo2 = keep ? second.lo : first.lo;
+    const uint64_t idx_mask = (1ull << L.idx_bits) - 1;
+    const uint64_t i1 = (lo1 >> 16) & idx_mask, i2 = (lo2 >> 16) & idx_mask;
+    const uint64_t orient = (((lo1 >> L.f_orient) & 1) << 1) | ((lo2 >> L.f_orient) & 1);      // (:169-178)
+    const uint64_t lib = blk_f >> cr;                                      // library of the first-seen end (:218); bits above are zero
+    const uint64_t block1 = (lib << cr) | p1;
+    const uint64_t delta = p2 - p1;
+    *far = ((p1 ^ p2) >> L.coord_bits) != 0 || delta >= (1ull << L.delta_bits);
+    E128 e;
+    e.lo = (((uint32_t) first.lo + (uint32_t) second.lo) & 0xFFFFu) | (i1 << 16);      // short + short (:245)
+    e.hi = 0;
+    if (!*far) {
+        const uint64_t key = (((block1 << 2) | orient) << L.delta_bits) | delta;
+        e.hi = key << (L.n_delta - 64);
+    } else {
+        bits_or(e, L.p_coord2, p2);      // [coord2][ref2], contiguous like the block
+        bits_or(e, L.p_orient, orient);
+        bits_or(e, L.p_coord1, block1);
+    }
     *idx1_local = (uint32_t) (i1 - idx_base);
     *idx2_local = (uint32_t) (i2 - idx_base);
     return e;

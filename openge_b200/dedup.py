@@ -46,7 +46,8 @@ class Stats(C.Structure):
                 ("ms_sort_pass_kernels", C.c_float), ("sort_pass_launches", C.c_uint32), ("sort_pass_bytes", C.c_uint64),
                 ("ms_inflate", C.c_float), ("ms_frame", C.c_float), ("inflate_blocks", C.c_uint64),
                 ("inflate_bytes_in", C.c_uint64), ("inflate_bytes_out", C.c_uint64), ("frame_repairs", C.c_uint64),
-                ("ms_inflate_h2d", C.c_float), ("ms_inflate_d2h", C.c_float)]
+                ("ms_inflate_h2d", C.c_float), ("ms_inflate_d2h", C.c_float),
+                ("n_local_pairs", C.c_uint64), ("n_join_leftovers", C.c_uint64), ("n_local_retracted", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

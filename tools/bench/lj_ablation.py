@@ -1,5 +1,5 @@
-"""Measurement only: the fused end-build + in-CTA join kernel with parts switched off (OGE_LJ_DBG, read by the
--DOGE_TESTING build; most settings give wrong results).  One JSON line per setting.
+"""Measurement only: end-build and mate join stage times, windowed join against the whole-file hash join (legacy),
+on one workload.  One JSON line per form.
 
     python tools/bench/lj_ablation.py [--scale 0.4] [--steps 3] [--dbg 0,1,2,4,8,12]
 """
@@ -26,27 +26,26 @@ def main():
     a = ap.parse_args()
     bam = synth.make(a.workload, a.scale)
 
-    def run_all():
-        for legacy in (False, True):
-            for d in ([0] if legacy or a.product else [int(x) for x in a.dbg.split(",")]):
-                os.environ["OGE_LJ_DBG"] = str(d)
-                with dedup.context_for(bam, legacy_join=legacy) as ctx:
-                    ctx.push(bam.records, bam.offsets)
-                    ms = []
-                    for i in range(a.steps + 2):
-                        ctx.run()
-                        st = ctx.stats()
-                        if i >= 2:
-                            ms.append((st["ms_endbuild"], st["ms_join"], st["ms_total"]))
-                    m = np.mean(np.asarray(ms), axis=0)
-                    print(json.dumps({"workload": a.workload, "reads": bam.n, "legacy": legacy, "dbg": d, "ms_endbuild": float(m[0]),
-                                      "ms_join": float(m[1]), "ms_total": float(m[2]), "dups": int(st["n_duplicates"])}), flush=True)
+    def run_all(label):
+        for legacy in ((False, True) if label == "product" else (False,)):
+            with dedup.context_for(bam, legacy_join=legacy) as ctx:
+                ctx.push(bam.records, bam.offsets)
+                ms = []
+                for i in range(a.steps + 2):
+                    ctx.run()
+                    st = ctx.stats()
+                    if i >= 2:
+                        ms.append((st["ms_endbuild"], st["ms_join"], st["ms_total"]))
+                m = np.mean(np.asarray(ms), axis=0)
+                print(json.dumps({"workload": a.workload, "reads": bam.n, "lib": label, "legacy": legacy, "ms_endbuild": float(m[0]),
+                                  "ms_join": float(m[1]), "ms_total": float(m[2]), "dups": int(st["n_duplicates"]),
+                                  "local_pairs": int(st["n_local_pairs"]), "leftovers": int(st["n_join_leftovers"]),
+                                  "local_retracted": int(st["n_local_retracted"]), "complex": int(st["n_complex_names"])}), flush=True)
 
-    if a.product:
-        run_all()
-    else:
+    run_all("product")
+    if not a.product:
         with dedup.testing_library():
-            run_all()
+            run_all("testing")
 
 
 if __name__ == "__main__":
