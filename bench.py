@@ -13,8 +13,9 @@ ends are exchanged, see openge_b200/sharded.py).
             stream, first kernel -> flags final), max over ranks
   e2e       reads/s through the C ABI from pinned HOST buffers: push (H2D) + run + flags (D2H),
             wall clock bracketed by device syncs
-  roofline  the onesweep radix-sort pass kernel: algorithmic bytes (32 per entry per launch) over
-            its CUDA-event duration, against MEASURED_PEAKS.json's HBM copy peak
+  roofline  per kernel (K1 end-build, K2 join, K3 sort pass, K4 select, K5 flags): SURVEY 8(d) algorithmic bytes over
+            the CUDA-event time of its launches, against MEASURED_PEAKS.json's HBM copy peak; the largest stage is the
+            line's `kernel`; `whole_path` is the 8(d) model over the whole step
   cpu_baseline  the compiled reference (oracle/_ref, its own threads) or the C oracle port on a
             bounded sample of the same workload, on this box's host cores
 
@@ -247,6 +248,154 @@ def bench_bgzf(ctx, rec, offs, text, contigs, n, flags_want, flags_pin, steps):
         comp_pin.free()
 
 
+
+# --------------------------------------------------------------------------------------- roofline
+def parse_bytes_per_read(rec, offs, n, sample=4000):
+    """SURVEY 8(d) stage A, from the workload's own records: 4 + 32 + l_read_name + 4 * n_cigar_op + l_seq (qualities;
+    the packed bases are not needed) + tag bytes up to and including the RG value.  Mean over a sample of records."""
+    idx = np.linspace(0, n - 1, num=min(n, sample)).astype(np.int64)
+    tot = 0
+    for i in idx:
+        o, e = int(offs[i]), int(offs[i + 1])
+        r = rec[o:e]
+        l_name = int(r[12])
+        n_cig = int(r[16]) | (int(r[17]) << 8)
+        l_seq = int.from_bytes(r[20:24].tobytes(), "little")
+        t = 36 + l_name + 4 * n_cig + (l_seq + 1) // 2 + l_seq
+        tags = r[t:].tobytes()
+        k = tags.find(b"RGZ")
+        rg = 0
+        if k >= 0:
+            z = tags.find(b"\0", k + 3)
+            rg = (z + 1) if z >= 0 else len(tags)
+        tot += 4 + 32 + l_name + 4 * n_cig + l_seq + rg
+    return tot / len(idx)
+
+
+def load_traffic():
+    """dram bytes per launch of the path's kernels from the committed ncu --set full captures (profiles/roofline_traffic.json:
+    {kernel: {dram_bytes_per_launch, reads, ...}}), or {}."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def roofline_table(n, a_parse, sts, peak, peak_src):
+    """Per-kernel roofline rows + the SURVEY 8(d) whole-path figure from the stats of the timed steps.
+    achieved = algorithmic bytes / CUDA-event time of that kernel's launches (profile_events), mean over the steps."""
+    def mean(f):
+        return float(np.mean([f(st) for st in sts]))
+    st = sts[-1]
+    n_frag, n_pairs, n_dup = st["n_frag_entries"], st["n_pair_entries"], st["n_duplicates"]
+    n_pe = 2 * n_pairs + st["n_join_leftovers"]
+    E_f, E_h, E_p = 16, 24, 32      # entry sizes fixed by the contract (SURVEY 8(d))
+    tr = load_traffic()
+    traffic = tr.get("kernels", {}) if tr.get("workload_reads") == n else {}      # a capture of another workload says nothing here
+    P_f, P_p = st["frag_sort_passes"], st["pair_sort_passes"]
+    frag_sorted = mean(lambda s: s["ms_sort_frag"]) > 0.01
+    ms_k = {k: mean(lambda s, k=k: s["ms_kernel"][k]) for k in st["ms_kernel"]}
+    pass_ms = mean(lambda s: s["ms_sort_pass_kernels"])
+    pass_launches = mean(lambda s: s["sort_pass_launches"])
+    pass_bytes = mean(lambda s: s["sort_pass_bytes"])
+    rows = [
+        ("K1 end-build", "endbuild_kernel", ms_k["endbuild"], n * a_parse + n_frag * E_f + n_pe * E_h, 1,
+         "A parse %.0f B/read + B emit (16 B per end, 24 B per map-eligible read)" % a_parse),
+        ("K2 mate join", "local_match_kernel + local_emit_kernel + mate_join_kernel + pair_check_kernel",
+         ms_k["match"] + ms_k["emit"] + ms_k["global_join"] + ms_k["check"], n_pe * 2 * E_h + n_pairs * E_p, 4,
+         "C join: 2 x 24 B per map-eligible read + 32 B per pair"),
+        ("K3 sort pass", "rs_pass_v2", pass_ms, pass_bytes, max(1.0, pass_launches),
+         "one LSD pass: 16 B read + 16 B written per entry (the contract's D stage counts 32-byte pair entries: see whole_path)"),
+        ("K4 select", "select_kernel", ms_k["select"], (n_pairs + (n_frag if frag_sorted else 0)) * 16 + 4 * n_dup, 1, "E: 16 B per sorted entry + 4 B per duplicate"),
+        ("K5 flags", "flags_kernel", ms_k["flags"], 4 * n, 1, "F: 2 B read + 2 B written per record"),
+    ]
+    stages = []
+    for label, kern, ms, alg, launches, what in rows:
+        names = [k.strip() for k in kern.split("+")]
+        dram = sum(traffic[k]["dram_bytes_per_launch"] * traffic[k]["launches_per_step"] for k in names if k in traffic) if all(k in traffic for k in names) else None
+        stages.append({"stage": label, "kernel": kern, "ms_per_step": ms, "algorithmic_bytes_per_step": float(alg),
+                       "achieved": (alg / 1e9) / (ms * 1e-3) if ms > 0 else None,
+                       "frac": (alg / 1e9) / (ms * 1e-3) / peak if ms > 0 else None,
+                       "launches_per_step": launches, "dram_bytes_per_step_ncu": dram,
+                       "dram_over_algorithmic": (dram / alg) if dram and alg else None, "bytes": what})
+    whole_alg = (n * a_parse + n_frag * E_f + n_pe * E_h + n_pe * 2 * E_h + n_pairs * E_p +
+                 (1 + 2 * P_f) * E_f * n_frag + (1 + 2 * P_p) * E_p * n_pairs + E_f * n_frag + E_p * n_pairs + 4 * n_dup + 4 * n)
+    # the key widths the contract's worked example assumes (frag 37 b -> 5 passes, pair 70 b -> 9 passes)
+    ms_total = mean(lambda s: s["ms_total"])
+    dom = max(stages, key=lambda r: r["ms_per_step"])
+    return {"bound": "hbm", "kernel": dom["kernel"] + " (" + dom["stage"] + ", the largest stage of the step)",
+            "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["frac"], "peak_source": peak_src,
+            "traffic": (dom["dram_bytes_per_step_ncu"] / dom["launches_per_step"]) if dom["dram_bytes_per_step_ncu"] else None,
+            "traffic_source": tr.get("source") if dom["dram_bytes_per_step_ncu"] else None,
+            "avg_launch_ms": dom["ms_per_step"] / dom["launches_per_step"],
+            "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_step"] / dom["launches_per_step"],
+            "timing": "CUDA events around every launch of the kernel on the library's stream inside the timed steps (profile_events)",
+            "stages": stages,
+            "whole_path": {"model": "SURVEY 8(d): A parse + B emit + C join + D sort ((1 + 2P) x entry, entry 16 B frag / 32 B pair, "
+                                    "P = the passes this run's keys need) + E select + F flags; the fragment D/E terms are counted even "
+                                    "when the reduced fragment pass skips that work",
+                           "algorithmic_bytes_per_read": whole_alg / n, "ms_per_step": ms_total,
+                           "achieved": (whole_alg / 1e9) / (ms_total * 1e-3), "frac": (whole_alg / 1e9) / (ms_total * 1e-3) / peak,
+                           "frac_of_nominal_8TBps": (whole_alg / 1e9) / (ms_total * 1e-3) / 8000.0}}
+
+
+class OracleCheck(threading.Thread):
+    """The C oracle on one workload in a host thread (ctypes releases the GIL), untimed and off the GPU's critical path:
+    joined before the result line is printed; the line carries the verdict."""
+
+    def __init__(self, rec, offs, text):
+        super().__init__(daemon=True)
+        self.rec, self.offs, self.text = rec, offs, text
+        self.flags = None
+        self.error = None
+        self.seconds = None
+
+    def run(self):
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import oracle
+            t0 = time.perf_counter()
+            self.flags = oracle.markdup(self.rec, self.offs, self.text)
+            self.seconds = time.perf_counter() - t0
+        except Exception as e:      # reported, not swallowed
+            self.error = "%s: %s" % (type(e).__name__, e)
+
+    def verdict(self, got):
+        self.join()
+        if self.error:
+            return {"checked": False, "error": self.error}
+        bad = int((got != self.flags).sum())
+        return {"checked": True, "records": int(len(got)), "mismatches": bad, "oracle_seconds_untimed": self.seconds}
+
+
+def side_configs(args, local_rank):
+    """Device-resident figures of the other single-GPU configs (C1, C3, C4 at their stated sizes), each checked record by
+    record against the oracle.  They are reported under config, not as bench lines."""
+    from openge_b200 import dedup, synth
+    out = {}
+    for name in ("C1", "C3", "C4"):
+        try:
+            bam = synth.make(name, 1.0)
+            chk = OracleCheck(bam.records, bam.offsets, bam.text)
+            chk.start()
+            with dedup.context_for(bam, device=local_rank) as ctx:
+                ctx.push(bam.records, bam.offsets)
+                ms = []
+                for i in range(2 + 3):
+                    ctx.run()
+                    if i >= 2:
+                        ms.append(ctx.stats()["ms_total"])
+                got = ctx.flags()
+                st = ctx.stats()
+            m = float(np.mean(ms))
+            out[name] = {"reads": bam.n, "ms_per_step": m, "reads_per_s": bam.n / (m * 1e-3), "duplicates": int(st["n_duplicates"]),
+                         "stage_ms": {k: st[k] for k in ("ms_endbuild", "ms_join", "ms_sort_pair", "ms_sort_frag", "ms_select", "ms_flags")},
+                         "oracle": chk.verdict(got)}
+        except Exception as ex:
+            out[name] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+    return out
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -254,15 +403,6 @@ def load_peaks():
         return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
-
-
-def load_traffic():
-    """dram bytes per launch of the pass kernel from the committed ncu --set full capture, or None."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            return json.load(f)
-    except Exception:
-        return None
 
 
 # --------------------------------------------------------------------------------------- CPU baselines
@@ -375,6 +515,12 @@ def run_ours(args):
     def push_all():
         ctx.push_async(rec.ctypes.data, rec.nbytes, offs_pin.ptr, n)
 
+    # ---- the oracle on the same records, in a host thread, untimed (joined before the line is printed)
+    check = None
+    if not args.no_oracle_check:
+        check = OracleCheck(rec, offs, text)
+        check.start()
+
     # ---- device-resident timing
     push_all()
     ctx.sync()
@@ -383,16 +529,14 @@ def run_ours(args):
     for _ in range(args.warmup):
         ctx.run()
     ctx.sync()
-    dev_ms, pass_ms, pass_bytes, pass_launches, launches = [], 0.0, 0, 0, 0
+    dev_ms, sts, launches = [], [], 0
     sampler.mark_begin()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         ctx.run()
         st = ctx.stats()
         dev_ms.append(st["ms_total"])
-        pass_ms += st["ms_sort_pass_kernels"]
-        pass_bytes += st["sort_pass_bytes"]
-        pass_launches += st["sort_pass_launches"]
+        sts.append(st)
         launches += st["launches"]
     ctx.sync()
     wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
@@ -427,18 +571,17 @@ def run_ours(args):
         except Exception as ex:      # an extra measurement must not take the contract line down
             e2e_bgzf = {"error": "%s: %s" % (type(ex).__name__, ex)}
 
-    # ---- roofline of the dominant kernel (onesweep pass)
+    # ---- roofline: per kernel, the largest stage on top, the SURVEY 8(d) whole-path figure next to it
     peak, peak_src = load_peaks()
-    achieved = (pass_bytes / 1e9) / (pass_ms * 1e-3) if pass_ms > 0 else 0.0
-    traffic = load_traffic()
-    roofline = {"bound": "hbm", "kernel": "rs_pass_v2 (onesweep radix-sort pass)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src,
-                "traffic": (traffic["ratio"] * pass_bytes / pass_launches) if traffic and pass_launches else None,
-                "traffic_source": ("profiles/roofline_traffic.json: dram bytes / algorithmic bytes = %.3f over the ncu --set full "
-                                   "capture of the same kernel at C2 size, applied to this run's bytes per launch" % traffic["ratio"]) if traffic else None,
-                "launches_timed": pass_launches,
-                "avg_launch_ms": pass_ms / pass_launches if pass_launches else None,
-                "algorithmic_bytes_per_launch": pass_bytes / pass_launches if pass_launches else None}
+    roofline = roofline_table(n, parse_bytes_per_read(rec, offs, n), sts, peak, peak_src)
+
+    # ---- the other single-GPU configs at their stated sizes, device-resident, each against the oracle
+    others = side_configs(args, local_rank) if not args.no_side_configs else None
+
+    # ---- parity verdict of the timed workload (the oracle thread started before the timing)
+    parity = check.verdict(flags_resident) if check else {"checked": False}
+    if parity.get("checked") and parity["mismatches"]:
+        raise SystemExit("bench.py: %d of %d flag words differ from the oracle" % (parity["mismatches"], n))
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1)
     cpu = None
@@ -462,7 +605,10 @@ def run_ours(args):
                    "duplicates_flagged": n_dup, "gen_seconds": t_gen, "stage_ms": {k: st[k] for k in (
                        "ms_endbuild", "ms_join", "ms_sort_pair", "ms_sort_frag", "ms_select", "ms_flags")},
                    "key_bits": [st["frag_key_bits"], st["pair_key_bits"]],
-                   "sort_passes": [st["frag_sort_passes"], st["pair_sort_passes"]]},
+                   "sort_passes": [st["frag_sort_passes"], st["pair_sort_passes"]],
+                   "join": {"pairs_settled_in_cta": st["n_local_pairs"], "records_to_global_join": st["n_join_leftovers"],
+                            "pairs_retracted_by_check": st["n_local_retracted"]},
+                   "parity_vs_oracle": parity, "other_configs": others},
         "e2e": {"value": n / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": int(rec.nbytes + offs.nbytes),
                 "d2h_bytes_per_step": int(n * 2), "ms_per_step": e2e_s * 1e3},
         "e2e_bgzf": e2e_bgzf,
@@ -490,6 +636,8 @@ def main():
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-oracle-check", action="store_true", help="skip the untimed record-by-record check against the C oracle")
+    ap.add_argument("--no-side-configs", action="store_true", help="skip the device-resident figures of C1 / C3 / C4")
     ap.add_argument("--legacy-join", action="store_true", help="A/B: separate end-build and whole-file hash join instead of the fused form")
     ap.add_argument("--no-bgzf", action="store_true", help="skip the extra end-to-end measurement from a BGZF-compressed BAM in host memory")
     args = ap.parse_args()

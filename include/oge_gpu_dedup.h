@@ -96,7 +96,12 @@ typedef struct oge_gpu_dedup_stats {
     /* fused end-build + in-CTA join: pairs settled inside the CTAs, records handed to the global join, local pairs the
      * check pass retracted (their names had leftovers) */
     uint64_t n_local_pairs, n_join_leftovers, n_local_retracted;
+    /* with profile_events: the kernels of the last run on their own (CUDA events around each launch, ms).  Order:
+     * OGE_K_ENDBUILD, OGE_K_MATCH (windowed join, K2a), OGE_K_EMIT (K2b), OGE_K_GLOBAL_JOIN (leftovers), OGE_K_CHECK,
+     * OGE_K_SELECT (all launches), OGE_K_FLAGS, OGE_K_SORT_HIST (histogram + scan of every sort). */
+    float ms_kernel[8];
 } oge_gpu_dedup_stats;
+enum { OGE_K_ENDBUILD = 0, OGE_K_MATCH, OGE_K_EMIT, OGE_K_GLOBAL_JOIN, OGE_K_CHECK, OGE_K_SELECT, OGE_K_FLAGS, OGE_K_SORT_HIST };
 
 /* Per-record view of the end-building kernel (buildReadEnds, mark_duplicates.cpp:147-164). */
 typedef struct oge_gpu_end {

@@ -82,6 +82,17 @@ struct oge_gpu_dedup_ctx {
     float *clk_slot[N_CLK];
     int clk_used = 0;
     cudaEvent_t pass_ev[2 * 48];      // profile_events: one pair per radix-sort pass launch
+    // profile_events: pairs around the other kernels of a run; k_slot[i] = which OGE_K_* figure pair i adds to
+    static constexpr int N_KEV = 24;
+    cudaEvent_t k_ev[2 * N_KEV];
+    int k_slot[N_KEV];
+    int k_used = 0;
+    void k_begin(int slot, cudaStream_t s) {
+        if (cfg.profile_events && k_used < N_KEV) { k_slot[k_used] = slot; cudaEventRecord(k_ev[2 * k_used], s); }
+    }
+    void k_end(cudaStream_t s) {
+        if (cfg.profile_events && k_used < N_KEV) { cudaEventRecord(k_ev[2 * k_used + 1], s); k_used++; }
+    }
 
     // resident input
     DevBuf<uint8_t> rec;

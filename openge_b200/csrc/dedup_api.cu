@@ -221,6 +221,7 @@ int oge_gpu_dedup_create(const oge_gpu_dedup_config *cfg, oge_gpu_dedup_ctx **ou
         for (auto &e : c->ev) cudaEventCreate(&e);
         for (auto &e : c->clk_ev) cudaEventCreate(&e);
         for (auto &e : c->pass_ev) { e = nullptr; if (cfg->profile_events) cudaEventCreate(&e); }
+        for (auto &e : c->k_ev) { e = nullptr; if (cfg->profile_events) cudaEventCreate(&e); }
         if (cudaHostAlloc((void **) &c->h_counters, CNT_N * 4, cudaHostAllocDefault) != cudaSuccess) {
             rc = fail_cuda(cudaGetLastError(), "cudaHostAlloc", __FILE__, __LINE__);
             break;
@@ -252,6 +253,7 @@ void oge_gpu_dedup_destroy(oge_gpu_dedup_ctx *c) {
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->clk_ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->pass_ev) if (e) cudaEventDestroy(e);
+    for (auto &e : c->k_ev) if (e) cudaEventDestroy(e);
     if (c->copy_done) cudaEventDestroy(c->copy_done);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -581,7 +583,10 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     jp.mate_of = c->mate_of.p; jp.cplx = c->sortbuf.p;
     jp.counters = c->counters.p; jp.rg = rg_table(c); jp.kl = c->kl; jp.verify_names = c->cfg.verify_names;
     jp.list = nullptr; jp.n_list = 0;
+    c->k_used = 0;
+    c->k_begin(OGE_K_ENDBUILD, s);
     if ((rc = launch_endbuild(eb, (uint32_t) (c->rec_bytes / n), c->sms, s, &launches))) return rc;
+    c->k_end(s);
     OGE_CUDA_TRY(cudaEventRecord(c->ev[1], s));
     if (fused) {
         // windowed join: every CTA pairs the reads of its contiguous record range in shared memory (no sizes needed from K1:
@@ -601,7 +606,7 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
         lj.pair_cap = (uint32_t) pair_cap; lj.far_cap = (uint32_t) far_cap;
         lj.mate_of = c->mate_of.p; lj.left = c->left.p; lj.n_buckets = 0; lj.tiles_per_cta = 0;
         jp.table = nullptr; jp.n_slots = 0; jp.pair = c->pair.p; jp.pair_far = c->pairf.p; jp.cplx_slots = nullptr;
-        if ((rc = launch_local_join(jp, lj, c->sms, s, &launches))) return rc;
+        if ((rc = launch_local_join(jp, lj, c->sms, s, &launches, c))) return rc;
     }
     OGE_CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, s));
     OGE_CUDA_TRY(cudaStreamSynchronize(s));
@@ -636,10 +641,14 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
         jp.table = c->table.p; jp.n_slots = n_slots;
         jp.pair = c->pair.p; jp.pair_far = c->pairf.p; jp.cplx_slots = c->cplx_slots.p;
         if (fused) { jp.list = c->left.p; jp.n_list = (uint32_t) n_left; }
+        c->k_begin(OGE_K_GLOBAL_JOIN, s);
         if ((rc = launch_mate_join(jp, s, &launches))) return rc;
+        c->k_end(s);
         if (fused) {
+            c->k_begin(OGE_K_CHECK, s);
             if ((rc = launch_pair_check(jp, c->pair_hk.p, n_loc, false, s, &launches))) return rc;
             if ((rc = launch_pair_check(jp, c->pairf_hk.p, n_loc_far, true, s, &launches))) return rc;
+            c->k_end(s);
         }
         OGE_CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, s));
         OGE_CUDA_TRY(cudaStreamSynchronize(s));
@@ -694,11 +703,15 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     OGE_CUDA_TRY(cudaEventRecord(c->ev[3], s));
     if (n_pairs > n_retracted) {      // retracted provisional pairs are all-ones entries: they sorted to the tail
         sp.sorted = sorted_pairs; sp.n_max = (uint32_t) (n_pairs - n_retracted);
+        c->k_begin(OGE_K_SELECT, s);
         if ((rc = launch_select_pairs(sp, false, s, &launches))) return rc;
+        c->k_end(s);
     }
     if (n_far > n_far_retracted) {
         sp.sorted = sorted_far; sp.n_max = (uint32_t) (n_far - n_far_retracted);
+        c->k_begin(OGE_K_SELECT, s);
         if ((rc = launch_select_pairs(sp, true, s, &launches))) return rc;
+        c->k_end(s);
     }
     OGE_CUDA_TRY(cudaEventRecord(c->ev[4], s));
 
@@ -746,7 +759,9 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     OGE_CUDA_TRY(cudaEventRecord(c->ev[5], s));
     if (frag_mode && n_fsel) {
         sp.sorted = sorted_frags; sp.n_max = (uint32_t) n_fsel;
+        c->k_begin(OGE_K_SELECT, s);
         if ((rc = launch_select_frags(sp, s, &launches))) return rc;
+        c->k_end(s);
     }
     OGE_CUDA_TRY(cudaEventRecord(c->ev[6], s));
 
@@ -754,7 +769,9 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     FlagParams fp;
     fp.rec = c->recs(); fp.off = c->off.p; fp.n = n; fp.flag_in = c->flag_in.p; fp.flag_out = c->flag_out.p;
     fp.dup = c->dup.p; fp.counters = c->counters.p; fp.quiet_index_bug = c->cfg.compat_quiet_index_bug;
+    c->k_begin(OGE_K_FLAGS, s);
     if ((rc = launch_flags(fp, s, &launches))) return rc;
+    c->k_end(s);
     OGE_CUDA_TRY(cudaEventRecord(c->ev[7], s));
     OGE_CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, s));
     OGE_CUDA_TRY(cudaStreamSynchronize(s));
@@ -791,6 +808,7 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     st.launches = launches;
     for (int i = 0; i < timer.used; i++) st.ms_sort_pass_kernels += ms_between(c->pass_ev[2 * i], c->pass_ev[2 * i + 1]);
     st.sort_pass_launches = timer.used;
+    for (int i = 0; i < c->k_used; i++) st.ms_kernel[c->k_slot[i]] += ms_between(c->k_ev[2 * i], c->k_ev[2 * i + 1]);
     st.sort_pass_bytes = timer.bytes;
     c->ran = true;
     return OGE_OK;

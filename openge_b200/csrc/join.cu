@@ -21,7 +21,7 @@
 // hundred records apart, so the second touch of a slot and the mate's name are L2 hits.
 #include <stdlib.h>
 
-#include "kernels.cuh"
+#include "ctx.cuh"
 #include "pairing.cuh"
 
 namespace oge {
@@ -624,7 +624,7 @@ void local_join_shape(uint64_t n, int sms, uint32_t *grid_out, uint32_t *tiles_p
     *tiles_per_cta = (uint32_t) tpc;
 }
 
-int launch_local_join(const JoinParams &P, LocalJoinParams J, int sms, cudaStream_t stream, uint64_t *launches) {
+int launch_local_join(const JoinParams &P, LocalJoinParams J, int sms, cudaStream_t stream, uint64_t *launches, oge_gpu_dedup_ctx *c) {
     if (P.n == 0) return 0;
     uint32_t grid = 0, tpc = 0;
     local_join_shape(P.n, sms, &grid, &tpc);
@@ -633,9 +633,12 @@ int launch_local_join(const JoinParams &P, LocalJoinParams J, int sms, cudaStrea
     J.couples_per_cta = tpc * (LJ_TILE / 2);
     const size_t smem = (size_t) LJ_BUCKETS * LJ_WAYS * LJ_ENTRY_BYTES;
     OGE_CUDA_TRY(cudaFuncSetAttribute(local_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    if (c) c->k_begin(OGE_K_MATCH, stream);
     local_match_kernel<<<grid, LJ_THREADS, smem, stream>>>(P, J);
+    if (c) { c->k_end(stream); c->k_begin(OGE_K_EMIT, stream); }
     const uint64_t slots = (uint64_t) grid * J.couples_per_cta;
     local_emit_kernel<<<(uint32_t) ((slots + JOIN_THREADS - 1) / JOIN_THREADS), JOIN_THREADS, 0, stream>>>(P, J, grid);
+    if (c) c->k_end(stream);
     *launches += 2;
     OGE_CUDA_TRY(cudaGetLastError());
     return 0;

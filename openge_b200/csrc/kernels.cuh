@@ -2,6 +2,8 @@
 #pragma once
 #include "common.cuh"
 
+struct oge_gpu_dedup_ctx;      // ctx.cuh
+
 namespace oge {
 
 // ---- K1 end-build (endbuild.cu) ---------------------------------------------------------------
@@ -107,7 +109,8 @@ struct JoinParams {
 
 int launch_mate_join(const JoinParams &P, cudaStream_t stream, uint64_t *launches);
 // windowed form: pairs settled inside the CTAs' contiguous record ranges; the rest goes on J.left
-int launch_local_join(const JoinParams &P, LocalJoinParams J, int sms, cudaStream_t stream, uint64_t *launches);
+int launch_local_join(const JoinParams &P, LocalJoinParams J, int sms, cudaStream_t stream, uint64_t *launches,
+                      ::oge_gpu_dedup_ctx *timing = nullptr /* profile_events: brackets the two launches */);
 // fused form: is the key hash of a pair formed inside a CTA among the records the global join has seen?  Then the pair
 // is retracted and its two records (with whatever the slot held) go to the exact path.
 int launch_pair_check(const JoinParams &P, const uint64_t *pair_hk, uint32_t n_pairs, bool far, cudaStream_t stream, uint64_t *launches);

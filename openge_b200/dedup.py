@@ -47,10 +47,16 @@ class Stats(C.Structure):
                 ("ms_inflate", C.c_float), ("ms_frame", C.c_float), ("inflate_blocks", C.c_uint64),
                 ("inflate_bytes_in", C.c_uint64), ("inflate_bytes_out", C.c_uint64), ("frame_repairs", C.c_uint64),
                 ("ms_inflate_h2d", C.c_float), ("ms_inflate_d2h", C.c_float),
-                ("n_local_pairs", C.c_uint64), ("n_join_leftovers", C.c_uint64), ("n_local_retracted", C.c_uint64)]
+                ("n_local_pairs", C.c_uint64), ("n_join_leftovers", C.c_uint64), ("n_local_retracted", C.c_uint64),
+                ("ms_kernel", C.c_float * 8)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["ms_kernel"] = dict(zip(KERNEL_NAMES, (float(x) for x in self.ms_kernel)))
+        return d
+
+
+KERNEL_NAMES = ("endbuild", "match", "emit", "global_join", "check", "select", "flags", "sort_hist")      # OGE_K_* order
 
 
 FLAGSTAT_FIELDS = ("reads", "mapped", "forward", "reverse", "failed_qc", "duplicates", "paired", "proper_pair",

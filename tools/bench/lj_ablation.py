@@ -22,19 +22,21 @@ def main():
     ap.add_argument("--scale", type=float, default=0.4)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--dbg", default="0,1,2,4,8,12")
-    ap.add_argument("--product", action="store_true", help="use the product library (dbg is ignored there)")
+    ap.add_argument("--product", action="store_true", help="the product library only")
+    ap.add_argument("--fused-only", action="store_true", help="skip the legacy (whole-file hash join) form")
+    ap.add_argument("--warm", type=int, default=2)
     a = ap.parse_args()
     bam = synth.make(a.workload, a.scale)
 
     def run_all(label):
-        for legacy in ((False, True) if label == "product" else (False,)):
+        for legacy in ((False, True) if label == "product" and not a.fused_only else (False,)):
             with dedup.context_for(bam, legacy_join=legacy) as ctx:
                 ctx.push(bam.records, bam.offsets)
                 ms = []
-                for i in range(a.steps + 2):
+                for i in range(a.steps + a.warm):
                     ctx.run()
                     st = ctx.stats()
-                    if i >= 2:
+                    if i >= a.warm:
                         ms.append((st["ms_endbuild"], st["ms_join"], st["ms_total"]))
                 m = np.mean(np.asarray(ms), axis=0)
                 print(json.dumps({"workload": a.workload, "reads": bam.n, "lib": label, "legacy": legacy, "ms_endbuild": float(m[0]),
