@@ -164,6 +164,18 @@ int oge_gpu_dedup_offsets(oge_gpu_dedup_ctx *ctx, uint64_t *out, uint64_t n_plus
  * may be called again on the same resident records. */
 int oge_gpu_dedup_run(oge_gpu_dedup_ctx *ctx);
 
+/* ReadSorter in front of MarkDuplicates (`openge mergesort -M`: commands/command_mergesort.cpp:68-100,
+ * algorithms/read_sorter.cpp:203-205,248-): sorts the resident records by coordinate on the device, in the order of
+ * Sort::ByPosition (util/bamtools/Sort.h:108-133): refID (records without one last), position, strand (forward first),
+ * name, flag.  Where the reference falls through to comparing the ADDRESSES of its heap objects (exact copies, and the
+ * order inside the unplaced tail) the input order is kept.  Afterwards the context holds the records in sorted order:
+ * run / flags / pull / flagstats refer to that order; oge_gpu_dedup_sort_order gives the permutation
+ * (perm[k] = input ordinal of the record now at position k). */
+int oge_gpu_dedup_sort(oge_gpu_dedup_ctx *ctx);
+int oge_gpu_dedup_sort_order(oge_gpu_dedup_ctx *ctx, uint32_t *perm_out, uint64_t n);
+/* what the last sort did: records that tied on (refID, position, strand), name-refinement rounds, kernel launches, device ms */
+int oge_gpu_dedup_sort_stats(oge_gpu_dedup_ctx *ctx, uint64_t *n_tied, uint64_t *rounds, uint64_t *launches, float *ms);
+
 /* Output side of runInternal (:443-465): the flag word of every record, in input order. */
 int oge_gpu_dedup_flags(oge_gpu_dedup_ctx *ctx, uint16_t *out, uint64_t n);
 
@@ -252,6 +264,9 @@ int oge_gpu_device_count(void);
 
 const char *oge_gpu_last_error(void);
 int oge_gpu_abi_version(void);
+/* sizeof of the structs of this header as the library was compiled: 0 config, 1 stats, 2 oge_gpu_end, 3 flagstats
+ * (a binding checks its own layout against these) */
+int oge_gpu_sizeof(int which);
 
 #ifdef __cplusplus
 }

@@ -124,6 +124,13 @@ struct oge_gpu_dedup_ctx {
     uint32_t *h_counters = nullptr;      // pinned
     uint64_t h_counters_k1_unpaired = 0;
 
+    // coordinate sort in front of the run (coordsort.cu)
+    DevBuf<uint32_t> cs_u32, perm;
+    DevBuf<uint64_t> cs_bsum, off2;
+    DevBuf<uint8_t> rec2;
+    uint64_t sort_stats[3] = {0, 0, 0};      // tied records, refinement rounds, kernel launches of the last sort
+    float ms_sort_records = 0;
+
     KeyLayout kl;
     bool ran = false;
     oge::ShardState sh;

@@ -164,6 +164,16 @@ extern "C" {
 
 int oge_gpu_abi_version(void) { return OGE_GPU_DEDUP_ABI_VERSION; }
 
+int oge_gpu_sizeof(int which) {
+    switch (which) {
+        case 0: return (int) sizeof(oge_gpu_dedup_config);
+        case 1: return (int) sizeof(oge_gpu_dedup_stats);
+        case 2: return (int) sizeof(oge_gpu_end);
+        case 3: return (int) sizeof(oge_gpu_flagstats);
+        default: return -1;
+    }
+}
+
 const char *oge_gpu_last_error(void) { return g_err; }
 
 int oge_gpu_device_count(void) {
@@ -248,7 +258,8 @@ void oge_gpu_dedup_destroy(oge_gpu_dedup_ctx *c) {
     c->rec.release(); c->off.release(); c->rg_bytes.release(); c->rg_off.release(); c->rg_lib.release();
     c->frag.release(); c->sortbuf.release(); c->pair.release(); c->pair2.release(); c->pairf.release(); c->pairf2.release(); c->ufrag.release(); c->ufrag2.release(); c->uset.release(); c->hk.release();
     c->tag.release(); c->flag_in.release(); c->flag_out.release(); c->dup.release(); c->scratch.release();
-    c->cplx_state.release(); c->cplx_slots.release(); c->cplx_sort.release(); c->pair_hk.release(); c->pairf_hk.release(); c->left.release(); c->couples.release(); c->couple_count.release(); c->mate_of.release(); c->counters.release(); c->table.release();
+    c->cplx_state.release(); c->cplx_slots.release(); c->cplx_sort.release(); c->pair_hk.release(); c->pairf_hk.release(); c->left.release(); c->couples.release(); c->couple_count.release();
+    c->cs_u32.release(); c->perm.release(); c->cs_bsum.release(); c->off2.release(); c->rec2.release(); c->mate_of.release(); c->counters.release(); c->table.release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->clk_ev) if (e) cudaEventDestroy(e);

@@ -73,7 +73,8 @@ EXPORTS = ["oge_gpu_dedup_create", "oge_gpu_dedup_destroy", "oge_gpu_dedup_set_r
            "oge_gpu_dedup_device_ptrs", "oge_gpu_host_alloc", "oge_gpu_host_free", "oge_gpu_device_count",
            "oge_gpu_last_error", "oge_gpu_abi_version", "oge_gpu_debug_sort128", "oge_gpu_debug_sort_bench",
            "oge_gpu_set_sort_variant", "oge_gpu_set_inflate_kernel", "oge_gpu_shard_setup", "oge_gpu_shard_begin", "oge_gpu_shard_probe",
-           "oge_gpu_shard_finish", "oge_gpu_shard_apply", "oge_gpu_copy_d2d"]
+           "oge_gpu_shard_finish", "oge_gpu_shard_apply", "oge_gpu_copy_d2d", "oge_gpu_dedup_sort", "oge_gpu_dedup_sort_order",
+           "oge_gpu_dedup_sort_stats", "oge_gpu_sizeof"]
 
 
 class DedupError(RuntimeError):
@@ -132,6 +133,9 @@ def _load(path):
         L.oge_gpu_dedup_frame.argtypes = [vp, C.POINTER(u64)]
         L.oge_gpu_dedup_offsets.argtypes = [vp, vp, u64]
         L.oge_gpu_dedup_run.argtypes = [vp]
+        L.oge_gpu_dedup_sort.argtypes = [vp]
+        L.oge_gpu_dedup_sort_order.argtypes = [vp, vp, u64]
+        L.oge_gpu_dedup_sort_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_float)]
         L.oge_gpu_dedup_flags.argtypes = [vp, vp, u64]
         L.oge_gpu_dedup_pull.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64), C.POINTER(u64)]
         L.oge_gpu_dedup_reset.argtypes = [vp]
@@ -157,6 +161,10 @@ def _load(path):
         L.oge_gpu_shard_apply.argtypes = [vp, vp, u64]
         for name in EXPORTS:
             getattr(L, name)
+        L.oge_gpu_sizeof.argtypes = [C.c_int]
+        if L.oge_gpu_sizeof(0) != C.sizeof(Config) or L.oge_gpu_sizeof(1) != C.sizeof(Stats):
+            raise ImportError("%s was built from another oge_gpu_dedup.h: config %d / %d bytes, stats %d / %d bytes" % (
+                os.path.basename(path), L.oge_gpu_sizeof(0), C.sizeof(Config), L.oge_gpu_sizeof(1), C.sizeof(Stats)))
     return L
 
 
@@ -269,6 +277,21 @@ class DedupContext:
         _check(lib().oge_gpu_dedup_sync(self._h))      # numpy buffers may go away
         self.n += nrec
         self.nbytes += records.nbytes
+
+    def sort(self):
+        """ReadSorter in front of MarkDuplicates (`openge mergesort -M`): coordinate-sort the resident records on the device.
+        Afterwards run / flags / pull refer to the sorted order; sort_order() gives the permutation."""
+        _check(lib().oge_gpu_dedup_sort(self._h))
+
+    def sort_order(self) -> np.ndarray:
+        out = np.zeros(max(1, self.n), dtype=np.uint32)
+        _check(lib().oge_gpu_dedup_sort_order(self._h, out.ctypes.data, self.n))
+        return out[: self.n]
+
+    def sort_stats(self) -> dict:
+        a, b, c, ms = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_float()
+        _check(lib().oge_gpu_dedup_sort_stats(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(ms)))
+        return {"tied_records": a.value, "refinement_rounds": b.value, "launches": c.value, "ms": ms.value}
 
     def push_async(self, records_ptr, nbytes, offsets_ptr, nrec):
         _check(lib().oge_gpu_dedup_push(self._h, records_ptr, nbytes, offsets_ptr, nrec))

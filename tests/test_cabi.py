@@ -28,9 +28,10 @@ def test_header_symbols_exported():
 def test_abi_version_and_struct_sizes():
     L = dedup.lib()
     assert L.oge_gpu_abi_version() == dedup.ABI_VERSION
-    assert C.sizeof(dedup.Config) == 80
-    assert C.sizeof(dedup.Stats) == 168
-    assert dedup.END_DTYPE.itemsize == 28
+    assert C.sizeof(dedup.Config) == 80 == L.oge_gpu_sizeof(0)
+    assert C.sizeof(dedup.Stats) == L.oge_gpu_sizeof(1)
+    assert dedup.END_DTYPE.itemsize == 28 == L.oge_gpu_sizeof(2)
+    assert L.oge_gpu_sizeof(3) == 13 * 8
 
 
 def test_no_cpu_fallback_without_device():
