@@ -5,9 +5,10 @@
 
 A step = one pass of the whole hot path (end-build, mate join, both radix sorts, select, flag
 write) over one synthetic coordinate-sorted paired-end BAM batch.  At N=1 the workload is
-config C2 of BASELINE.json (50 M reads, 2x150 bp, ~10 % duplicates); at N>1 every rank holds
-one coordinate range of an N x C2-sized file (weak scaling; cross-shard mates and boundary
-ends are exchanged, see openge_b200/sharded.py).
+config C2 of BASELINE.json (50 M reads, 2x150 bp, ~10 % duplicates); at N>1 the workload is config C5
+(800 M reads, 30x WGS shape) range-sharded by coordinate: every rank holds 1/8 of it (100 M reads: weak
+scaling, the whole of C5 at N=8), the cuts fall inside contigs, and the ends that straddle ranks are
+exchanged with NCCL all-to-alls (openge_b200/sharded.py).
 
   value     reads/s with the records resident in HBM; device time (CUDA events on the library's
             stream, first kernel -> flags final), max over ranks
@@ -340,6 +341,13 @@ def roofline_table(n, a_parse, sts, peak, peak_src):
                            "frac_of_nominal_8TBps": (whole_alg / 1e9) / (ms_total * 1e-3) / 8000.0}}
 
 
+def oracle_flags(records, offsets, text):
+    """The C oracle (test infrastructure) over one file: the checker of the untimed parity passes."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    return oracle.markdup(records, offsets, text)
+
+
 class OracleCheck(threading.Thread):
     """The C oracle on one workload in a host thread (ctypes releases the GIL), untimed and off the GPU's critical path:
     joined before the result line is printed; the line carries the verdict."""
@@ -633,7 +641,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--workload", default=None, help="default: C2 on one GPU (the configuration the metric is quoted on), C5 range-sharded on several")
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-oracle-check", action="store_true", help="skip the untimed record-by-record check against the C oracle")
@@ -641,6 +649,8 @@ def main():
     ap.add_argument("--legacy-join", action="store_true", help="A/B: separate end-build and whole-file hash join instead of the fused form")
     ap.add_argument("--no-bgzf", action="store_true", help="skip the extra end-to-end measurement from a BGZF-compressed BAM in host memory")
     args = ap.parse_args()
+    if args.workload is None:
+        args.workload = "C2" if max(args.gpus, env_int("WORLD_SIZE", 1)) <= 1 else "C5"
     if args.warmup < 3 and args.impl == "ours":
         sys.stderr.write("[bench] note: fewer than 3 warm-up steps\n")
     if args.impl == "reference":

@@ -76,6 +76,10 @@ int oge_bam_frame_records(oge_bam_file *f);
 /* ... or take the offsets from whoever framed the records already (oge_gpu_dedup_frame + oge_gpu_dedup_offsets). */
 int oge_bam_adopt_offsets(oge_bam_file *f, const uint64_t *offsets, uint64_t nrec);
 
+/* What ReadSorter does to the header it hands on (algorithms/read_sorter.cpp:256-258: setSortOrder): the @HD SO value the
+ * stored file will carry -- "coordinate" after oge_gpu_dedup_sort. */
+int oge_bam_set_sort_order(oge_bam_file *f, const char *so);
+
 const char *oge_bam_header_text(const oge_bam_file *f);        /* as stored in the file */
 int32_t oge_bam_n_ref(const oge_bam_file *f);
 const char *oge_bam_ref_name(const oge_bam_file *f, int32_t i);

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define OGE_GPU_DEDUP_ABI_VERSION 6
+#define OGE_GPU_DEDUP_ABI_VERSION 7
 
 enum {
     OGE_OK = 0,
@@ -218,29 +218,42 @@ int oge_gpu_debug_sort128(int device, void *entries, uint64_t n, int bit_lo, int
  * The reference is a single process; these entry points exist so that G ranks, each holding a contiguous
  * record range of one coordinate-sorted file, produce exactly the flags of its single-stream run
  * (`openge dedup --nosplit -v`; the reference's own split mode, command_dedup.cpp:71-95, does not: SURVEY F2).
- * Between the calls the host delivers every rank's output lists to every rank (all-to-all over NCCL): three
- * exchanges per run.  All pointers are DEVICE pointers; lists are arrays of 64-byte (published), 32-byte
- * (routed) or 4-byte (marks) items, valid until the next call on the context.  Order: setup once, then per
- * run begin -> probe -> finish -> apply; afterwards oge_gpu_dedup_flags / _pull / _get_stats. */
+ * Between the calls the host moves small lists with all-to-all exchanges (NCCL all_to_all_single with uneven
+ * splits): every output list comes ORDERED BY DESTINATION RANK with its per-destination item counts, every
+ * input list is what the other ranks (and this one) addressed to this rank, concatenated.  Only the 8-byte key
+ * hashes of the published entries go to every rank.  All pointers are DEVICE pointers, valid until the next
+ * call on the context.  Items: published entry = entry_bytes (below), routed end entry = 32 bytes, mark = 4,
+ * hash = 8.  Order: setup, key_bytes + set_entry_bytes once; then per run
+ * begin -> probe -> replay -> finish -> apply; afterwards oge_gpu_dedup_flags / _pull / _get_stats. */
 int oge_gpu_shard_setup(oge_gpu_dedup_ctx *ctx, uint64_t global_n, const uint64_t *bases /* world + 1 */,
                         const int32_t *split_ref, const int32_t *split_pos /* world - 1: first record of ranks 1.. */);
-/* K1 + local mate join (mark_duplicates.cpp:192-256 on the shard).  out: the records whose RG:name key was not
- * seen exactly twice on this rank (published, round 1), and copies of the fragment ends whose (refID,
- * unclipped coordinate) lies in another rank's key range. */
-int oge_gpu_shard_begin(oge_gpu_dedup_ctx *ctx, void **pub_dev, uint64_t *n_pub, void **frag_route_dev, uint64_t *n_frag_route);
-/* in: round-1 entries and routed fragment ends of all ranks.  A local couple of a name published elsewhere is
- * retracted and published (round 2); the fragment K3 + K4 (mark_duplicates.cpp:262-271, 371-390) start on a
- * side stream; out also: pair ends whose key lies in another rank's range. */
-int oge_gpu_shard_probe(oge_gpu_dedup_ctx *ctx, const void *pub_all_dev, uint64_t n_pub_all, const void *frag_route_all_dev,
-                        uint64_t n_frag_route_all, void **pub2_dev, uint64_t *n_pub2, void **pair_route_dev, uint64_t *n_pair_route);
-/* in: every published entry of both rounds and the routed pair ends of all ranks.  Replays ReadEndsMap's toggle
- * (picard_structures.h:87-96) over the published set in global file order, keeps the pairs whose key range this
- * rank owns, pair K3 + K4 (:336-355, 488-507).  out: global ordinals to mark that belong to other ranks
- * (two lists: from pairs, from fragments). */
-int oge_gpu_shard_finish(oge_gpu_dedup_ctx *ctx, const void *pub_both_dev, uint64_t n_pub_both, const void *pair_route_all_dev,
-                         uint64_t n_pair_route_all, void **marks_dev, uint64_t *n_marks, void **marks_frag_dev, uint64_t *n_marks_frag);
-/* in: marks of all ranks.  K5 (mark_duplicates.cpp:443-465). */
-int oge_gpu_shard_apply(oge_gpu_dedup_ctx *ctx, const void *marks_all_dev, uint64_t n_all);
+/* A published entry carries its whole pairing key RG + ":" + name (mark_duplicates.cpp:210-214), so that the rank
+ * that owns the name compares keys byte by byte whatever their length: key_bytes = the longest key among this
+ * rank's records; every rank then sets entry_bytes = 32 + the largest key_bytes of all ranks rounded up to 32. */
+int oge_gpu_shard_key_bytes(oge_gpu_dedup_ctx *ctx, uint32_t *max_key_bytes);
+int oge_gpu_shard_set_entry_bytes(oge_gpu_dedup_ctx *ctx, uint32_t entry_bytes);
+/* K1 + mate join of the shard (mark_duplicates.cpp:192-256 on its records).  out: the records whose RG:name key
+ * was not seen exactly twice on this rank -> the rank that owns the name (hash mod world); their key hashes ->
+ * every rank; copies of the fragment ends whose (refID, unclipped coordinate) lies in another rank's key range
+ * -> that rank. */
+int oge_gpu_shard_begin(oge_gpu_dedup_ctx *ctx, void **pub_dev, uint64_t *pub_counts /* world */, void **hash_dev, uint64_t *n_hash,
+                        void **frag_route_dev, uint64_t *frag_route_counts /* world */);
+/* in: the key hashes the OTHER ranks published; the fragment ends routed to this rank.  A local pair of a name
+ * published elsewhere is retracted and its two records published (round 2, to the name's owner); the fragment
+ * K3 + K4 (mark_duplicates.cpp:262-271, 371-390) start on a side stream; out also: local pair ends whose key
+ * lies in another rank's range -> that rank. */
+int oge_gpu_shard_probe(oge_gpu_dedup_ctx *ctx, const void *hash_in_dev, uint64_t n_hash_in, const void *frag_route_in_dev,
+                        uint64_t n_frag_route_in, void **pub2_dev, uint64_t *pub2_counts, void **pair_route_dev, uint64_t *pair_route_counts);
+/* in: every published entry (both rounds, all ranks) of the names this rank owns.  Replays ReadEndsMap's toggle
+ * (picard_structures.h:87-96) over them in global file order; pairs whose key range this rank owns join its
+ * lists, out: the others -> the rank that owns their key range. */
+int oge_gpu_shard_replay(oge_gpu_dedup_ctx *ctx, const void *pub_in_dev, uint64_t n_pub_in, void **owner_route_dev, uint64_t *owner_route_counts);
+/* in: the pair ends routed to this rank (probe and replay outputs of all ranks).  Pair K3 + K4 (:336-355, 488-507).
+ * out: global ordinals to mark -> the rank that holds the record. */
+int oge_gpu_shard_finish(oge_gpu_dedup_ctx *ctx, const void *pair_route_in_dev, uint64_t n_pair_route_in, void **marks_dev,
+                         uint64_t *marks_counts);
+/* in: the marks addressed to this rank.  K5 (mark_duplicates.cpp:443-465). */
+int oge_gpu_shard_apply(oge_gpu_dedup_ctx *ctx, const void *marks_in_dev, uint64_t n_marks_in);
 
 /* Measurement hook for K3 alone: sorts n device-generated entries (mode 0 uniform random, 1 = high key
  * bits follow the ordinal like a coordinate-sorted file) `reps` times after one warm-up; reports the

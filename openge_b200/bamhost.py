@@ -20,7 +20,7 @@ ERRORS = {-1: "OGE_BAM_ERR_IO", -2: "OGE_BAM_ERR_FORMAT", -3: "OGE_BAM_ERR_NOMEM
 EXPORTS = ["oge_bam_load", "oge_bam_open_bgzf", "oge_bam_bgzf_index", "oge_bam_records_buffer", "oge_bam_frame_records", "oge_bam_adopt_offsets", "oge_bam_close", "oge_bam_header_text", "oge_bam_n_ref", "oge_bam_ref_name", "oge_bam_ref_len",
            "oge_bam_records", "oge_bam_records_bytes", "oge_bam_offsets", "oge_bam_n_records", "oge_bam_library_table",
            "oge_bam_apply_flags", "oge_bam_store", "oge_bam_timings", "oge_bgzf_decompress", "oge_bgzf_compress",
-           "oge_bam_header_render", "oge_bam_buffer_free", "oge_bam_last_error"]
+           "oge_bam_header_render", "oge_bam_buffer_free", "oge_bam_last_error", "oge_bam_set_sort_order"]
 
 
 class BamHostError(RuntimeError):
@@ -47,6 +47,7 @@ def lib():
         L.oge_bam_records_buffer.restype = vp
         L.oge_bam_frame_records.argtypes = [vp]
         L.oge_bam_adopt_offsets.argtypes = [vp, vp, u64]
+        L.oge_bam_set_sort_order.argtypes = [vp, C.c_char_p]
         L.oge_bam_close.argtypes = [vp]
         L.oge_bam_close.restype = None
         L.oge_bam_header_text.argtypes = [vp]
@@ -153,6 +154,10 @@ class HostBam:
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         _check(lib().oge_bam_adopt_offsets(self._h, offsets.ctypes.data, len(offsets) - 1))
 
+    def set_sort_order(self, so: str):
+        """@HD SO of the stored file (what ReadSorter does to the header it hands on, read_sorter.cpp:256-258)."""
+        _check(lib().oge_bam_set_sort_order(self._h, so.encode()))
+
     def close(self):
         if self._h:
             lib().oge_bam_close(self._h)
@@ -224,9 +229,10 @@ class HostBam:
 
 def dedup_file(in_path: str, out_path: str, remove_duplicates: bool = False, level: int = 6, format: str | None = None,
                pg_command_line: str | None = None, threads: int = 0, device: int = 0, gpu_inflate: bool = True,
-               pinned: bool = False) -> dict:
+               pinned: bool = False, sort: bool = False) -> dict:
     """`openge dedup in.bam -o out.bam` on the GPU, file to file.  -> stats (dedup counters, flag statistics, timings).
-    gpu_inflate: the BGZF blocks are inflated on the device (DedupContext.push_bgzf), else by the host threads."""
+    gpu_inflate: the BGZF blocks are inflated on the device (DedupContext.push_bgzf), else by the host threads.
+    sort: coordinate sort on the device in front of the dedup (`openge mergesort -M`)."""
     from . import dedup
     with open(in_path, "rb") as fh:
         is_bgzf = fh.read(2) == b"\x1f\x8b"
@@ -242,6 +248,8 @@ def dedup_file(in_path: str, out_path: str, remove_duplicates: bool = False, lev
                 ctx.push_bgzf(ix["comp"], ix["comp_bytes"], ix["in_off"], ix["csize"], ix["isize"], ix["n_blocks"], ix["header_bytes"], None)
                 total = int(np.ctypeslib.as_array((C.c_uint32 * ix["n_blocks"]).from_address(ix["isize"])).sum()) if ix["n_blocks"] else 0
                 ctx.frame(total - ix["header_bytes"])
+                if sort:
+                    ctx.sort()
                 ctx.run()
                 flags = ctx.flags()
                 nb, nr = C.c_uint64(), C.c_uint64()
@@ -252,9 +260,20 @@ def dedup_file(in_path: str, out_path: str, remove_duplicates: bool = False, lev
             else:
                 ptr, nbytes, off_ptr = bam.records_ptr()
                 ctx.push_async(ptr, nbytes, off_ptr, bam.n)
+                if sort:
+                    ctx.sort()
                 ctx.run()
                 flags = ctx.flags()
+                if sort and bam.n:      # the records come back in their new order
+                    nb, nr = C.c_uint64(), C.c_uint64()
+                    offs = np.empty(bam.n + 1, dtype=np.uint64)
+                    from .dedup import _check as _gcheck, lib as _glib
+                    _gcheck(_glib().oge_gpu_dedup_pull(ctx._h, ptr, nbytes, offs.ctypes.data, len(offs), C.byref(nb), C.byref(nr)))
+                    bam.adopt_offsets(offs)
             out = {"dedup": ctx.stats(), "flagstats": ctx.flagstats(), "gpu_inflate": gpu_inflate}
+            if sort:
+                bam.set_sort_order("coordinate")
+                out["sort"] = ctx.sort_stats()
         bam.apply_flags(flags, remove_duplicates, threads)
         bam.store(out_path, format, level, pg_command_line, threads=threads)
         out["timings"] = bam.timings()

@@ -49,7 +49,12 @@ struct ShardState {
     uint64_t global_n = 0;
     std::vector<uint64_t> bases;          // world + 1 record ordinals
     std::vector<uint64_t> split_keys;     // world - 1 packed (ref << coord_bits | biased coord): first key of ranks 1..
-    DevBuf<uint64_t> d_split;
+    DevBuf<uint64_t> d_split, d_bases, pub_hash;
+    DevBuf<unsigned long long> hset;      // hashes other ranks published
+    DevBuf<uint8_t> pub_raw, pub_send, froute_send, proute_send, oroute_send, marks_send;      // lists ordered by destination rank
+    DevBuf<uint32_t> bk;                  // per-destination counters of the bucketing
+    uint32_t entry_bytes = 0;             // size of a published entry, agreed by all ranks
+    uint32_t n_loc = 0, n_loc_far = 0;    // pairs the windowed join settled (their hashes are kept by list position)
     DevBuf<PubEntry> pub, pub2;           // published entries, rounds 1 and 2
     DevBuf<RouteEntry> route, froute;
     DevBuf<uint32_t> marks, marks_frag, pub_list;
@@ -140,6 +145,12 @@ struct oge_gpu_dedup_ctx {
 
 namespace oge {
 
+struct JoinStage {      // what join_stage leaves behind (dedup_api.cu)
+    bool fused;
+    uint64_t n_frag, n_pe, n_unpaired, n_left, n_pairs, n_far, n_retracted, n_far_retracted, n_cplx, n_slots;
+    uint32_t n_loc, n_loc_far;
+};
+int join_stage(oge_gpu_dedup_ctx *c, bool replay_locally, JoinStage *out, uint64_t *launches);
 int compute_layout(oge_gpu_dedup_ctx *c, KeyLayout *L);
 RgTable rg_table(oge_gpu_dedup_ctx *c);
 int ensure_work(oge_gpu_dedup_ctx *c);

@@ -272,6 +272,8 @@ void oge_gpu_dedup_destroy(oge_gpu_dedup_ctx *c) {
     if (c->sh.ev_main) cudaEventDestroy(c->sh.ev_main);
     if (c->sh.ev_far) cudaEventDestroy(c->sh.ev_far);
     for (auto &e : c->sh.ev_side) if (e) cudaEventDestroy(e);
+    c->sh.d_bases.release(); c->sh.pub_hash.release(); c->sh.hset.release(); c->sh.pub_raw.release(); c->sh.pub_send.release();
+    c->sh.froute_send.release(); c->sh.proute_send.release(); c->sh.oroute_send.release(); c->sh.marks_send.release(); c->sh.bk.release();
     c->sh.d_split.release(); c->sh.pub.release(); c->sh.pub2.release(); c->sh.route.release(); c->sh.froute.release();
     c->sh.marks.release(); c->sh.marks_frag.release(); c->sh.pub_list.release(); c->sh.fm.release(); c->sh.fm_sort.release();
     c->sh.w_sort.release(); c->sh.w_sort2.release(); c->sh.scratch2.release();
@@ -544,50 +546,26 @@ int oge_gpu_dedup_reset(oge_gpu_dedup_ctx *c) {
     return OGE_OK;
 }
 
-int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
-    if (!c) return fail_msg(OGE_ERR_INVALID_ARG, "run: null context");
-    OGE_CUDA_TRY(cudaSetDevice(c->cfg.device));
+}  // extern "C"
+
+namespace oge {
+
+// K1 end-build + K2 mate join over the context's records: the windowed join inside the CTAs, the global join over what
+// they could not settle, the check pass, and -- replay_locally -- the exact path's replay.  The range-sharded path stops
+// before the replay: a name that is not a plain couple on this rank is published instead (shard_api.cu), with its local
+// pairs retracted by the fix-up as here.  Afterwards: pair lists and counters final for this rank, the mate table
+// (c->table, out->n_slots) holding the leftover names, the exact-path list in c->sortbuf (out->n_cplx).
+int join_stage(oge_gpu_dedup_ctx *c, bool replay_locally, JoinStage *out, uint64_t *launches_io) {
     cudaStream_t s = c->stream;
-    {   // the input-side figures (push_bgzf / frame) describe the resident records, not a run: they survive
-        const oge_gpu_dedup_stats keep = c->stats;
-        memset(&c->stats, 0, sizeof(c->stats));
-        c->stats.ms_inflate = keep.ms_inflate;
-        c->stats.inflate_blocks = keep.inflate_blocks;
-        c->stats.inflate_bytes_in = keep.inflate_bytes_in;
-        c->stats.inflate_bytes_out = keep.inflate_bytes_out;
-        c->stats.ms_frame = keep.ms_frame;
-        c->stats.frame_repairs = keep.frame_repairs;
-        c->stats.ms_inflate_h2d = keep.ms_inflate_h2d;
-        c->stats.ms_inflate_d2h = keep.ms_inflate_d2h;
-    }
-    c->stats.n_records = c->n;
-    if (c->n == 0) {
-        c->ran = true;
-        return OGE_OK;
-    }
-    int rc;
-    if ((rc = compute_layout(c, &c->kl))) return rc;
-    if ((rc = ensure_work(c))) return rc;
     const uint64_t n = c->n;
-    uint64_t launches = 0;
-    PassTimer timer{c->pass_ev, 48, 0, 0};
-    PassTimer *tp = c->cfg.profile_events ? &timer : nullptr;
-
-    // the pushes ran on the copy stream
-    OGE_CUDA_TRY(cudaEventRecord(c->copy_done, c->copy_stream));
-    OGE_CUDA_TRY(cudaStreamWaitEvent(s, c->copy_done, 0));
-
-    OGE_CUDA_TRY(cudaEventRecord(c->ev[0], s));
-    OGE_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, CNT_N * 4, s));
-    OGE_CUDA_TRY(cudaMemsetAsync(c->dup.p, 0, n, s));
-
-    // ---- K1 end-build (+ the in-CTA mate join in the fused form) and K2 mate join
     EndbuildParams eb;
     eb.rec = c->recs(); eb.off = c->off.p; eb.n = n; eb.idx_base = c->cfg.index_base;
     eb.frag = c->frag.p; eb.hk = c->hk.p; eb.tag = c->tag.p; eb.flag_in = c->flag_in.p;
     eb.counters = c->counters.p; eb.rg = rg_table(c); eb.kl = c->kl;
     const bool fused = !c->cfg.debug_legacy_join;      // windowed join (default) or the whole-file hash join
     uint64_t n_pairs = 0, n_far = 0, n_cplx = 0, n_retracted = 0, n_far_retracted = 0, n_left = 0, n_pe = 0;
+    uint64_t &launches = *launches_io;
+    int rc;
     JoinParams jp;
     jp.rec = c->recs(); jp.off = c->off.p; jp.n = n; jp.idx_base = c->cfg.index_base;
     jp.frag = c->frag.p; jp.hk = c->hk.p; jp.tag = c->tag.p;
@@ -626,7 +604,6 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
     n_pe = c->h_counters[CNT_PAIR_ELIGIBLE];
     c->h_counters_k1_unpaired = c->h_counters[CNT_UNPAIRED];
     n_left = c->h_counters[CNT_LEFT];
-    const uint64_t n_dead_k1 = 0;
 
     // ---- K2 mate join: every map-eligible record (legacy form), or what the CTAs could not settle (fused form)
     const uint64_t n_join = fused ? n_left : n_pe;
@@ -676,6 +653,7 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
             if ((rc = c->pairf2.reserve(need_far, false, s))) return rc;
             jp.pair = c->pair.p;
             jp.pair_far = c->pairf.p;
+            if (replay_locally) {
             // sort (hash, ordinal), replay the toggle map per hash value
             E128 *sorted = nullptr;
             if ((rc = c->cplx_sort.reserve(n_cplx, false, s))) return rc;
@@ -685,12 +663,70 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
             if ((rc = launch_mate_complex(jp, sorted, (uint32_t) n_cplx, c->cplx_state.p, s, &launches))) return rc;
             OGE_CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, s));
             OGE_CUDA_TRY(cudaStreamSynchronize(s));
+            }
         }
     }
     n_pairs = c->h_counters[CNT_PAIRS];
     n_far = c->h_counters[CNT_PAIRS_FAR];
     n_retracted = c->h_counters[CNT_PAIRS_RETRACTED];      // fused form: includes the reserved positions the CTAs did not use
     n_far_retracted = c->h_counters[CNT_FAR_RETRACTED];
+    out->fused = fused;
+    out->n_frag = n_frag; out->n_pe = n_pe; out->n_left = n_left; out->n_loc = n_loc; out->n_loc_far = n_loc_far;
+    out->n_pairs = n_pairs; out->n_far = n_far; out->n_retracted = n_retracted; out->n_far_retracted = n_far_retracted; out->n_cplx = n_cplx;
+    out->n_slots = n_join ? 2 * n_join + 1024 : 0;
+    out->n_unpaired = c->h_counters_k1_unpaired;
+    return 0;
+}
+
+}  // namespace oge
+
+extern "C" {
+
+int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
+    if (!c) return fail_msg(OGE_ERR_INVALID_ARG, "run: null context");
+    OGE_CUDA_TRY(cudaSetDevice(c->cfg.device));
+    cudaStream_t s = c->stream;
+    {   // the input-side figures (push_bgzf / frame) describe the resident records, not a run: they survive
+        const oge_gpu_dedup_stats keep = c->stats;
+        memset(&c->stats, 0, sizeof(c->stats));
+        c->stats.ms_inflate = keep.ms_inflate;
+        c->stats.inflate_blocks = keep.inflate_blocks;
+        c->stats.inflate_bytes_in = keep.inflate_bytes_in;
+        c->stats.inflate_bytes_out = keep.inflate_bytes_out;
+        c->stats.ms_frame = keep.ms_frame;
+        c->stats.frame_repairs = keep.frame_repairs;
+        c->stats.ms_inflate_h2d = keep.ms_inflate_h2d;
+        c->stats.ms_inflate_d2h = keep.ms_inflate_d2h;
+    }
+    c->stats.n_records = c->n;
+    if (c->n == 0) {
+        c->ran = true;
+        return OGE_OK;
+    }
+    int rc;
+    if ((rc = compute_layout(c, &c->kl))) return rc;
+    if ((rc = ensure_work(c))) return rc;
+    const uint64_t n = c->n;
+    uint64_t launches = 0;
+    PassTimer timer{c->pass_ev, 48, 0, 0};
+    PassTimer *tp = c->cfg.profile_events ? &timer : nullptr;
+
+    // the pushes ran on the copy stream
+    OGE_CUDA_TRY(cudaEventRecord(c->copy_done, c->copy_stream));
+    OGE_CUDA_TRY(cudaStreamWaitEvent(s, c->copy_done, 0));
+
+    OGE_CUDA_TRY(cudaEventRecord(c->ev[0], s));
+    OGE_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, CNT_N * 4, s));
+    OGE_CUDA_TRY(cudaMemsetAsync(c->dup.p, 0, n, s));
+
+    // ---- K1 end-build and K2 mate join (shared with the range-sharded path: join_stage)
+    JoinStage js;
+    if ((rc = join_stage(c, true, &js, &launches))) return rc;
+    const uint64_t n_frag = js.n_frag, n_pairs = js.n_pairs, n_far = js.n_far, n_cplx = js.n_cplx, n_retracted = js.n_retracted,
+                   n_far_retracted = js.n_far_retracted, n_left = js.n_left;
+    const bool fused = js.fused;
+    const uint32_t n_loc = js.n_loc, n_loc_far = js.n_loc_far;
+    const uint64_t n_dead_k1 = 0;
     OGE_CUDA_TRY(cudaEventRecord(c->ev[2], s));
 
     // ---- K3 + K4 on the pairs
@@ -793,7 +829,7 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
 #ifdef OGE_TESTING
     if (getenv("OGE_DEBUG_COUNTERS"))
         fprintf(stderr, "[oge] n=%llu frag=%llu pe=%llu near=%llu far=%llu cplx=%llu retracted=%llu/%llu\n", (unsigned long long) n,
-                (unsigned long long) n_frag, (unsigned long long) n_pe, (unsigned long long) n_pairs, (unsigned long long) n_far,
+                (unsigned long long) n_frag, (unsigned long long) js.n_pe, (unsigned long long) n_pairs, (unsigned long long) n_far,
                 (unsigned long long) n_cplx, (unsigned long long) n_retracted, (unsigned long long) n_far_retracted);
 #endif
     oge_gpu_dedup_stats &st = c->stats;

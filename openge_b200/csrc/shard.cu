@@ -9,7 +9,7 @@
 //     every end entry lives on the rank that owns its key range.
 // All lists that cross ranks are small (cross-shard mates, boundary ends, marks); the exchange
 // delivers every rank's list to every rank and the receiving kernels keep what concerns them.
-#include "kernels.cuh"
+#include "keyview.cuh"
 #include "pairing.cuh"
 
 namespace oge {
@@ -293,6 +293,222 @@ __global__ void __launch_bounds__(SH_THREADS) sh_apply_marks_kernel(const uint32
     if (l < n) dup[l] = 1;
 }
 
+
+// ======================================================================================================
+// Owner-routed protocol: what crosses ranks goes only where it is needed.
+//   published entries -> the rank that OWNS the name (key hash mod world), which alone replays it
+//   key hashes of the published entries -> every rank (8 bytes each), for the retraction of local pairs
+//   end entries whose key lies in another rank's range -> that rank; marks -> the rank that holds the record
+// A published entry carries the whole key string RG value + ":" + name, so the owner's comparison is exact
+// whatever the name length and whether or not the header lists the read group:
+//   [frag E128 : 16][key hash : 8][key length : 4][reserved : 4][key bytes ... padded to the entry size]
+// The entry size is agreed by all ranks from the longest key (oge_gpu_shard_key_bytes / _set_entry_bytes).
+
+__device__ __forceinline__ const uint8_t *pub2_at(const uint8_t *base, uint32_t stride, uint64_t j) { return base + j * stride; }
+
+__global__ void __launch_bounds__(SH_THREADS) sh_keylen_kernel(const uint8_t *__restrict__ rec, const uint64_t *__restrict__ off, uint64_t n,
+                                                               const uint64_t *__restrict__ hk, uint32_t *__restrict__ out_max) {
+    const uint64_t i = (uint64_t) blockIdx.x * SH_THREADS + threadIdx.x;
+    uint32_t l = 0;
+    if (i < n && (!hk || hk[i])) {
+        const KeyView v = key_view(rec, off, i);
+        l = v.rg_len + 1 + v.name_len;
+    }
+    for (int o = 16; o; o >>= 1) l = max(l, __shfl_xor_sync(0xFFFFFFFFu, l, o));
+    if ((threadIdx.x & 31) == 0 && l) atomicMax(out_max, l);
+}
+
+__global__ void __launch_bounds__(SH_THREADS) sh_gather2_kernel(const uint32_t *__restrict__ list, uint32_t n_list, const E128 *__restrict__ frag,
+                                                                const uint64_t *__restrict__ hk, const uint8_t *__restrict__ rec,
+                                                                const uint64_t *__restrict__ off, uint8_t *__restrict__ out, uint32_t stride,
+                                                                uint64_t *__restrict__ hashes, uint32_t *__restrict__ err) {
+    const uint32_t j = blockIdx.x * SH_THREADS + threadIdx.x;
+    if (j >= n_list) return;
+    const uint32_t i = list[j];
+    uint8_t *o = out + (uint64_t) j * stride;
+    const E128 f = ld_frag(frag + i);
+    const KeyView v = key_view(rec, off, i);
+    const uint32_t len = v.rg_len + 1 + v.name_len;
+    reinterpret_cast<ulonglong2 *>(o)[0] = make_ulonglong2(f.lo, f.hi);
+    reinterpret_cast<uint64_t *>(o)[2] = hk[i];
+    reinterpret_cast<uint32_t *>(o)[6] = len;
+    reinterpret_cast<uint32_t *>(o)[7] = 0;
+    if (32 + len > stride) { atomicOr(err, DEV_ERR_CAPACITY); return; }
+    for (uint32_t b = 0; b < stride - 32; b++) o[32 + b] = b < len ? key_byte(v, b) : (uint8_t) 0;
+    if (hashes) hashes[j] = hk[i];
+}
+
+// ---- a set of 64-bit hashes (open addressing, 0 = empty) -----------------------------------------------
+__global__ void __launch_bounds__(SH_THREADS) sh_set_build_kernel(const uint64_t *__restrict__ h, uint64_t n, unsigned long long *__restrict__ set,
+                                                                  uint64_t n_slots) {
+    const uint64_t j = (uint64_t) blockIdx.x * SH_THREADS + threadIdx.x;
+    if (j >= n) return;
+    const unsigned long long k = h[j];
+    if (!k) return;
+    uint64_t s = slot_of(k, n_slots);
+    while (true) {
+        const unsigned long long old = atomicCAS(set + s, 0ull, k);
+        if (old == 0 || old == k) return;
+        if (++s == n_slots) s = 0;
+    }
+}
+__device__ __forceinline__ bool sh_set_has(const unsigned long long *set, uint64_t n_slots, uint64_t k) {
+    uint64_t s = slot_of(k, n_slots);
+    while (true) {
+        const unsigned long long v = set[s];
+        if (v == k) return true;
+        if (v == 0) return false;
+        if (++s == n_slots) s = 0;
+    }
+}
+
+// A couple the global join over the leftovers formed (its slot holds two arrivals) whose name some other rank published:
+// retracted, both records published in the second round.
+__global__ void __launch_bounds__(SH_THREADS) sh_probe_table_kernel(MateSlot *__restrict__ table, uint64_t n_slots, const unsigned long long *__restrict__ set,
+                                                                    uint64_t set_slots, E128 *__restrict__ pair, E128 *__restrict__ pair_far,
+                                                                    uint32_t *__restrict__ list2, uint32_t *__restrict__ counters) {
+    const uint64_t s = (uint64_t) blockIdx.x * SH_THREADS + threadIdx.x;
+    if (s >= n_slots) return;
+    const uint64_t k = table[s].key;
+    if (!k || (table[s].val >> 32) != 2) return;      // not a couple (or complex / retracted: those were published in round 1)
+    if (!sh_set_has(set, set_slots, k)) return;
+    const uint32_t pos = table[s].pair_pos;
+    if (pos == SLOT_NO_PAIR) return;                  // hash-equal records with different names: published in round 1
+    table[s].val |= 1ull << 63;
+    const bool far = (pos & SLOT_PAIR_FAR) != 0;
+    reinterpret_cast<ulonglong2 *>(far ? pair_far : pair)[pos & ~SLOT_PAIR_FAR] = make_ulonglong2(~0ull, ~0ull);
+    atomicAdd(&counters[far ? CNT_FAR_RETRACTED : CNT_PAIRS_RETRACTED], 1u);
+    const uint32_t at = atomicAdd(&counters[CNT_PUB], 2u);
+    list2[at] = (uint32_t) (table[s].who >> 32);
+    list2[at + 1] = (uint32_t) table[s].who;
+}
+
+// The same for the pairs the windowed join settled inside its CTAs (they are in no table: their hashes are kept by list position).
+__global__ void __launch_bounds__(SH_THREADS) sh_probe_pairs_kernel(const uint64_t *__restrict__ pair_hk, uint32_t n_pairs, const unsigned long long *__restrict__ set,
+                                                                    uint64_t set_slots, E128 *__restrict__ list, int far, const uint32_t *__restrict__ mate_of,
+                                                                    ShardParams S, uint32_t *__restrict__ list2) {
+    const uint32_t pos = blockIdx.x * SH_THREADS + threadIdx.x;
+    if (pos >= n_pairs) return;
+    const uint64_t h = pair_hk[pos];
+    if (!h || !sh_set_has(set, set_slots, h)) return;
+    const E128 ent = ld_frag(list + pos);
+    if (is_dead(ent)) return;
+    const uint32_t i1 = (uint32_t) (bits_get(ent, S.kl.p_idx, S.kl.idx_bits) - S.idx_base);
+    const uint32_t i2 = (uint32_t) (mate_of[i1] - S.idx_base);
+    reinterpret_cast<ulonglong2 *>(list)[pos] = make_ulonglong2(~0ull, ~0ull);
+    atomicAdd(&S.counters[far ? CNT_FAR_RETRACTED : CNT_PAIRS_RETRACTED], 1u);
+    const uint32_t at = atomicAdd(&S.counters[CNT_PUB], 2u);
+    list2[at] = i1;
+    list2[at + 1] = i2;
+}
+
+// ---- replay at the name's owner ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(SH_THREADS) sh_wbuild2_kernel(const uint8_t *__restrict__ w, uint32_t stride, uint32_t n_w, KeyLayout L,
+                                                                E128 *__restrict__ out) {
+    const uint32_t j = blockIdx.x * SH_THREADS + threadIdx.x;
+    if (j >= n_w) return;
+    const uint8_t *p = pub2_at(w, stride, j);
+    const E128 f = ld_frag(reinterpret_cast<const E128 *>(p));
+    E128 e;
+    e.hi = reinterpret_cast<const uint64_t *>(p)[2];
+    e.lo = (bits_get(f, L.f_idx, L.idx_bits) << 32) | j;
+    out[j] = e;
+}
+
+__device__ __forceinline__ bool pub2_keys_equal(const uint8_t *a, const uint8_t *b) {
+    const uint32_t la = reinterpret_cast<const uint32_t *>(a)[6], lb = reinterpret_cast<const uint32_t *>(b)[6];
+    if (la != lb) return false;
+    const uint32_t *wa = reinterpret_cast<const uint32_t *>(a + 32), *wb = reinterpret_cast<const uint32_t *>(b + 32);
+    for (uint32_t k = 0; k < (la + 3) / 4; k++)      // the padding behind the key is zero in both
+        if (wa[k] != wb[k]) return false;
+    return true;
+}
+
+// One thread per hash value: the reference's toggle (tmp.put / tmp.remove, mark_duplicates.cpp:216-223) over that hash's
+// sightings in global file order, keys compared byte by byte.  A pair whose key range this rank owns joins its lists; the
+// others are handed to their owners (out, counters[CNT_ROUTE]).
+__global__ void __launch_bounds__(SH_THREADS) sh_replay2_kernel(const E128 *__restrict__ sorted, uint32_t n_w, const uint8_t *__restrict__ w, uint32_t stride,
+                                                                uint8_t *__restrict__ state, ShardParams S, E128 *__restrict__ pair,
+                                                                uint32_t pair_cap, E128 *__restrict__ pair_far, uint32_t far_cap,
+                                                                uint32_t *__restrict__ mate_of, uint64_t *__restrict__ fm, uint32_t fm_cap,
+                                                                RouteEntry *__restrict__ out, uint32_t out_cap) {
+    const uint32_t j = blockIdx.x * SH_THREADS + threadIdx.x;
+    if (j >= n_w) return;
+    const uint32_t h = (uint32_t) sorted[j].hi;
+    if (j > 0 && (uint32_t) sorted[j - 1].hi == h) return;      // not a segment head
+    uint32_t end = j;
+    while (end < n_w && (uint32_t) sorted[end].hi == h) state[end++] = 0;
+    for (uint32_t a = j; a < end; a++) {
+        const uint8_t *pa = pub2_at(w, stride, (uint32_t) sorted[a].lo);
+        if (a > j && sorted[a].lo >> 32 == sorted[a - 1].lo >> 32) continue;      // the same record published twice
+        int found = -1;
+        for (uint32_t b = j; b < a; b++) {
+            if (!state[b]) continue;
+            if (sorted[b].hi == sorted[a].hi && pub2_keys_equal(pa, pub2_at(w, stride, (uint32_t) sorted[b].lo))) { found = (int) b; break; }
+        }
+        if (found < 0) { state[a] = 1; continue; }
+        state[found] = 0;
+        const uint8_t *pb = pub2_at(w, stride, (uint32_t) sorted[found].lo);      // the earlier sighting
+        uint32_t i1, i2;
+        bool far;
+        const E128 ent = make_pair_entry(S.kl, ld_frag(reinterpret_cast<const E128 *>(pb)), ld_frag(reinterpret_cast<const E128 *>(pa)), &i1, &i2, 0, &far);
+        if (owner_of(S, pair_packed(S.kl, ent)) != S.rank) {
+            const uint32_t at = atomicAdd(&S.counters[CNT_ROUTE], 1u);
+            if (at < out_cap) {
+                RouteEntry r;
+                r.e = ent;
+                r.idx2 = i2;
+                r.kind = far ? 2u : 1u;
+                r.rsv = 0;
+                out[at] = r;
+            }
+            continue;
+        }
+        const uint32_t pos = atomicAdd(&S.counters[far ? CNT_PAIRS_FAR : CNT_PAIRS], 1u);
+        if (pos < (far ? far_cap : pair_cap)) reinterpret_cast<ulonglong2 *>(far ? pair_far : pair)[pos] = make_ulonglong2(ent.lo, ent.hi);
+        const uint64_t l1 = (uint64_t) i1 - S.idx_base;
+        if (l1 < S.n) mate_of[l1] = i2;
+        else {
+            const uint32_t at = atomicAdd(&S.counters[CNT_FM], 1u);
+            if (at < fm_cap) fm[at] = ((uint64_t) i1 << 32) | i2;
+        }
+    }
+}
+
+// ---- bucketing by destination rank: what a rank sends is ordered by destination, so that the exchange is one
+//      all-to-all with uneven splits.  kind 0: published entries (owner of the name = hash mod world), 1: routed end
+//      entries (owner of the key range), 2: marks (rank whose record range holds the ordinal; bases = world + 1 ordinals).
+__device__ __forceinline__ int sh_dest(int kind, const uint8_t *item, const ShardParams &S, const uint64_t *bases) {
+    if (kind == 0) return (int) (reinterpret_cast<const uint64_t *>(item)[2] % (uint64_t) S.world);
+    if (kind == 1) {
+        const RouteEntry *r = reinterpret_cast<const RouteEntry *>(item);
+        return owner_of(S, r->kind ? pair_packed(S.kl, r->e) : frag_packed(S.kl, r->e));
+    }
+    const uint64_t g = *reinterpret_cast<const uint32_t *>(item);
+    int o = 0;
+    for (int r = 1; r < S.world; r++) o += bases[r] <= g ? 1 : 0;
+    return o;
+}
+
+__global__ void __launch_bounds__(SH_THREADS) sh_bucket_count_kernel(const uint8_t *__restrict__ items, uint64_t n, uint32_t item_bytes, int kind,
+                                                                     ShardParams S, const uint64_t *__restrict__ bases, uint32_t *__restrict__ count) {
+    const uint64_t j = (uint64_t) blockIdx.x * SH_THREADS + threadIdx.x;
+    if (j >= n) return;
+    atomicAdd(&count[sh_dest(kind, items + j * item_bytes, S, bases)], 1u);
+}
+
+// start[d] = first slot of destination d in `out`; fill[d] counts up from zero
+__global__ void __launch_bounds__(SH_THREADS) sh_bucket_scatter_kernel(const uint8_t *__restrict__ items, uint64_t n, uint32_t item_bytes, int kind,
+                                                                       ShardParams S, const uint64_t *__restrict__ bases, const uint32_t *__restrict__ start,
+                                                                       uint32_t *__restrict__ fill, uint8_t *__restrict__ out) {
+    const uint64_t j = (uint64_t) blockIdx.x * SH_THREADS + threadIdx.x;
+    if (j >= n) return;
+    const uint8_t *src = items + j * item_bytes;
+    const int d = sh_dest(kind, src, S, bases);
+    uint8_t *dst = out + (uint64_t) (start[d] + atomicAdd(&fill[d], 1u)) * item_bytes;
+    for (uint32_t b = 0; b < item_bytes; b += 4) *reinterpret_cast<uint32_t *>(dst + b) = *reinterpret_cast<const uint32_t *>(src + b);
+}
+
 // ---- launchers --------------------------------------------------------------------------------------------
 static inline uint32_t grid_for(uint64_t n) { return (uint32_t) ((n + SH_THREADS - 1) / SH_THREADS); }
 
@@ -357,6 +573,52 @@ int launch_sh_fm_unpack(const E128 *in, uint32_t n, uint64_t *fm, cudaStream_t s
 int launch_sh_apply_marks(const uint32_t *marks, uint64_t n_marks, uint64_t idx_base, uint64_t n, uint8_t *dup, cudaStream_t s,
                           uint64_t *launches) {
     SH_LAUNCH(n_marks, (sh_apply_marks_kernel<<<grid_for(n_marks), SH_THREADS, 0, s>>>(marks, n_marks, idx_base, n, dup)));
+    return 0;
+}
+
+int launch_sh_keylen(const uint8_t *rec, const uint64_t *off, uint64_t n, const uint64_t *hk, uint32_t *out_max, cudaStream_t s, uint64_t *launches) {
+    SH_LAUNCH(n, (sh_keylen_kernel<<<grid_for(n), SH_THREADS, 0, s>>>(rec, off, n, hk, out_max)));
+    return 0;
+}
+int launch_sh_gather2(const uint32_t *list, uint32_t n_list, const E128 *frag, const uint64_t *hk, const uint8_t *rec, const uint64_t *off, uint8_t *out,
+                      uint32_t stride, uint64_t *hashes, uint32_t *err, cudaStream_t s, uint64_t *launches) {
+    SH_LAUNCH(n_list, (sh_gather2_kernel<<<grid_for(n_list), SH_THREADS, 0, s>>>(list, n_list, frag, hk, rec, off, out, stride, hashes, err)));
+    return 0;
+}
+int launch_sh_set_build(const uint64_t *h, uint64_t n, unsigned long long *set, uint64_t n_slots, cudaStream_t s, uint64_t *launches) {
+    SH_LAUNCH(n, (sh_set_build_kernel<<<grid_for(n), SH_THREADS, 0, s>>>(h, n, set, n_slots)));
+    return 0;
+}
+int launch_sh_probe_table(MateSlot *table, uint64_t n_slots, const unsigned long long *set, uint64_t set_slots, E128 *pair, E128 *pair_far, uint32_t *list2,
+                          uint32_t *counters, cudaStream_t s, uint64_t *launches) {
+    SH_LAUNCH(n_slots, (sh_probe_table_kernel<<<grid_for(n_slots), SH_THREADS, 0, s>>>(table, n_slots, set, set_slots, pair, pair_far, list2, counters)));
+    return 0;
+}
+int launch_sh_probe_pairs(const uint64_t *pair_hk, uint32_t n_pairs, const unsigned long long *set, uint64_t set_slots, E128 *list, int far,
+                          const uint32_t *mate_of, const ShardParams &S, uint32_t *list2, cudaStream_t s, uint64_t *launches) {
+    SH_LAUNCH(n_pairs, (sh_probe_pairs_kernel<<<grid_for(n_pairs), SH_THREADS, 0, s>>>(pair_hk, n_pairs, set, set_slots, list, far, mate_of, S, list2)));
+    return 0;
+}
+int launch_sh_wbuild2(const uint8_t *w, uint32_t stride, uint32_t n_w, const KeyLayout &L, E128 *out, cudaStream_t s, uint64_t *launches) {
+    SH_LAUNCH(n_w, (sh_wbuild2_kernel<<<grid_for(n_w), SH_THREADS, 0, s>>>(w, stride, n_w, L, out)));
+    return 0;
+}
+int launch_sh_replay2(const E128 *sorted, uint32_t n_w, const uint8_t *w, uint32_t stride, uint8_t *state, const ShardParams &S, E128 *pair, uint32_t pair_cap,
+                      E128 *pair_far, uint32_t far_cap, uint32_t *mate_of, uint64_t *fm, uint32_t fm_cap, RouteEntry *out, uint32_t out_cap, cudaStream_t s,
+                      uint64_t *launches) {
+    SH_LAUNCH(n_w, (sh_replay2_kernel<<<grid_for(n_w), SH_THREADS, 0, s>>>(sorted, n_w, w, stride, state, S, pair, pair_cap, pair_far, far_cap, mate_of,
+                                                                            fm, fm_cap, out, out_cap)));
+    return 0;
+}
+int launch_sh_bucket_count(const void *items, uint64_t n, uint32_t item_bytes, int kind, const ShardParams &S, const uint64_t *bases, uint32_t *count,
+                           cudaStream_t s, uint64_t *launches) {
+    SH_LAUNCH(n, (sh_bucket_count_kernel<<<grid_for(n), SH_THREADS, 0, s>>>((const uint8_t *) items, n, item_bytes, kind, S, bases, count)));
+    return 0;
+}
+int launch_sh_bucket_scatter(const void *items, uint64_t n, uint32_t item_bytes, int kind, const ShardParams &S, const uint64_t *bases, const uint32_t *start,
+                             uint32_t *fill, void *out, cudaStream_t s, uint64_t *launches) {
+    SH_LAUNCH(n, (sh_bucket_scatter_kernel<<<grid_for(n), SH_THREADS, 0, s>>>((const uint8_t *) items, n, item_bytes, kind, S, bases, start, fill,
+                                                                              (uint8_t *) out)));
     return 0;
 }
 

@@ -34,6 +34,22 @@ int launch_sh_fm_pack(const uint64_t *fm, uint32_t n, E128 *out, cudaStream_t s,
 int launch_sh_fm_unpack(const E128 *in, uint32_t n, uint64_t *fm, cudaStream_t s, uint64_t *launches);
 int launch_sh_apply_marks(const uint32_t *marks, uint64_t n_marks, uint64_t idx_base, uint64_t n, uint8_t *dup, cudaStream_t s,
                           uint64_t *launches);
+int launch_sh_keylen(const uint8_t *rec, const uint64_t *off, uint64_t n, const uint64_t *hk, uint32_t *out_max, cudaStream_t s, uint64_t *launches);
+int launch_sh_gather2(const uint32_t *list, uint32_t n_list, const E128 *frag, const uint64_t *hk, const uint8_t *rec, const uint64_t *off, uint8_t *out,
+                      uint32_t stride, uint64_t *hashes, uint32_t *err, cudaStream_t s, uint64_t *launches);
+int launch_sh_set_build(const uint64_t *h, uint64_t n, unsigned long long *set, uint64_t n_slots, cudaStream_t s, uint64_t *launches);
+int launch_sh_probe_table(MateSlot *table, uint64_t n_slots, const unsigned long long *set, uint64_t set_slots, E128 *pair, E128 *pair_far, uint32_t *list2,
+                          uint32_t *counters, cudaStream_t s, uint64_t *launches);
+int launch_sh_probe_pairs(const uint64_t *pair_hk, uint32_t n_pairs, const unsigned long long *set, uint64_t set_slots, E128 *list, int far,
+                          const uint32_t *mate_of, const ShardParams &S, uint32_t *list2, cudaStream_t s, uint64_t *launches);
+int launch_sh_wbuild2(const uint8_t *w, uint32_t stride, uint32_t n_w, const KeyLayout &L, E128 *out, cudaStream_t s, uint64_t *launches);
+int launch_sh_replay2(const E128 *sorted, uint32_t n_w, const uint8_t *w, uint32_t stride, uint8_t *state, const ShardParams &S, E128 *pair, uint32_t pair_cap,
+                      E128 *pair_far, uint32_t far_cap, uint32_t *mate_of, uint64_t *fm, uint32_t fm_cap, RouteEntry *out, uint32_t out_cap, cudaStream_t s,
+                      uint64_t *launches);
+int launch_sh_bucket_count(const void *items, uint64_t n, uint32_t item_bytes, int kind, const ShardParams &S, const uint64_t *bases, uint32_t *count,
+                           cudaStream_t s, uint64_t *launches);
+int launch_sh_bucket_scatter(const void *items, uint64_t n, uint32_t item_bytes, int kind, const ShardParams &S, const uint64_t *bases, const uint32_t *start,
+                             uint32_t *fill, void *out, cudaStream_t s, uint64_t *launches);
 }  // namespace oge
 
 namespace {
@@ -170,152 +186,210 @@ __global__ void sh_add_counter_kernel(uint32_t *dst, uint32_t base, const uint32
     *dst = v;
 }
 
-int oge_gpu_shard_begin(oge_gpu_dedup_ctx *c, void **pub_dev, uint64_t *n_pub, void **froute_dev, uint64_t *n_froute) {
+
+// What a rank sends, ordered by destination rank (kind 0: published entries by name owner, 1: routed end entries by key
+// owner, 2: marks by record owner): counts[d] items for rank d, back to back in `out`.  One host round trip (the counts
+// are what the exchange needs as its split sizes anyway).
+static int bucket_by_destination(oge_gpu_dedup_ctx *c, const void *items, uint64_t n, uint32_t item_bytes, int kind, DevBuf<uint8_t> &out,
+                                 uint64_t *counts, uint64_t *launches) {
+    ShardState &sh = c->sh;
+    cudaStream_t s = c->stream;
+    const int W = c->cfg.world;
+    for (int d = 0; d < W; d++) counts[d] = 0;
+    if (n == 0) return 0;
+    int rc;
+    if ((rc = sh.bk.reserve(3 * (size_t) W, false, s)) || (rc = out.reserve(n * item_bytes, false, s))) return rc;
+    OGE_CUDA_TRY(cudaMemsetAsync(sh.bk.p, 0, 3 * (size_t) W * 4, s));
+    const ShardParams S = shard_params(c);
+    if ((rc = launch_sh_bucket_count(items, n, item_bytes, kind, S, sh.d_bases.p, sh.bk.p, s, launches))) return rc;
+    std::vector<uint32_t> h(W), start(W);
+    OGE_CUDA_TRY(cudaMemcpyAsync(h.data(), sh.bk.p, (size_t) W * 4, cudaMemcpyDeviceToHost, s));
+    OGE_CUDA_TRY(cudaStreamSynchronize(s));
+    uint32_t acc = 0;
+    for (int d = 0; d < W; d++) { start[d] = acc; acc += h[d]; counts[d] = h[d]; }
+    if (acc != n) return fail_msg(OGE_ERR_STATE, "shard: bucket counts do not add up");
+    OGE_CUDA_TRY(cudaMemcpyAsync(sh.bk.p + W, start.data(), (size_t) W * 4, cudaMemcpyHostToDevice, s));
+    if ((rc = launch_sh_bucket_scatter(items, n, item_bytes, kind, S, sh.d_bases.p, sh.bk.p + W, sh.bk.p + 2 * W, out.p, s, launches))) return rc;
+    OGE_CUDA_TRY(cudaStreamSynchronize(s));      // `start` lives on this stack frame
+    return 0;
+}
+
+int oge_gpu_shard_key_bytes(oge_gpu_dedup_ctx *c, uint32_t *max_key_bytes) {
+    if (!c || !max_key_bytes) return fail_msg(OGE_ERR_INVALID_ARG, "shard_key_bytes: null argument");
+    OGE_CUDA_TRY(cudaSetDevice(c->cfg.device));
+    *max_key_bytes = 0;
+    if (c->n == 0) return OGE_OK;
+    cudaStream_t s = c->stream;
+    OGE_CUDA_TRY(cudaEventRecord(c->copy_done, c->copy_stream));
+    OGE_CUDA_TRY(cudaStreamWaitEvent(s, c->copy_done, 0));
+    uint64_t launches = 0;
+    OGE_CUDA_TRY(cudaMemsetAsync(c->counters.p + CNT_SCRATCH0, 0, 4, s));
+    int rc = launch_sh_keylen(c->recs(), c->off.p, c->n, nullptr, c->counters.p + CNT_SCRATCH0, s, &launches);
+    if (rc) return rc;
+    OGE_CUDA_TRY(cudaMemcpyAsync(max_key_bytes, c->counters.p + CNT_SCRATCH0, 4, cudaMemcpyDeviceToHost, s));
+    OGE_CUDA_TRY(cudaStreamSynchronize(s));
+    return OGE_OK;
+}
+
+int oge_gpu_shard_set_entry_bytes(oge_gpu_dedup_ctx *c, uint32_t entry_bytes) {
+    if (!c) return fail_msg(OGE_ERR_INVALID_ARG, "shard_set_entry_bytes: null context");
+    if (entry_bytes < 64 || entry_bytes % 32 || entry_bytes > 32 + 544) return fail_msg(OGE_ERR_INVALID_ARG, "shard_set_entry_bytes: %u", entry_bytes);
+    c->sh.entry_bytes = entry_bytes;
+    return OGE_OK;
+}
+
+int oge_gpu_shard_begin(oge_gpu_dedup_ctx *c, void **pub_dev, uint64_t *pub_counts, void **hash_dev, uint64_t *n_hash, void **froute_dev,
+                        uint64_t *froute_counts) {
     int rc = need_phase(c, c ? c->sh.phase : 0, "shard_begin");
     if (rc) return rc;
-    if (!pub_dev || !n_pub || !froute_dev || !n_froute) return fail_msg(OGE_ERR_INVALID_ARG, "shard_begin: null argument");
+    if (!pub_dev || !pub_counts || !hash_dev || !n_hash || !froute_dev || !froute_counts) return fail_msg(OGE_ERR_INVALID_ARG, "shard_begin: null argument");
     if (c->sh.bases[c->cfg.rank + 1] - c->sh.bases[c->cfg.rank] != c->n)
         return fail_msg(OGE_ERR_INVALID_ARG, "shard_begin: the context holds %llu records, the ranges say %llu", (unsigned long long) c->n,
                         (unsigned long long) (c->sh.bases[c->cfg.rank + 1] - c->sh.bases[c->cfg.rank]));
+    if (c->sh.entry_bytes == 0) return fail_msg(OGE_ERR_STATE, "shard_begin: call oge_gpu_shard_set_entry_bytes first (the size all ranks agreed on)");
     cudaStream_t s = c->stream;
     ShardState &sh = c->sh;
+    const int W = c->cfg.world;
     memset(&c->stats, 0, sizeof(c->stats));
     c->stats.n_records = c->n;
     c->ran = false;
     c->clk_used = 0;
-    *pub_dev = *froute_dev = nullptr;
-    *n_pub = *n_froute = 0;
+    *pub_dev = *froute_dev = *hash_dev = nullptr;
+    *n_hash = 0;
+    for (int d = 0; d < W; d++) pub_counts[d] = froute_counts[d] = 0;
     if ((rc = compute_layout(c, &c->kl))) return rc;
     const uint64_t n = c->n;
     uint64_t launches = 0;
-    // split keys in the entries' own packing: (ref << coord_bits) | (pos + bias)
+    // split keys in the entries' own packing: (ref << coord_bits) | (pos + bias); the record ranges
     {
-        std::vector<uint64_t> packed((size_t) std::max(1, c->cfg.world - 1), 0);
-        for (int r = 0; r + 1 < c->cfg.world; r++) {
+        std::vector<uint64_t> packed((size_t) std::max(1, W - 1), 0);
+        for (int r = 0; r + 1 < W; r++) {
             const int64_t ref = (int32_t) sh.split_keys[2 * r], pos = (int32_t) sh.split_keys[2 * r + 1];
             const int64_t biased = std::min<int64_t>(std::max<int64_t>(pos + c->kl.coord_bias, 0), (1ll << c->kl.coord_bits) - 1);
             packed[r] = ((uint64_t) std::max<int64_t>(ref, 0) << c->kl.coord_bits) | (uint64_t) biased;
             if (ref < 0) packed[r] = ~0ull;      // a shard that starts in the unmapped tail owns no key
         }
-        if ((rc = sh.d_split.reserve(packed.size(), false, s))) return rc;
+        if ((rc = sh.d_split.reserve(packed.size(), false, s)) || (rc = sh.d_bases.reserve(sh.bases.size(), false, s))) return rc;
         OGE_CUDA_TRY(cudaMemcpyAsync(sh.d_split.p, packed.data(), packed.size() * 8, cudaMemcpyHostToDevice, s));
+        OGE_CUDA_TRY(cudaMemcpyAsync(sh.d_bases.p, sh.bases.data(), sh.bases.size() * 8, cudaMemcpyHostToDevice, s));
         OGE_CUDA_TRY(cudaStreamSynchronize(s));
     }
     OGE_CUDA_TRY(cudaEventRecord(c->copy_done, c->copy_stream));
     OGE_CUDA_TRY(cudaStreamWaitEvent(s, c->copy_done, 0));
     sh.n_frag = sh.n_pe = sh.n_pairs = sh.n_retracted = sh.n_far = sh.n_far_dead = sh.n_slots = sh.n_fm = sh.n_froute_all = sh.n_unpaired = 0;
+    sh.n_loc = sh.n_loc_far = 0;
     sh.frag_mode = 0;
     sh.side_pass_used = 0;
     sh.side_pass_bytes = 0;
     OGE_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, CNT_N * 4, s));
-    uint64_t n_fr = 0;
+    uint64_t n_list = 0;
     if (n) {
         if ((rc = ensure_work(c))) return rc;
-        PhaseClock clk(c, &c->stats.ms_endbuild);
+        OGE_CUDA_TRY(cudaEventRecord(c->ev[0], s));
         OGE_CUDA_TRY(cudaMemsetAsync(c->dup.p, 0, n, s));
-        EndbuildParams eb;
-        eb.rec = c->recs(); eb.off = c->off.p; eb.n = n; eb.idx_base = c->cfg.index_base;
-        eb.frag = c->frag.p; eb.hk = c->hk.p; eb.tag = c->tag.p; eb.flag_in = c->flag_in.p;
-        eb.counters = c->counters.p; eb.rg = rg_table(c); eb.kl = c->kl;
-        if ((rc = launch_endbuild(eb, (uint32_t) (c->rec_bytes / n), c->sms, s, &launches))) return rc;
-        clk.stop();
-        if ((rc = read_counters(c))) return rc;
-        if ((rc = check_endbuild_errors(c))) return rc;
-        sh.n_frag = c->h_counters[CNT_FRAG];
-        sh.n_pe = c->h_counters[CNT_PAIR_ELIGIBLE];
-        sh.n_unpaired = c->h_counters[CNT_UNPAIRED];
-    }
-    uint64_t n_list = 0;
-    if (sh.n_pe) {
-        PhaseClock clk(c, &c->stats.ms_join);
-        const uint64_t n_pe = sh.n_pe;
-        sh.n_slots = 2 * n_pe + 1024;      // at most half full whatever the input (mates of most names may sit on other ranks)
-        if ((rc = c->table.reserve(sh.n_slots, false, s))) return rc;
-        if ((rc = c->pair.reserve(n_pe / 2 + 1024, false, s))) return rc;
-        if ((rc = c->pair2.reserve(n_pe / 2 + 1024, false, s))) return rc;
-        if ((rc = c->pairf.reserve(n_pe / 2 + 1024, false, s))) return rc;
-        if ((rc = c->pairf2.reserve(n_pe / 2 + 1024, false, s))) return rc;
-        if ((rc = c->cplx_slots.reserve(n_pe / 3 + 1024, false, s))) return rc;
-        if ((rc = sh.pub_list.reserve(n_pe + 16, false, s))) return rc;
-        OGE_CUDA_TRY(cudaMemsetAsync(c->table.p, 0, sh.n_slots * sizeof(MateSlot), s));
-        JoinParams jp;
-        jp.rec = c->recs(); jp.off = c->off.p; jp.n = n; jp.idx_base = c->cfg.index_base;
-        jp.frag = c->frag.p; jp.hk = c->hk.p; jp.tag = c->tag.p;
-        jp.table = c->table.p; jp.n_slots = sh.n_slots;
-        jp.pair = c->pair.p; jp.pair_far = c->pairf.p; jp.mate_of = c->mate_of.p; jp.cplx = c->sortbuf.p; jp.cplx_slots = c->cplx_slots.p;
-        jp.counters = c->counters.p; jp.rg = rg_table(c); jp.kl = c->kl; jp.verify_names = c->cfg.verify_names;
-        if ((rc = launch_mate_join(jp, s, &launches))) return rc;
-        if ((rc = read_counters(c))) return rc;
-        if (c->h_counters[CNT_COMPLEX_SLOTS]) {
-            if ((rc = launch_mate_fixup(jp, c->h_counters[CNT_COMPLEX_SLOTS], s, &launches))) return rc;
+        // K1 + the mate join of this rank's records, as on one GPU but without the replay of the exact path: a name that is
+        // not a plain couple here is published instead
+        JoinStage js;
+        if ((rc = join_stage(c, false, &js, &launches))) return rc;
+        OGE_CUDA_TRY(cudaEventRecord(c->ev[2], s));
+        sh.n_frag = js.n_frag; sh.n_pe = js.n_pe; sh.n_unpaired = js.n_unpaired;
+        sh.n_slots = js.n_slots; sh.n_loc = js.n_loc; sh.n_loc_far = js.n_loc_far;
+        sh.n_pairs = js.n_pairs; sh.n_retracted = js.n_retracted; sh.n_far = js.n_far; sh.n_far_dead = js.n_far_retracted;
+        c->stats.n_complex_names = js.n_cplx;
+        c->stats.n_local_pairs = js.n_loc + js.n_loc_far;
+        c->stats.n_join_leftovers = js.n_left;
+        // published: names seen once among the leftovers (their slot holds one arrival) and everything on the exact-path list
+        if (js.n_slots || js.n_cplx) {
+            if ((rc = sh.pub_list.reserve(js.n_left + js.n_cplx + 2 * (uint64_t) (js.n_loc + js.n_loc_far) / 1 + 16, false, s))) return rc;
+            if (js.n_slots && (rc = launch_sh_singletons(c->table.p, js.n_slots, sh.pub_list.p, c->counters.p, s, &launches))) return rc;
+            if ((rc = launch_sh_complex(c->sortbuf.p, (uint32_t) js.n_cplx, sh.pub_list.p, c->counters.p, s, &launches))) return rc;
             if ((rc = read_counters(c))) return rc;
+            n_list = c->h_counters[CNT_PUB];
         }
-        // published: names seen once (their slot holds one arrival) and everything on the exact-path list
-        if ((rc = launch_sh_singletons(c->table.p, sh.n_slots, sh.pub_list.p, c->counters.p, s, &launches))) return rc;
-        if ((rc = launch_sh_complex(c->sortbuf.p, c->h_counters[CNT_COMPLEX], sh.pub_list.p, c->counters.p, s, &launches))) return rc;
-        if ((rc = read_counters(c))) return rc;
-        n_list = c->h_counters[CNT_PUB];
-        sh.n_pairs = c->h_counters[CNT_PAIRS];
-        sh.n_retracted = c->h_counters[CNT_PAIRS_RETRACTED];
-        sh.n_far = c->h_counters[CNT_PAIRS_FAR];
-        sh.n_far_dead = c->h_counters[CNT_FAR_RETRACTED];
-        c->stats.n_complex_names = c->h_counters[CNT_COMPLEX];
-        if ((rc = sh.pub.reserve(n_list + 1, false, s))) return rc;
-        if ((rc = launch_sh_gather(sh.pub_list.p, (uint32_t) n_list, c->frag.p, c->hk.p, c->tag.p, sh.pub.p, s, &launches))) return rc;
+        OGE_CUDA_TRY(cudaStreamSynchronize(s));
+        c->stats.ms_endbuild += ms_between(c->ev[0], c->ev[1]);
+        c->stats.ms_join += ms_between(c->ev[1], c->ev[2]);
+        c->stats.ms_total += ms_between(c->ev[0], c->ev[2]);
+    }
+    {
+        PhaseClock clk(c, &c->stats.ms_join);
+        if (n_list) {
+            if ((rc = sh.pub_raw.reserve(n_list * sh.entry_bytes, false, s)) || (rc = sh.pub_hash.reserve(n_list, false, s))) return rc;
+            if ((rc = launch_sh_gather2(sh.pub_list.p, (uint32_t) n_list, c->frag.p, c->hk.p, c->recs(), c->off.p, sh.pub_raw.p, sh.entry_bytes,
+                                        sh.pub_hash.p, c->counters.p + CNT_ERR, s, &launches)))
+                return rc;
+        }
+        if ((rc = bucket_by_destination(c, sh.pub_raw.p, n_list, sh.entry_bytes, 0, sh.pub_send, pub_counts, &launches))) return rc;
         clk.stop();
     }
     // copies of the fragment ends whose key lies in another rank's range leave now: they travel with
     // the first exchange, so that the fragment sort can overlap the pair exchanges (the originals stay:
     // K4 leaves runs alone whose key another rank owns)
-    if (n && c->cfg.world > 1) {
+    uint64_t n_fr = 0;
+    if (n && W > 1) {
         PhaseClock clk(c, &c->stats.ms_select);
         E128 *lists[1] = {c->frag.p};
         const uint64_t counts[1] = {n};
         const int kinds[1] = {0};
         if ((rc = route_sweep(c, 1, lists, counts, kinds, 2, &n_fr, &launches))) return rc;
-        if ((rc = sh.froute.reserve(n_fr + 1, false, s))) return rc;
-        if (n_fr) OGE_CUDA_TRY(cudaMemcpyAsync(sh.froute.p, sh.route.p, n_fr * sizeof(RouteEntry), cudaMemcpyDeviceToDevice, s));
-        OGE_CUDA_TRY(cudaStreamSynchronize(s));
+        if ((rc = bucket_by_destination(c, sh.route.p, n_fr, sizeof(RouteEntry), 1, sh.froute_send, froute_counts, &launches))) return rc;
         clk.stop();
     }
-    OGE_CUDA_TRY(cudaStreamSynchronize(s));
+    if ((rc = read_counters(c))) return rc;
+    if (c->h_counters[CNT_ERR] & DEV_ERR_CAPACITY) return fail_msg(OGE_ERR_STATE, "shard_begin: a key is longer than the agreed entry size holds");
     resolve_clocks(c);
     c->stats.launches += launches;
-    *pub_dev = sh.pub.p;
-    *n_pub = n_list;
-    *froute_dev = sh.froute.p;
-    *n_froute = n_fr;
+    *pub_dev = sh.pub_send.p;
+    *hash_dev = sh.pub_hash.p;
+    *n_hash = n_list;
+    *froute_dev = sh.froute_send.p;
     sh.phase = 1;
     return OGE_OK;
 }
 
-int oge_gpu_shard_probe(oge_gpu_dedup_ctx *c, const void *pub_all_dev, uint64_t n_all, const void *froute_all_dev, uint64_t n_fr_all,
-                        void **pub2_dev, uint64_t *n_pub2, void **proute_dev, uint64_t *n_proute) {
+int oge_gpu_shard_probe(oge_gpu_dedup_ctx *c, const void *hash_in_dev, uint64_t n_hash_in, const void *froute_all_dev, uint64_t n_fr_all,
+                        void **pub2_dev, uint64_t *pub2_counts, void **proute_dev, uint64_t *proute_counts) {
     int rc = need_phase(c, 1, "shard_probe");
     if (rc) return rc;
-    if (!pub2_dev || !n_pub2 || !proute_dev || !n_proute || (n_all && !pub_all_dev) || (n_fr_all && !froute_all_dev))
+    if (!pub2_dev || !pub2_counts || !proute_dev || !proute_counts || (n_hash_in && !hash_in_dev) || (n_fr_all && !froute_all_dev))
         return fail_msg(OGE_ERR_INVALID_ARG, "shard_probe: null argument");
     cudaStream_t s = c->stream, s2 = c->side_stream;
     ShardState &sh = c->sh;
+    const int W = c->cfg.world;
     uint64_t launches = 0, n2 = 0, n_pr = 0;
     const uint64_t n = c->n;
+    for (int d = 0; d < W; d++) pub2_counts[d] = proute_counts[d] = 0;
+    *pub2_dev = *proute_dev = nullptr;
 
-    // ---- local couples of names published elsewhere are retracted and published (this reads the fragment
+    // ---- local pairs of names some other rank published are retracted and published (this reads the fragment
     //      array, so it comes before the fragment sort starts moving it)
-    if (sh.n_pe && n_all) {
+    if (sh.n_pe && n_hash_in) {
         PhaseClock clk(c, &c->stats.ms_join);
+        uint64_t set_slots = 1024;
+        while (set_slots < 2 * n_hash_in) set_slots <<= 1;
+        if ((rc = sh.hset.reserve(set_slots, false, s))) return rc;
+        OGE_CUDA_TRY(cudaMemsetAsync(sh.hset.p, 0, set_slots * 8, s));
+        if ((rc = launch_sh_set_build((const uint64_t *) hash_in_dev, n_hash_in, sh.hset.p, set_slots, s, &launches))) return rc;
         if ((rc = zero_counter(c, CNT_PUB))) return rc;
-        if ((rc = launch_sh_probe((const PubEntry *) pub_all_dev, n_all, shard_params(c), c->table.p, sh.n_slots, c->pair.p, c->pairf.p,
-                                  sh.pub_list.p, s, &launches)))
+        if ((rc = sh.pub_list.reserve(2 * (sh.n_pairs + sh.n_far) + 16, false, s))) return rc;
+        if (sh.n_slots && (rc = launch_sh_probe_table(c->table.p, sh.n_slots, sh.hset.p, set_slots, c->pair.p, c->pairf.p, sh.pub_list.p, c->counters.p, s, &launches)))
             return rc;
+        const ShardParams S = shard_params(c);
+        if ((rc = launch_sh_probe_pairs(c->pair_hk.p, sh.n_loc, sh.hset.p, set_slots, c->pair.p, 0, c->mate_of.p, S, sh.pub_list.p, s, &launches))) return rc;
+        if ((rc = launch_sh_probe_pairs(c->pairf_hk.p, sh.n_loc_far, sh.hset.p, set_slots, c->pairf.p, 1, c->mate_of.p, S, sh.pub_list.p, s, &launches))) return rc;
         if ((rc = read_counters(c))) return rc;
         n2 = c->h_counters[CNT_PUB];
         sh.n_retracted = c->h_counters[CNT_PAIRS_RETRACTED];
         sh.n_far_dead = c->h_counters[CNT_FAR_RETRACTED];
-        if ((rc = sh.pub2.reserve(n2 + 1, false, s))) return rc;
-        if ((rc = launch_sh_gather(sh.pub_list.p, (uint32_t) n2, c->frag.p, c->hk.p, c->tag.p, sh.pub2.p, s, &launches))) return rc;
+        if (n2) {
+            if ((rc = sh.pub_raw.reserve(n2 * sh.entry_bytes, false, s))) return rc;
+            if ((rc = launch_sh_gather2(sh.pub_list.p, (uint32_t) n2, c->frag.p, c->hk.p, c->recs(), c->off.p, sh.pub_raw.p, sh.entry_bytes, nullptr,
+                                        c->counters.p + CNT_ERR, s, &launches)))
+                return rc;
+        }
         clk.stop();
     }
+    if ((rc = bucket_by_destination(c, sh.pub_raw.p, n2, sh.entry_bytes, 0, sh.pub_send, pub2_counts, &launches))) return rc;
     // ---- side stream: the fragment ends are complete once the routed copies are in -> K3 + K4 on them,
     //      concurrently with the pair routing, the second exchange and the replay on the main stream
     sh.n_froute_all = n_fr_all;
@@ -336,7 +410,7 @@ int oge_gpu_shard_probe(oge_gpu_dedup_ctx *c, const void *pub_all_dev, uint64_t 
         if ((rc = c->frag.reserve(n_all_frag, true, s))) return rc;
         if (sh.frag_mode == 2) {
             if ((rc = c->sortbuf.reserve(n_all_frag, false, s))) return rc;
-            if ((rc = sh.scratch2.reserve(sort_scratch_bytes(std::max<uint64_t>(n_all_frag, sh.n_pe / 2 + n_all + 1024)), false, s))) return rc;
+            if ((rc = sh.scratch2.reserve(sort_scratch_bytes(std::max<uint64_t>(n_all_frag, sh.n_pe / 2 + n_hash_in + 1024)), false, s))) return rc;
         } else {
             uint64_t n_slots = 1024;
             while (n_slots < 4 * (sh.n_unpaired + n_fr_all)) n_slots <<= 1;
@@ -344,7 +418,7 @@ int oge_gpu_shard_probe(oge_gpu_dedup_ctx *c, const void *pub_all_dev, uint64_t 
             if ((rc = c->ufrag.reserve(sh.ucap, false, s))) return rc;
             if ((rc = c->ufrag2.reserve(sh.ucap, false, s))) return rc;
             if ((rc = c->uset.reserve(n_slots, false, s))) return rc;
-            if ((rc = sh.scratch2.reserve(sort_scratch_bytes(std::max<uint64_t>(sh.ucap, sh.n_pe / 2 + n_all + 1024)), false, s))) return rc;
+            if ((rc = sh.scratch2.reserve(sort_scratch_bytes(std::max<uint64_t>(sh.ucap, sh.n_pe / 2 + n_hash_in + 1024)), false, s))) return rc;
         }
         if ((rc = sh.marks_frag.reserve(n_fr_all + 16, false, s))) return rc;
         if (n == 0 && (rc = c->mate_of.reserve(1, false, s))) return rc;
@@ -414,59 +488,92 @@ int oge_gpu_shard_probe(oge_gpu_dedup_ctx *c, const void *pub_all_dev, uint64_t 
         sh.n_far_dead += n_pr ? c->h_counters[CNT_SCRATCH1] : 0;
         clk.stop();
     }
+    if ((rc = bucket_by_destination(c, sh.route.p, n_pr, sizeof(RouteEntry), 1, sh.proute_send, proute_counts, &launches))) return rc;
     OGE_CUDA_TRY(cudaStreamSynchronize(s));
     resolve_clocks(c);
     c->stats.launches += launches;
-    *pub2_dev = sh.pub2.p;
-    *n_pub2 = n2;
-    *proute_dev = sh.route.p;
-    *n_proute = n_pr;
+    *pub2_dev = sh.pub_send.p;
+    *proute_dev = sh.proute_send.p;
     sh.phase = 2;
     return OGE_OK;
 }
 
-int oge_gpu_shard_finish(oge_gpu_dedup_ctx *c, const void *w_dev, uint64_t n_w, const void *proute_all_dev, uint64_t n_all, void **marks_dev,
-                         uint64_t *n_marks, void **marks_frag_dev, uint64_t *n_marks_frag) {
-    int rc = need_phase(c, 2, "shard_finish");
+int oge_gpu_shard_replay(oge_gpu_dedup_ctx *c, const void *w_dev, uint64_t n_w, void **oroute_dev, uint64_t *oroute_counts) {
+    int rc = need_phase(c, 2, "shard_replay");
     if (rc) return rc;
-    if (!marks_dev || !n_marks || !marks_frag_dev || !n_marks_frag || (n_w && !w_dev) || (n_all && !proute_all_dev))
-        return fail_msg(OGE_ERR_INVALID_ARG, "shard_finish: null argument");
-    if (n_w >= (1ull << 30)) return fail_msg(OGE_ERR_TOO_LARGE, "shard_finish: published set too large");
+    if (!oroute_dev || !oroute_counts || (n_w && !w_dev)) return fail_msg(OGE_ERR_INVALID_ARG, "shard_replay: null argument");
+    if (n_w >= (1ull << 30)) return fail_msg(OGE_ERR_TOO_LARGE, "shard_replay: published set too large");
     cudaStream_t s = c->stream;
     ShardState &sh = c->sh;
-    uint64_t launches = 0;
+    const int W = c->cfg.world;
+    uint64_t launches = 0, n_or = 0;
     const uint64_t n = c->n;
+    sh.n_w = n_w;
+    *oroute_dev = nullptr;
+    for (int d = 0; d < W; d++) oroute_counts[d] = 0;
+    // ---- the names this rank owns, replayed over all ranks' sightings: the pairs whose key range it owns too join its
+    //      lists, the others leave for their owners
+    if (n_w) {
+        PhaseClock clk(c, &c->stats.ms_join);
+        const uint64_t pair_cap = sh.n_pairs + n_w / 2 + 16, far_cap = sh.n_far + n_w / 2 + 16;
+        if ((rc = c->pair.reserve(pair_cap, true, s))) return rc;
+        if ((rc = c->pair2.reserve(pair_cap, false, s))) return rc;
+        if ((rc = c->pairf.reserve(far_cap, true, s))) return rc;
+        if ((rc = c->pairf2.reserve(far_cap, false, s))) return rc;
+        if ((rc = sh.fm.reserve(n_w / 2 + 16, false, s))) return rc;
+        if ((rc = sh.route.reserve(n_w / 2 + 16, false, s))) return rc;
+        if ((rc = c->scratch.reserve(std::max(sort_scratch_bytes(std::max(std::max(n_w, pair_cap), far_cap)), c->scratch.cap), true, s))) return rc;
+        if (n == 0 && (rc = c->mate_of.reserve(1, false, s))) return rc;
+        if ((rc = sh.w_sort.reserve(n_w, false, s))) return rc;
+        if ((rc = sh.w_sort2.reserve(n_w, false, s))) return rc;
+        if ((rc = c->cplx_state.reserve(n_w, false, s))) return rc;
+        if ((rc = zero_counter(c, CNT_ROUTE))) return rc;
+        if ((rc = launch_sh_wbuild2((const uint8_t *) w_dev, sh.entry_bytes, (uint32_t) n_w, c->kl, sh.w_sort.p, s, &launches))) return rc;
+        E128 *sorted = nullptr;
+        if ((rc = radix_sort_128(sh.w_sort.p, sh.w_sort2.p, n_w, nullptr, 32, 96, c->scratch.p, s, &sorted, &launches))) return rc;
+        if ((rc = launch_sh_replay2(sorted, (uint32_t) n_w, (const uint8_t *) w_dev, sh.entry_bytes, c->cplx_state.p, shard_params(c), c->pair.p,
+                                    (uint32_t) c->pair.cap, c->pairf.p, (uint32_t) c->pairf.cap, c->mate_of.p, sh.fm.p, (uint32_t) sh.fm.cap,
+                                    sh.route.p, (uint32_t) sh.route.cap, s, &launches)))
+            return rc;
+        if ((rc = read_counters(c))) return rc;
+        n_or = c->h_counters[CNT_ROUTE];
+        if (n_or > sh.route.cap) return fail_msg(OGE_ERR_STATE, "shard_replay: route list overran its buffer");
+        clk.stop();
+    }
+    if ((rc = bucket_by_destination(c, sh.route.p, n_or, sizeof(RouteEntry), 1, sh.oroute_send, oroute_counts, &launches))) return rc;
+    OGE_CUDA_TRY(cudaStreamSynchronize(s));
+    resolve_clocks(c);
+    c->stats.launches += launches;
+    *oroute_dev = sh.oroute_send.p;
+    sh.phase = 3;
+    return OGE_OK;
+}
+
+int oge_gpu_shard_finish(oge_gpu_dedup_ctx *c, const void *proute_all_dev, uint64_t n_all, void **marks_dev, uint64_t *marks_counts) {
+    int rc = need_phase(c, 3, "shard_finish");
+    if (rc) return rc;
+    if (!marks_dev || !marks_counts || (n_all && !proute_all_dev)) return fail_msg(OGE_ERR_INVALID_ARG, "shard_finish: null argument");
+    cudaStream_t s = c->stream;
+    ShardState &sh = c->sh;
+    const int W = c->cfg.world;
+    uint64_t launches = 0;
+    const uint64_t n = c->n, n_w = sh.n_w;
     PassTimer timer{c->pass_ev, 48, 0, 0};
     PassTimer *tp = c->cfg.profile_events ? &timer : nullptr;
-    sh.n_w = n_w;
+    *marks_dev = nullptr;
+    for (int d = 0; d < W; d++) marks_counts[d] = 0;
 
-    // ---- replay of the published set: the pairs whose key this rank owns
-    if (n_w || n_all) {
+    // ---- pair ends other ranks handed over (their local pairs, and pairs their replay formed): the ones whose key this rank owns
+    if (n_all) {
+        PhaseClock clk(c, &c->stats.ms_select);
         const uint64_t pair_cap = sh.n_pairs + n_w / 2 + n_all + 16, far_cap = sh.n_far + n_w / 2 + n_all + 16;
         if ((rc = c->pair.reserve(pair_cap, true, s))) return rc;
         if ((rc = c->pair2.reserve(pair_cap, false, s))) return rc;
         if ((rc = c->pairf.reserve(far_cap, true, s))) return rc;
         if ((rc = c->pairf2.reserve(far_cap, false, s))) return rc;
-        if ((rc = sh.fm.reserve(n_w / 2 + n_all + 16, false, s))) return rc;
-        if ((rc = c->scratch.reserve(std::max(sort_scratch_bytes(std::max(std::max(n_w, pair_cap), far_cap)), c->scratch.cap), true, s))) return rc;
+        if ((rc = sh.fm.reserve(n_w / 2 + n_all + 16, true, s))) return rc;
+        if ((rc = c->scratch.reserve(std::max(sort_scratch_bytes(std::max(pair_cap, far_cap)), c->scratch.cap), true, s))) return rc;
         if (n == 0 && (rc = c->mate_of.reserve(1, false, s))) return rc;
-    }
-    if (n_w) {
-        PhaseClock clk(c, &c->stats.ms_join);
-        if ((rc = sh.w_sort.reserve(n_w, false, s))) return rc;
-        if ((rc = sh.w_sort2.reserve(n_w, false, s))) return rc;
-        if ((rc = c->cplx_state.reserve(n_w, false, s))) return rc;
-        if ((rc = launch_sh_wbuild((const PubEntry *) w_dev, (uint32_t) n_w, c->kl, sh.w_sort.p, s, &launches))) return rc;
-        E128 *sorted = nullptr;
-        if ((rc = radix_sort_128(sh.w_sort.p, sh.w_sort2.p, n_w, nullptr, 32, 96, c->scratch.p, s, &sorted, &launches))) return rc;
-        if ((rc = launch_sh_replay(sorted, (uint32_t) n_w, (const PubEntry *) w_dev, c->cplx_state.p, shard_params(c), c->pair.p,
-                                   (uint32_t) c->pair.cap, c->pairf.p, (uint32_t) c->pairf.cap, c->mate_of.p, sh.fm.p, (uint32_t) sh.fm.cap,
-                                   rg_table(c), s, &launches)))
-            return rc;
-        clk.stop();
-    }
-    if (n_all) {
-        PhaseClock clk(c, &c->stats.ms_select);
         if ((rc = launch_sh_receive((const RouteEntry *) proute_all_dev, n_all, shard_params(c), 6u, nullptr, 0, c->pair.p, (uint32_t) c->pair.cap,
                                     c->pairf.p, (uint32_t) c->pairf.cap, c->mate_of.p, sh.fm.p, (uint32_t) sh.fm.cap, s, &launches)))
             return rc;
@@ -595,10 +702,14 @@ int oge_gpu_shard_finish(oge_gpu_dedup_ctx *c, const void *w_dev, uint64_t n_w, 
     for (int i = 0; i < sh.side_pass_used; i++) c->stats.ms_sort_pass_kernels += ms_between(c->pass_ev[48 + 2 * i], c->pass_ev[48 + 2 * i + 1]);
     c->stats.sort_pass_launches = timer.used + sh.side_pass_used;
     c->stats.sort_pass_bytes = timer.bytes + sh.side_pass_bytes;
-    *marks_dev = sh.marks.p;
-    *n_marks = n_foreign;
-    *marks_frag_dev = sh.marks_frag.p;
-    *n_marks_frag = n_foreign_frag;
+    // both mark lists (from pairs, from fragments) leave as one, ordered by the rank that holds the record
+    if (n_foreign_frag) {
+        if ((rc = sh.marks.reserve(n_foreign + n_foreign_frag, true, s))) return rc;
+        OGE_CUDA_TRY(cudaMemcpyAsync(sh.marks.p + n_foreign, sh.marks_frag.p, n_foreign_frag * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    if ((rc = bucket_by_destination(c, sh.marks.p, n_foreign + n_foreign_frag, 4, 2, sh.marks_send, marks_counts, &launches))) return rc;
+    OGE_CUDA_TRY(cudaStreamSynchronize(s));
+    *marks_dev = sh.marks_send.p;
     sh.phase = 5;
     return OGE_OK;
 }

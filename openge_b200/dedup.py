@@ -19,7 +19,7 @@ import numpy as np
 from . import _build, header as _header
 from .bamio import BamFile
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 OGE_OK = 0
 ERRORS = {-1: "OGE_ERR_INVALID_ARG", -2: "OGE_ERR_CUDA", -3: "OGE_ERR_NOMEM", -4: "OGE_ERR_KEY_RANGE",
@@ -74,7 +74,7 @@ EXPORTS = ["oge_gpu_dedup_create", "oge_gpu_dedup_destroy", "oge_gpu_dedup_set_r
            "oge_gpu_last_error", "oge_gpu_abi_version", "oge_gpu_debug_sort128", "oge_gpu_debug_sort_bench",
            "oge_gpu_set_sort_variant", "oge_gpu_set_inflate_kernel", "oge_gpu_shard_setup", "oge_gpu_shard_begin", "oge_gpu_shard_probe",
            "oge_gpu_shard_finish", "oge_gpu_shard_apply", "oge_gpu_copy_d2d", "oge_gpu_dedup_sort", "oge_gpu_dedup_sort_order",
-           "oge_gpu_dedup_sort_stats", "oge_gpu_sizeof"]
+           "oge_gpu_dedup_sort_stats", "oge_gpu_sizeof", "oge_gpu_shard_key_bytes", "oge_gpu_shard_set_entry_bytes", "oge_gpu_shard_replay"]
 
 
 class DedupError(RuntimeError):
@@ -155,9 +155,12 @@ def _load(path):
         L.oge_gpu_set_inflate_kernel.argtypes = [C.c_int]
         L.oge_gpu_copy_d2d.argtypes = [vp, vp, vp, u64]
         L.oge_gpu_shard_setup.argtypes = [vp, u64, vp, vp, vp]
-        L.oge_gpu_shard_begin.argtypes = [vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(vp), C.POINTER(u64)]
+        L.oge_gpu_shard_key_bytes.argtypes = [vp, C.POINTER(C.c_uint32)]
+        L.oge_gpu_shard_set_entry_bytes.argtypes = [vp, C.c_uint32]
+        L.oge_gpu_shard_begin.argtypes = [vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(vp), C.POINTER(u64), C.POINTER(vp), C.POINTER(u64)]
         L.oge_gpu_shard_probe.argtypes = [vp, vp, u64, vp, u64, C.POINTER(vp), C.POINTER(u64), C.POINTER(vp), C.POINTER(u64)]
-        L.oge_gpu_shard_finish.argtypes = [vp, vp, u64, vp, u64, C.POINTER(vp), C.POINTER(u64), C.POINTER(vp), C.POINTER(u64)]
+        L.oge_gpu_shard_replay.argtypes = [vp, vp, u64, C.POINTER(vp), C.POINTER(u64)]
+        L.oge_gpu_shard_finish.argtypes = [vp, vp, u64, C.POINTER(vp), C.POINTER(u64)]
         L.oge_gpu_shard_apply.argtypes = [vp, vp, u64]
         for name in EXPORTS:
             getattr(L, name)
@@ -241,6 +244,7 @@ class DedupContext:
                      profile_events=int(profile_events), capacity_records=capacity_records, capacity_bytes=capacity_bytes, rank=rank, world=world,
                      index_base=index_base, debug_full_frag_sort=int(full_frag_sort), debug_legacy_join=int(legacy_join))
         _check(lib().oge_gpu_dedup_create(C.byref(cfg), C.byref(self._h)))
+        self.world = max(1, int(world))
         self.n = 0
         self.nbytes = 0
 
@@ -371,22 +375,42 @@ class DedupContext:
         p = np.ascontiguousarray(split_pos if len(split_pos) else [0], dtype=np.int32)
         _check(lib().oge_gpu_shard_setup(self._h, int(global_n), b.ctypes.data, r.ctypes.data, p.ctypes.data))
 
-    def _out2_call(self, fn, *args):
-        p1, c1, p2, c2 = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_uint64()
-        _check(fn(self._h, *args, C.byref(p1), C.byref(c1), C.byref(p2), C.byref(c2)))
-        return (p1.value or 0, int(c1.value)), (p2.value or 0, int(c2.value))
+    # ---- range sharding: every output list is ordered by destination rank -> (device pointer, [count per rank])
+    def _counts(self):
+        return (C.c_uint64 * max(1, self.world))()
+
+    def shard_key_bytes(self) -> int:
+        v = C.c_uint32()
+        _check(lib().oge_gpu_shard_key_bytes(self._h, C.byref(v)))
+        return int(v.value)
+
+    def shard_set_entry_bytes(self, entry_bytes: int):
+        _check(lib().oge_gpu_shard_set_entry_bytes(self._h, int(entry_bytes)))
+        self.entry_bytes = int(entry_bytes)
 
     def shard_begin(self):
-        """-> (published round 1, routed fragment ends): each a (device pointer, item count)."""
-        return self._out2_call(lib().oge_gpu_shard_begin)
+        """-> (published entries by name owner, (hash pointer, count), routed fragment ends by key owner)"""
+        p1, c1, ph, nh, p2, c2 = C.c_void_p(), self._counts(), C.c_void_p(), C.c_uint64(), C.c_void_p(), self._counts()
+        _check(lib().oge_gpu_shard_begin(self._h, C.byref(p1), c1, C.byref(ph), C.byref(nh), C.byref(p2), c2))
+        return (p1.value or 0, list(c1)), (ph.value or 0, int(nh.value)), (p2.value or 0, list(c2))
 
-    def shard_probe(self, pub_ptr, n_pub, fr_ptr, n_fr):
-        """-> (published round 2, routed pair ends)"""
-        return self._out2_call(lib().oge_gpu_shard_probe, pub_ptr, n_pub, fr_ptr, n_fr)
+    def shard_probe(self, hash_ptr, n_hash, fr_ptr, n_fr):
+        """-> (published round 2 by name owner, routed pair ends by key owner)"""
+        p1, c1, p2, c2 = C.c_void_p(), self._counts(), C.c_void_p(), self._counts()
+        _check(lib().oge_gpu_shard_probe(self._h, hash_ptr, n_hash, fr_ptr, n_fr, C.byref(p1), c1, C.byref(p2), c2))
+        return (p1.value or 0, list(c1)), (p2.value or 0, list(c2))
 
-    def shard_finish(self, w_ptr, n_w, pr_ptr, n_pr):
-        """-> (marks from pairs, marks from fragments)"""
-        return self._out2_call(lib().oge_gpu_shard_finish, w_ptr, n_w, pr_ptr, n_pr)
+    def shard_replay(self, pub_ptr, n_pub):
+        """-> pair ends the replay formed for other ranks' key ranges, by key owner"""
+        p1, c1 = C.c_void_p(), self._counts()
+        _check(lib().oge_gpu_shard_replay(self._h, pub_ptr, n_pub, C.byref(p1), c1))
+        return p1.value or 0, list(c1)
+
+    def shard_finish(self, pr_ptr, n_pr):
+        """-> marks by record owner"""
+        p1, c1 = C.c_void_p(), self._counts()
+        _check(lib().oge_gpu_shard_finish(self._h, pr_ptr, n_pr, C.byref(p1), c1))
+        return p1.value or 0, list(c1)
 
     def copy_d2d(self, dst_ptr, src_ptr, nbytes):
         _check(lib().oge_gpu_copy_d2d(self._h, dst_ptr, src_ptr, nbytes))

@@ -735,6 +735,18 @@ int oge_bam_adopt_offsets(oge_bam_file *f, const uint64_t *offsets, uint64_t nre
     return 0;
 }
 
+int oge_bam_set_sort_order(oge_bam_file *f, const char *so) {
+    if (!f || !so) return fail(OGE_BAM_ERR_ARG, "set_sort_order: null argument");
+    static const char *names[] = {"unknown", "unsorted", "queryname", "coordinate"};
+    for (int i = 0; i < 4; i++)
+        if (!strcmp(so, names[i])) {
+            f->header.sort = i;
+            if (f->header.version.empty()) f->header.version = "1.4";
+            return 0;
+        }
+    return fail(OGE_BAM_ERR_ARG, "Unknown sort order '%s'.", so);
+}
+
 int oge_bam_frame_records(oge_bam_file *f) {
     if (!f || !f->comp || !f->stream) return fail(OGE_BAM_ERR_ARG, "frame_records: call oge_bam_open_bgzf and fill oge_bam_records_buffer first");
     const double t0 = now_s();

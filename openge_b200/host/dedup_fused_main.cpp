@@ -41,13 +41,14 @@ static void die(const char *what, const char *msg) {
 static void usage() {
     fprintf(stderr,
             "usage: oge_dedup_fused [dedup] in.bam -o out.bam [-r] [-v] [-t threads] [-c level] [-F bam|rawbam] [--nopg] [--stats]\n"
-            "                       [--device N] [--cpu-inflate] [--pinned] [--nosplit] [-T tmpdir] [-d]\n");
+            "                       [--device N] [--cpu-inflate] [--pinned] [--nosplit] [-T tmpdir] [-d]\n"
+            "                       [--sort | -M]   coordinate sort on the GPU in front of the dedup (= openge mergesort -M)\n");
     exit(-1);
 }
 
 int main(int argc, char **argv) {
     std::string in, out, format;
-    bool remove_dups = false, verbose = false, nopg = false, stats = false, cpu_inflate = false, pinned = false;
+    bool remove_dups = false, verbose = false, nopg = false, stats = false, cpu_inflate = false, pinned = false, sort_first = false;
     int threads = 0, level = 6, device = 0;
     std::string command_line = "openge ";      // commands/commands.cpp:36-40
     for (int i = 1; i < argc; i++) {
@@ -71,6 +72,7 @@ int main(int argc, char **argv) {
         else if (a == "--nopg") nopg = true;
         else if (a == "--nosplit" || a == "-d" || a == "--nothreads") continue;
         else if (a == "--stats") stats = true;
+        else if (a == "--sort" || a == "-M") sort_first = true;      // `openge mergesort -M`: coordinate sort in front of the dedup
         else if (a == "--cpu-inflate") cpu_inflate = true;
         else if (a == "--pinned") pinned = true;
         else if (a == "--device") device = atoi(need());
@@ -143,6 +145,7 @@ int main(int argc, char **argv) {
         }
         t_framed = now_s();
         if (verbose) fprintf(stderr, "Read %llu records.\n", (unsigned long long) n);
+        if (sort_first && (rc = oge_gpu_dedup_sort(ctx))) die("ReadSorter (GPU): sort", oge_gpu_last_error());
         if ((rc = oge_gpu_dedup_run(ctx))) die("MarkDuplicates (GPU): run", oge_gpu_last_error());
         flags.resize(n ? n : 1);
         if ((rc = oge_gpu_dedup_flags(ctx, flags.data(), n))) die("MarkDuplicates (GPU): flags", oge_gpu_last_error());
@@ -160,9 +163,27 @@ int main(int argc, char **argv) {
         if (verbose) fprintf(stderr, "Read %llu records.\n", (unsigned long long) n);
         if ((rc = oge_gpu_dedup_push(ctx, oge_bam_records(bam), oge_bam_records_bytes(bam), oge_bam_offsets(bam), n)))
             die("MarkDuplicates (GPU): push", oge_gpu_last_error());
+        if (sort_first && (rc = oge_gpu_dedup_sort(ctx))) die("ReadSorter (GPU): sort", oge_gpu_last_error());
         if ((rc = oge_gpu_dedup_run(ctx))) die("MarkDuplicates (GPU): run", oge_gpu_last_error());
         flags.resize(n ? n : 1);
         if ((rc = oge_gpu_dedup_flags(ctx, flags.data(), n))) die("MarkDuplicates (GPU): flags", oge_gpu_last_error());
+        if (sort_first && n) {      // the records come back in their new order
+            std::vector<uint64_t> offs(n + 1);
+            uint64_t got_bytes = 0, got_n = 0;
+            if ((rc = oge_gpu_dedup_pull(ctx, oge_bam_records(bam), oge_bam_records_bytes(bam), offs.data(), n + 1, &got_bytes, &got_n)))
+                die("ReadSorter (GPU): pull", oge_gpu_last_error());
+            if ((rc = oge_bam_adopt_offsets(bam, offs.data(), n))) die("Error reading BAM", oge_bam_last_error());
+        }
+    }
+    if (sort_first) {
+        oge_bam_set_sort_order(bam, "coordinate");      // read_sorter.cpp:256-258
+        if (verbose) {
+            uint64_t tied = 0, rounds = 0, sl = 0;
+            float ms = 0;
+            oge_gpu_dedup_sort_stats(ctx, &tied, &rounds, &sl, &ms);
+            fprintf(stderr, "Sorted %llu records by coordinate on the GPU in %.3f ms (%llu tied on position, %llu name rounds, %llu kernel launches).\n",
+                    (unsigned long long) n, ms, (unsigned long long) tied, (unsigned long long) rounds, (unsigned long long) sl);
+        }
     }
     oge_gpu_dedup_stats st;
     oge_gpu_dedup_get_stats(ctx, &st);

@@ -1,32 +1,33 @@
 """Range-sharded dedup over several GPUs: host orchestration.
 
-One coordinate-sorted file is cut into contiguous record ranges, one per rank.  Each rank keeps its
-records, end entries, sorts and selects on its own GPU; small lists cross ranks in three exchanges per
-run, each delivering every rank's lists to every rank with an all-to-all (NCCL on GPUs, gloo in the
-CPU tests):
+One coordinate-sorted file is cut into contiguous record ranges, one per rank; the cuts may fall anywhere, inside
+contigs included.  Each rank keeps its records, end entries, sorts and selects on its own GPU.  What crosses ranks are
+small lists, and each goes only where it is needed -- an all-to-all with uneven splits per exchange (NCCL
+all_to_all_single on GPUs, gloo in the CPU tests), four per run:
 
-    begin   ->  published entries, round 1   (records whose RG:name key was not seen exactly twice locally)
-                + copies of the fragment ends whose key lies in another rank's coordinate range
-    probe   ->  published entries, round 2   (local couples of names published elsewhere, retracted)
-                + pair ends whose key lies in another rank's range; the fragment sort/select start on a
-                side stream and overlap the second exchange
-    finish  ->  every rank replays the published set in global file order and keeps the pairs it owns;
-                pair sort/select; marks on records of other ranks
+    begin   ->  published entries (records whose RG:name key was not seen exactly twice on the rank)  -> the rank that
+                OWNS the name (key hash mod world), which alone replays it; their 8-byte key hashes -> every other rank;
+                copies of the fragment ends whose key lies in another rank's coordinate range -> that rank
+    probe   ->  a local pair of a name published elsewhere is retracted, its two records published (round 2) -> the
+                name's owner; local pair ends whose key lies in another rank's range -> that rank; the fragment
+                sort/select start on a side stream
+    replay  ->  the owner replays its names over all ranks' sightings in global file order; pairs whose key range it
+                does not own -> the rank that does
+    finish  ->  pair sort/select over what the rank owns; marks -> the rank that holds the record
     apply       flag write
 
-The result equals the reference's single-stream `openge dedup --nosplit -v`, not its own
-split-by-chromosome mode.  The per-phase device work is behind `ShardEngine`;
-`CudaShardEngine` drives the C ABI (oge_gpu_shard_*), the test suite plugs in a numpy model of the
-same protocol (tests/sharded_model.py) to run the orchestration under gloo without a GPU.
+The result equals the reference's single-stream `openge dedup --nosplit -v`, not its own split-by-chromosome mode
+(SURVEY F2).  The per-phase device work is behind `ShardEngine`; `CudaShardEngine` drives the C ABI
+(oge_gpu_shard_*), the test suite plugs in a numpy model of the same protocol (tests/sharded_model.py) to run the
+orchestration under gloo without a GPU.
 """
 from __future__ import annotations
 
-import ctypes as C
 import time
 
 import numpy as np
 
-PUB_BYTES, ROUTE_BYTES, MARK_BYTES = 64, 32, 4
+ROUTE_BYTES, MARK_BYTES, HASH_BYTES = 32, 4, 8
 
 
 # --------------------------------------------------------------------------------------- ranges
@@ -67,15 +68,32 @@ def split_bam(bam, world: int):
     return ShardPlan(cuts, sref, spos), shards
 
 
-# --------------------------------------------------------------------------------------- engines
-class ShardEngine:
-    """Per-rank device work between the exchanges.  Lists are 1-D uint8 torch tensors on `device`."""
-    device = "cpu"
+# --------------------------------------------------------------------------------------- lists that cross ranks
+class Bucketed:
+    """What a phase hands to an exchange: items of `item` bytes ordered by destination rank, counts[d] of them for rank d.
+    `data` is a 1-D uint8 tensor or a DevChunk."""
 
-    def begin(self): raise NotImplementedError                          # -> (pub, frag_route)
-    def probe(self, pub_all, frag_route_all): raise NotImplementedError  # -> (pub2, pair_route)
-    def finish(self, pub_both, pair_route_all): raise NotImplementedError  # -> (marks, marks_frag)
-    def apply(self, marks_all): raise NotImplementedError
+    def __init__(self, data, counts, item):
+        self.data, self.counts, self.item = data, [int(c) for c in counts], int(item)
+
+    def segment(self, d):
+        t = as_tensor(self.data)
+        lo = sum(self.counts[:d]) * self.item
+        return t[lo: lo + self.counts[d] * self.item]
+
+
+class ShardEngine:
+    """Per-rank device work between the exchanges.  Inputs are 1-D uint8 torch tensors on `device`."""
+    device = "cpu"
+    entry_bytes = 64
+
+    def key_bytes(self): raise NotImplementedError                    # longest RG:name key of the rank's records
+    def set_entry_bytes(self, nbytes): raise NotImplementedError
+    def begin(self): raise NotImplementedError                        # -> (pub, hashes tensor, frag_route)
+    def probe(self, hashes_in, frag_route_in): raise NotImplementedError   # -> (pub2, pair_route)
+    def replay(self, pub_in): raise NotImplementedError               # -> owner_route
+    def finish(self, pair_route_in): raise NotImplementedError        # -> marks
+    def apply(self, marks_in): raise NotImplementedError
     def flags(self): raise NotImplementedError
 
 
@@ -87,25 +105,24 @@ class _DevView:
 
 
 class DevChunk:
-    """A list a shard call handed out: device pointer + size, valid until the next call on that context.
-    Quacks like the 1-D uint8 tensor the exchanges expect (numel, copy into a tensor slice)."""
+    """A list a shard call handed out: device pointer + size, valid until the next call on that context."""
 
     def __init__(self, engine, ptr, nbytes):
         self.engine, self.ptr, self.nbytes = engine, ptr, int(nbytes)
+        self._t = None
 
     def numel(self):
         return self.nbytes
 
-    def copy_into(self, dst):      # dst: uint8 tensor slice of the same length on the engine's device
-        if self.nbytes:
-            self.engine.ctx.copy_d2d(dst.data_ptr(), self.ptr, self.nbytes)
-
     def tensor(self):
-        torch = self.engine.torch
-        if not self.nbytes:
-            return torch.empty(0, dtype=torch.uint8, device=self.engine.device)
-        with torch.cuda.device(self.engine.device):
-            return torch.as_tensor(_DevView(self.ptr, self.nbytes), device=self.engine.device).clone()
+        if self._t is None:
+            torch = self.engine.torch
+            if not self.nbytes:
+                self._t = torch.empty(0, dtype=torch.uint8, device=self.engine.device)
+            else:
+                with torch.cuda.device(self.engine.device):
+                    self._t = torch.as_tensor(_DevView(self.ptr, self.nbytes), device=self.engine.device).clone()
+        return self._t
 
 
 def as_tensor(x):
@@ -121,7 +138,7 @@ class CudaShardEngine(ShardEngine):
         from . import dedup
         self.torch = torch
         self.device = "cuda:%d" % device
-        self.rank = rank
+        self.rank, self.world = rank, plan.world
         self.n = len(offsets) - 1
         max_len = max([l for _, l in refs], default=0)
         self.ctx = dedup.DedupContext(n_ref=len(refs), max_ref_len=max_len, device=device, rank=rank, world=plan.world,
@@ -138,8 +155,15 @@ class CudaShardEngine(ShardEngine):
             else:
                 self.ctx.push(records, offsets)
 
-    def _take(self, ptr, count, item):
-        return DevChunk(self, ptr, count * item)
+    def key_bytes(self):
+        return self.ctx.shard_key_bytes()
+
+    def set_entry_bytes(self, nbytes):
+        self.entry_bytes = int(nbytes)
+        self.ctx.shard_set_entry_bytes(nbytes)
+
+    def _bucketed(self, ptr, counts, item):
+        return Bucketed(DevChunk(self, ptr, sum(counts) * item), counts, item)
 
     def _give(self, t, item):
         torch = self.torch
@@ -148,19 +172,23 @@ class CudaShardEngine(ShardEngine):
         return (t.data_ptr() if t.numel() else None), t.numel() // item
 
     def begin(self):
-        pub, fr = self.ctx.shard_begin()
-        return self._take(*pub, PUB_BYTES), self._take(*fr, ROUTE_BYTES)
+        (pp, pc), (hp, nh), (fp, fc) = self.ctx.shard_begin()
+        return self._bucketed(pp, pc, self.entry_bytes), DevChunk(self, hp, nh * HASH_BYTES).tensor(), self._bucketed(fp, fc, ROUTE_BYTES)
 
-    def probe(self, pub_all, frag_route_all):
-        pub2, pr = self.ctx.shard_probe(*self._give(pub_all, PUB_BYTES), *self._give(frag_route_all, ROUTE_BYTES))
-        return self._take(*pub2, PUB_BYTES), self._take(*pr, ROUTE_BYTES)
+    def probe(self, hashes_in, frag_route_in):
+        (pp, pc), (rp, rc) = self.ctx.shard_probe(*self._give(hashes_in, HASH_BYTES), *self._give(frag_route_in, ROUTE_BYTES))
+        return self._bucketed(pp, pc, self.entry_bytes), self._bucketed(rp, rc, ROUTE_BYTES)
 
-    def finish(self, pub_both, pair_route_all):
-        m, mf = self.ctx.shard_finish(*self._give(pub_both, PUB_BYTES), *self._give(pair_route_all, ROUTE_BYTES))
-        return self._take(*m, MARK_BYTES), self._take(*mf, MARK_BYTES)
+    def replay(self, pub_in):
+        p, cnt = self.ctx.shard_replay(*self._give(pub_in, self.entry_bytes))
+        return self._bucketed(p, cnt, ROUTE_BYTES)
 
-    def apply(self, marks_all):
-        self.ctx.shard_apply(*self._give(marks_all, MARK_BYTES))
+    def finish(self, pair_route_in):
+        p, cnt = self.ctx.shard_finish(*self._give(pair_route_in, ROUTE_BYTES))
+        return self._bucketed(p, cnt, MARK_BYTES)
+
+    def apply(self, marks_in):
+        self.ctx.shard_apply(*self._give(marks_in, MARK_BYTES))
 
     def flags(self):
         return self.ctx.flags()
@@ -172,137 +200,49 @@ class CudaShardEngine(ShardEngine):
         self.ctx.close()
 
 
+def agree_entry_bytes(engines, dist=None, device=None):
+    """Every rank's published entries carry the whole key: 32 bytes + the longest key of ANY rank, rounded up to 32."""
+    k = max([e.key_bytes() for e in engines], default=0)
+    if dist is not None:
+        import torch
+        t = torch.tensor([k], dtype=torch.int64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        k = int(t.item())
+    nbytes = 32 + max(32, (k + 31) // 32 * 32)
+    for e in engines:
+        e.set_entry_bytes(nbytes)
+    return nbytes
+
+
 # --------------------------------------------------------------------------------------- exchanges
 class LocalExchange:
-    """All ranks live in this process (several contexts on one GPU, or the numpy model): every
-    rank's lists are simply concatenated in rank order.  `outs` = one tuple of lists per rank."""
+    """All ranks live in this process (several contexts on one GPU, or the numpy model): rank d receives, per list,
+    the segments every rank addressed to it, in rank order.  outs = one tuple of Bucketed per rank."""
 
     def __init__(self):
         self.bytes_moved = 0
 
+    def new_step(self):
+        pass
+
     def __call__(self, outs):
         import torch
-        outs = [tuple(as_tensor(t) for t in o) for o in outs]
-        k = len(outs[0])
-        self.bytes_moved += sum(int(t.numel()) for o in outs for t in o) * max(0, len(outs) - 1)
-        return tuple(torch.cat([o[j] for o in outs]) if len(outs) > 1 else outs[0][j] for j in range(k))
+        W, k = len(outs), len(outs[0])
+        res = []
+        for j in range(k):
+            per_dest = []
+            for d in range(W):
+                parts = [outs[r][j].segment(d) for r in range(W)]
+                self.bytes_moved += sum(int(p.numel()) for r, p in enumerate(parts) if r != d)
+                per_dest.append(torch.cat(parts) if W > 1 else parts[0])
+            res.append(per_dest)
+        return tuple(res)
 
 
 class AllToAllExchange:
-    """One rank per process under torch.distributed.  Every rank's lists go to every rank with
-    all_to_all_single (the path's only collective).  Returns, per list, the ranks' contributions
-    concatenated in rank order.
-
-    Two wire protocols.  Sized: the byte counts of the lists first, then one payload with uneven
-    splits (two collectives and a host round trip in between).  Framed: ONE collective of fixed-size
-    frames [k sizes | payload | padding], the frame capacity taken from the previous call at the same
-    place in the step (every rank sees every rank's sizes, so all ranks compute the same capacity); a
-    rank whose payload does not fit says so in its header and everybody falls back to the sized
-    protocol for that call.  Steady-state runs (same file shape step after step) use one collective
-    per exchange."""
-
-    HEADER = 64      # bytes: up to 7 int64 sizes + an overflow flag
-
-    def __init__(self, dist, device, timed=False, framed=True):
-        import torch
-        self.dist, self.torch, self.device = dist, torch, device
-        self.world = dist.get_world_size()
-        self.bytes_moved = 0
-        self.ms = 0.0
-        self.timed = timed and str(device).startswith("cuda")
-        self.framed = framed
-        self.cap = {}          # call site -> frame payload capacity agreed by all ranks
-        self.site = 0
-        self.calls = {"framed": 0, "sized": 0}
-
-    def new_step(self):
-        self.site = 0
-
-    def _split(self, out, per, recv_offsets):
-        torch, W = self.torch, self.world
-        res = []
-        for j in range(len(per[0])):
-            parts = []
-            for r in range(W):
-                o = recv_offsets[r] + sum(per[r][:j])
-                parts.append(out[o: o + per[r][j]])
-            res.append(torch.cat(parts) if W > 1 else parts[0])
-        return tuple(res)
-
-    def _sized(self, mine, payload):
-        torch, dist, W = self.torch, self.dist, self.world
-        k = len(mine)
-        sizes = torch.tensor([int(t.numel()) for t in mine] * W, dtype=torch.int64, device=self.device)
-        sizes_all = torch.empty(W * k, dtype=torch.int64, device=self.device)
-        dist.all_to_all_single(sizes_all, sizes)
-        per = sizes_all.view(W, k).tolist()                      # per[r][j] = bytes of rank r's list j
-        recv = [sum(p) for p in per]
-        out = torch.empty(sum(recv), dtype=torch.uint8, device=self.device)
-        if sum(recv) or payload.numel():
-            send = payload.repeat(W) if payload.numel() else payload
-            dist.all_to_all_single(out, send, output_split_sizes=recv, input_split_sizes=[int(payload.numel())] * W)
-        offs, pos = [], 0
-        for r in range(W):
-            offs.append(pos)
-            pos += recv[r]
-        self.calls["sized"] += 1
-        return self._split(out, per, offs), per
-
-    def _framed(self, mine, payload, cap):
-        torch, dist, W = self.torch, self.dist, self.world
-        k = len(mine)
-        frame = self.HEADER + cap
-        fits = int(payload.numel()) <= cap
-        hdr = torch.zeros(8, dtype=torch.int64, device=self.device)
-        hdr[:k] = torch.tensor([int(t.numel()) for t in mine], dtype=torch.int64, device=self.device)
-        hdr[7] = 0 if fits else 1
-        buf = torch.empty(frame, dtype=torch.uint8, device=self.device)
-        buf[: self.HEADER] = hdr.view(torch.uint8)
-        if fits and payload.numel():
-            buf[self.HEADER: self.HEADER + payload.numel()] = payload
-        out = torch.empty(W * frame, dtype=torch.uint8, device=self.device)
-        dist.all_to_all_single(out, buf.repeat(W))
-        heads = out.view(W, frame)[:, : self.HEADER].contiguous().view(torch.int64).view(W, 8).tolist()
-        per = [h[:k] for h in heads]
-        if any(h[7] for h in heads):
-            return None, per
-        self.calls["framed"] += 1
-        return self._split(out, per, [r * frame + self.HEADER for r in range(W)]), per
-
-    def __call__(self, outs):
-        torch = self.torch
-        (mine,) = outs
-        mine = tuple(as_tensor(t) for t in mine)
-        assert len(mine) <= 7
-        if self.timed:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        payload = torch.cat(list(mine)) if len(mine) > 1 else mine[0]
-        site, res = self.site, None
-        self.site += 1
-        if self.framed and site in self.cap:
-            res, per = self._framed(mine, payload, self.cap[site])
-        if res is None:
-            res, per = self._sized(mine, payload)
-        # capacity for the next call at this site: a quarter more than the largest contribution seen now
-        biggest = max(sum(p) for p in per)
-        self.cap[site] = max(4096, (biggest + biggest // 4 + 255) // 256 * 256)
-        if self.timed:
-            e1.record()
-            e1.synchronize()
-            self.ms += e0.elapsed_time(e1)
-        self.bytes_moved += int(payload.numel()) * (self.world - 1)
-        return res
-
-
-class GatherExchange:
-    """The same delivery (every rank's lists to every rank) as the all-gather it is: one
-    all_gather_into_tensor of fixed-size frames [sizes | payload | padding] per exchange, the frame
-    capacity agreed from the previous call at the same place in the step; the first call at a site, and
-    any call where some rank's payload outgrew the frame, gathers the sizes first and then frames of the
-    exact maximum.  No per-peer replication of the send buffer, persistent staging buffers."""
-
-    HEADER = 64
+    """One rank per process under torch.distributed: every exchange is an all-to-all with uneven splits (the path's
+    only collective) -- the item counts first, then ONE payload that carries all lists of the exchange, per destination
+    [list 0 | list 1 | ...].  outs = [tuple of Bucketed] (this rank's); returns, per list, [received tensor]."""
 
     def __init__(self, dist, device, timed=False):
         import torch
@@ -311,100 +251,80 @@ class GatherExchange:
         self.bytes_moved = 0
         self.ms = 0.0
         self.timed = timed and str(device).startswith("cuda")
-        self.cap, self.site = {}, 0
-        self.calls = {"framed": 0, "sized": 0}
-        self._send, self._recv = {}, {}
+        self.calls = 0
 
     def new_step(self):
-        self.site = 0
-
-    def _buffers(self, site, frame):
-        torch = self.torch
-        if site not in self._send or self._send[site].numel() != frame:
-            self._send[site] = torch.empty(frame, dtype=torch.uint8, device=self.device)
-            self._recv[site] = torch.empty(self.world * frame, dtype=torch.uint8, device=self.device)
-        return self._send[site], self._recv[site]
-
-    def _gather(self, site, mine, payload, cap, flag):
-        torch, dist, W, H = self.torch, self.dist, self.world, self.HEADER
-        frame = H + cap
-        buf, out = self._buffers(site, frame)
-        hdr = torch.tensor([int(t.numel()) for t in mine] + [0] * (7 - len(mine)) + [flag], dtype=torch.int64)
-        buf[:H] = hdr.view(torch.uint8).to(self.device, non_blocking=True)
-        if not flag:
-            pos = H
-            for t in mine:      # straight into the frame: no intermediate tensors
-                n = int(t.numel())
-                if n:
-                    if isinstance(t, DevChunk):
-                        t.copy_into(buf[pos: pos + n])
-                    else:
-                        buf[pos: pos + n] = t
-                pos += n
-        dist.all_gather_into_tensor(out, buf)
-        heads = out.view(W, frame)[:, :H].contiguous().view(torch.int64).view(W, 8).cpu().tolist()
-        return out, heads, frame
+        pass
 
     def __call__(self, outs):
-        torch, W, H = self.torch, self.world, self.HEADER
+        torch, dist, W = self.torch, self.dist, self.world
         (mine,) = outs
         k = len(mine)
-        assert k <= 7
         if self.timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        total = sum(int(t.numel()) for t in mine)
-        payload = None
-        site = self.site
-        self.site += 1
-        out = None
-        if site in self.cap:
-            cap = self.cap[site]
-            fits = total <= cap
-            out, heads, frame = self._gather(site, mine, payload, cap, 0 if fits else 1)
-            if any(h[7] for h in heads):
-                out = None
-            else:
-                self.calls["framed"] += 1
-        if out is None:      # sizes first (a frame without payload), then frames of the exact maximum
-            _, heads, _ = self._gather(("sz", site), mine, payload, 0, 1)
-            cap = max(256, (max(sum(h[:k]) for h in heads) + 255) // 256 * 256)
-            out, heads, frame = self._gather(site, mine, payload, cap, 0)
-            self.calls["sized"] += 1
-        per = [h[:k] for h in heads]
-        res = []
+        items = [b.item for b in mine]
+        send_counts = torch.tensor([[b.counts[d] for b in mine] for d in range(W)], dtype=torch.int64, device=self.device)
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts)
+        rc = recv_counts.tolist()                                    # rc[r][j] = items of list j rank r addressed to this rank
+        in_split = [sum(mine[j].counts[d] * items[j] for j in range(k)) for d in range(W)]
+        out_split = [sum(rc[r][j] * items[j] for j in range(k)) for r in range(W)]
+        parts = [mine[j].segment(d) for d in range(W) for j in range(k)]
+        send = torch.cat(parts) if parts else torch.empty(0, dtype=torch.uint8, device=self.device)
+        recv = torch.empty(sum(out_split), dtype=torch.uint8, device=self.device)
+        dist.all_to_all_single(recv, send, output_split_sizes=out_split, input_split_sizes=in_split)
+        res, base = [], []
+        pos = 0
+        for r in range(W):
+            base.append(pos)
+            pos += out_split[r]
         for j in range(k):
-            parts = []
+            pieces = []
             for r in range(W):
-                o = r * frame + H + sum(per[r][:j])
-                parts.append(out[o: o + per[r][j]])
-            res.append(torch.cat(parts))      # a copy: `out` is reused by the next step
-        biggest = max(sum(p) for p in per)
-        self.cap[site] = max(4096, (biggest + biggest // 4 + 255) // 256 * 256)
+                o = base[r] + sum(rc[r][i] * items[i] for i in range(j))
+                pieces.append(recv[o: o + rc[r][j] * items[j]])
+            res.append([torch.cat(pieces) if W > 1 else pieces[0]])
         if self.timed:
             e1.record()
             e1.synchronize()
             self.ms += e0.elapsed_time(e1)
-        self.bytes_moved += total * (W - 1)
+        self.bytes_moved += int(send.numel()) - in_split[dist.get_rank()]
+        self.calls += 1
         return tuple(res)
 
 
 # --------------------------------------------------------------------------------------- the protocol
-def run_phases(engines, exchange):
-    """Drive one sharded run over the local `engines` (one per process under torch.distributed, or
-    all ranks in-process): three exchanges.  Afterwards every engine's flags() are final."""
+def _hash_bucket(hashes, rank, world):
+    """The key hashes of a rank's published entries go to every OTHER rank: the same bytes once per destination."""
+    n = int(hashes.numel()) // HASH_BYTES
+    counts = [0 if d == rank else n for d in range(world)]
+    data = hashes.repeat(world - 1) if world > 1 and n else hashes[:0]
+    return Bucketed(data, counts, HASH_BYTES)
+
+
+def run_phases(engines, exchange, ranks=None, world=None):
+    """Drive one sharded run over the local `engines` (one per process under torch.distributed, or all ranks
+    in-process): four exchanges.  Afterwards every engine's flags() are final."""
     import torch
-    if hasattr(exchange, "new_step"):
-        exchange.new_step()
-    pub_all, frag_route_all = exchange([e.begin() for e in engines])
-    pub2_all, pair_route_all = exchange([e.probe(pub_all, frag_route_all) for e in engines])
-    w = torch.cat([pub_all, pub2_all]) if pub2_all.numel() else pub_all
-    marks_a, marks_b = exchange([e.finish(w, pair_route_all) for e in engines])
-    marks_all = torch.cat([marks_a, marks_b]) if marks_b.numel() else marks_a
-    for e in engines:
-        e.apply(marks_all)
-    return {"published": int(w.numel()) // PUB_BYTES, "routed": (int(frag_route_all.numel()) + int(pair_route_all.numel())) // ROUTE_BYTES,
-            "marks": int(marks_all.numel()) // MARK_BYTES}
+    exchange.new_step()
+    W = world or len(engines)
+    ranks = ranks if ranks is not None else list(range(len(engines)))
+    cat = lambda a, b: torch.cat([a, b]) if b.numel() else a      # noqa: E731
+    b = [e.begin() for e in engines]
+    pub_in, fr_in, hash_in = exchange([(o[0], o[2], _hash_bucket(o[1], r, W)) for o, r in zip(b, ranks)])
+    p = [e.probe(h, f) for e, h, f in zip(engines, hash_in, fr_in)]
+    pub2_in, pr_in = exchange(p)
+    o = [e.replay(cat(a, a2)) for e, a, a2 in zip(engines, pub_in, pub2_in)]
+    (or_in,) = exchange([(x,) for x in o])
+    m = [e.finish(cat(a, a2)) for e, a, a2 in zip(engines, pr_in, or_in)]
+    (m_in,) = exchange([(x,) for x in m])
+    for e, t in zip(engines, m_in):
+        e.apply(t)
+    E = engines[0].entry_bytes if engines else 64
+    return {"published": sum(int(a.numel()) + int(a2.numel()) for a, a2 in zip(pub_in, pub2_in)) // E,
+            "routed": sum(int(a.numel()) + int(c.numel()) + int(d.numel()) for a, c, d in zip(fr_in, pr_in, or_in)) // ROUTE_BYTES,
+            "marks": sum(int(t.numel()) for t in m_in) // MARK_BYTES, "entry_bytes": E}
 
 
 def dedup_in_process(bam, world: int, device: int = 0):
@@ -412,6 +332,7 @@ def dedup_in_process(bam, world: int, device: int = 0):
     plan, shards = split_bam(bam, world)
     engines = [CudaShardEngine(rec, off, bam.text, bam.refs, plan, r, device=device) for r, (rec, off) in enumerate(shards)]
     try:
+        agree_entry_bytes(engines)
         info = run_phases(engines, LocalExchange())
         flags = np.concatenate([e.flags() for e in engines]) if engines else np.zeros(0, np.uint16)
         info["stats"] = [e.stats() for e in engines]
@@ -422,19 +343,66 @@ def dedup_in_process(bam, world: int, device: int = 0):
 
 
 # --------------------------------------------------------------------------------------- bench support
+def _genome_slices(contigs, world):
+    """Equal slices of the concatenated genome, one per rank: -> per rank a list of pieces (contig index, start, length).
+    The cuts fall wherever they fall -- inside contigs, as the cuts of a real range-sharded file do."""
+    total = sum(l for _, l in contigs)
+    cuts = [total * r // world for r in range(world + 1)]
+    out = []
+    for r in range(world):
+        lo, hi, pos, pieces = cuts[r], cuts[r + 1], 0, []
+        for ci, (_, ln) in enumerate(contigs):
+            a, b = max(lo, pos), min(hi, pos + ln)
+            if b - a >= 4000:      # a sliver is not worth a piece (the generator needs room for an insert)
+                pieces.append((ci, a - pos, b - a))
+            pos += ln
+        out.append(pieces)
+    return out
+
+
+def _straddlers(contigs, slices, read_len, seed):
+    """Pairs whose two reads lie on either side of a cut between two ranks (what a 300-bp insert does at every cut of a real
+    file), plus three-sighting names across a cut: a few hundred records per cut, built identically on every rank."""
+    from . import bamio
+    rng = np.random.default_rng(seed)
+    recs = []
+    L = read_len
+    seq = ("ACGT" * (L // 4 + 1))[:L]
+    for r in range(1, len(slices)):
+        if not slices[r] or not slices[r - 1]:
+            continue
+        ci, start, _ = slices[r][0]
+        if start == 0:
+            continue      # the cut coincides with a contig start: nothing can straddle it
+        for k in range(160):
+            ins = int(rng.integers(L + 20, 520))
+            p1 = start - int(rng.integers(1, ins - 10))        # first read starts before the cut ...
+            p2 = p1 + ins - L                                  # ... its mate (reverse strand) ends behind it
+            if p1 < 0 or p2 < start:
+                p2 = max(p2, start)
+            name = "cut%d_%05d" % (r, k // (2 if k % 8 == 0 else 1))      # every eighth pair is a copy of its predecessor's name: 4 sightings
+            q1, q2 = int(rng.integers(20, 41)), int(rng.integers(20, 41))
+            tags = bamio.tag_z("RG", "rg1")
+            recs.append((ci, p1, bamio.build_record(name, 99, ci, p1, 60, "%dM" % L, ci, p2, ins, seq, q1, tags)))
+            recs.append((ci, p2, bamio.build_record(name, 147, ci, p2, 60, "%dM" % L, ci, p1, -ins, seq, q2, tags)))
+            if k % 5 == 0:      # duplicates of the straddling pair: same ends, other name
+                recs.append((ci, p1, bamio.build_record(name + "d", 99, ci, p1, 60, "%dM" % L, ci, p2, ins, seq, q2, tags)))
+                recs.append((ci, p2, bamio.build_record(name + "d", 147, ci, p2, 60, "%dM" % L, ci, p1, -ins, seq, q1, tags)))
+    recs.sort(key=lambda t: (t[0], t[1]))
+    return bamio.concat_records([t[2] for t in recs])
+
+
 def make_rank_shard(workload, scale, rank, world, pinned=True):
-    """Synthetic shard of rank `rank` for the weak-scaling bench: the genome is `world` copies of the
-    workload's contig set; rank r draws the workload's reads on its own copy (own seed), and every
-    rank draws the same small overlay of pairs whose mates lie on two different ranks' contigs
-    (0.5 % of the pairs, 10 % of them duplicates of each other) and merges in the overlay records that
-    fall on its contigs.  The concatenation of the shards is one coordinate-sorted file.
-    -> (records, offsets, header text, contigs, keepalive)"""
+    """Synthetic shard of rank `rank` of a range-sharded file (weak scaling: every rank holds 1/8 of the workload at the given
+    scale, so that 8 ranks hold the whole of it).  The genome is the workload's own contig set; rank r draws its reads on
+    slice r of the concatenated genome -- the cuts fall inside contigs -- with its own seed; every rank adds the records of
+    two small overlays that fall into its slice, generated identically everywhere: pairs whose mates lie on different
+    contigs (0.5 % of the pairs: most of them cross ranks) and pairs that straddle the cuts.  The concatenation of the
+    shards is one coordinate-sorted file.  -> (records, offsets, header text, contigs, keepalive)"""
     from . import dedup, synth
     cfg, contigs, rgs = synth.config(workload, scale)
-    nc = len(contigs)
-    if nc * world > 256:
-        raise ValueError("contig table holds 256 entries: %d ranks x %d contigs" % (world, nc))
-    all_contigs = [("c%d_%s" % (r, name), ln) for r in range(world) for name, ln in contigs]
+    per_rank = max(64, int(cfg.n_templates) // 8)
+    slices = _genome_slices(contigs, world)
     hold = {}
 
     def alloc(tag):
@@ -445,18 +413,75 @@ def make_rank_shard(workload, scale, rank, world, pinned=True):
             return np.empty(nbytes + 64, dtype=np.uint8)[:nbytes]
         return f
 
-    main = synth.restrict(cfg, all_contigs, rank * nc, (rank + 1) * nc, seed=cfg.seed * 1000 + rank, name_base=rank << 40)
+    pieces = slices[rank]
+    main = synth.SynthCfg.from_buffer_copy(bytes(cfg))
+    main.seed = cfg.seed * 1000 + rank
+    main.n_templates = per_rank
+    main.n_contigs = len(pieces)
+    for i, (_, _, ln) in enumerate(pieces):
+        main.contig_len[i] = ln
+    main.contig_lo = main.contig_hi = 0
     main.cross_contig_frac = 0.0
     rec, offs = synth.generate(main, records_out=alloc("main") if world == 1 else None)
+    synth.remap_pieces(rec, offs, [p[0] for p in pieces], [p[1] for p in pieces])
     if world > 1:
-        over = synth.restrict(cfg, all_contigs, 0, nc * world, seed=cfg.seed * 7919 + 17, name_base=1 << 60)
-        over.n_templates = max(16, int(cfg.n_templates * world * 0.005))
+        lo = (pieces[0][0], pieces[0][1])
+        hi = (pieces[-1][0], pieces[-1][1] + pieces[-1][2])
+        over = synth.SynthCfg.from_buffer_copy(bytes(cfg))
+        over.seed = cfg.seed * 7919 + 17
+        over.n_templates = max(16, int(per_rank * world * 0.005))
         over.cross_contig_frac, over.dup_frac = 1.0, 0.10
         over.single_frac = over.mate_unmapped_frac = over.unmapped_pair_frac = over.secondary_frac = over.supplementary_frac = 0.0
         orec, ooffs = synth.generate(over)
-        keep = synth.records_on_contigs(orec, ooffs, rank * nc, (rank + 1) * nc)
-        rec, offs = synth.merge_sorted(rec, offs, orec, ooffs, keep, records_out=alloc("merged"))
-    return rec, offs, synth.header_text(all_contigs, rgs), all_contigs, hold
+        rec, offs = synth.merge_sorted(rec, offs, orec, ooffs, synth.records_in_range(orec, ooffs, lo, hi))
+        srec, soffs = _straddlers(contigs, slices, int(cfg.read_len), cfg.seed * 31 + 7)
+        rec, offs = synth.merge_sorted(rec, offs, srec, soffs, synth.records_in_range(srec, soffs, lo, hi), records_out=alloc("merged"))
+    return rec, offs, synth.header_text(contigs, rgs), contigs, hold
+
+
+def parity_pass(workload, rank, world, local_rank, dist, dev, checker, reads=2_000_000):
+    """Untimed: a `reads`-record file of the same shape, sharded over the same ranks through the same NCCL exchanges, its
+    flags gathered on rank 0 and compared record by record with `checker(records, offsets, header text) -> flags` run over
+    the whole file (the caller -- bench.py, the tests -- supplies the CPU oracle; rank 0 regenerates every rank's shard: the
+    generator is deterministic).  -> verdict dict on rank 0, None elsewhere."""
+    import torch
+    from . import synth
+    cfg, _, _ = synth.config(workload, 1.0)
+    scale = max(1e-6, reads / (2.0 * int(cfg.n_templates)) * 8.0 / world)
+    rec, offs, text, contigs, hold = make_rank_shard(workload, scale, rank, world, pinned=False)
+    n = len(offs) - 1
+    mine = torch.tensor([n] + list(_first_key(rec, offs, 0) if n else (-1, -1)), dtype=torch.int64, device=dev)
+    allv = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allv, mine)
+    counts = [int(v[0]) for v in allv]
+    bases = [0]
+    for c in counts:
+        bases.append(bases[-1] + c)
+    plan = ShardPlan(bases, [int(v[1]) for v in allv[1:]], [int(v[2]) for v in allv[1:]])
+    eng = CudaShardEngine(rec, offs, text, contigs, plan, rank, device=local_rank)
+    try:
+        agree_entry_bytes([eng], dist, dev)
+        info = run_phases([eng], AllToAllExchange(dist, dev), ranks=[rank], world=world)
+        flags = torch.from_numpy(eng.flags().astype(np.int32)).to(dev)
+    finally:
+        eng.close()
+    pad = torch.zeros(max(counts), dtype=torch.int32, device=dev)
+    pad[:n] = flags
+    got = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(got, pad)
+    if rank != 0:
+        return None
+    parts = [make_rank_shard(workload, scale, r, world, pinned=False) for r in range(world)]
+    whole = np.concatenate([p[0] for p in parts])
+    wo = [np.zeros(1, np.uint64)]
+    acc = 0
+    for p in parts:
+        wo.append(p[1][1:] + np.uint64(acc))
+        acc += int(p[1][-1])
+    want = checker(whole, np.concatenate(wo), text)
+    have = np.concatenate([g[:c].cpu().numpy().astype(np.uint16) for g, c in zip(got, counts)])
+    return {"checked": True, "records": int(len(want)), "mismatches": int((have != want).sum()), "published": info["published"],
+            "routed": info["routed"], "marks": info["marks"], "through": "NCCL all_to_all_single, %d ranks" % world}
 
 
 def bench(args, rank, world, local_rank, rec, offs, text, contigs, metric, workload_name):
@@ -483,8 +508,14 @@ def bench(args, rank, world, local_rank, rec, offs, text, contigs, metric, workl
         bases.append(bases[-1] + c)
     plan = ShardPlan(bases, [int(v[1]) for v in allv[1:]], [int(v[2]) for v in allv[1:]])
 
+    # untimed: the same path on a small file of the same shape, record by record against the oracle
+    parity = None
+    if not args.no_oracle_check:
+        parity = parity_pass(args.workload, rank, world, local_rank, dist, dev, benchmod.oracle_flags)
+
     eng = CudaShardEngine(rec, offs, text, contigs, plan, rank, device=local_rank, pinned_ptr=rec.ctypes.data, profile_events=True)
-    ex = (AllToAllExchange if os.environ.get("OGE_EXCHANGE") == "alltoall" else GatherExchange)(dist, dev, timed=True)
+    entry_bytes = agree_entry_bytes([eng], dist, dev)
+    ex = AllToAllExchange(dist, dev, timed=True)
 
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
@@ -493,7 +524,7 @@ def bench(args, rank, world, local_rank, rec, offs, text, contigs, metric, workl
         # around the whole step see all of it: device phases, exchanges, and whatever overlaps them
         ex.ms = 0.0
         e0.record()
-        info = run_phases([eng], ex)
+        info = run_phases([eng], ex, ranks=[rank], world=world)
         e1.record()
         e1.synchronize()
         st = eng.stats()
@@ -507,14 +538,12 @@ def bench(args, rank, world, local_rank, rec, offs, text, contigs, metric, workl
     torch.cuda.synchronize()
     sampler.mark_begin()
     t0 = time.perf_counter()
-    ms, pass_ms, pass_bytes, pass_launches, launches, ex_ms = [], 0.0, 0, 0, 0, 0.0
+    ms, sts, launches, ex_ms = [], [], 0, 0.0
     for _ in range(args.steps):
         m, st, info, xm = step()
         ms.append(m)
+        sts.append(st)
         ex_ms += xm
-        pass_ms += st["ms_sort_pass_kernels"]
-        pass_bytes += st["sort_pass_bytes"]
-        pass_launches += st["sort_pass_launches"]
         launches += st["launches"]
     dist.barrier()
     torch.cuda.synchronize()
@@ -523,7 +552,8 @@ def bench(args, rank, world, local_rank, rec, offs, text, contigs, metric, workl
     clocks = sampler.stop()
 
     # max over ranks of the event-timed step
-    t = torch.tensor([float(np.mean(ms)), ex_ms / args.steps, float(st["n_duplicates"]), float(n), wall_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([float(np.mean(ms)), ex_ms / args.steps, float(st["n_duplicates"]), float(n), wall_ms,
+                      float(info["published"]), float(info["routed"]), float(info["marks"])], dtype=torch.float64, device=dev)
     mx = t.clone()
     dist.all_reduce(mx, op=dist.ReduceOp.MAX)
     sm = t.clone()
@@ -540,7 +570,7 @@ def bench(args, rank, world, local_rank, rec, offs, text, contigs, metric, workl
         t1 = time.perf_counter()
         if n:
             eng.ctx.push_async(rec.ctypes.data, int(rec.nbytes), eng._off_pin.ptr, n)
-        run_phases([eng], ex)
+        run_phases([eng], ex, ranks=[rank], world=world)
         eng.ctx.flags(flags_pin.array.view(np.uint16)[:n])
         dist.barrier()
         e2e.append(time.perf_counter() - t1)
@@ -551,33 +581,49 @@ def bench(args, rank, world, local_rank, rec, offs, text, contigs, metric, workl
 
     if rank == 0:
         peak, peak_src = benchmod.load_peaks()
-        achieved = (pass_bytes / 1e9) / (pass_ms * 1e-3) if pass_ms > 0 else 0.0
-        traffic = benchmod.load_traffic()
+        mean = lambda f: float(np.mean([f(s) for s in sts]))      # noqa: E731
+        k1_ms = mean(lambda s: s["ms_kernel"]["endbuild"])
+        a_parse = benchmod.parse_bytes_per_read(rec, offs, n)
+        n_pe = 2 * st["n_local_pairs"] + st["n_join_leftovers"]
+        k1_bytes = n * a_parse + st["n_frag_entries"] * 16 + n_pe * 24
+        pass_ms, pass_bytes, pass_launches = mean(lambda s: s["ms_sort_pass_kernels"]), mean(lambda s: s["sort_pass_bytes"]), mean(lambda s: s["sort_pass_launches"])
+        cpu = None
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            sb = benchmod.sample_bam(args.workload, 1_000_000)
+            secs, kind = benchmod.cpu_reference_run(sb, cores, reps=1, timeout=300)
+            cpu = {"value": sb.n / secs[0], "unit": "reads/s", "cores": cores if kind == "reference" else 1, "kind": kind,
+                   "sample": "%d reads of workload %s (same generator, scaled), one process on rank 0's host cores" % (sb.n, args.workload)}
         line = {
             "metric": metric, "value": total_reads / (ms_per_step * 1e-3), "unit": "reads/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64", "data": "synthetic",
-            "config": {"workload": "%s x %d ranks: every rank holds one coordinate range (a copy of the contig set) of a "
-                                   "%d-read file; 0.5%% of the pairs have their mates on two different ranks" % (workload_name, world, total_reads),
+            "config": {"workload": "%s, range-sharded over %d ranks: rank r holds slice r of the concatenated genome (the cuts fall inside "
+                                   "contigs), 1/8 of the workload's reads per rank; pairs straddle every cut, 0.5%% of the pairs have "
+                                   "their mates on different contigs" % (workload_name, world),
                        "reads": total_reads, "reads_rank0": n, "l2": "inputs larger than L2",
                        "wall_ms_per_step": float(mx[4]), "exchange_ms_per_step": float(mx[1]), "device_phase_ms_rank0": st["ms_total"],
                        "timing": "CUDA events around each step (phases sync the library streams before returning), max over ranks",
                        "duplicates_flagged": total_dups,
-                       "published_entries": info["published"], "routed_entries": info["routed"], "marks_exchanged": info["marks"],
+                       "published_entries": int(sm[5]), "routed_entries": int(sm[6]), "marks_exchanged": int(sm[7]), "published_entry_bytes": entry_bytes,
                        "stage_ms_rank0": {k: st[k] for k in ("ms_endbuild", "ms_join", "ms_sort_pair", "ms_sort_frag", "ms_select", "ms_flags")},
-                       "parallelism": "range-sharded x%d, three exchanges of small lists per step (%s)" % (world, type(ex).__name__)},
+                       "parity_vs_oracle": parity,
+                       "parallelism": "range-sharded x%d; four all-to-all exchanges (NCCL all_to_all_single with uneven splits) of small lists per "
+                                      "step: published entries to the name's owner (hash mod %d) + their hashes to all + boundary fragment ends, "
+                                      "round-2 entries + local pair ends, replayed pair ends, marks" % (world, world)},
             "e2e": {"value": total_reads / float(e2e_s[0]), "unit": "reads/s", "h2d_bytes_per_step": int(h2d[0]),
                     "d2h_bytes_per_step": int(h2d[1]), "ms_per_step": float(e2e_s[0]) * 1e3},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "rs_pass_v2", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "peak_source": peak_src,
-                         "traffic": (traffic["ratio"] * pass_bytes / pass_launches) if traffic and pass_launches else None,
-                "traffic_source": ("profiles/roofline_traffic.json: dram bytes / algorithmic bytes = %.3f over the ncu --set full "
-                                   "capture of the same kernel at C2 size, applied to this run's bytes per launch" % traffic["ratio"]) if traffic else None, "launches_timed": pass_launches,
-                         "avg_launch_ms": pass_ms / pass_launches if pass_launches else None,
-                         "algorithmic_bytes_per_launch": pass_bytes / pass_launches if pass_launches else None, "rank": 0},
-            "cpu_baseline": None,
+            "roofline": {"bound": "hbm", "kernel": "endbuild_kernel (K1 end-build on rank 0, the largest stage of the step)",
+                         "achieved": (k1_bytes / 1e9) / (k1_ms * 1e-3) if k1_ms > 0 else None, "peak": peak, "unit": "GB/s",
+                         "frac": (k1_bytes / 1e9) / (k1_ms * 1e-3) / peak if k1_ms > 0 else None, "peak_source": peak_src, "traffic": None,
+                         "avg_launch_ms": k1_ms, "algorithmic_bytes_per_launch": k1_bytes, "rank": 0,
+                         "stages": [{"stage": "K3 sort pass", "kernel": "rs_pass_v2", "ms_per_step": pass_ms,
+                                     "achieved": (pass_bytes / 1e9) / (pass_ms * 1e-3) if pass_ms > 0 else None,
+                                     "frac": (pass_bytes / 1e9) / (pass_ms * 1e-3) / peak if pass_ms > 0 else None,
+                                     "launches_per_step": pass_launches}]},
+            "cpu_baseline": cpu,
         }
         print(json.dumps(line))
     eng.close()

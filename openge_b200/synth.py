@@ -162,6 +162,30 @@ def restrict(cfg: SynthCfg, all_contigs, contig_lo: int, contig_hi: int, seed: i
     return c
 
 
+def remap_pieces(rec, offs, piece_ref, piece_start, nthreads: int = 0):
+    """Records drawn on "pieces" (stretches of real contigs, each generated as a contig of its own) onto the real contigs, in
+    place: refID piece -> piece_ref[piece], pos += piece_start[piece], same for the mate fields."""
+    L = lib()
+    pr = np.ascontiguousarray(piece_ref, dtype=np.int32)
+    ps = np.ascontiguousarray(piece_start, dtype=np.int32)
+    offs = np.ascontiguousarray(offs, dtype=np.uint64)
+    L.oge_synth_remap.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int]
+    rc = L.oge_synth_remap(rec.ctypes.data, offs.ctypes.data, len(offs) - 1, pr.ctypes.data, ps.ctypes.data, len(pr), nthreads or min(32, os.cpu_count() or 1))
+    if rc != 0:
+        raise RuntimeError("oge_synth_remap failed")
+
+
+def records_in_range(rec, offs, lo, hi) -> np.ndarray:
+    """uint8 mask over the records: (refID, pos) in [lo, hi), both (ref, pos) tuples; records without a reference never."""
+    o = offs[:-1].astype(np.int64)
+    if not len(o):
+        return np.zeros(0, np.uint8)
+    rp = rec[o[:, None] + np.arange(4, 12)].copy().view("<i4").reshape(-1, 2)
+    key = rp[:, 0].astype(np.int64) * (1 << 32) + rp[:, 1].astype(np.int64)
+    klo, khi = lo[0] * (1 << 32) + lo[1], hi[0] * (1 << 32) + hi[1]
+    return ((rp[:, 0] >= 0) & (key >= klo) & (key < khi)).astype(np.uint8)
+
+
 def records_on_contigs(rec, offs, contig_lo: int, contig_hi: int) -> np.ndarray:
     """uint8 mask over the records: refID in [contig_lo, contig_hi)."""
     o = offs[:-1].astype(np.int64)

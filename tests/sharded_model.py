@@ -60,11 +60,28 @@ def pairing_key(rec, o0, o1):
     return rg + b":" + name
 
 
+def _owner_of_key(key: bytes, world: int) -> int:
+    """The rank that owns a name: any function of the key bytes all ranks agree on (the CUDA engine uses its key hash)."""
+    import zlib
+    return zlib.crc32(key) % world
+
+
+def _bucket(rows, dests, dtype, world, item=None):
+    """rows ordered by destination -> Bucketed (stable inside a destination)."""
+    from openge_b200.sharded import Bucketed
+    order = sorted(range(len(rows)), key=lambda i: dests[i])
+    arr = np.array([rows[i] for i in order], dtype=dtype) if rows else np.zeros(0, dtype=dtype)
+    counts = [sum(1 for d in dests if d == r) for r in range(world)]
+    return Bucketed(_to_t(arr), counts, item or np.dtype(dtype).itemsize)
+
+
 class ModelShardEngine(ShardEngine):
     device = "cpu"
+    entry_bytes = PUB.itemsize
 
     def __init__(self, records, offsets, header_text, plan, rank):
         self.rank, self.plan = rank, plan
+        self.world = plan.world
         self.base = plan.bases[rank]
         self.n = len(offsets) - 1
         self.records, self.offsets = records, offsets
@@ -78,9 +95,18 @@ class ModelShardEngine(ShardEngine):
         self.dup = np.zeros(self.n, dtype=bool)
         self.splits = list(zip(plan.split_ref, plan.split_pos))
 
+    def key_bytes(self):
+        return max([len(pairing_key(self.records, int(self.offsets[i]), int(self.offsets[i + 1]))) for i in range(self.n)], default=0)
+
+    def set_entry_bytes(self, nbytes):
+        pass      # the model's entries always hold 256 key bytes
+
     # rank owning the key range of (ref, coord)
     def owner(self, ref, coord):
         return sum(1 for (r, p) in self.splits if r >= 0 and (r, p) <= (ref, coord))
+
+    def record_owner(self, g):
+        return sum(1 for r in range(1, self.world) if self.plan.bases[r] <= g)
 
     def _pub(self, i):
         e = self.ends[i]
@@ -104,6 +130,10 @@ class ModelShardEngine(ShardEngine):
         return (0, e["lib"], e["ref"], e["coord"], int(e["orientation"]), -1, -1, e["score"], self.base + i, -1,
                 1 if e["read2Sequence"] != -1 else 0)
 
+    def _pub_bucket(self, ids):
+        rows = [self._pub(i) for i in ids]
+        return _bucket(rows, [_owner_of_key(r[8], self.world) for r in rows], PUB, self.world)
+
     def begin(self):
         by_key = {}
         for i in range(self.n):
@@ -119,20 +149,21 @@ class ModelShardEngine(ShardEngine):
         # copies of the fragment ends another rank owns leave; the originals stay and are skipped at selection
         self.frags = [self._frag(i) for i in range(self.n) if self.ends[i]["eligible"]]
         out = [f for f in self.frags if self.owner(int(f[2]), int(f[3])) != self.rank]
-        return _to_t(np.array([self._pub(i) for i in pub], dtype=PUB)), _to_t(np.array(out, dtype=ROUTE))
+        # "hashes" of the published keys for every other rank: the model ships the key bytes themselves (8-byte digests)
+        import hashlib
+        hashes = np.array([np.frombuffer(hashlib.blake2b(self._pub(i)[8], digest_size=8).digest(), dtype="<u8")[0] for i in pub], dtype="<u8")
+        return self._pub_bucket(pub), _to_t(hashes), _bucket(out, [self.owner(int(f[2]), int(f[3])) for f in out], ROUTE, self.world)
 
-    def probe(self, pub_all, frag_route_all):
-        pa = _from_t(pub_all, PUB)
+    def probe(self, hashes_in, frag_route_in):
+        import hashlib
+        foreign = set(_from_t(hashes_in, "<u8").tolist())
         out = []
-        for e in pa:
-            if self.base <= e["gidx"] < self.base + self.n:
-                continue
-            key = bytes(e["key"])[: e["klen"]]
-            if key in self.couples:
+        for key in list(self.couples):
+            if int(np.frombuffer(hashlib.blake2b(key, digest_size=8).digest(), dtype="<u8")[0]) in foreign:
                 out += self.couples.pop(key)
-        for r in _from_t(frag_route_all, ROUTE):
-            if self.owner(int(r["ref1"]), int(r["coord1"])) == self.rank and not (self.base <= r["idx1"] < self.base + self.n):
-                self.frags.append(tuple(r))
+        for r in _from_t(frag_route_in, ROUTE):
+            assert self.owner(int(r["ref1"]), int(r["coord1"])) == self.rank
+            self.frags.append(tuple(r))
         # the remaining local couples: those whose key another rank owns leave
         route = []
         for key, (i, j) in self.couples.items():
@@ -140,7 +171,25 @@ class ModelShardEngine(ShardEngine):
             b = np.array([self._pub(j)], dtype=PUB)[0]
             p = self._pair(a, b)
             (route if self.owner(int(p[2]), int(p[3])) != self.rank else self.pairs).append(p)
-        return _to_t(np.array([self._pub(i) for i in out], dtype=PUB)), _to_t(np.array(route, dtype=ROUTE))
+        return self._pub_bucket(out), _bucket(route, [self.owner(int(p[2]), int(p[3])) for p in route], ROUTE, self.world)
+
+    def replay(self, pub_in):
+        wa = _from_t(pub_in, PUB)
+        groups = {}
+        seen = set()
+        for e in wa:
+            assert _owner_of_key(bytes(e["key"])[: e["klen"]], self.world) == self.rank
+            if int(e["gidx"]) in seen:
+                continue
+            seen.add(int(e["gidx"]))
+            groups.setdefault(bytes(e["key"])[: e["klen"]], []).append(e)
+        route = []
+        for key, es in groups.items():
+            es.sort(key=lambda e: int(e["gidx"]))
+            for k in range(0, len(es) - 1, 2):      # (1,2), (3,4), ...: the toggle of picard_structures.h:87-96
+                p = self._pair(es[k], es[k + 1])
+                (self.pairs if self.owner(int(p[2]), int(p[3])) == self.rank else route).append(p)
+        return _bucket(route, [self.owner(int(p[2]), int(p[3])) for p in route], ROUTE, self.world)
 
     def _mark(self, g, foreign):
         if self.base <= g < self.base + self.n:
@@ -148,24 +197,10 @@ class ModelShardEngine(ShardEngine):
         else:
             foreign.append(g)
 
-    def finish(self, w, pair_route_all):
-        wa = _from_t(w, PUB)
-        groups = {}
-        seen = set()
-        for e in wa:
-            if int(e["gidx"]) in seen:
-                continue
-            seen.add(int(e["gidx"]))
-            groups.setdefault(bytes(e["key"])[: e["klen"]], []).append(e)
-        for key, es in groups.items():
-            es.sort(key=lambda e: int(e["gidx"]))
-            for k in range(0, len(es) - 1, 2):      # (1,2), (3,4), ...: the toggle of picard_structures.h:87-96
-                p = self._pair(es[k], es[k + 1])
-                if self.owner(int(p[2]), int(p[3])) == self.rank:
-                    self.pairs.append(p)
-        for r in _from_t(pair_route_all, ROUTE):
-            if self.owner(int(r["ref1"]), int(r["coord1"])) == self.rank:
-                self.pairs.append(tuple(r))
+    def finish(self, pair_route_in):
+        for r in _from_t(pair_route_in, ROUTE):
+            assert self.owner(int(r["ref1"]), int(r["coord1"])) == self.rank
+            self.pairs.append(tuple(r))
         foreign = []
         groups = {}
         for p in self.pairs:
@@ -193,12 +228,12 @@ class ModelShardEngine(ShardEngine):
                 for f in g:
                     if f is not best:
                         self._mark(int(f[8]), foreign)
-        return _to_t(np.array(foreign, dtype=MARK)), torch.empty(0, dtype=torch.uint8)
+        return _bucket(foreign, [self.record_owner(g) for g in foreign], MARK, self.world)
 
-    def apply(self, marks_all):
-        for g in _from_t(marks_all, MARK):
-            if self.base <= g < self.base + self.n:
-                self.dup[int(g) - self.base] = True
+    def apply(self, marks_in):
+        for g in _from_t(marks_in, MARK):
+            assert self.base <= g < self.base + self.n
+            self.dup[int(g) - self.base] = True
 
     def flags(self):
         f = self.flag_in.copy()

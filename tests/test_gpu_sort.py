@@ -138,3 +138,42 @@ def test_sort_at_scale_then_dedup():
     assert np.array_equal(perm, want_perm)
     r, off = reorder(sh, want_perm)
     assert np.array_equal(flags, oracle.markdup(r, off, sh.text))
+
+
+@pytest.mark.parametrize("cpu_inflate", [False, True])
+def test_fused_binary_sort_then_dedup_is_mergesort_M(cpu_inflate):
+    """`oge_dedup_fused --sort` = `openge mergesort -M`: file in any order -> coordinate-sorted, duplicate-marked file.
+    Records and flags against the oracle's chain, the reference's `mergesort -M` flags where its order is defined,
+    @HD SO:coordinate in the stored header (read_sorter.cpp:256-258)."""
+    import subprocess
+    import tempfile
+    from openge_b200 import _build, bamhost
+    exe = _build.ensure_fused()
+    if not exe or not os.path.exists(exe):
+        pytest.skip("openge_b200/host/_build/oge_dedup_fused was not built")
+    gold = dict(np.load(os.path.join(GOLDEN, "sort_order.npz")))
+    name, scale, seed = "C3", 0.01, 5
+    bam = fixtures.shuffled(synth.make(name, scale, seed=seed), seed)
+    want_perm, tied = oracle.coordinate_order(bam.records, bam.offsets)
+    r_want, o_want = reorder(bam, want_perm)
+    f_want = oracle.markdup(r_want, o_want, bam.text)
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    with tempfile.TemporaryDirectory(dir=base) as d:
+        inp, out = os.path.join(d, "in.bam"), os.path.join(d, "out.rawbam")
+        bamio.write_bam(inp, bam)
+        cmd = [exe, inp, "-o", out, "-F", "rawbam", "-v", "--nopg", "--sort"] + (["--cpu-inflate"] if cpu_inflate else [])
+        r = subprocess.run(cmd, capture_output=True, timeout=300)
+        assert r.returncode == 0, r.stderr.decode()[-2000:]
+        assert b"by coordinate on the GPU" in r.stderr
+        got = bamio.read_bam(out)
+    assert "SO:coordinate" in got.text and got.text == bamhost.header_render(bam.text.replace("SO:unsorted", "SO:coordinate"))
+    assert np.array_equal(got.offsets, o_want)
+    assert np.array_equal(got.flags(), f_want)
+    # every byte but the flag word's duplicate bit (and the bin the writer recomputes) is the input record's
+    a, b = got.records.copy(), r_want.copy()
+    for arr in (a, b):
+        starts = o_want[:-1].astype(np.int64)
+        arr[starts + 14] = 0; arr[starts + 15] = 0; arr[starts + 19] &= 0xFB
+    assert np.array_equal(a, b)
+    key = "%s_%g_%d" % (name, scale, seed)
+    assert np.array_equal(got.flags()[~tied], gold[key + "_dedup_flags"][~tied])

@@ -113,7 +113,7 @@ def _free_port():
     return p
 
 
-def _gloo_worker(rank, world, port, out_dir, kind="alltoall"):
+def _gloo_worker(rank, world, port, out_dir):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -121,35 +121,64 @@ def _gloo_worker(rank, world, port, out_dir, kind="alltoall"):
         bam = straddling_case()
         plan, shards = sharded.split_bam(bam, world)
         rec, off = shards[rank]
-        ex = (sharded.GatherExchange if kind == "gather" else sharded.AllToAllExchange)(dist, torch.device("cpu"))
-        for it in range(3):      # first run: sized protocol; later runs: one framed collective per exchange
+        ex = sharded.AllToAllExchange(dist, torch.device("cpu"))
+        for it in range(2):
             eng = ModelShardEngine(rec, off, bam.text, plan, rank)
-            if it == 2:
-                ex.cap = {k: 4096 for k in ex.cap}      # frames too small: every rank must fall back together
-            info = sharded.run_phases([eng], ex)
+            sharded.agree_entry_bytes([eng], dist, torch.device("cpu"))
+            info = sharded.run_phases([eng], ex, ranks=[rank], world=world)
             np.save(os.path.join(out_dir, "flags%d_%d.npy" % (rank, it)), eng.flags())
         np.save(os.path.join(out_dir, "flags%d.npy" % rank), eng.flags())
-        np.save(os.path.join(out_dir, "info%d.npy" % rank), np.array([info["published"], info["routed"], info["marks"], ex.bytes_moved,
-                                                                      ex.calls["framed"], ex.calls["sized"]]))
+        tot = torch.tensor([info["published"], info["routed"], info["marks"]], dtype=torch.int64)
+        dist.all_reduce(tot)
+        np.save(os.path.join(out_dir, "info%d.npy" % rank), np.array(tot.tolist() + [ex.bytes_moved, ex.calls]))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind", ["alltoall", "gather"])
-def test_orchestration_under_gloo_world2(tmp_path, kind):
+def test_orchestration_under_gloo_world2(tmp_path):
     import torch.multiprocessing as mp
     world, port = 2, _free_port()
-    mp.spawn(_gloo_worker, args=(world, port, str(tmp_path), kind), nprocs=world, join=True)
+    mp.spawn(_gloo_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     bam = straddling_case()
     want = oracle.markdup(bam.records, bam.offsets, bam.text)
     got = np.concatenate([np.load(tmp_path / ("flags%d.npy" % r)) for r in range(world)])
     assert np.array_equal(got, want)
-    for it in range(3):
+    for it in range(2):
         got = np.concatenate([np.load(tmp_path / ("flags%d_%d.npy" % (r, it))) for r in range(world)])
         assert np.array_equal(got, want)
     i0, i1 = np.load(tmp_path / "info0.npy"), np.load(tmp_path / "info1.npy")
-    assert np.array_equal(i0[:3], i1[:3]) and i0[0] > 0      # both ranks saw the same exchanged lists
-    assert i0[4] >= 3 and i0[5] >= 4 and np.array_equal(i0[4:], i1[4:])      # framed calls happened; so did the joint fall-backs
+    assert np.array_equal(i0[:3], i1[:3]) and i0[0] > 0      # published, routed, marks over all ranks
+    assert i0[4] == 8 and i1[4] == 8                           # four all-to-all exchanges per run, two runs
+
+
+def test_bench_shards_cut_inside_contigs_and_form_one_sorted_file():
+    """The weak-scaling bench's per-rank generator (C5 shape): the cuts fall inside contigs, pairs straddle them, and the
+    concatenation of the shards is one coordinate-sorted file the protocol model dedups exactly like the oracle."""
+    world = 3
+    parts = [sharded.make_rank_shard("C5", 0.00002, r, world, pinned=False) for r in range(world)]
+    text, contigs = parts[0][2], parts[0][3]
+    rec = np.concatenate([p[0] for p in parts])
+    off = bamio.frame_records(rec.tobytes())
+    o = off[:-1].astype(np.int64)
+    rp = rec[o[:, None] + np.arange(4, 12)].copy().view("<i4").reshape(-1, 2)
+    key = rp[:, 0].astype(np.int64) * (1 << 32) + rp[:, 1]
+    assert (np.diff(key) >= 0).all()                                  # one coordinate-sorted file
+    firsts = [sharded._first_key(p[0], p[1], 0) for p in parts[1:]]
+    assert any(pos > 1000 for _, pos in firsts)                       # a cut inside a contig
+    names = {}
+    for r, p in enumerate(parts):
+        for i in range(len(p[1]) - 1):
+            q = p[0][int(p[1][i]):int(p[1][i + 1])]
+            names.setdefault(q[36:36 + int(q[12]) - 1].tobytes(), set()).add(r)
+    assert sum(1 for v in names.values() if len(v) > 1) > 50          # mates on two ranks: straddlers and cross-contig pairs
+    whole = bamio.BamFile(text=text, refs=contigs, records=rec, offsets=off)
+    want = oracle.markdup(whole.records, whole.offsets, whole.text)
+    bases = np.cumsum([0] + [len(p[1]) - 1 for p in parts])
+    plan = sharded.ShardPlan(bases, [f[0] for f in firsts], [f[1] for f in firsts])
+    engines = [ModelShardEngine(p[0], p[1], text, plan, r) for r, p in enumerate(parts)]
+    info = sharded.run_phases(engines, sharded.LocalExchange())
+    assert np.array_equal(np.concatenate([e.flags() for e in engines]), want)
+    assert info["published"] > 100 and info["marks"] > 0
 
 
 # ------------------------------------------------------------------------------------------- GPU
@@ -187,22 +216,105 @@ def test_cuda_shards_larger_synthetic():
 
 
 @pytest.mark.gpu
-def test_bench_shards_concatenate_to_one_sorted_file_and_match_oracle():
-    """The weak-scaling bench's per-rank generator: the shards form one coordinate-sorted file; the
-    sharded run over them equals the oracle on the concatenation."""
-    world = 2
-    parts = [sharded.make_rank_shard("C2", 0.002, r, world, pinned=False) for r in range(world)]
+@pytest.mark.parametrize("world", [2, 3])
+def test_bench_shards_on_the_cuda_engine_match_oracle(world):
+    """The bench's C5-shaped shards (cuts inside contigs, straddling pairs, cross-contig pairs, names with four sightings across
+    a cut) through the CUDA engine, all ranks as contexts on one GPU, against the oracle on the concatenation."""
+    parts = [sharded.make_rank_shard("C5", 0.0005, r, world, pinned=False) for r in range(world)]
     text, contigs = parts[0][2], parts[0][3]
     rec = np.concatenate([p[0] for p in parts])
     off = bamio.frame_records(rec.tobytes())
-    whole = bamio.BamFile(text=text, refs=contigs, records=rec, offsets=off)
-    want = oracle.markdup(whole.records, whole.offsets, whole.text)
+    want = oracle.markdup(rec, off, text)
     bases = np.cumsum([0] + [len(p[1]) - 1 for p in parts])
-    plan = sharded.ShardPlan(bases, [sharded._first_key(parts[1][0], parts[1][1], 0)[0]], [sharded._first_key(parts[1][0], parts[1][1], 0)[1]])
+    firsts = [sharded._first_key(p[0], p[1], 0) for p in parts[1:]]
+    plan = sharded.ShardPlan(bases, [f[0] for f in firsts], [f[1] for f in firsts])
     engines = [sharded.CudaShardEngine(p[0], p[1], text, contigs, plan, r) for r, p in enumerate(parts)]
-    info = sharded.run_phases(engines, sharded.LocalExchange())
-    got = np.concatenate([e.flags() for e in engines])
-    for e in engines:
-        e.close()
-    assert np.array_equal(got, want)
-    assert info["published"] > 0
+    try:
+        sharded.agree_entry_bytes(engines)
+        info = sharded.run_phases(engines, sharded.LocalExchange())
+        got = np.concatenate([e.flags() for e in engines])
+    finally:
+        for e in engines:
+            e.close()
+    bad = np.nonzero(got != want)[0]
+    assert len(bad) == 0, "%d flag words differ, first at record %d" % (len(bad), int(bad[0]))
+    assert info["published"] > 0 and info["routed"] > 0 and info["marks"] > 0
+
+
+def _nccl_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    ndev = torch.cuda.device_count()
+    local = rank % ndev
+    torch.cuda.set_device(local)
+    # one GPU per rank where the box has them (NCCL); ranks sharing one GPU cannot use NCCL: gloo moves the (CPU-staged) lists
+    backend = "nccl" if ndev >= world else "gloo"
+    dist.init_process_group(backend, rank=rank, world_size=world)
+    try:
+        dev = torch.device("cuda", local)
+        if backend == "nccl":
+            res = sharded.parity_pass("C5", rank, world, local, dist, dev, oracle.markdup, reads=400_000)
+        else:
+            res = _parity_pass_staged(rank, world, local, dist)
+        if rank == 0:
+            np.save(os.path.join(out_dir, "verdict.npy"), np.array([res["records"], res["mismatches"], res["published"], res["routed"], res["marks"],
+                                                                    1 if backend == "nccl" else 0]))
+    finally:
+        dist.destroy_process_group()
+
+
+class _StagedExchange(sharded.AllToAllExchange):
+    """all_to_all_single over gloo for CUDA engines on a box with fewer GPUs than ranks: the lists are staged through host memory."""
+
+    def __call__(self, outs):
+        (mine,) = outs
+        cpu = tuple(sharded.Bucketed(sharded.as_tensor(b.data).cpu(), b.counts, b.item) for b in mine)
+        res = super().__call__([cpu])
+        return tuple([t[0].cuda()] for t in res)
+
+
+def _parity_pass_staged(rank, world, local, dist):
+    cpu = torch.device("cpu")
+    scale = 400_000 / (2.0 * 400_000_000) * 8.0 / world
+    rec, offs, text, contigs, _ = sharded.make_rank_shard("C5", scale, rank, world, pinned=False)
+    n = len(offs) - 1
+    mine = torch.tensor([n] + list(sharded._first_key(rec, offs, 0)), dtype=torch.int64)
+    allv = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allv, mine)
+    counts = [int(v[0]) for v in allv]
+    bases = np.cumsum([0] + counts)
+    plan = sharded.ShardPlan(bases, [int(v[1]) for v in allv[1:]], [int(v[2]) for v in allv[1:]])
+    eng = sharded.CudaShardEngine(rec, offs, text, contigs, plan, rank, device=local)
+    try:
+        sharded.agree_entry_bytes([eng], dist, cpu)
+        info = sharded.run_phases([eng], _StagedExchange(dist, cpu), ranks=[rank], world=world)
+        flags = torch.from_numpy(eng.flags().astype(np.int32))
+    finally:
+        eng.close()
+    pad = torch.zeros(max(counts), dtype=torch.int32)
+    pad[:n] = flags
+    got = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(got, pad)
+    tot = torch.tensor([info["published"], info["routed"], info["marks"]], dtype=torch.int64)
+    dist.all_reduce(tot)
+    if rank != 0:
+        return None
+    parts = [sharded.make_rank_shard("C5", scale, r, world, pinned=False) for r in range(world)]
+    whole = np.concatenate([p[0] for p in parts])
+    want = oracle.markdup(whole, bamio.frame_records(whole.tobytes()), text)
+    have = np.concatenate([g[:c].numpy().astype(np.uint16) for g, c in zip(got, counts)])
+    return {"records": len(want), "mismatches": int((have != want).sum()), "published": int(tot[0]), "routed": int(tot[1]), "marks": int(tot[2])}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2])
+def test_cuda_engine_one_process_per_rank_over_the_real_exchange(tmp_path, world):
+    """One process per rank, the CUDA engine and torch.distributed's all_to_all_single between them -- NCCL when the box has a
+    GPU per rank, gloo (lists staged through the host) when the ranks have to share one -- on a C5-shaped file with cuts inside
+    contigs and keys longer than a name tag's 29 bytes; the flags gathered on rank 0 must equal the oracle's on the whole file."""
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_nccl_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    v = np.load(tmp_path / "verdict.npy")
+    assert v[0] > 300_000 and v[1] == 0, "%d of %d flag words differ from the oracle" % (v[1], v[0])
+    assert v[2] > 0 and v[3] > 0 and v[4] > 0

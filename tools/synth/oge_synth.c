@@ -526,3 +526,43 @@ uint64_t oge_merge_sorted(const uint8_t *a, const uint64_t *a_off, uint64_t na, 
     if (out_bytes) *out_bytes = pos;
     return n;
 }
+
+/* Range shards that cut INSIDE contigs: a rank draws its reads on "pieces" (stretches of real contigs) as if every piece
+ * were a contig of its own, and this maps the records onto the real contigs afterwards: refID piece -> piece_ref[piece],
+ * pos += piece_start[piece], same for the mate fields.  Records without a reference (refID -1) are left alone.
+ * The bin field keeps its piece-relative value (nothing on the dedup path reads it). */
+typedef struct {
+    uint8_t *rec;
+    const uint64_t *off;
+    uint64_t lo, hi;
+    const int32_t *piece_ref, *piece_start;
+    int32_t n_pieces;
+} RemapJob;
+
+static void *remap_worker(void *arg) {
+    RemapJob *j = (RemapJob *) arg;
+    uint64_t i;
+    for (i = j->lo; i < j->hi; i++) {
+        uint8_t *p = j->rec + j->off[i];
+        int32_t ref, pos, mref, mpos;
+        memcpy(&ref, p + 4, 4); memcpy(&pos, p + 8, 4); memcpy(&mref, p + 24, 4); memcpy(&mpos, p + 28, 4);
+        if (ref >= 0 && ref < j->n_pieces) { pos += j->piece_start[ref]; ref = j->piece_ref[ref]; }
+        if (mref >= 0 && mref < j->n_pieces) { mpos += j->piece_start[mref]; mref = j->piece_ref[mref]; }
+        memcpy(p + 4, &ref, 4); memcpy(p + 8, &pos, 4); memcpy(p + 24, &mref, 4); memcpy(p + 28, &mpos, 4);
+    }
+    return NULL;
+}
+
+int oge_synth_remap(uint8_t *records, const uint64_t *offsets, uint64_t n, const int32_t *piece_ref, const int32_t *piece_start,
+                    int32_t n_pieces, int nthreads) {
+    pthread_t th[64];
+    RemapJob jobs[64];
+    int t, nt = nthreads < 1 ? 1 : (nthreads > 64 ? 64 : nthreads);
+    for (t = 0; t < nt; t++) {
+        jobs[t].rec = records; jobs[t].off = offsets; jobs[t].lo = n * (uint64_t) t / nt; jobs[t].hi = n * (uint64_t)(t + 1) / nt;
+        jobs[t].piece_ref = piece_ref; jobs[t].piece_start = piece_start; jobs[t].n_pieces = n_pieces;
+        if (pthread_create(&th[t], NULL, remap_worker, &jobs[t])) return -1;
+    }
+    for (t = 0; t < nt; t++) pthread_join(th[t], NULL);
+    return 0;
+}
