@@ -255,6 +255,19 @@ int oge_gpu_shard_finish(oge_gpu_dedup_ctx *ctx, const void *pair_route_in_dev, 
 /* in: the marks addressed to this rank.  K5 (mark_duplicates.cpp:443-465). */
 int oge_gpu_shard_apply(oge_gpu_dedup_ctx *ctx, const void *marks_in_dev, uint64_t n_marks_in);
 
+/* The same step driven from C++, the four exchanges done by NCCL directly (grouped ncclSend / ncclRecv per peer = an
+ * all-to-all with uneven splits, on the library's stream; NCCL is loaded at run time, libnccl.so.2).  One rank creates an id
+ * (ncclGetUniqueId) and hands its 128 bytes to the others by any means; every rank then joins with its context (cfg.rank /
+ * cfg.world); oge_gpu_shard_step runs begin -> ... -> apply.  comm_destroy is also done by oge_gpu_dedup_destroy. */
+typedef struct oge_gpu_shard_step_info {
+    uint64_t published_in, routed_in, marks_in;   /* items this rank received */
+    uint64_t exchanges, bytes_sent;
+} oge_gpu_shard_step_info;
+int oge_gpu_shard_comm_id(uint8_t *id128);
+int oge_gpu_shard_comm_init(oge_gpu_dedup_ctx *ctx, const uint8_t *id128);
+void oge_gpu_shard_comm_destroy(oge_gpu_dedup_ctx *ctx);
+int oge_gpu_shard_step(oge_gpu_dedup_ctx *ctx, oge_gpu_shard_step_info *info /* may be NULL */);
+
 /* Measurement hook for K3 alone: sorts n device-generated entries (mode 0 uniform random, 1 = high key
  * bits follow the ordinal like a coordinate-sorted file) `reps` times after one warm-up; reports the
  * average CUDA-event time of one pass launch and of the whole sort, and verifies the result on the

@@ -116,7 +116,7 @@ def build_gpu(force=False, verbose=False, testing=False):
                     flags += ["-Xptxas", "-v"]
                 objs = _nvcc_objects(cu, flags, os.path.join(CSRC, "_obj", "testing" if testing else "product"), verbose)
                 tmp = target + ".tmp.%d" % os.getpid()
-                _run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", tmp, "-lcudart"])
+                _run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", tmp, "-lcudart", "-ldl"])
                 os.replace(tmp, target)      # readers never see a half-written library
     return target
 

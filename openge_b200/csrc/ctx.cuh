@@ -53,6 +53,13 @@ struct ShardState {
     DevBuf<unsigned long long> hset;      // hashes other ranks published
     DevBuf<uint8_t> pub_raw, pub_send, froute_send, proute_send, oroute_send, marks_send;      // lists ordered by destination rank
     DevBuf<uint32_t> bk;                  // per-destination counters of the bucketing
+    // the step driven from C++ over NCCL (shard_nccl.cu): communicator, count staging, receive buffers
+    void *nccl_comm = nullptr;
+    DevBuf<uint64_t> x_cnt;
+    DevBuf<uint8_t> r_pub, r_pub2, r_froute, r_hash, r_proute, r_oroute, r_marks;
+    uint64_t x_bytes = 0, x_calls = 0;
+    uint32_t k1_route_cap = 0;            // room K1 has for boundary fragment ends (0: the sweep does it)
+    uint64_t own_lo = 0, own_hi = ~0ull;  // this rank's key range, packed
     uint32_t entry_bytes = 0;             // size of a published entry, agreed by all ranks
     uint32_t n_loc = 0, n_loc_far = 0;    // pairs the windowed join settled (their hashes are kept by list position)
     DevBuf<PubEntry> pub, pub2;           // published entries, rounds 1 and 2

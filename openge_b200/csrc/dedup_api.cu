@@ -272,6 +272,9 @@ void oge_gpu_dedup_destroy(oge_gpu_dedup_ctx *c) {
     if (c->sh.ev_main) cudaEventDestroy(c->sh.ev_main);
     if (c->sh.ev_far) cudaEventDestroy(c->sh.ev_far);
     for (auto &e : c->sh.ev_side) if (e) cudaEventDestroy(e);
+    oge_gpu_shard_comm_destroy(c);
+    c->sh.x_cnt.release(); c->sh.r_pub.release(); c->sh.r_pub2.release(); c->sh.r_froute.release(); c->sh.r_hash.release();
+    c->sh.r_proute.release(); c->sh.r_oroute.release(); c->sh.r_marks.release();
     c->sh.d_bases.release(); c->sh.pub_hash.release(); c->sh.hset.release(); c->sh.pub_raw.release(); c->sh.pub_send.release();
     c->sh.froute_send.release(); c->sh.proute_send.release(); c->sh.oroute_send.release(); c->sh.marks_send.release(); c->sh.bk.release();
     c->sh.d_split.release(); c->sh.pub.release(); c->sh.pub2.release(); c->sh.route.release(); c->sh.froute.release();
@@ -562,6 +565,10 @@ int join_stage(oge_gpu_dedup_ctx *c, bool replay_locally, JoinStage *out, uint64
     eb.rec = c->recs(); eb.off = c->off.p; eb.n = n; eb.idx_base = c->cfg.index_base;
     eb.frag = c->frag.p; eb.hk = c->hk.p; eb.tag = c->tag.p; eb.flag_in = c->flag_in.p;
     eb.counters = c->counters.p; eb.rg = rg_table(c); eb.kl = c->kl;
+    if (c->sh.on && c->cfg.world > 1 && c->sh.k1_route_cap) {      // range sharding: boundary fragment ends are listed by K1 itself
+        eb.route_out = c->sh.route.p; eb.route_cap = c->sh.k1_route_cap;
+        eb.own_lo = c->sh.own_lo; eb.own_hi = c->sh.own_hi;
+    }
     const bool fused = !c->cfg.debug_legacy_join;      // windowed join (default) or the whole-file hash join
     uint64_t n_pairs = 0, n_far = 0, n_cplx = 0, n_retracted = 0, n_far_retracted = 0, n_left = 0, n_pe = 0;
     uint64_t &launches = *launches_io;

@@ -337,6 +337,17 @@ __device__ __forceinline__ void build_end(const EndbuildParams &P, const RgSmem 
                 bits_or(ent, L.f_coord, (uint64_t) sc);
                 bits_or(ent, L.f_ref, (uint64_t) ref | ((uint64_t) lib << L.ref_bits));                  // f_lib = f_ref + ref_bits
                 is_frag = true;
+                if (P.route_out) {
+                    const uint64_t packed = ((uint64_t) ref << L.coord_bits) | (uint64_t) sc;
+                    if (packed < P.own_lo || packed >= P.own_hi) {
+                        const uint32_t at = atomicAdd(&P.counters[CNT_ROUTE], 1u);
+                        if (at < P.route_cap) {
+                            RouteEntry re;
+                            re.e = ent; re.idx2 = 0; re.kind = 0; re.rsv = 0;
+                            reinterpret_cast<RouteEntry *>(P.route_out)[at] = re;
+                        }
+                    }
+                }
                 is_unpaired = !paired;      // only these can be marked by the fragment pass (mark_duplicates.cpp:379, 517-538)
                 if (pe) {
                     KeyHasher h;

@@ -46,6 +46,11 @@ struct EndbuildParams {
     uint32_t *counters;
     RgTable rg;
     KeyLayout kl;
+    // range sharding: copies of the fragment ends whose packed key (ref << coord_bits | biased coord) lies outside this
+    // rank's key range [own_lo, own_hi) are listed for their owners right here (RouteEntry list, counters[CNT_ROUTE])
+    void *route_out = nullptr;
+    uint32_t route_cap = 0;
+    uint64_t own_lo = 0, own_hi = ~0ull;
 };
 
 int launch_endbuild(const EndbuildParams &P, uint32_t avg_rec_bytes, int sms, cudaStream_t stream, uint64_t *launches);

@@ -273,6 +273,21 @@ int oge_gpu_shard_begin(oge_gpu_dedup_ctx *c, void **pub_dev, uint64_t *pub_coun
         OGE_CUDA_TRY(cudaMemcpyAsync(sh.d_split.p, packed.data(), packed.size() * 8, cudaMemcpyHostToDevice, s));
         OGE_CUDA_TRY(cudaMemcpyAsync(sh.d_bases.p, sh.bases.data(), sh.bases.size() * 8, cudaMemcpyHostToDevice, s));
         OGE_CUDA_TRY(cudaStreamSynchronize(s));
+        sh.own_lo = c->cfg.rank > 0 ? packed[c->cfg.rank - 1] : 0;
+        sh.own_hi = c->cfg.rank + 1 < W ? packed[c->cfg.rank] : ~0ull;
+        sh.k1_route_cap = 0;
+        if (W > 1 && c->n) {      // K1 lists the boundary fragment ends itself; the sweep below is the fall-back when they do not fit
+#ifdef OGE_TESTING
+            const bool forced_sweep = getenv("OGE_ROUTE_CAP") != nullptr;
+#else
+            const bool forced_sweep = false;
+#endif
+            const uint64_t cap = std::max<uint64_t>(1u << 16, c->n / 64);
+            if (!forced_sweep) {
+                if ((rc = sh.route.reserve(cap, false, s))) return rc;
+                sh.k1_route_cap = (uint32_t) cap;
+            }
+        }
     }
     OGE_CUDA_TRY(cudaEventRecord(c->copy_done, c->copy_stream));
     OGE_CUDA_TRY(cudaStreamWaitEvent(s, c->copy_done, 0));
@@ -310,6 +325,7 @@ int oge_gpu_shard_begin(oge_gpu_dedup_ctx *c, void **pub_dev, uint64_t *pub_coun
         c->stats.ms_endbuild += ms_between(c->ev[0], c->ev[1]);
         c->stats.ms_join += ms_between(c->ev[1], c->ev[2]);
         c->stats.ms_total += ms_between(c->ev[0], c->ev[2]);
+        for (int i = 0; i < c->k_used; i++) c->stats.ms_kernel[c->k_slot[i]] += ms_between(c->k_ev[2 * i], c->k_ev[2 * i + 1]);
     }
     {
         PhaseClock clk(c, &c->stats.ms_join);
@@ -328,10 +344,13 @@ int oge_gpu_shard_begin(oge_gpu_dedup_ctx *c, void **pub_dev, uint64_t *pub_coun
     uint64_t n_fr = 0;
     if (n && W > 1) {
         PhaseClock clk(c, &c->stats.ms_select);
-        E128 *lists[1] = {c->frag.p};
-        const uint64_t counts[1] = {n};
-        const int kinds[1] = {0};
-        if ((rc = route_sweep(c, 1, lists, counts, kinds, 2, &n_fr, &launches))) return rc;
+        n_fr = sh.k1_route_cap ? c->h_counters[CNT_ROUTE] : 0;
+        if (!sh.k1_route_cap || n_fr > sh.k1_route_cap) {      // not listed by K1 (or more of them than it had room for): sweep the end entries
+            E128 *lists[1] = {c->frag.p};
+            const uint64_t counts[1] = {n};
+            const int kinds[1] = {0};
+            if ((rc = route_sweep(c, 1, lists, counts, kinds, 2, &n_fr, &launches))) return rc;
+        }
         if ((rc = bucket_by_destination(c, sh.route.p, n_fr, sizeof(RouteEntry), 1, sh.froute_send, froute_counts, &launches))) return rc;
         clk.stop();
     }

@@ -56,6 +56,11 @@ class Stats(C.Structure):
         return d
 
 
+class StepInfo(C.Structure):
+    _fields_ = [("published_in", C.c_uint64), ("routed_in", C.c_uint64), ("marks_in", C.c_uint64), ("exchanges", C.c_uint64),
+                ("bytes_sent", C.c_uint64)]
+
+
 KERNEL_NAMES = ("endbuild", "match", "emit", "global_join", "check", "select", "flags", "sort_hist")      # OGE_K_* order
 
 
@@ -74,7 +79,8 @@ EXPORTS = ["oge_gpu_dedup_create", "oge_gpu_dedup_destroy", "oge_gpu_dedup_set_r
            "oge_gpu_last_error", "oge_gpu_abi_version", "oge_gpu_debug_sort128", "oge_gpu_debug_sort_bench",
            "oge_gpu_set_sort_variant", "oge_gpu_set_inflate_kernel", "oge_gpu_shard_setup", "oge_gpu_shard_begin", "oge_gpu_shard_probe",
            "oge_gpu_shard_finish", "oge_gpu_shard_apply", "oge_gpu_copy_d2d", "oge_gpu_dedup_sort", "oge_gpu_dedup_sort_order",
-           "oge_gpu_dedup_sort_stats", "oge_gpu_sizeof", "oge_gpu_shard_key_bytes", "oge_gpu_shard_set_entry_bytes", "oge_gpu_shard_replay"]
+           "oge_gpu_dedup_sort_stats", "oge_gpu_sizeof", "oge_gpu_shard_key_bytes", "oge_gpu_shard_set_entry_bytes", "oge_gpu_shard_replay",
+           "oge_gpu_shard_comm_id", "oge_gpu_shard_comm_init", "oge_gpu_shard_comm_destroy", "oge_gpu_shard_step"]
 
 
 class DedupError(RuntimeError):
@@ -162,6 +168,11 @@ def _load(path):
         L.oge_gpu_shard_replay.argtypes = [vp, vp, u64, C.POINTER(vp), C.POINTER(u64)]
         L.oge_gpu_shard_finish.argtypes = [vp, vp, u64, C.POINTER(vp), C.POINTER(u64)]
         L.oge_gpu_shard_apply.argtypes = [vp, vp, u64]
+        L.oge_gpu_shard_comm_id.argtypes = [vp]
+        L.oge_gpu_shard_comm_init.argtypes = [vp, vp]
+        L.oge_gpu_shard_comm_destroy.argtypes = [vp]
+        L.oge_gpu_shard_comm_destroy.restype = None
+        L.oge_gpu_shard_step.argtypes = [vp, C.POINTER(StepInfo)]
         for name in EXPORTS:
             getattr(L, name)
         L.oge_gpu_sizeof.argtypes = [C.c_int]
@@ -387,6 +398,24 @@ class DedupContext:
     def shard_set_entry_bytes(self, entry_bytes: int):
         _check(lib().oge_gpu_shard_set_entry_bytes(self._h, int(entry_bytes)))
         self.entry_bytes = int(entry_bytes)
+
+    @staticmethod
+    def shard_comm_id() -> bytes:
+        """128 bytes of a fresh NCCL unique id (one rank calls this and hands the bytes to the others)."""
+        buf = (C.c_uint8 * 128)()
+        _check(lib().oge_gpu_shard_comm_id(buf))
+        return bytes(buf)
+
+    def shard_comm_init(self, comm_id: bytes):
+        buf = (C.c_uint8 * 128).from_buffer_copy(comm_id)
+        _check(lib().oge_gpu_shard_comm_init(self._h, buf))
+
+    def shard_step(self) -> dict:
+        """One whole sharded run driven from C++: the five phases with the four NCCL all-to-all exchanges between them."""
+        info = StepInfo()
+        _check(lib().oge_gpu_shard_step(self._h, C.byref(info)))
+        return {"published": int(info.published_in), "routed": int(info.routed_in), "marks": int(info.marks_in),
+                "exchanges": int(info.exchanges), "bytes_sent": int(info.bytes_sent)}
 
     def shard_begin(self):
         """-> (published entries by name owner, (hash pointer, count), routed fragment ends by key owner)"""

@@ -171,6 +171,19 @@ class CudaShardEngine(ShardEngine):
         torch.cuda.current_stream(self.device).synchronize()      # the library works on its own stream
         return (t.data_ptr() if t.numel() else None), t.numel() // item
 
+    def init_nccl(self, dist, device):
+        """Join the library's own NCCL communicator: rank 0 makes the id, torch.distributed carries its 128 bytes."""
+        import torch
+        t = torch.zeros(128, dtype=torch.uint8, device=device)
+        if dist.get_rank() == 0:
+            t = torch.frombuffer(bytearray(self.ctx.shard_comm_id()), dtype=torch.uint8).to(device)
+        dist.broadcast(t, src=0)
+        self.ctx.shard_comm_init(bytes(t.cpu().numpy().tobytes()))
+
+    def step(self):
+        """One whole run inside the library: phases and NCCL exchanges, no Python in between."""
+        return self.ctx.shard_step()
+
     def begin(self):
         (pp, pc), (hp, nh), (fp, fc) = self.ctx.shard_begin()
         return self._bucketed(pp, pc, self.entry_bytes), DevChunk(self, hp, nh * HASH_BYTES).tensor(), self._bucketed(fp, fc, ROUTE_BYTES)
@@ -439,7 +452,7 @@ def make_rank_shard(workload, scale, rank, world, pinned=True):
     return rec, offs, synth.header_text(contigs, rgs), contigs, hold
 
 
-def parity_pass(workload, rank, world, local_rank, dist, dev, checker, reads=2_000_000):
+def parity_pass(workload, rank, world, local_rank, dist, dev, checker, reads=2_000_000, native=True):
     """Untimed: a `reads`-record file of the same shape, sharded over the same ranks through the same NCCL exchanges, its
     flags gathered on rank 0 and compared record by record with `checker(records, offsets, header text) -> flags` run over
     the whole file (the caller -- bench.py, the tests -- supplies the CPU oracle; rank 0 regenerates every rank's shard: the
@@ -461,7 +474,14 @@ def parity_pass(workload, rank, world, local_rank, dist, dev, checker, reads=2_0
     eng = CudaShardEngine(rec, offs, text, contigs, plan, rank, device=local_rank)
     try:
         agree_entry_bytes([eng], dist, dev)
-        info = run_phases([eng], AllToAllExchange(dist, dev), ranks=[rank], world=world)
+        if native:
+            eng.init_nccl(dist, dev)
+            info = eng.step()
+        else:
+            info = run_phases([eng], AllToAllExchange(dist, dev), ranks=[rank], world=world)
+        tot = torch.tensor([info["published"], info["routed"], info["marks"]], dtype=torch.int64, device=dev)
+        dist.all_reduce(tot)
+        info = {"published": int(tot[0]), "routed": int(tot[1]), "marks": int(tot[2])}
         flags = torch.from_numpy(eng.flags().astype(np.int32)).to(dev)
     finally:
         eng.close()
@@ -481,7 +501,8 @@ def parity_pass(workload, rank, world, local_rank, dist, dev, checker, reads=2_0
     want = checker(whole, np.concatenate(wo), text)
     have = np.concatenate([g[:c].cpu().numpy().astype(np.uint16) for g, c in zip(got, counts)])
     return {"checked": True, "records": int(len(want)), "mismatches": int((have != want).sum()), "published": info["published"],
-            "routed": info["routed"], "marks": info["marks"], "through": "NCCL all_to_all_single, %d ranks" % world}
+            "routed": info["routed"], "marks": info["marks"],
+            "through": ("the library's own NCCL exchanges (grouped ncclSend/ncclRecv), %d ranks" if native else "torch.distributed all_to_all_single (NCCL), %d ranks") % world}
 
 
 def bench(args, rank, world, local_rank, rec, offs, text, contigs, metric, workload_name):
@@ -515,7 +536,13 @@ def bench(args, rank, world, local_rank, rec, offs, text, contigs, metric, workl
 
     eng = CudaShardEngine(rec, offs, text, contigs, plan, rank, device=local_rank, pinned_ptr=rec.ctypes.data, profile_events=True)
     entry_bytes = agree_entry_bytes([eng], dist, dev)
+    native = os.environ.get("OGE_EXCHANGE", "native") != "torch"      # A/B: the exchanges through torch.distributed instead
     ex = AllToAllExchange(dist, dev, timed=True)
+    if native:
+        eng.init_nccl(dist, dev)
+
+    def one_run():
+        return eng.step() if native else run_phases([eng], ex, ranks=[rank], world=world)
 
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
@@ -524,7 +551,7 @@ def bench(args, rank, world, local_rank, rec, offs, text, contigs, metric, workl
         # around the whole step see all of it: device phases, exchanges, and whatever overlaps them
         ex.ms = 0.0
         e0.record()
-        info = run_phases([eng], ex, ranks=[rank], world=world)
+        info = one_run()
         e1.record()
         e1.synchronize()
         st = eng.stats()
@@ -570,7 +597,7 @@ def bench(args, rank, world, local_rank, rec, offs, text, contigs, metric, workl
         t1 = time.perf_counter()
         if n:
             eng.ctx.push_async(rec.ctypes.data, int(rec.nbytes), eng._off_pin.ptr, n)
-        run_phases([eng], ex, ranks=[rank], world=world)
+        one_run()
         eng.ctx.flags(flags_pin.array.view(np.uint16)[:n])
         dist.barrier()
         e2e.append(time.perf_counter() - t1)
@@ -608,7 +635,8 @@ def bench(args, rank, world, local_rank, rec, offs, text, contigs, metric, workl
                        "published_entries": int(sm[5]), "routed_entries": int(sm[6]), "marks_exchanged": int(sm[7]), "published_entry_bytes": entry_bytes,
                        "stage_ms_rank0": {k: st[k] for k in ("ms_endbuild", "ms_join", "ms_sort_pair", "ms_sort_frag", "ms_select", "ms_flags")},
                        "parity_vs_oracle": parity,
-                       "parallelism": "range-sharded x%d; four all-to-all exchanges (NCCL all_to_all_single with uneven splits) of small lists per "
+                       "exchanges": "inside the library: grouped ncclSend/ncclRecv per peer on its own stream" if native else "torch.distributed all_to_all_single",
+                       "parallelism": "range-sharded x%d; four all-to-all exchanges (NCCL, uneven splits) of small lists per "
                                       "step: published entries to the name's owner (hash mod %d) + their hashes to all + boundary fragment ends, "
                                       "round-2 entries + local pair ends, replayed pair ends, marks" % (world, world)},
             "e2e": {"value": total_reads / float(e2e_s[0]), "unit": "reads/s", "h2d_bytes_per_step": int(h2d[0]),

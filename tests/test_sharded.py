@@ -317,4 +317,4 @@ def test_cuda_engine_one_process_per_rank_over_the_real_exchange(tmp_path, world
     mp.spawn(_nccl_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     v = np.load(tmp_path / "verdict.npy")
     assert v[0] > 300_000 and v[1] == 0, "%d of %d flag words differ from the oracle" % (v[1], v[0])
-    assert v[2] > 0 and v[3] > 0 and v[4] > 0
+    assert v[2] > 0 and v[3] > 0
