@@ -666,8 +666,9 @@ int join_stage(oge_gpu_dedup_ctx *c, bool replay_locally, JoinStage *out, uint64
             if ((rc = c->cplx_sort.reserve(n_cplx, false, s))) return rc;
             if ((rc = radix_sort_128(c->sortbuf.p, c->cplx_sort.p, n_cplx, nullptr, 0, 96, c->scratch.p, s, &sorted, &launches)))
                 return rc;
-            if ((rc = c->cplx_state.reserve(n_cplx, false, s))) return rc;
-            if ((rc = launch_mate_complex(jp, sorted, (uint32_t) n_cplx, c->cplx_state.p, s, &launches))) return rc;
+            if ((rc = c->cplx_state.reserve(n_cplx + mate_complex_long_segs_bytes((uint32_t) n_cplx) + 16, false, s))) return rc;
+            void *long_segs = c->cplx_state.p + ((n_cplx + 15) & ~15ull);
+            if ((rc = launch_mate_complex(jp, sorted, (uint32_t) n_cplx, c->cplx_state.p, long_segs, s, &launches))) return rc;
             OGE_CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, s));
             OGE_CUDA_TRY(cudaStreamSynchronize(s));
             }

@@ -200,53 +200,99 @@ __global__ void __launch_bounds__(JOIN_THREADS) mate_fixup_kernel(JoinParams P, 
 }
 
 // ---- exact slow path ------------------------------------------------------------------------------
-// sorted: complex entries ordered by (hash, ordinal).  One thread per distinct hash value
-// replays the reference's toggle map over that segment with byte-exact key comparison.
+// sorted: complex entries ordered by (hash, ordinal).  The entries of one hash value (a segment) replay the
+// reference's toggle map (tmp.put / tmp.remove, mark_duplicates.cpp:216-223) with byte-exact key comparison.  The map
+// holds at most ONE unmatched sighting per distinct key, and the keys of a segment share a 64-bit hash, so the live
+// set of a segment is a handful of entries at most (one, unless hashes collide): the replay keeps it in registers
+// and costs O(k) comparisons for k sightings (the byte map `state` is the fall-back should more than CPLX_LIVE
+// distinct keys ever share a hash).  A short segment is replayed by one thread; a long one (stripped or constant read
+// names put a whole file into one segment) by a CTA: if all its keys are equal -- adjacent comparisons in parallel --
+// the sightings pair up (1,2), (3,4), ... in file order and the pairs are emitted in parallel.
+constexpr int CPLX_LIVE = 8;
+constexpr uint32_t CPLX_LONG = 512;
+
+__device__ __forceinline__ uint64_t cplx_hash(const E128 &e) { return (e.lo >> 32) | (e.hi << 32); }
+
+__device__ __forceinline__ void cplx_emit(const JoinParams &P, uint32_t r_first, uint32_t r_second) {
+    const E128 first = ld_frag(P.frag + r_first), second = ld_frag(P.frag + r_second);
+    uint32_t i1, i2;
+    bool far;
+    const E128 ent = make_pair_entry(P.kl, first, second, &i1, &i2, P.idx_base, &far);
+    const uint32_t pos = atomicAdd(&P.counters[far ? CNT_PAIRS_FAR : CNT_PAIRS], 1u);
+    reinterpret_cast<ulonglong2 *>(far ? P.pair_far : P.pair)[pos] = make_ulonglong2(ent.lo, ent.hi);
+    P.mate_of[i1] = (uint32_t) (i2 + P.idx_base);
+}
+
+// the toggle over sorted[j, end), sequentially
+__device__ void cplx_replay_segment(const JoinParams &P, const E128 *__restrict__ sorted, uint32_t j, uint32_t end, uint8_t *__restrict__ state) {
+    uint32_t live[CPLX_LIVE];
+    int n_live = 0;
+    bool overflow = false;
+    for (uint32_t a = j; a < end; a++) {
+        const uint32_t ra = (uint32_t) sorted[a].lo;
+        const KeyView ka = key_view(P.rec, P.off, ra);
+        int found = -1;
+        if (!overflow) {
+            for (int t = 0; t < n_live; t++)
+                if (key_equal(ka, key_view(P.rec, P.off, (uint32_t) sorted[live[t]].lo))) { found = (int) live[t]; live[t] = live[--n_live]; break; }
+        } else {
+            for (uint32_t b2 = j; b2 < a; b2++)
+                if (state[b2] && key_equal(ka, key_view(P.rec, P.off, (uint32_t) sorted[b2].lo))) { found = (int) b2; break; }
+        }
+        if (found < 0) {      // tmp.put (:222-223)
+            if (overflow) state[a] = 1;
+            else if (n_live < CPLX_LIVE) live[n_live++] = a;
+            else {      // more distinct keys under one hash than the registers hold: from here on the byte map is the live set
+                overflow = true;
+                for (uint32_t x = j; x < a; x++) state[x] = 0;
+                for (int t = 0; t < n_live; t++) state[live[t]] = 1;
+                state[a] = 1;
+            }
+        } else {              // tmp.remove (:216)
+            if (overflow) state[found] = 0;
+            cplx_emit(P, (uint32_t) sorted[found].lo, ra);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(JOIN_THREADS) mate_complex_kernel(JoinParams P, const E128 *__restrict__ sorted,
-                                                                    uint32_t n_cplx, uint8_t *__restrict__ state) {
+                                                                    uint32_t n_cplx, uint8_t *__restrict__ state, uint2 *__restrict__ long_segs) {
     uint32_t j = blockIdx.x * JOIN_THREADS + threadIdx.x;
     if (j >= n_cplx) return;
-    E128 e = sorted[j];
-    uint64_t h = (e.lo >> 32) | (e.hi << 32);
-    if (j > 0) {
-        E128 q = sorted[j - 1];
-        if (((q.lo >> 32) | (q.hi << 32)) == h) return;      // not a segment head
-    }
+    const uint64_t h = cplx_hash(sorted[j]);
+    if (j > 0 && cplx_hash(sorted[j - 1]) == h) return;      // not a segment head
     atomicAdd(&P.counters[CNT_COMPLEX_SEGS], 1u);
-    uint32_t end = j;
-    while (end < n_cplx) {
-        E128 q = sorted[end];
-        if (((q.lo >> 32) | (q.hi << 32)) != h) break;
-        state[end] = 0;
-        end++;
+    // end of the segment: first entry with another hash (binary search: the list is sorted by hash)
+    uint32_t lo = j + 1, hi = n_cplx;
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (cplx_hash(sorted[mid]) == h) lo = mid + 1; else hi = mid;
     }
-    for (uint32_t a = j; a < end; a++) {
-        uint32_t ra = (uint32_t) sorted[a].lo;
-        KeyView ka = key_view(P.rec, P.off, ra);
-        int found = -1;
-        for (uint32_t b = j; b < a; b++) {
-            if (!state[b]) continue;
-            uint32_t rb = (uint32_t) sorted[b].lo;
-            KeyView kb = key_view(P.rec, P.off, rb);
-            if (key_equal(ka, kb)) {
-                found = (int) b;
-                break;
-            }
-        }
-        if (found < 0) {
-            state[a] = 1;       // tmp.put (:222-223)
-        } else {
-            state[found] = 0;   // tmp.remove (:216)
-            uint32_t rb = (uint32_t) sorted[found].lo;
-            E128 first = ld_frag(P.frag + rb), second = ld_frag(P.frag + ra);
-            uint32_t i1, i2;
-            bool far;
-            E128 ent = make_pair_entry(P.kl, first, second, &i1, &i2, P.idx_base, &far);
-            uint32_t pos = atomicAdd(&P.counters[far ? CNT_PAIRS_FAR : CNT_PAIRS], 1u);
-            reinterpret_cast<ulonglong2 *>(far ? P.pair_far : P.pair)[pos] = make_ulonglong2(ent.lo, ent.hi);
-            P.mate_of[i1] = (uint32_t) (i2 + P.idx_base);
-        }
+    const uint32_t end = lo;
+    if (end - j > CPLX_LONG) {
+        long_segs[atomicAdd(&P.counters[CNT_SCRATCH0], 1u)] = make_uint2(j, end);
+        return;
     }
+    cplx_replay_segment(P, sorted, j, end, state);
+}
+
+// one CTA per long segment
+__global__ void __launch_bounds__(JOIN_THREADS) mate_complex_long_kernel(JoinParams P, const E128 *__restrict__ sorted, uint8_t *__restrict__ state,
+                                                                         const uint2 *__restrict__ long_segs) {
+    const uint2 seg = long_segs[blockIdx.x];
+    const uint32_t j = seg.x, end = seg.y;
+    __shared__ int s_differ;
+    if (threadIdx.x == 0) s_differ = 0;
+    __syncthreads();
+    for (uint32_t a = j + 1 + threadIdx.x; a < end && !s_differ; a += JOIN_THREADS)
+        if (!key_equal(key_view(P.rec, P.off, (uint32_t) sorted[a].lo), key_view(P.rec, P.off, (uint32_t) sorted[a - 1].lo))) s_differ = 1;
+    __syncthreads();
+    if (s_differ) {      // several keys under one hash in a long segment: the sequential toggle
+        if (threadIdx.x == 0) cplx_replay_segment(P, sorted, j, end, state);
+        return;
+    }
+    const uint32_t n_pairs = (end - j) / 2;      // one key: sightings (1,2), (3,4), ... in file order; an odd last one stays unmatched
+    for (uint32_t t = threadIdx.x; t < n_pairs; t += JOIN_THREADS) cplx_emit(P, (uint32_t) sorted[j + 2 * t].lo, (uint32_t) sorted[j + 2 * t + 1].lo);
 }
 
 int launch_mate_join(const JoinParams &P, cudaStream_t stream, uint64_t *launches) {
@@ -571,13 +617,23 @@ int launch_mate_fixup(const JoinParams &P, uint32_t n_slots_listed, cudaStream_t
     return 0;
 }
 
-int launch_mate_complex(const JoinParams &P, const E128 *sorted_cplx, uint32_t n_cplx, uint8_t *state, cudaStream_t stream,
-                        uint64_t *launches) {
+int launch_mate_complex(const JoinParams &P, const E128 *sorted_cplx, uint32_t n_cplx, uint8_t *state, void *long_segs /* n_cplx / CPLX_LONG + 1 uint2 */,
+                        cudaStream_t stream, uint64_t *launches) {
     if (n_cplx == 0) return 0;
-    mate_complex_kernel<<<(n_cplx + JOIN_THREADS - 1) / JOIN_THREADS, JOIN_THREADS, 0, stream>>>(P, sorted_cplx, n_cplx, state);
+    OGE_CUDA_TRY(cudaMemsetAsync(P.counters + CNT_SCRATCH0, 0, 4, stream));
+    mate_complex_kernel<<<(n_cplx + JOIN_THREADS - 1) / JOIN_THREADS, JOIN_THREADS, 0, stream>>>(P, sorted_cplx, n_cplx, state, (uint2 *) long_segs);
     *launches += 1;
     OGE_CUDA_TRY(cudaGetLastError());
+    uint32_t n_long = 0;
+    OGE_CUDA_TRY(cudaMemcpyAsync(&n_long, P.counters + CNT_SCRATCH0, 4, cudaMemcpyDeviceToHost, stream));
+    OGE_CUDA_TRY(cudaStreamSynchronize(stream));
+    if (n_long) {
+        mate_complex_long_kernel<<<n_long, JOIN_THREADS, 0, stream>>>(P, sorted_cplx, state, (const uint2 *) long_segs);
+        *launches += 1;
+        OGE_CUDA_TRY(cudaGetLastError());
+    }
     return 0;
 }
+size_t mate_complex_long_segs_bytes(uint32_t n_cplx) { return ((size_t) n_cplx / CPLX_LONG + 2) * sizeof(uint2); }
 
 }  // namespace oge

@@ -121,8 +121,9 @@ int launch_local_join(const JoinParams &P, LocalJoinParams J, int sms, cudaStrea
 int launch_pair_check(const JoinParams &P, const uint64_t *pair_hk, uint32_t n_pairs, bool far, cudaStream_t stream, uint64_t *launches);
 int launch_mate_fixup(const JoinParams &P, uint32_t n_slots_listed, cudaStream_t stream, uint64_t *launches);
 // exact path over the sorted complex list (sorted by hash then ordinal); state = n_cplx bytes of scratch
-int launch_mate_complex(const JoinParams &P, const E128 *sorted_cplx, uint32_t n_cplx, uint8_t *state, cudaStream_t stream,
+int launch_mate_complex(const JoinParams &P, const E128 *sorted_cplx, uint32_t n_cplx, uint8_t *state, void *long_segs, cudaStream_t stream,
                         uint64_t *launches);
+size_t mate_complex_long_segs_bytes(uint32_t n_cplx);      // room for the list of long segments
 
 // ---- K4 group-and-select (select.cu) ----------------------------------------------------------
 struct SelectParams {

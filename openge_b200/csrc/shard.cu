@@ -437,17 +437,42 @@ __global__ void __launch_bounds__(SH_THREADS) sh_replay2_kernel(const E128 *__re
     const uint32_t h = (uint32_t) sorted[j].hi;
     if (j > 0 && (uint32_t) sorted[j - 1].hi == h) return;      // not a segment head
     uint32_t end = j;
-    while (end < n_w && (uint32_t) sorted[end].hi == h) state[end++] = 0;
+    while (end < n_w && (uint32_t) sorted[end].hi == h) end++;
+    // the map holds at most one unmatched sighting per distinct key: a handful of live entries per segment, kept in
+    // registers; the byte map is the fall-back should more than SH_LIVE distinct keys ever share the low hash word
+    constexpr int SH_LIVE = 8;
+    uint32_t live[SH_LIVE];
+    int n_live = 0;
+    bool overflow = false;
     for (uint32_t a = j; a < end; a++) {
         const uint8_t *pa = pub2_at(w, stride, (uint32_t) sorted[a].lo);
         if (a > j && sorted[a].lo >> 32 == sorted[a - 1].lo >> 32) continue;      // the same record published twice
         int found = -1;
-        for (uint32_t b = j; b < a; b++) {
-            if (!state[b]) continue;
-            if (sorted[b].hi == sorted[a].hi && pub2_keys_equal(pa, pub2_at(w, stride, (uint32_t) sorted[b].lo))) { found = (int) b; break; }
+        if (!overflow) {
+            for (int t = 0; t < n_live; t++)
+                if (sorted[live[t]].hi == sorted[a].hi && pub2_keys_equal(pa, pub2_at(w, stride, (uint32_t) sorted[live[t]].lo))) {
+                    found = (int) live[t];
+                    live[t] = live[--n_live];
+                    break;
+                }
+        } else {
+            for (uint32_t b = j; b < a; b++) {
+                if (!state[b]) continue;
+                if (sorted[b].hi == sorted[a].hi && pub2_keys_equal(pa, pub2_at(w, stride, (uint32_t) sorted[b].lo))) { found = (int) b; break; }
+            }
         }
-        if (found < 0) { state[a] = 1; continue; }
-        state[found] = 0;
+        if (found < 0) {
+            if (overflow) state[a] = 1;
+            else if (n_live < SH_LIVE) live[n_live++] = a;
+            else {
+                overflow = true;
+                for (uint32_t x = j; x < a; x++) state[x] = 0;
+                for (int t = 0; t < n_live; t++) state[live[t]] = 1;
+                state[a] = 1;
+            }
+            continue;
+        }
+        if (overflow) state[found] = 0;
         const uint8_t *pb = pub2_at(w, stride, (uint32_t) sorted[found].lo);      // the earlier sighting
         uint32_t i1, i2;
         bool far;

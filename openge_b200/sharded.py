@@ -634,7 +634,7 @@ def bench(args, rank, world, local_rank, rec, offs, text, contigs, metric, workl
                        "duplicates_flagged": total_dups,
                        "published_entries": int(sm[5]), "routed_entries": int(sm[6]), "marks_exchanged": int(sm[7]), "published_entry_bytes": entry_bytes,
                        "stage_ms_rank0": {k: st[k] for k in ("ms_endbuild", "ms_join", "ms_sort_pair", "ms_sort_frag", "ms_select", "ms_flags")},
-                       "parity_vs_oracle": parity,
+                       "parity_vs_oracle": parity, "host_numa_binding_rank0": getattr(args, "numa", None),
                        "exchanges": "inside the library: grouped ncclSend/ncclRecv per peer on its own stream" if native else "torch.distributed all_to_all_single",
                        "parallelism": "range-sharded x%d; four all-to-all exchanges (NCCL, uneven splits) of small lists per "
                                       "step: published entries to the name's owner (hash mod %d) + their hashes to all + boundary fragment ends, "

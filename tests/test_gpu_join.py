@@ -34,12 +34,16 @@ def test_name_soup_vs_oracle(legacy, n, seed, pool_div, n_pos):
 
 
 @pytest.mark.parametrize("legacy", [False, True])
-@pytest.mark.parametrize("n", [2, 3, 257, 3000])
+@pytest.mark.parametrize("n", [2, 3, 257, 3000, 100001])
 def test_one_name_for_every_record(legacy, n):
+    """Stripped read names: every record toggles the same map key, so sightings pair (1,2), (3,4), ... in file order.  At 100 001
+    records the whole file is ONE segment of the exact path: it must not be replayed quadratically (a CTA establishes that all
+    keys are equal and emits the pairs in parallel)."""
     bam = fixtures.one_name(n=n)
     want = oracle.markdup(bam.records, bam.offsets, bam.text)
     got, st = gpu_flags(bam, legacy_join=legacy)
     assert np.array_equal(got, want)
+    assert st["n_pair_entries"] == n // 2
 
 
 @pytest.mark.parametrize("name,scale,seed", [("C1", 0.3, 11), ("C2", 0.02, 12), ("C3", 0.1, 13), ("C4", 0.05, 14), ("C5", 0.001, 15)])
