@@ -220,7 +220,8 @@ def make_shard(workload, scale, rank, world, pinned):
 
 def bench_bgzf(ctx, rec, offs, text, contigs, n, flags_want, flags_pin, steps):
     """reads/s from a BGZF-compressed BAM in host memory to flags in host memory through the C ABI:
-    oge_gpu_dedup_push_bgzf (H2D of the compressed file + inflate kernel) -> oge_gpu_dedup_frame -> run -> flags."""
+    oge_gpu_dedup_push_bgzf (H2D of the compressed file in pieces, each inflated by the hardware decompress engine under
+    the upload of the next) -> oge_gpu_dedup_frame -> run -> flags."""
     import ctypes as C
     from openge_b200 import bamhost, bamio
     head = bamio.serialize_bam_stream(bamio.BamFile(text=text, refs=list(contigs), records=np.zeros(0, np.uint8), offsets=np.zeros(1, np.uint64)))
@@ -252,24 +253,41 @@ def bench_bgzf(ctx, rec, offs, text, contigs, n, flags_want, flags_pin, steps):
         in_off = np.asarray(in_off, dtype=np.uint64)
         csize = np.asarray(csize, dtype=np.uint32)
         isize = np.asarray(isize, dtype=np.uint32)
-        times, st = [], None
+        times, st, wall = [], None, None
         for _ in range(1 + steps):      # first one is warm-up
             ctx.reset()
             ctx.sync()
             t1 = time.perf_counter()
             ctx.push_bgzf(comp.ctypes.data, comp.nbytes, in_off.ctypes.data, csize.ctypes.data, isize.ctypes.data, len(in_off), len(head), None)
+            t2 = time.perf_counter()
             ctx.frame(rec.nbytes)
+            t3 = time.perf_counter()
             ctx.run()
+            t4 = time.perf_counter()
             ctx.flags(flags_pin.array.view(np.uint16))
-            times.append(time.perf_counter() - t1)
+            t5 = time.perf_counter()
+            times.append(t5 - t1)
+            wall = {"push_bgzf": (t2 - t1) * 1e3, "frame": (t3 - t2) * 1e3, "run": (t4 - t3) * 1e3, "flags": (t5 - t4) * 1e3}
             st = ctx.stats()
         assert ctx.n == n and np.array_equal(flags_pin.array.view(np.uint16)[:n], flags_want), "flags from the BGZF path differ"
         secs = float(np.mean(times[1:]))
-        return {"value": n / secs, "unit": "reads/s", "h2d_bytes_per_step": int(comp.nbytes + in_off.nbytes + csize.nbytes),
+        # the decoder on its own (untimed extra pass): the whole file in ONE piece, i.e. upload, then inflate
+        ctx.reset()
+        _dedup.set_bgzf_chunk_bytes(2 ** 64 - 1)
+        try:
+            ctx.push_bgzf(comp.ctypes.data, comp.nbytes, in_off.ctypes.data, csize.ctypes.data, isize.ctypes.data, len(in_off), len(head), None)
+            alone = ctx.stats()
+        finally:
+            _dedup.set_bgzf_chunk_bytes(0)
+        return {"value": n / secs, "unit": "reads/s", "h2d_bytes_per_step": int(comp.nbytes + (0 if st["inflate_mode"] == 2 else in_off.nbytes + csize.nbytes)),
                 "d2h_bytes_per_step": int(n * 2), "ms_per_step": secs * 1e3, "bgzf_level": level, "bgzf_bytes": int(comp.nbytes),
                 "compress_seconds_untimed": t_comp, "host_buffer": "pinned",
-                "ms_inflate_kernel": st["ms_inflate"], "inflate_out_GBps": st["inflate_bytes_out"] / 1e6 / st["ms_inflate"] if st["ms_inflate"] else None,
-                "ms_upload": st["ms_inflate_h2d"], "ms_frame": st["ms_frame"], "frame_repairs": st["frame_repairs"], "ms_dedup": st["ms_total"]}
+                "decoder": {0: "kernel, thread per block", 1: "kernel, warp per block", 2: "hardware decompress engine (cuMemBatchDecompressAsync)"}[st["inflate_mode"]],
+                "pieces": st["inflate_pieces"], "host_wall_ms_last_step": wall, "ms_push_bgzf": st["ms_push_bgzf"], "ms_upload": st["ms_inflate_h2d"],
+                "ms_inflate_span_overlapped": st["ms_inflate"], "ms_first_inflate_starts_at": st["ms_inflate_start"],
+                "decoder_alone": {"ms_upload": alone["ms_inflate_h2d"], "ms_inflate": alone["ms_inflate"],
+                                  "inflate_out_GBps": alone["inflate_bytes_out"] / 1e6 / alone["ms_inflate"] if alone["ms_inflate"] else None},
+                "ms_frame": st["ms_frame"], "frame_repairs": st["frame_repairs"], "ms_dedup": st["ms_total"]}
     finally:
         comp = None
         comp_pin.free()
@@ -599,7 +617,7 @@ def run_ours(args):
     n_dup = int(((flags_e2e & 0x400) != 0).sum())
 
     # ---- end to end from a BGZF-compressed BAM held in host memory (what the reference's reader starts from): the
-    # compressed bytes cross PCIe, the device inflates (one warp per block), frames, dedups; the flags come back
+    # compressed bytes cross PCIe, the device inflates (decompress engine), frames, dedups; the flags come back
     e2e_bgzf = None
     if not args.no_bgzf:
         try:

@@ -105,6 +105,13 @@ int oge_bam_apply_flags(oge_bam_file *f, const uint16_t *flags, int remove_dupli
 int oge_bam_store(oge_bam_file *f, const char *path, const char *format, int level, const char *pg_command_line,
                   const char *pg_version, int threads);
 
+/* The same file with the record part already compressed: `members` = BGZF members holding the records (what
+ * oge_gpu_dedup_deflate makes on the device).  Writes the re-rendered header in members of its own (zlib, `level`), the
+ * given members, and the empty member that ends a BGZF file (util/bgzf_output_stream.cpp:225-250).  The file equals
+ * oge_bam_store's (and the reference's) after decompression; its block boundaries and deflate streams differ. */
+int oge_bam_store_members(oge_bam_file *f, const char *path, int level, const char *pg_command_line, const char *pg_version,
+                          const uint8_t *members, uint64_t members_bytes);
+
 /* seconds: [0] read file, [1] block scan, [2] inflate, [3] header + framing, [4] apply_flags, [5] store */
 int oge_bam_timings(const oge_bam_file *f, double *out, int n);
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define OGE_GPU_DEDUP_ABI_VERSION 7
+#define OGE_GPU_DEDUP_ABI_VERSION 8
 
 enum {
     OGE_OK = 0,
@@ -100,6 +100,16 @@ typedef struct oge_gpu_dedup_stats {
      * OGE_K_ENDBUILD, OGE_K_MATCH (windowed join, K2a), OGE_K_EMIT (K2b), OGE_K_GLOBAL_JOIN (leftovers), OGE_K_CHECK,
      * OGE_K_SELECT (all launches), OGE_K_FLAGS, OGE_K_SORT_HIST (histogram + scan of every sort). */
     float ms_kernel[8];
+    /* oge_gpu_dedup_push_bgzf as a whole (upload, inflate and copy-back overlapped piece by piece): device time from its
+     * first to its last operation; which decoder ran (0 thread per block, 1 warp per block, 2 hardware decompress engine);
+     * pieces the file was uploaded in.  With several pieces ms_inflate spans the inflates INCLUDING their waits for the
+     * upload; the decoder's own rate shows with one piece (oge_gpu_set_bgzf_chunk_bytes(~0)). */
+    float ms_push_bgzf;
+    uint32_t inflate_mode, inflate_pieces;
+    float ms_inflate_start;         /* device time from the start of push_bgzf to the start of the first piece's inflate */
+    /* oge_gpu_dedup_deflate: device time, blocks, bytes in (records) and out (BGZF members) */
+    float ms_deflate;
+    uint64_t deflate_blocks, deflate_bytes_in, deflate_bytes_out;
 } oge_gpu_dedup_stats;
 enum { OGE_K_ENDBUILD = 0, OGE_K_MATCH, OGE_K_EMIT, OGE_K_GLOBAL_JOIN, OGE_K_CHECK, OGE_K_SELECT, OGE_K_FLAGS, OGE_K_SORT_HIST };
 
@@ -138,8 +148,13 @@ int oge_gpu_dedup_sync(oge_gpu_dedup_ctx *ctx);
 
 /* The same input side for a BGZF-compressed BAM file, with the inflate on the device: stands in for
  * BgzfInputStream::BgzfBlock::decompress (util/bgzf_input_stream.cpp:65-142; one zlib call per block, raw deflate,
- * window 15; like there the inflated size is checked and the CRC is not) for every block of the file at once, one
- * warp per block.  comp = the whole file in host memory; the block table comes from the file's block headers
+ * window 15; like there the inflated size is checked and the CRC is not) for every block of the file, by the B200's
+ * hardware decompress engine (or one of two kernels, oge_gpu_set_inflate_kernel).  The file goes up in pieces
+ * (oge_gpu_set_bgzf_chunk_bytes): the upload of one piece runs under the inflate of the one before and under the
+ * copy-back of the one before that, like the reference's reader keeps reading while its block jobs decompress
+ * (bgzf_input_stream.cpp:144-207).  An invalid deflate stream fails with OGE_ERR_BAD_RECORD "Zlib inflate failed";
+ * when the engine was decoding, the CUDA context of the process is lost with it (the reference exit(-1)s there).
+ * comp = the whole file in host memory (pinned for the overlap); the block table comes from the file's block headers
  * (oge_bam_bgzf_index in oge_bam_host.h: offset, BSIZE + 1 and ISIZE of every block); header_bytes = inflated bytes in
  * front of the first record (magic, header text, reference list), which stay out of the record array.  host_copy
  * (optional) receives the inflated record bytes (total ISIZE - header_bytes) for the host side of the pipeline
@@ -184,6 +199,17 @@ int oge_gpu_dedup_flags(oge_gpu_dedup_ctx *ctx, uint16_t *out, uint64_t n);
  * out_offsets (optional) receives out_nrec+1 offsets. */
 int oge_gpu_dedup_pull(oge_gpu_dedup_ctx *ctx, uint8_t *out_records, uint64_t cap_bytes,
                        uint64_t *out_offsets, uint64_t cap_records, uint64_t *out_bytes, uint64_t *out_nrec);
+
+/* Output side as a finished file body: the flag-patched records (with remove_duplicates: the ones that stay, :456-458), the
+ * bin of every record recomputed as the reference's serialiser does (util/bam_serializer.h:88-126), cut into blocks of 65280
+ * bytes and compressed into BGZF members ON THE DEVICE -- 18-byte header, raw deflate stream, CRC32, ISIZE, back to back: the
+ * part of BgzfOutputStream (util/bgzf_output_stream.cpp:59-144, 170-250) between the BAM header and the empty end-of-file
+ * block, which the host writes around it (oge_bam_store_members).  The deflate streams are NOT zlib's (a warp-parallel match
+ * finder, its own prefix codes; compression in zlib level 1's class): the file is identical to the reference's after
+ * decompression, not byte for byte -- for that, oge_gpu_dedup_pull + oge_bam_store.  deflate leaves the members resident and
+ * reports their size, the number of blocks and of records; pull_bgzf copies them out. */
+int oge_gpu_dedup_deflate(oge_gpu_dedup_ctx *ctx, uint64_t *out_bytes, uint64_t *out_blocks, uint64_t *out_nrec);
+int oge_gpu_dedup_pull_bgzf(oge_gpu_dedup_ctx *ctx, uint8_t *out, uint64_t cap_bytes);
 
 /* The counters of the reference's Statistics module (algorithms/statistics.cpp:77-162: what `openge stats` prints,
  * and what a Statistics stage placed behind MarkDuplicates would count) over the resident records and their
@@ -277,9 +303,15 @@ int oge_gpu_debug_sort_bench(int device, uint64_t n, int bit_lo, int bit_hi, int
 /* Tuning hook: pass-kernel variant (0: 2048-entry tiles of 256 threads; 2: 4096-entry tiles of 512 threads, default). */
 int oge_gpu_set_sort_variant(int variant);
 
-/* Tuning hook: which BGZF inflate kernel oge_gpu_dedup_push_bgzf launches (1: one warp per block, default; 0: one thread
- * per block, 32 streams per warp as a converged state machine).  Also settable with OGE_INFLATE_KERNEL=warp|threads. */
+/* Which BGZF decoder oge_gpu_dedup_push_bgzf uses: 2 = the hardware decompress engine (default where the device and
+ * driver have one), 1 = one warp per block (default elsewhere), 0 = one thread per block (32 streams per warp as a
+ * converged state machine), -1 = back to the default.  Also OGE_INFLATE_KERNEL=engine|warp|threads.
+ * oge_gpu_inflate_kernel(device) -> the decoder push_bgzf would use on that device now (or a negative error). */
 int oge_gpu_set_inflate_kernel(int kernel);
+int oge_gpu_inflate_kernel(int device);
+/* Tuning hook: compressed bytes per piece of push_bgzf's overlapped upload (0 = default: 64 MB for the engine, 512 MB for the
+ * kernels; ~0 = the whole file in one piece, i.e. upload, then inflate, then copy-back). */
+int oge_gpu_set_bgzf_chunk_bytes(uint64_t bytes);
 
 /* Pinned host memory for push/pull buffers. */
 void *oge_gpu_host_alloc(size_t nbytes);

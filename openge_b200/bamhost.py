@@ -19,7 +19,7 @@ ERRORS = {-1: "OGE_BAM_ERR_IO", -2: "OGE_BAM_ERR_FORMAT", -3: "OGE_BAM_ERR_NOMEM
 
 EXPORTS = ["oge_bam_load", "oge_bam_open_bgzf", "oge_bam_bgzf_index", "oge_bam_records_buffer", "oge_bam_frame_records", "oge_bam_adopt_offsets", "oge_bam_close", "oge_bam_header_text", "oge_bam_n_ref", "oge_bam_ref_name", "oge_bam_ref_len",
            "oge_bam_records", "oge_bam_records_bytes", "oge_bam_offsets", "oge_bam_n_records", "oge_bam_library_table",
-           "oge_bam_apply_flags", "oge_bam_store", "oge_bam_timings", "oge_bgzf_decompress", "oge_bgzf_compress",
+           "oge_bam_apply_flags", "oge_bam_store", "oge_bam_store_members", "oge_bam_timings", "oge_bgzf_decompress", "oge_bgzf_compress",
            "oge_bam_header_render", "oge_bam_buffer_free", "oge_bam_last_error", "oge_bam_set_sort_order"]
 
 
@@ -69,6 +69,7 @@ def lib():
         L.oge_bam_library_table.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int32), C.POINTER(C.c_int16), C.POINTER(C.c_int32)]
         L.oge_bam_apply_flags.argtypes = [vp, vp, C.c_int, C.c_int]
         L.oge_bam_store.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int]
+        L.oge_bam_store_members.argtypes = [vp, C.c_char_p, C.c_int, C.c_char_p, C.c_char_p, vp, C.c_uint64]
         L.oge_bam_timings.argtypes = [vp, C.POINTER(C.c_double), C.c_int]
         L.oge_bgzf_decompress.argtypes = [vp, C.c_size_t, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
         L.oge_bgzf_compress.argtypes = [vp, C.c_size_t, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
@@ -221,6 +222,13 @@ class HostBam:
         _check(lib().oge_bam_store(self._h, os.fsencode(path), format.encode() if format else None, level,
                                    pg_command_line.encode() if pg_command_line else None, pg_version.encode(), threads))
 
+    def store_members(self, path: str, members: np.ndarray, level: int = 6, pg_command_line: str | None = None,
+                      pg_version: str = "0.3-b200"):
+        """The output file around record members that are already compressed (DedupContext.deflate)."""
+        m = np.ascontiguousarray(members, dtype=np.uint8)
+        _check(lib().oge_bam_store_members(self._h, os.fsencode(path), level, pg_command_line.encode() if pg_command_line else None,
+                                           pg_version.encode(), m.ctypes.data if m.nbytes else None, m.nbytes))
+
     def timings(self) -> dict:
         t = (C.c_double * 6)()
         _check(lib().oge_bam_timings(self._h, t, 6))
@@ -229,18 +237,22 @@ class HostBam:
 
 def dedup_file(in_path: str, out_path: str, remove_duplicates: bool = False, level: int = 6, format: str | None = None,
                pg_command_line: str | None = None, threads: int = 0, device: int = 0, gpu_inflate: bool = True,
-               pinned: bool = False, sort: bool = False) -> dict:
+               pinned: bool = False, sort: bool = False, gpu_deflate: bool = False) -> dict:
     """`openge dedup in.bam -o out.bam` on the GPU, file to file.  -> stats (dedup counters, flag statistics, timings).
     gpu_inflate: the BGZF blocks are inflated on the device (DedupContext.push_bgzf), else by the host threads.
-    sort: coordinate sort on the device in front of the dedup (`openge mergesort -M`)."""
+    sort: coordinate sort on the device in front of the dedup (`openge mergesort -M`).
+    gpu_deflate: the output's BGZF blocks are made on the device as well (DedupContext.deflate): the records never come back
+    uncompressed; the file equals the reference's after decompression (not byte for byte, which the default gives)."""
     from . import dedup
     with open(in_path, "rb") as fh:
         is_bgzf = fh.read(2) == b"\x1f\x8b"
     gpu_inflate = gpu_inflate and is_bgzf
     with HostBam(in_path, threads=threads, pinned=pinned, defer_inflate=gpu_inflate) as bam:
         refs = bam.refs
-        ctx = dedup.DedupContext(n_ref=len(refs), max_ref_len=max([l for _, l in refs], default=0), device=device)
-        with ctx:      # -r is applied by the host layer (apply_flags), so pull() returns every record
+        gpu_deflate = gpu_deflate and (format in (None, "bam"))
+        ctx = dedup.DedupContext(n_ref=len(refs), max_ref_len=max([l for _, l in refs], default=0), device=device,
+                                 remove_duplicates=bool(remove_duplicates and gpu_deflate))
+        with ctx:      # without gpu_deflate -r is applied by the host layer (apply_flags), so pull() returns every record
             ctx.set_header(bam.text)
             if gpu_inflate:
                 # compressed bytes up, inflate + framing + dedup on the device, ONE copy of the (flag-patched) records back
@@ -252,11 +264,12 @@ def dedup_file(in_path: str, out_path: str, remove_duplicates: bool = False, lev
                     ctx.sort()
                 ctx.run()
                 flags = ctx.flags()
-                nb, nr = C.c_uint64(), C.c_uint64()
-                offs = np.empty(ctx.n + 1, dtype=np.uint64)
-                from .dedup import _check as _gcheck, lib as _glib
-                _gcheck(_glib().oge_gpu_dedup_pull(ctx._h, bam.records_buffer(), ctx.nbytes, offs.ctypes.data, len(offs), C.byref(nb), C.byref(nr)))
-                bam.adopt_offsets(offs)
+                if not gpu_deflate:
+                    nb, nr = C.c_uint64(), C.c_uint64()
+                    offs = np.empty(ctx.n + 1, dtype=np.uint64)
+                    from .dedup import _check as _gcheck, lib as _glib
+                    _gcheck(_glib().oge_gpu_dedup_pull(ctx._h, bam.records_buffer(), ctx.nbytes, offs.ctypes.data, len(offs), C.byref(nb), C.byref(nr)))
+                    bam.adopt_offsets(offs)
             else:
                 ptr, nbytes, off_ptr = bam.records_ptr()
                 ctx.push_async(ptr, nbytes, off_ptr, bam.n)
@@ -264,18 +277,26 @@ def dedup_file(in_path: str, out_path: str, remove_duplicates: bool = False, lev
                     ctx.sort()
                 ctx.run()
                 flags = ctx.flags()
-                if sort and bam.n:      # the records come back in their new order
+                if sort and bam.n and not gpu_deflate:      # the records come back in their new order
                     nb, nr = C.c_uint64(), C.c_uint64()
                     offs = np.empty(bam.n + 1, dtype=np.uint64)
                     from .dedup import _check as _gcheck, lib as _glib
                     _gcheck(_glib().oge_gpu_dedup_pull(ctx._h, ptr, nbytes, offs.ctypes.data, len(offs), C.byref(nb), C.byref(nr)))
                     bam.adopt_offsets(offs)
-            out = {"dedup": ctx.stats(), "flagstats": ctx.flagstats(), "gpu_inflate": gpu_inflate}
+            members = None
+            if gpu_deflate:
+                members, _, n_out = ctx.deflate()
+            out = {"dedup": ctx.stats(), "flagstats": ctx.flagstats(), "gpu_inflate": gpu_inflate, "gpu_deflate": gpu_deflate}
             if sort:
                 bam.set_sort_order("coordinate")
                 out["sort"] = ctx.sort_stats()
-        bam.apply_flags(flags, remove_duplicates, threads)
-        bam.store(out_path, format, level, pg_command_line, threads=threads)
-        out["timings"] = bam.timings()
-        out["n_out"] = bam.n
+        if gpu_deflate:
+            bam.store_members(out_path, members, level, pg_command_line)
+            out["timings"] = bam.timings()
+            out["n_out"] = n_out
+        else:
+            bam.apply_flags(flags, remove_duplicates, threads)
+            bam.store(out_path, format, level, pg_command_line, threads=threads)
+            out["timings"] = bam.timings()
+            out["n_out"] = bam.n
     return out

@@ -86,8 +86,11 @@ struct oge_gpu_dedup_ctx {
     oge_gpu_dedup_config cfg;
     int sms = 148;
     cudaStream_t stream = nullptr, copy_stream = nullptr, side_stream = nullptr;
+    cudaStream_t inflate_stream = nullptr;      // push_bgzf: engine submissions / inflate kernels only, never a host-to-device copy
+
     cudaEvent_t copy_done = nullptr;
     cudaEvent_t ev[10];
+    cudaEvent_t ev_piece[3] = {nullptr, nullptr, nullptr};      // push_bgzf: stream hand-overs per piece (no timing)
     // sharded path: phase clocks are resolved lazily (no host sync per phase)
     static constexpr int N_CLK = 48;
     cudaEvent_t clk_ev[2 * N_CLK];
@@ -112,6 +115,14 @@ struct oge_gpu_dedup_ctx {
     uint64_t n = 0, rec_bytes = 0;
     uint64_t rec_lead = 0;      // records start at rec.p + rec_lead (non-zero after push_bgzf: the BAM header sits in front)
     uint8_t *recs() const { return rec.p + rec_lead; }
+
+    // push_bgzf: the compressed file and its block table on the device
+    DevBuf<uint8_t> zcomp;
+    DevBuf<uint64_t> zoff;
+    DevBuf<uint32_t> zcs;
+    // oge_gpu_dedup_deflate: the finished BGZF members of the output
+    DevBuf<uint8_t> zfile;
+    uint64_t zfile_bytes = 0;
 
     // read-group table
     DevBuf<uint8_t> rg_bytes;

@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <string>
@@ -220,6 +221,7 @@ int oge_gpu_dedup_create(const oge_gpu_dedup_config *cfg, oge_gpu_dedup_ctx **ou
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&c->inflate_stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&c->sh.ev_main, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&c->sh.ev_far, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreate(&c->sh.ev_side[0]) != cudaSuccess || cudaEventCreate(&c->sh.ev_side[1]) != cudaSuccess ||
@@ -229,6 +231,7 @@ int oge_gpu_dedup_create(const oge_gpu_dedup_config *cfg, oge_gpu_dedup_ctx **ou
             break;
         }
         for (auto &e : c->ev) cudaEventCreate(&e);
+        for (auto &e : c->ev_piece) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
         for (auto &e : c->clk_ev) cudaEventCreate(&e);
         for (auto &e : c->pass_ev) { e = nullptr; if (cfg->profile_events) cudaEventCreate(&e); }
         for (auto &e : c->k_ev) { e = nullptr; if (cfg->profile_events) cudaEventCreate(&e); }
@@ -255,6 +258,7 @@ void oge_gpu_dedup_destroy(oge_gpu_dedup_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->side_stream) cudaStreamSynchronize(c->side_stream);
+    c->zcomp.release(); c->zoff.release(); c->zcs.release(); c->zfile.release();
     c->rec.release(); c->off.release(); c->rg_bytes.release(); c->rg_off.release(); c->rg_lib.release();
     c->frag.release(); c->sortbuf.release(); c->pair.release(); c->pair2.release(); c->pairf.release(); c->pairf2.release(); c->ufrag.release(); c->ufrag2.release(); c->uset.release(); c->hk.release();
     c->tag.release(); c->flag_in.release(); c->flag_out.release(); c->dup.release(); c->scratch.release();
@@ -262,6 +266,7 @@ void oge_gpu_dedup_destroy(oge_gpu_dedup_ctx *c) {
     c->cs_u32.release(); c->perm.release(); c->cs_bsum.release(); c->off2.release(); c->rec2.release(); c->mate_of.release(); c->counters.release(); c->table.release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : c->ev_piece) if (e) cudaEventDestroy(e);
     for (auto &e : c->clk_ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->pass_ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->k_ev) if (e) cudaEventDestroy(e);
@@ -269,6 +274,7 @@ void oge_gpu_dedup_destroy(oge_gpu_dedup_ctx *c) {
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
+    if (c->inflate_stream) cudaStreamDestroy(c->inflate_stream);
     if (c->sh.ev_main) cudaEventDestroy(c->sh.ev_main);
     if (c->sh.ev_far) cudaEventDestroy(c->sh.ev_far);
     for (auto &e : c->sh.ev_side) if (e) cudaEventDestroy(e);
@@ -314,6 +320,8 @@ int oge_gpu_dedup_set_readgroups(oge_gpu_dedup_ctx *c, const char *const *ids, c
     return OGE_OK;
 }
 
+static uint64_t g_bgzf_chunk_bytes = 0;      // 0: per-mode default (oge_gpu_set_bgzf_chunk_bytes)
+
 int oge_gpu_dedup_push_bgzf(oge_gpu_dedup_ctx *c, const uint8_t *comp, uint64_t comp_bytes, const uint64_t *block_in_off,
                             const uint32_t *block_csize, const uint32_t *block_isize, uint64_t n_blocks, uint64_t header_bytes,
                             uint8_t *host_copy) {
@@ -321,10 +329,13 @@ int oge_gpu_dedup_push_bgzf(oge_gpu_dedup_ctx *c, const uint8_t *comp, uint64_t 
     if (c->n || c->rec_bytes) return fail_msg(OGE_ERR_STATE, "push_bgzf: the context already holds records (oge_gpu_dedup_reset first)");
     OGE_CUDA_TRY(cudaSetDevice(c->cfg.device));
     std::vector<uint64_t> out_off(n_blocks + 1);
-    uint64_t total = 0;
+    uint64_t total = 0, prev_end = 0;
+    bool in_file_order = true;      // blocks back to back in the order of the table (any BGZF file): the upload can go in pieces
     for (uint64_t b = 0; b < n_blocks; b++) {
         if (block_csize[b] < 26 || block_isize[b] > 65536 || block_in_off[b] + block_csize[b] > comp_bytes)
             return fail_msg(OGE_ERR_BAD_RECORD, "push_bgzf: block %llu does not fit the file or inflates to more than 65536 bytes", (unsigned long long) b);
+        if (block_in_off[b] < prev_end) in_file_order = false;
+        prev_end = block_in_off[b] + block_csize[b];
         out_off[b] = total;
         total += block_isize[b];
     }
@@ -332,51 +343,153 @@ int oge_gpu_dedup_push_bgzf(oge_gpu_dedup_ctx *c, const uint8_t *comp, uint64_t 
     if (header_bytes > total) return fail_msg(OGE_ERR_INVALID_ARG, "push_bgzf: header_bytes beyond the inflated stream");
     const uint64_t rec_bytes = total - header_bytes;
     const uint64_t lead = (header_bytes + 255) & ~255ull;      // the first record lands on a 256-byte boundary of the buffer
-    cudaStream_t s = c->stream;
+    cudaStream_t s = c->stream, up = c->copy_stream, down = c->side_stream;
+    const int mode = inflate_mode_for(c->cfg.device);
+    const bool engine = mode == INFLATE_ENGINE;
     int rc;
-    if ((rc = c->rec.reserve(lead + rec_bytes, false, s))) return rc;
-    DevBuf<uint8_t> zcomp;
-    DevBuf<uint64_t> zoff;       // in_off[n_blocks], out_off[n_blocks + 1]
-    DevBuf<uint32_t> zcs;        // csize[n_blocks], err[2]
-    auto done = [&](int code) {
-        zcomp.release();
-        zoff.release();
-        zcs.release();
-        return code;
-    };
-    if ((rc = zcomp.reserve(comp_bytes + 64, false, s)) || (rc = zoff.reserve(2 * n_blocks + 1, false, s)) || (rc = zcs.reserve(n_blocks + 2, false, s)))
+    // the engine is not bounded by a block's ISIZE (bgzf_inflate.cu): room for the longest operation behind the last block
+    if ((rc = c->rec.reserve(lead + rec_bytes + (engine ? engine_inflate_slack(c->cfg.device) : 0), false, s))) return rc;
+    // staging of the compressed file and its block table: kept by the context (cudaFree of 10 GB costs 240 ms and cudaMalloc
+    // 70 ms on the B200, more than the whole upload saves; oge_gpu_dedup_reset keeps them, destroy frees them)
+    DevBuf<uint8_t> &zcomp = c->zcomp;
+    DevBuf<uint64_t> &zoff = c->zoff;       // in_off[n_blocks], out_off[n_blocks + 1]
+    DevBuf<uint32_t> &zcs = c->zcs;         // csize[n_blocks], err[2], act[n_blocks]
+    auto done = [&](int code) { return code; };
+    if ((rc = zcomp.reserve(comp_bytes + 64, false, s)) || (rc = zoff.reserve(2 * n_blocks + 1, false, s)) || (rc = zcs.reserve(2 * n_blocks + 2, false, s)))
         return done(rc);
-    cudaEvent_t e0 = c->ev[8], e1 = c->ev[9], eu = c->ev[0], ed = c->ev[1];
-    cudaError_t e = cudaEventRecord(eu, s);
-    if (e == cudaSuccess) e = cudaMemsetAsync(zcomp.p + comp_bytes, 0, 64, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(zcomp.p, comp, comp_bytes, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(zoff.p, block_in_off, n_blocks * 8, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(zoff.p + n_blocks, out_off.data(), (n_blocks + 1) * 8, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(zcs.p, block_csize, n_blocks * 4, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess) e = cudaMemsetAsync(zcs.p + n_blocks, 0, 8, s);
-    if (e == cudaSuccess) e = cudaEventRecord(e0, s);
-    if (e != cudaSuccess) return done(fail_cuda(e, "push_bgzf upload", __FILE__, __LINE__));
-    BgzfParams P;
-    P.comp = zcomp.p;
-    P.in_off = zoff.p;
-    P.out_off = zoff.p + n_blocks;
-    P.csize = zcs.p;
-    P.n_blocks = n_blocks;
-    P.out = c->rec.p + (lead - header_bytes);
-    P.err = zcs.p + n_blocks;
-    uint64_t launches = 0;
-    if ((rc = launch_bgzf_inflate(P, c->sms, s, &launches))) return done(rc);
+    uint32_t *d_err = zcs.p + n_blocks, *d_act = zcs.p + n_blocks + 2;
+    uint8_t *d_out = c->rec.p + (lead - header_bytes);
+    // ---- the pieces: the upload of piece k + 1 (copy stream) runs under the inflate of piece k (main stream) and the copy-back
+    //      of piece k - 1 (side stream, host_copy only).  Piece size: a few inflate-milliseconds, so that the last piece's inflate
+    //      -- the only part of it the upload does not hide -- is small, but enough blocks to fill the machine for the kernels.
+    uint64_t piece = g_bgzf_chunk_bytes ? g_bgzf_chunk_bytes : (engine ? (64ull << 20) : (512ull << 20));
+    if (!in_file_order) piece = ~0ull;
+    // Streams.  The inflates go on a stream of their own that never carries a host-to-device copy: measured on the B200
+    // (profiles/r2_push_bgzf_stream_trace.txt), engine work submitted on a stream that has done H2D copies is not started
+    // while ANOTHER stream's H2D copies are queued -- piece 0's inflate began when the last piece's upload ended -- whereas on
+    // a stream that has only ever seen engine work and memsets it starts the moment its own piece has landed.
+    cudaStream_t zs = c->inflate_stream;
+    cudaEvent_t t_up0 = c->ev[0], t_up1 = c->ev[1], t_inf0 = c->ev[8], t_inf1 = c->ev[9], t_all0 = c->ev[2], t_all1 = c->ev[3], t_dn0 = c->ev[4], t_dn1 = c->ev[5];
+    cudaError_t e = cudaEventRecord(t_all0, s);
+    // the three side streams start behind whatever the main stream was doing with these buffers
+    if (e == cudaSuccess) e = cudaEventRecord(c->ev_piece[0], s);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(up, c->ev_piece[0], 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(down, c->ev_piece[0], 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(zs, c->ev_piece[0], 0);
+    if (e == cudaSuccess) e = cudaMemsetAsync(zcomp.p + comp_bytes, 0, 64, zs);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_err, 0, 8, zs);
+    if (e == cudaSuccess && engine) e = cudaMemsetAsync(d_act, 0, n_blocks * 4, zs);
+    if (e == cudaSuccess) e = cudaEventRecord(t_up0, up);
+    if (e == cudaSuccess) e = cudaEventRecord(t_dn0, down);
+    // block tables: in front of the pieces on the copy stream (the kernels read them on the device; the engine takes the
+    // table from the host and only the size check reads out_off)
+    if (e == cudaSuccess) e = cudaMemcpyAsync(zoff.p + n_blocks, out_off.data(), (n_blocks + 1) * 8, cudaMemcpyHostToDevice, up);
+    if (e == cudaSuccess && !engine) {
+        e = cudaMemcpyAsync(zoff.p, block_in_off, n_blocks * 8, cudaMemcpyHostToDevice, up);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(zcs.p, block_csize, n_blocks * 4, cudaMemcpyHostToDevice, up);
+    }
+    if (e != cudaSuccess) return done(fail_cuda(e, "push_bgzf setup", __FILE__, __LINE__));
+    uint64_t launches = 0, pieces = 0, engine_ops = 0;
+    const bool trace = getenv("OGE_TRACE_PUSH") != nullptr;
+    auto wall = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; };
+    const double w0 = wall();
+    std::vector<cudaEvent_t> tr_ev;      // trace: per piece upload done / inflate start / inflate done
+    for (uint64_t b0 = 0; b0 < n_blocks && e == cudaSuccess;) {
+        uint64_t b1 = b0, bytes = 0;
+        while (b1 < n_blocks && (bytes < piece || b1 == b0)) bytes += block_csize[b1++];
+        // file bytes of the piece (the whole file when the table is not in file order)
+        const uint64_t lo = in_file_order ? block_in_off[b0] : 0, hi = in_file_order ? block_in_off[b1 - 1] + block_csize[b1 - 1] : comp_bytes;
+        e = cudaMemcpyAsync(zcomp.p + lo, comp + lo, hi - lo, cudaMemcpyHostToDevice, up);
+        if (trace) {
+            cudaEvent_t ta, tb, tc;
+            cudaEventCreate(&ta); cudaEventCreate(&tb); cudaEventCreate(&tc);
+            tr_ev.push_back(ta); tr_ev.push_back(tb); tr_ev.push_back(tc);
+            cudaEventRecord(ta, up);
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(c->ev_piece[1], up);      // re-recorded per piece: a wait binds to the record before it
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(zs, c->ev_piece[1], 0);
+        if (trace) cudaEventRecord(tr_ev[tr_ev.size() - 2], zs);
+        if (e == cudaSuccess && pieces == 0) e = cudaEventRecord(t_inf0, zs);
+        if (e != cudaSuccess) break;
+        if (engine) {
+            if ((rc = engine_inflate_submit(zcomp.p, block_in_off, block_csize, block_isize, out_off.data(), d_out, d_act, b0, b1, zs, &engine_ops))) {
+                cudaStreamSynchronize(up);
+                cudaStreamSynchronize(zs);
+                return done(rc);
+            }
+        } else {
+            BgzfParams P;
+            P.comp = zcomp.p;
+            P.in_off = zoff.p + b0;
+            P.out_off = zoff.p + n_blocks + b0;
+            P.csize = zcs.p + b0;
+            P.n_blocks = b1 - b0;
+            P.block_base = b0;
+            P.out = d_out;
+            P.err = d_err;
+            if ((rc = launch_bgzf_inflate(P, mode, c->sms, zs, &launches))) {
+                cudaStreamSynchronize(up);
+                cudaStreamSynchronize(zs);
+                return done(rc);
+            }
+        }
+        if (trace) cudaEventRecord(tr_ev[tr_ev.size() - 1], zs);
+        if (host_copy && rec_bytes) {
+            // inflated bytes of the piece that belong to the record array -> the caller's buffer
+            const uint64_t o0 = std::max(out_off[b0], header_bytes), o1 = std::max(out_off[b1], header_bytes);
+            if (o1 > o0) {
+                e = cudaEventRecord(c->ev_piece[2], zs);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(down, c->ev_piece[2], 0);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(host_copy + (o0 - header_bytes), d_out + o0, o1 - o0, cudaMemcpyDeviceToHost, down);
+            }
+        }
+        pieces++;
+        b0 = b1;
+    }
+    const double w1 = wall();
     uint32_t err[2] = {0, 0};
-    e = cudaEventRecord(e1, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(err, zcs.p + n_blocks, 8, cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess && host_copy && rec_bytes) e = cudaMemcpyAsync(host_copy, c->rec.p + lead, rec_bytes, cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaEventRecord(ed, s);
+    if (e == cudaSuccess) e = cudaEventRecord(t_up1, up);
+    if (e == cudaSuccess) e = cudaEventRecord(t_inf1, zs);
+    if (e == cudaSuccess) e = cudaEventRecord(t_dn1, down);
+    // back on the main stream: the size check (engine), the verdict, the end
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s, t_inf1, 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s, t_up1, 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s, t_dn1, 0);
+    if (e == cudaSuccess && engine && (rc = launch_bgzf_check_sizes(d_act, zoff.p + n_blocks, n_blocks, d_err, s, &launches))) e = cudaErrorUnknown;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(err, d_err, 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaEventRecord(t_all1, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) return done(fail_cuda(e, "push_bgzf inflate", __FILE__, __LINE__));
+    if (e != cudaSuccess) {
+        cudaStreamSynchronize(up);
+        cudaStreamSynchronize(down);
+        cudaStreamSynchronize(zs);
+        // the engine's verdict on a stream that is not valid deflate is a launch failure, which surfaces at whichever call
+        // looks first and takes the context with it (bgzf_inflate.cu)
+        if (engine && (e == cudaErrorLaunchFailure || cudaDeviceSynchronize() == cudaErrorLaunchFailure)) {
+            cudaGetLastError();
+            return done(fail_msg(OGE_ERR_BAD_RECORD, "Zlib inflate failed (a BGZF block is not a valid deflate stream; reported by the hardware decompress "
+                                                     "engine as a launch failure, the CUDA context of this process is lost: select a kernel decoder, "
+                                                     "OGE_INFLATE_KERNEL=warp, to locate the block)."));
+        }
+        return done(fail_cuda(e, "push_bgzf inflate", __FILE__, __LINE__));
+    }
+    if (trace) {
+        for (size_t k = 0; k < tr_ev.size() / 3; k++)
+            if (k < 4 || k + 2 >= tr_ev.size() / 3 || k == tr_ev.size() / 6)
+                fprintf(stderr, "push_bgzf trace: piece %zu: upload done at %.2f ms, inflate start %.2f, inflate done %.2f\n", k, ms_between(t_all0, tr_ev[3 * k]),
+                        ms_between(t_all0, tr_ev[3 * k + 1]), ms_between(t_all0, tr_ev[3 * k + 2]));
+        for (auto &ev : tr_ev) cudaEventDestroy(ev);
+    }
+    if (trace)
+        fprintf(stderr, "push_bgzf trace: %llu pieces issued in %.2f ms, drained after %.2f ms more\n", (unsigned long long) pieces, w1 - w0, wall() - w1);
     if (err[0]) return done(fail_msg(OGE_ERR_BAD_RECORD, "Zlib inflate failed (BGZF block %u, code %u).", err[1], err[0]));
-    c->stats.ms_inflate = ms_between(e0, e1);
-    c->stats.ms_inflate_h2d = ms_between(eu, e0);
-    c->stats.ms_inflate_d2h = ms_between(e1, ed);
+    c->stats.ms_inflate = ms_between(t_inf0, t_inf1);
+    c->stats.ms_inflate_h2d = ms_between(t_up0, t_up1);
+    c->stats.ms_inflate_d2h = host_copy ? ms_between(t_dn0, t_dn1) : 0.f;
+    c->stats.ms_push_bgzf = ms_between(t_all0, t_all1);
+    c->stats.ms_inflate_start = ms_between(t_all0, t_inf0);
+    c->stats.inflate_mode = (uint32_t) mode;
+    c->stats.inflate_pieces = (uint32_t) pieces;
     c->stats.ms_frame = 0;
     c->stats.frame_repairs = 0;
     c->stats.inflate_blocks = n_blocks;
@@ -705,6 +818,11 @@ int oge_gpu_dedup_run(oge_gpu_dedup_ctx *c) {
         c->stats.frame_repairs = keep.frame_repairs;
         c->stats.ms_inflate_h2d = keep.ms_inflate_h2d;
         c->stats.ms_inflate_d2h = keep.ms_inflate_d2h;
+        c->stats.ms_push_bgzf = keep.ms_push_bgzf;
+        c->stats.ms_inflate_start = keep.ms_inflate_start;
+        c->zfile_bytes = 0;      // a new run: the members made from the last one are stale
+        c->stats.inflate_mode = keep.inflate_mode;
+        c->stats.inflate_pieces = keep.inflate_pieces;
     }
     c->stats.n_records = c->n;
     if (c->n == 0) {
@@ -927,6 +1045,100 @@ int oge_gpu_dedup_pull(oge_gpu_dedup_ctx *c, uint8_t *out_records, uint64_t cap_
     return OGE_OK;
 }
 
+int oge_gpu_dedup_deflate(oge_gpu_dedup_ctx *c, uint64_t *out_bytes, uint64_t *out_blocks, uint64_t *out_nrec) {
+    if (!c || !out_bytes || !out_blocks || !out_nrec) return fail_msg(OGE_ERR_INVALID_ARG, "deflate: null argument");
+    if (!c->ran) return fail_msg(OGE_ERR_STATE, "deflate: call oge_gpu_dedup_run first");
+    OGE_CUDA_TRY(cudaSetDevice(c->cfg.device));
+    cudaStream_t s = c->stream;
+    *out_bytes = 0;
+    *out_blocks = 0;
+    *out_nrec = 0;
+    c->zfile_bytes = 0;
+    c->stats.ms_deflate = 0;
+    c->stats.deflate_blocks = c->stats.deflate_bytes_in = c->stats.deflate_bytes_out = 0;
+    if (c->n == 0) return OGE_OK;
+    int rc;
+    uint64_t launches = 0;
+    cudaEvent_t e0 = c->ev[8], e1 = c->ev[9];
+    OGE_CUDA_TRY(cudaEventRecord(e0, s));
+    // the writer's bin for every record (bam_serializer.h:112-116), in place: idempotent, and what pull returns afterwards
+    // carries it as well
+    OGE_CUDA_TRY(cudaMemsetAsync(c->counters.p + CNT_ERR, 0, 4, s));
+    if ((rc = launch_fix_bins(c->recs(), c->off.p, c->n, c->counters.p + CNT_ERR, s, &launches))) return rc;
+    const uint8_t *in = c->recs();
+    uint64_t total = c->rec_bytes, nrec = c->n;
+    DevBuf<uint8_t> kept;         // -r: the records that stay, compacted
+    DevBuf<uint64_t> kept_off;
+    DevBuf<uint8_t> stage;
+    DevBuf<uint32_t> sizes;       // dsize[n_blocks], crc[n_blocks], ticket (2 words)
+    DevBuf<uint64_t> moff;
+    DevBuf<uint8_t> seqs;
+    auto done = [&](int code) {
+        kept.release(); kept_off.release(); stage.release(); sizes.release(); moff.release(); seqs.release();
+        return code;
+    };
+    uint32_t bin_err = 0;
+    if (c->cfg.remove_duplicates) {      // :456-458
+        if ((rc = kept.reserve(c->rec_bytes, false, s)) || (rc = kept_off.reserve(c->n + 1, false, s))) return done(rc);
+        if ((rc = launch_compact(c->recs(), c->off.p, c->n, c->flag_out.p, 1, kept.p, kept_off.p, reinterpret_cast<uint64_t *>(c->scratch.p),
+                                 c->counters.p, s, &launches)))
+            return done(rc);
+        uint64_t totals[2] = {0, 0};
+        OGE_CUDA_TRY(cudaMemcpyAsync(totals, c->scratch.p, 16, cudaMemcpyDeviceToHost, s));
+        OGE_CUDA_TRY(cudaMemcpyAsync(&bin_err, c->counters.p + CNT_ERR, 4, cudaMemcpyDeviceToHost, s));
+        OGE_CUDA_TRY(cudaStreamSynchronize(s));
+        nrec = totals[0];
+        total = totals[1];
+        in = kept.p;
+    }
+    const uint64_t n_blocks = (total + DEFLATE_PAYLOAD - 1) / DEFLATE_PAYLOAD;
+    if (n_blocks) {
+        if ((rc = stage.reserve(n_blocks * (uint64_t) DEFLATE_STAGE_STRIDE, false, s)) || (rc = sizes.reserve(2 * n_blocks + 4, false, s)) ||
+            (rc = moff.reserve(n_blocks + 1, false, s)) || (rc = seqs.reserve(deflate_seq_bytes(c->sms), false, s)))
+            return done(rc);
+        DeflateParams P;
+        P.in = in;
+        P.total = total;
+        P.payload = DEFLATE_PAYLOAD;
+        P.n_blocks = n_blocks;
+        P.stage = stage.p;
+        P.dsize = sizes.p;
+        P.crc = sizes.p + n_blocks;
+        P.seqs = seqs.p;
+        P.ticket = reinterpret_cast<unsigned long long *>(sizes.p + ((2 * n_blocks + 1) & ~1ull));
+        if ((rc = launch_bgzf_deflate(P, c->sms, s, &launches)) || (rc = launch_scan_sizes(P.dsize, n_blocks, moff.p, s, &launches))) return done(rc);
+        uint64_t file_bytes = 0;
+        OGE_CUDA_TRY(cudaMemcpyAsync(&file_bytes, moff.p + n_blocks, 8, cudaMemcpyDeviceToHost, s));
+        if (!c->cfg.remove_duplicates) OGE_CUDA_TRY(cudaMemcpyAsync(&bin_err, c->counters.p + CNT_ERR, 4, cudaMemcpyDeviceToHost, s));
+        OGE_CUDA_TRY(cudaStreamSynchronize(s));
+        if ((rc = c->zfile.reserve(file_bytes, false, s))) return done(rc);
+        if ((rc = launch_bgzf_assemble(P, moff.p, c->zfile.p, s, &launches))) return done(rc);
+        c->zfile_bytes = file_bytes;
+    }
+    OGE_CUDA_TRY(cudaEventRecord(e1, s));
+    OGE_CUDA_TRY(cudaStreamSynchronize(s));
+    if (bin_err) return done(fail_msg(OGE_ERR_BAD_RECORD, "deflate: a record's name and CIGAR overrun the record"));
+    c->stats.ms_deflate = ms_between(e0, e1);
+    c->stats.deflate_blocks = n_blocks;
+    c->stats.deflate_bytes_in = total;
+    c->stats.deflate_bytes_out = c->zfile_bytes;
+    *out_bytes = c->zfile_bytes;
+    *out_blocks = n_blocks;
+    *out_nrec = nrec;
+    return done(OGE_OK);
+}
+
+int oge_gpu_dedup_pull_bgzf(oge_gpu_dedup_ctx *c, uint8_t *out, uint64_t cap_bytes) {
+    if (!c || (!out && c && c->zfile_bytes)) return fail_msg(OGE_ERR_INVALID_ARG, "pull_bgzf: null argument");
+    if (cap_bytes < c->zfile_bytes) return fail_msg(OGE_ERR_INVALID_ARG, "pull_bgzf: need %llu bytes", (unsigned long long) c->zfile_bytes);
+    OGE_CUDA_TRY(cudaSetDevice(c->cfg.device));
+    if (c->zfile_bytes) {
+        OGE_CUDA_TRY(cudaMemcpyAsync(out, c->zfile.p, c->zfile_bytes, cudaMemcpyDeviceToHost, c->stream));
+        OGE_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    return OGE_OK;
+}
+
 int oge_gpu_dedup_flagstats(oge_gpu_dedup_ctx *c, oge_gpu_flagstats *out) {
     if (!c || !out) return fail_msg(OGE_ERR_INVALID_ARG, "flagstats: null argument");
     if (!c->ran) return fail_msg(OGE_ERR_STATE, "flagstats: call oge_gpu_dedup_run first");
@@ -1144,8 +1356,19 @@ extern "C" int oge_gpu_debug_sort_bench(int device, uint64_t n, int bit_lo, int 
 }
 
 extern "C" int oge_gpu_set_inflate_kernel(int kernel) {
-    if (kernel != 0 && kernel != 1) return fail_msg(OGE_ERR_INVALID_ARG, "set_inflate_kernel: 0 (thread per block) or 1 (warp per block)");
+    if (kernel < -1 || kernel > 2)
+        return fail_msg(OGE_ERR_INVALID_ARG, "set_inflate_kernel: 0 (thread per block), 1 (warp per block), 2 (hardware decompress engine) or -1 (default)");
     oge::set_inflate_kernel(kernel);
+    return OGE_OK;
+}
+
+extern "C" int oge_gpu_inflate_kernel(int device) {
+    if (device < 0 || device >= oge_gpu_device_count()) return fail_msg(OGE_ERR_INVALID_ARG, "inflate_kernel: device %d", device);
+    return oge::inflate_mode_for(device);
+}
+
+extern "C" int oge_gpu_set_bgzf_chunk_bytes(uint64_t bytes) {
+    g_bgzf_chunk_bytes = bytes;
     return OGE_OK;
 }
 

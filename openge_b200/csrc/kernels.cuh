@@ -171,18 +171,49 @@ struct FlagParams {
 
 int launch_flags(const FlagParams &P, cudaStream_t stream, uint64_t *launches);
 
-// ---- BGZF inflate (bgzf_inflate.cu): one warp per block
+// ---- BGZF inflate (bgzf_inflate.cu): the hardware decompress engine, or one of two SIMT decoders
 struct BgzfParams {
     const uint8_t *comp;        // the compressed file
     const uint64_t *in_off;     // [n_blocks] byte offset of every block in comp
     const uint32_t *csize;      // [n_blocks] BSIZE + 1
     const uint64_t *out_off;    // [n_blocks + 1] byte offset of every block's payload in the inflated stream
     uint64_t n_blocks;
+    uint64_t block_base;        // index of block 0 of this launch in the file (error reports)
     uint8_t *out;               // where byte 0 of the inflated stream goes
     uint32_t *err;              // [2]: first inflate error code, block index
 };
-int launch_bgzf_inflate(const BgzfParams &P, int sms, cudaStream_t stream, uint64_t *launches);
-void set_inflate_kernel(int mode);      // 0: thread per block, 1: warp per block
+enum { INFLATE_THREADS = 0, INFLATE_WARP = 1, INFLATE_ENGINE = 2 };
+int launch_bgzf_inflate(const BgzfParams &P, int mode, int sms, cudaStream_t stream, uint64_t *launches);
+void set_inflate_kernel(int mode);      // INFLATE_*; -1: back to the default (OGE_INFLATE_KERNEL, else the engine where the device has one)
+int inflate_mode_for(int device);       // the mode push_bgzf uses on this device
+// Hardware decompress engine (cuMemBatchDecompressAsync): one operation per block of [b0, b1), host-side block table;
+// the engine writes the byte count of every block to act[b].  Blocks that inflate to nothing are not submitted.
+int engine_inflate_submit(const uint8_t *d_comp, const uint64_t *h_in_off, const uint32_t *h_csize, const uint32_t *h_isize,
+                          const uint64_t *h_out_off, uint8_t *d_out, uint32_t *d_act, uint64_t b0, uint64_t b1, cudaStream_t stream,
+                          uint64_t *submitted);
+// act[b] against ISIZE for every block (the reference's assert(zs.total_out == uncompressed_size)) -> err[0..1]
+int launch_bgzf_check_sizes(const uint32_t *act, const uint64_t *out_off, uint64_t n_blocks, uint32_t *err, cudaStream_t stream, uint64_t *launches);
+uint64_t engine_inflate_slack(int device);      // bytes the destination buffer keeps free behind the last block
+
+// ---- BGZF members made on the device (bgzf_deflate.cu): bins, one warp per block deflate + CRC-32, packing
+constexpr uint32_t DEFLATE_PAYLOAD = 65280;          // inflated bytes per block (any split is a valid BGZF file; htslib's)
+constexpr uint32_t DEFLATE_STAGE_STRIDE = 65536;     // staging slot per block: the stream is at most payload + 5 bytes (+ 3 of word padding)
+struct DeflateParams {
+    const uint8_t *in;          // the byte stream to compress, 4-byte aligned, readable 8 bytes beyond its end
+    uint64_t total;
+    uint32_t payload;
+    uint64_t n_blocks;
+    uint8_t *stage;             // [n_blocks][DEFLATE_STAGE_STRIDE]
+    uint32_t *dsize;            // [n_blocks] bytes of every block's deflate stream
+    uint32_t *crc;              // [n_blocks] CRC-32 of every block's payload
+    void *seqs;                 // parse scratch, deflate_seq_bytes(sms)
+    unsigned long long *ticket; // block dispenser
+};
+size_t deflate_seq_bytes(int sms);
+int launch_fix_bins(uint8_t *rec, const uint64_t *off, uint64_t n, uint32_t *err, cudaStream_t stream, uint64_t *launches);
+int launch_bgzf_deflate(const DeflateParams &P, int sms, cudaStream_t stream, uint64_t *launches);
+int launch_scan_sizes(const uint32_t *dsize, uint64_t n, uint64_t *moff /* n + 1 */, cudaStream_t stream, uint64_t *launches);
+int launch_bgzf_assemble(const DeflateParams &P, uint64_t *moff, uint8_t *out, cudaStream_t stream, uint64_t *launches);
 
 // ---- record framing on the device (frame.cu): speculative parallel chain walk + proof
 struct FrameParams {

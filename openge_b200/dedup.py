@@ -19,7 +19,7 @@ import numpy as np
 from . import _build, header as _header
 from .bamio import BamFile
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 OGE_OK = 0
 ERRORS = {-1: "OGE_ERR_INVALID_ARG", -2: "OGE_ERR_CUDA", -3: "OGE_ERR_NOMEM", -4: "OGE_ERR_KEY_RANGE",
@@ -48,7 +48,10 @@ class Stats(C.Structure):
                 ("inflate_bytes_in", C.c_uint64), ("inflate_bytes_out", C.c_uint64), ("frame_repairs", C.c_uint64),
                 ("ms_inflate_h2d", C.c_float), ("ms_inflate_d2h", C.c_float),
                 ("n_local_pairs", C.c_uint64), ("n_join_leftovers", C.c_uint64), ("n_local_retracted", C.c_uint64),
-                ("ms_kernel", C.c_float * 8)]
+                ("ms_kernel", C.c_float * 8),
+                ("ms_push_bgzf", C.c_float), ("inflate_mode", C.c_uint32), ("inflate_pieces", C.c_uint32),
+                ("ms_inflate_start", C.c_float),
+                ("ms_deflate", C.c_float), ("deflate_blocks", C.c_uint64), ("deflate_bytes_in", C.c_uint64), ("deflate_bytes_out", C.c_uint64)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_}
@@ -73,11 +76,11 @@ END_DTYPE = np.dtype([("eligible", "<i4"), ("pair_eligible", "<i4"), ("ref", "<i
 
 EXPORTS = ["oge_gpu_dedup_create", "oge_gpu_dedup_destroy", "oge_gpu_dedup_set_readgroups", "oge_gpu_dedup_push",
            "oge_gpu_dedup_push_bgzf", "oge_gpu_dedup_set_offsets", "oge_gpu_dedup_frame", "oge_gpu_dedup_offsets",
-           "oge_gpu_dedup_sync", "oge_gpu_dedup_run", "oge_gpu_dedup_flags", "oge_gpu_dedup_pull",
+           "oge_gpu_dedup_sync", "oge_gpu_dedup_run", "oge_gpu_dedup_flags", "oge_gpu_dedup_pull", "oge_gpu_dedup_deflate", "oge_gpu_dedup_pull_bgzf",
            "oge_gpu_dedup_reset", "oge_gpu_dedup_flagstats", "oge_gpu_dedup_get_stats", "oge_gpu_dedup_debug_ends",
            "oge_gpu_dedup_device_ptrs", "oge_gpu_host_alloc", "oge_gpu_host_free", "oge_gpu_device_count",
            "oge_gpu_last_error", "oge_gpu_abi_version", "oge_gpu_debug_sort128", "oge_gpu_debug_sort_bench",
-           "oge_gpu_set_sort_variant", "oge_gpu_set_inflate_kernel", "oge_gpu_shard_setup", "oge_gpu_shard_begin", "oge_gpu_shard_probe",
+           "oge_gpu_set_sort_variant", "oge_gpu_set_inflate_kernel", "oge_gpu_inflate_kernel", "oge_gpu_set_bgzf_chunk_bytes", "oge_gpu_shard_setup", "oge_gpu_shard_begin", "oge_gpu_shard_probe",
            "oge_gpu_shard_finish", "oge_gpu_shard_apply", "oge_gpu_copy_d2d", "oge_gpu_dedup_sort", "oge_gpu_dedup_sort_order",
            "oge_gpu_dedup_sort_stats", "oge_gpu_sizeof", "oge_gpu_shard_key_bytes", "oge_gpu_shard_set_entry_bytes", "oge_gpu_shard_replay",
            "oge_gpu_shard_comm_id", "oge_gpu_shard_comm_init", "oge_gpu_shard_comm_destroy", "oge_gpu_shard_step"]
@@ -144,6 +147,8 @@ def _load(path):
         L.oge_gpu_dedup_sort_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_float)]
         L.oge_gpu_dedup_flags.argtypes = [vp, vp, u64]
         L.oge_gpu_dedup_pull.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64), C.POINTER(u64)]
+        L.oge_gpu_dedup_deflate.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+        L.oge_gpu_dedup_pull_bgzf.argtypes = [vp, vp, u64]
         L.oge_gpu_dedup_reset.argtypes = [vp]
         L.oge_gpu_dedup_get_stats.argtypes = [vp, C.POINTER(Stats)]
         L.oge_gpu_dedup_flagstats.argtypes = [vp, vp]
@@ -159,6 +164,8 @@ def _load(path):
                                                C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.oge_gpu_set_sort_variant.argtypes = [C.c_int]
         L.oge_gpu_set_inflate_kernel.argtypes = [C.c_int]
+        L.oge_gpu_inflate_kernel.argtypes = [C.c_int]
+        L.oge_gpu_set_bgzf_chunk_bytes.argtypes = [u64]
         L.oge_gpu_copy_d2d.argtypes = [vp, vp, vp, u64]
         L.oge_gpu_shard_setup.argtypes = [vp, u64, vp, vp, vp]
         L.oge_gpu_shard_key_bytes.argtypes = [vp, C.POINTER(C.c_uint32)]
@@ -203,9 +210,26 @@ def set_sort_variant(variant: int):
     _check(lib().oge_gpu_set_sort_variant(variant))
 
 
+INFLATE_KERNELS = {"threads": 0, "warp": 1, "engine": 2, "default": -1}
+
+
 def set_inflate_kernel(kernel: str):
-    """Tuning hook: "warp" (one warp per BGZF block, default) or "threads" (one thread per block)."""
-    _check(lib().oge_gpu_set_inflate_kernel({"threads": 0, "warp": 1}[kernel]))
+    """Which BGZF decoder push_bgzf uses: "engine" (the B200's hardware decompress engine, default where the device has
+    one), "warp" (one warp per block), "threads" (one thread per block), "default"."""
+    _check(lib().oge_gpu_set_inflate_kernel(INFLATE_KERNELS[kernel]))
+
+
+def inflate_kernel(device: int = 0) -> str:
+    """The decoder push_bgzf would use on `device` now."""
+    k = lib().oge_gpu_inflate_kernel(device)
+    if k < 0:
+        _check(k)
+    return {v: n for n, v in INFLATE_KERNELS.items()}[k]
+
+
+def set_bgzf_chunk_bytes(nbytes: int):
+    """Tuning hook: compressed bytes per piece of push_bgzf's overlapped upload (0 default, 2**64-1 one piece)."""
+    _check(lib().oge_gpu_set_bgzf_chunk_bytes(nbytes))
 
 
 def debug_sort_bench(n, bit_lo, bit_hi, variant=0, mode=0, reps=3, seed=1, device=0) -> dict:
@@ -361,6 +385,15 @@ class DedupContext:
         if nr.value == 0:
             off[0] = 0
         return rec[: nb.value], off[: nr.value + 1]
+
+    def deflate(self):
+        """The output records (flag-patched, bins recomputed, -r applied) compressed into BGZF members on the device
+        -> (member bytes as uint8, blocks, records).  Identical to the reference's output after decompression."""
+        nb, nblk, nr = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(lib().oge_gpu_dedup_deflate(self._h, C.byref(nb), C.byref(nblk), C.byref(nr)))
+        out = np.empty(nb.value, dtype=np.uint8)
+        _check(lib().oge_gpu_dedup_pull_bgzf(self._h, out.ctypes.data, out.nbytes))
+        return out, int(nblk.value), int(nr.value)
 
     def stats(self) -> dict:
         st = Stats()

@@ -829,19 +829,8 @@ int oge_bam_apply_flags(oge_bam_file *f, const uint16_t *flags, int remove_dupli
     return 0;
 }
 
-int oge_bam_store(oge_bam_file *f, const char *path, const char *format, int level, const char *pg_command_line,
-                  const char *pg_version, int threads) {
-    if (!f || !path) return fail(OGE_BAM_ERR_ARG, "store: null argument");
-    threads = clamp_threads(threads);
-    const double t0 = now_s();
-    bool raw = false;
-    if (format && *format) {
-        if (!strcmp(format, "rawbam")) raw = true;
-        else if (strcmp(format, "bam")) return fail(OGE_BAM_ERR_ARG, "Unknown file format specified: %s.", format);
-    }
-    if (level < 0 || level > 9) return fail(OGE_BAM_ERR_ARG, "store: compression level %d", level);
-
-    // ---- header bytes: BamSerializer::open (util/bam_serializer.h:46-79) over the re-rendered header
+// header bytes: BamSerializer::open (util/bam_serializer.h:46-79) over the re-rendered header
+static std::vector<uint8_t> render_head(const oge_bam_file *f, const char *pg_command_line, const char *pg_version) {
     HeaderModel h = f->header;
     if (pg_command_line && *pg_command_line) {      // file_writer.cpp:76-89
         PgRec pg;
@@ -872,6 +861,23 @@ int oge_bam_store(oge_bam_file *f, const char *path, const char *format, int lev
         put(&len, 4);
     }
 
+    return head;
+}
+
+int oge_bam_store(oge_bam_file *f, const char *path, const char *format, int level, const char *pg_command_line,
+                  const char *pg_version, int threads) {
+    if (!f || !path) return fail(OGE_BAM_ERR_ARG, "store: null argument");
+    threads = clamp_threads(threads);
+    const double t0 = now_s();
+    bool raw = false;
+    if (format && *format) {
+        if (!strcmp(format, "rawbam")) raw = true;
+        else if (strcmp(format, "bam")) return fail(OGE_BAM_ERR_ARG, "Unknown file format specified: %s.", format);
+    }
+    if (level < 0 || level > 9) return fail(OGE_BAM_ERR_ARG, "store: compression level %d", level);
+
+    const std::vector<uint8_t> head = render_head(f, pg_command_line, pg_version);
+
     const int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
     if (fd < 0) return fail(OGE_BAM_ERR_IO, "cannot open %s for writing: %s", path, strerror(errno));
     Sink sink;
@@ -885,6 +891,37 @@ int oge_bam_store(oge_bam_file *f, const char *path, const char *format, int lev
         seg.add(head.data(), head.size());
         seg.add(f->stream + f->first_record, f->rec_bytes);
         rc = bgzf_deflate_stream(seg, level, threads, sink);
+    }
+    if (close(fd) != 0 && !rc) rc = fail(OGE_BAM_ERR_IO, "close failed on %s", path);
+    f->t[5] = now_s() - t0;
+    return rc;
+}
+
+int oge_bam_store_members(oge_bam_file *f, const char *path, int level, const char *pg_command_line, const char *pg_version,
+                          const uint8_t *members, uint64_t members_bytes) {
+    if (!f || !path || (!members && members_bytes)) return fail(OGE_BAM_ERR_ARG, "store_members: null argument");
+    if (level < 0 || level > 9) return fail(OGE_BAM_ERR_ARG, "store_members: compression level %d", level);
+    const double t0 = now_s();
+    const std::vector<uint8_t> head = render_head(f, pg_command_line, pg_version);
+    // the header in members of its own (host zlib, `level`), then the record members as they come, then the empty member that
+    // ends a BGZF file (BgzfOutputStream::close, util/bgzf_output_stream.cpp:225-250)
+    std::vector<uint8_t> hz(BGZF_BLOCK);
+    const int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return fail(OGE_BAM_ERR_IO, "cannot open %s for writing: %s", path, strerror(errno));
+    Sink sink;
+    sink.fd = fd;
+    int rc = 0;
+    const uint32_t full = level == 0 ? BGZF_BLOCK - 64 : BGZF_BLOCK;
+    for (size_t at = 0; at < head.size() && !rc; at += full) {
+        uint32_t n = 0;
+        rc = bgzf_compress_block(head.data() + at, (uint32_t) std::min<size_t>(full, head.size() - at), level, hz.data(), &n);
+        if (!rc) rc = sink.write(hz.data(), n);
+    }
+    if (!rc && members_bytes) rc = sink.write(members, members_bytes);
+    if (!rc) {
+        uint32_t n = 0;
+        rc = bgzf_compress_block(head.data(), 0, level, hz.data(), &n);
+        if (!rc) rc = sink.write(hz.data(), n);
     }
     if (close(fd) != 0 && !rc) rc = fail(OGE_BAM_ERR_IO, "close failed on %s", path);
     f->t[5] = now_s() - t0;

@@ -11,6 +11,9 @@
 // BGZF input is inflated ON THE GPU (oge_gpu_dedup_push_bgzf: one warp per block; the compressed file crosses PCIe and the
 // records are born in HBM); --cpu-inflate keeps the inflate on the host threads (oge_bam_load).  --pinned puts the host
 // copy of the records in page-locked memory.
+// --gpu-deflate makes the OUTPUT file's BGZF blocks on the GPU as well (oge_gpu_dedup_deflate: bins, -r filter, one warp per
+// block deflate + CRC-32): the records never come back uncompressed and the host's zlib leaves the path; the file then is
+// identical to the reference's after decompression instead of byte for byte (block boundaries and deflate streams differ).
 // --nosplit, -T and -d are accepted and have no effect: the result is always that of the canonical single-chain run
 // (`--nosplit -v`), nothing is spilled to disk, and there is one pipeline.  --stats prints the report of
 // the reference's Statistics module (algorithms/statistics.cpp:150-174) for the output stream, counted on the device.
@@ -41,14 +44,14 @@ static void die(const char *what, const char *msg) {
 static void usage() {
     fprintf(stderr,
             "usage: oge_dedup_fused [dedup] in.bam -o out.bam [-r] [-v] [-t threads] [-c level] [-F bam|rawbam] [--nopg] [--stats]\n"
-            "                       [--device N] [--cpu-inflate] [--pinned] [--nosplit] [-T tmpdir] [-d]\n"
+            "                       [--device N] [--cpu-inflate] [--gpu-deflate] [--pinned] [--nosplit] [-T tmpdir] [-d]\n"
             "                       [--sort | -M]   coordinate sort on the GPU in front of the dedup (= openge mergesort -M)\n");
     exit(-1);
 }
 
 int main(int argc, char **argv) {
     std::string in, out, format;
-    bool remove_dups = false, verbose = false, nopg = false, stats = false, cpu_inflate = false, pinned = false, sort_first = false;
+    bool remove_dups = false, verbose = false, nopg = false, stats = false, cpu_inflate = false, pinned = false, sort_first = false, gpu_deflate = false;
     int threads = 0, level = 6, device = 0;
     std::string command_line = "openge ";      // commands/commands.cpp:36-40
     for (int i = 1; i < argc; i++) {
@@ -74,6 +77,7 @@ int main(int argc, char **argv) {
         else if (a == "--stats") stats = true;
         else if (a == "--sort" || a == "-M") sort_first = true;      // `openge mergesort -M`: coordinate sort in front of the dedup
         else if (a == "--cpu-inflate") cpu_inflate = true;
+        else if (a == "--gpu-deflate") gpu_deflate = true;
         else if (a == "--pinned") pinned = true;
         else if (a == "--device") device = atoi(need());
         else if (!a.empty() && a[0] == '-') usage();
@@ -82,6 +86,7 @@ int main(int argc, char **argv) {
         else die("oge_dedup_fused", "one input file only (merge inputs with `openge mergesort` first).");
     }
     if (in.empty() || out.empty()) usage();
+    if (format == "rawbam") gpu_deflate = false;      // nothing to compress
 
     const double t_start = now_s();
     oge_bam_file *bam = NULL;
@@ -106,7 +111,7 @@ int main(int argc, char **argv) {
     cfg.n_ref = oge_bam_n_ref(bam);
     for (int32_t i = 0; i < cfg.n_ref; i++)
         if (oge_bam_ref_len(bam, i) > cfg.max_ref_len) cfg.max_ref_len = oge_bam_ref_len(bam, i);
-    cfg.remove_duplicates = 0;      // -r is applied by oge_bam_apply_flags: oge_gpu_dedup_pull returns every record
+    cfg.remove_duplicates = gpu_deflate && remove_dups ? 1 : 0;      // else -r is applied by oge_bam_apply_flags: oge_gpu_dedup_pull returns every record
     cfg.verify_names = -1;
     if (!gpu_inflate) {
         cfg.capacity_records = oge_bam_n_records(bam);
@@ -133,7 +138,8 @@ int main(int argc, char **argv) {
         uint64_t comp_bytes, n_blocks, header_bytes;
         oge_bam_bgzf_index(bam, &comp, &comp_bytes, &in_off, &csize, &isize, &n_blocks, &header_bytes);
         uint8_t *host_records = NULL;
-        std::thread prefault([&] { host_records = oge_bam_records_buffer(bam); });      // page the host buffer in meanwhile
+        // page the host buffer in meanwhile (not needed when the output is compressed on the device: the records stay there)
+        std::thread prefault([&] { if (!gpu_deflate) host_records = oge_bam_records_buffer(bam); });
         if ((rc = oge_gpu_dedup_push_bgzf(ctx, comp, comp_bytes, in_off, csize, isize, n_blocks, header_bytes, NULL))) {
             prefault.join();
             die("Error reading BAM", oge_gpu_last_error());
@@ -150,6 +156,7 @@ int main(int argc, char **argv) {
         flags.resize(n ? n : 1);
         if ((rc = oge_gpu_dedup_flags(ctx, flags.data(), n))) die("MarkDuplicates (GPU): flags", oge_gpu_last_error());
         prefault.join();
+        if (!gpu_deflate) {
         if (!host_records) die("Error reading BAM", oge_bam_last_error());
         std::vector<uint64_t> offs(n + 1);
         uint64_t got_bytes = 0, got_n = 0;
@@ -158,6 +165,7 @@ int main(int argc, char **argv) {
         if ((rc = oge_gpu_dedup_pull(ctx, host_records, total - header_bytes, offs.data(), n + 1, &got_bytes, &got_n))) die("MarkDuplicates (GPU): pull", oge_gpu_last_error());
         if (n == 0) offs[0] = 0;
         if ((rc = oge_bam_adopt_offsets(bam, offs.data(), n))) die("Error reading BAM", oge_bam_last_error());
+        }
     } else {
         n = oge_bam_n_records(bam);
         if (verbose) fprintf(stderr, "Read %llu records.\n", (unsigned long long) n);
@@ -167,7 +175,7 @@ int main(int argc, char **argv) {
         if ((rc = oge_gpu_dedup_run(ctx))) die("MarkDuplicates (GPU): run", oge_gpu_last_error());
         flags.resize(n ? n : 1);
         if ((rc = oge_gpu_dedup_flags(ctx, flags.data(), n))) die("MarkDuplicates (GPU): flags", oge_gpu_last_error());
-        if (sort_first && n) {      // the records come back in their new order
+        if (sort_first && n && !gpu_deflate) {      // the records come back in their new order
             std::vector<uint64_t> offs(n + 1);
             uint64_t got_bytes = 0, got_n = 0;
             if ((rc = oge_gpu_dedup_pull(ctx, oge_bam_records(bam), oge_bam_records_bytes(bam), offs.data(), n + 1, &got_bytes, &got_n)))
@@ -190,6 +198,15 @@ int main(int argc, char **argv) {
     oge_gpu_flagstats fs;
     memset(&fs, 0, sizeof(fs));
     if (stats && (rc = oge_gpu_dedup_flagstats(ctx, &fs))) die("Statistics (GPU)", oge_gpu_last_error());
+    uint8_t *members = NULL;
+    uint64_t members_bytes = 0, member_blocks = 0, n_written = 0;
+    if (gpu_deflate) {      // the output's BGZF members, made where the records are
+        if ((rc = oge_gpu_dedup_deflate(ctx, &members_bytes, &member_blocks, &n_written))) die("Error writing BAM", oge_gpu_last_error());
+        members = (uint8_t *) (pinned ? oge_gpu_host_alloc(members_bytes + 1) : malloc(members_bytes + 1));
+        if (!members) die("Error writing BAM", "cannot allocate the output buffer.");
+        if ((rc = oge_gpu_dedup_pull_bgzf(ctx, members, members_bytes))) die("Error writing BAM", oge_gpu_last_error());
+        oge_gpu_dedup_get_stats(ctx, &st);
+    }
     oge_gpu_dedup_destroy(ctx);
     const double t_gpu = now_s();
     if (verbose) {
@@ -198,10 +215,18 @@ int main(int argc, char **argv) {
         fprintf(stderr, "Marking %llu records as duplicates.\n", (unsigned long long) st.n_duplicates);
     }
 
-    if ((rc = oge_bam_apply_flags(bam, flags.data(), remove_dups ? 1 : 0, threads))) die("Error rewriting records", oge_bam_last_error());
-    if ((rc = oge_bam_store(bam, out.c_str(), format.empty() ? NULL : format.c_str(), level, nopg ? NULL : command_line.c_str(),
-                            OGE_VERSION_STRING, threads)))
-        die("Error writing BAM", oge_bam_last_error());
+    if (gpu_deflate) {
+        if ((rc = oge_bam_store_members(bam, out.c_str(), level, nopg ? NULL : command_line.c_str(), OGE_VERSION_STRING, members, members_bytes)))
+            die("Error writing BAM", oge_bam_last_error());
+        if (pinned) oge_gpu_host_free(members);
+        else free(members);
+    } else {
+        if ((rc = oge_bam_apply_flags(bam, flags.data(), remove_dups ? 1 : 0, threads))) die("Error rewriting records", oge_bam_last_error());
+        if ((rc = oge_bam_store(bam, out.c_str(), format.empty() ? NULL : format.c_str(), level, nopg ? NULL : command_line.c_str(),
+                                OGE_VERSION_STRING, threads)))
+            die("Error writing BAM", oge_bam_last_error());
+        n_written = oge_bam_n_records(bam);
+    }
     const double t_end = now_s();
 
     if (stats) {      // the report of algorithms/statistics.cpp:150-174 (with -r the reference's Statistics stage would sit
@@ -226,7 +251,10 @@ int main(int argc, char **argv) {
     if (verbose) {
         double t[6];
         oge_bam_timings(bam, t, 6);
-        fprintf(stderr, "Written %llu records.\n", (unsigned long long) oge_bam_n_records(bam));
+        fprintf(stderr, "Written %llu records.\n", (unsigned long long) n_written);
+        if (gpu_deflate)
+            fprintf(stderr, "gpu deflate: %llu blocks, %.1f MB -> %.1f MB in %.3f ms on the device (%.1f GB/s in).\n", (unsigned long long) member_blocks,
+                    st.deflate_bytes_in / 1e6, st.deflate_bytes_out / 1e6, st.ms_deflate, st.ms_deflate > 0 ? st.deflate_bytes_in / 1e6 / st.ms_deflate : 0.0);
         if (gpu_inflate)
             fprintf(stderr,
                     "Timing: open %.3f s (read %.3f, scan %.3f) | gpu inflate %.3f s (upload %.1f ms, kernel %.3f ms = %.1f GB/s out) | gpu frame %.3f s "

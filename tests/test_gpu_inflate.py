@@ -4,6 +4,7 @@ import ctypes as C
 import hashlib
 import os
 import subprocess
+import sys
 import tempfile
 import zlib
 
@@ -52,12 +53,16 @@ def gpu_inflate_file(path):
     return ctx, h
 
 
-@pytest.fixture(params=["warp", "threads"])
+@pytest.fixture(params=["engine", "warp", "threads"])
 def inflate_kernel(request):
-    """Both device decoders: one warp per block (default) and one thread per block."""
+    """All three decoders: the hardware decompress engine (default on the B200), one warp per block, one thread per block."""
     dedup.set_inflate_kernel(request.param)
+    if dedup.inflate_kernel() != request.param:
+        dedup.set_inflate_kernel("default")
+        pytest.skip("this device / driver has no hardware decompress engine")
     yield request.param
-    dedup.set_inflate_kernel("warp")
+    dedup.set_inflate_kernel("default")
+    dedup.set_bgzf_chunk_bytes(0)
 
 
 @pytest.mark.parametrize("level,strategy,block", [(6, zlib.Z_DEFAULT_STRATEGY, 65536), (1, zlib.Z_DEFAULT_STRATEGY, 65280),
@@ -74,6 +79,7 @@ def test_device_inflate_matches_zlib(tmp, inflate_kernel, level, strategy, block
         assert np.array_equal(h.records, bam.records) and np.array_equal(h.offsets, bam.offsets)      # the D2H copy
         st = ctx.stats()
         assert st["inflate_bytes_out"] == len(raw) and st["ms_inflate"] > 0
+        assert st["inflate_mode"] == dedup.INFLATE_KERNELS[inflate_kernel] and st["inflate_pieces"] == 1 and st["ms_push_bgzf"] > 0
         # and what stayed in HBM is the same: run the dedup on it
         ptr, nbytes, off_ptr = h.records_ptr()
         ctx.set_header(h.text)
@@ -107,7 +113,63 @@ def test_device_inflate_other_writers_and_large_headers(tmp, inflate_kernel):
             assert np.array_equal(h.records, b.records) and np.array_equal(h.offsets, b.offsets)
 
 
+@pytest.mark.parametrize("piece", [1, 150000, 1 << 20])
+def test_device_inflate_in_pieces(tmp, inflate_kernel, piece):
+    # the overlapped form of push_bgzf: upload, inflate and copy-back piece by piece on three streams (a piece of 1 byte =
+    # one BGZF block per piece); the header spans several blocks, so the first pieces hold no record bytes
+    bam = synth.make("C4", 0.01, seed=77)
+    text = bam.text + "".join("@CO\tpadding line %06d to push the header over one BGZF block\n" % i for i in range(3000))
+    b2 = bamio.BamFile(text=text, refs=bam.refs, records=bam.records, offsets=bam.offsets)
+    raw = bamio.serialize_bam_stream(b2)
+    p = os.path.join(tmp, "pieces.bam")
+    open(p, "wb").write(bgzf_blocks(raw, 1, zlib.Z_DEFAULT_STRATEGY, 20000))
+    dedup.set_bgzf_chunk_bytes(piece)
+    ctx, h = gpu_inflate_file(p)
+    with ctx, h:
+        st = ctx.stats()
+        assert 3 < st["inflate_pieces"] <= -(-st["inflate_bytes_in"] // piece) and (piece > 1 or st["inflate_pieces"] == st["inflate_blocks"])
+        assert h.n == bam.n and np.array_equal(h.records, bam.records) and np.array_equal(h.offsets, bam.offsets)      # the copy-back, piece by piece
+        n = ctx.frame()      # and what stayed in HBM
+        assert n == bam.n
+        ctx.set_header(h.text)
+        ctx.run()
+        assert np.array_equal(ctx.flags(), oracle.markdup(bam.records, bam.offsets, bam.text))
+
+
+def test_engine_reports_a_corrupt_stream_like_the_reference(tmp):
+    # the hardware engine answers an invalid deflate stream with a launch failure that takes the CUDA context with it (the
+    # reference exit(-1)s in the same place): checked in a process of its own; the library must still name the cause
+    dedup.set_inflate_kernel("engine")
+    have = dedup.inflate_kernel() == "engine"
+    dedup.set_inflate_kernel("default")
+    if not have:
+        pytest.skip("this device / driver has no hardware decompress engine")
+    bam = synth.make("C1", 0.01, seed=9)
+    z = bytearray(bamhost.bgzf_compress(bamio.serialize_bam_stream(bam), 6))
+    bs0 = int.from_bytes(z[16:18], "little") + 1
+    for k in range(bs0 + 600, bs0 + 640):
+        z[k] ^= 0xA5
+    p = os.path.join(tmp, "bad.bam")
+    open(p, "wb").write(bytes(z))
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from openge_b200 import bamhost, dedup\n"
+            "h = bamhost.HostBam(%r, defer_inflate=True)\n"
+            "ctx = dedup.DedupContext(n_ref=len(h.refs), max_ref_len=100000000)\n"
+            "ix = h.bgzf_index()\n"
+            "try:\n"
+            "    ctx.push_bgzf(ix['comp'], ix['comp_bytes'], ix['in_off'], ix['csize'], ix['isize'], ix['n_blocks'], ix['header_bytes'], None)\n"
+            "except dedup.DedupError as e:\n"
+            "    print('CODE', e.code, str(e)); sys.stdout.flush()\n"
+            "    import os; os._exit(0)\n"
+            "print('NO ERROR')\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), p)
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300,
+                       env=dict(os.environ, OGE_INFLATE_KERNEL="engine"))
+    assert "CODE -7" in r.stdout and "Zlib inflate failed" in r.stdout, r.stdout
+
+
 def test_device_inflate_rejects_corrupt_blocks(tmp, inflate_kernel):
+    if inflate_kernel == "engine":
+        pytest.skip("see test_engine_reports_a_corrupt_stream_like_the_reference: the engine's failure ends the CUDA context")
     bam = synth.make("C1", 0.01, seed=9)
     z = bytearray(bamhost.bgzf_compress(bamio.serialize_bam_stream(bam), 6))
     bs0 = int.from_bytes(z[16:18], "little") + 1

@@ -1,6 +1,7 @@
-"""The BGZF inflate kernel on its own: CUDA-event time of oge_gpu_dedup_push_bgzf's kernel for one kernel form.
+"""The BGZF decoder on its own: CUDA-event time of oge_gpu_dedup_push_bgzf's inflate for one decoder, the file uploaded
+in ONE piece first (no overlap with the upload, so the time is the decoder's).
 
-    python tools/bench/inflate_ab.py --config C2 --scale 0.1 --level 1 --mode threads|warp [--reps 3]
+    python tools/bench/inflate_ab.py --config C2 --scale 0.1 --level 1 --mode engine|threads|warp [--reps 3]
 
 Run once per mode (the form is chosen by OGE_INFLATE_KERNEL when the library first launches it).  Prints one JSON
 line; the inflated bytes are verified against the generator's stream every time."""
@@ -19,12 +20,14 @@ def main():
     ap.add_argument("--config", default="C2")
     ap.add_argument("--scale", type=float, default=0.1)
     ap.add_argument("--level", type=int, default=1)
-    ap.add_argument("--mode", default="threads", choices=["threads", "warp"])
+    ap.add_argument("--mode", default="threads", choices=["engine", "threads", "warp"])
     ap.add_argument("--reps", type=int, default=3)
     a = ap.parse_args()
     os.environ["OGE_INFLATE_KERNEL"] = a.mode
     import numpy as np
     from openge_b200 import bamhost, bamio, dedup, synth
+    dedup.set_bgzf_chunk_bytes(2 ** 64 - 1)
+    assert dedup.inflate_kernel() == a.mode, "decoder %s is not available here" % a.mode
     bam = synth.make(a.config, a.scale, seed=2)
     raw = bamio.serialize_bam_stream(bam)
     with tempfile.TemporaryDirectory(dir="/dev/shm") as d:
