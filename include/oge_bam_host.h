@@ -111,6 +111,11 @@ int oge_bam_store(oge_bam_file *f, const char *path, const char *format, int lev
  * oge_bam_store's (and the reference's) after decompression; its block boundaries and deflate streams differ. */
 int oge_bam_store_members(oge_bam_file *f, const char *path, int level, const char *pg_command_line, const char *pg_version,
                           const uint8_t *members, uint64_t members_bytes);
+/* ... with the members arriving in pieces: fill(user, &data, &nbytes) hands out the next piece (valid until the next call),
+ * nbytes = 0 at the end, a non-zero return aborts.  Pieces need not end on member boundaries. */
+typedef int (*oge_bam_fill_fn)(void *user, const uint8_t **data, uint64_t *nbytes);
+int oge_bam_store_members_stream(oge_bam_file *f, const char *path, int level, const char *pg_command_line, const char *pg_version,
+                                 oge_bam_fill_fn fill, void *user);
 
 /* seconds: [0] read file, [1] block scan, [2] inflate, [3] header + framing, [4] apply_flags, [5] store */
 int oge_bam_timings(const oge_bam_file *f, double *out, int n);

@@ -210,6 +210,12 @@ int oge_gpu_dedup_pull(oge_gpu_dedup_ctx *ctx, uint8_t *out_records, uint64_t ca
  * reports their size, the number of blocks and of records; pull_bgzf copies them out. */
 int oge_gpu_dedup_deflate(oge_gpu_dedup_ctx *ctx, uint64_t *out_bytes, uint64_t *out_blocks, uint64_t *out_nrec);
 int oge_gpu_dedup_pull_bgzf(oge_gpu_dedup_ctx *ctx, uint8_t *out, uint64_t cap_bytes);
+/* The same in parts, for a writer that streams the members through small pinned buffers into the file while the next part
+ * is on its way (the reference's writer thread does the same with its block queue, bgzf_output_stream.cpp:170-223):
+ * _part queues the copy of members[offset, offset + nbytes) on a side stream and returns; _wait returns when every queued
+ * part has landed.  Any split is fine for a file (parts need not end on member boundaries). */
+int oge_gpu_dedup_pull_bgzf_part(oge_gpu_dedup_ctx *ctx, uint64_t offset, uint64_t nbytes, uint8_t *out);
+int oge_gpu_dedup_pull_bgzf_wait(oge_gpu_dedup_ctx *ctx);
 
 /* The counters of the reference's Statistics module (algorithms/statistics.cpp:77-162: what `openge stats` prints,
  * and what a Statistics stage placed behind MarkDuplicates would count) over the resident records and their

@@ -19,7 +19,7 @@ ERRORS = {-1: "OGE_BAM_ERR_IO", -2: "OGE_BAM_ERR_FORMAT", -3: "OGE_BAM_ERR_NOMEM
 
 EXPORTS = ["oge_bam_load", "oge_bam_open_bgzf", "oge_bam_bgzf_index", "oge_bam_records_buffer", "oge_bam_frame_records", "oge_bam_adopt_offsets", "oge_bam_close", "oge_bam_header_text", "oge_bam_n_ref", "oge_bam_ref_name", "oge_bam_ref_len",
            "oge_bam_records", "oge_bam_records_bytes", "oge_bam_offsets", "oge_bam_n_records", "oge_bam_library_table",
-           "oge_bam_apply_flags", "oge_bam_store", "oge_bam_store_members", "oge_bam_timings", "oge_bgzf_decompress", "oge_bgzf_compress",
+           "oge_bam_apply_flags", "oge_bam_store", "oge_bam_store_members", "oge_bam_store_members_stream", "oge_bam_timings", "oge_bgzf_decompress", "oge_bgzf_compress",
            "oge_bam_header_render", "oge_bam_buffer_free", "oge_bam_last_error", "oge_bam_set_sort_order"]
 
 
@@ -90,7 +90,7 @@ def _check(rc):
 
 def _take(ptr, n) -> bytes:
     try:
-        return C.string_at(ptr.value, n) if n else b""
+        return bytes((C.c_char * n).from_address(ptr.value)) if n else b""      # (string_at takes a C int: 2 GB at most)
     finally:
         lib().oge_bam_buffer_free(ptr)
 

@@ -1139,6 +1139,23 @@ int oge_gpu_dedup_pull_bgzf(oge_gpu_dedup_ctx *c, uint8_t *out, uint64_t cap_byt
     return OGE_OK;
 }
 
+int oge_gpu_dedup_pull_bgzf_part(oge_gpu_dedup_ctx *c, uint64_t offset, uint64_t nbytes, uint8_t *out) {
+    if (!c || (!out && nbytes)) return fail_msg(OGE_ERR_INVALID_ARG, "pull_bgzf_part: null argument");
+    if (offset > c->zfile_bytes || nbytes > c->zfile_bytes - offset)
+        return fail_msg(OGE_ERR_INVALID_ARG, "pull_bgzf_part: [%llu, +%llu) is outside the %llu bytes of members", (unsigned long long) offset,
+                        (unsigned long long) nbytes, (unsigned long long) c->zfile_bytes);
+    OGE_CUDA_TRY(cudaSetDevice(c->cfg.device));
+    if (nbytes) OGE_CUDA_TRY(cudaMemcpyAsync(out, c->zfile.p + offset, nbytes, cudaMemcpyDeviceToHost, c->side_stream));
+    return OGE_OK;
+}
+
+int oge_gpu_dedup_pull_bgzf_wait(oge_gpu_dedup_ctx *c) {
+    if (!c) return fail_msg(OGE_ERR_INVALID_ARG, "pull_bgzf_wait: null context");
+    OGE_CUDA_TRY(cudaSetDevice(c->cfg.device));
+    OGE_CUDA_TRY(cudaStreamSynchronize(c->side_stream));
+    return OGE_OK;
+}
+
 int oge_gpu_dedup_flagstats(oge_gpu_dedup_ctx *c, oge_gpu_flagstats *out) {
     if (!c || !out) return fail_msg(OGE_ERR_INVALID_ARG, "flagstats: null argument");
     if (!c->ran) return fail_msg(OGE_ERR_STATE, "flagstats: call oge_gpu_dedup_run first");

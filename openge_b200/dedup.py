@@ -76,7 +76,7 @@ END_DTYPE = np.dtype([("eligible", "<i4"), ("pair_eligible", "<i4"), ("ref", "<i
 
 EXPORTS = ["oge_gpu_dedup_create", "oge_gpu_dedup_destroy", "oge_gpu_dedup_set_readgroups", "oge_gpu_dedup_push",
            "oge_gpu_dedup_push_bgzf", "oge_gpu_dedup_set_offsets", "oge_gpu_dedup_frame", "oge_gpu_dedup_offsets",
-           "oge_gpu_dedup_sync", "oge_gpu_dedup_run", "oge_gpu_dedup_flags", "oge_gpu_dedup_pull", "oge_gpu_dedup_deflate", "oge_gpu_dedup_pull_bgzf",
+           "oge_gpu_dedup_sync", "oge_gpu_dedup_run", "oge_gpu_dedup_flags", "oge_gpu_dedup_pull", "oge_gpu_dedup_deflate", "oge_gpu_dedup_pull_bgzf", "oge_gpu_dedup_pull_bgzf_part", "oge_gpu_dedup_pull_bgzf_wait",
            "oge_gpu_dedup_reset", "oge_gpu_dedup_flagstats", "oge_gpu_dedup_get_stats", "oge_gpu_dedup_debug_ends",
            "oge_gpu_dedup_device_ptrs", "oge_gpu_host_alloc", "oge_gpu_host_free", "oge_gpu_device_count",
            "oge_gpu_last_error", "oge_gpu_abi_version", "oge_gpu_debug_sort128", "oge_gpu_debug_sort_bench",
@@ -149,6 +149,8 @@ def _load(path):
         L.oge_gpu_dedup_pull.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64), C.POINTER(u64)]
         L.oge_gpu_dedup_deflate.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
         L.oge_gpu_dedup_pull_bgzf.argtypes = [vp, vp, u64]
+        L.oge_gpu_dedup_pull_bgzf_part.argtypes = [vp, u64, u64, vp]
+        L.oge_gpu_dedup_pull_bgzf_wait.argtypes = [vp]
         L.oge_gpu_dedup_reset.argtypes = [vp]
         L.oge_gpu_dedup_get_stats.argtypes = [vp, C.POINTER(Stats)]
         L.oge_gpu_dedup_flagstats.argtypes = [vp, vp]
@@ -338,7 +340,7 @@ class DedupContext:
         self.nbytes += nbytes
 
     def push_bgzf(self, comp_ptr, comp_bytes, in_off_ptr, csize_ptr, isize_ptr, n_blocks, header_bytes, host_copy_ptr=None):
-        """Inflate a whole BGZF file on the device (one warp per block); records land in HBM, and in host_copy."""
+        """Inflate a whole BGZF file on the device (decompress engine, or a kernel); records land in HBM, and in host_copy."""
         _check(lib().oge_gpu_dedup_push_bgzf(self._h, comp_ptr, comp_bytes, in_off_ptr, csize_ptr, isize_ptr, n_blocks, header_bytes, host_copy_ptr))
 
     def set_offsets(self, offsets_ptr, nrec, nbytes):

@@ -897,9 +897,9 @@ int oge_bam_store(oge_bam_file *f, const char *path, const char *format, int lev
     return rc;
 }
 
-int oge_bam_store_members(oge_bam_file *f, const char *path, int level, const char *pg_command_line, const char *pg_version,
-                          const uint8_t *members, uint64_t members_bytes) {
-    if (!f || !path || (!members && members_bytes)) return fail(OGE_BAM_ERR_ARG, "store_members: null argument");
+int oge_bam_store_members_stream(oge_bam_file *f, const char *path, int level, const char *pg_command_line, const char *pg_version,
+                                 oge_bam_fill_fn fill, void *user) {
+    if (!f || !path || !fill) return fail(OGE_BAM_ERR_ARG, "store_members: null argument");
     if (level < 0 || level > 9) return fail(OGE_BAM_ERR_ARG, "store_members: compression level %d", level);
     const double t0 = now_s();
     const std::vector<uint8_t> head = render_head(f, pg_command_line, pg_version);
@@ -917,7 +917,16 @@ int oge_bam_store_members(oge_bam_file *f, const char *path, int level, const ch
         rc = bgzf_compress_block(head.data() + at, (uint32_t) std::min<size_t>(full, head.size() - at), level, hz.data(), &n);
         if (!rc) rc = sink.write(hz.data(), n);
     }
-    if (!rc && members_bytes) rc = sink.write(members, members_bytes);
+    while (!rc) {
+        const uint8_t *data = nullptr;
+        uint64_t n = 0;
+        if (fill(user, &data, &n)) {
+            rc = fail(OGE_BAM_ERR_IO, "store_members: the source of the members failed");
+            break;
+        }
+        if (!n) break;
+        rc = sink.write(data, n);
+    }
     if (!rc) {
         uint32_t n = 0;
         rc = bgzf_compress_block(head.data(), 0, level, hz.data(), &n);
@@ -926,6 +935,27 @@ int oge_bam_store_members(oge_bam_file *f, const char *path, int level, const ch
     if (close(fd) != 0 && !rc) rc = fail(OGE_BAM_ERR_IO, "close failed on %s", path);
     f->t[5] = now_s() - t0;
     return rc;
+}
+
+namespace {
+struct OneChunk {
+    const uint8_t *p;
+    uint64_t n;
+};
+int one_chunk_fill(void *user, const uint8_t **data, uint64_t *nbytes) {
+    OneChunk *c = (OneChunk *) user;
+    *data = c->p;
+    *nbytes = c->n;
+    c->n = 0;
+    return 0;
+}
+}  // namespace
+
+int oge_bam_store_members(oge_bam_file *f, const char *path, int level, const char *pg_command_line, const char *pg_version,
+                          const uint8_t *members, uint64_t members_bytes) {
+    if (!members && members_bytes) return fail(OGE_BAM_ERR_ARG, "store_members: null argument");
+    OneChunk c = {members, members_bytes};
+    return oge_bam_store_members_stream(f, path, level, pg_command_line, pg_version, one_chunk_fill, &c);
 }
 
 int oge_bam_timings(const oge_bam_file *f, double *out, int n) {

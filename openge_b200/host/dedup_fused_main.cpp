@@ -21,6 +21,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <chrono>
 #include <string>
@@ -41,17 +42,46 @@ static void die(const char *what, const char *msg) {
     exit(-1);
 }
 
+// The device-made BGZF members on their way into the file: two pinned buffers, the copy of part k + 1 in flight while the
+// writer has part k (oge_bam_store_members_stream pulls the parts through this).
+struct MemberStream {
+    oge_gpu_dedup_ctx *ctx;
+    uint64_t total, issued, handed;
+    uint8_t *buf[2];
+    uint64_t len[2];
+    int cur;
+    static constexpr uint64_t PART = 32ull << 20;
+    int issue(int which) {
+        len[which] = total - issued < PART ? total - issued : PART;
+        const int rc = len[which] ? oge_gpu_dedup_pull_bgzf_part(ctx, issued, len[which], buf[which]) : 0;
+        issued += len[which];
+        return rc;
+    }
+    static int fill(void *user, const uint8_t **data, uint64_t *nbytes) {
+        MemberStream *m = (MemberStream *) user;
+        if (m->handed == 0 && m->issued == 0 && m->issue(0)) return -1;
+        if (oge_gpu_dedup_pull_bgzf_wait(m->ctx)) return -1;      // the current part has landed
+        const int cur = m->cur;
+        *data = m->buf[cur];
+        *nbytes = m->len[cur];
+        m->handed += m->len[cur];
+        m->cur ^= 1;
+        if (m->issue(m->cur)) return -1;      // the next one travels while the caller writes this one
+        return 0;
+    }
+};
+
 static void usage() {
     fprintf(stderr,
             "usage: oge_dedup_fused [dedup] in.bam -o out.bam [-r] [-v] [-t threads] [-c level] [-F bam|rawbam] [--nopg] [--stats]\n"
-            "                       [--device N] [--cpu-inflate] [--gpu-deflate] [--pinned] [--nosplit] [-T tmpdir] [-d]\n"
+            "                       [--device N] [--cpu-inflate] [--gpu-deflate] [--pinned] [--tidy] [--nosplit] [-T tmpdir] [-d]\n"
             "                       [--sort | -M]   coordinate sort on the GPU in front of the dedup (= openge mergesort -M)\n");
     exit(-1);
 }
 
 int main(int argc, char **argv) {
     std::string in, out, format;
-    bool remove_dups = false, verbose = false, nopg = false, stats = false, cpu_inflate = false, pinned = false, sort_first = false, gpu_deflate = false;
+    bool remove_dups = false, verbose = false, nopg = false, stats = false, cpu_inflate = false, pinned = false, sort_first = false, gpu_deflate = false, tidy = false;
     int threads = 0, level = 6, device = 0;
     std::string command_line = "openge ";      // commands/commands.cpp:36-40
     for (int i = 1; i < argc; i++) {
@@ -78,6 +108,7 @@ int main(int argc, char **argv) {
         else if (a == "--sort" || a == "-M") sort_first = true;      // `openge mergesort -M`: coordinate sort in front of the dedup
         else if (a == "--cpu-inflate") cpu_inflate = true;
         else if (a == "--gpu-deflate") gpu_deflate = true;
+        else if (a == "--tidy") tidy = true;      // free every buffer before exit (leak checkers); default: leave it to the exit
         else if (a == "--pinned") pinned = true;
         else if (a == "--device") device = atoi(need());
         else if (!a.empty() && a[0] == '-') usage();
@@ -198,29 +229,35 @@ int main(int argc, char **argv) {
     oge_gpu_flagstats fs;
     memset(&fs, 0, sizeof(fs));
     if (stats && (rc = oge_gpu_dedup_flagstats(ctx, &fs))) die("Statistics (GPU)", oge_gpu_last_error());
-    uint8_t *members = NULL;
     uint64_t members_bytes = 0, member_blocks = 0, n_written = 0;
-    if (gpu_deflate) {      // the output's BGZF members, made where the records are
+    double t_gpu = 0;
+    if (gpu_deflate) {      // the output's BGZF members, made where the records are, streamed into the file
         if ((rc = oge_gpu_dedup_deflate(ctx, &members_bytes, &member_blocks, &n_written))) die("Error writing BAM", oge_gpu_last_error());
-        members = (uint8_t *) (pinned ? oge_gpu_host_alloc(members_bytes + 1) : malloc(members_bytes + 1));
-        if (!members) die("Error writing BAM", "cannot allocate the output buffer.");
-        if ((rc = oge_gpu_dedup_pull_bgzf(ctx, members, members_bytes))) die("Error writing BAM", oge_gpu_last_error());
         oge_gpu_dedup_get_stats(ctx, &st);
+        t_gpu = now_s();
+        MemberStream ms;
+        ms.ctx = ctx;
+        ms.total = members_bytes;
+        ms.issued = ms.handed = 0;
+        ms.cur = 0;
+        ms.len[0] = ms.len[1] = 0;
+        ms.buf[0] = (uint8_t *) oge_gpu_host_alloc(MemberStream::PART);
+        ms.buf[1] = (uint8_t *) oge_gpu_host_alloc(MemberStream::PART);
+        if (!ms.buf[0] || !ms.buf[1]) die("Error writing BAM", "cannot allocate the output staging buffers.");
+        if ((rc = oge_bam_store_members_stream(bam, out.c_str(), level, nopg ? NULL : command_line.c_str(), OGE_VERSION_STRING, MemberStream::fill, &ms)))
+            die("Error writing BAM", oge_bam_last_error());
+        oge_gpu_host_free(ms.buf[0]);
+        oge_gpu_host_free(ms.buf[1]);
     }
-    oge_gpu_dedup_destroy(ctx);
-    const double t_gpu = now_s();
+    if (tidy) oge_gpu_dedup_destroy(ctx);      // else the process exit does it: cudaFree of tens of GB costs 24 ms per GB
+    if (!gpu_deflate) t_gpu = now_s();
     if (verbose) {
         fprintf(stderr, "Sorted %llu pair ends and %llu fragment ends on the GPU in %.3f ms (%llu kernel launches).\n",
                 (unsigned long long) st.n_pair_entries, (unsigned long long) st.n_frag_entries, st.ms_total, (unsigned long long) st.launches);
         fprintf(stderr, "Marking %llu records as duplicates.\n", (unsigned long long) st.n_duplicates);
     }
 
-    if (gpu_deflate) {
-        if ((rc = oge_bam_store_members(bam, out.c_str(), level, nopg ? NULL : command_line.c_str(), OGE_VERSION_STRING, members, members_bytes)))
-            die("Error writing BAM", oge_bam_last_error());
-        if (pinned) oge_gpu_host_free(members);
-        else free(members);
-    } else {
+    if (!gpu_deflate) {
         if ((rc = oge_bam_apply_flags(bam, flags.data(), remove_dups ? 1 : 0, threads))) die("Error rewriting records", oge_bam_last_error());
         if ((rc = oge_bam_store(bam, out.c_str(), format.empty() ? NULL : format.c_str(), level, nopg ? NULL : command_line.c_str(),
                                 OGE_VERSION_STRING, threads)))
@@ -267,6 +304,11 @@ int main(int argc, char **argv) {
                     "Timing: load %.3f s (read %.3f, scan %.3f, inflate %.3f, frame %.3f) | gpu %.3f s (device %.3f ms) | rewrite %.3f s | store %.3f s | total %.3f s\n",
                     t_loaded - t_start, t[0], t[1], t[2], t[3], t_gpu - t_loaded, st.ms_total, t[4], t[5], t_end - t_start);
     }
-    oge_bam_close(bam);
-    return 0;
+    if (tidy) {
+        oge_bam_close(bam);
+        return 0;
+    }
+    fflush(stdout);
+    fflush(stderr);
+    _exit(0);      // the output file is closed; tearing down the CUDA context and unmapping the buffers is the kernel's job now
 }

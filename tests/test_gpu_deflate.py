@@ -1,12 +1,12 @@
 """GPU suite: the output file's BGZF blocks made on the device (oge_gpu_dedup_deflate: bins, -r, one warp per block
 deflate + CRC-32, packing).  The bar is "identical to the reference's output after decompression": every member must pass
-gzip's own checks (valid deflate stream, CRC-32, ISIZE), the inflated file must equal the inflated file of the
+gzip's checks (valid deflate stream by zlib's verdict, CRC-32, ISIZE), the inflated file must equal the inflated file of the
 byte-identical host writer (whose compressed bytes are pinned to the compiled reference's, tests/test_gpu_fused.py), and the
 compiled reference must read the file."""
-import gzip
 import os
 import subprocess
 import tempfile
+import zlib
 
 import numpy as np
 import pytest
@@ -24,6 +24,22 @@ def tmp():
         yield d
 
 
+def inflate_members(z: bytes) -> bytes:
+    """What gzip.decompress does for a multi-member file (which is quadratic in the number of members): every member's
+    deflate stream inflated by zlib, its CRC-32 and ISIZE checked."""
+    out, pos = [], 0
+    while pos < len(z):
+        bs = int.from_bytes(z[pos + 16:pos + 18], "little") + 1
+        d = zlib.decompressobj(-15)
+        raw = d.decompress(z[pos + 18:pos + bs - 8])
+        assert d.eof and d.unused_data == b""
+        assert zlib.crc32(raw) == int.from_bytes(z[pos + bs - 8:pos + bs - 4], "little")
+        assert len(raw) == int.from_bytes(z[pos + bs - 4:pos + bs], "little")
+        out.append(raw)
+        pos += bs
+    return b"".join(out)
+
+
 def members_of(z: bytes):
     """-> [(csize, isize)] of a BGZF file, walking the member headers."""
     out, pos = [], 0
@@ -37,7 +53,7 @@ def members_of(z: bytes):
 
 
 @pytest.mark.parametrize("name,scale,seed,remove", [("C1", 0.02, 3, False), ("C3", 0.01, 99, False), ("C3", 0.01, 99, True),
-                                                    ("C4", 0.01, 6, False), ("C4", 0.01, 6, True), ("C5", 0.002, 11, False)])
+                                                    ("C4", 0.01, 6, False), ("C4", 0.01, 6, True), ("C5", 0.001, 11, False)])
 def test_device_made_file_equals_the_host_made_file_after_decompression(tmp, name, scale, seed, remove):
     bam = synth.make(name, scale, seed=seed)
     inp, out_host, out_dev = (os.path.join(tmp, f) for f in ("in.bam", "host.bam", "dev.bam"))
@@ -46,8 +62,8 @@ def test_device_made_file_equals_the_host_made_file_after_decompression(tmp, nam
     st = bamhost.dedup_file(inp, out_dev, remove_duplicates=remove, level=1, pg_command_line="openge dedup x", gpu_deflate=True)
     assert st["gpu_deflate"] and st["dedup"]["deflate_blocks"] > 0 and st["dedup"]["ms_deflate"] > 0
     z_host, z_dev = open(out_host, "rb").read(), open(out_dev, "rb").read()
-    want = gzip.decompress(z_host)
-    got = gzip.decompress(z_dev)      # checks every member: deflate stream, CRC-32, ISIZE
+    want = inflate_members(z_host)
+    got = inflate_members(z_dev)      # checks every member: valid deflate stream, CRC-32, ISIZE
     assert got == want
     ms = members_of(z_dev)
     assert ms[-1] == (28, 0)                                     # the end-of-file member
@@ -81,7 +97,7 @@ def test_block_edges_and_tiny_files(tmp):
         bamio.write_bam(inp, sub)
         bamhost.dedup_file(inp, out_host, level=6)
         st = bamhost.dedup_file(inp, out_dev, level=6, gpu_deflate=True)
-        assert gzip.decompress(open(out_dev, "rb").read()) == gzip.decompress(open(out_host, "rb").read())
+        assert inflate_members(open(out_dev, "rb").read()) == inflate_members(open(out_host, "rb").read())
         assert st["n_out"] == k
 
 
@@ -104,7 +120,7 @@ def test_incompressible_records_are_stored(tmp):
     bamio.write_bam(inp, noisy)
     bamhost.dedup_file(inp, out_host, level=1)
     bamhost.dedup_file(inp, out_dev, level=1, gpu_deflate=True)
-    assert gzip.decompress(open(out_dev, "rb").read()) == gzip.decompress(open(out_host, "rb").read())
+    assert inflate_members(open(out_dev, "rb").read()) == inflate_members(open(out_host, "rb").read())
     assert all(c <= 65536 for c, _ in members_of(open(out_dev, "rb").read()))
 
 
@@ -143,7 +159,7 @@ def test_fused_binary_with_gpu_deflate(tmp):
         r = subprocess.run([exe, "dedup", inp, "-o", out, "-v", "-c", "1"] + extra, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
         assert r.returncode == 0, r.stderr.decode()
         assert (b"gpu deflate:" in r.stderr) == ("--gpu-deflate" in extra)
-        outs.append(gzip.decompress(open(out, "rb").read()))
+        outs.append(inflate_members(open(out, "rb").read()))
     # same command line apart from the flag: the @PG line differs by it, so compare from the first record on
     def records(raw):
         l_text = int.from_bytes(raw[4:8], "little")

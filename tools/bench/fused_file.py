@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--level", type=int, default=6)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--modes", default="", help="comma-separated subset of the fused modes (default: all)")
     a = ap.parse_args()
     fused = _build.ensure_fused()
     ref = _build.REF_BIN if os.path.exists(_build.REF_BIN) else None
@@ -53,17 +54,26 @@ def main():
         base = [fused, "dedup", inp, "-o", o1, "-v", "--nopg", "-c", str(a.level)] + (["-t", str(a.threads)] if a.threads else [])
         run(base, 1800)      # warm-up: CUDA context, page cache
         digests = set()
-        for mode, extra in (("gpu_inflate", []), ("gpu_inflate_pinned", ["--pinned"]), ("cpu_inflate", ["--cpu-inflate"]),
-                            ("cpu_inflate_pinned", ["--cpu-inflate", "--pinned"]), ("gpu_inflate_rawbam_out", ["-F", "rawbam"])):
+        modes = [("gpu_inflate", []), ("gpu_inflate_pinned", ["--pinned"]), ("cpu_inflate", ["--cpu-inflate"]),
+                 ("cpu_inflate_pinned", ["--cpu-inflate", "--pinned"]), ("gpu_inflate_rawbam_out", ["-F", "rawbam"]),
+                 ("gpu_deflate", ["--gpu-deflate"]), ("gpu_deflate_pinned", ["--gpu-deflate", "--pinned"])]
+        if a.modes:
+            modes = [m for m in modes if m[0] in a.modes.split(",")]
+        for mode, extra in modes:
             secs, r = run(base + extra, 1800)
             assert r.returncode == 0, r.stderr.decode()[-2000:]
-            timing = [l for l in r.stderr.decode().splitlines() if l.startswith("Timing:")]
+            timing = [l for l in r.stderr.decode().splitlines() if l.startswith("Timing:") or l.startswith("gpu deflate:")]
             out["fused" if mode == "gpu_inflate" else "fused_" + mode] = {
-                "reads": n, "raw_bytes": raw_bytes, "file_bytes": os.path.getsize(inp), "seconds": secs,
-                "reads_per_s": n / secs, "phases": timing[-1] if timing else None}
-            if "rawbam" not in mode:
+                "reads": n, "raw_bytes": raw_bytes, "file_bytes": os.path.getsize(inp), "out_file_bytes": os.path.getsize(o1), "seconds": secs,
+                "reads_per_s": n / secs, "phases": timing if timing else None}
+            if "rawbam" not in mode and "deflate" not in mode:
                 digests.add(hashlib.sha256(open(o1, "rb").read()).hexdigest())
-        out["all_modes_same_output"] = len(digests) == 1
+            if "deflate" in mode:      # identical after decompression, not byte for byte
+                out["fused_" + mode]["inflated_sha256"] = hashlib.sha256(bamhost.bgzf_decompress(open(o1, "rb").read())).hexdigest()
+        out["all_modes_same_output"] = len(digests) <= 1
+        if "fused" in out and any("deflate" in m for m, _ in modes):
+            run(base, 1800)
+            out["byte_identical_path_inflated_sha256"] = hashlib.sha256(bamhost.bgzf_decompress(open(o1, "rb").read())).hexdigest()
         if ref:
             inp2 = os.path.join(d, "in2.bam")
             n2, _ = write_input(inp2, a.config, a.ref_scale, a.seed)
@@ -74,7 +84,10 @@ def main():
             assert r3.returncode == 0
             same = hashlib.sha256(open(o2, "rb").read()).digest() == hashlib.sha256(open(o3, "rb").read()).digest()
             out["reference"] = {"reads": n2, "seconds": secs2, "reads_per_s": n2 / secs2, "output_files_identical": same}
-            out["speedup_file_to_file"] = out["fused"]["reads_per_s"] / out["reference"]["reads_per_s"]
+            if "fused" in out:
+                out["speedup_file_to_file"] = out["fused"]["reads_per_s"] / out["reference"]["reads_per_s"]
+            if "fused_gpu_deflate" in out:
+                out["speedup_file_to_file_gpu_deflate"] = out["fused_gpu_deflate"]["reads_per_s"] / out["reference"]["reads_per_s"]
     print(json.dumps(out))
 
 
