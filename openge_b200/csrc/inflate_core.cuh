@@ -120,19 +120,25 @@ OGE_HD uint32_t bit_reverse(uint32_t v, int n) {
 // Canonical Huffman tables from code lengths (RFC 1951 3.2.2).  cnt[l] = codes of length l, sym[] = symbols in
 // canonical order; tab[] = primary lookup on the next `bits` stream bits: symbol | length << 9, or 0 for "longer
 // than `bits`, or no such code".  Lane 0 counts and orders, all lanes fill the lookup table.
-// Returns (in every lane) 0, or INF_ERR_LENGTHS for an over-subscribed set.
+// Returns (in every lane) 0, or INF_ERR_LENGTHS for a set zlib's inflate_table rejects: over-subscribed, or incomplete --
+// except that a literal/length or distance code (not the code-length code: is_cl) may consist of ONE code of length 1, and
+// that a set without any code passes here and fails when a symbol is asked of it (inftrees.c: "no symbols, but wait for
+// decoding to report error").  The reference inflates with zlib (util/bgzf_input_stream.cpp:110-128), so this is its verdict.
 template <int LANES>
-OGE_HD_NOINLINE int build_tables(const uint8_t *lens, int n, int bits, uint16_t *tab, uint16_t *sym, uint16_t *cnt, int32_t *status, int lane) {
+OGE_HD_NOINLINE int build_tables(const uint8_t *lens, int n, int bits, uint16_t *tab, uint16_t *sym, uint16_t *cnt, int32_t *status, int lane,
+                                 bool is_cl = false) {
     sync_lanes<LANES>();
     if (lane == 0) {
         for (int l = 0; l < 16; l++) cnt[l] = 0;
         for (int i = 0; i < n; i++) cnt[lens[i]]++;
-        int left = 1, bad = 0;
+        int left = 1, bad = 0, max_len = 0;
         for (int l = 1; l < 16; l++) {
             left <<= 1;
             left -= cnt[l];
             if (left < 0) bad = 1;
+            if (cnt[l]) max_len = l;
         }
+        if (left > 0 && max_len > 0 && (is_cl || max_len != 1)) bad = 1;      // incomplete
         uint16_t offs[16];
         offs[1] = 0;
         for (int l = 1; l < 15; l++) offs[l + 1] = (uint16_t) (offs[l] + cnt[l]);
@@ -233,9 +239,9 @@ OGE_HD int block_header(BitReader &r, const uint8_t *in, uint32_t in_len, uint8_
     int n_lit, n_dist;
     if (type == 1) {      // fixed code (RFC 1951 3.2.6)
         for (int i = lane; i < 288; i += LANES) TR.lens[i] = i < 144 ? 8 : (i < 256 ? 9 : (i < 280 ? 7 : 8));
-        for (int i = lane; i < 30; i += LANES) TR.lens[288 + i] = 5;
+        for (int i = lane; i < 32; i += LANES) TR.lens[288 + i] = 5;      // 32 codes of 5 bits: a complete code; 30 and 31 are invalid when met
         n_lit = 288;
-        n_dist = 30;
+        n_dist = 32;
     } else {              // dynamic code (3.2.7)
         br_refill(r);
         n_lit = (int) br_take(r, 5) + 257;
@@ -251,7 +257,7 @@ OGE_HD int block_header(BitReader &r, const uint8_t *in, uint32_t in_len, uint8_
             const uint32_t v = br_take(r, 3);
             if (lane == 0) cl[cl_order(i)] = (uint8_t) v;
         }
-        int rc = build_tables<LANES>(cl, 19, CL_BITS, TR.cl_tab, TR.cl_sym, TR.cl_cnt, TR.status, lane);
+        int rc = build_tables<LANES>(cl, 19, CL_BITS, TR.cl_tab, TR.cl_sym, TR.cl_cnt, TR.status, lane, true);
         if (rc) return rc;
         int i = 0;
         uint32_t prev = 0;

@@ -158,3 +158,79 @@ def test_decoder_fuzz_against_zlib(lib):
             n_cases += 1
     SMALL[0] = 0
     assert n_cases == 1200
+
+
+class _Bits:
+    def __init__(self):
+        self.v, self.n = 0, 0
+
+    def put(self, value, nbits):            # LSB first (header fields, extra bits)
+        self.v |= value << self.n
+        self.n += nbits
+
+    def code(self, code, nbits):            # a Huffman code: most significant bit first
+        for k in range(nbits - 1, -1, -1):
+            self.put((code >> k) & 1, 1)
+
+    def bytes(self):
+        return self.v.to_bytes((self.n + 7) // 8, "little")
+
+
+def _canonical(lens):
+    """{symbol: length} -> {symbol: (code, length)} (RFC 1951 3.2.2)."""
+    out, code = {}, 0
+    for l in range(1, 16):
+        for s in sorted(k for k, v in lens.items() if v == l):
+            out[s] = (code, l)
+            code += 1
+        code <<= 1
+    return out
+
+
+def _dynamic_block(lit, dist, symbols, cl=None):
+    """One final dynamic-Huffman block whose code lengths are given verbatim (no repeat codes), the code-length code being
+    `cl` (default: a complete code over the length values 0, 1, 2)."""
+    cl = cl or {0: 1, 1: 2, 2: 2}
+    cl_codes = _canonical(cl)
+    n_lit, n_dist = 257, max(dist, default=0) + 1
+    b = _Bits()
+    b.put(1, 1); b.put(2, 2); b.put(n_lit - 257, 5); b.put(n_dist - 1, 5); b.put(19 - 4, 4)
+    for s in (16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15):
+        b.put(cl.get(s, 0), 3)
+    for s in range(n_lit):
+        b.code(*cl_codes[lit.get(s, 0)])
+    for s in range(n_dist):
+        b.code(*cl_codes[dist.get(s, 0)])
+    lit_codes = _canonical(lit)
+    for s in symbols:
+        b.code(*lit_codes[s])
+    b.put(0, 16)      # padding the decoders may look at
+    return b.bytes()
+
+
+@pytest.mark.parametrize("small", [0, 1, 2])
+def test_incomplete_code_sets_get_zlibs_verdict(lib, small):
+    # zlib (and with it the reference, util/bgzf_input_stream.cpp:110-128) rejects over-subscribed AND incomplete sets of code
+    # lengths, except a literal/length or distance code made of one code of length 1
+    SMALL[0] = small
+    cases = [
+        ("complete literal code, single distance code of length 1", _dynamic_block({65: 1, 256: 1}, {0: 1}, [65, 65, 256]), b"AA"),
+        ("incomplete literal code (two codes of length 2)", _dynamic_block({65: 2, 256: 2}, {0: 1}, [65, 256]), None),
+        ("one literal code of length 1: the end-of-block symbol alone", _dynamic_block({256: 1}, {}, [256]), b""),
+        ("incomplete distance code (two codes of length 2)", _dynamic_block({65: 1, 256: 1}, {0: 2, 1: 2}, [65, 256]), None),
+        ("incomplete code-length code", _dynamic_block({65: 1, 256: 1}, {0: 1}, [65, 256], cl={0: 2, 1: 2, 2: 2}), None),
+        ("over-subscribed literal code", _dynamic_block({65: 1, 66: 1, 256: 1}, {0: 1}, [65, 256]), None),
+    ]
+    for what, z, want in cases:
+        d = zlib.decompressobj(-15)
+        try:
+            theirs = d.decompress(z)
+            ok = d.eof
+        except zlib.error:
+            theirs, ok = None, False
+        assert (theirs if ok else None) == want, what      # the test's own expectation equals zlib's verdict
+        rc, out = inflate(lib, z, len(want) if want is not None else 2)
+        assert (rc == 0) == (want is not None), (what, rc)
+        if want is not None:
+            assert out == want, what
+    SMALL[0] = 0
