@@ -20,6 +20,7 @@ SYNTH_LIB = os.path.join(ROOT, "tools", "synth", "libogesynth.so")
 ORACLE_LIB = os.path.join(ROOT, "oracle", "liboge_oracle.so")
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "oge_ref_dedup")
 HOST_BIN = os.path.join(ROOT, "openge_b200", "host", "_build", "oge_dedup_gpu")
+HOST_SORT_BIN = os.path.join(ROOT, "openge_b200", "host", "_build", "oge_mergesort_gpu")
 BAMHOST_LIB = os.path.join(ROOT, "openge_b200", "liboge_bamhost.so")
 FUSED_BIN = os.path.join(ROOT, "openge_b200", "host", "_build", "oge_dedup_fused")
 
@@ -151,9 +152,10 @@ def ensure_host(force=False):
     Needs the reference sources; elsewhere the prebuilt binary (it travels with the snapshot) is used."""
     if os.path.isdir("/root/reference/openge/src"):
         d = os.path.join(ROOT, "openge_b200", "host")
-        deps = [os.path.join(d, "mark_duplicates_gpu.cpp"), os.path.join(d, "Makefile"), GPU_LIB,
+        deps = [os.path.join(d, "mark_duplicates_gpu.cpp"), os.path.join(d, "read_sorter_gpu.cpp"), os.path.join(d, "record_batch.h"),
+                os.path.join(d, "Makefile"), GPU_LIB,
                 os.path.join(ROOT, "oracle", "ref_build", "ref_driver.cpp"), os.path.join(ROOT, "include", "oge_gpu_dedup.h")]
-        if force or _stale(HOST_BIN, deps):
+        if force or _stale(HOST_BIN, deps) or _stale(HOST_SORT_BIN, deps):
             _run(["make", "-C", d] + (["-B"] if force else []))
     return HOST_BIN if os.path.exists(HOST_BIN) else None
 

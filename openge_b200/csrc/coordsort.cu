@@ -319,6 +319,7 @@ extern "C" int oge_gpu_dedup_sort(oge_gpu_dedup_ctx *c) {
     cudaStream_t s = c->stream;
     const uint64_t n = c->n;
     c->ran = false;
+    c->sorted = true;
     c->sort_stats[0] = c->sort_stats[1] = c->sort_stats[2] = 0;
     if (n == 0) return OGE_OK;
     if (n >= (1ull << 30)) return fail_msg(OGE_ERR_TOO_LARGE, "sort: more than 2^30-1 records");

@@ -120,6 +120,8 @@ struct oge_gpu_dedup_ctx {
     DevBuf<uint8_t> zcomp;
     DevBuf<uint64_t> zoff;
     DevBuf<uint32_t> zcs;
+    DevBuf<uint64_t> frame_w;      // oge_gpu_dedup_frame: per-chunk entry / exit / count / base
+    DevBuf<uint32_t> frame_wb;
     // oge_gpu_dedup_deflate: the finished BGZF members of the output
     DevBuf<uint8_t> zfile;
     uint64_t zfile_bytes = 0;
@@ -156,6 +158,7 @@ struct oge_gpu_dedup_ctx {
 
     KeyLayout kl;
     bool ran = false;
+    bool sorted = false;      // oge_gpu_dedup_sort has run on the resident records (pull may follow without a run)
     oge::ShardState sh;
     oge_gpu_dedup_stats stats;
 };

@@ -258,7 +258,7 @@ void oge_gpu_dedup_destroy(oge_gpu_dedup_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->side_stream) cudaStreamSynchronize(c->side_stream);
-    c->zcomp.release(); c->zoff.release(); c->zcs.release(); c->zfile.release();
+    c->zcomp.release(); c->zoff.release(); c->zcs.release(); c->zfile.release(); c->frame_w.release(); c->frame_wb.release();
     c->rec.release(); c->off.release(); c->rg_bytes.release(); c->rg_off.release(); c->rg_lib.release();
     c->frag.release(); c->sortbuf.release(); c->pair.release(); c->pair2.release(); c->pairf.release(); c->pairf2.release(); c->ufrag.release(); c->ufrag2.release(); c->uset.release(); c->hk.release();
     c->tag.release(); c->flag_in.release(); c->flag_out.release(); c->dup.release(); c->scratch.release();
@@ -499,6 +499,7 @@ int oge_gpu_dedup_push_bgzf(oge_gpu_dedup_ctx *c, const uint8_t *comp, uint64_t 
     c->rec_bytes = rec_bytes;
     c->n = 0;
     c->ran = false;
+    c->sorted = false;
     return done(OGE_OK);
 }
 
@@ -522,14 +523,11 @@ int oge_gpu_dedup_frame(oge_gpu_dedup_ctx *c, uint64_t *nrec_out) {
     P.n_chunks = (P.total + P.chunk - 1) / P.chunk;
     P.n_ref = c->cfg.n_ref;
     const uint64_t nc = P.n_chunks;
-    DevBuf<uint64_t> w;      // entry, exit, count, base
-    DevBuf<uint32_t> wb;
+    // entry, exit, count, base per chunk: kept by the context (a cudaFree in this path was seen to take 100 ms on a busy box)
+    DevBuf<uint64_t> &w = c->frame_w;
+    DevBuf<uint32_t> &wb = c->frame_wb;
     int rc;
-    auto done = [&](int code) {
-        w.release();
-        wb.release();
-        return code;
-    };
+    auto done = [&](int code) { return code; };
     if ((rc = w.reserve(4 * nc, false, s)) || (rc = wb.reserve(nc, false, s))) return done(rc);
     P.entry = w.p;
     P.exit_ = w.p + nc;
@@ -590,6 +588,7 @@ int oge_gpu_dedup_frame(oge_gpu_dedup_ctx *c, uint64_t *nrec_out) {
     c->stats.frame_repairs = repairs;
     c->n = n;
     c->ran = false;
+    c->sorted = false;
     *nrec_out = n;
     return done(OGE_OK);
 }
@@ -615,6 +614,7 @@ int oge_gpu_dedup_set_offsets(oge_gpu_dedup_ctx *c, const uint64_t *offsets, uin
     OGE_CUDA_TRY(cudaMemcpyAsync(c->off.p, offsets, (nrec + 1) * 8, cudaMemcpyHostToDevice, c->copy_stream));
     c->n = nrec;
     c->ran = false;
+    c->sorted = false;
     return OGE_OK;
 }
 
@@ -640,6 +640,7 @@ int oge_gpu_dedup_push(oge_gpu_dedup_ctx *c, const uint8_t *records, uint64_t nb
     c->rec_bytes += nbytes;
     c->n += nrec;
     c->ran = false;
+    c->sorted = false;
     return OGE_OK;
 }
 
@@ -659,6 +660,7 @@ int oge_gpu_dedup_reset(oge_gpu_dedup_ctx *c) {
     c->rec_bytes = 0;
     c->rec_lead = 0;
     c->ran = false;
+    c->sorted = false;
     return OGE_OK;
 }
 
@@ -1001,7 +1003,8 @@ int oge_gpu_dedup_flags(oge_gpu_dedup_ctx *c, uint16_t *out, uint64_t n) {
 int oge_gpu_dedup_pull(oge_gpu_dedup_ctx *c, uint8_t *out_records, uint64_t cap_bytes, uint64_t *out_offsets, uint64_t cap_records,
                        uint64_t *out_bytes, uint64_t *out_nrec) {
     if (!c || !out_bytes || !out_nrec) return fail_msg(OGE_ERR_INVALID_ARG, "pull: null argument");
-    if (!c->ran) return fail_msg(OGE_ERR_STATE, "pull: call oge_gpu_dedup_run first");
+    // after a run: the flag-patched records; after a sort alone (the ReadSorter drop-in): the records in their new order
+    if (!c->ran && !(c->sorted && !c->cfg.remove_duplicates)) return fail_msg(OGE_ERR_STATE, "pull: call oge_gpu_dedup_run first");
     OGE_CUDA_TRY(cudaSetDevice(c->cfg.device));
     cudaStream_t s = c->stream;
     *out_bytes = 0;

@@ -21,6 +21,7 @@
 #include "algorithms/mark_duplicates.h"
 
 #include "oge_gpu_dedup.h"
+#include "record_batch.h"
 
 #include <stdint.h>
 #include <stdlib.h>
@@ -32,28 +33,15 @@
 #include <vector>
 
 using namespace std;
+using namespace oge_host;
 
 namespace {
-
-const size_t BATCH_BYTES = (size_t) 128 << 20;      // one pinned staging buffer
-
-struct Batch {
-    uint8_t * data;             // pinned (oge_gpu_host_alloc)
-    size_t used;
-    vector<uint64_t> offsets;   // n + 1, relative to data
-    Batch() : data(NULL), used(0) { offsets.push_back(0); }
-};
 
 void gpu_fail(const char * what, int rc) {
     // the reference's convention for fatal errors: message on cerr, exit(-1) (e.g. util/bam_deserializer.h:155-163)
     cerr << "MarkDuplicates (GPU): " << what << " failed (" << rc << "): " << oge_gpu_last_error() << endl;
     exit(-1);
 }
-
-inline void put_u32(uint8_t * p, uint32_t v) { memcpy(p, &v, 4); }
-inline uint32_t get_u32(const uint8_t * p) { uint32_t v; memcpy(&v, p, 4); return v; }
-inline int32_t get_i32(const uint8_t * p) { int32_t v; memcpy(&v, p, 4); return v; }
-inline uint16_t get_u16(const uint8_t * p) { uint16_t v; memcpy(&v, p, 2); return v; }
 
 int env_int(const char * name, int dflt) {
     const char * v = getenv(name);
@@ -119,8 +107,7 @@ int MarkDuplicates::runInternal() {
     while (true) {
         OGERead * al = getInputAlignment();
         if (!al) break;
-        const string & chars = al->getSupportData().getAllCharData();
-        const size_t rec_len = 4 + 32 + chars.size();
+        const size_t rec_len = record_bytes(*al);
         if (rec_len > BATCH_BYTES) { cerr << "MarkDuplicates (GPU): record of " << rec_len << " bytes. Aborting." << endl; exit(-1); }
         if (!cur || cur->used + rec_len > BATCH_BYTES) {
             if (cur) {
@@ -132,19 +119,7 @@ int MarkDuplicates::runInternal() {
             if (!cur->data) { cerr << "MarkDuplicates (GPU): cannot allocate a pinned staging buffer. Aborting." << endl; exit(-1); }
             batches.push_back(cur);
         }
-        uint8_t * p = cur->data + cur->used;
-        put_u32(p, (uint32_t) (32 + chars.size()));
-        put_u32(p + 4, (uint32_t) al->getRefID());
-        put_u32(p + 8, (uint32_t) al->getPosition());
-        put_u32(p + 12, ((uint32_t) al->getBin() << 16) | ((uint32_t) (al->getMapQuality() & 0xFF) << 8) | (uint32_t) (al->getNameLength() & 0xFF));
-        put_u32(p + 16, ((uint32_t) al->getAlignmentFlag() << 16) | (uint32_t) (al->getNumCigarOps() & 0xFFFF));
-        put_u32(p + 20, (uint32_t) al->getLength());
-        put_u32(p + 24, (uint32_t) al->getMateRefID());
-        put_u32(p + 28, (uint32_t) al->getMatePosition());
-        put_u32(p + 32, (uint32_t) al->getInsertSize());
-        memcpy(p + 36, chars.data(), chars.size());
-        cur->used += rec_len;
-        cur->offsets.push_back(cur->used);
+        append_read(*cur, *al);
         OGERead::deallocate(al);
         n_records++;
         if (verbose && n_records % 100000 == 0) cerr << "\rRead " << n_records << " records." << std::flush;
@@ -178,18 +153,7 @@ int MarkDuplicates::runInternal() {
         for (size_t k = 0; k + 1 < bt->offsets.size(); k++, i++) {
             const uint16_t flag = flags[i];
             if (removeDuplicates && (flag & 0x400)) continue;
-            const uint8_t * p = bt->data + bt->offsets[k];
-            const uint32_t block = get_u32(p);
-            OGERead * al = OGERead::allocate();
-            al->setRefID(get_i32(p + 4));
-            al->setPosition(get_i32(p + 8));
-            al->setMapQuality(p[13]);
-            al->setBin(get_u16(p + 14));
-            al->setAlignmentFlag(flag);
-            al->setMateRefID(get_i32(p + 24));
-            al->setMatePosition(get_i32(p + 28));
-            al->setInsertSize(get_i32(p + 32));
-            al->setBamStringData((const char *) p + 36, block - 32, get_u16(p + 16), get_u32(p + 20), p[12]);
+            OGERead * al = rebuild_read(bt->data + bt->offsets[k], flag);
             putOutputAlignment(al);
             if (verbose && read_count && ++written % 100000 == 0)
                 cerr << "\rWritten " << written << " records (" << written * 100 / read_count << "%)." << std::flush;

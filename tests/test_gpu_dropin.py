@@ -103,3 +103,63 @@ def test_dropin_class_behind_the_reference_sorter_is_mergesort_M(gpu_exe):
         tied = gold[key + "_tied"]
         assert got.n == bam.n
         assert np.array_equal(got.flags()[~tied], gold[key + "_dedup_flags"][~tied])
+
+
+@pytest.fixture(scope="module")
+def gpu_sort_exe():
+    _build.ensure_host()
+    if not os.path.exists(_build.HOST_SORT_BIN):
+        pytest.skip("openge_b200/host/_build/oge_mergesort_gpu was not built (needs the reference sources at build time)")
+    return _build.HOST_SORT_BIN
+
+
+def test_dropin_read_sorter_is_mergesort(gpu_sort_exe):
+    """`openge mergesort [-M]` (commands/command_mergesort.cpp:68-100) with BOTH stages replaced: this repo's ReadSorter
+    (read_sorter_gpu.cpp -> oge_gpu_dedup_sort) and MarkDuplicates inside the reference's own pipeline.  The sorter's output
+    must be the oracle's restatement of ReadSorter + Sort::ByPosition record for record (which is pinned to the compiled
+    reference's sorter wherever the reference defines the order), the chain's flags the compiled reference's."""
+    import fixtures
+    import oracle
+    from conftest import GOLDEN
+    gold = dict(np.load(os.path.join(GOLDEN, "sort_order.npz")))
+    for name, scale, seed in (("C4", 0.003, 6), ("C3", 0.01, 5)):
+        bam = fixtures.shuffled(synth.make(name, scale, seed=seed), seed)
+        key = "%s_%g_%d" % (name, scale, seed)
+        want_perm, _ = oracle.coordinate_order(bam.records, bam.offsets)
+        base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+        with tempfile.TemporaryDirectory(dir=base) as d:
+            inp = os.path.join(d, "in.rawbam")
+            bamio.write_bam(inp, bam, raw=True)
+            outs = {}
+            for mode, extra in (("sort", ["--nodedup"]), ("chain", [])):
+                out = os.path.join(d, mode + ".rawbam")
+                cmd = [gpu_sort_exe, "-T", d, "--sort", "-v", "-F", "rawbam"] + extra + [inp, out]
+                got = None
+                for _ in range(4):
+                    try:
+                        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+                    except subprocess.TimeoutExpired:
+                        continue
+                    assert r.returncode == 0, r.stderr.decode()[-2000:]
+                    assert "by coordinate on the GPU" in r.stderr.decode()
+                    got = bamio.read_bam(out)
+                    break
+                if got is None:
+                    pytest.skip("pipeline did not terminate")
+                outs[mode] = got
+        # the sorter alone: the records in the oracle's order, byte for byte (the writer recomputes the bin: bytes 14-15)
+        s = outs["sort"]
+        assert s.n == bam.n and "SO:coordinate" in s.text
+        sizes = np.diff(bam.offsets.astype(np.int64))
+        assert np.array_equal(np.diff(s.offsets.astype(np.int64)), sizes[want_perm])
+        starts = bam.offsets[:-1].astype(np.int64)[want_perm]
+        idx = np.concatenate([np.arange(a, a + l) for a, l in zip(starts, sizes[want_perm])])
+        keep = np.ones(len(s.records), dtype=bool)
+        pos = s.offsets[:-1].astype(np.int64)
+        for o in (14, 15):
+            keep[pos + o] = False
+        assert np.array_equal(s.records[keep], bam.records[idx][keep])
+        # the chain: the compiled reference's flags wherever its order is defined
+        tied = gold[key + "_tied"]
+        assert outs["chain"].n == bam.n
+        assert np.array_equal(outs["chain"].flags()[~tied], gold[key + "_dedup_flags"][~tied])
