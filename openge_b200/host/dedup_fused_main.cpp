@@ -20,9 +20,11 @@
 // Errors: message on stderr, exit(-1), as everywhere in the reference.
 #include <stdio.h>
 #include <stdlib.h>
+#include <pthread.h>
 #include <string.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <chrono>
 #include <string>
 #include <thread>
@@ -71,18 +73,95 @@ struct MemberStream {
     }
 };
 
+// ---- `--gpus N`: the records range-sharded over N GPUs of this node, one host thread and one context per GPU, the four
+// exchanges done by NCCL inside the library (oge_gpu_shard_step).  The flags are those of the
+// single-stream run, whatever N (tests/test_gpu_fused.py compares the output files).
+struct ShardJob {
+    int rank, world, device;
+    oge_bam_file *bam;
+    const uint64_t *bases;              // world + 1 record ordinals
+    const int32_t *split_ref, *split_pos;
+    const uint8_t *comm_id;
+    uint16_t *flags;                    // the whole file's flag words; this rank fills [bases[rank], bases[rank + 1])
+    uint32_t *key_bytes;                // [world]: every rank's longest pairing key
+    pthread_barrier_t *barrier;
+    std::atomic<int> *failed;           // set by any rank that cannot go on: nobody enters NCCL then
+    oge_gpu_dedup_stats stats;
+    oge_gpu_shard_step_info info;
+    std::string error;
+};
+
+static void shard_worker(ShardJob *j) {
+    auto fail = [&](const char *what) {
+        j->error = std::string(what) + ": " + oge_gpu_last_error();
+        j->failed->store(1);
+    };
+    oge_bam_file *bam = j->bam;
+    const uint64_t lo = j->bases[j->rank], hi = j->bases[j->rank + 1], n = hi - lo;
+    const uint64_t *off = oge_bam_offsets(bam);
+    const uint8_t *rec = oge_bam_records(bam);
+    oge_gpu_dedup_config cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.abi_version = OGE_GPU_DEDUP_ABI_VERSION;
+    cfg.device = j->device;
+    cfg.n_ref = oge_bam_n_ref(bam);
+    for (int32_t i = 0; i < cfg.n_ref; i++)
+        if (oge_bam_ref_len(bam, i) > cfg.max_ref_len) cfg.max_ref_len = oge_bam_ref_len(bam, i);
+    cfg.verify_names = -1;
+    cfg.rank = j->rank;
+    cfg.world = j->world;
+    cfg.index_base = lo;
+    cfg.capacity_records = n;
+    cfg.capacity_bytes = off[hi] - off[lo];
+    oge_gpu_dedup_ctx *ctx = NULL;
+    bool ok = oge_gpu_dedup_create(&cfg, &ctx) == 0;
+    if (!ok) fail("oge_gpu_dedup_create");
+    if (ok) {
+        const char *const *ids;
+        const int16_t *libs;
+        int32_t n_rg, n_libs;
+        int16_t unknown;
+        oge_bam_library_table(bam, &ids, &libs, &n_rg, &unknown, &n_libs);
+        if (oge_gpu_dedup_set_readgroups(ctx, ids, libs, n_rg, unknown, n_libs)) { fail("set_readgroups"); ok = false; }
+    }
+    if (ok && oge_gpu_shard_setup(ctx, j->bases[j->world], j->bases, j->split_ref, j->split_pos)) { fail("oge_gpu_shard_setup"); ok = false; }
+    std::vector<uint64_t> local_off;
+    if (ok && n) {      // the shard's offsets, relative to its first record
+        local_off.resize(n + 1);
+        for (uint64_t i = 0; i <= n; i++) local_off[i] = off[lo + i] - off[lo];
+        if (oge_gpu_dedup_push(ctx, rec + off[lo], off[hi] - off[lo], local_off.data(), n) || oge_gpu_dedup_sync(ctx)) { fail("oge_gpu_dedup_push"); ok = false; }
+    }
+    uint32_t kb = 0;
+    if (ok && oge_gpu_shard_key_bytes(ctx, &kb)) { fail("oge_gpu_shard_key_bytes"); ok = false; }
+    j->key_bytes[j->rank] = kb;
+    // every rank reaches the barriers, failed or not: nobody is left waiting
+    pthread_barrier_wait(j->barrier);
+    uint32_t k = 0;
+    for (int r = 0; r < j->world; r++) k = j->key_bytes[r] > k ? j->key_bytes[r] : k;
+    const uint32_t entry_bytes = 32 + (k + 31) / 32 * 32 < 64 ? 64 : 32 + (k + 31) / 32 * 32;
+    if (ok && oge_gpu_shard_set_entry_bytes(ctx, entry_bytes)) { fail("oge_gpu_shard_set_entry_bytes"); ok = false; }
+    pthread_barrier_wait(j->barrier);
+    if (j->failed->load()) ok = false;      // a rank that failed before this point would leave the others hanging in NCCL
+    if (ok && oge_gpu_shard_comm_init(ctx, j->comm_id)) { fail("oge_gpu_shard_comm_init"); ok = false; }
+    if (ok && oge_gpu_shard_step(ctx, &j->info)) { fail("oge_gpu_shard_step"); ok = false; }
+    if (ok && n && oge_gpu_dedup_flags(ctx, j->flags + lo, n)) { fail("oge_gpu_dedup_flags"); ok = false; }
+    if (ok) oge_gpu_dedup_get_stats(ctx, &j->stats);
+    if (ctx) oge_gpu_dedup_destroy(ctx);
+}
+
 static void usage() {
     fprintf(stderr,
             "usage: oge_dedup_fused [dedup] in.bam -o out.bam [-r] [-v] [-t threads] [-c level] [-F bam|rawbam] [--nopg] [--stats]\n"
             "                       [--device N] [--cpu-inflate] [--gpu-deflate] [--pinned] [--tidy] [--nosplit] [-T tmpdir] [-d]\n"
-            "                       [--sort | -M]   coordinate sort on the GPU in front of the dedup (= openge mergesort -M)\n");
+            "                       [--sort | -M]   coordinate sort on the GPU in front of the dedup (= openge mergesort -M)\n"
+            "                       [--gpus N]      range-shard the records over N GPUs of this node (devices --device .. --device + N - 1)\n");
     exit(-1);
 }
 
 int main(int argc, char **argv) {
     std::string in, out, format;
     bool remove_dups = false, verbose = false, nopg = false, stats = false, cpu_inflate = false, pinned = false, sort_first = false, gpu_deflate = false, tidy = false;
-    int threads = 0, level = 6, device = 0;
+    int threads = 0, level = 6, device = 0, gpus = 1;
     std::string command_line = "openge ";      // commands/commands.cpp:36-40
     for (int i = 1; i < argc; i++) {
         command_line += argv[i];
@@ -111,6 +190,7 @@ int main(int argc, char **argv) {
         else if (a == "--tidy") tidy = true;      // free every buffer before exit (leak checkers); default: leave it to the exit
         else if (a == "--pinned") pinned = true;
         else if (a == "--device") device = atoi(need());
+        else if (a == "--gpus") gpus = atoi(need());
         else if (!a.empty() && a[0] == '-') usage();
         else if (in.empty()) in = a;
         else if (out.empty()) out = a;
@@ -118,6 +198,14 @@ int main(int argc, char **argv) {
     }
     if (in.empty() || out.empty()) usage();
     if (format == "rawbam") gpu_deflate = false;      // nothing to compress
+    if (gpus < 1) usage();
+    if (gpus > 1) {
+        if (sort_first) die("oge_dedup_fused", "--sort and --gpus do not go together (the device sort works on one GPU).");
+        if (stats) die("oge_dedup_fused", "--stats and --gpus do not go together (the counters are reduced on one GPU).");
+        if (oge_gpu_device_count() < device + gpus) die("MarkDuplicates (GPU)", "fewer CUDA devices than --gpus asks for.");
+        cpu_inflate = true;      // the shards are cut from the framed records on the host
+        gpu_deflate = false;     // the output is written by the host writer (byte-identical)
+    }
 
     const double t_start = now_s();
     oge_bam_file *bam = NULL;
@@ -134,6 +222,76 @@ int main(int argc, char **argv) {
     }
     if (!gpu_inflate && (rc = oge_bam_load(in.c_str(), threads, alloc_fn, free_fn, &bam))) die("Error reading BAM", oge_bam_last_error());
     const double t_loaded = now_s();
+
+    if (gpus > 1) {
+        const uint64_t n = oge_bam_n_records(bam);
+        if (verbose) fprintf(stderr, "Read %llu records.\n", (unsigned long long) n);
+        std::vector<uint64_t> bases(gpus + 1);
+        std::vector<int32_t> split_ref(gpus - 1), split_pos(gpus - 1);
+        const uint64_t *off = oge_bam_offsets(bam);
+        const uint8_t *rec = oge_bam_records(bam);
+        for (int r = 0; r <= gpus; r++) bases[r] = n * (uint64_t) r / gpus;
+        for (int r = 1; r < gpus; r++) {      // the key range of rank r starts at its first record; an empty tail shard owns no key
+            split_ref[r - 1] = split_pos[r - 1] = -1;
+            if (bases[r] < n) {
+                memcpy(&split_ref[r - 1], rec + off[bases[r]] + 4, 4);
+                memcpy(&split_pos[r - 1], rec + off[bases[r]] + 8, 4);
+            }
+        }
+        uint8_t comm_id[128];
+        if (oge_gpu_shard_comm_id(comm_id)) die("MarkDuplicates (GPU): NCCL", oge_gpu_last_error());
+        std::vector<uint16_t> flags(n ? n : 1);
+        std::vector<uint32_t> key_bytes(gpus, 0);
+        pthread_barrier_t barrier;
+        pthread_barrier_init(&barrier, NULL, gpus);
+        std::atomic<int> failed(0);
+        std::vector<ShardJob> jobs(gpus);
+        std::vector<std::thread> workers;
+        for (int r = 0; r < gpus; r++) {
+            ShardJob &j = jobs[r];
+            j.rank = r; j.world = gpus; j.device = device + r; j.bam = bam; j.bases = bases.data();
+            j.split_ref = split_ref.data(); j.split_pos = split_pos.data(); j.comm_id = comm_id; j.flags = flags.data();
+            j.key_bytes = key_bytes.data(); j.barrier = &barrier; j.failed = &failed;
+            memset(&j.stats, 0, sizeof(j.stats));
+            memset(&j.info, 0, sizeof(j.info));
+            workers.emplace_back(shard_worker, &j);
+        }
+        for (auto &w : workers) w.join();
+        pthread_barrier_destroy(&barrier);
+        uint64_t dups = 0, published = 0, routed = 0;
+        float ms = 0;
+        for (int r = 0; r < gpus; r++) {
+            if (!jobs[r].error.empty()) die("MarkDuplicates (GPU)", jobs[r].error.c_str());
+            dups += jobs[r].stats.n_duplicates;
+            published += jobs[r].info.published_in;
+            routed += jobs[r].info.routed_in;
+            ms = jobs[r].stats.ms_total > ms ? jobs[r].stats.ms_total : ms;
+        }
+        const double t_gpu = now_s();
+        if (verbose) {
+            fprintf(stderr, "Range-sharded over %d GPUs: %llu published entries and %llu routed ends crossed ranks; %.3f ms on the slowest device.\n", gpus,
+                    (unsigned long long) published, (unsigned long long) routed, ms);
+            fprintf(stderr, "Marking %llu records as duplicates.\n", (unsigned long long) dups);
+        }
+        if ((rc = oge_bam_apply_flags(bam, flags.data(), remove_dups ? 1 : 0, threads))) die("Error rewriting records", oge_bam_last_error());
+        if ((rc = oge_bam_store(bam, out.c_str(), format.empty() ? NULL : format.c_str(), level, nopg ? NULL : command_line.c_str(),
+                                OGE_VERSION_STRING, threads)))
+            die("Error writing BAM", oge_bam_last_error());
+        if (verbose) {
+            double t[6];
+            oge_bam_timings(bam, t, 6);
+            fprintf(stderr, "Written %llu records.\n", (unsigned long long) oge_bam_n_records(bam));
+            fprintf(stderr, "Timing: load %.3f s | %d gpus %.3f s | rewrite %.3f s | store %.3f s | total %.3f s\n", t_loaded - t_start, gpus, t_gpu - t_loaded,
+                    t[4], t[5], now_s() - t_start);
+        }
+        if (tidy) {
+            oge_bam_close(bam);
+            return 0;
+        }
+        fflush(stdout);
+        fflush(stderr);
+        _exit(0);
+    }
 
     oge_gpu_dedup_config cfg;
     memset(&cfg, 0, sizeof(cfg));

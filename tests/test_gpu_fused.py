@@ -11,7 +11,7 @@ import pytest
 
 import oracle
 from conftest import GOLDEN, load_golden
-from openge_b200 import _build, bamhost, bamio, synth
+from openge_b200 import _build, bamhost, bamio, dedup, synth
 
 pytestmark = pytest.mark.gpu
 
@@ -104,3 +104,28 @@ def test_fused_binary_reports_errors_like_the_reference(tmp, fused_exe):
     open(p, "wb").write(b"\x1f\x8b\x08\x04" + b"\0" * 60)
     r = subprocess.run([fused_exe, p, "-o", os.path.join(tmp, "o.bam")], capture_output=True, timeout=60)
     assert r.returncode != 0 and b"Aborting." in r.stderr
+
+
+def test_fused_binary_over_several_gpus_writes_the_same_file(tmp):
+    """`oge_dedup_fused --gpus N`: the records range-sharded over N GPUs of the node (one host thread and one context per GPU,
+    the exchanges done by NCCL inside the library) must write the file of the single-GPU run, byte for byte -- cuts inside
+    contigs, mates and duplicate sets straddling them."""
+    n_dev = dedup.device_count()
+    if n_dev < 2:
+        pytest.skip("needs at least two GPUs on the box")
+    exe = _build.FUSED_BIN
+    for name, scale, seed in (("C5", 0.0005, 4), ("C3", 0.02, 8), ("C4", 0.01, 3)):
+        bam = synth.make(name, scale, seed=seed)
+        inp = os.path.join(tmp, "in_%s.bam" % name)
+        bamio.write_bam(inp, bam)
+        outs = []
+        for gpus in [1, 2] + ([n_dev] if n_dev > 2 else []):
+            for extra in ([], ["-r"]):
+                out = os.path.join(tmp, "o_%s_%d_%d.bam" % (name, gpus, len(extra)))
+                r = subprocess.run([exe, "dedup", inp, "-o", out, "-v", "--nopg", "-c", "1", "--gpus", str(gpus)] + extra,
+                                   stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+                assert r.returncode == 0, r.stderr.decode()[-2000:]
+                assert ("Range-sharded over %d GPUs" % gpus in r.stderr.decode()) == (gpus > 1)
+                outs.append((gpus, len(extra), hashlib.sha256(open(out, "rb").read()).hexdigest()))
+        for remove in (0, 1):
+            assert len({h for g, e, h in outs if e == remove}) == 1, outs
