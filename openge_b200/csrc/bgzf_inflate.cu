@@ -33,6 +33,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "inflate_core.cuh"
@@ -116,6 +117,8 @@ static void *driver_entry(const char *name) {
 // -> bit 0: the device inflates raw deflate in hardware; max bytes of one operation in *max_len
 static bool engine_query(int device, int *max_len) {
     static int cached_dev[16], cached_ok[16], cached_len[16], n_cached = 0;      // a handful of devices per process
+    static std::mutex guard;      // contexts of several devices may be set up by several host threads at once
+    std::lock_guard<std::mutex> lock(guard);
     for (int i = 0; i < n_cached; i++)
         if (cached_dev[i] == device) {
             if (max_len) *max_len = cached_len[i];

@@ -390,7 +390,11 @@ int oge_gpu_dedup_push_bgzf(oge_gpu_dedup_ctx *c, const uint8_t *comp, uint64_t 
     }
     if (e != cudaSuccess) return done(fail_cuda(e, "push_bgzf setup", __FILE__, __LINE__));
     uint64_t launches = 0, pieces = 0, engine_ops = 0;
-    const bool trace = getenv("OGE_TRACE_PUSH") != nullptr;
+#ifdef OGE_TESTING
+    const bool trace = getenv("OGE_TRACE_PUSH") != nullptr;      // measurement hook of the -DOGE_TESTING build: per-piece device timestamps on stderr
+#else
+    const bool trace = false;
+#endif
     auto wall = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; };
     const double w0 = wall();
     std::vector<cudaEvent_t> tr_ev;      // trace: per piece upload done / inflate start / inflate done
@@ -448,6 +452,7 @@ int oge_gpu_dedup_push_bgzf(oge_gpu_dedup_ctx *c, const uint8_t *comp, uint64_t 
     }
     const double w1 = wall();
     uint32_t err[2] = {0, 0};
+    if (e == cudaSuccess && pieces == 0) e = cudaEventRecord(t_inf0, zs);      // a file without blocks: the clocks still read
     if (e == cudaSuccess) e = cudaEventRecord(t_up1, up);
     if (e == cudaSuccess) e = cudaEventRecord(t_inf1, zs);
     if (e == cudaSuccess) e = cudaEventRecord(t_dn1, down);

@@ -1,5 +1,5 @@
-"""push_bgzf on its own, with the library's trace (OGE_TRACE_PUSH): how the pieces of the upload and their inflates
-line up on the device, for a few piece sizes.  Measurement tool.
+"""push_bgzf on its own, with the trace of the library's -DOGE_TESTING build (OGE_TRACE_PUSH): how the pieces of the upload
+and their inflates line up on the device, for a few piece sizes.  Measurement tool.
 
     OGE_TRACE_PUSH=1 python tools/bench/bgzf_push_probe.py --scale 0.2
 """
@@ -36,7 +36,7 @@ def main():
         pos += bs
     in_off = np.asarray(in_off, dtype=np.uint64); csize = np.asarray(csize, dtype=np.uint32); isize = np.asarray(isize, dtype=np.uint32)
     head = len(raw) - bam.records.nbytes
-    with dedup.context_for(bam, device=0) as ctx:
+    with dedup.testing_library(), dedup.context_for(bam, device=0) as ctx:      # the product library carries no trace hook
         for piece in (0, 16 << 20, 2 ** 64 - 1, 0):
             dedup.set_bgzf_chunk_bytes(piece)
             for rep in range(2):
