@@ -441,7 +441,7 @@ def side_configs(args, local_rank):
                 got = ctx.flags()
                 st = ctx.stats()
             m = float(np.mean(ms))
-            out[name] = {"reads": bam.n, "ms_per_step": m, "reads_per_s": bam.n / (m * 1e-3), "duplicates": int(st["n_duplicates"]),
+            out[name] = {"reads": bam.n, "ms_per_step": m, "step_ms": [float(x) for x in ms], "reads_per_s": bam.n / (m * 1e-3), "duplicates": int(st["n_duplicates"]),
                          "stage_ms": {k: st[k] for k in ("ms_endbuild", "ms_join", "ms_sort_pair", "ms_sort_frag", "ms_select", "ms_flags")}}
             checks[name] = (OracleCheck(bam.records, bam.offsets, bam.text), got)
         except Exception as ex:
@@ -666,6 +666,7 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": workload_name(args), "reads": n, "record_bytes": int(rec.nbytes),
                    "l2": "inputs (%.1f GB) larger than L2" % (rec.nbytes / 1e9), "wall_ms_per_step": wall_ms,
+                   "step_ms": [float(x) for x in dev_ms],
                    "duplicates_flagged": n_dup, "gen_seconds": t_gen, "stage_ms": {k: st[k] for k in (
                        "ms_endbuild", "ms_join", "ms_sort_pair", "ms_sort_frag", "ms_select", "ms_flags")},
                    "key_bits": [st["frag_key_bits"], st["pair_key_bits"]],

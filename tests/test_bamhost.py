@@ -258,3 +258,38 @@ def test_host_layer_has_no_cuda_and_no_oracle():
     assert "cuda" not in src.lower().replace("no cuda", "") and "oracle" not in src
     out = subprocess.run(["ldd", _build.ensure_bamhost()], capture_output=True, text=True).stdout
     assert "libcudart" not in out and "openge_b200" not in out
+
+
+def test_store_members_writes_the_same_stream_as_store(tmp):
+    """oge_bam_store_members: the output file around record members that were compressed elsewhere (on the device,
+    oge_gpu_dedup_deflate; here: by python's zlib in blocks of another size).  After decompression the file must equal
+    oge_bam_store's -- header re-rendered the same way, @PG line, the records, the empty end-of-file member last."""
+    import zlib
+    bam = synth.make("C3", 0.01, seed=12)
+    inp = os.path.join(tmp, "in.bam")
+    bamio.write_bam(inp, bam)
+    for pg in (None, "openge dedup in.bam -o out.bam"):
+        a, b = os.path.join(tmp, "a.bam"), os.path.join(tmp, "b.bam")
+        with bamhost.HostBam(inp) as h:
+            flags = oracle.markdup(h.records.copy(), h.offsets.copy(), h.text)
+            h.apply_flags(flags, False, 0)
+            h.store(a, None, 6, pg)
+            rec = h.records.tobytes()      # flag-patched, bins recomputed
+            members = []
+            for k in range(0, len(rec), 50000):
+                chunk = rec[k:k + 50000]
+                co = zlib.compressobj(1, zlib.DEFLATED, -15)
+                z = co.compress(chunk) + co.flush()
+                members.append(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + (len(z) + 25).to_bytes(2, "little") + z +
+                               zlib.crc32(chunk).to_bytes(4, "little") + len(chunk).to_bytes(4, "little"))
+            h.store_members(b, np.frombuffer(b"".join(members), dtype=np.uint8), 6, pg)
+        za, zb = open(a, "rb").read(), open(b, "rb").read()
+        assert bamhost.bgzf_decompress(za) == bamhost.bgzf_decompress(zb)
+        assert zb.endswith(za[-28:]) and za[-28:].endswith(b"\x00\x00\x00\x00\x00\x00\x00\x00")      # the empty member ends both files
+        got = bamio.read_bam(b)
+        assert got.n == bam.n and np.array_equal(got.flags(), flags) and (pg is None) == ("@PG" not in got.text.replace(bam.text, ""))
+    # no records at all: header members and the end-of-file member
+    with bamhost.HostBam(inp) as h:
+        e = os.path.join(tmp, "e.bam")
+        h.store_members(e, np.zeros(0, dtype=np.uint8), 6, None)
+    assert bamio.read_bam(e).n == 0
