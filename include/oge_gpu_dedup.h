@@ -318,6 +318,11 @@ int oge_gpu_inflate_kernel(int device);
 /* Tuning hook: compressed bytes per piece of push_bgzf's overlapped upload (0 = default: 64 MB for the engine, 512 MB for the
  * kernels; ~0 = the whole file in one piece, i.e. upload, then inflate, then copy-back). */
 int oge_gpu_set_bgzf_chunk_bytes(uint64_t bytes);
+/* A compressed file in PAGEABLE host memory goes up through two pinned staging buffers of the context (32 MB each by
+ * default), filled by several host threads while the previous one is on its way.  stage_bytes = their size; 0 = leave
+ * pageable sources to the driver's own staging (one copy stream: 11 GB/s on the B200 box against 55 GB/s from page-locked
+ * memory).  Files smaller than two buffers go up directly. */
+int oge_gpu_set_bgzf_staging(uint64_t stage_bytes);
 
 /* Pinned host memory for push/pull buffers. */
 void *oge_gpu_host_alloc(size_t nbytes);

@@ -91,6 +91,9 @@ struct oge_gpu_dedup_ctx {
     cudaEvent_t copy_done = nullptr;
     cudaEvent_t ev[10];
     cudaEvent_t ev_piece[3] = {nullptr, nullptr, nullptr};      // push_bgzf: stream hand-overs per piece (no timing)
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr};               // push_bgzf from pageable memory: a staging buffer's upload has left it
+    uint8_t *h_stage[2] = {nullptr, nullptr};                    // ... the two pinned staging buffers (allocated on first use)
+    uint64_t h_stage_bytes = 0;
     // sharded path: phase clocks are resolved lazily (no host sync per phase)
     static constexpr int N_CLK = 48;
     cudaEvent_t clk_ev[2 * N_CLK];

@@ -80,7 +80,7 @@ EXPORTS = ["oge_gpu_dedup_create", "oge_gpu_dedup_destroy", "oge_gpu_dedup_set_r
            "oge_gpu_dedup_reset", "oge_gpu_dedup_flagstats", "oge_gpu_dedup_get_stats", "oge_gpu_dedup_debug_ends",
            "oge_gpu_dedup_device_ptrs", "oge_gpu_host_alloc", "oge_gpu_host_free", "oge_gpu_device_count",
            "oge_gpu_last_error", "oge_gpu_abi_version", "oge_gpu_debug_sort128", "oge_gpu_debug_sort_bench",
-           "oge_gpu_set_sort_variant", "oge_gpu_set_inflate_kernel", "oge_gpu_inflate_kernel", "oge_gpu_set_bgzf_chunk_bytes", "oge_gpu_shard_setup", "oge_gpu_shard_begin", "oge_gpu_shard_probe",
+           "oge_gpu_set_sort_variant", "oge_gpu_set_inflate_kernel", "oge_gpu_inflate_kernel", "oge_gpu_set_bgzf_chunk_bytes", "oge_gpu_set_bgzf_staging", "oge_gpu_shard_setup", "oge_gpu_shard_begin", "oge_gpu_shard_probe",
            "oge_gpu_shard_finish", "oge_gpu_shard_apply", "oge_gpu_copy_d2d", "oge_gpu_dedup_sort", "oge_gpu_dedup_sort_order",
            "oge_gpu_dedup_sort_stats", "oge_gpu_sizeof", "oge_gpu_shard_key_bytes", "oge_gpu_shard_set_entry_bytes", "oge_gpu_shard_replay",
            "oge_gpu_shard_comm_id", "oge_gpu_shard_comm_init", "oge_gpu_shard_comm_destroy", "oge_gpu_shard_step"]
@@ -168,6 +168,7 @@ def _load(path):
         L.oge_gpu_set_inflate_kernel.argtypes = [C.c_int]
         L.oge_gpu_inflate_kernel.argtypes = [C.c_int]
         L.oge_gpu_set_bgzf_chunk_bytes.argtypes = [u64]
+        L.oge_gpu_set_bgzf_staging.argtypes = [u64]
         L.oge_gpu_copy_d2d.argtypes = [vp, vp, vp, u64]
         L.oge_gpu_shard_setup.argtypes = [vp, u64, vp, vp, vp]
         L.oge_gpu_shard_key_bytes.argtypes = [vp, C.POINTER(C.c_uint32)]
@@ -227,6 +228,11 @@ def inflate_kernel(device: int = 0) -> str:
     if k < 0:
         _check(k)
     return {v: n for n, v in INFLATE_KERNELS.items()}[k]
+
+
+def set_bgzf_staging(stage_bytes: int = 32 << 20):
+    """Size of the two pinned staging buffers a compressed file in pageable memory goes up through (0: off)."""
+    _check(lib().oge_gpu_set_bgzf_staging(stage_bytes))
 
 
 def set_bgzf_chunk_bytes(nbytes: int):

@@ -39,8 +39,11 @@
 
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
+static std::thread *g_warm = NULL;      // the thread that brings the CUDA context up: joined before the process exits
+
 static void die(const char *what, const char *msg) {
     fprintf(stderr, "%s: %s Aborting.\n", what, msg);
+    if (g_warm && g_warm->joinable() && std::this_thread::get_id() != g_warm->get_id()) g_warm->join();
     exit(-1);
 }
 
@@ -52,7 +55,7 @@ struct MemberStream {
     uint8_t *buf[2];
     uint64_t len[2];
     int cur;
-    static constexpr uint64_t PART = 32ull << 20;
+    static constexpr uint64_t PART = 64ull << 20;
     int issue(int which) {
         len[which] = total - issued < PART ? total - issued : PART;
         const int rc = len[which] ? oge_gpu_dedup_pull_bgzf_part(ctx, issued, len[which], buf[which]) : 0;
@@ -209,7 +212,21 @@ int main(int argc, char **argv) {
 
     const double t_start = now_s();
     oge_bam_file *bam = NULL;
-    if (oge_gpu_device_count() < 1) die("MarkDuplicates (GPU)", "no CUDA device: this path has no CPU fallback.");
+    // the CUDA context (0.4-0.7 s on the B200 box) comes up while the file is being read and scanned
+    int n_devices = -1;
+    std::thread warm([&] {
+        n_devices = oge_gpu_device_count();
+        if (n_devices > device) {
+            oge_gpu_dedup_config wc;
+            memset(&wc, 0, sizeof(wc));
+            wc.abi_version = OGE_GPU_DEDUP_ABI_VERSION;
+            wc.device = device;
+            wc.verify_names = -1;
+            oge_gpu_dedup_ctx *w = NULL;
+            if (oge_gpu_dedup_create(&wc, &w) == 0) oge_gpu_dedup_destroy(w);
+        }
+    });
+    g_warm = &warm;
     oge_bam_alloc_fn alloc_fn = pinned ? oge_gpu_host_alloc : NULL;
     oge_bam_free_fn free_fn = pinned ? oge_gpu_host_free : NULL;
     // BGZF input: open in two stages and let the GPU inflate; an uncompressed stream (or --cpu-inflate) loads on the host
@@ -221,6 +238,9 @@ int main(int argc, char **argv) {
         else if (rc) die("Error reading BAM", oge_bam_last_error());
     }
     if (!gpu_inflate && (rc = oge_bam_load(in.c_str(), threads, alloc_fn, free_fn, &bam))) die("Error reading BAM", oge_bam_last_error());
+    warm.join();
+    g_warm = NULL;
+    if (n_devices < 1) die("MarkDuplicates (GPU)", "no CUDA device: this path has no CPU fallback.");
     const double t_loaded = now_s();
 
     if (gpus > 1) {
@@ -402,7 +422,7 @@ int main(int argc, char **argv) {
         ms.buf[0] = (uint8_t *) oge_gpu_host_alloc(MemberStream::PART);
         ms.buf[1] = (uint8_t *) oge_gpu_host_alloc(MemberStream::PART);
         if (!ms.buf[0] || !ms.buf[1]) die("Error writing BAM", "cannot allocate the output staging buffers.");
-        if ((rc = oge_bam_store_members_stream(bam, out.c_str(), level, nopg ? NULL : command_line.c_str(), OGE_VERSION_STRING, MemberStream::fill, &ms)))
+        if ((rc = oge_bam_store_members_stream(bam, out.c_str(), level, nopg ? NULL : command_line.c_str(), OGE_VERSION_STRING, MemberStream::fill, &ms, threads)))
             die("Error writing BAM", oge_bam_last_error());
         oge_gpu_host_free(ms.buf[0]);
         oge_gpu_host_free(ms.buf[1]);

@@ -142,3 +142,39 @@ def test_codes_are_complete_and_short(lib):
             p = f[f > 0] / f.sum()
             entropy_bits = float(-(f[f > 0] * np.log2(p)).sum())
             assert bits <= entropy_bits + f.sum() + 16
+
+
+def test_compressor_fuzz_round_trips_through_zlib(lib):
+    """Randomised structure (runs, repeats at every distance class, literals of varying entropy, text-like records): every
+    stream the compressor writes must inflate back to its input with zlib; a few hundred blocks of every size class."""
+    rng = np.random.default_rng(77)
+    n_cases = 0
+    for case in range(250):
+        parts = []
+        size = int(rng.integers(1, 65536))
+        while sum(len(p) for p in parts) < size:
+            kind = int(rng.integers(0, 5))
+            if kind == 0:
+                parts.append(rng.integers(0, int(rng.integers(1, 257)), int(rng.integers(1, 4000)), dtype=np.uint8).tobytes())
+            elif kind == 1:
+                parts.append(bytes([int(rng.integers(0, 256))]) * int(rng.integers(1, 3000)))
+            elif kind == 2 and parts:
+                prev = b"".join(parts)
+                d = int(rng.integers(1, min(len(prev), 40000) + 1))
+                l = int(rng.integers(3, 600))
+                parts.append((prev[-d:] * (l // d + 1))[:l])
+            elif kind == 3:
+                p = np.array([2.0 ** -(i / float(rng.integers(2, 12))) for i in range(256)])
+                parts.append(rng.choice(256, size=int(rng.integers(1, 5000)), p=p / p.sum()).astype(np.uint8).tobytes())
+            else:
+                words = [b"chr1", b"ACGT", b"read", b"\x00\x01\x02", b"IIIIIIII", b"RG:Z:rg1"]
+                parts.append(b"".join(words[int(x)] for x in rng.integers(0, len(words), int(rng.integers(1, 300)))))
+        data = b"".join(parts)[:65535]
+        z = deflate(lib, data)
+        d = zlib.decompressobj(-15)
+        back = d.decompress(z)
+        assert d.eof and d.unused_data == b"" and back == data, ("case", case, len(data), len(z))
+        assert len(z) <= len(data) + 5
+        assert lib.oge_test_crc32(data, len(data), 32) == zlib.crc32(data)
+        n_cases += 1
+    assert n_cases == 250
