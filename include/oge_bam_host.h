@@ -112,11 +112,12 @@ int oge_bam_store(oge_bam_file *f, const char *path, const char *format, int lev
 int oge_bam_store_members(oge_bam_file *f, const char *path, int level, const char *pg_command_line, const char *pg_version,
                           const uint8_t *members, uint64_t members_bytes);
 /* ... with the members arriving in pieces: fill(user, &data, &nbytes) hands out the next piece (valid until the next call),
- * nbytes = 0 at the end, a non-zero return aborts.  Pieces need not end on member boundaries.  A large piece is written by
- * up to `threads` writers at disjoint offsets (0 = all host threads). */
+ * nbytes = 0 at the end, a non-zero return aborts.  Pieces need not end on member boundaries.  members_bytes_hint = the
+ * total of all pieces when known (it must then be exact), 0 otherwise: with it the file is sized first and filled through
+ * a shared mapping by up to `threads` threads (0 = all), without it the pieces are written one after the other. */
 typedef int (*oge_bam_fill_fn)(void *user, const uint8_t **data, uint64_t *nbytes);
 int oge_bam_store_members_stream(oge_bam_file *f, const char *path, int level, const char *pg_command_line, const char *pg_version,
-                                 oge_bam_fill_fn fill, void *user, int threads);
+                                 oge_bam_fill_fn fill, void *user, uint64_t members_bytes_hint, int threads);
 
 /* seconds: [0] read file, [1] block scan, [2] inflate, [3] header + framing, [4] apply_flags, [5] store */
 int oge_bam_timings(const oge_bam_file *f, double *out, int n);

@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
+#include <sys/mman.h>
 #include <unistd.h>
 #include <zlib.h>
 
@@ -197,9 +198,6 @@ struct Segments {
 struct Sink {      // where compressed bytes go: a file descriptor or a growing buffer
     int fd = -1;
     std::vector<uint8_t> *buf = nullptr;
-    // a large piece into a regular file with several writers (pwrite at disjoint offsets): one write() stream copies
-    // into the page cache at 3-4 GB/s, which is what a file-to-file run was waiting for once the deflate had left the host
-    int write_parallel(const uint8_t *p, size_t n, int threads);
     int write(const uint8_t *p, size_t n) {
         if (buf) {
             buf->insert(buf->end(), p, p + n);
@@ -214,27 +212,6 @@ struct Sink {      // where compressed bytes go: a file descriptor or a growing 
         return 0;
     }
 };
-
-int Sink::write_parallel(const uint8_t *p, size_t n, int threads) {
-    const size_t MIN_PART = (size_t) 4 << 20;
-    if (buf || threads < 2 || n < 2 * MIN_PART) return write(p, n);
-    const off_t at = lseek(fd, 0, SEEK_CUR);
-    if (at < 0) return write(p, n);      // not seekable (a pipe): one stream
-    const int parts = (int) std::min<size_t>((size_t) threads, n / MIN_PART);
-    const size_t per = (n + parts - 1) / parts;
-    const int fdc = fd;
-    int rc = parallel_run(parts, [&](int w) -> int {
-        size_t a = (size_t) w * per, b = std::min(n, a + per);
-        while (a < b) {
-            const ssize_t k = pwrite(fdc, p + a, b - a, at + (off_t) a);
-            if (k < 0) return fail(OGE_BAM_ERR_IO, "write failed: %s", strerror(errno));
-            a += (size_t) k;
-        }
-        return 0;
-    });
-    if (!rc && lseek(fd, at + (off_t) n, SEEK_SET) < 0) rc = fail(OGE_BAM_ERR_IO, "seek failed: %s", strerror(errno));
-    return rc;
-}
 
 // The block sequence of BgzfOutputStream::write + close (:170-250): full blocks, the current block (whatever it
 // holds, possibly nothing), an empty block.  Blocks are compressed in waves of WAVE blocks by all threads, and a
@@ -922,26 +899,56 @@ int oge_bam_store(oge_bam_file *f, const char *path, const char *format, int lev
 }
 
 int oge_bam_store_members_stream(oge_bam_file *f, const char *path, int level, const char *pg_command_line, const char *pg_version,
-                                 oge_bam_fill_fn fill, void *user, int threads) {
+                                 oge_bam_fill_fn fill, void *user, uint64_t members_bytes_hint, int threads) {
     if (!f || !path || !fill) return fail(OGE_BAM_ERR_ARG, "store_members: null argument");
-    threads = clamp_threads(threads);
     if (level < 0 || level > 9) return fail(OGE_BAM_ERR_ARG, "store_members: compression level %d", level);
+    threads = clamp_threads(threads);
     const double t0 = now_s();
     const std::vector<uint8_t> head = render_head(f, pg_command_line, pg_version);
     // the header in members of its own (host zlib, `level`), then the record members as they come, then the empty member that
     // ends a BGZF file (BgzfOutputStream::close, util/bgzf_output_stream.cpp:225-250)
-    std::vector<uint8_t> hz(BGZF_BLOCK);
-    const int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
-    if (fd < 0) return fail(OGE_BAM_ERR_IO, "cannot open %s for writing: %s", path, strerror(errno));
-    Sink sink;
-    sink.fd = fd;
-    int rc = 0;
+    std::vector<uint8_t> front, hz(BGZF_BLOCK);
     const uint32_t full = level == 0 ? BGZF_BLOCK - 64 : BGZF_BLOCK;
+    int rc = 0;
     for (size_t at = 0; at < head.size() && !rc; at += full) {
         uint32_t n = 0;
         rc = bgzf_compress_block(head.data() + at, (uint32_t) std::min<size_t>(full, head.size() - at), level, hz.data(), &n);
-        if (!rc) rc = sink.write(hz.data(), n);
+        if (!rc) front.insert(front.end(), hz.data(), hz.data() + n);
     }
+    uint32_t eof_n = 0;
+    if (!rc) rc = bgzf_compress_block(head.data(), 0, level, hz.data(), &eof_n);
+    if (rc) return rc;
+    const int fd = open(path, O_RDWR | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return fail(OGE_BAM_ERR_IO, "cannot open %s for writing: %s", path, strerror(errno));
+    // With the size of the members known the file is sized first and filled through a shared mapping by several threads: one
+    // write() stream into the page cache runs at 3-4 GB/s, and writers at disjoint offsets of one file queue up behind its lock.
+    const uint64_t total = front.size() + members_bytes_hint + eof_n;
+    uint8_t *map = nullptr;
+    if (members_bytes_hint >= ((uint64_t) 64 << 20) && threads > 1 && ftruncate(fd, (off_t) total) == 0) {
+        void *m = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        if (m != MAP_FAILED) map = (uint8_t *) m;
+        else if (ftruncate(fd, 0) != 0) rc = fail(OGE_BAM_ERR_IO, "truncate failed on %s: %s", path, strerror(errno));
+    }
+    Sink sink;
+    sink.fd = fd;
+    uint64_t pos = 0;
+    auto put = [&](const uint8_t *p, uint64_t n) -> int {
+        if (!map) return sink.write(p, n);
+        if (pos + n > total) return fail(OGE_BAM_ERR_ARG, "store_members: more member bytes than announced");
+        const int parts = (int) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) threads, n / ((uint64_t) 4 << 20)));
+        const uint64_t per = (n + parts - 1) / parts;
+        uint8_t *dst = map + pos;
+        if (parts == 1) memcpy(dst, p, n);
+        else parallel_run(parts, [&](int w) -> int {
+            const uint64_t a = per * w, b = std::min(n, a + per);
+            if (b > a) memcpy(dst + a, p + a, b - a);
+            return 0;
+        });
+        pos += n;
+        return 0;
+    };
+    if (!rc) rc = put(front.data(), front.size());
+    uint64_t got = 0;
     while (!rc) {
         const uint8_t *data = nullptr;
         uint64_t n = 0;
@@ -950,12 +957,14 @@ int oge_bam_store_members_stream(oge_bam_file *f, const char *path, int level, c
             break;
         }
         if (!n) break;
-        rc = sink.write_parallel(data, n, threads);
+        got += n;
+        rc = put(data, n);
     }
-    if (!rc) {
-        uint32_t n = 0;
-        rc = bgzf_compress_block(head.data(), 0, level, hz.data(), &n);
-        if (!rc) rc = sink.write(hz.data(), n);
+    if (!rc) rc = put(hz.data(), eof_n);
+    if (map) {
+        if (munmap(map, total) != 0 && !rc) rc = fail(OGE_BAM_ERR_IO, "munmap failed on %s: %s", path, strerror(errno));
+        if (!rc && got != members_bytes_hint) rc = fail(OGE_BAM_ERR_ARG, "store_members: %llu member bytes announced, %llu delivered",
+                                                        (unsigned long long) members_bytes_hint, (unsigned long long) got);
     }
     if (close(fd) != 0 && !rc) rc = fail(OGE_BAM_ERR_IO, "close failed on %s", path);
     f->t[5] = now_s() - t0;
@@ -980,7 +989,7 @@ int oge_bam_store_members(oge_bam_file *f, const char *path, int level, const ch
                           const uint8_t *members, uint64_t members_bytes) {
     if (!members && members_bytes) return fail(OGE_BAM_ERR_ARG, "store_members: null argument");
     OneChunk c = {members, members_bytes};
-    return oge_bam_store_members_stream(f, path, level, pg_command_line, pg_version, one_chunk_fill, &c, 0);
+    return oge_bam_store_members_stream(f, path, level, pg_command_line, pg_version, one_chunk_fill, &c, members_bytes, 0);
 }
 
 int oge_bam_timings(const oge_bam_file *f, double *out, int n) {

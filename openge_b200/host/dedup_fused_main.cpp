@@ -39,11 +39,8 @@
 
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-static std::thread *g_warm = NULL;      // the thread that brings the CUDA context up: joined before the process exits
-
 static void die(const char *what, const char *msg) {
     fprintf(stderr, "%s: %s Aborting.\n", what, msg);
-    if (g_warm && g_warm->joinable() && std::this_thread::get_id() != g_warm->get_id()) g_warm->join();
     exit(-1);
 }
 
@@ -212,21 +209,9 @@ int main(int argc, char **argv) {
 
     const double t_start = now_s();
     oge_bam_file *bam = NULL;
-    // the CUDA context (0.4-0.7 s on the B200 box) comes up while the file is being read and scanned
-    int n_devices = -1;
-    std::thread warm([&] {
-        n_devices = oge_gpu_device_count();
-        if (n_devices > device) {
-            oge_gpu_dedup_config wc;
-            memset(&wc, 0, sizeof(wc));
-            wc.abi_version = OGE_GPU_DEDUP_ABI_VERSION;
-            wc.device = device;
-            wc.verify_names = -1;
-            oge_gpu_dedup_ctx *w = NULL;
-            if (oge_gpu_dedup_create(&wc, &w) == 0) oge_gpu_dedup_destroy(w);
-        }
-    });
-    g_warm = &warm;
+    // (Bringing the CUDA context up on a second thread while the file is read was measured and dropped: the two contend for the
+    // process's address-space lock -- context creation took 0.70 s next to the read against 0.25 s after it.)
+    if (oge_gpu_device_count() < 1) die("MarkDuplicates (GPU)", "no CUDA device: this path has no CPU fallback.");
     oge_bam_alloc_fn alloc_fn = pinned ? oge_gpu_host_alloc : NULL;
     oge_bam_free_fn free_fn = pinned ? oge_gpu_host_free : NULL;
     // BGZF input: open in two stages and let the GPU inflate; an uncompressed stream (or --cpu-inflate) loads on the host
@@ -238,9 +223,6 @@ int main(int argc, char **argv) {
         else if (rc) die("Error reading BAM", oge_bam_last_error());
     }
     if (!gpu_inflate && (rc = oge_bam_load(in.c_str(), threads, alloc_fn, free_fn, &bam))) die("Error reading BAM", oge_bam_last_error());
-    warm.join();
-    g_warm = NULL;
-    if (n_devices < 1) die("MarkDuplicates (GPU)", "no CUDA device: this path has no CPU fallback.");
     const double t_loaded = now_s();
 
     if (gpus > 1) {
@@ -408,11 +390,12 @@ int main(int argc, char **argv) {
     memset(&fs, 0, sizeof(fs));
     if (stats && (rc = oge_gpu_dedup_flagstats(ctx, &fs))) die("Statistics (GPU)", oge_gpu_last_error());
     uint64_t members_bytes = 0, member_blocks = 0, n_written = 0;
-    double t_gpu = 0;
+    double t_gpu = 0, t_mark[4] = {0, 0, 0, 0};
     if (gpu_deflate) {      // the output's BGZF members, made where the records are, streamed into the file
         if ((rc = oge_gpu_dedup_deflate(ctx, &members_bytes, &member_blocks, &n_written))) die("Error writing BAM", oge_gpu_last_error());
         oge_gpu_dedup_get_stats(ctx, &st);
         t_gpu = now_s();
+        t_mark[0] = t_gpu;
         MemberStream ms;
         ms.ctx = ctx;
         ms.total = members_bytes;
@@ -422,10 +405,13 @@ int main(int argc, char **argv) {
         ms.buf[0] = (uint8_t *) oge_gpu_host_alloc(MemberStream::PART);
         ms.buf[1] = (uint8_t *) oge_gpu_host_alloc(MemberStream::PART);
         if (!ms.buf[0] || !ms.buf[1]) die("Error writing BAM", "cannot allocate the output staging buffers.");
-        if ((rc = oge_bam_store_members_stream(bam, out.c_str(), level, nopg ? NULL : command_line.c_str(), OGE_VERSION_STRING, MemberStream::fill, &ms, threads)))
+        t_mark[1] = now_s();
+        if ((rc = oge_bam_store_members_stream(bam, out.c_str(), level, nopg ? NULL : command_line.c_str(), OGE_VERSION_STRING, MemberStream::fill, &ms, members_bytes, threads)))
             die("Error writing BAM", oge_bam_last_error());
+        t_mark[2] = now_s();
         oge_gpu_host_free(ms.buf[0]);
         oge_gpu_host_free(ms.buf[1]);
+        t_mark[3] = now_s();
     }
     if (tidy) oge_gpu_dedup_destroy(ctx);      // else the process exit does it: cudaFree of tens of GB costs 24 ms per GB
     if (!gpu_deflate) t_gpu = now_s();
@@ -467,6 +453,9 @@ int main(int argc, char **argv) {
         double t[6];
         oge_bam_timings(bam, t, 6);
         fprintf(stderr, "Written %llu records.\n", (unsigned long long) n_written);
+        if (gpu_deflate)
+            fprintf(stderr, "Timing (output): staging buffers %.3f s, members streamed into the file %.3f s, staging freed %.3f s\n", t_mark[1] - t_mark[0],
+                    t_mark[2] - t_mark[1], t_mark[3] - t_mark[2]);
         if (gpu_deflate)
             fprintf(stderr, "gpu deflate: %llu blocks, %.1f MB -> %.1f MB in %.3f ms on the device (%.1f GB/s in).\n", (unsigned long long) member_blocks,
                     st.deflate_bytes_in / 1e6, st.deflate_bytes_out / 1e6, st.ms_deflate, st.ms_deflate > 0 ? st.deflate_bytes_in / 1e6 / st.ms_deflate : 0.0);

@@ -293,3 +293,28 @@ def test_store_members_writes_the_same_stream_as_store(tmp):
         e = os.path.join(tmp, "e.bam")
         h.store_members(e, np.zeros(0, dtype=np.uint8), 6, None)
     assert bamio.read_bam(e).n == 0
+
+
+def test_store_members_large_goes_through_the_mapping(tmp):
+    # 80 MB of members: above the size from which the file is sized first and filled through a shared mapping by several threads
+    import zlib
+    bam = synth.make("C1", 0.002, seed=1)
+    inp, out = os.path.join(tmp, "in.bam"), os.path.join(tmp, "big.bam")
+    bamio.write_bam(inp, bam)
+    rng = np.random.default_rng(5)
+    payload = rng.integers(0, 256, 65000, dtype=np.uint8).tobytes()
+    co = zlib.compressobj(0, zlib.DEFLATED, -15)
+    z = co.compress(payload) + co.flush()
+    member = (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + (len(z) + 25).to_bytes(2, "little") + z +
+              zlib.crc32(payload).to_bytes(4, "little") + len(payload).to_bytes(4, "little"))
+    n = (80 << 20) // len(member) + 1
+    members = np.frombuffer(member * n, dtype=np.uint8)
+    with bamhost.HostBam(inp) as h:
+        h.store_members(out, members, 6, None)
+        small = os.path.join(tmp, "small.bam")
+        h.store_members(small, members[:len(member) * 3], 6, None)
+    zb = open(out, "rb").read()
+    zs = open(small, "rb").read()
+    head_len = len(zs) - 3 * len(member) - 28
+    assert zb[:head_len] == zs[:head_len] and zb[-28:] == zs[-28:]      # same header members, same end-of-file member
+    assert zb[head_len:-28] == members.tobytes()
