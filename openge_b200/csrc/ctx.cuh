@@ -16,8 +16,12 @@ struct DevBuf {
     size_t cap = 0;      // elements
     int reserve(size_t n, bool keep, cudaStream_t s) {
         if (n <= cap) return 0;
-        // grow with slack: sizes that follow data-dependent (and race-dependent) counts must not reallocate on every run
-        size_t want = keep && cap ? std::max(n, cap + cap / 2) : (cap ? n + n / 8 + 4096 : n);
+        // grow with slack: sizes that follow data-dependent (and race-dependent) counts must not reallocate on every run.  The
+        // FIRST allocation of a small buffer gets the slack as well: a count that came out a little higher on the second or
+        // third run used to put a cudaFree + cudaMalloc (3 ms and more) into that run (bench: one slow step out of five).  The
+        // big buffers (records, per-record arrays) are sized from the input and stay exact.
+        const bool small_buf = n * sizeof(T) < ((size_t) 256 << 20);
+        size_t want = keep && cap ? std::max(n, cap + cap / 2) : (cap || small_buf ? n + n / 8 + 4096 : n);
         T *q = nullptr;
         cudaError_t e = cudaMalloc((void **) &q, want * sizeof(T) + 256);
         if (e != cudaSuccess && want > n) {
