@@ -107,7 +107,8 @@ typedef struct oge_gpu_dedup_stats {
     float ms_push_bgzf;
     uint32_t inflate_mode, inflate_pieces;
     float ms_inflate_start;         /* device time from the start of push_bgzf to the start of the first piece's inflate */
-    /* oge_gpu_dedup_deflate: device time, blocks, bytes in (records) and out (BGZF members) */
+    /* oge_gpu_dedup_deflate: time on the context's stream from its first to its last operation (bins, -r compaction, deflate,
+     * packing, and the device allocations between them), blocks, bytes in (records) and out (BGZF members) */
     float ms_deflate;
     uint64_t deflate_blocks, deflate_bytes_in, deflate_bytes_out;
 } oge_gpu_dedup_stats;

@@ -1132,6 +1132,12 @@ int oge_gpu_dedup_deflate(oge_gpu_dedup_ctx *c, uint64_t *out_bytes, uint64_t *o
         kept.release(); kept_off.release(); stage.release(); sizes.release(); moff.release(); seqs.release();
         return code;
     };
+    // CUDA failures from here on release the temporaries as well
+#define OGE_DEFLATE_TRY(expr)                                                            \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) return done(fail_cuda(_e, #expr, __FILE__, __LINE__));    \
+    } while (0)
     uint32_t bin_err = 0;
     if (c->cfg.remove_duplicates) {      // :456-458
         if ((rc = kept.reserve(c->rec_bytes, false, s)) || (rc = kept_off.reserve(c->n + 1, false, s))) return done(rc);
@@ -1139,9 +1145,9 @@ int oge_gpu_dedup_deflate(oge_gpu_dedup_ctx *c, uint64_t *out_bytes, uint64_t *o
                                  c->counters.p, s, &launches)))
             return done(rc);
         uint64_t totals[2] = {0, 0};
-        OGE_CUDA_TRY(cudaMemcpyAsync(totals, c->scratch.p, 16, cudaMemcpyDeviceToHost, s));
-        OGE_CUDA_TRY(cudaMemcpyAsync(&bin_err, c->counters.p + CNT_ERR, 4, cudaMemcpyDeviceToHost, s));
-        OGE_CUDA_TRY(cudaStreamSynchronize(s));
+        OGE_DEFLATE_TRY(cudaMemcpyAsync(totals, c->scratch.p, 16, cudaMemcpyDeviceToHost, s));
+        OGE_DEFLATE_TRY(cudaMemcpyAsync(&bin_err, c->counters.p + CNT_ERR, 4, cudaMemcpyDeviceToHost, s));
+        OGE_DEFLATE_TRY(cudaStreamSynchronize(s));
         nrec = totals[0];
         total = totals[1];
         in = kept.p;
@@ -1163,15 +1169,15 @@ int oge_gpu_dedup_deflate(oge_gpu_dedup_ctx *c, uint64_t *out_bytes, uint64_t *o
         P.ticket = reinterpret_cast<unsigned long long *>(sizes.p + ((2 * n_blocks + 1) & ~1ull));
         if ((rc = launch_bgzf_deflate(P, c->sms, s, &launches)) || (rc = launch_scan_sizes(P.dsize, n_blocks, moff.p, s, &launches))) return done(rc);
         uint64_t file_bytes = 0;
-        OGE_CUDA_TRY(cudaMemcpyAsync(&file_bytes, moff.p + n_blocks, 8, cudaMemcpyDeviceToHost, s));
-        if (!c->cfg.remove_duplicates) OGE_CUDA_TRY(cudaMemcpyAsync(&bin_err, c->counters.p + CNT_ERR, 4, cudaMemcpyDeviceToHost, s));
-        OGE_CUDA_TRY(cudaStreamSynchronize(s));
+        OGE_DEFLATE_TRY(cudaMemcpyAsync(&file_bytes, moff.p + n_blocks, 8, cudaMemcpyDeviceToHost, s));
+        if (!c->cfg.remove_duplicates) OGE_DEFLATE_TRY(cudaMemcpyAsync(&bin_err, c->counters.p + CNT_ERR, 4, cudaMemcpyDeviceToHost, s));
+        OGE_DEFLATE_TRY(cudaStreamSynchronize(s));
         if ((rc = c->zfile.reserve(file_bytes, false, s))) return done(rc);
         if ((rc = launch_bgzf_assemble(P, moff.p, c->zfile.p, s, &launches))) return done(rc);
         c->zfile_bytes = file_bytes;
     }
-    OGE_CUDA_TRY(cudaEventRecord(e1, s));
-    OGE_CUDA_TRY(cudaStreamSynchronize(s));
+    OGE_DEFLATE_TRY(cudaEventRecord(e1, s));
+    OGE_DEFLATE_TRY(cudaStreamSynchronize(s));
     if (bin_err) return done(fail_msg(OGE_ERR_BAD_RECORD, "deflate: a record's name and CIGAR overrun the record"));
     c->stats.ms_deflate = ms_between(e0, e1);
     c->stats.deflate_blocks = n_blocks;
@@ -1181,6 +1187,7 @@ int oge_gpu_dedup_deflate(oge_gpu_dedup_ctx *c, uint64_t *out_bytes, uint64_t *o
     *out_blocks = n_blocks;
     *out_nrec = nrec;
     return done(OGE_OK);
+#undef OGE_DEFLATE_TRY
 }
 
 int oge_gpu_dedup_pull_bgzf(oge_gpu_dedup_ctx *c, uint8_t *out, uint64_t cap_bytes) {
