@@ -629,7 +629,7 @@ def bench(args, rank, world, local_rank, rec, offs, text, contigs, metric, workl
                                    "contigs), 1/8 of the workload's reads per rank; pairs straddle every cut, 0.5%% of the pairs have "
                                    "their mates on different contigs" % (workload_name, world),
                        "reads": total_reads, "reads_rank0": n, "l2": "inputs larger than L2",
-                       "wall_ms_per_step": float(mx[4]), "exchange_ms_per_step": float(mx[1]), "device_phase_ms_rank0": st["ms_total"],
+                       "wall_ms_per_step": float(mx[4]), "step_ms_rank0": [float(x) for x in ms], "exchange_ms_per_step": float(mx[1]), "device_phase_ms_rank0": st["ms_total"],
                        "timing": "CUDA events around each step (phases sync the library streams before returning), max over ranks",
                        "duplicates_flagged": total_dups,
                        "published_entries": int(sm[5]), "routed_entries": int(sm[6]), "marks_exchanged": int(sm[7]), "published_entry_bytes": entry_bytes,
