@@ -141,7 +141,8 @@ def ensure_ref(force=False):
     """TEST-ONLY: compile the reference's dedup path in place (only where its sources exist)."""
     if os.path.isdir("/root/reference/openge/src"):
         d = os.path.join(ROOT, "oracle", "ref_build")
-        if force or _stale(REF_BIN, [os.path.join(d, "ref_driver.cpp"), os.path.join(d, "Makefile")]):
+        cli = os.path.join(ROOT, "openge_b200", "host", "refcli", "ref_driver.cpp")      # the command-line front-end shared with the drop-in binaries
+        if force or _stale(REF_BIN, [cli, os.path.join(d, "Makefile")]):
             _run(["make", "-C", d] + (["-B"] if force else []))
     return REF_BIN if os.path.exists(REF_BIN) else None
 
@@ -154,7 +155,7 @@ def ensure_host(force=False):
         d = os.path.join(ROOT, "openge_b200", "host")
         deps = [os.path.join(d, "mark_duplicates_gpu.cpp"), os.path.join(d, "read_sorter_gpu.cpp"), os.path.join(d, "record_batch.h"),
                 os.path.join(d, "Makefile"), GPU_LIB,
-                os.path.join(ROOT, "oracle", "ref_build", "ref_driver.cpp"), os.path.join(ROOT, "include", "oge_gpu_dedup.h")]
+                os.path.join(ROOT, "openge_b200", "host", "refcli", "ref_driver.cpp"), os.path.join(ROOT, "include", "oge_gpu_dedup.h")]
         if force or _stale(HOST_BIN, deps) or _stale(HOST_SORT_BIN, deps):
             _run(["make", "-C", d] + (["-B"] if force else []))
     return HOST_BIN if os.path.exists(HOST_BIN) else None

@@ -1,7 +1,11 @@
-// TEST INFRASTRUCTURE ONLY -- not part of the shipped product path.
+// Command-line front-end of the reference's own pipeline, for builds without Boost: it stands in for the argument parsing
+// of commands/command_dedup.cpp and command_mergesort.cpp and nothing else.  Two users: oracle/ref_build/Makefile links it
+// with the UNMODIFIED reference classes (-> oracle/_ref/oge_ref_dedup, the compiled reference: test infrastructure), and
+// openge_b200/host/Makefile links it with this repo's drop-in MarkDuplicates / ReadSorter (-> oge_dedup_gpu,
+// oge_mergesort_gpu).  It holds no duplicate-marking logic of its own.
 //
-// Driver that wires the UNMODIFIED reference classes (compiled in place from
-// /root/reference/openge/src, see Makefile) the way `openge dedup` does:
+// It wires the reference classes (compiled in place from /root/reference/openge/src, see the Makefiles) the way
+// `openge dedup` does:
 //   command_dedup.cpp:48-69   single chain  FileReader -> MarkDuplicates -> FileWriter
 //   command_dedup.cpp:70-113  split chains  FileReader -> SplitByChromosome -> {MarkDuplicates} -> SortedMerge -> FileWriter
 //   commands.cpp:59-84,110-112  verbose / threads / pool set-up and tear-down

@@ -1,6 +1,6 @@
 """Regenerates tests/golden/flagstats.npz with the COMPILED REFERENCE's own Statistics module
 (algorithms/statistics.cpp) chained behind its MarkDuplicates: `oge_ref_dedup --nosplit -v --stats`
-(oracle/ref_build/ref_driver.cpp).  Run in the build container only:
+(openge_b200/host/refcli/ref_driver.cpp).  Run in the build container only:
 
     python tests/golden/make_flagstats_golden.py
 

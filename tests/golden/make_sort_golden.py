@@ -1,5 +1,5 @@
 """Regenerates tests/golden/sort_order.npz with the COMPILED REFERENCE's ReadSorter chain (`openge mergesort`,
-algorithms/read_sorter.cpp; oracle/ref_build/ref_driver.cpp --sort).  Run in the build container only:
+algorithms/read_sorter.cpp; openge_b200/host/refcli/ref_driver.cpp --sort).  Run in the build container only:
 
     python tests/golden/make_sort_golden.py
 
