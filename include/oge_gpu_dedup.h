@@ -52,9 +52,10 @@ typedef struct oge_gpu_dedup_config {
     int32_t max_ref_len;            /* largest @SQ LN; <=0 -> full 32-bit coordinate field */
     int32_t clip_margin;            /* slack for clipped ends beyond [0, max_ref_len); <=0 -> 1<<20 */
     int32_t remove_duplicates;      /* MarkDuplicates::removeDuplicates (-r); affects oge_gpu_dedup_pull only */
-    int32_t verify_names;           /* 1 (default when <0): hash-matched mates are confirmed by comparing the
-                                       RG+":"+name bytes (ReadEndsMap is keyed by that string,
-                                       picard_structures.h:82-109, mark_duplicates.cpp:210-214) */
+    int32_t verify_names;           /* hash-matched mates are confirmed by comparing the RG+":"+name bytes (ReadEndsMap is
+                                       keyed by that string, picard_structures.h:82-109, mark_duplicates.cpp:210-214).
+                                       Always on in the product library (the field is read by the -DOGE_TESTING build
+                                       alone, where 0 measures hash-only pairing) */
     int32_t compat_quiet_index_bug; /* 1: reproduce non-verbose runs of the reference, where the record index
                                        never advances (mark_duplicates.cpp:250).  Default 0. */
     int32_t debug_keep_ends;        /* 1: keep a copy of the per-record end entries for oge_gpu_dedup_debug_ends */

@@ -214,7 +214,11 @@ int oge_gpu_dedup_create(const oge_gpu_dedup_config *cfg, oge_gpu_dedup_ctx **ou
         return fail_msg(OGE_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
     oge_gpu_dedup_ctx *c = new oge_gpu_dedup_ctx();
     c->cfg = *cfg;
+#ifdef OGE_TESTING
     if (c->cfg.verify_names < 0) c->cfg.verify_names = 1;
+#else
+    c->cfg.verify_names = 1;      // the product library always pairs by the key's bytes: hash-only pairing is a measurement knob
+#endif
     c->sms = prop.multiProcessorCount;
     memset(&c->stats, 0, sizeof(c->stats));
     int rc = 0;
