@@ -446,9 +446,12 @@ def make_rank_shard(workload, scale, rank, world, pinned=True):
         over.cross_contig_frac, over.dup_frac = 1.0, 0.10
         over.single_frac = over.mate_unmapped_frac = over.unmapped_pair_frac = over.secondary_frac = over.supplementary_frac = 0.0
         orec, ooffs = synth.generate(over)
-        rec, offs = synth.merge_sorted(rec, offs, orec, ooffs, synth.records_in_range(orec, ooffs, lo, hi))
         srec, soffs = _straddlers(contigs, slices, int(cfg.read_len), cfg.seed * 31 + 7)
-        rec, offs = synth.merge_sorted(rec, offs, srec, soffs, synth.records_in_range(srec, soffs, lo, hi), records_out=alloc("merged"))
+        # the two small overlays are merged with each other first, so that the shard's 30 GB are copied once, not twice
+        none = np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.uint64)
+        orec, ooffs = synth.merge_sorted(none[0], none[1], orec, ooffs, synth.records_in_range(orec, ooffs, lo, hi))
+        orec, ooffs = synth.merge_sorted(orec, ooffs, srec, soffs, synth.records_in_range(srec, soffs, lo, hi))
+        rec, offs = synth.merge_sorted(rec, offs, orec, ooffs, np.ones(len(ooffs) - 1, dtype=np.uint8), records_out=alloc("merged"))
     return rec, offs, synth.header_text(contigs, rgs), contigs, hold
 
 
