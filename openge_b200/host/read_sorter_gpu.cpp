@@ -124,7 +124,8 @@ int ReadSorter::runInternal()
         delete batches[b];
     }
     const uint64_t n = (uint64_t) m_numberOfAlignments;
-    uint8_t * sorted = (uint8_t *) oge_gpu_host_alloc(total_bytes ? total_bytes : 1);
+    // one copy back: page-locking the whole output (0.4 s per GB) would cost more than the pageable copy loses
+    uint8_t * sorted = (uint8_t *) malloc(total_bytes ? total_bytes : 1);
     vector<uint64_t> offs(n + 1);
     if (!sorted) { cerr << "ReadSorter (GPU): cannot allocate the output buffer. Aborting." << endl; exit(-1); }
     uint64_t got_bytes = 0, got_n = 0;
@@ -137,7 +138,7 @@ int ReadSorter::runInternal()
         const uint8_t * p = sorted + offs[i];
         putOutputAlignment(rebuild_read(p, (uint16_t) (get_u32(p + 16) >> 16)));
     }
-    oge_gpu_host_free(sorted);
+    free(sorted);
     return true;      // the reference returns its bool (read_sorter.cpp:272)
 }
 
